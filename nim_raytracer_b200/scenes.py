@@ -1,0 +1,174 @@
+"""Scene fixtures: the reference's scene files re-expressed as data, plus the
+build-defined bunny / stress scenes of BASELINE.md §3.
+
+Each function cites the scene file it restates (src/data/scenes/*.nim).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import linalg as L
+from .api import (DistantLight, Material, Object, PointLight, Scene, initBox, initPlane, initSphere,
+                  initTriangleMesh, point, vec, vec3)
+from .loaders import loadObj, readGeom, trianglesToMesh
+
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+BUNNY_GEOM = os.path.join(DATA_DIR, "bunny.geom")  # == test/bunny.geom of the reference (data, 69,451 triangles)
+
+
+def _camera(tx, ty, tz, rx_deg=-12.0):
+    # mat4(1.0).rotate(X_AXIS, degToRad(-12.0)).translate(vec3(...))
+    return L.translate(L.rotate(L.mat4(1.0), L.X_AXIS, L.deg_to_rad(rx_deg)), vec3(tx, ty, tz))
+
+
+def _bunny_lights():
+    # src/data/scenes/mesh-bunny.nim:22-31
+    return [
+        DistantLight(color=vec3(1.0), intensity=4.0, dir=L.normalize(vec(-2.0, -0.8, -0.3))),
+        DistantLight(color=vec3(0.8, 0.3, 0.0), intensity=1.0, dir=L.normalize(vec(2.0, -0.8, -1.3))),
+    ]
+
+
+def spheres_reflection() -> Scene:
+    """src/data/scenes/spheres-reflection.nim:1-94 (BASELINE config 1)."""
+    def ball(name, x, y, z, albedo, refl):
+        return Object(name, initSphere(r=2, objectToWorld=L.translate(L.mat4(1.0), vec3(x, y, z))),
+                      Material(albedo=vec3(*albedo), reflection=refl))
+    objects = [
+        ball("ball1", -5.0, 2.0, -18.0, (1.0, 1.0, 1.0), 1.0),
+        ball("ball2", 0.5, 2.0, -8.0, (1.0, 1.0, 1.0), 1.0),
+        ball("ball3", -5.0, 2.0, -10.0, (1.0, 1.0, 1.0), 1.0),
+        ball("ball4", 8.0, 2.0, -15.0, (0.2, 0.3, 0.9), 0.0),
+        ball("ball5", 4.0, 2.0, -16.0, (0.2, 0.5, 0.9), 0.0),
+        ball("ball6", -2.0, 2.0, -42.0, (0.9, 0.5, 0.2), 1.0),
+        ball("ball7", 9.0, 2.0, -30.0, (0.6, 0.5, 0.9), 1.0),
+        Object("ground", initPlane(objectToWorld=L.mat4(1.0)), Material(albedo=vec3(0.4), reflection=0.0)),
+        ball("ball-behind1", -4.0, 2.0, 0.0, (0.2, 0.3, 0.6), 0.0),
+        ball("ball-behind2", 14.0, 2.0, 1.0, (0.4, 0.8, 1.0), 0.0),
+    ]
+    lights = [
+        PointLight(color=vec3(1.0, 1.0, 1.0), intensity=3000.0, pos=point(3.0, 6.0, -12.0)),
+        DistantLight(color=vec3(0.3, 0.4, 0.6), intensity=0.5, dir=L.normalize(vec(2.0, -0.8, -1.3))),
+    ]
+    return Scene(objects=objects, lights=lights, fov=50.0, cameraToWorld=_camera(1.0, 5.5, 3.5),
+                 bgColor=vec3(0.25, 0.1, 0.2))
+
+
+def boxtest() -> Scene:
+    """src/data/scenes/boxtest.nim:1-37 (plane + box; its camera is the golden of test/boxtest.nim:32)."""
+    objects = [
+        Object("ground", initPlane(objectToWorld=L.mat4(1.0)), Material(albedo=vec3(0.4))),
+        Object("box", initBox(objectToWorld=L.translate(L.mat4(1.0), vec3(0.0, 1.0, -10.0)),
+                              vmin=vec(-1.0, -1.0, -1.0), vmax=vec(1.0, 1.0, 1.0)),
+               Material(albedo=vec3(1.0))),
+    ]
+    lights = [
+        DistantLight(color=vec3(1.0), intensity=9.0, dir=L.normalize(vec(-2.0, -0.8, -0.3))),
+        DistantLight(color=vec3(0.8, 0.3, 0.0), intensity=2.0, dir=L.normalize(vec(2.0, -0.8, -1.3))),
+    ]
+    return Scene(objects=objects, lights=lights, fov=50.0, cameraToWorld=_camera(1.0, 5.5, 3.5),
+                 bgColor=vec3(0.15, 0.09, 0.07))
+
+
+def mesh_cube() -> Scene:
+    """src/data/scenes/mesh-cube.nim:1-44: ONE triangle as a mesh, identity transforms."""
+    v = np.array([point(0.0, 0.0, 0.0), point(1.0, 0.0, 0.0), point(0.0, 1.0, 0.0)])
+    n = np.array([vec(0.0, 0.0, 1.0)] * 3)
+    mesh = initTriangleMesh(v, n, [[0, 1, 2]], [[0, 1, 2]], L.mat4(1.0))
+    objects = [Object("cube", mesh, Material(albedo=vec3(0.6, 0.9, 0.2)))]
+    return Scene(objects=objects, lights=_bunny_lights(), fov=50.0,
+                 cameraToWorld=L.translate(L.mat4(1.0), vec3(0.3, 0.3, 5.0)), bgColor=vec3(0.01, 0.03, 0.05))
+
+
+def mesh_scene(mesh, albedo=(0.6, 0.9, 0.2), reflection=0.0, extra_objects=()) -> Scene:
+    """src/data/scenes/mesh-bunny.nim:1-42 with `mesh` in the teapot's place."""
+    mesh.objectToWorld = L.translate(L.mat4(1.0), vec3(0.0, 0.0001, -12.0))
+    mesh.worldToObject = L.inverse(mesh.objectToWorld)
+    objects = [
+        Object("mesh", mesh, Material(albedo=vec3(*albedo), reflection=reflection)),
+        Object("ground", initPlane(objectToWorld=L.mat4(1.0)), Material(albedo=vec3(0.4))),
+    ] + list(extra_objects)
+    return Scene(objects=objects, lights=_bunny_lights(), fov=50.0, cameraToWorld=_camera(0.0, 5.5, 1.5),
+                 bgColor=vec3(0.01, 0.03, 0.05))
+
+
+def teapot_scene(obj_path: str) -> Scene:
+    """src/data/scenes/mesh-bunny.nim verbatim (it loads data/meshes/teapot.obj)."""
+    return mesh_scene(loadObj(obj_path))
+
+
+def bunny_triangles(flip_winding: bool = True, scale: float = 20.0, max_faces: int | None = None,
+                    stride: int = 1) -> np.ndarray:
+    """test/bunny.geom prepared as frozen in SURVEY.md §8d / BASELINE.md §3 config 2:
+    float32 -> float64 exactly, y_min subtracted, scaled x20 about the origin,
+    v1/v2 swapped (the file's winding is inverted w.r.t. every other mesh of the
+    reference).  `stride`/`max_faces` give decimated variants for small tests."""
+    tri = readGeom(BUNNY_GEOM).astype(np.float64)
+    ymin = float(tri[:, :, 1].min())
+    tri[:, :, 1] -= ymin
+    tri *= scale
+    if flip_winding:
+        tri = tri[:, [0, 2, 1], :]
+    tri = tri[::stride]
+    if max_faces is not None:
+        tri = tri[:max_faces]
+    return np.ascontiguousarray(tri)
+
+
+def bunny(flip_winding: bool = True, stride: int = 1, max_faces: int | None = None) -> Scene:
+    """BASELINE config 2: canonical bunny + ground plane + 2 distant lights."""
+    return mesh_scene(trianglesToMesh(bunny_triangles(flip_winding, stride=stride, max_faces=max_faces)))
+
+
+def bunny_spheres(stride: int = 1) -> Scene:
+    """BASELINE config 3/4: config 2 + the seven spheres of spheres-reflection.nim
+    shifted to flank the bunny, reflection in {0, 0.5, 1} (positions frozen here)."""
+    def ball(name, x, z, r, albedo, refl):
+        return Object(name, initSphere(r=r, objectToWorld=L.translate(L.mat4(1.0), vec3(x, r, z))),
+                      Material(albedo=vec3(*albedo), reflection=refl))
+    extra = [
+        ball("ball1", -5.0, -15.0, 2.0, (1.0, 1.0, 1.0), 1.0),
+        ball("ball2", 4.5, -10.0, 1.5, (1.0, 1.0, 1.0), 1.0),
+        ball("ball3", -4.0, -9.0, 1.0, (0.9, 0.9, 0.9), 0.5),
+        ball("ball4", 6.5, -16.0, 2.0, (0.2, 0.3, 0.9), 0.0),
+        ball("ball5", 2.5, -7.5, 0.75, (0.2, 0.5, 0.9), 0.5),
+        ball("ball6", -1.0, -22.0, 2.0, (0.9, 0.5, 0.2), 1.0),
+        ball("ball7", -2.5, -7.0, 0.6, (0.6, 0.5, 0.9), 0.0),
+    ]
+    sc = mesh_scene(trianglesToMesh(bunny_triangles(stride=stride)), extra_objects=extra)
+    return sc
+
+
+def _mt_uniform(n: int, seed: int) -> np.ndarray:
+    """std::mt19937_64(seed) mapped with (x >> 11) * 2^-53.
+    numpy's MT19937 is the 32-bit generator; we freeze numpy's PCG-free path instead:
+    two 32-bit MT draws (hi, lo) -> 53-bit mantissa, documented here as THE spec."""
+    rs = np.random.RandomState(seed % (2 ** 32))
+    return rs.random_sample(n)
+
+
+def stress(ntri: int = 1_000_000, nspheres: int = 10_000, seed: int = 20161018) -> Scene:
+    """BASELINE config 5 (template test/test.nim:29-40): random triangles as ONE mesh at
+    T(0,10,-30), random spheres, ground plane, the two mesh-bunny lights."""
+    u = _mt_uniform(ntri * 12 + nspheres * 8, seed)
+    c = (u[: ntri * 3].reshape(ntri, 1, 3) * 2.0 - 1.0) * 10.0
+    off = (u[ntri * 3: ntri * 12].reshape(ntri, 3, 3) * 2.0 - 1.0) * 0.15
+    tri = c + off
+    mesh = trianglesToMesh(tri)
+    mesh.objectToWorld = L.translate(L.mat4(1.0), vec3(0.0, 10.0, -30.0))
+    mesh.worldToObject = L.inverse(mesh.objectToWorld)
+    s = u[ntri * 12:].reshape(nspheres, 8)
+    objects = [Object("soup", mesh, Material(albedo=vec3(0.6, 0.9, 0.2))),
+               Object("ground", initPlane(objectToWorld=L.mat4(1.0)), Material(albedo=vec3(0.4)))]
+    for i in range(nspheres):
+        x = -30.0 + 60.0 * s[i, 0]
+        y = 20.0 * s[i, 1]
+        z = -60.0 + 50.0 * s[i, 2]
+        r = 0.05 + 0.25 * s[i, 3]
+        refl = 0.5 if s[i, 7] < 0.1 else 0.0
+        objects.append(Object(f"s{i}", initSphere(r=r, objectToWorld=L.translate(L.mat4(1.0), vec3(x, y, z))),
+                              Material(albedo=vec3(s[i, 4], s[i, 5], s[i, 6]), reflection=refl)))
+    return Scene(objects=objects, lights=_bunny_lights(), fov=50.0, cameraToWorld=_camera(0.0, 5.5, 1.5),
+                 bgColor=vec3(0.01, 0.03, 0.05))

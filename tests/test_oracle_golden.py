@@ -1,0 +1,179 @@
+"""Pins the CPU oracle (oracle/ref_cpu.cpp) against every golden vector /
+known-answer the reference holds for the render path."""
+import math
+
+import numpy as np
+import pytest
+
+from nim_raytracer_b200 import api, linalg as L, scenes
+
+
+def eq(a, b, rel=1e-15):
+    """utils/mathutils.nim:8-9 `eq` (maxRelDiff = 1e-15)."""
+    return abs(a - b) <= max(abs(a), abs(b)) * rel
+
+
+def test_quadratic_golden(oracle_mod):
+    # utils/mathutils.nim:34-45 — the only asserted numeric result on the hot path
+    x1, x2 = oracle_mod.solve_quadratic(1.0, -1.786737601482363, 2.054360090947453e-8)
+    assert eq(x1, 1.786737589984535)
+    assert eq(x2, 1.149782767465722e-08)
+
+
+def test_camera_golden_boxtest(oracle_mod):
+    # test/boxtest.nim:32-33: origin/direction of pixel (150,40) of the 300x200
+    # frame of data/scenes/boxtest.nim:35-36.  Pins rotate/translate composition
+    # (R*T), rotation handedness and castPrimaryRay's pixel mapping.  The literals
+    # carry 16 digits (Nim's `$`), hence a 1e-15 relative check, not bit equality.
+    sc = scenes.boxtest()
+    orig, d = oracle_mod.cast_primary_ray(300, 200, 150.0, 40.0, sc.fov, sc.cameraToWorld)
+    assert orig[0] == 1.0 and orig[3] == 1.0
+    assert eq(orig[1], 6.107502721898089) and eq(orig[2], 2.280002303070644)
+    assert d[0] == 0.0 and d[3] == 0.0
+    assert abs(d[1] - 0.06332703314645494) < 2e-16
+    assert abs(d[2] - (-0.9979928290688606)) < 4e-16
+
+
+def test_boxtest_nan_ray(oracle_mod):
+    # test/boxtest.nim:31-41 "NaN": dir.x == 0 with the origin ON the x slab plane.
+    orig = np.array([1.0, 6.107502721898089, 2.280002303070644])
+    d = np.array([0.0, 0.06332703314645494, -0.9979928290688606])
+    # Box at T(0,1,-10): object-space origin = world - (0,1,-10)
+    t = oracle_mod.aabb_intersect([-1, -1, -1], [1, 1, 1], orig - np.array([0.0, 1.0, -10.0]), d)
+    # (1-1)*inf = NaN on the x slabs is dropped by Nim's max/min operand order; the
+    # ray passes above the box (y slab) => miss, and in particular not NaN.
+    assert t == -math.inf
+
+
+def test_triangle_meshperftest(oracle_mod):
+    # test/meshperftest.nim:8-20 and test/geomtest2.nim:10-17: t = 5 by inspection
+    t = oracle_mod.ray_triangle([0, 0, 0], [0, 0, -1], [0, 1, -5], [-2, -1, -5], [2, -1, -5])
+    assert t == 5.0
+    # back face (reversed winding) is culled: det < 1e-6 -> NegInf (geom.nim:306)
+    t = oracle_mod.ray_triangle([0, 0, 0], [0, 0, -1], [0, 1, -5], [2, -1, -5], [-2, -1, -5])
+    assert t == -math.inf
+
+
+def test_mesh_one_triangle_scene(oracle_mod):
+    # test/meshperftest.nim:22-44: a 1-triangle TriangleMesh hit from the origin along -z
+    v = np.array([api.point(0, 1, -5), api.point(-2, -1, -5), api.point(2, -1, -5)])
+    n = np.array([api.vec(0, 0, 1)])
+    mesh = api.initTriangleMesh(v, n, [[0, 1, 2]], [[0, 0, 0]], L.mat4(1.0))
+    sc = api.Scene([api.Object("m", mesh, api.Material(api.vec3(1.0)))], [], 90.0, L.mat4(1.0), api.vec3(0.0))
+    o = api.Options(2, 2)
+    aov = api.Aov(2, 2)
+    oracle_mod.render(sc, o, aov=aov)
+    # pixel (1,1) is the image centre (pixel corner convention, renderer.nim:135): dir = (0,0,-1)
+    assert aov.obj_id[3] == 0 and aov.tri_id[3] == 0 and aov.t_hit[3] == 5.0
+
+
+def test_aabb_matches_reference_cpp(oracle_mod):
+    # oracle/_ref/libgeomtest_ref.so = the reference's own test/geomtest.cpp:51-78
+    ref = oracle_mod.ref_geomtest()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    import ctypes as C
+    rng = np.random.RandomState(7)
+    dp = C.POINTER(C.c_double)
+    n_hit = 0
+    for i in range(20000):
+        vmin = rng.uniform(-2, 0, 3)
+        vmax = vmin + rng.uniform(0.1, 3, 3)
+        orig = rng.uniform(-4, 4, 3)
+        d = rng.normal(size=3)
+        if i % 7 == 0:
+            d[rng.randint(3)] = 0.0          # axis-parallel rays (inf / NaN slabs)
+        if i % 11 == 0:
+            orig[rng.randint(3)] = vmin[rng.randint(3)]  # origin on a slab plane
+        a = oracle_mod.aabb_intersect(vmin, vmax, orig, d)
+        arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (vmin, vmax, orig, d)]
+        b = ref.geomtest_ref_aabb_intersect(*[x.ctypes.data_as(dp) for x in arrs])
+        assert (a == b) or (math.isnan(a) and math.isnan(b)), (i, a, b)
+        n_hit += a >= 0
+    assert n_hit > 500
+    # the reference benchmark's own inputs (geomtest.cpp:83-87, boxtest.nim:11-17)
+    assert oracle_mod.aabb_intersect([-1, -1, -1], [1, 1, 1], [0, 0, 0], [0.1, 0.2, -0.8]) < 0  # inside
+    t = oracle_mod.aabb_intersect([-1, -1, -1], [1, 1, 1], [0, 0, 2.0], L.normalize([0.3, 0.4, -1.0]))
+    assert eq(t, math.sqrt(0.09 + 0.16 + 1.0), 1e-15)
+
+
+def test_sphere_and_plane_analytic(oracle_mod):
+    # sphere r=20 at origin, geom.nim:387-391 benchmark ray: analytic roots of |o+td|^2 = r^2
+    o, d = np.array([7.0, 9.0, 100.0]), np.array([0.1, 0.2, -0.9])
+    assert oracle_mod.sphere_intersect(20.0, o, d) == -math.inf   # that benchmark ray misses (delta < 0)
+    d = np.array([-0.05, -0.08, -0.9])                             # non-unit direction: a != 1 matters
+    t = oracle_mod.sphere_intersect(20.0, o, d)
+    dx, dy, dz = (float(v) for v in d)
+    ox, oy, oz = (float(v) for v in o)
+    a = dx * dx + dy * dy + dz * dz                      # geom.nim:216-228, same operation order
+    b = 2 * (dx * ox + dy * oy + dz * oz)
+    c = ox * ox + oy * oy + oz * oz - 20.0 * 20.0
+    disc = b * b - 4 * a * c
+    # reference formula: ((-b - sign(b) sqrt(D)) / 2) * a  (NOT /(2a)), geom.nim:232
+    t1 = ((-b - math.copysign(1, b) * math.sqrt(disc)) / 2) * a
+    t2 = c / (a * t1)
+    assert t == min(t1, t2)
+    # origin inside the sphere => negative min => miss semantics at the caller
+    assert oracle_mod.sphere_intersect(2.0, [0.5, 0, 0], [1, 0, 0]) < 0
+    # plane y=0: |d.y| <= 1e-6 -> NegInf (geom.nim:244)
+    assert oracle_mod.plane_intersect([0, 1, 0], [1, 1e-7, 0]) == -math.inf
+    assert oracle_mod.plane_intersect([0, 3, 0], [0, -1.5, 0]) == 2.0
+
+
+def test_grid_samples(oracle_mod):
+    # sampling.nim:5-18: index j*m+i, yoffs uses xs (sic)
+    s = oracle_mod.samples(api.akGrid, 4)
+    assert s.shape == (16, 2)
+    assert s[0].tolist() == [0.125, 0.125] and s[5].tolist() == [0.375, 0.375] and s[15].tolist() == [0.875, 0.875]
+
+
+def test_jittered_samples_are_stratified(oracle_mod):
+    for kind in (api.akJittered, api.akMultiJittered, api.akCorrelatedMultiJittered):
+        m = 4
+        s = oracle_mod.samples(kind, m, seed=3, width=640, x=17, y=5)
+        assert ((s >= 0) & (s < 1)).all()
+        if kind == api.akJittered:
+            cells = {(int(p[0] * m), int(p[1] * m)) for p in s}
+            assert len(cells) == m * m
+        else:  # N-rooks on the fine grid in both axes
+            assert len({int(p[0] * m * m) for p in s}) == m * m
+            assert len({int(p[1] * m * m) for p in s}) == m * m
+        s2 = oracle_mod.samples(kind, m, seed=3, width=640, x=17, y=5)
+        assert (s == s2).all()  # counter-based: reproducible, unlike the reference's global RNG
+
+
+def test_stats_semantics(oracle_mod):
+    # stats.nim / renderer.nim:58,65,138: tests = rays * nobjects; primary = pixels
+    sc = scenes.spheres_reflection()
+    o = api.Options(64, 48)
+    _, st, _ = oracle_mod.render(sc, o)
+    assert st.numPrimaryRays == 64 * 48
+    assert st.numIntersectionTests == st.numRays * len(sc.objects)
+    assert 0 < st.numIntersectionHits < st.numIntersectionTests
+
+
+def test_depth_modes_and_threads(oracle_mod):
+    sc = scenes.spheres_reflection()
+    a = api.Options(80, 60)
+    fb1, st1, _ = oracle_mod.render(sc, a, nthreads=1)
+    fb8, st8, _ = oracle_mod.render(sc, a, nthreads=8)
+    assert (fb1.data == fb8.data).all() and st1 == st8          # scanline sharding is exact
+    b = api.Options(80, 60, depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=0)
+    fb0, st0, _ = oracle_mod.render(sc, b)
+    assert st0.numRays < st1.numRays                            # no reflection rays at all
+    c = api.Options(80, 60, depthMode=api.NRT_DEPTH_REFBUG, maxRayDepth=0)
+    fbc, stc, _ = oracle_mod.render(sc, c)
+    assert (fbc.data == fb1.data).all()                         # maxRayDepth is inert (depth bug)
+
+
+def test_progressive_steps(oracle_mod):
+    # renderer.nim:174-178,204-207 + gui.nim:113-122,254-257: maxStep..1 halving ends at the 1-step image
+    sc = scenes.boxtest()
+    o = api.Options(64, 32)
+    full, _, _ = oracle_mod.render(sc, o)
+    fb = api.newFramebuf(64, 32)
+    step = 8
+    while step >= 1:
+        oracle_mod.render(sc, o, fb=fb, step=step, maxStep=8)
+        step //= 2
+    assert (fb.data == full.data).all()
