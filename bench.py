@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — measures the render hot path on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            (N=1)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N>1)
+  python bench.py --impl reference ...                      (the CPU restatement, host cores)
+
+A "step" is one whole frame of the workload (default: BASELINE config 2 — the
+canonical bunny scene, 1920x1080, 1 spp, primary + shadow rays).  The frame is
+strong-scaled: rank r of N renders the scanlines y mod N == r and every rank's
+final pixel-store kernel writes its rows into rank 0's device framebuffer over
+NVLink (CUDA IPC peer pointer); `value` = rays traced by all ranks / max-over-ranks
+device time.  `e2e` goes through the host-buffer C-ABI call (nrt_scene_update +
+nrt_render): scene host->device and framebuffer device->host inside the timed
+region.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/sec"
+UNIT = "Mrays/s"
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.45 at clocks.max.sm
+
+
+def workload(name: str):
+    from nim_raytracer_b200 import api, scenes
+    if name == "config2":
+        return scenes.bunny(), api.Options(1920, 1080), "bunny.geom 69,451 tris + plane, 2 distant lights, 1920x1080, 1 spp (BASELINE config 2)"
+    if name == "config3":
+        o = api.Options(1920, 1080, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+        return scenes.bunny_spheres(), o, "bunny + 7 spheres (reflection 0/0.5/1), 1920x1080, 16 spp grid, depth 8 (BASELINE config 3)"
+    if name == "config4":
+        o = api.Options(3840, 2160, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+        return scenes.bunny_spheres(), o, "bunny + 7 spheres, 3840x2160, 16 spp grid, depth 8 (BASELINE config 4)"
+    if name == "config1":
+        return scenes.spheres_reflection(), api.Options(640, 480), "spheres-reflection.nim 640x480, 1 spp (BASELINE config 1)"
+    if name == "tiny":  # CI-sized
+        return scenes.bunny(stride=8), api.Options(320, 180), "decimated bunny 320x180 (smoke)"
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled during the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path timed on the host cores.
+    The reference (Nim) cannot be built here, so this is the oracle port (oracle/ref_cpu.cpp,
+    -ffast-math build mirroring src/nim.cfg:2), one scanline per work item over all host threads
+    (src/raytracer.nim:61-70, concurrency/workerpool.nim:172)."""
+    if rank != 0:
+        return
+    import oracle
+    from nim_raytracer_b200 import api
+    scene, opts, desc = workload(args.workload)
+    sd = api.SceneDesc(scene)
+    cores = oracle.hardware_threads()
+    h = opts.height
+    # bounded sample: every k-th scanline, k chosen from a probe so that one step is ~target seconds
+    probe_rows = list(range(0, h, 64))
+    t = time.time()
+    _, st = oracle.render_rows(sd, opts, probe_rows, fast=True)
+    dt = max(time.time() - t, 1e-3)
+    full_est = dt * h / len(probe_rows)
+    target = float(os.environ.get("NRT_REF_STEP_SECONDS", "8"))
+    k = max(1, int(np.ceil(full_est / target)))
+    rows = list(range(0, h, k))
+    for _ in range(args.warmup if k > 1 else min(args.warmup, 1)):
+        oracle.render_rows(sd, opts, rows, fast=True)
+    rays = 0
+    t0 = time.time()
+    for _ in range(args.steps):
+        _, st = oracle.render_rows(sd, opts, rows, fast=True)
+        rays += st.numRays
+    el = time.time() - t0
+    v = rays / el / 1e6
+    sample = f"every {k}th scanline of the frame ({len(rows)} of {h} lines) per step, all {cores} host threads, float64 -O3 -ffast-math"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "note": "CPU restatement of the reference (Nim toolchain absent); ms_per_step is for the sampled lines only"},
+        "frames_per_s_extrapolated": 1.0 / (el / args.steps * h / len(rows)),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(scene_desc, opts, budget_s=12.0):
+    import oracle
+    cores = oracle.hardware_threads()
+    h = opts.height
+    probe_rows = list(range(0, h, 64))
+    t = time.time()
+    oracle.render_rows(scene_desc, opts, probe_rows, fast=True)
+    dt = max(time.time() - t, 1e-3)
+    k = max(1, int(np.ceil(dt * h / len(probe_rows) / budget_s)))
+    rows = list(range(0, h, k))
+    t = time.time()
+    _, st = oracle.render_rows(scene_desc, opts, rows, fast=True)
+    el = time.time() - t
+    return {"value": st.numRays / el / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"every {k}th scanline ({len(rows)} of {h}) of the same frame, {el:.1f} s, oracle -O3 -ffast-math float64, all host threads",
+            "frames_per_s_extrapolated": 1.0 / (el * h / len(rows))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("NRT_WORKLOAD", "config2"))
+    ap.add_argument("--gather", default="ipc", choices=["ipc", "gather"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    from nim_raytracer_b200 import api, distributed as D
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allreduce(v, op):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    L = api.lib()
+    api.initRenderer(devices=[local_rank])
+    api.setPartition(rank, world)
+    scene, opts, desc = workload(args.workload)
+    ds = api.DeviceScene(scene)
+    W, H = opts.width, opts.height
+    fb_bytes = W * H * 3 * 4
+    co = opts.to_c()
+
+    peer = None
+    local_t = None
+    if args.gather == "ipc":
+        try:
+            peer = D.PeerFramebuffer(fb_bytes, rank, world, dist)
+        except Exception as e:  # CUDA IPC unavailable in this container: gather with NCCL instead
+            if rank == 0:
+                print(f"[bench] CUDA IPC unavailable ({e}); falling back to --gather gather", file=sys.stderr)
+            peer = None
+    if peer is None:
+        local_t = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    cs = api.nrt_stats()
+
+    def step_resident():
+        target = peer.ptr if peer is not None else C.c_void_p(local_t.data_ptr())
+        api.check(L.nrt_render_device(ds.handle, C.byref(co), 0, H, 1, 1, target, C.byref(cs), None), "nrt_render_device")
+        if peer is None and world > 1:
+            return D.gather_rows(local_t, rank, world, dist)
+        return None
+
+    # ---- device-resident throughput ------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    prof_acc = {"mesh_ms": 0.0, "flops": 0.0, "launches": 0, "klaunches": 0, "tests": 0, "tests_ref": 0, "cand": 0, "rays_mesh": 0, "frame_ms": 0.0}
+    barrier()
+    t0 = time.perf_counter()
+    api.check(L.nrt_timer_begin(), "nrt_timer_begin")
+    rays = 0
+    for _ in range(args.steps):
+        flush.fill_(1)                      # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        step_resident()
+        rays += cs.num_rays
+        p = ds.profile()
+        prof_acc["mesh_ms"] += p.mesh_filter_ms; prof_acc["flops"] += p.fp32_flops
+        prof_acc["launches"] += p.mesh_filter_launches; prof_acc["klaunches"] += p.kernel_launches
+        prof_acc["tests"] += p.mesh_tests; prof_acc["tests_ref"] += p.mesh_tests_ref; prof_acc["cand"] += p.candidates
+        prof_acc["rays_mesh"] += p.mesh_rays; prof_acc["frame_ms"] += p.total_ms
+    ms_dev = C.c_double()
+    api.check(L.nrt_timer_end(C.byref(ms_dev)), "nrt_timer_end")
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    OP = None
+    if dist is not None:
+        OP = dist.ReduceOp
+    t_ms = allreduce(max(wall_ms, ms_dev.value), OP.MAX if OP else None)
+    total_rays = allreduce(float(rays), OP.SUM if OP else None)
+    klaunches = allreduce(float(prof_acc["klaunches"]), OP.SUM if OP else None)
+    value = total_rays / (t_ms * 1e-3) / 1e6
+
+    # ---- end to end: host scene -> device, framebuffer -> pinned host, every step ---
+    hp = C.c_void_p()
+    api.check(L.nrt_host_alloc_pinned(fb_bytes, C.byref(hp)), "nrt_host_alloc_pinned")
+    host_fb = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(W * H * 3,))
+    h2d = sum(int(g.vertices.nbytes + g.normals.nbytes + g.vertexIdx.nbytes + g.normalIdx.nbytes)
+              for g in {id(o.geometry): o.geometry for o in scene.objects if o.geometry.kind == api.NRT_GEOM_MESH}.values())
+    h2d += len(scene.objects) * C.sizeof(api.nrt_object) + len(scene.lights) * C.sizeof(api.nrt_light) + 512
+
+    def step_e2e():
+        ds.update()                                           # scene: host -> device (+ device-side precompute)
+        if world == 1:
+            api.check(L.nrt_render(ds.handle, C.byref(co), 0, H, 1, 1, hp, C.byref(cs), None), "nrt_render")
+        else:
+            out = step_resident()
+            barrier()
+            if rank == 0:
+                if peer is not None:
+                    peer.to_host(host_fb)
+                else:
+                    host_fb[:] = out.reshape(-1).cpu().numpy()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    rays_e = 0
+    for _ in range(args.steps):
+        step_e2e()
+        rays_e += cs.num_rays
+    barrier()
+    e_ms = allreduce((time.perf_counter() - t0) * 1e3, OP.MAX if OP else None)
+    rays_e = allreduce(float(rays_e), OP.SUM if OP else None)
+    e2e = {"value": rays_e / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": fb_bytes + 64,
+           "ms_per_step": e_ms / args.steps, "frames_per_s": args.steps / (e_ms * 1e-3)}
+    checksum = float(np.asarray(host_fb, dtype=np.float64).sum()) if rank == 0 else 0.0
+
+    if rank == 0:
+        peak = C.c_double(); clk = C.c_double()
+        api.check(L.nrt_measure_fp32_peak(C.byref(peak), C.byref(clk)), "nrt_measure_fp32_peak")
+        achieved = prof_acc["flops"] / max(prof_acc["mesh_ms"] * 1e-3, 1e-12) / 1e12
+        roofline = {
+            "bound": "fp32", "kernel": "k_mesh_filter", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+            "frac": achieved / peak.value if peak.value > 0 else None,
+            "peak_source": "FFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
+            "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
+            "traffic": None,
+            "flops_per_test": 32, "tests_per_step": prof_acc["tests"] / args.steps,
+            "ref_tests_per_step": prof_acc["tests_ref"] / args.steps,
+            "avg_launch_ms": prof_acc["mesh_ms"] / max(prof_acc["launches"], 1),
+            "kernel_share_of_step": prof_acc["mesh_ms"] / max(prof_acc["frame_ms"], 1e-9),
+            "gtests_per_s": prof_acc["tests"] / max(prof_acc["mesh_ms"] * 1e-3, 1e-12) / 1e9,
+            "candidates_per_step": prof_acc["cand"] / args.steps, "mesh_rays_per_step": prof_acc["rays_mesh"] / args.steps,
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 filter + f64 exact", "data": "synthetic",
+            "config": {"workload": desc, "parallelism": f"scanline-interleaved x{world}, {'CUDA-IPC peer stores' if peer is not None else 'NCCL row gather'} to rank 0",
+                       "l2": "256 MiB device fill between timed steps (inside the timed region)"},
+            "frames_per_s": args.steps / (t_ms * 1e-3), "rays_per_frame": total_rays / args.steps,
+            "device_ms_per_step": ms_dev.value / args.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(klaunches),
+            "roofline": roofline, "fb_checksum": checksum,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(ds.desc, opts)
+        print(json.dumps(line), flush=True)
+
+    L.nrt_host_free_pinned(hp)
+    if peer is not None:
+        barrier()
+        peer.close()
+    ds.close()
+    api.shutdown()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

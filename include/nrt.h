@@ -254,6 +254,11 @@ int nrt_device_synchronize(void);
  * micro-kernel, CUDA-event timed) — the denominator BASELINE.md asks for. */
 int nrt_measure_fp32_peak(double* tflops, double* sm_clock_mhz_hint);
 
+/* CUDA-event bracket on the library's own stream(s): elapsed device time between
+ * the two calls, max over the selected devices (bench.py's timed region). */
+int nrt_timer_begin(void);
+int nrt_timer_end(double* ms);
+
 /* Pinned host memory helpers for callers that want async D2H (bench e2e). */
 int nrt_host_alloc_pinned(int64_t bytes, void** host_ptr);
 int nrt_host_free_pinned(void* host_ptr);

@@ -160,6 +160,7 @@ def lib() -> C.CDLL:
     L.nrt_ipc_open.argtypes = [C.POINTER(nrt_ipc_handle), C.POINTER(vp)]
     L.nrt_ipc_close.argtypes = [vp]
     L.nrt_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.nrt_timer_end.argtypes = [C.POINTER(C.c_double)]
     L.nrt_host_alloc_pinned.argtypes = [i64, C.POINTER(vp)]
     L.nrt_host_free_pinned.argtypes = [vp]
     _lib = L

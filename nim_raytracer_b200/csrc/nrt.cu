@@ -1,0 +1,807 @@
+// nrt.cu — CUDA backend (sm_100a) + the C ABI of include/nrt.h.
+//
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
+//        -fmad=false --shared -Xcompiler -fPIC nrt.cu -o libnrt.so
+// -fmad=false: float64 code must round exactly like the IEEE oracle; the float32
+// hot loop fuses explicitly with fmaf (FFMA in SASS).
+//
+// There is no CPU implementation in this library: every entry point that
+// computes anything needs a CUDA device and fails with NRT_ERR_NO_DEVICE otherwise.
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <stdexcept>
+#include <mutex>
+#include <thread>
+
+#include "nrt_renderer.h"
+
+namespace nrt {
+
+// ------------------------------------------------------------------ errors ----
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define NRT_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      char b_[512];                                                                             \
+      snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      throw std::runtime_error(b_);                                                             \
+    }                                                                                           \
+  } while (0)
+
+// ----------------------------------------------------------------- kernels ----
+static constexpr int kBlock = 256;
+
+template <class F>
+__global__ void __launch_bounds__(kBlock) k_for_each(F f, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  if (i < n) f(i);
+}
+
+template <class F>
+__global__ void __launch_bounds__(kBlock) k_for_each_stats(F f, int64_t n, unsigned long long* stats) {
+  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  StatDelta d = zeroStats();
+  if (i < n) d = f(i);
+  __shared__ unsigned long long sh[ST_COUNT];
+  if (threadIdx.x < ST_COUNT) sh[threadIdx.x] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k <= ST_CONT; ++k) {
+    unsigned long long v = d.v[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x <= ST_CONT && sh[threadIdx.x]) atomicAdd(&stats[threadIdx.x], sh[threadIdx.x]);
+}
+
+// Elements [0, min(*count, cap)) with a device-resident count (no host sync).
+template <class F>
+__global__ void __launch_bounds__(kBlock) k_for_each_counted(F f, const uint32_t* count, int64_t cap) {
+  int64_t n = *count;
+  if (n > cap) n = cap;
+  for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) f(i);
+}
+
+// AABB gate + warp-ballot compaction of the rays that enter each mesh's box.
+__global__ void __launch_bounds__(kBlock) k_gate(Gate g, int64_t n, int nMO, uint32_t* cnt) {
+  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
+  const ChunkState& cs = g.cs;
+  for (int mo = 0; mo < nMO; ++mo) {
+    const GateOut o = g(i, mo);
+    const bool toFilter = o.pass && o.safe, toExact = o.pass && !o.safe;
+    const unsigned fm = __ballot_sync(0xffffffffu, toFilter);
+    if (fm) {
+      const int leader = __ffs(fm) - 1;
+      uint32_t base = 0;
+      if (int(lane) == leader) base = atomicAdd(&cnt[mo * CNT_STRIDE + CNT_QUEUE], uint32_t(__popc(fm)));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (toFilter) {
+        const int64_t slot = int64_t(mo) * cs.NR + base + __popc(fm & lt);
+        cs.qref[slot] = uint32_t(i);
+        float4* p0 = reinterpret_cast<float4*>(cs.qray + int64_t(mo) * cs.NR * 8);
+        float4* p1 = p0 + cs.NR;
+        const int64_t q = base + __popc(fm & lt);
+        p0[q] = make_float4(o.fr.dx, o.fr.dy, o.fr.dz, o.fr.rr);
+        p1[q] = make_float4(o.fr.mx, o.fr.my, o.fr.mz, 0.f);
+      }
+    }
+    const unsigned xm = __ballot_sync(0xffffffffu, toExact);
+    if (xm) {
+      const int leader = __ffs(xm) - 1;
+      uint32_t base = 0;
+      if (int(lane) == leader) base = atomicAdd(&cnt[mo * CNT_STRIDE + CNT_EXACT], uint32_t(__popc(xm)));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (toExact) cs.xref[int64_t(mo) * cs.NR + base + __popc(xm & lt)] = uint32_t(i);
+    }
+  }
+}
+
+// ------------------------------------------------------------- mesh filter ----
+// The hot kernel: every queued ray x every triangle of one mesh, float32,
+// 15 FFMA + 2 FADD + ~1.5 LOP3 per test (nrt_core.h: filterTest).  Persistent
+// CTAs pull (ray tile x triangle block) work items from an atomic counter; the
+// triangle records of a block are staged in shared memory in 16-byte vectors and
+// read back as warp-broadcast LDS.128; each thread keeps FT_R rays in registers.
+static constexpr int FT_THREADS = 256;
+static constexpr int FT_R = 4;        // rays per thread
+static constexpr int FT_TC = 256;     // triangles per shared-memory chunk (16 KB)
+static constexpr int FT_TB = 1024;    // triangles per work item
+static constexpr int FT_RAYS = FT_THREADS * FT_R;
+
+struct FilterArgs {
+  const float4* recs;     // padded to a multiple of FT_TC records
+  int ntri_padded;
+  const float4* q0;       // (d, rr)
+  const float4* q1;       // (m, pad)
+  const uint32_t* qref;
+  uint32_t* cnt;          // CNT_* of this (wave, mesh object)
+  uint32_t* candRef;
+  uint32_t* candTri;
+  uint32_t candCap;
+};
+
+__global__ void __launch_bounds__(FT_THREADS, 2) k_mesh_filter(FilterArgs a) {
+  __shared__ __align__(16) float4 tile[FT_TC * 4];
+  __shared__ uint32_t s_item;
+  const uint32_t nq = a.cnt[CNT_QUEUE];
+  if (nq == 0) return;
+  const uint32_t nRayTiles = (nq + FT_RAYS - 1) / FT_RAYS;
+  const uint32_t nTriBlocks = (uint32_t(a.ntri_padded) + FT_TB - 1) / FT_TB;
+  const uint32_t nItems = nRayTiles * nTriBlocks;
+  const int tid = threadIdx.x;
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(&a.cnt[CNT_TILE], 1u);
+    __syncthreads();
+    const uint32_t item = s_item;
+    __syncthreads();
+    if (item >= nItems) break;
+    const uint32_t rt = item / nTriBlocks, tb = item - rt * nTriBlocks;
+    float dx[FT_R], dy[FT_R], dz[FT_R], mx[FT_R], my[FT_R], mz[FT_R];
+    uint32_t ref[FT_R];
+    float rr = 0.f;
+#pragma unroll
+    for (int r = 0; r < FT_R; ++r) {
+      const uint32_t idx = rt * FT_RAYS + r * FT_THREADS + tid;
+      const uint32_t ic = idx < nq ? idx : nq - 1;  // tail: duplicate a real ray, never emit for it
+      const float4 p0 = __ldg(a.q0 + ic), p1 = __ldg(a.q1 + ic);
+      dx[r] = p0.x; dy[r] = p0.y; dz[r] = p0.z; mx[r] = p1.x; my[r] = p1.y; mz[r] = p1.z;
+      rr = fmaxf(rr, p0.w);
+      ref[r] = idx < nq ? __ldg(a.qref + ic) : kInvalidRef;
+    }
+    const int tri0 = int(tb) * FT_TB;
+    const int tri1 = min(a.ntri_padded, tri0 + FT_TB);
+    for (int base = tri0; base < tri1; base += FT_TC) {
+      const float4* src = a.recs + int64_t(base) * 4;
+#pragma unroll
+      for (int k = 0; k < (FT_TC * 4) / FT_THREADS; ++k) tile[k * FT_THREADS + tid] = __ldg(src + k * FT_THREADS + tid);
+      __syncthreads();
+#pragma unroll 1
+      for (int t = 0; t < FT_TC; t += 2) {
+        const float4 a0 = tile[t * 4 + 0], a1 = tile[t * 4 + 1], a2 = tile[t * 4 + 2], a3 = tile[t * 4 + 3];
+        const float4 b0 = tile[t * 4 + 4], b1 = tile[t * 4 + 5], b2 = tile[t * 4 + 6], b3 = tile[t * 4 + 7];
+        const float qa[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+        const float qb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+        const float ebA = a0.w * rr, kdA = ebA * kFilterKd;
+        const float ebB = b0.w * rr, kdB = ebB * kFilterKd;
+        uint32_t xa[FT_R], xb[FT_R];
+        uint32_t acc = 0xFFFFFFFFu;
+#pragma unroll
+        for (int r = 0; r < FT_R; ++r) {
+          xa[r] = filterTest(qa, dx[r], dy[r], dz[r], mx[r], my[r], mz[r], ebA, kdA);
+          xb[r] = filterTest(qb, dx[r], dy[r], dz[r], mx[r], my[r], mz[r], ebB, kdB);
+          acc &= xa[r] & xb[r];
+        }
+        if (int(acc) >= 0) {  // some test has all three sign bits clear: rare
+#pragma unroll
+          for (int r = 0; r < FT_R; ++r) {
+            if (ref[r] == kInvalidRef) continue;
+            if (int(xa[r]) >= 0) {
+              const uint32_t slot = atomicAdd(&a.cnt[CNT_CAND], 1u);
+              if (slot < a.candCap) { a.candRef[slot] = ref[r]; a.candTri[slot] = uint32_t(base + t); }
+            }
+            if (int(xb[r]) >= 0) {
+              const uint32_t slot = atomicAdd(&a.cnt[CNT_CAND], 1u);
+              if (slot < a.candCap) { a.candRef[slot] = ref[r]; a.candTri[slot] = uint32_t(base + t + 1); }
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// clamp -> sRGB -> 8 bit (utils/framebuf.nim:74-78, utils/color.nim:17-22)
+__global__ void __launch_bounds__(kBlock) k_srgb8(const float* fb, unsigned char* out, int64_t n, int srgb) {
+  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  if (i >= n) return;
+  float c = fb[i];
+  c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
+  if (srgb) {
+    if (c <= 0.0031308f) c = 12.92f * c;
+    else c = float((1.0 + 0.055) * double(powf(c, float(1 / 2.4))) - 0.055);
+  }
+  out[i] = (unsigned char)(roundf(c * 255.f));
+}
+
+// register-resident FFMA loop: the float32 roofline denominator
+__global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = float(threadIdx.x + k);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = fmaf(x[k], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += x[k];
+  if (s == 12345.678f) out[0] = s;
+}
+
+// ----------------------------------------------------------------- backend ----
+struct CudaBackend {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sms = 148;
+  int64_t launches = 0;
+  // profiling of the mesh filter
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> filterEvents;
+  size_t filterUsed = 0;
+
+  struct Atom {
+    static __device__ __forceinline__ void min64(uint64_t* p, uint64_t v) {
+      atomicMin(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
+    }
+    static __device__ __forceinline__ void min32(uint32_t* p, uint32_t v) { atomicMin(p, v); }
+  };
+
+  void use() { NRT_CUDA(cudaSetDevice(device)); }
+  void* dalloc(size_t bytes) { use(); void* p = nullptr; NRT_CUDA(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
+  void dfree(void* p) { if (p) { cudaSetDevice(device); cudaFree(p); } }
+  void zero(void* p, size_t bytes) { use(); NRT_CUDA(cudaMemsetAsync(p, 0, bytes, stream)); }
+  void upload(void* dst, const void* src, size_t bytes) {
+    use();
+    NRT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    // pageable sources are staged by the runtime before the call returns; callers may reuse src
+  }
+  void download(void* dst, const void* src, size_t bytes) {
+    use();
+    NRT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+    NRT_CUDA(cudaStreamSynchronize(stream));
+  }
+  void sync() { use(); NRT_CUDA(cudaStreamSynchronize(stream)); }
+  static unsigned blocksFor(int64_t n) { return unsigned((n + kBlock - 1) / kBlock); }
+
+  template <class F> void forEach(int64_t n, const F& f) {
+    if (n <= 0) return;
+    use();
+    k_for_each<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n);
+    NRT_CUDA(cudaGetLastError()); ++launches;
+  }
+  template <class F> void forEachStats(int64_t n, const F& f, unsigned long long* stats) {
+    if (n <= 0) return;
+    use();
+    k_for_each_stats<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, stats);
+    NRT_CUDA(cudaGetLastError()); ++launches;
+  }
+  template <class F> void forEachCounted(const uint32_t* count, int64_t cap, const F& f) {
+    use();
+    k_for_each_counted<F><<<unsigned(sms * 8), kBlock, 0, stream>>>(f, count, cap);
+    NRT_CUDA(cudaGetLastError()); ++launches;
+  }
+  void gate(const Gate& g, int64_t n, int nMO, uint32_t* cnt) {
+    use();
+    k_gate<<<blocksFor(n), kBlock, 0, stream>>>(g, n, nMO, cnt);
+    NRT_CUDA(cudaGetLastError()); ++launches;
+  }
+  void filter(const DMesh& m, const ChunkState& cs, int mo, uint32_t* cnt) {
+    use();
+    FilterArgs a;
+    a.recs = reinterpret_cast<const float4*>(m.recs);
+    a.ntri_padded = int(paddedFaces(m.nfaces));
+    static_assert(kRecPad % FT_TC == 0, "record padding must cover whole shared-memory chunks");
+    a.q0 = reinterpret_cast<const float4*>(cs.qray + int64_t(mo) * cs.NR * 8);
+    a.q1 = a.q0 + cs.NR;
+    a.qref = cs.qref + int64_t(mo) * cs.NR;
+    a.cnt = cnt;
+    a.candRef = cs.candRef; a.candTri = cs.candTri;
+    a.candCap = uint32_t(std::min<int64_t>(cs.candCap, 0xFFFFFFFFll));
+    if (filterUsed == filterEvents.size()) {
+      cudaEvent_t e0, e1;
+      NRT_CUDA(cudaEventCreate(&e0)); NRT_CUDA(cudaEventCreate(&e1));
+      filterEvents.push_back({e0, e1});
+    }
+    auto& ev = filterEvents[filterUsed++];
+    NRT_CUDA(cudaEventRecord(ev.first, stream));
+    k_mesh_filter<<<unsigned(sms * 2), FT_THREADS, 0, stream>>>(a);
+    NRT_CUDA(cudaGetLastError()); ++launches;
+    NRT_CUDA(cudaEventRecord(ev.second, stream));
+  }
+  // call after a stream sync
+  double filterMs(int64_t* n) {
+    double ms = 0;
+    for (size_t i = 0; i < filterUsed; ++i) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, filterEvents[i].first, filterEvents[i].second) == cudaSuccess) ms += t;
+    }
+    *n = int64_t(filterUsed);
+    filterUsed = 0;
+    return ms;
+  }
+  void destroy() {
+    cudaSetDevice(device);
+    for (auto& e : filterEvents) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    filterEvents.clear();
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
+
+// ------------------------------------------------------------ global state ----
+struct DeviceCtx {
+  CudaBackend be;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // frame bracket (nrt_profile.total_ms)
+  cudaEvent_t tb0 = nullptr, tb1 = nullptr;   // user bracket (nrt_timer_begin/end)
+};
+
+static std::mutex g_mu;
+static std::vector<DeviceCtx*> g_devs;
+static int g_part_index = 0, g_part_count = 1;
+
+struct PerDevice {
+  SceneData<CudaBackend> sd;
+  Renderer<CudaBackend> rn;
+  float* fbStage = nullptr; int64_t fbStageN = 0;
+  int32_t* aovObj = nullptr; int32_t* aovTri = nullptr; double* aovT = nullptr; int64_t aovN = 0;
+};
+
+}  // namespace nrt
+
+struct nrt_scene {
+  std::vector<nrt::PerDevice> dev;
+  nrt_profile prof{};
+};
+
+namespace nrt {
+
+static int initLocked(int ngpu, const int* ids) {
+  if (!g_devs.empty()) return NRT_OK;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(NRT_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+  std::vector<int> use;
+  if (ids && ngpu > 0) use.assign(ids, ids + ngpu);
+  else if (ngpu == 0) for (int i = 0; i < count; ++i) use.push_back(i);
+  else for (int i = 0; i < std::min(std::max(ngpu, 1), count); ++i) use.push_back(i);
+  for (int id : use)
+    if (id < 0 || id >= count) return fail(NRT_ERR_INVALID, "device id out of range");
+  try {
+    for (int id : use) {
+      cudaDeviceProp p;
+      NRT_CUDA(cudaGetDeviceProperties(&p, id));
+      if (p.major < 10) return fail(NRT_ERR_NO_DEVICE, std::string("device ") + p.name + " is not sm_100 class; libnrt.so is built for sm_100a only");
+      auto* d = new DeviceCtx();
+      d->be.device = id;
+      d->be.sms = p.multiProcessorCount;
+      NRT_CUDA(cudaSetDevice(id));
+      NRT_CUDA(cudaStreamCreateWithFlags(&d->be.stream, cudaStreamNonBlocking));
+      NRT_CUDA(cudaEventCreate(&d->ev0)); NRT_CUDA(cudaEventCreate(&d->ev1));
+      NRT_CUDA(cudaEventCreate(&d->tb0)); NRT_CUDA(cudaEventCreate(&d->tb1));
+      g_devs.push_back(d);
+    }
+    // peer access between the selected devices (NVLink): finalize stores go straight to device 0
+    for (size_t i = 0; i < g_devs.size(); ++i)
+      for (size_t j = 0; j < g_devs.size(); ++j) {
+        if (i == j) continue;
+        int can = 0;
+        NRT_CUDA(cudaDeviceCanAccessPeer(&can, g_devs[i]->be.device, g_devs[j]->be.device));
+        if (can) {
+          NRT_CUDA(cudaSetDevice(g_devs[i]->be.device));
+          cudaError_t pe = cudaDeviceEnablePeerAccess(g_devs[j]->be.device, 0);
+          if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) NRT_CUDA(pe);
+          cudaGetLastError();
+        }
+      }
+  } catch (const std::exception& ex) {
+    return fail(NRT_ERR_CUDA, ex.what());
+  }
+  return NRT_OK;
+}
+
+// rows [y0,y1) with (y-y0) % step == 0 owned by `worker` of `nworkers` (scanline interleave)
+static std::vector<int32_t> rowsFor(int height, int y0, int y1, int step, int worker, int nworkers) {
+  std::vector<int32_t> r;
+  for (int y = std::max(0, y0); y < std::min(y1, height); ++y)
+    if ((y - y0) % step == 0 && (y % nworkers) == worker) r.push_back(y);
+  return r;
+}
+
+static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int step, int max_step, float* fb,
+                      nrt_stats* stats, const nrt_aov* aov, bool deviceOut) {
+  if (!sc || !o || !fb) return fail(NRT_ERR_INVALID, "null scene, options or framebuffer");
+  if (o->width <= 0 || o->height <= 0) return fail(NRT_ERR_INVALID, "non-positive image size");
+  if (!isPow2(step) || !isPow2(max_step) || max_step < step)
+    return fail(NRT_ERR_UNSUPPORTED, "step and maxStep must be powers of two with maxStep >= step (renderer.nim:166-168)");
+  if (o->aa_kind < NRT_AA_NONE || o->aa_kind > NRT_AA_CORRELATED_MULTI_JITTERED) return fail(NRT_ERR_INVALID, "bad antialias kind");
+  if (o->aa_kind != NRT_AA_NONE && (o->grid_size <= 0 || o->grid_size > 64)) return fail(NRT_ERR_INVALID, "gridSize must be in 1..64");
+  if (o->aa_kind >= NRT_AA_JITTERED && o->grid_size > kMaxJitterGrid) return fail(NRT_ERR_UNSUPPORTED, "jittered kinds support gridSize <= 16");
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called");
+  const int nd = int(sc->dev.size());
+  const int nworkers = nd * g_part_count;
+  const int64_t npx = int64_t(o->width) * o->height;
+  std::vector<int> rc(nd, NRT_OK);
+  std::vector<std::string> errs(nd);
+  std::vector<std::vector<unsigned long long>> st(nd, std::vector<unsigned long long>(ST_COUNT, 0));
+  const bool wantAov = aov && (aov->obj_id || aov->tri_id || aov->t_hit);
+
+  auto work = [&](int di) {
+    PerDevice& pd = sc->dev[di];
+    DeviceCtx* dc = g_devs[di];
+    CudaBackend& be = dc->be;
+    try {
+      be.use();
+      const int worker = g_part_index * nd + di;
+      const std::vector<int32_t> rows = rowsFor(o->height, y0, y1, step, worker, nworkers);
+      float* target = fb;
+      int32_t *aObj = nullptr, *aTri = nullptr; double* aT = nullptr;
+      if (!deviceOut) {
+        if (pd.fbStageN < npx * 3) {
+          be.dfree(pd.fbStage);
+          pd.fbStage = static_cast<float*>(be.dalloc(sizeof(float) * npx * 3));
+          pd.fbStageN = npx * 3;
+        }
+        target = pd.fbStage;
+        if (wantAov) {
+          if (pd.aovN < npx) {
+            be.dfree(pd.aovObj); be.dfree(pd.aovTri); be.dfree(pd.aovT);
+            pd.aovObj = static_cast<int32_t*>(be.dalloc(sizeof(int32_t) * npx));
+            pd.aovTri = static_cast<int32_t*>(be.dalloc(sizeof(int32_t) * npx));
+            pd.aovT = static_cast<double*>(be.dalloc(sizeof(double) * npx));
+            pd.aovN = npx;
+          }
+          aObj = aov->obj_id ? pd.aovObj : nullptr; aTri = aov->tri_id ? pd.aovTri : nullptr; aT = aov->t_hit ? pd.aovT : nullptr;
+        }
+      } else if (wantAov) {
+        aObj = aov->obj_id; aTri = aov->tri_id; aT = aov->t_hit;
+      }
+      be.launches = 0;
+      NRT_CUDA(cudaEventRecord(dc->ev0, be.stream));
+      rc[di] = pd.rn.render(pd.sd, *o, rows, step, max_step, target, aObj, aTri, aT, st[di].data(), errs[di]);
+      if (rc[di] == NRT_OK && !deviceOut) {
+        // device -> host, only the rows this worker produced (incl. their step x step fill rows)
+        const size_t rowB = size_t(o->width) * 3 * sizeof(float);
+        size_t i = 0;
+        while (i < rows.size()) {
+          // group equally spaced rows into one 2D copy (scanline interleave => one call)
+          size_t j = i + 1;
+          const int fill = std::min(step, o->height - rows[i]);
+          int stride = (j < rows.size()) ? rows[j] - rows[i] : 0;
+          while (j < rows.size() && rows[j] - rows[j - 1] == stride && std::min(step, o->height - rows[j]) == fill) ++j;
+          const size_t cnt = j - i;
+          const size_t off = size_t(rows[i]) * o->width * 3;
+          if (cnt == 1 || stride <= 0) {
+            NRT_CUDA(cudaMemcpyAsync(fb + off, target + off, rowB * fill, cudaMemcpyDeviceToHost, be.stream));
+            if (aObj) NRT_CUDA(cudaMemcpyAsync(aov->obj_id + off / 3, aObj + off / 3, sizeof(int32_t) * o->width * fill, cudaMemcpyDeviceToHost, be.stream));
+            if (aTri) NRT_CUDA(cudaMemcpyAsync(aov->tri_id + off / 3, aTri + off / 3, sizeof(int32_t) * o->width * fill, cudaMemcpyDeviceToHost, be.stream));
+            if (aT) NRT_CUDA(cudaMemcpyAsync(aov->t_hit + off / 3, aT + off / 3, sizeof(double) * o->width * fill, cudaMemcpyDeviceToHost, be.stream));
+            j = i + 1;
+          } else {
+            NRT_CUDA(cudaMemcpy2DAsync(fb + off, rowB * stride, target + off, rowB * stride, rowB * fill, cnt, cudaMemcpyDeviceToHost, be.stream));
+            const size_t po = off / 3, w = size_t(o->width);
+            if (aObj) NRT_CUDA(cudaMemcpy2DAsync(aov->obj_id + po, 4 * w * stride, aObj + po, 4 * w * stride, 4 * w * fill, cnt, cudaMemcpyDeviceToHost, be.stream));
+            if (aTri) NRT_CUDA(cudaMemcpy2DAsync(aov->tri_id + po, 4 * w * stride, aTri + po, 4 * w * stride, 4 * w * fill, cnt, cudaMemcpyDeviceToHost, be.stream));
+            if (aT) NRT_CUDA(cudaMemcpy2DAsync(aov->t_hit + po, 8 * w * stride, aT + po, 8 * w * stride, 8 * w * fill, cnt, cudaMemcpyDeviceToHost, be.stream));
+          }
+          i = j;
+        }
+      }
+      NRT_CUDA(cudaEventRecord(dc->ev1, be.stream));
+      NRT_CUDA(cudaStreamSynchronize(be.stream));
+    } catch (const std::exception& ex) {
+      rc[di] = NRT_ERR_CUDA;
+      errs[di] = ex.what();
+    }
+  };
+
+  if (nd == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int d = 1; d < nd; ++d) th.emplace_back(work, d);
+    work(0);
+    for (auto& t : th) t.join();
+  }
+  for (int d = 0; d < nd; ++d)
+    if (rc[d] != NRT_OK) return fail(rc[d], errs[d]);
+
+  nrt_profile& p = sc->prof;
+  p = nrt_profile{};
+  unsigned long long tot[ST_COUNT] = {0};
+  for (int d = 0; d < nd; ++d) {
+    for (int k = 0; k < ST_COUNT; ++k) tot[k] += st[d][k];
+    DeviceCtx* dc = g_devs[d];
+    float ms = 0;
+    cudaSetDevice(dc->be.device);
+    cudaEventElapsedTime(&ms, dc->ev0, dc->ev1);
+    p.total_ms = std::max(p.total_ms, double(ms));
+    int64_t nl = 0;
+    const double fms = dc->be.filterMs(&nl);
+    p.mesh_filter_ms = std::max(p.mesh_filter_ms, fms);
+    p.mesh_filter_launches += nl;
+    const ProfileAcc& a = sc->dev[d].rn.prof;
+    p.mesh_tests += a.mesh_tests; p.mesh_tests_ref += a.mesh_tests_ref; p.mesh_rays += a.mesh_rays;
+    p.candidates += a.candidates;
+    p.kernel_launches += dc->be.launches;
+    p.mesh_tests_by_mode[0] += a.mesh_tests;
+    p.mesh_ms_by_mode[0] = std::max(p.mesh_ms_by_mode[0], fms);
+  }
+  // executed float32 flops per filter test: 15 FFMA (30) + 2 FADD (nrt_core.h: filterTest)
+  p.fp32_flops = double(p.mesh_tests) * 32.0;
+  if (stats) {
+    stats->num_primary_rays = int64_t(tot[ST_PRIMARY]);
+    stats->num_intersection_tests = int64_t(tot[ST_TESTS]);
+    stats->num_intersection_hits = int64_t(tot[ST_HITS]);
+    stats->num_rays = int64_t(tot[ST_RAYS]);
+    stats->num_capped_samples = int64_t(tot[ST_CAPPED]);
+  }
+  return NRT_OK;
+}
+
+}  // namespace nrt
+
+using namespace nrt;
+
+// ---------------------------------------------------------------- C ABI ------
+extern "C" {
+
+int nrt_abi_version(void) { return NRT_ABI_VERSION; }
+const char* nrt_last_error(void) { return g_err.c_str(); }
+int nrt_band_rows(void) { return 1; }
+
+int nrt_init(int ngpu, const int* dev_ids) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return initLocked(ngpu, dev_ids);
+}
+
+void nrt_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto* d : g_devs) {
+    cudaSetDevice(d->be.device);
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->tb0) cudaEventDestroy(d->tb0);
+    if (d->tb1) cudaEventDestroy(d->tb1);
+    d->be.destroy();
+    delete d;
+  }
+  g_devs.clear();
+  g_part_index = 0; g_part_count = 1;
+}
+
+int nrt_device_count(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return int(g_devs.size());
+}
+
+int nrt_set_partition(int index, int count) {
+  if (count <= 0 || index < 0 || index >= count) return fail(NRT_ERR_INVALID, "bad partition");
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_part_index = index; g_part_count = count;
+  return NRT_OK;
+}
+
+static int sceneBuild(nrt_scene* s, const nrt_scene_desc* desc, bool reuse) {
+  for (size_t d = 0; d < s->dev.size(); ++d) {
+    std::string err;
+    try {
+      PerDevice& pd = s->dev[d];
+      pd.rn.be = &g_devs[d]->be;
+      const int rc = pd.sd.build(&g_devs[d]->be, desc, reuse, err);
+      if (rc != NRT_OK) return fail(rc, err);
+      g_devs[d]->be.sync();
+    } catch (const std::exception& ex) {
+      return fail(NRT_ERR_CUDA, ex.what());
+    }
+  }
+  return NRT_OK;
+}
+
+int nrt_scene_create(const nrt_scene_desc* desc, nrt_scene** out) {
+  if (!desc || !out) return fail(NRT_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called");
+  auto* s = new nrt_scene();
+  s->dev.resize(g_devs.size());
+  const int rc = sceneBuild(s, desc, false);
+  if (rc != NRT_OK) {
+    for (auto& pd : s->dev) pd.sd.destroy();
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return NRT_OK;
+}
+
+int nrt_scene_update(nrt_scene* scene, const nrt_scene_desc* desc) {
+  if (!scene || !desc) return fail(NRT_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called");
+  return sceneBuild(scene, desc, true);
+}
+
+void nrt_scene_destroy(nrt_scene* scene) {
+  if (!scene) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (size_t d = 0; d < scene->dev.size() && d < g_devs.size(); ++d) {
+    PerDevice& pd = scene->dev[d];
+    CudaBackend& be = g_devs[d]->be;
+    pd.sd.destroy();
+    pd.rn.freeAll();
+    be.dfree(pd.fbStage); be.dfree(pd.aovObj); be.dfree(pd.aovTri); be.dfree(pd.aovT);
+  }
+  delete scene;
+}
+
+int nrt_render(nrt_scene* scene, const nrt_options* opts, int y0, int y1, int step, int max_step, float* fb,
+               nrt_stats* stats, const nrt_aov* aov) {
+  return renderImpl(scene, opts, y0, y1, step, max_step, fb, stats, aov, false);
+}
+
+int nrt_render_device(nrt_scene* scene, const nrt_options* opts, int y0, int y1, int step, int max_step, float* fb_dev,
+                      nrt_stats* stats, const nrt_aov* aov_dev) {
+  return renderImpl(scene, opts, y0, y1, step, max_step, fb_dev, stats, aov_dev, true);
+}
+
+int nrt_get_profile(const nrt_scene* scene, nrt_profile* out) {
+  if (!scene || !out) return fail(NRT_ERR_INVALID, "null argument");
+  *out = scene->prof;
+  return NRT_OK;
+}
+
+int nrt_framebuf_to_srgb8(const float* fb_host, int width, int height, int srgb, unsigned char* rgb8) {
+  if (!fb_host || !rgb8 || width <= 0 || height <= 0) return fail(NRT_ERR_INVALID, "bad argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called");
+  CudaBackend& be = g_devs[0]->be;
+  const int64_t n = int64_t(width) * height * 3;
+  float* d = nullptr; unsigned char* o = nullptr;
+  try {
+    d = static_cast<float*>(be.dalloc(n * sizeof(float)));
+    o = static_cast<unsigned char*>(be.dalloc(n));
+    be.upload(d, fb_host, n * sizeof(float));
+    k_srgb8<<<CudaBackend::blocksFor(n), kBlock, 0, be.stream>>>(d, o, n, srgb);
+    NRT_CUDA(cudaGetLastError());
+    be.download(rgb8, o, n);
+  } catch (const std::exception& ex) {
+    be.dfree(d); be.dfree(o);
+    return fail(NRT_ERR_CUDA, ex.what());
+  }
+  be.dfree(d); be.dfree(o);
+  return NRT_OK;
+}
+
+#define NRT_NEED_DEV0()                                                               \
+  std::lock_guard<std::mutex> lk(g_mu);                                               \
+  if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called"); \
+  CudaBackend& be = g_devs[0]->be;
+
+int nrt_device_alloc(int64_t bytes, void** dev_ptr) {
+  if (!dev_ptr || bytes < 0) return fail(NRT_ERR_INVALID, "bad argument");
+  NRT_NEED_DEV0();
+  try { *dev_ptr = be.dalloc(size_t(bytes)); } catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
+  return NRT_OK;
+}
+int nrt_device_free(void* dev_ptr) {
+  NRT_NEED_DEV0();
+  be.dfree(dev_ptr);
+  return NRT_OK;
+}
+int nrt_device_memset(void* dev_ptr, int value, int64_t bytes) {
+  NRT_NEED_DEV0();
+  try { be.use(); NRT_CUDA(cudaMemsetAsync(dev_ptr, value, size_t(bytes), be.stream)); be.sync(); }
+  catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
+  return NRT_OK;
+}
+int nrt_copy_to_host(void* host_dst, const void* dev_src, int64_t bytes) {
+  NRT_NEED_DEV0();
+  try { be.download(host_dst, dev_src, size_t(bytes)); } catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
+  return NRT_OK;
+}
+int nrt_device_synchronize(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  try { for (auto* d : g_devs) d->be.sync(); } catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
+  return NRT_OK;
+}
+int nrt_ipc_export(void* dev_ptr, nrt_ipc_handle* out) {
+  if (!dev_ptr || !out) return fail(NRT_ERR_INVALID, "null argument");
+  NRT_NEED_DEV0();
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(nrt_ipc_handle), "handle size");
+  cudaIpcMemHandle_t h;
+  be.use();
+  cudaError_t e = cudaIpcGetMemHandle(&h, dev_ptr);
+  if (e != cudaSuccess) return fail(NRT_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  std::memset(out, 0, sizeof(*out));
+  std::memcpy(out->bytes, &h, sizeof(h));
+  return NRT_OK;
+}
+int nrt_ipc_open(const nrt_ipc_handle* handle, void** dev_ptr) {
+  if (!handle || !dev_ptr) return fail(NRT_ERR_INVALID, "null argument");
+  NRT_NEED_DEV0();
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle->bytes, sizeof(h));
+  be.use();
+  cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(NRT_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  return NRT_OK;
+}
+int nrt_ipc_close(void* dev_ptr) {
+  NRT_NEED_DEV0();
+  be.use();
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  if (e != cudaSuccess) return fail(NRT_ERR_CUDA, std::string("cudaIpcCloseMemHandle: ") + cudaGetErrorString(e));
+  return NRT_OK;
+}
+
+int nrt_measure_fp32_peak(double* tflops, double* sm_clock_mhz_hint) {
+  if (!tflops) return fail(NRT_ERR_INVALID, "null argument");
+  NRT_NEED_DEV0();
+  try {
+    be.use();
+    float* out = static_cast<float*>(be.dalloc(16));
+    cudaEvent_t e0, e1;
+    NRT_CUDA(cudaEventCreate(&e0)); NRT_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = be.sms * 8;
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+      NRT_CUDA(cudaEventRecord(e0, be.stream));
+      k_ffma_peak<<<blocks, 256, 0, be.stream>>>(out, iters, 1.0001f, 0.0001f);
+      NRT_CUDA(cudaEventRecord(e1, be.stream));
+      NRT_CUDA(cudaStreamSynchronize(be.stream));
+      float ms = 0;
+      NRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double fl = double(blocks) * 256.0 * iters * 16.0 * 2.0;
+      if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    be.dfree(out);
+    *tflops = best;
+    if (sm_clock_mhz_hint) {
+      int khz = 0;
+      cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, be.device);
+      *sm_clock_mhz_hint = khz / 1000.0;
+    }
+  } catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
+  return NRT_OK;
+}
+
+int nrt_timer_begin(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called");
+  try {
+    for (auto* d : g_devs) { d->be.use(); NRT_CUDA(cudaEventRecord(d->tb0, d->be.stream)); }
+  } catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
+  return NRT_OK;
+}
+
+int nrt_timer_end(double* ms) {
+  if (!ms) return fail(NRT_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called");
+  try {
+    double worst = 0;
+    for (auto* d : g_devs) { d->be.use(); NRT_CUDA(cudaEventRecord(d->tb1, d->be.stream)); }
+    for (auto* d : g_devs) {
+      d->be.use();
+      NRT_CUDA(cudaEventSynchronize(d->tb1));
+      float t = 0;
+      NRT_CUDA(cudaEventElapsedTime(&t, d->tb0, d->tb1));
+      worst = std::max(worst, double(t));
+    }
+    *ms = worst;
+  } catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
+  return NRT_OK;
+}
+
+int nrt_host_alloc_pinned(int64_t bytes, void** host_ptr) {
+  if (!host_ptr || bytes < 0) return fail(NRT_ERR_INVALID, "bad argument");
+  cudaError_t e = cudaHostAlloc(host_ptr, size_t(bytes ? bytes : 16), cudaHostAllocPortable);
+  if (e != cudaSuccess) return fail(NRT_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  return NRT_OK;
+}
+int nrt_host_free_pinned(void* host_ptr) {
+  if (host_ptr) cudaFreeHost(host_ptr);
+  return NRT_OK;
+}
+
+}  // extern "C"

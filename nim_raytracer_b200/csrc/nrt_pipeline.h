@@ -1,0 +1,475 @@
+// nrt_pipeline.h — wavefront formulation of the reference's per-pixel path.
+//
+// The reference evaluates  renderLine -> calcPixel* -> castPrimaryRay / trace /
+// shade  recursively per pixel on CPU threads (renderer.nim:31-211).  Here the
+// same computation is organised as waves of rays over a chunk of samples:
+//
+//   gen      : castPrimaryRay for every sample              (renderer.nim:31-44,132-159)
+//   per bounce:
+//     gate   : per (ray, mesh object) AABB gate of TriangleMesh.intersect
+//              (geom.nim:340) + ballot-compacted queue of float32 filter rays
+//     filter : float32 ray x triangle filter over the queue (the hot kernel)
+//     verify : float64 exact re-evaluation of the candidates, nearest hit with
+//              first-index-wins ties                        (geom.nim:346-358)
+//     shade  : trace()'s in-order object scan + hit point/normal (renderer.nim:47-88)
+//     gate/filter/verify again for the shadow rays          (renderer.nim:93-104)
+//     resolve: shadow tests, shadeDiffuse, reflection ray   (renderer.nim:93-127)
+//   finalize : per-pixel sample sum, * 1/N, float32 store   (renderer.nim:147-159,204-209)
+//
+// The functors below are the per-element bodies; a backend (CUDA in nrt.cu,
+// plain loops in the test-only emulation) supplies launch/alloc primitives.
+#pragma once
+
+#include "nrt_core.h"
+
+namespace nrt {
+
+enum WaveKind { WAVE_PATH = 0, WAVE_SHADOW = 1 };
+
+// Counter slots per (wave, mesh object)
+enum { CNT_QUEUE = 0, CNT_EXACT = 1, CNT_CAND = 2, CNT_TILE = 3, CNT_STRIDE = 4 };
+// Stats slots
+enum { ST_PRIMARY = 0, ST_TESTS = 1, ST_HITS = 2, ST_RAYS = 3, ST_CAPPED = 4, ST_CONT = 5, ST_COUNT = 8 };
+
+struct FrameParams {
+  int32_t width, height;
+  int32_t aa_kind, grid, spp;
+  int32_t step, max_step;
+  int32_t depth_mode, max_ray_depth, bounce_cap;
+  int32_t nx;              // x positions per row = ceil(width / step)
+  int32_t _pad;
+  double bias;
+  uint64_t seed;
+};
+
+// Device-resident state of one chunk of samples (component-major SoA).
+struct ChunkState {
+  int64_t S;         // sample capacity
+  int64_t NR;        // wave-ray capacity = S * max(1, nlights)
+  int32_t nMO;       // mesh objects in the scene
+  int32_t nL;        // lights
+  int64_t candCap;
+  // per sample
+  double* rayO;      // 4*S
+  double* rayD;      // 4*S
+  double* hitW;      // 4*S
+  double* nrm;       // 4*S
+  double* accum;     // 3*S
+  double* weight;    // S
+  int32_t* hitObj;   // S (-1 none)
+  int32_t* bounce;   // S
+  uint8_t* active;   // S
+  // per wave ray and mesh object
+  uint64_t* tBest;   // nMO*NR   (bit pattern of a float64)
+  uint32_t* triBest; // nMO*NR
+  uint32_t* qref;    // nMO*NR   filter queue: wave-ray index
+  float* qray;       // nMO*NR*8 filter queue: plane 0 (d, rr) then plane 1 (m, pad), float4 each
+  uint32_t* xref;    // nMO*NR   exact (float64 brute force) queue
+  // candidates of the current (wave, mesh object)
+  uint32_t* candRef; // candCap
+  uint32_t* candTri; // candCap
+  double* candT;     // candCap
+  uint32_t* counters;  // maxWaves*nMO*CNT_STRIDE
+  unsigned long long* stats;  // ST_COUNT
+  // pixel list of this worker
+  const int32_t* rows; // device array of row indices
+  int64_t p0;          // first pixel (in the worker's pixel list) of this chunk
+  int64_t npix;        // pixels in this chunk
+  // outputs
+  float* fb;           // width*height*3 (may be peer memory)
+  int32_t* aovObj;     // may be null
+  int32_t* aovTri;
+  double* aovT;
+};
+
+NRT_HD V4 ld4(const double* a, int64_t n, int64_t i) { return v4(a[i], a[n + i], a[2 * n + i], a[3 * n + i]); }
+NRT_HD void st4(double* a, int64_t n, int64_t i, V4 v) { a[i] = v.x; a[n + i] = v.y; a[2 * n + i] = v.z; a[3 * n + i] = v.w; }
+
+NRT_HD void pixelOf(const FrameParams& fp, const ChunkState& cs, int64_t p, int& x, int& y) {
+  const int64_t ri = p / fp.nx;
+  x = int(p - ri * fp.nx) * fp.step;
+  y = cs.rows[ri];
+}
+NRT_HD bool pixelSkipped(const FrameParams& fp, int x, int y) {  // renderer.nim:175-178
+  if (fp.step < fp.max_step) {
+    const int mask = fp.step * 2 - 1;
+    if (((x & mask) == 0) && ((y & mask) == 0)) return true;
+  }
+  return false;
+}
+
+// sampling.nim:5-113 for one pixel; px/py have m*m entries.  Max grid 16 for jittered kinds.
+static constexpr int kMaxJitterGrid = 16;
+NRT_HD void makeSamples(int kind, int m, PixelRng& rng, double* px, double* py) {
+  const int n = m;
+  if (kind == AA_GRID) {
+    const double xs = 1.0 / double(n), ys = 1.0 / double(m);
+    const double xoffs = xs * 0.5, yoffs = xs * 0.5;
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < n; ++i) { px[j * m + i] = double(i) * xs + xoffs; py[j * m + i] = double(j) * ys + yoffs; }
+  } else if (kind == AA_JITTERED) {
+    const double xs = 1.0 / double(n), ys = 1.0 / double(m);
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < n; ++i) {
+        const double rx = rng.random(xs), ry = rng.random(ys);
+        px[j * m + i] = double(i) * xs + rx;
+        py[j * m + i] = double(j) * ys + ry;
+      }
+  } else {
+    const double xs = 1.0 / double(n), ys = 1.0 / double(m);
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < m; ++i) {
+        const double jj = j, ii = i;
+        const double r1 = rng.random(1.0), r2 = rng.random(1.0);
+        px[j * m + i] = (ii + (jj + r1) * xs) * ys;
+        py[j * m + i] = (jj + (ii + r2) * ys) * xs;
+      }
+    if (kind == AA_MULTI_JITTERED) {
+      for (int j = 0; j < n; ++j)
+        for (int i = 0; i < m; ++i) {
+          const int k = j + int(rng.random(1.0) * double(n - j));
+          const double t = px[j * m + i]; px[j * m + i] = px[k * m + i]; px[k * m + i] = t;
+        }
+      for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) {
+          const int k = i + int(rng.random(1.0) * double(m - i));
+          const double t = py[j * m + i]; py[j * m + i] = py[j * m + k]; py[j * m + k] = t;
+        }
+    } else {
+      for (int j = 0; j < n; ++j) {
+        const int k = j + int(rng.random(1.0) * double(n - j));
+        for (int i = 0; i < m; ++i) { const double t = px[j * m + i]; px[j * m + i] = px[k * m + i]; px[k * m + i] = t; }
+      }
+      for (int i = 0; i < m; ++i) {
+        const int k = i + int(rng.random(1.0) * double(m - i));
+        for (int j = 0; j < n; ++j) { const double t = py[j * m + i]; py[j * m + i] = py[j * m + k]; py[j * m + k] = t; }
+      }
+    }
+  }
+}
+
+NRT_HD void initSample(const ChunkState& cs, int64_t s, bool alive, V4 o, V4 d) {
+  st4(cs.rayO, cs.S, s, o);
+  st4(cs.rayD, cs.S, s, d);
+  cs.accum[s] = 0.0; cs.accum[cs.S + s] = 0.0; cs.accum[2 * cs.S + s] = 0.0;
+  cs.weight[s] = 1.0;
+  cs.hitObj[s] = -1;
+  cs.bounce[s] = 0;
+  cs.active[s] = alive ? 1 : 0;
+}
+
+// ---- gen: one element per SAMPLE (akNone / akGrid) ---------------------------
+struct GenSimple {
+  const DScene* sc; FrameParams fp; ChunkState cs;
+  NRT_HD void operator()(int64_t s) const {
+    const int64_t p = cs.p0 + s / fp.spp;
+    const int k = int(s % fp.spp);
+    int x, y; pixelOf(fp, cs, p, x, y);
+    const bool alive = !pixelSkipped(fp, x, y);
+    double sx = 0.0, sy = 0.0;
+    if (fp.aa_kind == AA_GRID) {  // sampling.nim:5-18, element j*m+i
+      const int m = fp.grid, i = k % m, j = k / m;
+      const double xs = 1.0 / double(m), ys = 1.0 / double(m);
+      const double xoffs = xs * 0.5, yoffs = xs * 0.5;
+      sx = double(i) * xs + xoffs; sy = double(j) * ys + yoffs;
+    }
+    V4 o, d;
+    // akNone: (x.float, y.float) — the pixel corner (renderer.nim:135); else x.float + sample
+    castPrimaryRay(*sc, fp.width, fp.height, fp.aa_kind == AA_NONE ? double(x) : double(x) + sx,
+                   fp.aa_kind == AA_NONE ? double(y) : double(y) + sy, o, d);
+    initSample(cs, s, alive, o, d);
+  }
+};
+
+// ---- gen: one element per PIXEL (jittered kinds need the whole pattern) ------
+struct GenJittered {
+  const DScene* sc; FrameParams fp; ChunkState cs;
+  NRT_HD void operator()(int64_t pl) const {
+    const int64_t p = cs.p0 + pl;
+    int x, y; pixelOf(fp, cs, p, x, y);
+    const bool alive = !pixelSkipped(fp, x, y);
+    double px[kMaxJitterGrid * kMaxJitterGrid], py[kMaxJitterGrid * kMaxJitterGrid];
+    PixelRng rng = pixelRng(fp.seed, fp.width, x, y);
+    makeSamples(fp.aa_kind, fp.grid, rng, px, py);
+    for (int k = 0; k < fp.spp; ++k) {
+      V4 o, d;
+      castPrimaryRay(*sc, fp.width, fp.height, double(x) + px[k], double(y) + py[k], o, d);
+      initSample(cs, pl * fp.spp + k, alive, o, d);
+    }
+  }
+};
+
+// World-space ray `i` of a wave.  PATH: the sample's current ray.  SHADOW: ray
+// (sample = i / nL, light = i % nL) rebuilt from the hit record (renderer.nim:93-99).
+NRT_HD bool waveRay(const DScene& sc, const FrameParams& fp, const ChunkState& cs, int kind, int64_t i, V4& o, V4& d) {
+  if (kind == WAVE_PATH) {
+    if (!cs.active[i]) return false;
+    o = ld4(cs.rayO, cs.S, i); d = ld4(cs.rayD, cs.S, i);
+    return true;
+  }
+  const int64_t s = i / cs.nL;
+  const int l = int(i - s * cs.nL);
+  if (cs.hitObj[s] < 0) return false;
+  const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
+  const ShadingInfo si = getShadingInfo(sc.lights[l], hitW);
+  o = add(hitW, scale(n, fp.bias));
+  d = scale(si.lightDir, -1.0);
+  return true;
+}
+
+NRT_HD Ray objectRay(const DObject& ob, V4 o, V4 d) {  // renderer.nim:54-55
+  return initRay(mulm(ob.w2o, o), mulm(ob.w2o, d));
+}
+
+NRT_HD bool filterSafe(const DMesh& m, const Ray& r) {
+  const double big = 1e15, tiny = 1e-15;
+  const double ox = r.orig.x - m.center[0], oy = r.orig.y - m.center[1], oz = r.orig.z - m.center[2];
+  const double di = fmax(fabs(r.dir.x), fmax(fabs(r.dir.y), fabs(r.dir.z)));
+  const double oi = fmax(fabs(ox), fmax(fabs(oy), fabs(oz)));
+  // NaN compares false => unsafe
+  return (di < big) && (di > tiny) && (oi < big) && (m.L < big) && (m.L > tiny);
+}
+
+// ---- gate: TriangleMesh.intersect's AABB test (geom.nim:340) per (ray, mesh object)
+struct GateOut { bool pass, safe; FilterRay fr; };
+struct Gate {
+  const DScene* sc; FrameParams fp; ChunkState cs; int kind; int64_t n; int force_exact;
+  NRT_HD GateOut operator()(int64_t i, int mo) const {
+    GateOut g; g.pass = false; g.safe = false;
+    V4 o, d;
+    const bool valid = (i < n) && waveRay(*sc, fp, cs, kind, i, o, d);
+    if (!valid) return g;
+    const DObject& ob = sc->objects[sc->mesh_obj_index[mo]];
+    const DMesh& m = sc->meshes[ob.mesh];
+    const Ray r = objectRay(ob, o, d);
+    const double tmin = aabbIntersect(m.bmin, m.bmax, r);
+    g.pass = !(tmin < 0);
+    cs.tBest[int64_t(mo) * cs.NR + i] = dbits(g.pass ? NRT_INF : NRT_NEG_INF);
+    cs.triBest[int64_t(mo) * cs.NR + i] = kNoTri;
+    if (g.pass) {
+      g.safe = !force_exact && filterSafe(m, r);
+      if (g.safe) g.fr = makeFilterRay(m, r);
+    }
+    return g;
+  }
+};
+
+// ---- exact: float64 brute force over ALL faces for rays the filter cannot take
+struct ExactMesh {
+  const DScene* sc; FrameParams fp; ChunkState cs; int kind; int mo; const uint32_t* count;
+  NRT_HD void operator()(int64_t qi) const {
+    const uint32_t ref = cs.xref[int64_t(mo) * cs.NR + qi];
+    V4 o, d;
+    if (!waveRay(*sc, fp, cs, kind, ref, o, d)) return;
+    const DObject& ob = sc->objects[sc->mesh_obj_index[mo]];
+    const DMesh& m = sc->meshes[ob.mesh];
+    const Ray r = objectRay(ob, o, d);
+    double tMin = NRT_INF; uint32_t tri = kNoTri;
+    for (int64_t f = 0; f < m.nfaces; ++f) {  // geom.nim:346-356
+      const double t = rayTriangleExact(r, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1],
+                                        m.verts + 4 * m.vidx[3 * f + 2]);
+      if (t >= 0 && t < tMin) { tMin = t; tri = uint32_t(f); }
+    }
+    cs.tBest[int64_t(mo) * cs.NR + ref] = dbits(tMin == 0 ? 0.0 : tMin);
+    cs.triBest[int64_t(mo) * cs.NR + ref] = tri;
+  }
+};
+
+// atomics supplied by the backend
+template <class A>
+struct Verify1 {  // float64 re-evaluation of candidate c; running minimum of t per ray
+  const DScene* sc; FrameParams fp; ChunkState cs; int kind; int mo;
+  NRT_HD void operator()(int64_t c) const {
+    const uint32_t ref = cs.candRef[c], tri = cs.candTri[c];
+    V4 o, d;
+    double t = NRT_NEG_INF;
+    if (waveRay(*sc, fp, cs, kind, ref, o, d)) {
+      const DObject& ob = sc->objects[sc->mesh_obj_index[mo]];
+      const DMesh& m = sc->meshes[ob.mesh];
+      const Ray r = objectRay(ob, o, d);
+      t = rayTriangleExact(r, m.verts + 4 * m.vidx[3 * int64_t(tri)], m.verts + 4 * m.vidx[3 * int64_t(tri) + 1],
+                           m.verts + 4 * m.vidx[3 * int64_t(tri) + 2]);
+    }
+    if (t >= 0) {             // geom.nim:354 `tHit >= 0` (NaN and NegInf fail)
+      if (t == 0) t = 0.0;    // -0.0 -> +0.0 so that bit patterns order like values
+      A::min64(&cs.tBest[int64_t(mo) * cs.NR + ref], dbits(t));
+    }
+    cs.candT[c] = t;
+  }
+};
+template <class A>
+struct Verify2 {  // among candidates attaining the minimum, the lowest face index wins (geom.nim:354 strict <)
+  ChunkState cs; int mo;
+  NRT_HD void operator()(int64_t c) const {
+    const double t = cs.candT[c];
+    if (!(t >= 0)) return;
+    const uint32_t ref = cs.candRef[c];
+    if (dbits(t) == cs.tBest[int64_t(mo) * cs.NR + ref]) A::min32(&cs.triBest[int64_t(mo) * cs.NR + ref], cs.candTri[c]);
+  }
+};
+
+// trace(): renderer.nim:47-67 with the mesh results looked up.  `wi` = wave-ray index.
+struct TraceOut { int obj; double t; uint32_t tri; int tests, hits; };
+NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d, double tNear, int64_t wi) {
+  TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
+  for (int i = 0; i < sc.nobjects; ++i) {
+    const DObject& ob = sc.objects[i];
+    double t; uint32_t tri = kNoTri;
+    if (ob.kind == GEOM_MESH) {
+      t = bitsd(cs.tBest[int64_t(ob.mesh_obj) * cs.NR + wi]);
+      tri = cs.triBest[int64_t(ob.mesh_obj) * cs.NR + wi];
+    } else {
+      const Ray ro = objectRay(ob, o, d);
+      t = ob.kind == GEOM_SPHERE ? sphereIntersect(ob.radius, ro)
+          : ob.kind == GEOM_PLANE ? planeIntersect(ro)
+          : ob.kind == GEOM_BOX ? aabbIntersect(ob.bmin, ob.bmax, ro) : NRT_NEG_INF;
+    }
+    r.tests++;
+    if (t >= 0 && t < r.t) { r.t = t; r.obj = i; r.tri = tri; r.hits++; }
+  }
+  return r;
+}
+
+struct StatDelta { unsigned long long v[ST_COUNT]; };
+NRT_HD StatDelta zeroStats() { StatDelta s; for (int i = 0; i < ST_COUNT; ++i) s.v[i] = 0; return s; }
+
+// ---- shade: nearest hit of the path ray, hit point and normal (renderer.nim:71-88)
+struct Shade {
+  const DScene* sc; FrameParams fp; ChunkState cs;
+  NRT_HD StatDelta operator()(int64_t s) const {
+    StatDelta st = zeroStats();
+    if (!cs.active[s]) return st;
+    const V4 o = ld4(cs.rayO, cs.S, s), d = ld4(cs.rayD, cs.S, s);
+    const TraceOut tr = traceObjects(*sc, cs, o, d, NRT_INF, s);
+    st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
+    const int bounce = cs.bounce[s];
+    if (bounce == 0) {
+      st.v[ST_PRIMARY] = 1;
+      if (s % fp.spp == 0 && (cs.aovObj || cs.aovTri || cs.aovT)) {
+        int x, y; pixelOf(fp, cs, cs.p0 + s / fp.spp, x, y);
+        const int64_t pi = int64_t(y) * fp.width + x;
+        if (cs.aovObj) cs.aovObj[pi] = tr.obj;
+        if (cs.aovTri) cs.aovTri[pi] = (tr.obj >= 0 && tr.tri != kNoTri) ? int32_t(tr.tri) : -1;
+        if (cs.aovT) cs.aovT[pi] = tr.t;
+      }
+    }
+    if (tr.obj < 0) {  // renderer.nim:74-75 (or :123-124 for a reflection ray): background
+      const double w = cs.weight[s];
+      cs.accum[s] = cs.accum[s] + sc->bg[0] * w;
+      cs.accum[cs.S + s] = cs.accum[cs.S + s] + sc->bg[1] * w;
+      cs.accum[2 * cs.S + s] = cs.accum[2 * cs.S + s] + sc->bg[2] * w;
+      cs.active[s] = 0;
+      cs.hitObj[s] = -1;
+      return st;
+    }
+    const DObject& ob = sc->objects[tr.obj];
+    const V4 hitW = add(o, scale(d, tr.t));
+    V4 n;
+    if (tr.tri == kNoTri) {
+      const V4 hitO = mulm(ob.w2o, hitW);
+      n = mulm(ob.o2w, geomNormal(ob, hitO));
+    } else {
+      const DMesh& m = sc->meshes[ob.mesh];
+      const double* nn = m.normals + 4 * m.nidx[3 * int64_t(tr.tri)];
+      n = mulm(ob.o2w, v4(nn[0], nn[1], nn[2], nn[3]));
+    }
+    st4(cs.hitW, cs.S, s, hitW);
+    st4(cs.nrm, cs.S, s, n);
+    cs.hitObj[s] = tr.obj;
+    return st;
+  }
+};
+
+// ---- resolve: shadow tests + diffuse + reflection set-up (renderer.nim:90-127)
+struct Resolve {
+  const DScene* sc; FrameParams fp; ChunkState cs;
+  NRT_HD StatDelta operator()(int64_t s) const {
+    StatDelta st = zeroStats();
+    const int objHit = cs.hitObj[s];
+    if (objHit < 0) return st;
+    const DObject& ob = sc->objects[objHit];
+    const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
+    V3 local = v3(0.0, 0.0, 0.0);
+    for (int l = 0; l < cs.nL; ++l) {
+      const ShadingInfo si = getShadingInfo(sc->lights[l], hitW);
+      const V4 so = add(hitW, scale(n, fp.bias)), sd = scale(si.lightDir, -1.0);
+      const TraceOut tr = traceObjects(*sc, cs, so, sd, si.lightDistance, s * cs.nL + l);
+      st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
+      if (tr.obj < 0) local = add(local, shadeDiffuse(ob, si, n));
+    }
+    const double k = ob.reflection, w = cs.weight[s];
+    const int bounce = cs.bounce[s];
+    const int depth = (fp.depth_mode == DEPTH_INTENDED) ? (1 + bounce) : 0;  // renderer.nim:108 + depth bug
+    bool cont = false;
+    double wl = w;  // weight of `local` in the pixel
+    if (k > 0.0 && depth <= fp.max_ray_depth) {
+      if (bounce >= fp.bounce_cap) {
+        st.v[ST_CAPPED] = 1;
+      } else {
+        cont = true;
+        wl = w * (1.0 - k);  // result = (1-k)*result + k*reflColor (renderer.nim:126-127)
+      }
+    }
+    cs.accum[s] = cs.accum[s] + local.x * wl;
+    cs.accum[cs.S + s] = cs.accum[cs.S + s] + local.y * wl;
+    cs.accum[2 * cs.S + s] = cs.accum[2 * cs.S + s] + local.z * wl;
+    cs.hitObj[s] = -1;
+    if (cont) {
+      const V4 i = ld4(cs.rayD, cs.S, s);
+      const V4 r = sub(i, scale(n, 2 * dot(n, i)));  // renderer.nim:112
+      st4(cs.rayO, cs.S, s, add(hitW, scale(r, fp.bias)));
+      st4(cs.rayD, cs.S, s, r);
+      cs.weight[s] = w * k;
+      cs.bounce[s] = bounce + 1;
+      cs.active[s] = 1;
+      st.v[ST_CONT] = 1;
+    } else {
+      cs.active[s] = 0;
+    }
+    return st;
+  }
+};
+
+// ---- finalize: sample sum in order, * 1/N, float32 store (+ step x step fill)
+struct Finalize {
+  FrameParams fp; ChunkState cs;
+  NRT_HD void operator()(int64_t pl) const {
+    int x, y; pixelOf(fp, cs, cs.p0 + pl, x, y);
+    if (pixelSkipped(fp, x, y)) return;
+    double r, g, b;
+    const int64_t s0 = pl * fp.spp;
+    if (fp.aa_kind == AA_NONE) {
+      r = cs.accum[s0]; g = cs.accum[cs.S + s0]; b = cs.accum[2 * cs.S + s0];
+    } else {
+      r = 0.0; g = 0.0; b = 0.0;
+      for (int k = 0; k < fp.spp; ++k) {
+        r = r + cs.accum[s0 + k]; g = g + cs.accum[cs.S + s0 + k]; b = b + cs.accum[2 * cs.S + s0 + k];
+      }
+      const double inv = 1 / double(fp.spp);  // renderer.nim:159
+      r = r * inv; g = g * inv; b = b * inv;
+    }
+    const float fr = float(r), fg = float(g), fbv = float(b);  // framebuf.nim:26-28
+    const int x1 = (fp.step > 1) ? (x + fp.step < fp.width ? x + fp.step : fp.width) : x + 1;
+    const int y1 = (fp.step > 1) ? (y + fp.step < fp.height ? y + fp.step : fp.height) : y + 1;
+    for (int j = y; j < y1; ++j)
+      for (int i = x; i < x1; ++i) {
+        float* p = cs.fb + (int64_t(j) * fp.width + i) * 3;
+        p[0] = fr; p[1] = fg; p[2] = fbv;
+      }
+  }
+};
+
+// ---- per-mesh precompute: float32 filter records (one element per face)
+struct BuildRecs {
+  DMesh m;
+  NRT_HD void operator()(int64_t f) const {
+    if (f >= m.nfaces) {  // padding record
+      for (int k = 0; k < 16; ++k) m.recs[16 * f + k] = (k == 3) ? -1.0f : 0.0f;
+      return;
+    }
+    makeFilterRec(m, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2],
+                  m.recs + 16 * f);
+  }
+};
+
+}  // namespace nrt

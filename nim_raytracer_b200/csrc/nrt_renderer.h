@@ -1,0 +1,315 @@
+// nrt_renderer.h — backend-independent host orchestration of the wavefront
+// pipeline (nrt_pipeline.h): scene flattening/upload and the per-chunk wave loop.
+// `BE` supplies memory, launches and atomics: CudaBackend in nrt.cu (the
+// product) or the loop backend of the test-only emulation.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nrt.h"
+#include "nrt_pipeline.h"
+
+namespace nrt {
+
+struct ProfileAcc {
+  int64_t mesh_tests = 0, mesh_tests_ref = 0, mesh_rays = 0, candidates = 0, exact_rays = 0;
+};
+
+inline bool isPow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// ------------------------------------------------------------------ scene ----
+template <class BE>
+struct SceneData {
+  BE* be = nullptr;
+  DScene h{};                 // host copy of the header (device pointers inside)
+  DScene* d = nullptr;        // device copy
+  std::vector<DObject> objs;
+  std::vector<DLight> lights;
+  std::vector<DMesh> meshes;  // device pointers inside
+  std::vector<int32_t> moIndex;
+  DObject* dObjs = nullptr; DLight* dLights = nullptr; DMesh* dMeshes = nullptr; int32_t* dMo = nullptr;
+  std::vector<void*> owned;
+  bool anyReflective = false;
+  int64_t bytes_uploaded = 0;
+
+  // geom.nim:175-188
+  static void calcAABB(const double* v, int64_t n, double* bmin, double* bmax) {
+    bmin[0] = bmin[1] = bmin[2] = NRT_INF; bmin[3] = 1.0;
+    bmax[0] = bmax[1] = bmax[2] = NRT_NEG_INF; bmax[3] = 1.0;
+    for (int64_t i = 0; i < n; ++i) {
+      const double* p = v + 4 * i;
+      for (int k = 0; k < 3; ++k) {
+        if (p[k] < bmin[k]) bmin[k] = p[k];
+        if (p[k] > bmax[k]) bmax[k] = p[k];
+      }
+    }
+  }
+
+  template <class T>
+  T* up(const T* src, int64_t n, T* reuse = nullptr) {
+    if (n <= 0) n = 1;
+    T* p = reuse;
+    if (!p) { p = static_cast<T*>(be->dalloc(sizeof(T) * n)); owned.push_back(p); }
+    if (src) { be->upload(p, src, sizeof(T) * n); bytes_uploaded += int64_t(sizeof(T)) * n; }
+    return p;
+  }
+
+  // Validates and flattens `desc`; with `reuse` the existing device buffers are refilled.
+  int build(BE* backend, const nrt_scene_desc* desc, bool reuse, std::string& err) {
+    be = backend;
+    if (!desc || desc->nobjects < 0 || desc->nlights < 0 || desc->nmeshes < 0 ||
+        (desc->nobjects > 0 && !desc->objects) || (desc->nlights > 0 && !desc->lights) ||
+        (desc->nmeshes > 0 && !desc->meshes)) { err = "null or negative-sized scene description"; return NRT_ERR_INVALID; }
+    if (reuse && (desc->nobjects != h.nobjects || desc->nlights != h.nlights || desc->nmeshes != h.nmeshes)) {
+      err = "nrt_scene_update: scene shape differs from the created scene"; return NRT_ERR_INVALID;
+    }
+    bytes_uploaded = 0;
+    std::vector<DMesh> old = meshes;
+    objs.assign(desc->nobjects, DObject{});
+    lights.assign(desc->nlights, DLight{});
+    meshes.assign(desc->nmeshes, DMesh{});
+    moIndex.clear();
+    for (int i = 0; i < desc->nmeshes; ++i) {
+      const nrt_mesh& m = desc->meshes[i];
+      if (m.nverts < 0 || m.nfaces < 0 || m.nnormals < 0 || (m.nfaces > 0 && (!m.vertices || !m.vertex_idx || !m.normal_idx)) ||
+          m.nfaces > 0xFFFFFFF0ll) { err = "bad mesh description"; return NRT_ERR_INVALID; }
+      if (reuse && (m.nverts != old[i].nverts || m.nfaces != old[i].nfaces || m.nnormals != old[i].nnormals)) {
+        err = "nrt_scene_update: mesh shape differs"; return NRT_ERR_INVALID;
+      }
+      for (int64_t f = 0; f < m.nfaces * 3; ++f) {
+        if (m.vertex_idx[f] < 0 || m.vertex_idx[f] >= m.nverts) { err = "vertex index out of range"; return NRT_ERR_INVALID; }
+        // only normalIdx[0] of a face is ever read (renderer.nim:87)
+        if (f % 3 == 0 && (m.normal_idx[f] < 0 || m.normal_idx[f] >= m.nnormals)) { err = "normal index out of range"; return NRT_ERR_INVALID; }
+      }
+      DMesh& dm = meshes[i];
+      dm.nverts = m.nverts; dm.nnormals = m.nnormals; dm.nfaces = m.nfaces;
+      dm.verts = up(m.vertices, m.nverts * 4, reuse ? const_cast<double*>(old[i].verts) : nullptr);
+      dm.normals = up(m.normals, m.nnormals * 4, reuse ? const_cast<double*>(old[i].normals) : nullptr);
+      dm.vidx = up(m.vertex_idx, m.nfaces * 3, reuse ? const_cast<int64_t*>(old[i].vidx) : nullptr);
+      dm.nidx = up(m.normal_idx, m.nfaces * 3, reuse ? const_cast<int64_t*>(old[i].nidx) : nullptr);
+      dm.recs = up<float>(nullptr, paddedFaces(m.nfaces) * 16, reuse ? old[i].recs : nullptr);
+      calcAABB(m.vertices, m.nverts, dm.bmin, dm.bmax);
+      double L = 0;
+      for (int k = 0; k < 3; ++k) {
+        dm.center[k] = 0.5 * (dm.bmin[k] + dm.bmax[k]);
+        L = std::max(L, 0.5 * (dm.bmax[k] - dm.bmin[k]));
+      }
+      if (!(L > 0) || !std::isfinite(L)) { L = 0; for (int k = 0; k < 3; ++k) dm.center[k] = 0; }  // => every ray takes the exact path
+      dm.L = L;
+    }
+    anyReflective = false;
+    for (int i = 0; i < desc->nobjects; ++i) {
+      const nrt_object& o = desc->objects[i];
+      DObject& dob = objs[i];
+      if (o.kind < 0 || o.kind > 3) { err = "bad geometry kind"; return NRT_ERR_INVALID; }
+      dob.kind = o.kind; dob.mesh = -1; dob.mesh_obj = -1;
+      std::memcpy(dob.o2w, o.object_to_world, sizeof(dob.o2w));
+      std::memcpy(dob.w2o, o.world_to_object, sizeof(dob.w2o));
+      dob.radius = o.radius;
+      std::memcpy(dob.bmin, o.vmin, sizeof(dob.bmin));
+      std::memcpy(dob.bmax, o.vmax, sizeof(dob.bmax));
+      std::memcpy(dob.albedo, o.albedo, sizeof(dob.albedo));
+      dob.reflection = o.reflection;
+      if (o.reflection > 0.0) anyReflective = true;
+      if (o.kind == NRT_GEOM_MESH) {
+        if (o.mesh < 0 || o.mesh >= desc->nmeshes) { err = "mesh index out of range"; return NRT_ERR_INVALID; }
+        dob.mesh = o.mesh;
+        dob.mesh_obj = int32_t(moIndex.size());
+        moIndex.push_back(i);
+        std::memcpy(dob.bmin, meshes[o.mesh].bmin, sizeof(dob.bmin));
+        std::memcpy(dob.bmax, meshes[o.mesh].bmax, sizeof(dob.bmax));
+      }
+    }
+    for (int i = 0; i < desc->nlights; ++i) {
+      const nrt_light& l = desc->lights[i];
+      if (l.kind != NRT_LIGHT_DISTANT && l.kind != NRT_LIGHT_POINT) { err = "bad light kind"; return NRT_ERR_INVALID; }
+      DLight& dl = lights[i];
+      dl.kind = l.kind;
+      std::memcpy(dl.color, l.color, sizeof(dl.color));
+      dl.intensity = l.intensity;
+      std::memcpy(dl.dir, l.dir, sizeof(dl.dir));
+      std::memcpy(dl.pos, l.pos, sizeof(dl.pos));
+    }
+    dObjs = up(objs.data(), int64_t(objs.size()), reuse ? dObjs : nullptr);
+    dLights = up(lights.data(), int64_t(lights.size()), reuse ? dLights : nullptr);
+    dMeshes = up(meshes.data(), int64_t(meshes.size()), reuse ? dMeshes : nullptr);
+    dMo = up(moIndex.data(), int64_t(moIndex.size()), reuse ? dMo : nullptr);
+    h.nobjects = desc->nobjects; h.nlights = desc->nlights; h.nmeshes = desc->nmeshes;
+    h.nmesh_objs = int32_t(moIndex.size());
+    h.objects = dObjs; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo;
+    std::memcpy(h.c2w, desc->camera_to_world, sizeof(h.c2w));
+    h.tan_half_fov = std::tan((desc->fov * (kPi / 180.0)) / 2);  // renderer.nim:38; Nim degToRad = d * (PI/180)
+    std::memcpy(h.bg, desc->bg_color, sizeof(h.bg));
+    d = up(&h, 1, reuse ? d : nullptr);
+    for (auto& m : meshes)
+      if (m.nfaces > 0) be->forEach(paddedFaces(m.nfaces), BuildRecs{m});
+    return NRT_OK;
+  }
+
+  void destroy() {
+    for (void* p : owned) be->dfree(p);
+    owned.clear();
+  }
+};
+
+// --------------------------------------------------------------- renderer ----
+template <class BE>
+struct Renderer {
+  BE* be = nullptr;
+  ChunkState cs{};
+  int64_t capS = 0, capNR = 0, capCand = 0;
+  int capMO = -1, capWaves = 0, capRows = 0;
+  std::vector<void*> owned;
+  int32_t* dRows = nullptr;
+  ProfileAcc prof;
+  int64_t launches_hint = 0;
+
+  void freeAll() {
+    for (void* p : owned) be->dfree(p);
+    owned.clear();
+    capS = capNR = capCand = 0; capMO = -1; capWaves = 0; capRows = 0; dRows = nullptr;
+  }
+  template <class T> T* al(int64_t n) { T* p = static_cast<T*>(be->dalloc(sizeof(T) * std::max<int64_t>(n, 1))); owned.push_back(p); return p; }
+
+  static int64_t envInt(const char* name, int64_t dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoll(v) : dflt;
+  }
+
+  void ensure(int64_t S, int nL, int nMO, int waves, int64_t cand, int nrows) {
+    const int64_t NR = S * std::max(1, nL);
+    if (S > capS || NR > capNR || nMO > capMO || waves > capWaves || cand > capCand || nrows > capRows) {
+      freeAll();
+      capS = S; capNR = NR; capMO = nMO; capWaves = waves; capCand = cand; capRows = nrows;
+      cs.rayO = al<double>(4 * S); cs.rayD = al<double>(4 * S); cs.hitW = al<double>(4 * S); cs.nrm = al<double>(4 * S);
+      cs.accum = al<double>(3 * S); cs.weight = al<double>(S);
+      cs.hitObj = al<int32_t>(S); cs.bounce = al<int32_t>(S); cs.active = al<uint8_t>(S);
+      const int64_t m = int64_t(std::max(nMO, 1)) * NR;
+      cs.tBest = al<uint64_t>(m); cs.triBest = al<uint32_t>(m);
+      cs.qref = al<uint32_t>(m); cs.qray = al<float>(m * 8); cs.xref = al<uint32_t>(m);
+      cs.candRef = al<uint32_t>(cand); cs.candTri = al<uint32_t>(cand); cs.candT = al<double>(cand);
+      cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * CNT_STRIDE);
+      cs.stats = al<unsigned long long>(ST_COUNT);
+      dRows = al<int32_t>(nrows);
+    }
+    cs.S = capS; cs.NR = capNR; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.rows = dRows;
+  }
+
+  // One mesh wave: gate + per mesh object filter / exact / verify.
+  void meshWave(const SceneData<BE>& sd, const FrameParams& fp, int kind, int64_t n, int wave, int force_exact) {
+    const int nMO = cs.nMO;
+    if (nMO == 0 || n == 0) return;
+    uint32_t* cnt = cs.counters + int64_t(wave) * nMO * CNT_STRIDE;
+    be->gate(Gate{sd.d, fp, cs, kind, n, force_exact}, n, nMO, cnt);
+    for (int mo = 0; mo < nMO; ++mo) {
+      uint32_t* c = cnt + mo * CNT_STRIDE;
+      const DMesh& m = sd.meshes[sd.objs[sd.moIndex[mo]].mesh];
+      if (m.nfaces == 0) continue;
+      be->filter(m, cs, mo, c);
+      be->forEachCounted(c + CNT_EXACT, cs.NR, ExactMesh{sd.d, fp, cs, kind, mo, c + CNT_EXACT});
+      be->forEachCounted(c + CNT_CAND, cs.candCap, Verify1<typename BE::Atom>{sd.d, fp, cs, kind, mo});
+      be->forEachCounted(c + CNT_CAND, cs.candCap, Verify2<typename BE::Atom>{cs, mo});
+    }
+  }
+
+  // Renders the rows `rows` (already filtered by step) of one worker.
+  int render(const SceneData<BE>& sd, const nrt_options& o, const std::vector<int32_t>& rows, int step, int max_step,
+             float* fb, int32_t* aovObj, int32_t* aovTri, double* aovT, unsigned long long* statsOut, std::string& err) {
+    FrameParams fp{};
+    fp.width = o.width; fp.height = o.height; fp.aa_kind = o.aa_kind;
+    fp.grid = o.aa_kind == NRT_AA_NONE ? 1 : o.grid_size;
+    fp.spp = fp.grid * fp.grid;
+    fp.step = step; fp.max_step = max_step;
+    fp.depth_mode = o.depth_mode; fp.max_ray_depth = o.max_ray_depth;
+    fp.bounce_cap = o.bounce_cap > 0 ? o.bounce_cap : 64;
+    fp.nx = (o.width + step - 1) / step;
+    fp.bias = o.bias; fp.seed = o.seed;
+    for (int k = 0; k < ST_COUNT; ++k) statsOut[k] = 0;
+    if (rows.empty() || fp.nx == 0) return NRT_OK;
+
+    const int nL = sd.h.nlights, nMO = sd.h.nmesh_objs;
+    const bool jitter = o.aa_kind >= NRT_AA_JITTERED;
+    // An INTENDED-mode frame can reflect at most max_ray_depth times.
+    int maxBounces = sd.anyReflective ? fp.bounce_cap : 0;
+    if (sd.anyReflective && o.depth_mode == NRT_DEPTH_INTENDED) maxBounces = std::min(maxBounces, std::max(0, o.max_ray_depth));
+    const int waves = 2 * (maxBounces + 1);
+    const int64_t npixTotal = int64_t(rows.size()) * fp.nx;
+    int64_t S = envInt("NRT_CHUNK_SAMPLES", int64_t(1) << 22);
+    // keep the per-(ray, mesh object) wave arrays within ~8 GB
+    const int64_t perSample = 240 + int64_t(56) * std::max(1, nL) * std::max(1, nMO);
+    S = std::min<int64_t>(S, (int64_t(8) << 30) / perSample);
+    S = std::max<int64_t>(S, fp.spp);
+    S = std::min<int64_t>(S, npixTotal * fp.spp);
+    int64_t chunkPix = std::max<int64_t>(1, S / fp.spp);
+    S = chunkPix * fp.spp;
+    int64_t cand = std::max<int64_t>(envInt("NRT_CAND_CAP", 0), 0);
+    if (cand == 0) cand = std::max<int64_t>(int64_t(1) << 20, 8 * S * std::max(1, nL));
+    const int force_exact = int(envInt("NRT_FORCE_EXACT", 0));
+
+    for (int attempt = 0;; ++attempt) {
+      ensure(S, nL, nMO, waves, cand, int(rows.size()));
+      cs.fb = fb; cs.aovObj = aovObj; cs.aovTri = aovTri; cs.aovT = aovT;
+      be->upload(dRows, rows.data(), sizeof(int32_t) * rows.size());
+      bool overflow = false;
+      unsigned long long total[ST_COUNT] = {0};
+      ProfileAcc pacc;
+      for (int64_t p0 = 0; p0 < npixTotal && !overflow; p0 += chunkPix) {
+        const int64_t npix = std::min(chunkPix, npixTotal - p0);
+        const int64_t nS = npix * fp.spp;
+        cs.p0 = p0; cs.npix = npix;
+        const int64_t ncnt = int64_t(waves) * std::max(nMO, 1) * CNT_STRIDE;
+        be->zero(cs.counters, sizeof(uint32_t) * ncnt);
+        be->zero(cs.stats, sizeof(unsigned long long) * ST_COUNT);
+        if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
+        else be->forEach(nS, GenSimple{sd.d, fp, cs});
+        int wave = 0;
+        unsigned long long contPrev = 0;
+        for (int bounce = 0;; ++bounce) {
+          meshWave(sd, fp, WAVE_PATH, nS, wave++, force_exact);
+          be->forEachStats(nS, Shade{sd.d, fp, cs}, cs.stats);
+          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, nS * nL, wave++, force_exact);
+          else wave++;
+          be->forEachStats(nS, Resolve{sd.d, fp, cs}, cs.stats);
+          if (bounce >= maxBounces) break;
+          unsigned long long cont = 0;
+          be->download(&cont, cs.stats + ST_CONT, sizeof(cont));
+          if (cont == contPrev) break;  // no sample continued
+          contPrev = cont;
+        }
+        be->forEach(npix, Finalize{fp, cs});
+        // chunk epilogue: counters (profile + overflow check) and stats
+        std::vector<uint32_t> hc(ncnt);
+        unsigned long long hs[ST_COUNT];
+        be->download(hc.data(), cs.counters, sizeof(uint32_t) * ncnt);
+        be->download(hs, cs.stats, sizeof(hs));
+        for (int w = 0; w < wave && nMO > 0; ++w)
+          for (int mo = 0; mo < nMO; ++mo) {
+            const uint32_t* c = hc.data() + (int64_t(w) * nMO + mo) * CNT_STRIDE;
+            const int64_t nf = sd.meshes[sd.objs[sd.moIndex[mo]].mesh].nfaces;
+            if (c[CNT_CAND] > uint64_t(cs.candCap)) overflow = true;
+            pacc.mesh_rays += int64_t(c[CNT_QUEUE]) + c[CNT_EXACT];
+            pacc.exact_rays += c[CNT_EXACT];
+            pacc.mesh_tests += int64_t(c[CNT_QUEUE]) * nf;
+            pacc.mesh_tests_ref += (int64_t(c[CNT_QUEUE]) + c[CNT_EXACT]) * nf;
+            pacc.candidates += c[CNT_CAND];
+          }
+        for (int k = 0; k < ST_COUNT; ++k) total[k] += hs[k];
+      }
+      if (!overflow) {
+        for (int k = 0; k < ST_COUNT; ++k) statsOut[k] = total[k];
+        prof = pacc;
+        return NRT_OK;
+      }
+      if (attempt >= 3) { err = "candidate buffer overflow"; return NRT_ERR_OVERFLOW; }
+      cand *= 4;  // re-render the frame with a larger candidate buffer (outputs are simply overwritten)
+    }
+  }
+};
+
+}  // namespace nrt

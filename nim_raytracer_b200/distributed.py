@@ -1,0 +1,99 @@
+"""One-process-per-GPU sharding of a frame (torchrun) — host-side plumbing only.
+
+The reference shards a frame by scanline with zero communication
+(src/raytracer.nim:67-70: one WorkMsg per line pulled by worker threads).  Here
+rank r of W renders the scanlines y with y mod W == r (nrt_set_partition; same
+rule as rowsFor() in csrc/nrt.cu) and the float32 framebuffer is assembled on
+rank 0 in one of two ways:
+
+  * "ipc"  — rank 0 owns the device framebuffer, exports it with CUDA IPC
+             (nrt_ipc_export) and every rank's final pixel-store kernel writes its
+             rows straight into it over NVLink (nrt_render_device on the opened
+             pointer): no gather pass, no NCCL.
+  * "gather" — every rank renders into a local buffer and the rows are gathered
+             with torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+
+torch.distributed is used for rendezvous, barriers, the max-over-ranks timing
+reduction and (only in "gather" mode) the row gather.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+
+def rows_of(rank: int, world: int, height: int, y0: int = 0, y1: Optional[int] = None, step: int = 1) -> List[int]:
+    """Scanlines of [y0, y1) with (y - y0) mod step == 0 owned by `rank` (csrc/nrt.cu: rowsFor)."""
+    y1 = height if y1 is None else y1
+    return [y for y in range(max(0, y0), min(y1, height)) if (y - y0) % step == 0 and y % world == rank]
+
+
+def merge_rows(dst: np.ndarray, src: np.ndarray, rank: int, world: int) -> None:
+    """Copies the rows owned by `rank` from a full-size (H, ...) buffer into dst."""
+    dst[rank::world] = src[rank::world]
+
+
+def gather_rows(local, rank: int, world: int, dist=None, group=None, dst: int = 0):
+    """Gathers the row-interleaved pieces of a (H, W, C) torch tensor on rank `dst`.
+
+    Every rank passes its full-size buffer of which only rows rank::world are
+    valid.  Works with any torch.distributed backend (nccl for CUDA tensors,
+    gloo for CPU tensors).  Returns the assembled frame on `dst`, None elsewhere."""
+    import torch
+
+    if world == 1:
+        return local
+    H = local.shape[0]
+    per = (H + world - 1) // world
+    mine = local[rank::world]
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: mine.shape[0]] = mine
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, gather_list=bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = torch.empty_like(local)
+    for r in range(world):
+        n = out[r::world].shape[0]
+        out[r::world] = bufs[r][:n]
+    return out
+
+
+class PeerFramebuffer:
+    """Device framebuffer owned by rank 0 and mapped into every rank with CUDA IPC."""
+
+    def __init__(self, nbytes: int, rank: int, world: int, dist=None):
+        from . import api
+
+        self.api, self.rank, self.world, self.nbytes = api, rank, world, nbytes
+        self.ptr = C.c_void_p()
+        self.owner = rank == 0
+        L = api.lib()
+        if self.owner:
+            api.check(L.nrt_device_alloc(nbytes, C.byref(self.ptr)), "nrt_device_alloc")
+            api.check(L.nrt_device_memset(self.ptr, 0, nbytes), "nrt_device_memset")
+        if world > 1:
+            h = api.nrt_ipc_handle()
+            if self.owner:
+                api.check(L.nrt_ipc_export(self.ptr, C.byref(h)), "nrt_ipc_export")
+            box = [bytes(h.bytes)]
+            dist.broadcast_object_list(box, src=0)
+            if not self.owner:
+                h = api.nrt_ipc_handle()
+                C.memmove(h.bytes, box[0], 64)
+                api.check(L.nrt_ipc_open(C.byref(h), C.byref(self.ptr)), "nrt_ipc_open")
+
+    def to_host(self, out: np.ndarray) -> None:
+        self.api.check(self.api.lib().nrt_copy_to_host(out.ctypes.data_as(C.c_void_p), self.ptr, out.nbytes),
+                       "nrt_copy_to_host")
+
+    def close(self) -> None:
+        L = self.api.lib()
+        if self.ptr:
+            if self.owner:
+                L.nrt_device_free(self.ptr)
+            else:
+                L.nrt_ipc_close(self.ptr)
+            self.ptr = C.c_void_p()

@@ -85,6 +85,26 @@ def render(scene, opts: api.Options, fb: api.Framebuf = None, aov: api.Aov = Non
     return fb, api.Stats.from_c(cs), aov
 
 
+def render_rows(scene, opts: api.Options, rows, fb: api.Framebuf = None, nthreads: int = 0, fast: bool = False):
+    """oracle_render_rows: the worker-pool loop over an explicit scanline list."""
+    desc = scene if isinstance(scene, api.SceneDesc) else api.SceneDesc(scene)
+    fb = fb or api.newFramebuf(opts.width, opts.height)
+    co, cs = opts.to_c(), api.nrt_stats()
+    r = np.ascontiguousarray(rows, dtype=np.int32)
+    L = lib(fast)
+    L.oracle_render_rows.argtypes = [C.POINTER(api.nrt_scene_desc), C.POINTER(api.nrt_options), C.c_void_p, C.c_int,
+                                     C.c_void_p, C.POINTER(api.nrt_stats), C.c_int]
+    rc = L.oracle_render_rows(desc.ref(), C.byref(co), r.ctypes.data_as(C.c_void_p), len(r),
+                              fb.data.ctypes.data_as(C.c_void_p), C.byref(cs), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_render_rows failed: {rc}")
+    return fb, api.Stats.from_c(cs)
+
+
+def hardware_threads() -> int:
+    return int(lib().oracle_hardware_threads())
+
+
 def solve_quadratic(a, b, c):
     t1, t2 = C.c_double(), C.c_double()
     lib().oracle_solve_quadratic(a, b, c, C.byref(t1), C.byref(t2))

@@ -543,6 +543,41 @@ int oracle_render(const nrt_scene_desc* desc, const nrt_options* opts, int y0, i
   return NRT_OK;
 }
 
+// Same worker-pool loop over an explicit list of scanlines (step = maxStep = 1):
+// used by bench.py to time a bounded, uniformly spread sample of a frame.
+int oracle_render_rows(const nrt_scene_desc* desc, const nrt_options* opts, const int* rows, int nrows, float* fb,
+                       nrt_stats* stats, int nthreads) {
+  if (!desc || !opts || !fb || (nrows > 0 && !rows)) return NRT_ERR_INVALID;
+  Scene sc = build_scene(desc);
+  Opts op{opts, opts->bounce_cap > 0 ? opts->bounce_cap : 64};
+  Target tg{fb, nullptr};
+  if (nthreads <= 0) nthreads = int(std::thread::hardware_concurrency());
+  if (nthreads <= 0) nthreads = 1;
+  std::atomic<int> next{0};
+  std::vector<Stats> per(nthreads);
+  auto worker = [&](int tid) {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= nrows) break;
+      if (rows[i] >= 0 && rows[i] < opts->height) renderLine(sc, op, tg, rows[i], 1, 1, per[tid]);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
+  worker(0);
+  for (auto& t : th) t.join();
+  if (stats) {
+    Stats s;
+    for (auto& p : per) { s.primary += p.primary; s.tests += p.tests; s.hits += p.hits; s.rays += p.rays; s.capped += p.capped; }
+    stats->num_primary_rays = s.primary;
+    stats->num_intersection_tests = s.tests;
+    stats->num_intersection_hits = s.hits;
+    stats->num_rays = s.rays;
+    stats->num_capped_samples = s.capped;
+  }
+  return NRT_OK;
+}
+
 int oracle_hardware_threads(void) { return int(std::thread::hardware_concurrency()); }
 
 // ---- unit entry points used by the golden-vector tests ---------------------

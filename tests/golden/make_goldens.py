@@ -1,0 +1,59 @@
+"""Generates the committed golden fixtures from the CPU oracle (oracle/ref_cpu.cpp).
+
+Run here (no GPU needed):  python tests/golden/make_goldens.py
+The oracle itself is pinned to the reference by tests/test_oracle_golden.py; these
+fixtures let the -m gpu tests check full-size frames (BASELINE configs) without
+re-running the brute-force CPU renderer on the GPU box.
+
+Each fixture stores sha256 digests of the whole float32 framebuffer / id AOVs, the
+Stats, and every 8th row verbatim (ids + float32 RGB) so a mismatch can be located.
+"""
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import oracle  # noqa: E402
+from nim_raytracer_b200 import api, scenes  # noqa: E402
+
+
+def digest(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def make(name, scene, opts, row_stride=8):
+    t = time.time()
+    aov = api.Aov(opts.width, opts.height)
+    fb, st, _ = oracle.render(scene, opts, aov=aov)
+    h, w = opts.height, opts.width
+    rows = np.arange(0, h, row_stride)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        width=w, height=h,
+        fb_sha256=digest(fb.data), obj_sha256=digest(aov.obj_id), tri_sha256=digest(aov.tri_id),
+        t_sha256=digest(aov.t_hit),
+        stats=np.array([st.numPrimaryRays, st.numIntersectionTests, st.numIntersectionHits, st.numRays,
+                        st.numCappedSamples], dtype=np.int64),
+        rows=rows,
+        fb_rows=fb.image()[rows], obj_rows=aov.obj_id.reshape(h, w)[rows].astype(np.int8),
+        tri_rows=aov.tri_id.reshape(h, w)[rows],
+    )
+    print(f"{name}: {time.time() - t:.1f}s  {st}")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["config1", "config2", "config3_small"]
+    if "config1" in which:   # BASELINE config 1: spheres-reflection 640x480, akNone
+        make("config1_spheres_640x480", scenes.spheres_reflection(), api.Options(640, 480))
+    if "config2" in which:   # BASELINE config 2: canonical bunny 1920x1080, akNone
+        make("config2_bunny_1920x1080", scenes.bunny(), api.Options(1920, 1080), row_stride=8)
+    if "config3_small" in which:  # config 3 scene, reduced size: 480x270, 4 spp grid, intended depth 8
+        make("config3_bunny_spheres_480x270_g2", scenes.bunny_spheres(),
+             api.Options(480, 270, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED,
+                         maxRayDepth=8), row_stride=4)

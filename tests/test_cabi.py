@@ -1,0 +1,89 @@
+"""The C-ABI library loads on a CPU-only machine, exports every entry point declared in
+include/nrt.h, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from nim_raytracer_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "nrt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nrt_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    import __graft_entry__ as g
+    g.build_cuda()
+    return api.lib()
+
+
+def test_exports_every_declared_symbol(built_lib):
+    names = declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(built_lib, n), f"{n} declared in include/nrt.h but not exported by libnrt.so"
+    assert built_lib.nrt_abi_version() == 1
+
+
+def test_built_for_sm_100a_only(built_lib):
+    out = subprocess.run(["cuobjdump", "-lelf", api.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_struct_layout_matches_header():
+    # sizes the C compiler gives the POD structs == the ctypes mirror (api.py)
+    code = r'''
+    #include "nrt.h"
+    #include <stdio.h>
+    int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(nrt_object), sizeof(nrt_mesh), sizeof(nrt_light),
+      sizeof(nrt_scene_desc), sizeof(nrt_options), sizeof(nrt_stats), sizeof(nrt_aov), sizeof(nrt_profile));return 0;}
+    '''
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "s.c"), "w").write(code)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "s.c"), "-o", os.path.join(td, "s")], check=True)
+        sizes = [int(x) for x in subprocess.run([os.path.join(td, "s")], capture_output=True, text=True).stdout.split()]
+    mirror = [api.nrt_object, api.nrt_mesh, api.nrt_light, api.nrt_scene_desc, api.nrt_options, api.nrt_stats,
+              api.nrt_aov, api.nrt_profile]
+    assert sizes == [C.sizeof(m) for m in mirror]
+
+
+def test_no_cpu_fallback_without_gpu(built_lib):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    assert built_lib.nrt_init(1, None) == -3                       # NRT_ERR_NO_DEVICE
+    assert b"no CPU fallback" in built_lib.nrt_last_error()
+    h = C.c_void_p()
+    from nim_raytracer_b200 import scenes
+    d = api.SceneDesc(scenes.boxtest())
+    assert built_lib.nrt_scene_create(d.ref(), C.byref(h)) == -4   # NRT_ERR_NOT_INIT: nothing renders on the CPU
+    with pytest.raises(api.NrtError):
+        api.initRenderer(1)
+
+
+def test_product_never_touches_the_oracle():
+    # nothing under nim_raytracer_b200/ or include/ may import, link or name oracle/ or the emulation
+    bad = []
+    for base in ("nim_raytracer_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".h", ".cu", ".cuh", ".hpp", ".cpp")):
+                    s = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"^\s*(import|from)\s+oracle\b", s, flags=re.M) or "liboracle" in s or "libnrt_emu" in s:
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+    syms = subprocess.run(["nm", "-D", "--defined-only", api.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle_" not in syms and "emu_" not in syms

@@ -1,0 +1,112 @@
+"""CPU-side (no GPU) checks of the device code: the SAME per-element bodies and the SAME
+host orchestration that libnrt.so compiles for sm_100a (csrc/nrt_core.h, nrt_pipeline.h,
+nrt_renderer.h) run through the test-only loop backend (tests/emu) and must reproduce the
+oracle bit for bit.  This validates the wavefront logic, the float64 arithmetic order and —
+most importantly — that the float32 mesh filter never drops a pair the float64 reference
+accepts.  The -m gpu tests repeat the same comparisons on the real CUDA path."""
+import numpy as np
+import pytest
+
+import emu_binding as emu
+from nim_raytracer_b200 import api, scenes
+
+
+def check(scene, opts, oracle_mod, **kw):
+    a1, a2 = api.Aov(opts.width, opts.height), api.Aov(opts.width, opts.height)
+    rfb, rst, _ = oracle_mod.render(scene, opts, aov=a1, **kw)
+    fb, st, _, prof = emu.render(scene, opts, aov=a2, **kw)
+    assert (a1.obj_id == a2.obj_id).all() and (a1.tri_id == a2.tri_id).all() and (a1.t_hit == a2.t_hit).all()
+    assert (fb.data == rfb.data).all()
+    assert st == rst
+    return prof
+
+
+def test_spheres_boxes_no_mesh(oracle_mod):
+    check(scenes.spheres_reflection(), api.Options(160, 120), oracle_mod)
+    check(scenes.boxtest(), api.Options(96, 64), oracle_mod)
+
+
+def test_one_triangle_mesh(oracle_mod):
+    prof = check(scenes.mesh_cube(), api.Options(64, 64), oracle_mod)
+    assert prof["mesh_rays"] > 0
+
+
+def test_bunny_full_mesh(oracle_mod):
+    prof = check(scenes.bunny(), api.Options(160, 90), oracle_mod)
+    assert prof["exact_rays"] == 0 and prof["mesh_tests"] == prof["mesh_rays"] * 69451
+    # the filter is selective: ~1 float64 re-evaluation per ray that enters the box
+    assert prof["candidates"] < 2 * prof["mesh_rays"]
+
+
+def test_bunny_native_winding(oracle_mod):
+    check(scenes.bunny(flip_winding=False, stride=4), api.Options(160, 90), oracle_mod)
+
+
+def test_reflection_grid_aa_both_depth_modes(oracle_mod):
+    sc = scenes.bunny_spheres(stride=8)
+    check(sc, api.Options(120, 68, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8), oracle_mod)
+    check(sc, api.Options(96, 54), oracle_mod)
+    check(sc, api.Options(64, 36, depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=0), oracle_mod)
+    check(sc, api.Options(64, 36, bounceCap=2), oracle_mod)        # safety cap reached: counted, same colours
+
+
+@pytest.mark.parametrize("kind", [api.akJittered, api.akMultiJittered, api.akCorrelatedMultiJittered])
+def test_jittered(oracle_mod, kind):
+    check(scenes.spheres_reflection(), api.Options(48, 36, antialias=api.Antialias(kind, 3), seed=5), oracle_mod)
+
+
+def test_progressive_and_line_ranges(oracle_mod):
+    sc, o = scenes.bunny(stride=32), api.Options(64, 36)
+    fb, rfb = api.newFramebuf(64, 36), api.newFramebuf(64, 36)
+    step = 8
+    while step >= 1:
+        emu.render(sc, o, fb=fb, step=step, maxStep=8)
+        oracle_mod.render(sc, o, fb=rfb, step=step, maxStep=8)
+        assert (fb.data == rfb.data).all()
+        step //= 2
+    fb2 = api.newFramebuf(64, 36)
+    for y in range(0, 36, 5):                                        # ragged line ranges
+        emu.render(sc, o, fb=fb2, y0=y, y1=min(y + 5, 36))
+    assert (fb2.data == fb.data).all()
+
+
+def test_chunking_overflow_retry_and_exact_path(oracle_mod, monkeypatch):
+    sc, o = scenes.bunny_spheres(stride=16), api.Options(100, 60, antialias=api.Antialias(api.akGrid, 2))
+    monkeypatch.setenv("NRT_CHUNK_SAMPLES", "1000")
+    check(sc, o, oracle_mod)
+    monkeypatch.setenv("NRT_CAND_CAP", "8")
+    check(sc, o, oracle_mod)
+    monkeypatch.delenv("NRT_CAND_CAP")
+    monkeypatch.setenv("NRT_FORCE_EXACT", "1")
+    prof = check(sc, o, oracle_mod)
+    assert prof["mesh_tests"] == 0 and prof["exact_rays"] == prof["mesh_rays"]
+
+
+def test_filter_is_conservative_on_random_soup(oracle_mod):
+    # random triangle soup (template test/test.nim:29-40), rays from many origins incl. reflections
+    rs = np.random.RandomState(3)
+    tri = (rs.uniform(-1, 1, (4000, 1, 3)) * 3.0) + rs.uniform(-0.4, 0.4, (4000, 3, 3))
+    from nim_raytracer_b200 import loaders, linalg as L
+    mesh = loaders.trianglesToMesh(tri)
+    sc = scenes.mesh_scene(mesh, reflection=0.5)
+    sc.objects[0].geometry.objectToWorld = L.translate(L.mat4(1.0), api.vec3(0.0, 3.5, -12.0))
+    sc.objects[0].geometry.worldToObject = L.inverse(sc.objects[0].geometry.objectToWorld)
+    check(sc, api.Options(120, 68), oracle_mod)
+
+
+def test_degenerate_meshes(oracle_mod):
+    from nim_raytracer_b200 import loaders, linalg as L
+    # zero-area and needle triangles, duplicated coplanar faces (first index must win)
+    tri = np.array([
+        [[0, 0, 0], [0, 0, 0], [0, 0, 0]],
+        [[-1, 0.5, 0], [1, 0.5, 0], [0, 2.0, 0]],
+        [[-1, 0.5, 0], [1, 0.5, 0], [0, 2.0, 0]],
+        [[-1, 0.5, -1e-9], [1, 0.5, -1e-9], [0, 2.0, -1e-9]],
+        [[0, 0.5, 0], [1e-7, 0.5, 0], [0, 3, 0]],
+    ], dtype=np.float64)
+    mesh = loaders.trianglesToMesh(tri)
+    sc = scenes.mesh_scene(mesh)
+    a1 = api.Aov(96, 54)
+    oracle_mod.render(sc, api.Options(96, 54), aov=a1)
+    assert set(np.unique(a1.tri_id)) >= {-1, 1}          # duplicate #2 never wins over #1
+    check(sc, api.Options(96, 54), oracle_mod)

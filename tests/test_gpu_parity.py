@@ -1,0 +1,242 @@
+"""-m gpu: parity of the CUDA path (through the C ABI, include/nrt.h) against the
+CPU oracle on the same inputs, plus full-size golden fixtures and size-independent
+properties.  Integer/index outputs must be bit-exact; the float32 framebuffer is
+compared bit-exactly too (all shading is float64 in the reference's operation
+order), with the north-star tolerance (|dRGB| <= 1/255 on >= 99.9 % of pixels)
+asserted as the contractual bound."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from nim_raytracer_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    api.initRenderer(1)
+    yield
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def gpu_render(scene, opts, **kw):
+    fb, aov = api.newFramebuf(opts.width, opts.height), api.Aov(opts.width, opts.height)
+    st = api.renderFrame(scene, opts, fb, aov=aov, **kw)
+    return fb, st, aov
+
+
+def assert_parity(scene, opts, oracle_mod, **kw):
+    fb, st, aov = gpu_render(scene, opts, **kw)
+    rfb, rst, raov = oracle_mod.render(scene, opts, aov=api.Aov(opts.width, opts.height), **kw)
+    assert (aov.obj_id == raov.obj_id).all(), f"{(aov.obj_id != raov.obj_id).sum()} object ids differ"
+    assert (aov.tri_id == raov.tri_id).all(), f"{(aov.tri_id != raov.tri_id).sum()} primitive ids differ"
+    assert (aov.t_hit == raov.t_hit).all()
+    d = np.abs(fb.image().astype(np.float64) - rfb.image().astype(np.float64)).max(axis=2)
+    assert (d <= 1.0 / 255.0).mean() >= 0.999           # north-star tolerance
+    assert (fb.data == rfb.data).all(), f"max |dRGB| = {d.max()}"  # and in fact bit-exact
+    assert st == rst
+    return fb, st, aov
+
+
+def test_config1_spheres_reflection(oracle_mod):
+    # BASELINE config 1: spheres-reflection.nim, 640x480, akNone, bias 1e-8, maxRayDepth 5
+    assert_parity(scenes.spheres_reflection(), api.Options(640, 480), oracle_mod)
+
+
+def test_boxtest_and_one_triangle_mesh(oracle_mod):
+    assert_parity(scenes.boxtest(), api.Options(300, 200), oracle_mod)       # data/scenes/boxtest.nim
+    assert_parity(scenes.mesh_cube(), api.Options(128, 128), oracle_mod)     # data/scenes/mesh-cube.nim
+
+
+def test_meshperftest_triangle():
+    # test/meshperftest.nim:22-44: 1-triangle mesh from the origin along -z => t = 5
+    from nim_raytracer_b200 import linalg as L
+    v = np.array([api.point(0, 1, -5), api.point(-2, -1, -5), api.point(2, -1, -5)])
+    mesh = api.initTriangleMesh(v, np.array([api.vec(0, 0, 1)]), [[0, 1, 2]], [[0, 0, 0]], L.mat4(1.0))
+    sc = api.Scene([api.Object("m", mesh, api.Material(api.vec3(1.0)))], [], 90.0, L.mat4(1.0), api.vec3(0.0))
+    fb, st, aov = gpu_render(sc, api.Options(2, 2))
+    assert aov.obj_id[3] == 0 and aov.tri_id[3] == 0 and aov.t_hit[3] == 5.0
+
+
+def test_bunny_full_mesh_small_frame(oracle_mod):
+    # all 69,451 triangles, 320x180 (the oracle finishes in seconds)
+    _, _, aov = assert_parity(scenes.bunny(), api.Options(320, 180), oracle_mod)
+    assert (aov.tri_id >= 0).sum() > 1000
+
+
+def test_bunny_native_winding(oracle_mod):
+    # secondary parity case of SURVEY §8d: the unflipped mesh (what the reference would literally do)
+    assert_parity(scenes.bunny(flip_winding=False, stride=2), api.Options(240, 135), oracle_mod)
+
+
+def test_config3_reflection_grid_aa(oracle_mod):
+    sc = scenes.bunny_spheres(stride=4)
+    o = api.Options(240, 135, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+    assert_parity(sc, o, oracle_mod)
+    o = api.Options(160, 90, antialias=api.Antialias(api.akGrid, 4))   # literal reference depth semantics (REFBUG)
+    assert_parity(sc, o, oracle_mod)
+
+
+@pytest.mark.parametrize("kind", [api.akJittered, api.akMultiJittered, api.akCorrelatedMultiJittered])
+def test_jittered_kinds(oracle_mod, kind):
+    o = api.Options(160, 120, antialias=api.Antialias(kind, 3), seed=20161018)
+    assert_parity(scenes.spheres_reflection(), o, oracle_mod)
+
+
+def test_progressive_refinement(oracle_mod):
+    # gui.nim:113-122,254-257: step halves from maxStep to 1; the result is the 1-step frame
+    sc, o = scenes.bunny(stride=16), api.Options(128, 72)
+    full, _, _ = gpu_render(sc, o)
+    fb = api.newFramebuf(128, 72)
+    rfb = api.newFramebuf(128, 72)
+    step = 8
+    while step >= 1:
+        api.renderFrame(sc, o, fb, step=step, maxStep=8)
+        oracle_mod.render(sc, o, fb=rfb, step=step, maxStep=8)
+        assert (fb.data == rfb.data).all(), f"step {step}"
+        step //= 2
+    assert (fb.data == full.data).all()
+
+
+def test_render_line_matches_frame(oracle_mod):
+    # renderer.nim:162: the per-scanline entry point used by the worker-pool caller
+    sc, o = scenes.boxtest(), api.Options(96, 64)
+    ds = api.DeviceScene(sc)
+    fb = api.newFramebuf(96, 64)
+    total = api.Stats()
+    for y in range(64):
+        total += api.renderLine(ds, o, fb, y)
+    rfb, rst, _ = oracle_mod.render(sc, o)
+    assert (fb.data == rfb.data).all() and total == rst
+    with pytest.raises(AssertionError):
+        api.renderLine(ds, o, fb, 0, step=3)             # renderer.nim:166 assert isPowerOfTwo(step)
+
+
+def test_chunked_and_exact_paths_agree(oracle_mod, monkeypatch):
+    sc, o = scenes.bunny_spheres(stride=8), api.Options(200, 112, antialias=api.Antialias(api.akGrid, 2))
+    ref, rst, raov = gpu_render(sc, o)
+    monkeypatch.setenv("NRT_CHUNK_SAMPLES", "4096")      # many chunks
+    fb, st, aov = gpu_render(sc, o)
+    assert (fb.data == ref.data).all() and st == rst and (aov.tri_id == raov.tri_id).all()
+    monkeypatch.setenv("NRT_FORCE_EXACT", "1")           # float64 brute force instead of filter + verify
+    fb, st, aov = gpu_render(sc, o)
+    assert (fb.data == ref.data).all() and st == rst and (aov.tri_id == raov.tri_id).all()
+    monkeypatch.delenv("NRT_FORCE_EXACT")
+    monkeypatch.setenv("NRT_CAND_CAP", "64")             # forces the overflow -> retry path
+    fb, st, aov = gpu_render(sc, o)
+    assert (fb.data == ref.data).all() and st == rst
+
+
+def _check_golden(name, scene, opts):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    fb, st, aov = gpu_render(scene, opts)
+    h, w = opts.height, opts.width
+    rows = g["rows"]
+    obj_rows = aov.obj_id.reshape(h, w)[rows]
+    tri_rows = aov.tri_id.reshape(h, w)[rows]
+    assert (obj_rows == g["obj_rows"]).all(), f"{(obj_rows != g['obj_rows']).sum()} object ids differ on the sampled rows"
+    assert (tri_rows == g["tri_rows"]).all(), f"{(tri_rows != g['tri_rows']).sum()} primitive ids differ on the sampled rows"
+    d = np.abs(fb.image()[rows].astype(np.float64) - g["fb_rows"].astype(np.float64)).max(axis=2)
+    assert (d <= 1.0 / 255.0).mean() >= 0.999
+    assert (fb.image()[rows] == g["fb_rows"]).all(), f"max |dRGB| on sampled rows = {d.max()}"
+    assert digest(aov.obj_id) == str(g["obj_sha256"]) and digest(aov.tri_id) == str(g["tri_sha256"])
+    assert digest(aov.t_hit) == str(g["t_sha256"])
+    assert digest(fb.data) == str(g["fb_sha256"])
+    assert [st.numPrimaryRays, st.numIntersectionTests, st.numIntersectionHits, st.numRays,
+            st.numCappedSamples] == g["stats"].tolist()
+    return fb, st, aov
+
+
+def test_golden_config1_full_size():
+    _check_golden("config1_spheres_640x480", scenes.spheres_reflection(), api.Options(640, 480))
+
+
+def test_golden_config2_full_size():
+    # BASELINE config 2 at its full size: 1920x1080, 69,451 triangles, primary + shadow rays
+    fb, st, aov = _check_golden("config2_bunny_1920x1080", scenes.bunny(), api.Options(1920, 1080))
+    # size-independent properties: Stats identities of renderer.nim:58,138
+    assert st.numPrimaryRays == 1920 * 1080 and st.numIntersectionTests == st.numRays * 2
+
+
+def test_golden_config3_reduced():
+    o = api.Options(480, 270, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+    _check_golden("config3_bunny_spheres_480x270_g2", scenes.bunny_spheres(), o)
+
+
+def test_full_size_filter_vs_exact(monkeypatch):
+    # BASELINE config 2 scene at 960x540: float32 filter + float64 verify == float64 brute force, all ids
+    sc, o = scenes.bunny(), api.Options(960, 540)
+    a_fb, a_st, a_aov = gpu_render(sc, o)
+    monkeypatch.setenv("NRT_FORCE_EXACT", "1")
+    b_fb, b_st, b_aov = gpu_render(sc, o)
+    assert (a_aov.tri_id == b_aov.tri_id).all() and (a_aov.obj_id == b_aov.obj_id).all()
+    assert (a_fb.data == b_fb.data).all() and a_st == b_st
+
+
+def test_error_behaviour():
+    import ctypes as C
+    L = api.lib()
+    ds = api.DeviceScene(scenes.boxtest())
+    o = api.Options(16, 16).to_c()
+    fb = api.newFramebuf(16, 16)
+    p = fb.data.ctypes.data_as(C.c_void_p)
+    assert L.nrt_render(ds.handle, C.byref(o), 0, 16, 3, 4, p, None, None) == -6      # NRT_ERR_UNSUPPORTED
+    assert L.nrt_render(ds.handle, C.byref(o), 0, 16, 4, 2, p, None, None) == -6      # maxStep < step
+    assert L.nrt_render(None, C.byref(o), 0, 16, 1, 1, p, None, None) == -1           # NRT_ERR_INVALID
+    assert L.nrt_render(ds.handle, C.byref(o), 0, 16, 1, 1, None, None, None) == -1
+    assert b"null" in L.nrt_last_error()
+    assert L.nrt_render(ds.handle, C.byref(o), 5, 5, 1, 1, p, None, None) == 0        # empty line range: no-op
+    bad = api.Options(16, 16, antialias=api.Antialias(api.akGrid, 0)).to_c()
+    assert L.nrt_render(ds.handle, C.byref(bad), 0, 16, 1, 1, p, None, None) == -1
+
+
+def test_empty_scene_and_no_lights(oracle_mod):
+    from nim_raytracer_b200 import linalg as L
+    sc = api.Scene([], [], 50.0, L.mat4(1.0), api.vec3(0.1, 0.2, 0.3))
+    fb, st, aov = assert_parity(sc, api.Options(32, 16), oracle_mod)
+    assert (aov.obj_id == -1).all() and np.allclose(fb.image()[0, 0], [0.1, 0.2, 0.3])
+    sc = scenes.bunny(stride=32)
+    sc.lights = []
+    assert_parity(sc, api.Options(64, 36), oracle_mod)
+
+
+def test_scene_update_and_srgb_output(oracle_mod):
+    sc = scenes.bunny(stride=16)
+    ds = api.DeviceScene(sc)
+    o = api.Options(160, 90)
+    fb = api.newFramebuf(160, 90)
+    api.renderFrame(ds, o, fb)
+    sc.objects[0].material.albedo = api.vec3(0.9, 0.2, 0.1)
+    sc.cameraToWorld = scenes._camera(0.5, 5.0, 2.0)
+    ds.update(sc)
+    api.renderFrame(ds, o, fb)
+    rfb, _, _ = oracle_mod.render(sc, o)
+    assert (fb.data == rfb.data).all()
+    # output stage (utils/framebuf.nim:74-78, utils/color.nim:17-22) within 1 LSB of a numpy restatement
+    img = api.framebufToSrgb8(fb)
+    c = np.clip(rfb.image(), 0.0, 1.0).astype(np.float32)
+    s = np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, np.float32(1 / 2.4)).astype(np.float64) - 0.055)
+    ref8 = np.round(s.astype(np.float32) * np.float32(255)).astype(np.int32)
+    assert np.abs(img.astype(np.int32) - ref8).max() <= 1
+    assert (img.astype(np.int32) == ref8).mean() > 0.999
+
+
+def test_two_gpus_in_process_match_one(oracle_mod):
+    import ctypes as C
+    api.shutdown()
+    api.initRenderer(0)                                   # all visible devices
+    try:
+        n = api.lib().nrt_device_count()
+        if n < 2:
+            pytest.skip("single GPU box")
+        assert_parity(scenes.bunny(stride=8), api.Options(256, 144), oracle_mod)
+    finally:
+        api.shutdown()
+        api.initRenderer(1)
