@@ -55,36 +55,56 @@ def workload(name: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (the clocks line of
+    /opt/skills/guides/B200_PROFILING.md) through NVML in a background thread — an
+    `nvidia-smi -lms` child process perturbs short frames and buffers its output."""
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index: int, period_s: float = 0.05):
+        self.gpu, self.period, self.rows, self.stop_flag, self.thread, self.err = gpu_index, period_s, [], False, None, None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((sm, mx, rs, pw))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                break
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"], "samples": 0}
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = sorted({name for r in self.rows for b, name in bits.items() if r[2] & b})
+        return {"sm_mhz": statistics.median(r[0] for r in self.rows), "sm_max_mhz": max(r[1] for r in self.rows),
+                "reasons": reasons, "samples": len(self.rows), "power_w_max": max(r[3] for r in self.rows)}
 
 
 def run_reference(args, rank, world):

@@ -458,35 +458,38 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
       }
       be.launches = 0;
       NRT_CUDA(cudaEventRecord(dc->ev0, be.stream));
-      rc[di] = pd.rn.render(pd.sd, *o, rows, step, max_step, target, aObj, aTri, aT, st[di].data(), errs[di]);
-      if (rc[di] == NRT_OK && !deviceOut) {
-        // device -> host, only the rows this worker produced (incl. their step x step fill rows)
-        const size_t rowB = size_t(o->width) * 3 * sizeof(float);
+      // Host <-> staging copies of exactly the rows this worker renders (and their step x step
+      // fill rows); equally spaced rows (scanline interleave) go out as one 2D copy.
+      auto copyRows = [&](bool toHost) {
+        const cudaMemcpyKind kind = toHost ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+        auto one = [&](void* host, void* devp, size_t elem, size_t firstRow, int stride, int fill, size_t cnt) {
+          const size_t rowB = size_t(o->width) * elem;
+          char* h = static_cast<char*>(host) + firstRow * rowB;
+          char* d = static_cast<char*>(devp) + firstRow * rowB;
+          void* dst = toHost ? static_cast<void*>(h) : static_cast<void*>(d);
+          const void* src = toHost ? static_cast<const void*>(d) : static_cast<const void*>(h);
+          if (cnt == 1) NRT_CUDA(cudaMemcpyAsync(dst, src, rowB * fill, kind, be.stream));
+          else NRT_CUDA(cudaMemcpy2DAsync(dst, rowB * stride, src, rowB * stride, rowB * fill, cnt, kind, be.stream));
+        };
         size_t i = 0;
         while (i < rows.size()) {
-          // group equally spaced rows into one 2D copy (scanline interleave => one call)
           size_t j = i + 1;
           const int fill = std::min(step, o->height - rows[i]);
-          int stride = (j < rows.size()) ? rows[j] - rows[i] : 0;
-          while (j < rows.size() && rows[j] - rows[j - 1] == stride && std::min(step, o->height - rows[j]) == fill) ++j;
+          const int stride = (j < rows.size()) ? rows[j] - rows[i] : 0;
+          while (stride > 0 && j < rows.size() && rows[j] - rows[j - 1] == stride && std::min(step, o->height - rows[j]) == fill) ++j;
           const size_t cnt = j - i;
-          const size_t off = size_t(rows[i]) * o->width * 3;
-          if (cnt == 1 || stride <= 0) {
-            NRT_CUDA(cudaMemcpyAsync(fb + off, target + off, rowB * fill, cudaMemcpyDeviceToHost, be.stream));
-            if (aObj) NRT_CUDA(cudaMemcpyAsync(aov->obj_id + off / 3, aObj + off / 3, sizeof(int32_t) * o->width * fill, cudaMemcpyDeviceToHost, be.stream));
-            if (aTri) NRT_CUDA(cudaMemcpyAsync(aov->tri_id + off / 3, aTri + off / 3, sizeof(int32_t) * o->width * fill, cudaMemcpyDeviceToHost, be.stream));
-            if (aT) NRT_CUDA(cudaMemcpyAsync(aov->t_hit + off / 3, aT + off / 3, sizeof(double) * o->width * fill, cudaMemcpyDeviceToHost, be.stream));
-            j = i + 1;
-          } else {
-            NRT_CUDA(cudaMemcpy2DAsync(fb + off, rowB * stride, target + off, rowB * stride, rowB * fill, cnt, cudaMemcpyDeviceToHost, be.stream));
-            const size_t po = off / 3, w = size_t(o->width);
-            if (aObj) NRT_CUDA(cudaMemcpy2DAsync(aov->obj_id + po, 4 * w * stride, aObj + po, 4 * w * stride, 4 * w * fill, cnt, cudaMemcpyDeviceToHost, be.stream));
-            if (aTri) NRT_CUDA(cudaMemcpy2DAsync(aov->tri_id + po, 4 * w * stride, aTri + po, 4 * w * stride, 4 * w * fill, cnt, cudaMemcpyDeviceToHost, be.stream));
-            if (aT) NRT_CUDA(cudaMemcpy2DAsync(aov->t_hit + po, 8 * w * stride, aT + po, 8 * w * stride, 8 * w * fill, cnt, cudaMemcpyDeviceToHost, be.stream));
-          }
+          one(fb, target, 3 * sizeof(float), size_t(rows[i]), stride, fill, cnt);
+          if (aObj) one(aov->obj_id, aObj, sizeof(int32_t), size_t(rows[i]), stride, fill, cnt);
+          if (aTri) one(aov->tri_id, aTri, sizeof(int32_t), size_t(rows[i]), stride, fill, cnt);
+          if (aT) one(aov->t_hit, aT, sizeof(double), size_t(rows[i]), stride, fill, cnt);
           i = j;
         }
-      }
+      };
+      // Progressive passes leave some pixels of the touched rows untouched (renderer.nim:175-178,
+      // and AOVs exist only at rendered pixels): round-trip the caller's current content.
+      if (!deviceOut && (step > 1 || step < max_step)) copyRows(false);
+      rc[di] = pd.rn.render(pd.sd, *o, rows, step, max_step, target, aObj, aTri, aT, st[di].data(), errs[di]);
+      if (rc[di] == NRT_OK && !deviceOut) copyRows(true);
       NRT_CUDA(cudaEventRecord(dc->ev1, be.stream));
       NRT_CUDA(cudaStreamSynchronize(be.stream));
     } catch (const std::exception& ex) {
