@@ -59,10 +59,11 @@ class ClockSampler:
     /opt/skills/guides/B200_PROFILING.md) through NVML in a background thread — an
     `nvidia-smi -lms` child process perturbs short frames and buffers its output."""
 
-    def __init__(self, gpu_index: int, period_s: float = 0.05):
+    def __init__(self, gpu_index: int, period_s: float = 0.01):
         self.gpu, self.period, self.rows, self.stop_flag, self.thread, self.err = gpu_index, period_s, [], False, None, None
 
-    def start(self):
+    def prepare(self):
+        """NVML init + the slow one-off queries, outside the timed region."""
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -75,21 +76,28 @@ class ClockSampler:
                 except Exception:
                     idx = self.gpu
             self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.thread = threading.Thread(target=self._run, daemon=True)
-            self.thread.start()
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception as e:  # noqa: BLE001
             self.err = str(e)
+            self.nv = None
+
+    def start(self):
+        if getattr(self, "nv", None) is None:
+            self.prepare()
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def _run(self):
         nv = self.nv
         while not self.stop_flag:
             try:
                 sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
                 rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
-                self.rows.append((sm, mx, rs, pw))
+                self.rows.append((sm, self.max_mhz, rs, pw))
             except Exception as e:  # noqa: BLE001
                 self.err = str(e)
                 break
@@ -245,21 +253,36 @@ def main():
         return None
 
     # ---- device-resident throughput ------------------------------------------------
+    # W untimed warm-up steps, then keep warming until the GPU has been busy for ~0.4 s: a B200
+    # that was idle runs its first tens of milliseconds below the sustained clock.
     for _ in range(args.warmup):
+        flush.fill_(1)          # also warms torch's fill kernel (its first launch costs ~20 ms)
         step_resident()
+    tw = time.perf_counter()
+    extra_warm = 0
+    while time.perf_counter() - tw < 0.4:
+        step_resident()
+        extra_warm += 1
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
+        sampler.prepare()
+        barrier_free = True  # noqa: F841 (NVML init done before the timed region starts)
         sampler.start()
     prof_acc = {"mesh_ms": 0.0, "flops": 0.0, "launches": 0, "klaunches": 0, "tests": 0, "tests_ref": 0, "cand": 0, "rays_mesh": 0, "frame_ms": 0.0}
     barrier()
     t0 = time.perf_counter()
     api.check(L.nrt_timer_begin(), "nrt_timer_begin")
     rays = 0
+    dbg = []
     for _ in range(args.steps):
+        ta = time.perf_counter()
         flush.fill_(1)                      # L2 flush between timed iterations
         torch.cuda.synchronize()
+        tb = time.perf_counter()
         step_resident()
+        tc = time.perf_counter()
+        dbg.append((tb - ta, tc - tb))
         rays += cs.num_rays
         p = ds.profile()
         prof_acc["mesh_ms"] += p.mesh_filter_ms; prof_acc["flops"] += p.fp32_flops
@@ -271,6 +294,9 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("NRT_BENCH_DEBUG") and rank == 0:
+        print("[bench debug] per-step (flush+sync ms, render ms):", [(round(a * 1e3, 2), round(b * 1e3, 2)) for a, b in dbg[:12]],
+              "frame_ms avg", prof_acc["frame_ms"] / args.steps, file=sys.stderr)
     OP = None
     if dist is not None:
         OP = dist.ReduceOp
@@ -336,7 +362,8 @@ def main():
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 filter + f64 exact", "data": "synthetic",
             "config": {"workload": desc, "parallelism": f"scanline-interleaved x{world}, {'CUDA-IPC peer stores' if peer is not None else 'NCCL row gather'} to rank 0",
-                       "l2": "256 MiB device fill between timed steps (inside the timed region)"},
+                       "l2": "256 MiB device fill between timed steps (inside the timed region)",
+                       "warmup_extra_steps": extra_warm},
             "frames_per_s": args.steps / (t_ms * 1e-3), "rays_per_frame": total_rays / args.steps,
             "device_ms_per_step": ms_dev.value / args.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(klaunches),

@@ -69,128 +69,210 @@ __global__ void __launch_bounds__(kBlock) k_for_each_counted(F f, const uint32_t
   for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) f(i);
 }
 
-// AABB gate + warp-ballot compaction of the rays that enter each mesh's box.
+// AABB gate + warp-ballot compaction of the rays that enter each mesh's box, one queue
+// per ray bundle (0 = arbitrary / shared-origin rays, 1 + l = shadow rays of DistantLight l).
 __global__ void __launch_bounds__(kBlock) k_gate(Gate g, int64_t n, int nMO, uint32_t* cnt) {
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
   const ChunkState& cs = g.cs;
+  const int nB = 1 + cs.nL, cst = cntStride(cs.nL);
   for (int mo = 0; mo < nMO; ++mo) {
     const GateOut o = g(i, mo);
+    uint32_t* c = cnt + mo * cst;
     const bool toFilter = o.pass && o.safe, toExact = o.pass && !o.safe;
-    const unsigned fm = __ballot_sync(0xffffffffu, toFilter);
-    if (fm) {
-      const int leader = __ffs(fm) - 1;
-      uint32_t base = 0;
-      if (int(lane) == leader) base = atomicAdd(&cnt[mo * CNT_STRIDE + CNT_QUEUE], uint32_t(__popc(fm)));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (toFilter) {
-        const int64_t slot = int64_t(mo) * cs.NR + base + __popc(fm & lt);
-        cs.qref[slot] = uint32_t(i);
-        float4* p0 = reinterpret_cast<float4*>(cs.qray + int64_t(mo) * cs.NR * 8);
-        float4* p1 = p0 + cs.NR;
-        const int64_t q = base + __popc(fm & lt);
-        p0[q] = make_float4(o.fr.dx, o.fr.dy, o.fr.dz, o.fr.rr);
-        p1[q] = make_float4(o.fr.mx, o.fr.my, o.fr.mz, 0.f);
+    if (__ballot_sync(0xffffffffu, toFilter)) {
+      for (int b = 0; b < nB; ++b) {
+        const bool mine = toFilter && o.bundle == b;
+        const unsigned fm = __ballot_sync(0xffffffffu, mine);
+        if (!fm) continue;
+        const int leader = __ffs(fm) - 1;
+        uint32_t base = 0;
+        if (int(lane) == leader) base = atomicAdd(&c[cntQueue(b)], uint32_t(__popc(fm)));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (mine) {
+          const int64_t q = base + __popc(fm & lt);
+          const int64_t at = queueBase(cs, mo, b) + q;
+          cs.qref[at] = uint32_t(i);
+          reinterpret_cast<float4*>(cs.qray0)[at] = make_float4(o.fr.ax, o.fr.ay, o.fr.az, o.fr.rr);
+          if (b == 0) reinterpret_cast<float4*>(cs.qray1)[int64_t(mo) * cs.NR + q] = make_float4(o.fr.mx, o.fr.my, o.fr.mz, 0.f);
+        }
       }
     }
     const unsigned xm = __ballot_sync(0xffffffffu, toExact);
     if (xm) {
       const int leader = __ffs(xm) - 1;
       uint32_t base = 0;
-      if (int(lane) == leader) base = atomicAdd(&cnt[mo * CNT_STRIDE + CNT_EXACT], uint32_t(__popc(xm)));
+      if (int(lane) == leader) base = atomicAdd(&c[CNT_EXACT], uint32_t(__popc(xm)));
       base = __shfl_sync(0xffffffffu, base, leader);
       if (toExact) cs.xref[int64_t(mo) * cs.NR + base + __popc(xm & lt)] = uint32_t(i);
     }
   }
 }
 
+// Filter-record build with culling: ballot-compacted, stored pair-interleaved (nrt_filter.h).
+template <class F, int MODE>
+__global__ void __launch_bounds__(kBlock) k_compact_recs(F f, int64_t n, float* recs, uint32_t* count) {
+  constexpr int NC = recFloats(MODE);
+  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  RecOut o; o.keep = false;
+  if (i < n) o = f(i);
+  const unsigned m = __ballot_sync(0xffffffffu, o.keep);
+  if (!m) return;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (int(lane) == leader) base = atomicAdd(count, uint32_t(__popc(m)));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (o.keep) {
+    const int64_t r = base + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+    for (int k = 0; k < NC; ++k) recs[recIndex(r, k, NC)] = o.c[k];
+  }
+}
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_pad_recs(float* recs, const uint32_t* count) {
+  constexpr int NC = recFloats(MODE);
+  const int64_t n = *count, np = paddedFaces(n);
+  float c[16];
+  neverHitRecord(MODE, c);
+  for (int64_t r = n + threadIdx.x; r < np; r += kBlock)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) recs[recIndex(r, k, NC)] = c[k];
+}
+
 // ------------------------------------------------------------- mesh filter ----
-// The hot kernel: every queued ray x every triangle of one mesh, float32,
-// 15 FFMA + 2 FADD + ~1.5 LOP3 per test (nrt_core.h: filterTest).  Persistent
-// CTAs pull (ray tile x triangle block) work items from an atomic counter; the
-// triangle records of a block are staged in shared memory in 16-byte vectors and
-// read back as warp-broadcast LDS.128; each thread keeps FT_R rays in registers.
+// The hot kernel: every queued ray of a bundle x every record of one record set, float32.
+// Two triangles are evaluated per FFMA2 (fma.rn.f32x2): records are pair-interleaved, ray
+// components are held duplicated in 64-bit register pairs.  Per (ray, triangle) test:
+//   GENERAL 15 FFMA + 2 FADD, ORIGIN 9 FFMA + 2 FADD, DIR 6 FFMA + 2 FADD  (+ ~1.5 LOP3 on the ALU pipe).
+// Persistent CTAs pull (ray tile x record block) work items from an atomic counter; the
+// records of a block are staged in shared memory in 16-byte vectors and read back as
+// warp-broadcast LDS.128; each thread keeps FT_R rays in registers.  Candidates (sign bits of
+// u', v', w' all clear) are appended to a global list for the float64 pass.
 static constexpr int FT_THREADS = 256;
-static constexpr int FT_R = 4;        // rays per thread
-static constexpr int FT_TC = 256;     // triangles per shared-memory chunk (16 KB)
-static constexpr int FT_TB = 1024;    // triangles per work item
+static constexpr int FT_R = 8;        // rays per thread
+static constexpr int FT_TC = 256;     // records per shared-memory chunk
+static constexpr int FT_TB = 256;     // records per work item (= one chunk: fine-grained items keep the tail short)
 static constexpr int FT_RAYS = FT_THREADS * FT_R;
+static_assert(kRecPad % FT_TC == 0, "record padding must cover whole shared-memory chunks");
 
 struct FilterArgs {
-  const float4* recs;     // padded to a multiple of FT_TC records
-  int ntri_padded;
-  const float4* q0;       // (d, rr)
-  const float4* q1;       // (m, pad)
-  const uint32_t* qref;
-  uint32_t* cnt;          // CNT_* of this (wave, mesh object)
+  const float4* recs;       // pair-interleaved records, padded to a multiple of kRecPad
+  const uint32_t* nrec;     // number of records (device)
+  const float4* q0;         // ray plane 0: (d | o', rr)
+  const float4* q1;         // ray plane 1: (m, 0)  (GENERAL)
+  const uint32_t* qref;     // wave-ray index per queued ray
+  const uint32_t* qcount;   // queued rays (device)
+  uint32_t* tilectr;        // work-item counter
+  uint32_t* candctr;        // candidate counter
   uint32_t* candRef;
   uint32_t* candTri;
   uint32_t candCap;
 };
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+
+template <int MODE>
 __global__ void __launch_bounds__(FT_THREADS, 2) k_mesh_filter(FilterArgs a) {
-  __shared__ __align__(16) float4 tile[FT_TC * 4];
+  constexpr int NC = recFloats(MODE);   // float2 per record pair
+  constexpr int NP4 = NC / 2;           // float4 per record pair
+  __shared__ __align__(16) float4 tile[(FT_TC / 2) * NP4];
   __shared__ uint32_t s_item;
-  const uint32_t nq = a.cnt[CNT_QUEUE];
+  const uint32_t nq = *a.qcount;
   if (nq == 0) return;
+  const uint32_t nrecPadded = uint32_t(paddedFaces(int64_t(*a.nrec)));
+  if (nrecPadded == 0) return;
   const uint32_t nRayTiles = (nq + FT_RAYS - 1) / FT_RAYS;
-  const uint32_t nTriBlocks = (uint32_t(a.ntri_padded) + FT_TB - 1) / FT_TB;
-  const uint32_t nItems = nRayTiles * nTriBlocks;
+  const uint32_t nBlocks = (nrecPadded + FT_TB - 1) / FT_TB;
+  const uint32_t nItems = nRayTiles * nBlocks;
   const int tid = threadIdx.x;
+  const float2 k16 = dup2(kFilterKd), one2 = dup2(1.0f);
   for (;;) {
-    if (tid == 0) s_item = atomicAdd(&a.cnt[CNT_TILE], 1u);
+    if (tid == 0) s_item = atomicAdd(a.tilectr, 1u);
     __syncthreads();
     const uint32_t item = s_item;
     __syncthreads();
     if (item >= nItems) break;
-    const uint32_t rt = item / nTriBlocks, tb = item - rt * nTriBlocks;
-    float dx[FT_R], dy[FT_R], dz[FT_R], mx[FT_R], my[FT_R], mz[FT_R];
+    const uint32_t rt = item / nBlocks, tb = item - rt * nBlocks;
+    float2 ax[FT_R], ay[FT_R], az[FT_R], mx[FT_R], my[FT_R], mz[FT_R];
     uint32_t ref[FT_R];
-    float rr = 0.f;
+    float rrs = 0.f;
 #pragma unroll
     for (int r = 0; r < FT_R; ++r) {
       const uint32_t idx = rt * FT_RAYS + r * FT_THREADS + tid;
       const uint32_t ic = idx < nq ? idx : nq - 1;  // tail: duplicate a real ray, never emit for it
-      const float4 p0 = __ldg(a.q0 + ic), p1 = __ldg(a.q1 + ic);
-      dx[r] = p0.x; dy[r] = p0.y; dz[r] = p0.z; mx[r] = p1.x; my[r] = p1.y; mz[r] = p1.z;
-      rr = fmaxf(rr, p0.w);
+      const float4 p0 = __ldg(a.q0 + ic);
+      ax[r] = dup2(p0.x); ay[r] = dup2(p0.y); az[r] = dup2(p0.z);
+      rrs = fmaxf(rrs, p0.w);
+      if (MODE == FM_GENERAL) {
+        const float4 p1 = __ldg(a.q1 + ic);
+        mx[r] = dup2(p1.x); my[r] = dup2(p1.y); mz[r] = dup2(p1.z);
+      }
       ref[r] = idx < nq ? __ldg(a.qref + ic) : kInvalidRef;
     }
-    const int tri0 = int(tb) * FT_TB;
-    const int tri1 = min(a.ntri_padded, tri0 + FT_TB);
-    for (int base = tri0; base < tri1; base += FT_TC) {
-      const float4* src = a.recs + int64_t(base) * 4;
-#pragma unroll
-      for (int k = 0; k < (FT_TC * 4) / FT_THREADS; ++k) tile[k * FT_THREADS + tid] = __ldg(src + k * FT_THREADS + tid);
+    const float2 rr = dup2(rrs);
+    const uint32_t rec0 = tb * FT_TB;
+    const uint32_t rec1 = min(nrecPadded, rec0 + FT_TB);
+    for (uint32_t base = rec0; base < rec1; base += FT_TC) {
+      const float4* src = a.recs + size_t(base / 2) * NP4;
+      for (int k = tid; k < (FT_TC / 2) * NP4; k += FT_THREADS) tile[k] = __ldg(src + k);
       __syncthreads();
 #pragma unroll 1
-      for (int t = 0; t < FT_TC; t += 2) {
-        const float4 a0 = tile[t * 4 + 0], a1 = tile[t * 4 + 1], a2 = tile[t * 4 + 2], a3 = tile[t * 4 + 3];
-        const float4 b0 = tile[t * 4 + 4], b1 = tile[t * 4 + 5], b2 = tile[t * 4 + 6], b3 = tile[t * 4 + 7];
-        const float qa[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
-        const float qb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
-        const float ebA = a0.w * rr, kdA = ebA * kFilterKd;
-        const float ebB = b0.w * rr, kdB = ebB * kFilterKd;
+      for (int t = 0; t < FT_TC / 2; ++t) {
+        float2 q[NC];
+#pragma unroll
+        for (int c = 0; c < NP4; ++c) {
+          const float4 v4 = tile[t * NP4 + c];
+          q[2 * c] = make_float2(v4.x, v4.y);
+          q[2 * c + 1] = make_float2(v4.z, v4.w);
+        }
+        const float2 eb = fmul2(q[recSlotS(MODE)], rr);
+        float2 kk, pu, qv;
+        if (MODE == FM_DIR) { kk = ffma2(eb, k16, one2); pu = fadd2(q[3], eb); qv = fadd2(q[7], eb); }
+        else { kk = fmul2(eb, k16); pu = eb; qv = eb; }
         uint32_t xa[FT_R], xb[FT_R];
         uint32_t acc = 0xFFFFFFFFu;
 #pragma unroll
         for (int r = 0; r < FT_R; ++r) {
-          xa[r] = filterTest(qa, dx[r], dy[r], dz[r], mx[r], my[r], mz[r], ebA, kdA);
-          xb[r] = filterTest(qb, dx[r], dy[r], dz[r], mx[r], my[r], mz[r], ebB, kdB);
+          float2 u, v, w;
+          if (MODE == FM_GENERAL) {
+            u = ffma2(q[7], mx[r], ffma2(q[8], my[r], ffma2(q[9], mz[r], ffma2(q[4], ax[r], ffma2(q[5], ay[r], ffma2(q[6], az[r], eb))))));
+            v = ffma2(q[13], mx[r], ffma2(q[14], my[r], ffma2(q[15], mz[r], ffma2(q[10], ax[r], ffma2(q[11], ay[r], ffma2(q[12], az[r], eb))))));
+            const float2 det = ffma2(q[0], ax[r], ffma2(q[1], ay[r], ffma2(q[2], az[r], kk)));
+            w = fadd2(fadd2(det, neg2(u)), neg2(v));
+          } else if (MODE == FM_ORIGIN) {
+            u = ffma2(q[4], ax[r], ffma2(q[5], ay[r], ffma2(q[6], az[r], eb)));
+            v = ffma2(q[8], ax[r], ffma2(q[9], ay[r], ffma2(q[10], az[r], eb)));
+            const float2 det = ffma2(q[0], ax[r], ffma2(q[1], ay[r], ffma2(q[2], az[r], kk)));
+            w = fadd2(fadd2(det, neg2(u)), neg2(v));
+          } else {
+            u = ffma2(q[0], ax[r], ffma2(q[1], ay[r], ffma2(q[2], az[r], pu)));
+            v = ffma2(q[4], ax[r], ffma2(q[5], ay[r], ffma2(q[6], az[r], qv)));
+            w = fadd2(fadd2(kk, neg2(u)), neg2(v));
+          }
+          xa[r] = __float_as_uint(u.x) | __float_as_uint(v.x) | __float_as_uint(w.x);
+          xb[r] = __float_as_uint(u.y) | __float_as_uint(v.y) | __float_as_uint(w.y);
           acc &= xa[r] & xb[r];
         }
         if (int(acc) >= 0) {  // some test has all three sign bits clear: rare
+          uint32_t ida, idb;
+          if (MODE == FM_GENERAL) { ida = base + 2 * t; idb = ida + 1; }
+          else { ida = __float_as_uint(q[recSlotId(MODE) < 0 ? 0 : recSlotId(MODE)].x); idb = __float_as_uint(q[recSlotId(MODE) < 0 ? 0 : recSlotId(MODE)].y); }
 #pragma unroll
           for (int r = 0; r < FT_R; ++r) {
             if (ref[r] == kInvalidRef) continue;
             if (int(xa[r]) >= 0) {
-              const uint32_t slot = atomicAdd(&a.cnt[CNT_CAND], 1u);
-              if (slot < a.candCap) { a.candRef[slot] = ref[r]; a.candTri[slot] = uint32_t(base + t); }
+              const uint32_t slot = atomicAdd(a.candctr, 1u);
+              if (slot < a.candCap) { a.candRef[slot] = ref[r]; a.candTri[slot] = ida; }
             }
             if (int(xb[r]) >= 0) {
-              const uint32_t slot = atomicAdd(&a.cnt[CNT_CAND], 1u);
-              if (slot < a.candCap) { a.candRef[slot] = ref[r]; a.candTri[slot] = uint32_t(base + t + 1); }
+              const uint32_t slot = atomicAdd(a.candctr, 1u);
+              if (slot < a.candCap) { a.candRef[slot] = ref[r]; a.candTri[slot] = idb; }
             }
           }
         }
@@ -237,6 +319,7 @@ struct CudaBackend {
   // profiling of the mesh filter
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> filterEvents;
   size_t filterUsed = 0;
+  std::vector<int> filterModes;
 
   struct Atom {
     static __device__ __forceinline__ void min64(uint64_t* p, uint64_t v) {
@@ -284,35 +367,53 @@ struct CudaBackend {
     k_gate<<<blocksFor(n), kBlock, 0, stream>>>(g, n, nMO, cnt);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
-  void filter(const DMesh& m, const ChunkState& cs, int mo, uint32_t* cnt) {
+  template <class F> void compactRecs(int64_t n, const F& f, float* recs, int mode, uint32_t* count) {
+    use();
+    if (mode == FM_ORIGIN) {
+      k_compact_recs<F, FM_ORIGIN><<<blocksFor(n), kBlock, 0, stream>>>(f, n, recs, count);
+      k_pad_recs<FM_ORIGIN><<<1, kBlock, 0, stream>>>(recs, count);
+    } else {
+      k_compact_recs<F, FM_DIR><<<blocksFor(n), kBlock, 0, stream>>>(f, n, recs, count);
+      k_pad_recs<FM_DIR><<<1, kBlock, 0, stream>>>(recs, count);
+    }
+    NRT_CUDA(cudaGetLastError()); launches += 2;
+  }
+  void filter(int mode, const float* recs, const uint32_t* nrec, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
     use();
     FilterArgs a;
-    a.recs = reinterpret_cast<const float4*>(m.recs);
-    a.ntri_padded = int(paddedFaces(m.nfaces));
-    static_assert(kRecPad % FT_TC == 0, "record padding must cover whole shared-memory chunks");
-    a.q0 = reinterpret_cast<const float4*>(cs.qray + int64_t(mo) * cs.NR * 8);
-    a.q1 = a.q0 + cs.NR;
-    a.qref = cs.qref + int64_t(mo) * cs.NR;
-    a.cnt = cnt;
+    a.recs = reinterpret_cast<const float4*>(recs);
+    a.nrec = nrec;
+    const int64_t base = queueBase(cs, mo, b);
+    a.q0 = reinterpret_cast<const float4*>(cs.qray0) + base;
+    a.q1 = reinterpret_cast<const float4*>(cs.qray1) + int64_t(mo) * cs.NR;
+    a.qref = cs.qref + base;
+    a.qcount = cnt + cntQueue(b);
+    a.tilectr = cnt + cntTile(b);
+    a.candctr = cnt + CNT_CAND;
     a.candRef = cs.candRef; a.candTri = cs.candTri;
     a.candCap = uint32_t(std::min<int64_t>(cs.candCap, 0xFFFFFFFFll));
     if (filterUsed == filterEvents.size()) {
       cudaEvent_t e0, e1;
       NRT_CUDA(cudaEventCreate(&e0)); NRT_CUDA(cudaEventCreate(&e1));
       filterEvents.push_back({e0, e1});
+      filterModes.push_back(0);
     }
-    auto& ev = filterEvents[filterUsed++];
+    auto& ev = filterEvents[filterUsed];
+    filterModes[filterUsed++] = mode;
     NRT_CUDA(cudaEventRecord(ev.first, stream));
-    k_mesh_filter<<<unsigned(sms * 2), FT_THREADS, 0, stream>>>(a);
+    const unsigned grid = unsigned(sms * 2);
+    if (mode == FM_GENERAL) k_mesh_filter<FM_GENERAL><<<grid, FT_THREADS, 0, stream>>>(a);
+    else if (mode == FM_ORIGIN) k_mesh_filter<FM_ORIGIN><<<grid, FT_THREADS, 0, stream>>>(a);
+    else k_mesh_filter<FM_DIR><<<grid, FT_THREADS, 0, stream>>>(a);
     NRT_CUDA(cudaGetLastError()); ++launches;
     NRT_CUDA(cudaEventRecord(ev.second, stream));
   }
   // call after a stream sync
-  double filterMs(int64_t* n) {
+  double filterMs(int64_t* n, double* byMode) {
     double ms = 0;
     for (size_t i = 0; i < filterUsed; ++i) {
       float t = 0;
-      if (cudaEventElapsedTime(&t, filterEvents[i].first, filterEvents[i].second) == cudaSuccess) ms += t;
+      if (cudaEventElapsedTime(&t, filterEvents[i].first, filterEvents[i].second) == cudaSuccess) { ms += t; byMode[filterModes[i]] += t; }
     }
     *n = int64_t(filterUsed);
     filterUsed = 0;
@@ -519,18 +620,21 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     cudaEventElapsedTime(&ms, dc->ev0, dc->ev1);
     p.total_ms = std::max(p.total_ms, double(ms));
     int64_t nl = 0;
-    const double fms = dc->be.filterMs(&nl);
+    double byMode[4] = {0, 0, 0, 0};
+    const double fms = dc->be.filterMs(&nl, byMode);
     p.mesh_filter_ms = std::max(p.mesh_filter_ms, fms);
     p.mesh_filter_launches += nl;
     const ProfileAcc& a = sc->dev[d].rn.prof;
     p.mesh_tests += a.mesh_tests; p.mesh_tests_ref += a.mesh_tests_ref; p.mesh_rays += a.mesh_rays;
     p.candidates += a.candidates;
     p.kernel_launches += dc->be.launches;
-    p.mesh_tests_by_mode[0] += a.mesh_tests;
-    p.mesh_ms_by_mode[0] = std::max(p.mesh_ms_by_mode[0], fms);
+    for (int m = 0; m < 3; ++m) {
+      p.mesh_tests_by_mode[m] += a.tests_by_mode[m];
+      p.mesh_ms_by_mode[m] = std::max(p.mesh_ms_by_mode[m], byMode[m]);
+      // executed float32 flops per filter test (FFMA = 2): nrt_filter.h filterFlops()
+      p.fp32_flops += double(a.tests_by_mode[m]) * filterFlops(m);
+    }
   }
-  // executed float32 flops per filter test: 15 FFMA (30) + 2 FADD (nrt_core.h: filterTest)
-  p.fp32_flops = double(p.mesh_tests) * 32.0;
   if (stats) {
     stats->num_primary_rays = int64_t(tot[ST_PRIMARY]);
     stats->num_intersection_tests = int64_t(tot[ST_TESTS]);

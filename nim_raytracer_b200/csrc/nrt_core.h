@@ -95,7 +95,7 @@ struct DMesh {
   double bmin[4], bmax[4];  // calcAABB (geom.nim:175-188)
   double center[3];         // filter frame origin (AABB centre)
   double L;                 // filter length scale (max AABB half extent)
-  float* recs;              // nfaces * 16 floats: general-mode filter records
+  float* recs;              // general-mode filter records (nrt_filter.h), pair-interleaved
 };
 
 struct DScene {
@@ -263,97 +263,6 @@ NRT_HD uint64_t dbits(double d) { union { double d; uint64_t u; } c; c.d = d; re
 NRT_HD double bitsd(uint64_t u) { union { double d; uint64_t u; } c; c.u = u; return c.d; }
 NRT_HD uint32_t fbits(float f) { union { float f; uint32_t u; } c; c.f = f; return c.u; }
 
-// ---------------------------------------------------- float32 mesh filter -----
-// Möller–Trumbore (geom.nim:283-336) rewritten with scalar triple products in a
-// frame centred at the mesh AABB centre C, ray = (d, m = (o - C) x d):
-//   det = e1.(d x e2)            = N . d            N  = -(e1 x e2)
-//   u'  = (o - v0).(d x e2)      = E2 . m + A . d   A  = (v0 - C) x e2
-//   v'  = d.((o - v0) x e1)      = E1n . m + B . d  E1n = -e1, B = e1 x (v0 - C)
-// (u' = u*det, v' = v*det.)  A float32 evaluation with margin Eb decides
-// "possibly hit"; every such (ray, triangle) pair is re-evaluated in float64 with
-// the reference's exact operation order (rayTriangleExact).  The `t` tests of the
-// reference (t >= 0, t < tMin) are not needed in the filter: the mesh is only
-// tested when the ray origin is outside its AABB and the box is in front
-// (geom.nim:340), so every line/triangle crossing has t >= 0 up to rounding —
-// and the float64 pass applies them exactly anyway.
-//
-// Record layout (16 floats = 4 x 16-byte vectors, loaded with LDS.128):
-//   q0 = (N.x,  N.y,  N.z,  S)      S = per-triangle magnitude scale (see below)
-//   q1 = (A.x,  A.y,  A.z,  E2.x)
-//   q2 = (E2.y, E2.z, B.x,  B.y)
-//   q3 = (B.z,  E1n.x,E1n.y,E1n.z)
-//
-// Error bound (unit roundoff u = 2^-24, round-to-nearest, no overflow): each of
-// u', v' is a 6-term fmaf chain of float32-rounded inputs, so
-//   |fl(u') - u'| <= 9u (|E2|.|m| + |A|.|d|) <= 9u S (|m|_inf + L |d|_inf)
-// with S = max(|e1|_1, |e2|_1, |A|_1 / L, |B|_1 / L) and L = max AABB half extent;
-// det (3 terms) errs by <= 5u |N|_1 |d|_inf <= 30u S L |d|_inf.  With
-//   Rr = 16u (|m|_inf + L |d|_inf)  (per ray),  Eb = S * Rr,  Kd = 16 Eb
-// the tests  u'+Eb >= 0,  v'+Eb >= 0,  (det+Kd) - (u'+Eb) - (v'+Eb) >= 0  hold for
-// every pair the float64 reference accepts (margin analysis in DESIGN.md §4).
-struct FilterRay {   // 8 floats = 2 x 16-byte vectors
-  float dx, dy, dz, rr;
-  float mx, my, mz, pad;
-};
-
-static constexpr double kFilterU = 5.9604644775390625e-8;  // 2^-24
-
-NRT_HD float roundUpF(double v) {  // float >= v (v >= 0)
-  float f = (float)v;
-  if ((double)f < v) f = f * 1.0000002f + 1e-45f;
-  return f;
-}
-
-// Builds the filter-side representation of an object-space ray (float64 in).
-NRT_HD FilterRay makeFilterRay(const DMesh& m, const Ray& r) {
-  const double ox = r.orig.x - m.center[0], oy = r.orig.y - m.center[1], oz = r.orig.z - m.center[2];
-  const double dx = r.dir.x, dy = r.dir.y, dz = r.dir.z;
-  const double mx = oy * dz - oz * dy, my = oz * dx - ox * dz, mz = ox * dy - oy * dx;
-  const double mi = fmax(fabs(mx), fmax(fabs(my), fabs(mz)));
-  const double di = fmax(fabs(dx), fmax(fabs(dy), fabs(dz)));
-  // + the float64 cancellation error of m itself (2^-52 |o||d|, negligible but counted)
-  const double oi = fmax(fabs(ox), fmax(fabs(oy), fabs(oz)));
-  const double rr = 16.0 * kFilterU * (mi + m.L * di) + 4.0 * 2.220446049250313e-16 * oi * di;
-  FilterRay f;
-  f.dx = (float)dx; f.dy = (float)dy; f.dz = (float)dz;
-  f.mx = (float)mx; f.my = (float)my; f.mz = (float)mz;
-  f.rr = roundUpF(rr);
-  f.pad = 0.f;
-  return f;
-}
-
-// Builds the 16-float record of triangle (v0, v1, v2) (object space, float64).
-NRT_HD void makeFilterRec(const DMesh& m, const double* p0, const double* p1, const double* p2, float* q) {
-  const double e1x = p1[0] - p0[0], e1y = p1[1] - p0[1], e1z = p1[2] - p0[2];
-  const double e2x = p2[0] - p0[0], e2y = p2[1] - p0[1], e2z = p2[2] - p0[2];
-  const double cx = p0[0] - m.center[0], cy = p0[1] - m.center[1], cz = p0[2] - m.center[2];
-  const double nx = -(e1y * e2z - e1z * e2y), ny = -(e1z * e2x - e1x * e2z), nz = -(e1x * e2y - e1y * e2x);
-  const double ax = cy * e2z - cz * e2y, ay = cz * e2x - cx * e2z, az = cx * e2y - cy * e2x;   // c x e2
-  const double bx = e1y * cz - e1z * cy, by = e1z * cx - e1x * cz, bz = e1x * cy - e1y * cx;   // e1 x c
-  const double s1 = fmax(fabs(e1x) + fabs(e1y) + fabs(e1z), fabs(e2x) + fabs(e2y) + fabs(e2z));
-  const double s2 = fmax(fabs(ax) + fabs(ay) + fabs(az), fabs(bx) + fabs(by) + fabs(bz));
-  const double S = fmax(s1, s2 / m.L);
-  q[0] = (float)nx; q[1] = (float)ny; q[2] = (float)nz; q[3] = roundUpF(S * 1.0000005);
-  q[4] = (float)ax; q[5] = (float)ay; q[6] = (float)az; q[7] = (float)e2x;
-  q[8] = (float)e2y; q[9] = (float)e2z; q[10] = (float)bx; q[11] = (float)by;
-  q[12] = (float)bz; q[13] = (float)(-e1x); q[14] = (float)(-e1y); q[15] = (float)(-e1z);
-}
-
-// One filter test.  Returns the OR of the three sign words: sign bit clear <=> candidate.
-NRT_HD uint32_t filterTest(const float* q, float dx, float dy, float dz, float mx, float my, float mz,
-                           float eb, float kd) {
-  const float u = fmaf(q[7], mx, fmaf(q[8], my, fmaf(q[9], mz, fmaf(q[4], dx, fmaf(q[5], dy, fmaf(q[6], dz, eb))))));
-  const float v = fmaf(q[13], mx, fmaf(q[14], my, fmaf(q[15], mz, fmaf(q[10], dx, fmaf(q[11], dy, fmaf(q[12], dz, eb))))));
-  const float det = fmaf(q[0], dx, fmaf(q[1], dy, fmaf(q[2], dz, kd)));
-  const float w = (det - u) - v;
-  return fbits(u) | fbits(v) | fbits(w);
-}
-
-static constexpr float kFilterKd = 16.0f;
-
-// Records are padded to a multiple of kRecPad faces with never-hit records
-// (all zero, S = -1 => Eb < 0 => u' + Eb < 0) so the hot loop has no tail.
-static constexpr int64_t kRecPad = 256;
-NRT_HD int64_t paddedFaces(int64_t nfaces) { return (nfaces + kRecPad - 1) / kRecPad * kRecPad; }
-
 }  // namespace nrt
+
+#include "nrt_filter.h"

@@ -26,8 +26,13 @@ namespace nrt {
 
 enum WaveKind { WAVE_PATH = 0, WAVE_SHADOW = 1 };
 
-// Counter slots per (wave, mesh object)
-enum { CNT_QUEUE = 0, CNT_EXACT = 1, CNT_CAND = 2, CNT_TILE = 3, CNT_STRIDE = 4 };
+// Counter block per (wave, mesh object): [EXACT, CAND, then (QUEUE_b, TILE_b) per ray bundle b].
+// Bundle 0 holds arbitrary rays (GENERAL mode; ORIGIN mode for the primary wave, whose rays share
+// the camera origin); bundle 1 + l holds the shadow rays of DistantLight l (DIR mode).
+enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_BUNDLE0 = 2 };
+NRT_HD int cntStride(int nL) { return CNT_BUNDLE0 + 2 * (1 + nL); }
+NRT_HD int cntQueue(int b) { return CNT_BUNDLE0 + 2 * b; }
+NRT_HD int cntTile(int b) { return CNT_BUNDLE0 + 2 * b + 1; }
 // Stats slots
 enum { ST_PRIMARY = 0, ST_TESTS = 1, ST_HITS = 2, ST_RAYS = 3, ST_CAPPED = 4, ST_CONT = 5, ST_COUNT = 8 };
 
@@ -62,14 +67,17 @@ struct ChunkState {
   // per wave ray and mesh object
   uint64_t* tBest;   // nMO*NR   (bit pattern of a float64)
   uint32_t* triBest; // nMO*NR
-  uint32_t* qref;    // nMO*NR   filter queue: wave-ray index
-  float* qray;       // nMO*NR*8 filter queue: plane 0 (d, rr) then plane 1 (m, pad), float4 each
-  uint32_t* xref;    // nMO*NR   exact (float64 brute force) queue
+  // filter queues: per mesh object QCAP = NR + nL*S entries; bundle 0 at [0, NR), bundle 1+l at NR + l*S
+  int64_t QCAP;
+  uint32_t* qref;    // nMO*QCAP   wave-ray index
+  float* qray0;      // nMO*QCAP*4 plane 0 (float4): (d | o', rr)
+  float* qray1;      // nMO*NR*4   plane 1 (float4), bundle 0 only: (m, 0)
+  uint32_t* xref;    // nMO*NR     exact (float64 brute force) queue
   // candidates of the current (wave, mesh object)
   uint32_t* candRef; // candCap
   uint32_t* candTri; // candCap
   double* candT;     // candCap
-  uint32_t* counters;  // maxWaves*nMO*CNT_STRIDE
+  uint32_t* counters;  // maxWaves*nMO*cntStride(nL)
   unsigned long long* stats;  // ST_COUNT
   // pixel list of this worker
   const int32_t* rows; // device array of row indices
@@ -81,6 +89,10 @@ struct ChunkState {
   int32_t* aovTri;
   double* aovT;
 };
+
+NRT_HD int64_t queueBase(const ChunkState& cs, int mo, int b) {
+  return int64_t(mo) * cs.QCAP + (b == 0 ? 0 : cs.NR + int64_t(b - 1) * cs.S);
+}
 
 NRT_HD V4 ld4(const double* a, int64_t n, int64_t i) { return v4(a[i], a[n + i], a[2 * n + i], a[3 * n + i]); }
 NRT_HD void st4(double* a, int64_t n, int64_t i, V4 v) { a[i] = v.x; a[n + i] = v.y; a[2 * n + i] = v.z; a[3 * n + i] = v.w; }
@@ -221,21 +233,13 @@ NRT_HD Ray objectRay(const DObject& ob, V4 o, V4 d) {  // renderer.nim:54-55
   return initRay(mulm(ob.w2o, o), mulm(ob.w2o, d));
 }
 
-NRT_HD bool filterSafe(const DMesh& m, const Ray& r) {
-  const double big = 1e15, tiny = 1e-15;
-  const double ox = r.orig.x - m.center[0], oy = r.orig.y - m.center[1], oz = r.orig.z - m.center[2];
-  const double di = fmax(fabs(r.dir.x), fmax(fabs(r.dir.y), fabs(r.dir.z)));
-  const double oi = fmax(fabs(ox), fmax(fabs(oy), fabs(oz)));
-  // NaN compares false => unsafe
-  return (di < big) && (di > tiny) && (oi < big) && (m.L < big) && (m.L > tiny);
-}
-
 // ---- gate: TriangleMesh.intersect's AABB test (geom.nim:340) per (ray, mesh object)
-struct GateOut { bool pass, safe; FilterRay fr; };
+struct GateOut { bool pass, safe; int bundle; FilterRay fr; };
 struct Gate {
   const DScene* sc; FrameParams fp; ChunkState cs; int kind; int64_t n; int force_exact;
+  int path_mode;   // FM_ORIGIN for the primary wave (all rays share the camera origin), else FM_GENERAL
   NRT_HD GateOut operator()(int64_t i, int mo) const {
-    GateOut g; g.pass = false; g.safe = false;
+    GateOut g; g.pass = false; g.safe = false; g.bundle = 0;
     V4 o, d;
     const bool valid = (i < n) && waveRay(*sc, fp, cs, kind, i, o, d);
     if (!valid) return g;
@@ -246,9 +250,15 @@ struct Gate {
     g.pass = !(tmin < 0);
     cs.tBest[int64_t(mo) * cs.NR + i] = dbits(g.pass ? NRT_INF : NRT_NEG_INF);
     cs.triBest[int64_t(mo) * cs.NR + i] = kNoTri;
-    if (g.pass) {
-      g.safe = !force_exact && filterSafe(m, r);
-      if (g.safe) g.fr = makeFilterRay(m, r);
+    if (g.pass && !force_exact) {
+      int mode = path_mode;
+      if (kind == WAVE_SHADOW) {
+        const int l = int(i % cs.nL);
+        if (sc->lights[l].kind == LIGHT_DISTANT) { mode = FM_DIR; g.bundle = 1 + l; }
+        else mode = FM_GENERAL;
+      }
+      g.safe = makeFilterRay(mode, m, r, g.fr);
+      if (!g.safe) g.bundle = 0;
     }
     return g;
   }
@@ -459,16 +469,52 @@ struct Finalize {
   }
 };
 
-// ---- per-mesh precompute: float32 filter records (one element per face)
-struct BuildRecs {
+// ---- filter records (nrt_filter.h), one element per face (or per padding slot) ----
+struct RecOut { bool keep; float c[16]; };
+
+// GENERAL: depends on the mesh only; stored at its own index (face id == record index).
+struct BuildRecsGeneral {
   DMesh m;
   NRT_HD void operator()(int64_t f) const {
-    if (f >= m.nfaces) {  // padding record
-      for (int k = 0; k < 16; ++k) m.recs[16 * f + k] = (k == 3) ? -1.0f : 0.0f;
-      return;
-    }
-    makeFilterRec(m, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2],
-                  m.recs + 16 * f);
+    float c[16];
+    if (f < m.nfaces) makeRecGeneral(m, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2], c);
+    else neverHitRecord(FM_GENERAL, c);
+    for (int k = 0; k < 16; ++k) m.recs[recIndex(f, k, 16)] = c[k];
+  }
+};
+
+// ORIGIN: per (mesh object, camera): culled against the shared origin; compacted by the backend.
+struct BuildRecsOrigin {
+  const DScene* sc; int mo;
+  NRT_HD RecOut operator()(int64_t f) const {
+    RecOut o;
+    const DObject& ob = sc->objects[sc->mesh_obj_index[mo]];
+    const DMesh& m = sc->meshes[ob.mesh];
+    const V4 ow = mulm(sc->c2w, v4(0.0, 0.0, 0.0, 1.0));   // castPrimaryRay's origin (renderer.nim:42)
+    const V4 oo = mulm(ob.w2o, ow);                        // trace()'s object-space origin (renderer.nim:54)
+    const double O[3] = {oo.x, oo.y, oo.z};
+    o.keep = makeRecOrigin(O, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2],
+                           uint32_t(f), o.c);
+    // a record float32 cannot hold (|v0 - O| or S overflow) becomes an always-candidate record
+    if (o.keep && !(o.c[3] < 1e30f)) { for (int k = 0; k < 12; ++k) o.c[k] = 0.f; o.c[3] = 1e30f; o.c[7] = bitsToFloat(uint32_t(f)); }
+    return o;
+  }
+};
+
+// DIR: per (mesh object, DistantLight l): culled by det < 1e-6 for the shared direction.
+struct BuildRecsDir {
+  const DScene* sc; int mo; int l;
+  NRT_HD RecOut operator()(int64_t f) const {
+    RecOut o;
+    const DObject& ob = sc->objects[sc->mesh_obj_index[mo]];
+    const DMesh& m = sc->meshes[ob.mesh];
+    const DLight& li = sc->lights[l];
+    const V4 dw = scale(v4(li.dir[0], li.dir[1], li.dir[2], li.dir[3]), -1.0);   // renderer.nim:96
+    const V4 dobj = mulm(ob.w2o, dw);                                             // renderer.nim:55
+    const double D[3] = {dobj.x, dobj.y, dobj.z};
+    o.keep = makeRecDir(m, D, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2],
+                        uint32_t(f), o.c);
+    return o;
   }
 };
 

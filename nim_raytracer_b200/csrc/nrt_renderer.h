@@ -19,6 +19,7 @@ namespace nrt {
 
 struct ProfileAcc {
   int64_t mesh_tests = 0, mesh_tests_ref = 0, mesh_rays = 0, candidates = 0, exact_rays = 0;
+  int64_t tests_by_mode[3] = {0, 0, 0};
 };
 
 inline bool isPow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -35,8 +36,19 @@ struct SceneData {
   std::vector<int32_t> moIndex;
   DObject* dObjs = nullptr; DLight* dLights = nullptr; DMesh* dMeshes = nullptr; int32_t* dMo = nullptr;
   std::vector<void*> owned;
-  bool anyReflective = false;
+  bool anyReflective = false, anyPointLight = false;
   int64_t bytes_uploaded = 0;
+  // Filter record sets per mesh object (device): ORIGIN (camera) and DIR per DistantLight.
+  struct MoRecs { float* origin = nullptr; std::vector<float*> dir; };
+  std::vector<MoRecs> moRecs;
+  uint32_t* dRecCount = nullptr;          // [mo * recStride() + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
+  std::vector<uint32_t> hRecCount;
+  int recStride() const { return 2 + h.nlights; }
+  const float* recsOf(int mo, int mode, int l) const {
+    return mode == FM_GENERAL ? meshes[objs[moIndex[mo]].mesh].recs : (mode == FM_ORIGIN ? moRecs[mo].origin : moRecs[mo].dir[l]);
+  }
+  const uint32_t* recCountOf(int mo, int mode, int l) const { return dRecCount + mo * recStride() + (mode == FM_GENERAL ? 0 : (mode == FM_ORIGIN ? 1 : 2 + l)); }
+  uint32_t hostRecCount(int mo, int mode, int l) const { return hRecCount[mo * recStride() + (mode == FM_GENERAL ? 0 : (mode == FM_ORIGIN ? 1 : 2 + l))]; }
 
   // geom.nim:175-188
   static void calcAABB(const double* v, int64_t n, double* bmin, double* bmax) {
@@ -71,6 +83,7 @@ struct SceneData {
     }
     bytes_uploaded = 0;
     std::vector<DMesh> old = meshes;
+    std::vector<MoRecs> oldRecs = moRecs;
     objs.assign(desc->nobjects, DObject{});
     lights.assign(desc->nlights, DLight{});
     meshes.assign(desc->nmeshes, DMesh{});
@@ -103,7 +116,7 @@ struct SceneData {
       if (!(L > 0) || !std::isfinite(L)) { L = 0; for (int k = 0; k < 3; ++k) dm.center[k] = 0; }  // => every ray takes the exact path
       dm.L = L;
     }
-    anyReflective = false;
+    anyReflective = false; anyPointLight = false;
     for (int i = 0; i < desc->nobjects; ++i) {
       const nrt_object& o = desc->objects[i];
       DObject& dob = objs[i];
@@ -131,6 +144,7 @@ struct SceneData {
       if (l.kind != NRT_LIGHT_DISTANT && l.kind != NRT_LIGHT_POINT) { err = "bad light kind"; return NRT_ERR_INVALID; }
       DLight& dl = lights[i];
       dl.kind = l.kind;
+      if (l.kind == NRT_LIGHT_POINT) anyPointLight = true;
       std::memcpy(dl.color, l.color, sizeof(dl.color));
       dl.intensity = l.intensity;
       std::memcpy(dl.dir, l.dir, sizeof(dl.dir));
@@ -147,8 +161,29 @@ struct SceneData {
     h.tan_half_fov = std::tan((desc->fov * (kPi / 180.0)) / 2);  // renderer.nim:38; Nim degToRad = d * (PI/180)
     std::memcpy(h.bg, desc->bg_color, sizeof(h.bg));
     d = up(&h, 1, reuse ? d : nullptr);
+    // ---- filter records: GENERAL per mesh; ORIGIN / DIR per mesh object (device-side build) ----
     for (auto& m : meshes)
-      if (m.nfaces > 0) be->forEach(paddedFaces(m.nfaces), BuildRecs{m});
+      if (m.nfaces > 0) be->forEach(paddedFaces(m.nfaces), BuildRecsGeneral{m});
+    const int nMO = int(moIndex.size()), rs = recStride();
+    moRecs.assign(nMO, MoRecs{});
+    hRecCount.assign(size_t(std::max(1, nMO * rs)), 0u);
+    for (int mo = 0; mo < nMO; ++mo) hRecCount[mo * rs] = uint32_t(meshes[objs[moIndex[mo]].mesh].nfaces);
+    dRecCount = up(hRecCount.data(), int64_t(hRecCount.size()), reuse ? dRecCount : nullptr);
+    for (int mo = 0; mo < nMO; ++mo) {
+      const int64_t nf = meshes[objs[moIndex[mo]].mesh].nfaces;
+      MoRecs& r = moRecs[mo];
+      r.origin = up<float>(nullptr, paddedFaces(nf) * recFloats(FM_ORIGIN), reuse ? oldRecs[mo].origin : nullptr);
+      r.dir.assign(size_t(desc->nlights), nullptr);
+      if (nf > 0) {
+        be->compactRecs(nf, BuildRecsOrigin{d, mo}, r.origin, FM_ORIGIN, dRecCount + mo * rs + 1);
+      }
+      for (int l = 0; l < desc->nlights; ++l) {
+        if (lights[l].kind != NRT_LIGHT_DISTANT) continue;
+        r.dir[l] = up<float>(nullptr, paddedFaces(nf) * recFloats(FM_DIR), reuse ? oldRecs[mo].dir[l] : nullptr);
+        if (nf > 0) be->compactRecs(nf, BuildRecsDir{d, mo, l}, r.dir[l], FM_DIR, dRecCount + mo * rs + 2 + l);
+      }
+    }
+    be->download(hRecCount.data(), dRecCount, sizeof(uint32_t) * hRecCount.size());
     return NRT_OK;
   }
 
@@ -164,7 +199,7 @@ struct Renderer {
   BE* be = nullptr;
   ChunkState cs{};
   int64_t capS = 0, capNR = 0, capCand = 0;
-  int capMO = -1, capWaves = 0, capRows = 0;
+  int capMO = -1, capNL = -1, capWaves = 0, capRows = 0;
   std::vector<void*> owned;
   int32_t* dRows = nullptr;
   ProfileAcc prof;
@@ -173,7 +208,7 @@ struct Renderer {
   void freeAll() {
     for (void* p : owned) be->dfree(p);
     owned.clear();
-    capS = capNR = capCand = 0; capMO = -1; capWaves = 0; capRows = 0; dRows = nullptr;
+    capS = capNR = capCand = 0; capMO = -1; capNL = -1; capWaves = 0; capRows = 0; dRows = nullptr;
   }
   template <class T> T* al(int64_t n) { T* p = static_cast<T*>(be->dalloc(sizeof(T) * std::max<int64_t>(n, 1))); owned.push_back(p); return p; }
 
@@ -184,34 +219,45 @@ struct Renderer {
 
   void ensure(int64_t S, int nL, int nMO, int waves, int64_t cand, int nrows) {
     const int64_t NR = S * std::max(1, nL);
-    if (S > capS || NR > capNR || nMO > capMO || waves > capWaves || cand > capCand || nrows > capRows) {
+    if (S > capS || NR > capNR || nMO > capMO || nL != capNL || waves > capWaves || cand > capCand || nrows > capRows) {
       freeAll();
-      capS = S; capNR = NR; capMO = nMO; capWaves = waves; capCand = cand; capRows = nrows;
+      capS = S; capNR = NR; capMO = nMO; capNL = nL; capWaves = waves; capCand = cand; capRows = nrows;
       cs.rayO = al<double>(4 * S); cs.rayD = al<double>(4 * S); cs.hitW = al<double>(4 * S); cs.nrm = al<double>(4 * S);
       cs.accum = al<double>(3 * S); cs.weight = al<double>(S);
       cs.hitObj = al<int32_t>(S); cs.bounce = al<int32_t>(S); cs.active = al<uint8_t>(S);
       const int64_t m = int64_t(std::max(nMO, 1)) * NR;
+      const int64_t qcap = NR + int64_t(nL) * S, mq = int64_t(std::max(nMO, 1)) * qcap;
       cs.tBest = al<uint64_t>(m); cs.triBest = al<uint32_t>(m);
-      cs.qref = al<uint32_t>(m); cs.qray = al<float>(m * 8); cs.xref = al<uint32_t>(m);
+      cs.qref = al<uint32_t>(mq); cs.qray0 = al<float>(mq * 4); cs.qray1 = al<float>(m * 4); cs.xref = al<uint32_t>(m);
       cs.candRef = al<uint32_t>(cand); cs.candTri = al<uint32_t>(cand); cs.candT = al<double>(cand);
-      cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * CNT_STRIDE);
+      cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * cntStride(nL));
       cs.stats = al<unsigned long long>(ST_COUNT);
       dRows = al<int32_t>(nrows);
     }
-    cs.S = capS; cs.NR = capNR; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.rows = dRows;
+    cs.S = capS; cs.NR = capNR; cs.QCAP = capNR + int64_t(nL) * capS; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.rows = dRows;
   }
 
-  // One mesh wave: gate + per mesh object filter / exact / verify.
-  void meshWave(const SceneData<BE>& sd, const FrameParams& fp, int kind, int64_t n, int wave, int force_exact) {
-    const int nMO = cs.nMO;
+  // One mesh wave: gate + per mesh object { filter per ray bundle, exact, verify }.
+  void meshWave(const SceneData<BE>& sd, const FrameParams& fp, int kind, int64_t n, int wave, bool primary, int force_exact) {
+    const int nMO = cs.nMO, nL = cs.nL, cst = cntStride(nL);
     if (nMO == 0 || n == 0) return;
-    uint32_t* cnt = cs.counters + int64_t(wave) * nMO * CNT_STRIDE;
-    be->gate(Gate{sd.d, fp, cs, kind, n, force_exact}, n, nMO, cnt);
+    uint32_t* cnt = cs.counters + int64_t(wave) * nMO * cst;
+    const int pathMode = primary ? FM_ORIGIN : FM_GENERAL;
+    be->gate(Gate{sd.d, fp, cs, kind, n, force_exact, pathMode}, n, nMO, cnt);
     for (int mo = 0; mo < nMO; ++mo) {
-      uint32_t* c = cnt + mo * CNT_STRIDE;
+      uint32_t* c = cnt + mo * cst;
       const DMesh& m = sd.meshes[sd.objs[sd.moIndex[mo]].mesh];
       if (m.nfaces == 0) continue;
-      be->filter(m, cs, mo, c);
+      if (!force_exact) {
+        if (kind == WAVE_PATH) {
+          be->filter(pathMode, sd.recsOf(mo, pathMode, 0), sd.recCountOf(mo, pathMode, 0), cs, mo, 0, c);
+        } else {
+          if (sd.anyPointLight) be->filter(FM_GENERAL, sd.recsOf(mo, FM_GENERAL, 0), sd.recCountOf(mo, FM_GENERAL, 0), cs, mo, 0, c);
+          for (int l = 0; l < nL; ++l)
+            if (sd.lights[l].kind == NRT_LIGHT_DISTANT)
+              be->filter(FM_DIR, sd.recsOf(mo, FM_DIR, l), sd.recCountOf(mo, FM_DIR, l), cs, mo, 1 + l, c);
+        }
+      }
       be->forEachCounted(c + CNT_EXACT, cs.NR, ExactMesh{sd.d, fp, cs, kind, mo, c + CNT_EXACT});
       be->forEachCounted(c + CNT_CAND, cs.candCap, Verify1<typename BE::Atom>{sd.d, fp, cs, kind, mo});
       be->forEachCounted(c + CNT_CAND, cs.candCap, Verify2<typename BE::Atom>{cs, mo});
@@ -263,7 +309,7 @@ struct Renderer {
         const int64_t npix = std::min(chunkPix, npixTotal - p0);
         const int64_t nS = npix * fp.spp;
         cs.p0 = p0; cs.npix = npix;
-        const int64_t ncnt = int64_t(waves) * std::max(nMO, 1) * CNT_STRIDE;
+        const int64_t ncnt = int64_t(waves) * std::max(nMO, 1) * cntStride(nL);
         be->zero(cs.counters, sizeof(uint32_t) * ncnt);
         be->zero(cs.stats, sizeof(unsigned long long) * ST_COUNT);
         if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
@@ -271,10 +317,10 @@ struct Renderer {
         int wave = 0;
         unsigned long long contPrev = 0;
         for (int bounce = 0;; ++bounce) {
-          meshWave(sd, fp, WAVE_PATH, nS, wave++, force_exact);
+          meshWave(sd, fp, WAVE_PATH, nS, wave, bounce == 0, force_exact); ++wave;
           be->forEachStats(nS, Shade{sd.d, fp, cs}, cs.stats);
-          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, nS * nL, wave++, force_exact);
-          else wave++;
+          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, nS * nL, wave, false, force_exact);
+          ++wave;
           be->forEachStats(nS, Resolve{sd.d, fp, cs}, cs.stats);
           if (bounce >= maxBounces) break;
           unsigned long long cont = 0;
@@ -288,15 +334,25 @@ struct Renderer {
         unsigned long long hs[ST_COUNT];
         be->download(hc.data(), cs.counters, sizeof(uint32_t) * ncnt);
         be->download(hs, cs.stats, sizeof(hs));
+        const int cst = cntStride(nL);
         for (int w = 0; w < wave && nMO > 0; ++w)
           for (int mo = 0; mo < nMO; ++mo) {
-            const uint32_t* c = hc.data() + (int64_t(w) * nMO + mo) * CNT_STRIDE;
+            const uint32_t* c = hc.data() + (int64_t(w) * nMO + mo) * cst;
             const int64_t nf = sd.meshes[sd.objs[sd.moIndex[mo]].mesh].nfaces;
             if (c[CNT_CAND] > uint64_t(cs.candCap)) overflow = true;
-            pacc.mesh_rays += int64_t(c[CNT_QUEUE]) + c[CNT_EXACT];
+            int64_t queued = 0;
+            for (int b = 0; b <= nL; ++b) {
+              const int64_t q = c[cntQueue(b)];
+              if (!q) continue;
+              // wave parity: even = path wave (primary for w == 0), odd = shadow wave
+              const int mode = b > 0 ? FM_DIR : ((w & 1) ? FM_GENERAL : (w == 0 ? FM_ORIGIN : FM_GENERAL));
+              const int64_t t = q * int64_t(sd.hostRecCount(mo, mode, b > 0 ? b - 1 : 0));
+              pacc.mesh_tests += t; pacc.tests_by_mode[mode] += t;
+              queued += q;
+            }
+            pacc.mesh_rays += queued + c[CNT_EXACT];
             pacc.exact_rays += c[CNT_EXACT];
-            pacc.mesh_tests += int64_t(c[CNT_QUEUE]) * nf;
-            pacc.mesh_tests_ref += (int64_t(c[CNT_QUEUE]) + c[CNT_EXACT]) * nf;
+            pacc.mesh_tests_ref += (queued + int64_t(c[CNT_EXACT])) * nf;
             pacc.candidates += c[CNT_CAND];
           }
         for (int k = 0; k < ST_COUNT; ++k) total[k] += hs[k];

@@ -38,56 +38,78 @@ struct LoopBackend {
     for (int64_t i = 0; i < n; ++i) f(i);
     ++launches;
   }
+  template <class F> void compactRecs(int64_t n, const F& f, float* recs, int mode, uint32_t* count) {
+    const int nc = recFloats(mode);
+    for (int64_t i = 0; i < n; ++i) {
+      const RecOut o = f(i);
+      if (!o.keep) continue;
+      const int64_t r = (*count)++;
+      for (int k = 0; k < nc; ++k) recs[recIndex(r, k, nc)] = o.c[k];
+    }
+    float c[16];
+    neverHitRecord(mode, c);
+    for (int64_t r = *count; r < paddedFaces(*count); ++r)
+      for (int k = 0; k < nc; ++k) recs[recIndex(r, k, nc)] = c[k];
+    ++launches;
+  }
   void gate(const Gate& g, int64_t n, int nMO, uint32_t* cnt) {
     const ChunkState& cs = g.cs;
+    const int cst = cntStride(cs.nL);
     for (int64_t i = 0; i < n; ++i)
       for (int mo = 0; mo < nMO; ++mo) {
         const GateOut o = g(i, mo);
+        uint32_t* c = cnt + mo * cst;
         if (o.pass && o.safe) {
-          const int64_t q = cnt[mo * CNT_STRIDE + CNT_QUEUE]++;
-          cs.qref[int64_t(mo) * cs.NR + q] = uint32_t(i);
-          float* p0 = cs.qray + int64_t(mo) * cs.NR * 8;
-          float* p1 = p0 + cs.NR * 4;
-          p0[4 * q + 0] = o.fr.dx; p0[4 * q + 1] = o.fr.dy; p0[4 * q + 2] = o.fr.dz; p0[4 * q + 3] = o.fr.rr;
-          p1[4 * q + 0] = o.fr.mx; p1[4 * q + 1] = o.fr.my; p1[4 * q + 2] = o.fr.mz; p1[4 * q + 3] = 0.f;
+          const int64_t q = c[cntQueue(o.bundle)]++;
+          const int64_t at = queueBase(cs, mo, o.bundle) + q;
+          cs.qref[at] = uint32_t(i);
+          float* p0 = cs.qray0 + 4 * at;
+          p0[0] = o.fr.ax; p0[1] = o.fr.ay; p0[2] = o.fr.az; p0[3] = o.fr.rr;
+          if (o.bundle == 0) {
+            float* p1 = cs.qray1 + 4 * (int64_t(mo) * cs.NR + q);
+            p1[0] = o.fr.mx; p1[1] = o.fr.my; p1[2] = o.fr.mz; p1[3] = 0.f;
+          }
         } else if (o.pass) {
-          const int64_t q = cnt[mo * CNT_STRIDE + CNT_EXACT]++;
+          const int64_t q = c[CNT_EXACT]++;
           cs.xref[int64_t(mo) * cs.NR + q] = uint32_t(i);
         }
       }
     ++launches;
   }
-  // Same thread/ray assignment as k_mesh_filter (256 threads x 4 rays, rr = max over a thread's rays).
-  void filter(const DMesh& m, const ChunkState& cs, int mo, uint32_t* cnt) {
-    const int T = 256, R = 4;
-    const uint32_t nq = cnt[CNT_QUEUE];
-    const float* p0 = cs.qray + int64_t(mo) * cs.NR * 8;
-    const float* p1 = p0 + cs.NR * 4;
-    const uint32_t* qref = cs.qref + int64_t(mo) * cs.NR;
-    const int64_t np = paddedFaces(m.nfaces);
+  // Same thread/ray assignment as k_mesh_filter (FT_THREADS threads x FT_R rays, Rr = max over a thread's rays).
+  void filter(int mode, const float* recs, const uint32_t* count, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
+    const int T = 256, R = 8;
+    const uint32_t nq = cnt[cntQueue(b)];
+    const int64_t base = queueBase(cs, mo, b);
+    const float* p0 = cs.qray0 + 4 * base;
+    const float* p1 = cs.qray1 + 4 * (int64_t(mo) * cs.NR);
+    const uint32_t* qref = cs.qref + base;
+    const int64_t np = paddedFaces(*count);
+    const int nc = recFloats(mode), idSlot = recSlotId(mode);
     for (uint32_t rt = 0; rt * T * R < nq; ++rt)
       for (int tid = 0; tid < T; ++tid) {
         uint32_t ic[R], ref[R]; float rr = 0.f;
+        bool any = false;
         for (int r = 0; r < R; ++r) {
           const uint32_t idx = rt * T * R + r * T + tid;
           ic[r] = idx < nq ? idx : nq - 1;
           ref[r] = idx < nq ? qref[ic[r]] : kInvalidRef;
           rr = std::max(rr, p0[4 * ic[r] + 3]);
+          any |= ref[r] != kInvalidRef;
         }
-        bool any = false;
-        for (int r = 0; r < R; ++r) any |= ref[r] != kInvalidRef;
         if (!any) continue;
         for (int64_t t = 0; t < np; ++t) {
-          const float* q = m.recs + 16 * t;
-          const float eb = q[3] * rr, kd = eb * kFilterKd;
+          float q[16];
+          for (int k = 0; k < nc; ++k) q[k] = recs[recIndex(t, k, nc)];
           for (int r = 0; r < R; ++r) {
             if (ref[r] == kInvalidRef) continue;
-            const uint32_t x = filterTest(q, p0[4 * ic[r]], p0[4 * ic[r] + 1], p0[4 * ic[r] + 2], p1[4 * ic[r]],
-                                          p1[4 * ic[r] + 1], p1[4 * ic[r] + 2], eb, kd);
+            const uint32_t x = filterTest(mode, q, p0 + 4 * ic[r], p1 + 4 * ic[r], rr);
             ++filter_tests;
             if (int32_t(x) >= 0) {
               const uint32_t slot = cnt[CNT_CAND]++;
-              if (slot < cs.candCap) { cs.candRef[slot] = ref[r]; cs.candTri[slot] = uint32_t(t); }
+              uint32_t tri = uint32_t(t);
+              if (idSlot >= 0) std::memcpy(&tri, &q[idSlot], 4);
+              if (slot < cs.candCap) { cs.candRef[slot] = ref[r]; cs.candTri[slot] = tri; }
             }
           }
         }

@@ -33,7 +33,9 @@ def test_one_triangle_mesh(oracle_mod):
 
 def test_bunny_full_mesh(oracle_mod):
     prof = check(scenes.bunny(), api.Options(160, 90), oracle_mod)
-    assert prof["exact_rays"] == 0 and prof["mesh_tests"] == prof["mesh_rays"] * 69451
+    # shared-origin (primary) and shared-direction (distant-light shadow) bundles drop the faces
+    # that can never be hit (plane faces away / det < 1e-6): roughly half of the 69,451
+    assert prof["exact_rays"] == 0 and 0.4 * 69451 < prof["mesh_tests"] / prof["mesh_rays"] < 0.6 * 69451
     # the filter is selective: ~1 float64 re-evaluation per ray that enters the box
     assert prof["candidates"] < 2 * prof["mesh_rays"]
 
