@@ -167,10 +167,11 @@ typedef struct nrt_profile {
   double total_ms;              /* CUDA-event time of the whole frame on device 0  */
   double mesh_filter_ms;        /* summed CUDA-event time of the mesh kernel       */
   int64_t mesh_filter_launches;
-  int64_t mesh_tests;           /* (ray, triangle) pairs evaluated by that kernel  */
+  int64_t mesh_tests;           /* (ray, triangle) pairs evaluated by the prefilter */
   int64_t mesh_tests_ref;       /* pairs the reference would evaluate (geom.nim:346) */
   int64_t mesh_rays;            /* rays that passed the AABB gate (geom.nim:340)   */
   int64_t candidates;           /* pairs re-evaluated in float64                   */
+  int64_t pre_candidates;       /* prefilter survivors re-tested by the float32 sign test */
   int64_t kernel_launches;      /* all kernels launched for the frame              */
   double fp32_flops;            /* FP32 flops executed by the mesh kernel (2/FFMA) */
   int64_t mesh_tests_by_mode[4];/* general / shared-origin / shared-dir / reserved */

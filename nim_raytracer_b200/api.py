@@ -111,6 +111,7 @@ class nrt_profile(C.Structure):
         ("total_ms", C.c_double), ("mesh_filter_ms", C.c_double),
         ("mesh_filter_launches", C.c_int64), ("mesh_tests", C.c_int64),
         ("mesh_tests_ref", C.c_int64), ("mesh_rays", C.c_int64), ("candidates", C.c_int64),
+        ("pre_candidates", C.c_int64),
         ("kernel_launches", C.c_int64), ("fp32_flops", C.c_double),
         ("mesh_tests_by_mode", C.c_int64 * 4), ("mesh_ms_by_mode", C.c_double * 4),
     ]

@@ -95,7 +95,11 @@ __global__ void __launch_bounds__(kBlock) k_gate(Gate g, int64_t n, int nMO, uin
           const int64_t at = queueBase(cs, mo, b) + q;
           cs.qref[at] = uint32_t(i);
           reinterpret_cast<float4*>(cs.qray0)[at] = make_float4(o.fr.ax, o.fr.ay, o.fr.az, o.fr.rr);
-          if (b == 0) reinterpret_cast<float4*>(cs.qray1)[int64_t(mo) * cs.NR + q] = make_float4(o.fr.mx, o.fr.my, o.fr.mz, 0.f);
+          reinterpret_cast<float4*>(cs.qhot0)[at] = make_float4(o.hr.a0, o.hr.a1, o.hr.a2, o.hr.a3);
+          if (b == 0) {
+            reinterpret_cast<float4*>(cs.qray1)[int64_t(mo) * cs.NR + q] = make_float4(o.fr.mx, o.fr.my, o.fr.mz, 0.f);
+            reinterpret_cast<float4*>(cs.qhot1)[int64_t(mo) * cs.NR + q] = make_float4(o.hr.b0, o.hr.b1, o.hr.b2, 0.f);
+          }
         }
       }
     }
@@ -112,8 +116,8 @@ __global__ void __launch_bounds__(kBlock) k_gate(Gate g, int64_t n, int nMO, uin
 
 // Filter-record build with culling: ballot-compacted, stored pair-interleaved (nrt_filter.h).
 template <class F, int MODE>
-__global__ void __launch_bounds__(kBlock) k_compact_recs(F f, int64_t n, float* recs, uint32_t* count) {
-  constexpr int NC = recFloats(MODE);
+__global__ void __launch_bounds__(kBlock) k_compact_recs(F f, int64_t n, float* recs, float* hot, uint32_t* count) {
+  constexpr int NC = recFloats(MODE), NH = hotFloats(MODE);
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   RecOut o; o.keep = false;
@@ -128,157 +132,144 @@ __global__ void __launch_bounds__(kBlock) k_compact_recs(F f, int64_t n, float* 
     const int64_t r = base + __popc(m & ((1u << lane) - 1u));
 #pragma unroll
     for (int k = 0; k < NC; ++k) recs[recIndex(r, k, NC)] = o.c[k];
+#pragma unroll
+    for (int k = 0; k < NH; ++k) hot[recIndex(r, k, NH)] = o.h[k];
   }
 }
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_pad_recs(float* recs, const uint32_t* count) {
-  constexpr int NC = recFloats(MODE);
+__global__ void __launch_bounds__(kBlock) k_pad_recs(float* recs, float* hot, const uint32_t* count) {
+  constexpr int NC = recFloats(MODE), NH = hotFloats(MODE);
   const int64_t n = *count, np = paddedFaces(n);
-  float c[16];
+  float c[16], h[4];
   neverHitRecord(MODE, c);
-  for (int64_t r = n + threadIdx.x; r < np; r += kBlock)
+  neverHitHot(MODE, h);
+  for (int64_t r = n + threadIdx.x; r < np; r += kBlock) {
 #pragma unroll
     for (int k = 0; k < NC; ++k) recs[recIndex(r, k, NC)] = c[k];
+#pragma unroll
+    for (int k = 0; k < NH; ++k) hot[recIndex(r, k, NH)] = h[k];
+  }
 }
 
-// ------------------------------------------------------------- mesh filter ----
-// The hot kernel: every queued ray of a bundle x every record of one record set, float32.
-// Two triangles are evaluated per FFMA2 (fma.rn.f32x2): records are pair-interleaved, ray
-// components are held duplicated in 64-bit register pairs.  Per (ray, triangle) test:
-//   GENERAL 15 FFMA + 2 FADD, ORIGIN 9 FFMA + 2 FADD, DIR 6 FFMA + 2 FADD  (+ ~1.5 LOP3 on the ALU pipe).
-// Persistent CTAs pull (ray tile x record block) work items from an atomic counter; the
-// records of a block are staged in shared memory in 16-byte vectors and read back as
-// warp-broadcast LDS.128; each thread keeps FT_R rays in registers.  Candidates (sign bits of
-// u', v', w' all clear) are appended to a global list for the float64 pass.
+// ---------------------------------------------------------- mesh prefilter ----
+// The hot kernel: every queued ray of a bundle x every hot record (bounding circle / sphere,
+// nrt_filter.h) of one record set, float32.  Two triangles are evaluated per FFMA2
+// (fma.rn.f32x2): records are pair-interleaved; ray components are scalar operands that the
+// hardware broadcasts to both halves.  Per (ray, triangle) test:
+//   ORIGIN / DIR  1 FADD + 2 FFMA  (2-D point in circle),   GENERAL  1 FADD + 1 FMUL + 6 FFMA
+// plus 0.5 LOP3 (sign accumulation) on the ALU pipe.  Persistent CTAs pull (ray tile x
+// record chunk) work items from an atomic counter; a chunk of hot records is staged in shared
+// memory in 16-byte vectors and read back as warp-broadcast LDS.128; each thread keeps R rays
+// in registers.  Survivors (sign bit of g clear) are appended to the pre-candidate list.
 static constexpr int FT_THREADS = 256;
-static constexpr int FT_R = 8;        // rays per thread
-static constexpr int FT_TC = 256;     // records per shared-memory chunk
-static constexpr int FT_TB = 256;     // records per work item (= one chunk: fine-grained items keep the tail short)
-static constexpr int FT_RAYS = FT_THREADS * FT_R;
+static constexpr int FT_TC = 256;     // records per shared-memory chunk == records per work item
 static_assert(kRecPad % FT_TC == 0, "record padding must cover whole shared-memory chunks");
+template <int MODE> struct PreCfg { static constexpr int R = (MODE == FM_GENERAL) ? 4 : 8; };
 
-struct FilterArgs {
-  const float4* recs;       // pair-interleaved records, padded to a multiple of kRecPad
+struct PreArgs {
+  const float4* hot;        // pair-interleaved hot records, padded to a multiple of kRecPad
   const uint32_t* nrec;     // number of records (device)
-  const float4* q0;         // ray plane 0: (d | o', rr)
-  const float4* q1;         // ray plane 1: (m, 0)  (GENERAL)
-  const uint32_t* qref;     // wave-ray index per queued ray
+  const float4* h0;         // ray plane H0: (x, y, q, 0) | (dh, q)
+  const float4* h1;         // ray plane H1: (2 p0, 0)   (GENERAL)
   const uint32_t* qcount;   // queued rays (device)
   uint32_t* tilectr;        // work-item counter
-  uint32_t* candctr;        // candidate counter
-  uint32_t* candRef;
-  uint32_t* candTri;
-  uint32_t candCap;
+  uint32_t* prectr;         // pre-candidate counter
+  uint32_t* preRay;
+  uint32_t* preRec;
+  uint32_t preCap;
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 
 template <int MODE>
-__global__ void __launch_bounds__(FT_THREADS, 2) k_mesh_filter(FilterArgs a) {
-  constexpr int NC = recFloats(MODE);   // float2 per record pair
-  constexpr int NP4 = NC / 2;           // float4 per record pair
-  __shared__ __align__(16) float4 tile[(FT_TC / 2) * NP4];
+__global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
+  constexpr int R = PreCfg<MODE>::R;
+  constexpr int NH = hotFloats(MODE);      // float2 per record pair
+  constexpr int Q4 = NH;                   // float4 per record QUAD (2 pairs = 4 NH floats... = NH float4)
+  __shared__ __align__(16) float4 tile[(FT_TC / 4) * Q4];
   __shared__ uint32_t s_item;
   const uint32_t nq = *a.qcount;
   if (nq == 0) return;
   const uint32_t nrecPadded = uint32_t(paddedFaces(int64_t(*a.nrec)));
   if (nrecPadded == 0) return;
-  const uint32_t nRayTiles = (nq + FT_RAYS - 1) / FT_RAYS;
-  const uint32_t nBlocks = (nrecPadded + FT_TB - 1) / FT_TB;
-  const uint32_t nItems = nRayTiles * nBlocks;
+  constexpr uint32_t RAYS = FT_THREADS * R;
+  const uint32_t nRayTiles = (nq + RAYS - 1) / RAYS;
+  const uint32_t nChunks = nrecPadded / FT_TC;
+  const uint32_t nItems = nRayTiles * nChunks;
   const int tid = threadIdx.x;
-  const float2 k16 = dup2(kFilterKd), one2 = dup2(1.0f);
   for (;;) {
     if (tid == 0) s_item = atomicAdd(a.tilectr, 1u);
     __syncthreads();
     const uint32_t item = s_item;
-    __syncthreads();
     if (item >= nItems) break;
-    const uint32_t rt = item / nBlocks, tb = item - rt * nBlocks;
-    float2 ax[FT_R], ay[FT_R], az[FT_R], mx[FT_R], my[FT_R], mz[FT_R];
-    uint32_t ref[FT_R];
-    float rrs = 0.f;
+    const uint32_t rt = item / nChunks, ch = item - rt * nChunks;
+    // stage the chunk (previous readers are past the barrier above only after the trailing barrier below)
+    const float4* src = a.hot + size_t(ch) * (FT_TC / 4) * Q4;
+    for (int k = tid; k < (FT_TC / 4) * Q4; k += FT_THREADS) tile[k] = __ldg(src + k);
+    float ra0[R], ra1[R], ra2[R], ra3[R], rb0[R], rb1[R], rb2[R];
+    uint32_t ridx[R];
 #pragma unroll
-    for (int r = 0; r < FT_R; ++r) {
-      const uint32_t idx = rt * FT_RAYS + r * FT_THREADS + tid;
+    for (int r = 0; r < R; ++r) {
+      const uint32_t idx = rt * RAYS + r * FT_THREADS + tid;
       const uint32_t ic = idx < nq ? idx : nq - 1;  // tail: duplicate a real ray, never emit for it
-      const float4 p0 = __ldg(a.q0 + ic);
-      ax[r] = dup2(p0.x); ay[r] = dup2(p0.y); az[r] = dup2(p0.z);
-      rrs = fmaxf(rrs, p0.w);
+      const float4 p0 = __ldg(a.h0 + ic);
+      ra0[r] = p0.x; ra1[r] = p0.y; ra2[r] = p0.z; ra3[r] = p0.w;
       if (MODE == FM_GENERAL) {
-        const float4 p1 = __ldg(a.q1 + ic);
-        mx[r] = dup2(p1.x); my[r] = dup2(p1.y); mz[r] = dup2(p1.z);
-      }
-      ref[r] = idx < nq ? __ldg(a.qref + ic) : kInvalidRef;
+        const float4 p1 = __ldg(a.h1 + ic);
+        rb0[r] = p1.x; rb1[r] = p1.y; rb2[r] = p1.z;
+      } else { rb0[r] = rb1[r] = rb2[r] = 0.f; }
+      ridx[r] = idx < nq ? idx : kInvalidRef;
     }
-    const float2 rr = dup2(rrs);
-    const uint32_t rec0 = tb * FT_TB;
-    const uint32_t rec1 = min(nrecPadded, rec0 + FT_TB);
-    for (uint32_t base = rec0; base < rec1; base += FT_TC) {
-      const float4* src = a.recs + size_t(base / 2) * NP4;
-      for (int k = tid; k < (FT_TC / 2) * NP4; k += FT_THREADS) tile[k] = __ldg(src + k);
-      __syncthreads();
+    __syncthreads();
+    const uint32_t base = ch * FT_TC;
 #pragma unroll 1
-      for (int t = 0; t < FT_TC / 2; ++t) {
-        float2 q[NC];
+    for (int t = 0; t < FT_TC / 4; ++t) {
+      float2 q[2 * NH];   // two record pairs: q[j * NH + k] = coefficient k of pair j
 #pragma unroll
-        for (int c = 0; c < NP4; ++c) {
-          const float4 v4 = tile[t * NP4 + c];
-          q[2 * c] = make_float2(v4.x, v4.y);
-          q[2 * c + 1] = make_float2(v4.z, v4.w);
-        }
-        const float2 eb = fmul2(q[recSlotS(MODE)], rr);
-        float2 kk, pu, qv;
-        if (MODE == FM_DIR) { kk = ffma2(eb, k16, one2); pu = fadd2(q[3], eb); qv = fadd2(q[7], eb); }
-        else { kk = fmul2(eb, k16); pu = eb; qv = eb; }
-        uint32_t xa[FT_R], xb[FT_R];
-        uint32_t acc = 0xFFFFFFFFu;
+      for (int c = 0; c < Q4; ++c) {
+        const float4 v4 = tile[t * Q4 + c];
+        q[2 * c] = make_float2(v4.x, v4.y);
+        q[2 * c + 1] = make_float2(v4.z, v4.w);
+      }
+      float2 g[R][2];
+      uint32_t acc = 0xFFFFFFFFu;
 #pragma unroll
-        for (int r = 0; r < FT_R; ++r) {
-          float2 u, v, w;
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float2* h = q + j * NH;
           if (MODE == FM_GENERAL) {
-            u = ffma2(q[7], mx[r], ffma2(q[8], my[r], ffma2(q[9], mz[r], ffma2(q[4], ax[r], ffma2(q[5], ay[r], ffma2(q[6], az[r], eb))))));
-            v = ffma2(q[13], mx[r], ffma2(q[14], my[r], ffma2(q[15], mz[r], ffma2(q[10], ax[r], ffma2(q[11], ay[r], ffma2(q[12], az[r], eb))))));
-            const float2 det = ffma2(q[0], ax[r], ffma2(q[1], ay[r], ffma2(q[2], az[r], kk)));
-            w = fadd2(fadd2(det, neg2(u)), neg2(v));
-          } else if (MODE == FM_ORIGIN) {
-            u = ffma2(q[4], ax[r], ffma2(q[5], ay[r], ffma2(q[6], az[r], eb)));
-            v = ffma2(q[8], ax[r], ffma2(q[9], ay[r], ffma2(q[10], az[r], eb)));
-            const float2 det = ffma2(q[0], ax[r], ffma2(q[1], ay[r], ffma2(q[2], az[r], kk)));
-            w = fadd2(fadd2(det, neg2(u)), neg2(v));
+            const float2 s = ffma2(h[0], dup2(ra0[r]), ffma2(h[1], dup2(ra1[r]), fmul2(h[2], dup2(ra2[r]))));
+            const float2 tt = ffma2(h[0], dup2(rb0[r]), ffma2(h[1], dup2(rb1[r]), ffma2(h[2], dup2(rb2[r]), fadd2(h[3], dup2(ra3[r])))));
+            g[r][j] = ffma2(s, s, tt);
           } else {
-            u = ffma2(q[0], ax[r], ffma2(q[1], ay[r], ffma2(q[2], az[r], pu)));
-            v = ffma2(q[4], ax[r], ffma2(q[5], ay[r], ffma2(q[6], az[r], qv)));
-            w = fadd2(fadd2(kk, neg2(u)), neg2(v));
+            g[r][j] = ffma2(h[0], dup2(ra0[r]), ffma2(h[1], dup2(ra1[r]), fadd2(h[2], dup2(ra2[r]))));
           }
-          xa[r] = __float_as_uint(u.x) | __float_as_uint(v.x) | __float_as_uint(w.x);
-          xb[r] = __float_as_uint(u.y) | __float_as_uint(v.y) | __float_as_uint(w.y);
-          acc &= xa[r] & xb[r];
+          acc &= __float_as_uint(g[r][j].x) & __float_as_uint(g[r][j].y);
         }
-        if (int(acc) >= 0) {  // some test has all three sign bits clear: rare
-          uint32_t ida, idb;
-          if (MODE == FM_GENERAL) { ida = base + 2 * t; idb = ida + 1; }
-          else { ida = __float_as_uint(q[recSlotId(MODE) < 0 ? 0 : recSlotId(MODE)].x); idb = __float_as_uint(q[recSlotId(MODE) < 0 ? 0 : recSlotId(MODE)].y); }
+      }
+      if (int(acc) >= 0) {  // some test has its sign bit clear: rare
 #pragma unroll
-          for (int r = 0; r < FT_R; ++r) {
-            if (ref[r] == kInvalidRef) continue;
-            if (int(xa[r]) >= 0) {
-              const uint32_t slot = atomicAdd(a.candctr, 1u);
-              if (slot < a.candCap) { a.candRef[slot] = ref[r]; a.candTri[slot] = ida; }
+        for (int r = 0; r < R; ++r) {
+          if (ridx[r] == kInvalidRef) continue;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (int(__float_as_uint(g[r][j].x)) >= 0) {
+              const uint32_t slot = atomicAdd(a.prectr, 1u);
+              if (slot < a.preCap) { a.preRay[slot] = ridx[r]; a.preRec[slot] = base + 4 * t + 2 * j; }
             }
-            if (int(xb[r]) >= 0) {
-              const uint32_t slot = atomicAdd(a.candctr, 1u);
-              if (slot < a.candCap) { a.candRef[slot] = ref[r]; a.candTri[slot] = idb; }
+            if (int(__float_as_uint(g[r][j].y)) >= 0) {
+              const uint32_t slot = atomicAdd(a.prectr, 1u);
+              if (slot < a.preCap) { a.preRay[slot] = ridx[r]; a.preRec[slot] = base + 4 * t + 2 * j + 1; }
             }
           }
         }
       }
-      __syncthreads();
     }
+    __syncthreads();   // everyone is done with `tile` and `s_item` before the next item overwrites them
   }
 }
 
@@ -320,12 +311,14 @@ struct CudaBackend {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> filterEvents;
   size_t filterUsed = 0;
   std::vector<int> filterModes;
+  int gridPerSm = 4;   // resident prefilter CTAs per SM (NRT_PREFILTER_CTAS_PER_SM)
 
   struct Atom {
     static __device__ __forceinline__ void min64(uint64_t* p, uint64_t v) {
       atomicMin(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
     }
     static __device__ __forceinline__ void min32(uint32_t* p, uint32_t v) { atomicMin(p, v); }
+    static __device__ __forceinline__ uint32_t add32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
   };
 
   void use() { NRT_CUDA(cudaSetDevice(device)); }
@@ -367,31 +360,31 @@ struct CudaBackend {
     k_gate<<<blocksFor(n), kBlock, 0, stream>>>(g, n, nMO, cnt);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
-  template <class F> void compactRecs(int64_t n, const F& f, float* recs, int mode, uint32_t* count) {
+  template <class F> void compactRecs(int64_t n, const F& f, float* recs, float* hot, int mode, uint32_t* count) {
     use();
     if (mode == FM_ORIGIN) {
-      k_compact_recs<F, FM_ORIGIN><<<blocksFor(n), kBlock, 0, stream>>>(f, n, recs, count);
-      k_pad_recs<FM_ORIGIN><<<1, kBlock, 0, stream>>>(recs, count);
+      k_compact_recs<F, FM_ORIGIN><<<blocksFor(n), kBlock, 0, stream>>>(f, n, recs, hot, count);
+      k_pad_recs<FM_ORIGIN><<<1, kBlock, 0, stream>>>(recs, hot, count);
     } else {
-      k_compact_recs<F, FM_DIR><<<blocksFor(n), kBlock, 0, stream>>>(f, n, recs, count);
-      k_pad_recs<FM_DIR><<<1, kBlock, 0, stream>>>(recs, count);
+      k_compact_recs<F, FM_DIR><<<blocksFor(n), kBlock, 0, stream>>>(f, n, recs, hot, count);
+      k_pad_recs<FM_DIR><<<1, kBlock, 0, stream>>>(recs, hot, count);
     }
     NRT_CUDA(cudaGetLastError()); launches += 2;
   }
-  void filter(int mode, const float* recs, const uint32_t* nrec, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
+  // prefilter launch for one ray bundle of one mesh object
+  void filter(int mode, const float* hot, const uint32_t* nrec, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
     use();
-    FilterArgs a;
-    a.recs = reinterpret_cast<const float4*>(recs);
+    PreArgs a;
+    a.hot = reinterpret_cast<const float4*>(hot);
     a.nrec = nrec;
     const int64_t base = queueBase(cs, mo, b);
-    a.q0 = reinterpret_cast<const float4*>(cs.qray0) + base;
-    a.q1 = reinterpret_cast<const float4*>(cs.qray1) + int64_t(mo) * cs.NR;
-    a.qref = cs.qref + base;
+    a.h0 = reinterpret_cast<const float4*>(cs.qhot0) + base;
+    a.h1 = reinterpret_cast<const float4*>(cs.qhot1) + int64_t(mo) * cs.NR;
     a.qcount = cnt + cntQueue(b);
     a.tilectr = cnt + cntTile(b);
-    a.candctr = cnt + CNT_CAND;
-    a.candRef = cs.candRef; a.candTri = cs.candTri;
-    a.candCap = uint32_t(std::min<int64_t>(cs.candCap, 0xFFFFFFFFll));
+    a.prectr = cnt + cntPre(b);
+    a.preRay = cs.preRay; a.preRec = cs.preRec;
+    a.preCap = uint32_t(std::min<int64_t>(cs.preCap, 0xFFFFFFFFll));
     if (filterUsed == filterEvents.size()) {
       cudaEvent_t e0, e1;
       NRT_CUDA(cudaEventCreate(&e0)); NRT_CUDA(cudaEventCreate(&e1));
@@ -401,10 +394,9 @@ struct CudaBackend {
     auto& ev = filterEvents[filterUsed];
     filterModes[filterUsed++] = mode;
     NRT_CUDA(cudaEventRecord(ev.first, stream));
-    const unsigned grid = unsigned(sms * 2);
-    if (mode == FM_GENERAL) k_mesh_filter<FM_GENERAL><<<grid, FT_THREADS, 0, stream>>>(a);
-    else if (mode == FM_ORIGIN) k_mesh_filter<FM_ORIGIN><<<grid, FT_THREADS, 0, stream>>>(a);
-    else k_mesh_filter<FM_DIR><<<grid, FT_THREADS, 0, stream>>>(a);
+    if (mode == FM_GENERAL) k_mesh_prefilter<FM_GENERAL><<<unsigned(sms * gridPerSm), FT_THREADS, 0, stream>>>(a);
+    else if (mode == FM_ORIGIN) k_mesh_prefilter<FM_ORIGIN><<<unsigned(sms * gridPerSm), FT_THREADS, 0, stream>>>(a);
+    else k_mesh_prefilter<FM_DIR><<<unsigned(sms * gridPerSm), FT_THREADS, 0, stream>>>(a);
     NRT_CUDA(cudaGetLastError()); ++launches;
     NRT_CUDA(cudaEventRecord(ev.second, stream));
   }
@@ -475,6 +467,7 @@ static int initLocked(int ngpu, const int* ids) {
       auto* d = new DeviceCtx();
       d->be.device = id;
       d->be.sms = p.multiProcessorCount;
+      if (const char* e = std::getenv("NRT_PREFILTER_CTAS_PER_SM")) d->be.gridPerSm = std::max(1, std::atoi(e));
       NRT_CUDA(cudaSetDevice(id));
       NRT_CUDA(cudaStreamCreateWithFlags(&d->be.stream, cudaStreamNonBlocking));
       NRT_CUDA(cudaEventCreate(&d->ev0)); NRT_CUDA(cudaEventCreate(&d->ev1));
@@ -627,12 +620,13 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     const ProfileAcc& a = sc->dev[d].rn.prof;
     p.mesh_tests += a.mesh_tests; p.mesh_tests_ref += a.mesh_tests_ref; p.mesh_rays += a.mesh_rays;
     p.candidates += a.candidates;
+    p.pre_candidates += a.pre_candidates;
     p.kernel_launches += dc->be.launches;
     for (int m = 0; m < 3; ++m) {
       p.mesh_tests_by_mode[m] += a.tests_by_mode[m];
       p.mesh_ms_by_mode[m] = std::max(p.mesh_ms_by_mode[m], byMode[m]);
-      // executed float32 flops per filter test (FFMA = 2): nrt_filter.h filterFlops()
-      p.fp32_flops += double(a.tests_by_mode[m]) * filterFlops(m);
+      // executed float32 flops per prefilter test (FFMA = 2): nrt_filter.h prefilterFlops()
+      p.fp32_flops += double(a.tests_by_mode[m]) * prefilterFlops(m);
     }
   }
   if (stats) {

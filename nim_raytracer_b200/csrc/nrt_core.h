@@ -95,8 +95,11 @@ struct DMesh {
   double bmin[4], bmax[4];  // calcAABB (geom.nim:175-188)
   double center[3];         // filter frame origin (AABB centre)
   double L;                 // filter length scale (max AABB half extent)
-  float* recs;              // general-mode filter records (nrt_filter.h), pair-interleaved
+  float* recs;              // GENERAL-mode full filter records (nrt_filter.h), pair-interleaved
+  float* hot;               // GENERAL-mode hot (bounding sphere) records, pair-interleaved
 };
+
+struct BundleFrame;  // nrt_filter.h
 
 struct DScene {
   int32_t nobjects, nlights, nmeshes, nmesh_objs;
@@ -104,6 +107,7 @@ struct DScene {
   const DLight* lights;
   const DMesh* meshes;
   const int32_t* mesh_obj_index;  // mesh object k -> object index
+  const BundleFrame* frames;      // [mo * (2 + nlights) + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
   double c2w[16];
   double tan_half_fov;            // f of renderer.nim:38 (host libm, shared with nothing else)
   double bg[3];

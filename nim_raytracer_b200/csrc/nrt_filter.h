@@ -66,6 +66,11 @@ NRT_HD float roundUpF(double v) {  // smallest-ish float >= v (v >= 0)
   return f;
 }
 NRT_HD float bitsToFloat(uint32_t u) { union { float f; uint32_t u; } c; c.u = u; return c.f; }
+NRT_HD float roundUpSigned(double v) {  // a float >= v, either sign
+  float f = (float)v;
+  if ((double)f < v) f = (v >= 0) ? f * 1.0000002f + 1e-45f : f * 0.9999998f;
+  return f;
+}
 
 NRT_HD void neverHitRecord(int mode, float* c) {
   for (int k = 0; k < recFloats(mode); ++k) c[k] = 0.f;
@@ -211,6 +216,206 @@ NRT_HD uint32_t filterTest(int mode, const float* q, const float* a, const float
   const float v = fmaf(q[4], a[0], fmaf(q[5], a[1], fmaf(q[6], a[2], q[7] + eb)));
   const float w = (k1 - u) - v;
   return fbits(u) | fbits(v) | fbits(w);
+}
+
+// =====================================================================================
+// PREFILTER (the hot loop): bounding circle / sphere of every triangle.
+//
+// A ray can only hit a triangle if its line passes through the triangle's minimal enclosing
+// sphere (centre c, radius r).  For ray bundles this collapses to 2-D:
+//   DIR     orthographic projection along the shared direction D onto the plane (b1, b2):
+//           the ray is a point p = (x, y); the triangle projects to a 2-D triangle with
+//           enclosing circle (c, r);  hit  =>  |p - c|^2 <= r^2
+//   ORIGIN  perspective projection from the shared origin O onto the plane z = 1 of the frame
+//           (b1, b2, f):  p = (d.b1, d.b2) / d.f,  vertices (v-O).b / (v-O).f  — lines map to
+//           lines, so the projected triangle (all three vertices in front: z > 0) bounds the
+//           rays that can hit it; triangles touching z <= 0 become always-candidates.
+//   GENERAL distance from the sphere centre to the ray line, with the ray given by its unit
+//           direction dh and the point p0 of the line closest to the mesh centre (p0 . dh = 0):
+//           dist^2 = |c - p0|^2 - (c . dh)^2 <= r^2
+// Expanded so that every term is a product of one per-triangle and one per-ray quantity:
+//   2-D:     g = (r^2 - |c|^2) + (-|p|^2) + 2c.p                      1 FADD + 2 FFMA
+//   GENERAL: g = (r^2 - |c|^2) + (-|p0|^2) + 2c.p0 + (c.dh)^2         1 FADD + 7 FFMA (1 FMUL)
+// and the candidate condition is g >= 0 (one sign bit).  Margins that bound the float32
+// evaluation error are folded into the two additive constants at build time:
+//   per triangle  mt = 8u (2|c|^2 + |r^2 - |c|^2|)   (GENERAL: 32u|c|^2 + 8u|K0|)
+//   per ray       mr = 16u |p|^2 (+ float64 slack)
+// Survivors ("pre-candidates") go through the float32 sign test above (refine stage) and
+// only then to the float64 evaluation, so the hot loop touches 12-16 bytes per triangle.
+// =====================================================================================
+
+// floats per hot record (pair-interleaved like the full records)
+NRT_HD constexpr int hotFloats(int mode) { return mode == FM_GENERAL ? 4 : 3; }
+NRT_HD constexpr int prefilterFlops(int mode) { return mode == FM_GENERAL ? 16 : 5; }
+
+// Shared frame of a ray bundle (object space), built on the host in float64.
+struct BundleFrame {
+  double org[3];   // ORIGIN: the shared origin O;  DIR / GENERAL: the mesh AABB centre C
+  double b1[3], b2[3], f[3];   // orthonormal; f = projection axis (DIR: the shared direction, unit)
+  double valid;    // 0: no usable frame (degenerate direction) => the bundle's rays are treated as GENERAL
+};
+NRT_HD int frameIndex(int nlights, int mo, int mode, int l) { return mo * (2 + nlights) + (mode == FM_GENERAL ? 0 : (mode == FM_ORIGIN ? 1 : 2 + l)); }
+
+NRT_HD void neverHitHot(int mode, float* h) {
+  for (int k = 0; k < hotFloats(mode); ++k) h[k] = 0.f;
+  h[mode == FM_GENERAL ? 3 : 2] = -1e30f;
+}
+NRT_HD void alwaysHot(int mode, float* h) {
+  for (int k = 0; k < hotFloats(mode); ++k) h[k] = 0.f;
+  h[mode == FM_GENERAL ? 3 : 2] = 1e30f;
+}
+
+// Minimal enclosing circle of a 2-D triangle (float64).  Returns false if degenerate beyond use.
+NRT_HD void enclosingCircle2(const double* a, const double* b, const double* c, double& cx, double& cy, double& r2) {
+  // longest edge first
+  const double ab = (b[0] - a[0]) * (b[0] - a[0]) + (b[1] - a[1]) * (b[1] - a[1]);
+  const double bc = (c[0] - b[0]) * (c[0] - b[0]) + (c[1] - b[1]) * (c[1] - b[1]);
+  const double ca = (a[0] - c[0]) * (a[0] - c[0]) + (a[1] - c[1]) * (a[1] - c[1]);
+  const double *p = a, *q = b, *o = c; double l2 = ab;
+  if (bc >= l2) { p = b; q = c; o = a; l2 = bc; }
+  if (ca >= l2) { p = c; q = a; o = b; l2 = ca; }
+  // angle at o >= 90 deg  <=>  (p-o).(q-o) <= 0: the circle on pq as diameter encloses o
+  const double dotv = (p[0] - o[0]) * (q[0] - o[0]) + (p[1] - o[1]) * (q[1] - o[1]);
+  cx = 0.5 * (p[0] + q[0]); cy = 0.5 * (p[1] + q[1]); r2 = 0.25 * l2;
+  if (dotv > 0) {  // acute: circumcircle
+    const double bx = q[0] - p[0], by = q[1] - p[1], ex = o[0] - p[0], ey = o[1] - p[1];
+    const double d = 2 * (bx * ey - by * ex);
+    const double b2 = bx * bx + by * by, e2 = ex * ex + ey * ey;
+    if (d != 0) {
+      const double ux = (ey * b2 - by * e2) / d, uy = (bx * e2 - ex * b2) / d;
+      const double rr = ux * ux + uy * uy;
+      if (rr < 4 * l2) { cx = p[0] + ux; cy = p[1] + uy; r2 = rr; }   // acute => R <= longest edge; else keep diameter circle
+      else {  // numerically degenerate: fall back to a circle around the longest edge's midpoint
+        const double mx = o[0] - cx, my = o[1] - cy;
+        r2 = fmax(r2, mx * mx + my * my);
+      }
+    }
+  }
+  // make it enclose all three vertices despite rounding
+  double m = 0;
+  const double* v[3] = {a, b, c};
+  for (int i = 0; i < 3; ++i) { const double x = v[i][0] - cx, y = v[i][1] - cy; m = fmax(m, x * x + y * y); }
+  r2 = fmax(r2, m) * (1.0 + 1e-9);
+}
+
+// Minimal enclosing sphere of a 3-D triangle (centre in its plane), float64.
+NRT_HD void enclosingSphere3(const double* a, const double* b, const double* c, double* ctr, double& r2) {
+  double ab = 0, bc = 0, ca = 0;
+  for (int k = 0; k < 3; ++k) { ab += (b[k] - a[k]) * (b[k] - a[k]); bc += (c[k] - b[k]) * (c[k] - b[k]); ca += (a[k] - c[k]) * (a[k] - c[k]); }
+  const double *p = a, *q = b, *o = c; double l2 = ab;
+  if (bc >= l2) { p = b; q = c; o = a; l2 = bc; }
+  if (ca >= l2) { p = c; q = a; o = b; l2 = ca; }
+  double dotv = 0;
+  for (int k = 0; k < 3; ++k) { dotv += (p[k] - o[k]) * (q[k] - o[k]); ctr[k] = 0.5 * (p[k] + q[k]); }
+  r2 = 0.25 * l2;
+  if (dotv > 0) {
+    double u[3], w[3], n[3];
+    for (int k = 0; k < 3; ++k) { u[k] = q[k] - p[k]; w[k] = o[k] - p[k]; }
+    n[0] = u[1] * w[2] - u[2] * w[1]; n[1] = u[2] * w[0] - u[0] * w[2]; n[2] = u[0] * w[1] - u[1] * w[0];
+    const double n2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    const double u2 = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], w2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    if (n2 > 0) {
+      // circumcentre - p = (|w|^2 (n x u)... ) : ( w2 * (u x n)... ) standard form: (u2 (w x n) ... )
+      // c - p = ( |u|^2 (w x n) ... ) is error-prone; use: ((n x u) w2 + (w x n) u2) / (2 n2)
+      double nu[3] = {n[1] * u[2] - n[2] * u[1], n[2] * u[0] - n[0] * u[2], n[0] * u[1] - n[1] * u[0]};
+      double wn[3] = {w[1] * n[2] - w[2] * n[1], w[2] * n[0] - w[0] * n[2], w[0] * n[1] - w[1] * n[0]};
+      double t[3], rr = 0;
+      for (int k = 0; k < 3; ++k) { t[k] = (nu[k] * w2 + wn[k] * u2) / (2 * n2); rr += t[k] * t[k]; }
+      if (rr < 4 * l2) { for (int k = 0; k < 3; ++k) ctr[k] = p[k] + t[k]; r2 = rr; }
+      else { double m = 0; for (int k = 0; k < 3; ++k) m += (o[k] - ctr[k]) * (o[k] - ctr[k]); r2 = fmax(r2, m); }
+    }
+  }
+  double m = 0;
+  const double* v[3] = {a, b, c};
+  for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += (v[i][k] - ctr[k]) * (v[i][k] - ctr[k]); m = fmax(m, s); }
+  r2 = fmax(r2, m) * (1.0 + 1e-9);
+}
+
+NRT_HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// Hot record of triangle (p0, p1, p2) for a bundle frame.  h has hotFloats(mode) entries.
+NRT_HD void makeHotRec(int mode, const BundleFrame& fr, const double* p0, const double* p1, const double* p2, float* h) {
+  const double* v[3] = {p0, p1, p2};
+  if (mode == FM_GENERAL) {
+    double a[3], b[3], c[3], ctr[3], r2;
+    for (int k = 0; k < 3; ++k) { a[k] = p0[k] - fr.org[k]; b[k] = p1[k] - fr.org[k]; c[k] = p2[k] - fr.org[k]; }
+    enclosingSphere3(a, b, c, ctr, r2);
+    const double c2 = dot3(ctr, ctr), K0 = r2 - c2;
+    const double mt = 32.0 * kFilterU * c2 + 8.0 * kFilterU * fabs(K0) + 8.0 * kFilterU * r2;
+    if (!(c2 < 1e30) || !(r2 < 1e30)) { alwaysHot(mode, h); return; }
+    h[0] = (float)ctr[0]; h[1] = (float)ctr[1]; h[2] = (float)ctr[2]; h[3] = roundUpSigned(K0 + mt);
+    return;
+  }
+  double q[3][2];
+  for (int i = 0; i < 3; ++i) {
+    double w[3] = {v[i][0] - fr.org[0], v[i][1] - fr.org[1], v[i][2] - fr.org[2]};
+    double x = dot3(w, fr.b1), y = dot3(w, fr.b2);
+    if (mode == FM_ORIGIN) {
+      const double z = dot3(w, fr.f);
+      const double wl = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
+      if (!(z > 1e-6 * wl) || !(z > 1e-290)) { alwaysHot(mode, h); return; }   // vertex at / behind the projection plane
+      x /= z; y /= z;
+    }
+    q[i][0] = x; q[i][1] = y;
+  }
+  double cx, cy, r2;
+  enclosingCircle2(q[0], q[1], q[2], cx, cy, r2);
+  const double c2 = cx * cx + cy * cy, c0 = r2 - c2;
+  const double mt = 8.0 * kFilterU * (2.0 * c2 + fabs(c0)) + 8.0 * kFilterU * r2;
+  if (!(c2 < 1e30) || !(r2 < 1e30)) { alwaysHot(mode, h); return; }
+  h[0] = (float)(2.0 * cx); h[1] = (float)(2.0 * cy);
+  h[2] = roundUpSigned(c0 + mt);
+}
+
+// Hot representation of a ray: plane H0 = (x, y, q, 0) [2-D] or (dh.xyz, q) [GENERAL]; plane H1 = (2 p0, 0).
+struct HotRay { float a0, a1, a2, a3; float b0, b1, b2, b3; };
+
+NRT_HD bool makeHotRay(int mode, const BundleFrame& fr, const Ray& r, HotRay& h) {
+  const double big = 1e15;
+  h.a0 = h.a1 = h.a2 = h.a3 = h.b0 = h.b1 = h.b2 = h.b3 = 0.f;
+  const double d[3] = {r.dir.x, r.dir.y, r.dir.z};
+  const double o[3] = {r.orig.x - fr.org[0], r.orig.y - fr.org[1], r.orig.z - fr.org[2]};
+  const double oi = fmax(fabs(o[0]), fmax(fabs(o[1]), fabs(o[2])));
+  if (mode == FM_ORIGIN) {
+    const double z = dot3(d, fr.f), dl = fabs(d[0]) + fabs(d[1]) + fabs(d[2]);
+    if (!(z > 1e-6 * dl) || !(z > 1e-290)) return false;   // not in front of the projection plane
+    const double x = dot3(d, fr.b1) / z, y = dot3(d, fr.b2) / z;
+    const double p2 = x * x + y * y;
+    if (!(p2 < big)) return false;
+    const double q = -p2 + 16.0 * kFilterU * p2 + 1e-14 * (1.0 + p2);
+    h.a0 = (float)x; h.a1 = (float)y; h.a2 = roundUpSigned(q);
+    return true;
+  }
+  if (!(oi < big)) return false;
+  if (mode == FM_DIR) {
+    const double x = dot3(o, fr.b1), y = dot3(o, fr.b2);
+    const double p2 = x * x + y * y;
+    const double q = -p2 + 16.0 * kFilterU * p2 + 64.0 * kEps64 * oi * oi;
+    h.a0 = (float)x; h.a1 = (float)y; h.a2 = roundUpSigned(q);
+    return true;
+  }
+  const double dl2 = dot3(d, d);
+  if (!(dl2 > 1e-290) || !(dl2 < 1e290)) return false;
+  const double il = 1.0 / sqrt(dl2);
+  const double dh[3] = {d[0] * il, d[1] * il, d[2] * il};
+  const double s = dot3(o, dh);
+  const double p0[3] = {o[0] - s * dh[0], o[1] - s * dh[1], o[2] - s * dh[2]};
+  const double p2 = dot3(p0, p0);
+  const double q = -p2 + 16.0 * kFilterU * p2 + 64.0 * kEps64 * oi * oi;
+  h.a0 = (float)dh[0]; h.a1 = (float)dh[1]; h.a2 = (float)dh[2]; h.a3 = roundUpSigned(q);
+  h.b0 = (float)(2.0 * p0[0]); h.b1 = (float)(2.0 * p0[1]); h.b2 = (float)(2.0 * p0[2]);
+  return true;
+}
+
+// Scalar statement of one prefilter test (the CUDA kernel evaluates two records per FFMA2 with
+// exactly these operations per component).  Sign bit of the result clear <=> pre-candidate.
+NRT_HD uint32_t prefilterTest(int mode, const float* h, const HotRay& r) {
+  if (mode == FM_GENERAL) {
+    const float s = fmaf(h[0], r.a0, fmaf(h[1], r.a1, h[2] * r.a2));
+    const float t = fmaf(h[0], r.b0, fmaf(h[1], r.b1, fmaf(h[2], r.b2, h[3] + r.a3)));
+    return fbits(fmaf(s, s, t));
+  }
+  return fbits(fmaf(h[0], r.a0, fmaf(h[1], r.a1, h[2] + r.a2)));
 }
 
 // executed float32 flops per test (FFMA = 2): reported next to the roofline

@@ -26,13 +26,14 @@ namespace nrt {
 
 enum WaveKind { WAVE_PATH = 0, WAVE_SHADOW = 1 };
 
-// Counter block per (wave, mesh object): [EXACT, CAND, then (QUEUE_b, TILE_b) per ray bundle b].
+// Counter block per (wave, mesh object): [EXACT, CAND, then (QUEUE_b, TILE_b, PRE_b) per ray bundle b].
 // Bundle 0 holds arbitrary rays (GENERAL mode; ORIGIN mode for the primary wave, whose rays share
 // the camera origin); bundle 1 + l holds the shadow rays of DistantLight l (DIR mode).
 enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_BUNDLE0 = 2 };
-NRT_HD int cntStride(int nL) { return CNT_BUNDLE0 + 2 * (1 + nL); }
-NRT_HD int cntQueue(int b) { return CNT_BUNDLE0 + 2 * b; }
-NRT_HD int cntTile(int b) { return CNT_BUNDLE0 + 2 * b + 1; }
+NRT_HD int cntStride(int nL) { return CNT_BUNDLE0 + 3 * (1 + nL); }
+NRT_HD int cntQueue(int b) { return CNT_BUNDLE0 + 3 * b; }      // rays queued for the bundle
+NRT_HD int cntTile(int b) { return CNT_BUNDLE0 + 3 * b + 1; }   // prefilter work-item counter
+NRT_HD int cntPre(int b) { return CNT_BUNDLE0 + 3 * b + 2; }    // pre-candidates (prefilter survivors)
 // Stats slots
 enum { ST_PRIMARY = 0, ST_TESTS = 1, ST_HITS = 2, ST_RAYS = 3, ST_CAPPED = 4, ST_CONT = 5, ST_COUNT = 8 };
 
@@ -72,6 +73,12 @@ struct ChunkState {
   uint32_t* qref;    // nMO*QCAP   wave-ray index
   float* qray0;      // nMO*QCAP*4 plane 0 (float4): (d | o', rr)
   float* qray1;      // nMO*NR*4   plane 1 (float4), bundle 0 only: (m, 0)
+  float* qhot0;      // nMO*QCAP*4 prefilter plane 0 (float4): (x, y, q, 0) | (dh, q)
+  float* qhot1;      // nMO*NR*4   prefilter plane 1 (float4), bundle 0 only: (2 p0, 0)
+  // pre-candidates of the current bundle: (queue index, record position)
+  int64_t preCap;
+  uint32_t* preRay;  // preCap
+  uint32_t* preRec;  // preCap
   uint32_t* xref;    // nMO*NR     exact (float64 brute force) queue
   // candidates of the current (wave, mesh object)
   uint32_t* candRef; // candCap
@@ -234,7 +241,7 @@ NRT_HD Ray objectRay(const DObject& ob, V4 o, V4 d) {  // renderer.nim:54-55
 }
 
 // ---- gate: TriangleMesh.intersect's AABB test (geom.nim:340) per (ray, mesh object)
-struct GateOut { bool pass, safe; int bundle; FilterRay fr; };
+struct GateOut { bool pass, safe; int bundle; FilterRay fr; HotRay hr; };
 struct Gate {
   const DScene* sc; FrameParams fp; ChunkState cs; int kind; int64_t n; int force_exact;
   int path_mode;   // FM_ORIGIN for the primary wave (all rays share the camera origin), else FM_GENERAL
@@ -251,13 +258,15 @@ struct Gate {
     cs.tBest[int64_t(mo) * cs.NR + i] = dbits(g.pass ? NRT_INF : NRT_NEG_INF);
     cs.triBest[int64_t(mo) * cs.NR + i] = kNoTri;
     if (g.pass && !force_exact) {
-      int mode = path_mode;
+      int mode = path_mode, l = 0;
       if (kind == WAVE_SHADOW) {
-        const int l = int(i % cs.nL);
-        if (sc->lights[l].kind == LIGHT_DISTANT) { mode = FM_DIR; g.bundle = 1 + l; }
-        else mode = FM_GENERAL;
+        l = int(i % cs.nL);
+        mode = (sc->lights[l].kind == LIGHT_DISTANT) ? FM_DIR : FM_GENERAL;
       }
-      g.safe = makeFilterRay(mode, m, r, g.fr);
+      if (mode != FM_GENERAL && !(sc->frames[frameIndex(sc->nlights, mo, mode, l)].valid > 0)) mode = FM_GENERAL;
+      g.bundle = (mode == FM_DIR) ? 1 + l : 0;
+      const BundleFrame& fr = sc->frames[frameIndex(sc->nlights, mo, mode, l)];
+      g.safe = makeFilterRay(mode, m, r, g.fr) && makeHotRay(mode, fr, r, g.hr);
       if (!g.safe) g.bundle = 0;
     }
     return g;
@@ -282,6 +291,27 @@ struct ExactMesh {
     }
     cs.tBest[int64_t(mo) * cs.NR + ref] = dbits(tMin == 0 ? 0.0 : tMin);
     cs.triBest[int64_t(mo) * cs.NR + ref] = tri;
+  }
+};
+
+// ---- refine: float32 sign test (nrt_filter.h: filterTest) on the prefilter survivors ----
+template <class A>
+struct Refine {
+  ChunkState cs; int mode; const float* recs; int mo; int b; uint32_t* candCount;
+  NRT_HD void operator()(int64_t i) const {
+    const uint32_t rq = cs.preRay[i], pos = cs.preRec[i];
+    const int nc = recFloats(mode);
+    float q[16];
+    for (int k = 0; k < nc; ++k) q[k] = recs[recIndex(pos, k, nc)];
+    const int64_t at = queueBase(cs, mo, b) + rq;
+    const float* p0 = cs.qray0 + 4 * at;
+    const float* p1 = cs.qray1 + 4 * (int64_t(mo) * cs.NR + rq);   // read only in GENERAL mode (b == 0)
+    const uint32_t x = filterTest(mode, q, p0, p1, p0[3]);
+    if (int32_t(x) < 0) return;
+    uint32_t tri = pos;
+    if (recSlotId(mode) >= 0) tri = fbits(q[recSlotId(mode)]);
+    const uint32_t slot = A::add32(candCount, 1u);
+    if (slot < cs.candCap) { cs.candRef[slot] = cs.qref[at]; cs.candTri[slot] = tri; }
   }
 };
 
@@ -470,16 +500,26 @@ struct Finalize {
 };
 
 // ---- filter records (nrt_filter.h), one element per face (or per padding slot) ----
-struct RecOut { bool keep; float c[16]; };
+struct RecOut { bool keep; float c[16]; float h[4]; };
 
 // GENERAL: depends on the mesh only; stored at its own index (face id == record index).
 struct BuildRecsGeneral {
   DMesh m;
   NRT_HD void operator()(int64_t f) const {
-    float c[16];
-    if (f < m.nfaces) makeRecGeneral(m, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2], c);
-    else neverHitRecord(FM_GENERAL, c);
+    float c[16], h[4];
+    if (f < m.nfaces) {
+      const double *p0 = m.verts + 4 * m.vidx[3 * f], *p1 = m.verts + 4 * m.vidx[3 * f + 1], *p2 = m.verts + 4 * m.vidx[3 * f + 2];
+      makeRecGeneral(m, p0, p1, p2, c);
+      BundleFrame fr;
+      fr.org[0] = m.center[0]; fr.org[1] = m.center[1]; fr.org[2] = m.center[2];
+      makeHotRec(FM_GENERAL, fr, p0, p1, p2, h);
+      if (!(c[3] < 1e30f)) alwaysHot(FM_GENERAL, h);
+    } else {
+      neverHitRecord(FM_GENERAL, c);
+      neverHitHot(FM_GENERAL, h);
+    }
     for (int k = 0; k < 16; ++k) m.recs[recIndex(f, k, 16)] = c[k];
+    for (int k = 0; k < 4; ++k) m.hot[recIndex(f, k, 4)] = h[k];
   }
 };
 
@@ -493,10 +533,16 @@ struct BuildRecsOrigin {
     const V4 ow = mulm(sc->c2w, v4(0.0, 0.0, 0.0, 1.0));   // castPrimaryRay's origin (renderer.nim:42)
     const V4 oo = mulm(ob.w2o, ow);                        // trace()'s object-space origin (renderer.nim:54)
     const double O[3] = {oo.x, oo.y, oo.z};
-    o.keep = makeRecOrigin(O, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2],
-                           uint32_t(f), o.c);
+    const double *p0 = m.verts + 4 * m.vidx[3 * f], *p1 = m.verts + 4 * m.vidx[3 * f + 1], *p2 = m.verts + 4 * m.vidx[3 * f + 2];
+    o.keep = makeRecOrigin(O, p0, p1, p2, uint32_t(f), o.c);
+    if (!o.keep) return o;
+    makeHotRec(FM_ORIGIN, sc->frames[frameIndex(sc->nlights, mo, FM_ORIGIN, 0)], p0, p1, p2, o.h);
     // a record float32 cannot hold (|v0 - O| or S overflow) becomes an always-candidate record
-    if (o.keep && !(o.c[3] < 1e30f)) { for (int k = 0; k < 12; ++k) o.c[k] = 0.f; o.c[3] = 1e30f; o.c[7] = bitsToFloat(uint32_t(f)); }
+    if (!(o.c[3] < 1e30f)) {
+      for (int k = 0; k < 12; ++k) o.c[k] = 0.f;
+      o.c[3] = 1e30f; o.c[7] = bitsToFloat(uint32_t(f));
+      alwaysHot(FM_ORIGIN, o.h);
+    }
     return o;
   }
 };
@@ -512,8 +558,11 @@ struct BuildRecsDir {
     const V4 dw = scale(v4(li.dir[0], li.dir[1], li.dir[2], li.dir[3]), -1.0);   // renderer.nim:96
     const V4 dobj = mulm(ob.w2o, dw);                                             // renderer.nim:55
     const double D[3] = {dobj.x, dobj.y, dobj.z};
-    o.keep = makeRecDir(m, D, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2],
-                        uint32_t(f), o.c);
+    const double *p0 = m.verts + 4 * m.vidx[3 * f], *p1 = m.verts + 4 * m.vidx[3 * f + 1], *p2 = m.verts + 4 * m.vidx[3 * f + 2];
+    o.keep = makeRecDir(m, D, p0, p1, p2, uint32_t(f), o.c);
+    if (!o.keep) return o;
+    makeHotRec(FM_DIR, sc->frames[frameIndex(sc->nlights, mo, FM_DIR, l)], p0, p1, p2, o.h);
+    if (!(o.c[8] < 1e29f)) alwaysHot(FM_DIR, o.h);
     return o;
   }
 };

@@ -20,6 +20,7 @@ namespace nrt {
 struct ProfileAcc {
   int64_t mesh_tests = 0, mesh_tests_ref = 0, mesh_rays = 0, candidates = 0, exact_rays = 0;
   int64_t tests_by_mode[3] = {0, 0, 0};
+  int64_t pre_candidates = 0;
 };
 
 inline bool isPow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -39,13 +40,37 @@ struct SceneData {
   bool anyReflective = false, anyPointLight = false;
   int64_t bytes_uploaded = 0;
   // Filter record sets per mesh object (device): ORIGIN (camera) and DIR per DistantLight.
-  struct MoRecs { float* origin = nullptr; std::vector<float*> dir; };
+  struct MoRecs { float* origin = nullptr; float* originHot = nullptr; std::vector<float*> dir, dirHot; };
+  std::vector<BundleFrame> frames;        // host copy, [mo * recStride() + j]
+  BundleFrame* dFrames = nullptr;
+  bool anyGeneralShadow = false;          // some shadow rays need the GENERAL bundle (point light / unusable frame)
   std::vector<MoRecs> moRecs;
   uint32_t* dRecCount = nullptr;          // [mo * recStride() + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
   std::vector<uint32_t> hRecCount;
   int recStride() const { return 2 + h.nlights; }
   const float* recsOf(int mo, int mode, int l) const {
     return mode == FM_GENERAL ? meshes[objs[moIndex[mo]].mesh].recs : (mode == FM_ORIGIN ? moRecs[mo].origin : moRecs[mo].dir[l]);
+  }
+  const float* hotOf(int mo, int mode, int l) const {
+    return mode == FM_GENERAL ? meshes[objs[moIndex[mo]].mesh].hot : (mode == FM_ORIGIN ? moRecs[mo].originHot : moRecs[mo].dirHot[l]);
+  }
+  bool frameValid(int mo, int mode, int l) const { return frames[frameIndex(h.nlights, mo, mode, l)].valid > 0; }
+
+  static bool makeBasis(const double* axis, BundleFrame& fr) {
+    const double n2 = axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2];
+    if (!(n2 > 1e-280) || !(n2 < 1e280)) return false;
+    const double il = 1.0 / std::sqrt(n2);
+    for (int k = 0; k < 3; ++k) fr.f[k] = axis[k] * il;
+    const double ax = std::fabs(fr.f[0]), ay = std::fabs(fr.f[1]), az = std::fabs(fr.f[2]);
+    double a[3] = {0, 0, 0};
+    a[(ax <= ay && ax <= az) ? 0 : (ay <= az ? 1 : 2)] = 1.0;
+    double c[3] = {a[1] * fr.f[2] - a[2] * fr.f[1], a[2] * fr.f[0] - a[0] * fr.f[2], a[0] * fr.f[1] - a[1] * fr.f[0]};
+    const double cl = 1.0 / std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    for (int k = 0; k < 3; ++k) fr.b1[k] = c[k] * cl;
+    fr.b2[0] = fr.f[1] * fr.b1[2] - fr.f[2] * fr.b1[1];
+    fr.b2[1] = fr.f[2] * fr.b1[0] - fr.f[0] * fr.b1[2];
+    fr.b2[2] = fr.f[0] * fr.b1[1] - fr.f[1] * fr.b1[0];
+    return true;
   }
   const uint32_t* recCountOf(int mo, int mode, int l) const { return dRecCount + mo * recStride() + (mode == FM_GENERAL ? 0 : (mode == FM_ORIGIN ? 1 : 2 + l)); }
   uint32_t hostRecCount(int mo, int mode, int l) const { return hRecCount[mo * recStride() + (mode == FM_GENERAL ? 0 : (mode == FM_ORIGIN ? 1 : 2 + l))]; }
@@ -106,7 +131,8 @@ struct SceneData {
       dm.normals = up(m.normals, m.nnormals * 4, reuse ? const_cast<double*>(old[i].normals) : nullptr);
       dm.vidx = up(m.vertex_idx, m.nfaces * 3, reuse ? const_cast<int64_t*>(old[i].vidx) : nullptr);
       dm.nidx = up(m.normal_idx, m.nfaces * 3, reuse ? const_cast<int64_t*>(old[i].nidx) : nullptr);
-      dm.recs = up<float>(nullptr, paddedFaces(m.nfaces) * 16, reuse ? old[i].recs : nullptr);
+      dm.recs = up<float>(nullptr, paddedFaces(m.nfaces) * recFloats(FM_GENERAL), reuse ? old[i].recs : nullptr);
+      dm.hot = up<float>(nullptr, paddedFaces(m.nfaces) * hotFloats(FM_GENERAL), reuse ? old[i].hot : nullptr);
       calcAABB(m.vertices, m.nverts, dm.bmin, dm.bmax);
       double L = 0;
       for (int k = 0; k < 3; ++k) {
@@ -156,7 +182,40 @@ struct SceneData {
     dMo = up(moIndex.data(), int64_t(moIndex.size()), reuse ? dMo : nullptr);
     h.nobjects = desc->nobjects; h.nlights = desc->nlights; h.nmeshes = desc->nmeshes;
     h.nmesh_objs = int32_t(moIndex.size());
-    h.objects = dObjs; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo;
+    // ---- bundle frames (float64, host): projection frames of the ORIGIN / DIR bundles ----
+    {
+      const int nMOf = int(moIndex.size()), rsf = 2 + desc->nlights;
+      frames.assign(size_t(std::max(1, nMOf * rsf)), BundleFrame{});
+      anyGeneralShadow = anyPointLight;
+      for (int mo = 0; mo < nMOf; ++mo) {
+        const DObject& ob = objs[moIndex[mo]];
+        const DMesh& m = meshes[ob.mesh];
+        BundleFrame& fg = frames[mo * rsf];
+        for (int k = 0; k < 3; ++k) fg.org[k] = m.center[k];
+        fg.valid = 1.0;
+        // ORIGIN: shared origin = trace()'s object-space image of castPrimaryRay's origin; axis = camera forward
+        BundleFrame& fo = frames[mo * rsf + 1];
+        const V4 ow = mulm(desc->camera_to_world, v4(0.0, 0.0, 0.0, 1.0));
+        const V4 oo = mulm(ob.w2o, ow);
+        const V4 fw = mulm(ob.w2o, mulm(desc->camera_to_world, v4(0.0, 0.0, -1.0, 0.0)));
+        fo.org[0] = oo.x; fo.org[1] = oo.y; fo.org[2] = oo.z;
+        const double fa[3] = {fw.x, fw.y, fw.z};
+        fo.valid = (makeBasis(fa, fo) && std::isfinite(oo.x) && std::isfinite(oo.y) && std::isfinite(oo.z)) ? 1.0 : 0.0;
+        for (int l = 0; l < desc->nlights; ++l) {
+          BundleFrame& fd = frames[mo * rsf + 2 + l];
+          for (int k = 0; k < 3; ++k) fd.org[k] = m.center[k];
+          fd.valid = 0.0;
+          if (lights[l].kind != NRT_LIGHT_DISTANT) continue;
+          const V4 dw = scale(v4(lights[l].dir[0], lights[l].dir[1], lights[l].dir[2], lights[l].dir[3]), -1.0);
+          const V4 dobj = mulm(ob.w2o, dw);
+          const double da[3] = {dobj.x, dobj.y, dobj.z};
+          fd.valid = makeBasis(da, fd) ? 1.0 : 0.0;
+          if (!(fd.valid > 0)) anyGeneralShadow = true;
+        }
+      }
+      dFrames = up(frames.data(), int64_t(frames.size()), reuse ? dFrames : nullptr);
+    }
+    h.objects = dObjs; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames;
     std::memcpy(h.c2w, desc->camera_to_world, sizeof(h.c2w));
     h.tan_half_fov = std::tan((desc->fov * (kPi / 180.0)) / 2);  // renderer.nim:38; Nim degToRad = d * (PI/180)
     std::memcpy(h.bg, desc->bg_color, sizeof(h.bg));
@@ -173,14 +232,16 @@ struct SceneData {
       const int64_t nf = meshes[objs[moIndex[mo]].mesh].nfaces;
       MoRecs& r = moRecs[mo];
       r.origin = up<float>(nullptr, paddedFaces(nf) * recFloats(FM_ORIGIN), reuse ? oldRecs[mo].origin : nullptr);
+      r.originHot = up<float>(nullptr, paddedFaces(nf) * hotFloats(FM_ORIGIN), reuse ? oldRecs[mo].originHot : nullptr);
       r.dir.assign(size_t(desc->nlights), nullptr);
-      if (nf > 0) {
-        be->compactRecs(nf, BuildRecsOrigin{d, mo}, r.origin, FM_ORIGIN, dRecCount + mo * rs + 1);
-      }
+      r.dirHot.assign(size_t(desc->nlights), nullptr);
+      if (nf > 0 && frameValid(mo, FM_ORIGIN, 0))
+        be->compactRecs(nf, BuildRecsOrigin{d, mo}, r.origin, r.originHot, FM_ORIGIN, dRecCount + mo * rs + 1);
       for (int l = 0; l < desc->nlights; ++l) {
-        if (lights[l].kind != NRT_LIGHT_DISTANT) continue;
+        if (lights[l].kind != NRT_LIGHT_DISTANT || !frameValid(mo, FM_DIR, l)) continue;
         r.dir[l] = up<float>(nullptr, paddedFaces(nf) * recFloats(FM_DIR), reuse ? oldRecs[mo].dir[l] : nullptr);
-        if (nf > 0) be->compactRecs(nf, BuildRecsDir{d, mo, l}, r.dir[l], FM_DIR, dRecCount + mo * rs + 2 + l);
+        r.dirHot[l] = up<float>(nullptr, paddedFaces(nf) * hotFloats(FM_DIR), reuse ? oldRecs[mo].dirHot[l] : nullptr);
+        if (nf > 0) be->compactRecs(nf, BuildRecsDir{d, mo, l}, r.dir[l], r.dirHot[l], FM_DIR, dRecCount + mo * rs + 2 + l);
       }
     }
     be->download(hRecCount.data(), dRecCount, sizeof(uint32_t) * hRecCount.size());
@@ -229,12 +290,14 @@ struct Renderer {
       const int64_t qcap = NR + int64_t(nL) * S, mq = int64_t(std::max(nMO, 1)) * qcap;
       cs.tBest = al<uint64_t>(m); cs.triBest = al<uint32_t>(m);
       cs.qref = al<uint32_t>(mq); cs.qray0 = al<float>(mq * 4); cs.qray1 = al<float>(m * 4); cs.xref = al<uint32_t>(m);
+      cs.qhot0 = al<float>(mq * 4); cs.qhot1 = al<float>(m * 4);
+      cs.preRay = al<uint32_t>(4 * cand); cs.preRec = al<uint32_t>(4 * cand);
       cs.candRef = al<uint32_t>(cand); cs.candTri = al<uint32_t>(cand); cs.candT = al<double>(cand);
       cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * cntStride(nL));
       cs.stats = al<unsigned long long>(ST_COUNT);
       dRows = al<int32_t>(nrows);
     }
-    cs.S = capS; cs.NR = capNR; cs.QCAP = capNR + int64_t(nL) * capS; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.rows = dRows;
+    cs.S = capS; cs.NR = capNR; cs.QCAP = capNR + int64_t(nL) * capS; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.preCap = 4 * capCand; cs.rows = dRows;
   }
 
   // One mesh wave: gate + per mesh object { filter per ray bundle, exact, verify }.
@@ -249,13 +312,19 @@ struct Renderer {
       const DMesh& m = sd.meshes[sd.objs[sd.moIndex[mo]].mesh];
       if (m.nfaces == 0) continue;
       if (!force_exact) {
+        // prefilter (hot) -> refine (float32 sign test) per ray bundle; both feed the candidate list of (wave, mo)
+        auto run = [&](int mode, int l, int b) {
+          be->filter(mode, sd.hotOf(mo, mode, l), sd.recCountOf(mo, mode, l), cs, mo, b, c);
+          be->forEachCounted(c + cntPre(b), cs.preCap,
+                             Refine<typename BE::Atom>{cs, mode, sd.recsOf(mo, mode, l), mo, b, c + CNT_CAND});
+        };
         if (kind == WAVE_PATH) {
-          be->filter(pathMode, sd.recsOf(mo, pathMode, 0), sd.recCountOf(mo, pathMode, 0), cs, mo, 0, c);
+          const int mode = (primary && sd.frameValid(mo, FM_ORIGIN, 0)) ? FM_ORIGIN : FM_GENERAL;
+          run(mode, 0, 0);
         } else {
-          if (sd.anyPointLight) be->filter(FM_GENERAL, sd.recsOf(mo, FM_GENERAL, 0), sd.recCountOf(mo, FM_GENERAL, 0), cs, mo, 0, c);
+          if (sd.anyGeneralShadow) run(FM_GENERAL, 0, 0);
           for (int l = 0; l < nL; ++l)
-            if (sd.lights[l].kind == NRT_LIGHT_DISTANT)
-              be->filter(FM_DIR, sd.recsOf(mo, FM_DIR, l), sd.recCountOf(mo, FM_DIR, l), cs, mo, 1 + l, c);
+            if (sd.lights[l].kind == NRT_LIGHT_DISTANT && sd.frameValid(mo, FM_DIR, l)) run(FM_DIR, l, 1 + l);
         }
       }
       be->forEachCounted(c + CNT_EXACT, cs.NR, ExactMesh{sd.d, fp, cs, kind, mo, c + CNT_EXACT});
@@ -343,9 +412,11 @@ struct Renderer {
             int64_t queued = 0;
             for (int b = 0; b <= nL; ++b) {
               const int64_t q = c[cntQueue(b)];
+              if (c[cntPre(b)] > uint64_t(cs.preCap)) overflow = true;
+              pacc.pre_candidates += c[cntPre(b)];
               if (!q) continue;
               // wave parity: even = path wave (primary for w == 0), odd = shadow wave
-              const int mode = b > 0 ? FM_DIR : ((w & 1) ? FM_GENERAL : (w == 0 ? FM_ORIGIN : FM_GENERAL));
+              const int mode = b > 0 ? FM_DIR : ((w & 1) ? FM_GENERAL : ((w == 0 && sd.frameValid(mo, FM_ORIGIN, 0)) ? FM_ORIGIN : FM_GENERAL));
               const int64_t t = q * int64_t(sd.hostRecCount(mo, mode, b > 0 ? b - 1 : 0));
               pacc.mesh_tests += t; pacc.tests_by_mode[mode] += t;
               queued += q;

@@ -21,6 +21,7 @@ struct LoopBackend {
   struct Atom {
     static void min64(uint64_t* p, uint64_t v) { if (v < *p) *p = v; }
     static void min32(uint32_t* p, uint32_t v) { if (v < *p) *p = v; }
+    static uint32_t add32(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p += v; return o; }
   };
   void* dalloc(size_t b) { return std::calloc(b ? b : 16, 1); }
   void dfree(void* p) { std::free(p); }
@@ -38,18 +39,22 @@ struct LoopBackend {
     for (int64_t i = 0; i < n; ++i) f(i);
     ++launches;
   }
-  template <class F> void compactRecs(int64_t n, const F& f, float* recs, int mode, uint32_t* count) {
-    const int nc = recFloats(mode);
+  template <class F> void compactRecs(int64_t n, const F& f, float* recs, float* hot, int mode, uint32_t* count) {
+    const int nc = recFloats(mode), nh = hotFloats(mode);
     for (int64_t i = 0; i < n; ++i) {
       const RecOut o = f(i);
       if (!o.keep) continue;
       const int64_t r = (*count)++;
       for (int k = 0; k < nc; ++k) recs[recIndex(r, k, nc)] = o.c[k];
+      for (int k = 0; k < nh; ++k) hot[recIndex(r, k, nh)] = o.h[k];
     }
-    float c[16];
+    float c[16], h[4];
     neverHitRecord(mode, c);
-    for (int64_t r = *count; r < paddedFaces(*count); ++r)
+    neverHitHot(mode, h);
+    for (int64_t r = *count; r < paddedFaces(*count); ++r) {
       for (int k = 0; k < nc; ++k) recs[recIndex(r, k, nc)] = c[k];
+      for (int k = 0; k < nh; ++k) hot[recIndex(r, k, nh)] = h[k];
+    }
     ++launches;
   }
   void gate(const Gate& g, int64_t n, int nMO, uint32_t* cnt) {
@@ -65,9 +70,13 @@ struct LoopBackend {
           cs.qref[at] = uint32_t(i);
           float* p0 = cs.qray0 + 4 * at;
           p0[0] = o.fr.ax; p0[1] = o.fr.ay; p0[2] = o.fr.az; p0[3] = o.fr.rr;
+          float* h0 = cs.qhot0 + 4 * at;
+          h0[0] = o.hr.a0; h0[1] = o.hr.a1; h0[2] = o.hr.a2; h0[3] = o.hr.a3;
           if (o.bundle == 0) {
             float* p1 = cs.qray1 + 4 * (int64_t(mo) * cs.NR + q);
             p1[0] = o.fr.mx; p1[1] = o.fr.my; p1[2] = o.fr.mz; p1[3] = 0.f;
+            float* h1 = cs.qhot1 + 4 * (int64_t(mo) * cs.NR + q);
+            h1[0] = o.hr.b0; h1[1] = o.hr.b1; h1[2] = o.hr.b2; h1[3] = 0.f;
           }
         } else if (o.pass) {
           const int64_t q = c[CNT_EXACT]++;
@@ -76,44 +85,29 @@ struct LoopBackend {
       }
     ++launches;
   }
-  // Same thread/ray assignment as k_mesh_filter (FT_THREADS threads x FT_R rays, Rr = max over a thread's rays).
-  void filter(int mode, const float* recs, const uint32_t* count, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
-    const int T = 256, R = 8;
+  // Prefilter: every queued ray of the bundle x every hot record (bounding circle / sphere).
+  void filter(int mode, const float* hot, const uint32_t* count, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
     const uint32_t nq = cnt[cntQueue(b)];
     const int64_t base = queueBase(cs, mo, b);
-    const float* p0 = cs.qray0 + 4 * base;
-    const float* p1 = cs.qray1 + 4 * (int64_t(mo) * cs.NR);
-    const uint32_t* qref = cs.qref + base;
+    const float* h0 = cs.qhot0 + 4 * base;
+    const float* h1 = cs.qhot1 + 4 * (int64_t(mo) * cs.NR);
     const int64_t np = paddedFaces(*count);
-    const int nc = recFloats(mode), idSlot = recSlotId(mode);
-    for (uint32_t rt = 0; rt * T * R < nq; ++rt)
-      for (int tid = 0; tid < T; ++tid) {
-        uint32_t ic[R], ref[R]; float rr = 0.f;
-        bool any = false;
-        for (int r = 0; r < R; ++r) {
-          const uint32_t idx = rt * T * R + r * T + tid;
-          ic[r] = idx < nq ? idx : nq - 1;
-          ref[r] = idx < nq ? qref[ic[r]] : kInvalidRef;
-          rr = std::max(rr, p0[4 * ic[r] + 3]);
-          any |= ref[r] != kInvalidRef;
-        }
-        if (!any) continue;
-        for (int64_t t = 0; t < np; ++t) {
-          float q[16];
-          for (int k = 0; k < nc; ++k) q[k] = recs[recIndex(t, k, nc)];
-          for (int r = 0; r < R; ++r) {
-            if (ref[r] == kInvalidRef) continue;
-            const uint32_t x = filterTest(mode, q, p0 + 4 * ic[r], p1 + 4 * ic[r], rr);
-            ++filter_tests;
-            if (int32_t(x) >= 0) {
-              const uint32_t slot = cnt[CNT_CAND]++;
-              uint32_t tri = uint32_t(t);
-              if (idSlot >= 0) std::memcpy(&tri, &q[idSlot], 4);
-              if (slot < cs.candCap) { cs.candRef[slot] = ref[r]; cs.candTri[slot] = tri; }
-            }
-          }
+    const int nh = hotFloats(mode);
+    for (uint32_t rq = 0; rq < nq; ++rq) {
+      HotRay r;
+      r.a0 = h0[4 * rq]; r.a1 = h0[4 * rq + 1]; r.a2 = h0[4 * rq + 2]; r.a3 = h0[4 * rq + 3];
+      r.b0 = r.b1 = r.b2 = r.b3 = 0.f;
+      if (mode == FM_GENERAL) { r.b0 = h1[4 * rq]; r.b1 = h1[4 * rq + 1]; r.b2 = h1[4 * rq + 2]; }
+      for (int64_t t = 0; t < np; ++t) {
+        float h[4];
+        for (int k = 0; k < nh; ++k) h[k] = hot[recIndex(t, k, nh)];
+        ++filter_tests;
+        if (int32_t(prefilterTest(mode, h, r)) >= 0) {
+          const uint32_t slot = cnt[cntPre(b)]++;
+          if (slot < cs.preCap) { cs.preRay[slot] = rq; cs.preRec[slot] = uint32_t(t); }
         }
       }
+    }
     ++launches;
   }
 };
@@ -126,7 +120,7 @@ extern "C" {
 
 // Whole-frame render through the emulated pipeline (single worker).
 int emu_render(const nrt_scene_desc* desc, const nrt_options* o, int y0, int y1, int step, int max_step, float* fb,
-               nrt_stats* stats, const nrt_aov* aov, int64_t* prof /* 6 values, may be null */) {
+               nrt_stats* stats, const nrt_aov* aov, int64_t* prof /* 7 values, may be null */) {
   if (!desc || !o || !fb) return NRT_ERR_INVALID;
   if (!isPow2(step) || !isPow2(max_step) || max_step < step) return NRT_ERR_UNSUPPORTED;
   LoopBackend be;
@@ -152,7 +146,7 @@ int emu_render(const nrt_scene_desc* desc, const nrt_options* o, int y0, int y1,
   }
   if (prof) {
     prof[0] = rn.prof.mesh_rays; prof[1] = rn.prof.mesh_tests; prof[2] = rn.prof.candidates;
-    prof[3] = rn.prof.exact_rays; prof[4] = be.launches; prof[5] = be.filter_tests;
+    prof[3] = rn.prof.exact_rays; prof[4] = be.launches; prof[5] = be.filter_tests; prof[6] = rn.prof.pre_candidates;
   }
   rn.freeAll();
   sd.destroy();

@@ -38,10 +38,10 @@ def render(scene, opts: api.Options, fb=None, aov=None, step=1, maxStep=1, y0=0,
     fb = fb or api.newFramebuf(opts.width, opts.height)
     co, cs = opts.to_c(), api.nrt_stats()
     ca = aov.to_c() if aov is not None else None
-    prof = (C.c_int64 * 6)()
+    prof = (C.c_int64 * 7)()
     rc = lib().emu_render(desc.ref(), C.byref(co), y0, opts.height if y1 is None else y1, step, maxStep,
                           fb.data.ctypes.data_as(C.c_void_p), C.byref(cs), C.byref(ca) if ca is not None else None, prof)
     if rc != 0:
         raise RuntimeError(f"emu_render failed: {rc}")
-    names = ("mesh_rays", "mesh_tests", "candidates", "exact_rays", "launches", "filter_tests")
+    names = ("mesh_rays", "mesh_tests", "candidates", "exact_rays", "launches", "filter_tests", "pre_candidates")
     return fb, api.Stats.from_c(cs), aov, dict(zip(names, list(prof)))
