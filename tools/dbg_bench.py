@@ -66,3 +66,15 @@ for use_sampler in (False, True, False, True):
     wall=(time.perf_counter()-t0)*1e3
     r = s.stop() if use_sampler else None
     print("bench-like loop sampler", use_sampler, "ms/step dev", ms.value/10, "wall", wall/10, r)
+
+# ---- e2e breakdown: scene update (H2D + record build) vs host-buffer render (D2H) ----
+hp = C.c_void_p(); L.nrt_host_alloc_pinned(W*H*12, C.byref(hp))
+import numpy as np
+pageable = np.zeros(W*H*3, dtype=np.float32)
+for label, target in (("pinned fb", hp), ("pageable fb", pageable.ctypes.data_as(C.c_void_p))):
+    tu=[]; tr=[]
+    for _ in range(8):
+        t0=time.perf_counter(); ds.update(); t1=time.perf_counter()
+        api.check(L.nrt_render(ds.handle, C.byref(co), 0, H, 1, 1, target, C.byref(cs), None), "r"); t2=time.perf_counter()
+        tu.append((t1-t0)*1e3); tr.append((t2-t1)*1e3)
+    print("e2e", label, "update ms", [round(x,2) for x in tu[2:6]], "render ms", [round(x,2) for x in tr[2:6]], "frame", round(ds.profile().total_ms,2))
