@@ -9,6 +9,7 @@
 // computes anything needs a CUDA device and fails with NRT_ERR_NO_DEVICE otherwise.
 
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 
 #include <atomic>
 #include <cstdio>
@@ -184,12 +185,25 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 
+// left-hand side of one prefilter test pair (two records) for one ray: exactly the operations of prefilterTest()
+template <int MODE>
+__device__ __forceinline__ float2 prefilterPair(const float2* h, float a0, float a1, float a2, float b0, float b1, float b2) {
+  if (MODE == FM_GENERAL) {
+    const float2 s = ffma2(h[0], dup2(a0), ffma2(h[1], dup2(a1), fmul2(h[2], dup2(a2))));
+    const float2 tt = ffma2(h[0], dup2(b0), ffma2(h[1], dup2(b1), ffma2(h[2], dup2(b2), h[3])));
+    return ffma2(s, s, tt);
+  }
+  return ffma2(h[0], dup2(a0), ffma2(h[1], dup2(a1), h[2]));
+}
+
+static constexpr int FT_GROUP = 4;   // chunks per work item (double-buffered in shared memory)
+
 template <int MODE>
 __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
   constexpr int R = PreCfg<MODE>::R;
-  constexpr int NH = hotFloats(MODE);      // float2 per record pair
-  constexpr int Q4 = NH;                   // float4 per record QUAD (2 pairs = 4 NH floats... = NH float4)
-  __shared__ __align__(16) float4 tile[(FT_TC / 4) * Q4];
+  constexpr int NH = hotFloats(MODE);      // float2 per record pair == float4 per record quad
+  constexpr int CH4 = (FT_TC / 4) * NH;    // float4 per chunk
+  __shared__ __align__(16) float4 tile[2][CH4];
   __shared__ uint32_t s_item;
   const uint32_t nq = *a.qcount;
   if (nq == 0) return;
@@ -198,17 +212,23 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
   constexpr uint32_t RAYS = FT_THREADS * R;
   const uint32_t nRayTiles = (nq + RAYS - 1) / RAYS;
   const uint32_t nChunks = nrecPadded / FT_TC;
-  const uint32_t nItems = nRayTiles * nChunks;
+  const uint32_t nGroups = (nChunks + FT_GROUP - 1) / FT_GROUP;
+  const uint32_t nItems = nRayTiles * nGroups;
   const int tid = threadIdx.x;
+  // asynchronous global -> shared copy of one chunk (cp.async, 16 bytes per thread)
+  auto stage = [&](uint32_t chunk, int buf) {
+    const float4* src = a.hot + size_t(chunk) * CH4;
+    for (int k = tid; k < CH4; k += FT_THREADS) __pipeline_memcpy_async(&tile[buf][k], src + k, 16);
+    __pipeline_commit();
+  };
   for (;;) {
     if (tid == 0) s_item = atomicAdd(a.tilectr, 1u);
     __syncthreads();
     const uint32_t item = s_item;
     if (item >= nItems) break;
-    const uint32_t rt = item / nChunks, ch = item - rt * nChunks;
-    // stage the chunk (previous readers are past the barrier above only after the trailing barrier below)
-    const float4* src = a.hot + size_t(ch) * (FT_TC / 4) * Q4;
-    for (int k = tid; k < (FT_TC / 4) * Q4; k += FT_THREADS) tile[k] = __ldg(src + k);
+    const uint32_t rt = item / nGroups, gr = item - rt * nGroups;
+    const uint32_t c0 = gr * FT_GROUP, c1 = min(nChunks, c0 + FT_GROUP);
+    stage(c0, 0);
     float ra0[R], ra1[R], ra2[R], ra3[R], rb0[R], rb1[R], rb2[R];
     uint32_t ridx[R];
 #pragma unroll
@@ -223,53 +243,55 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
       } else { rb0[r] = rb1[r] = rb2[r] = 0.f; }
       ridx[r] = idx < nq ? idx : kInvalidRef;
     }
-    __syncthreads();
-    const uint32_t base = ch * FT_TC;
+    for (uint32_t ch = c0; ch < c1; ++ch) {
+      const int buf = int(ch - c0) & 1;
+      __pipeline_wait_prior(0);
+      __syncthreads();                       // chunk `ch` is in tile[buf]; everyone left tile[buf ^ 1]
+      if (ch + 1 < c1) stage(ch + 1, buf ^ 1);
+      const uint32_t base = ch * FT_TC;
+      const float4* tl = tile[buf];
 #pragma unroll 1
-    for (int t = 0; t < FT_TC / 4; ++t) {
-      float2 q[2 * NH];   // two record pairs: q[j * NH + k] = coefficient k of pair j
+      for (int t = 0; t < FT_TC / 4; ++t) {
+        float2 q[2 * NH];   // two record pairs: q[j * NH + k] = coefficient k of pair j
 #pragma unroll
-      for (int c = 0; c < Q4; ++c) {
-        const float4 v4 = tile[t * Q4 + c];
-        q[2 * c] = make_float2(v4.x, v4.y);
-        q[2 * c + 1] = make_float2(v4.z, v4.w);
-      }
-      float2 g[R][2];
-      uint32_t acc = 0xFFFFFFFFu;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float2* h = q + j * NH;
-          if (MODE == FM_GENERAL) {
-            const float2 s = ffma2(h[0], dup2(ra0[r]), ffma2(h[1], dup2(ra1[r]), fmul2(h[2], dup2(ra2[r]))));
-            const float2 tt = ffma2(h[0], dup2(rb0[r]), ffma2(h[1], dup2(rb1[r]), ffma2(h[2], dup2(rb2[r]), fadd2(h[3], dup2(ra3[r])))));
-            g[r][j] = ffma2(s, s, tt);
-          } else {
-            g[r][j] = ffma2(h[0], dup2(ra0[r]), ffma2(h[1], dup2(ra1[r]), fadd2(h[2], dup2(ra2[r]))));
-          }
-          acc &= __float_as_uint(g[r][j].x) & __float_as_uint(g[r][j].y);
+        for (int c = 0; c < NH; ++c) {
+          const float4 v4 = tl[t * NH + c];
+          q[2 * c] = make_float2(v4.x, v4.y);
+          q[2 * c + 1] = make_float2(v4.z, v4.w);
         }
-      }
-      if (int(acc) >= 0) {  // some test has its sign bit clear: rare
+        bool any = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (ridx[r] == kInvalidRef) continue;
+          const float thr = (MODE == FM_GENERAL) ? ra3[r] : ra2[r];
+          const float2 g0 = prefilterPair<MODE>(q, ra0[r], ra1[r], ra2[r], rb0[r], rb1[r], rb2[r]);
+          const float2 g1 = prefilterPair<MODE>(q + NH, ra0[r], ra1[r], ra2[r], rb0[r], rb1[r], rb2[r]);
+          // one compare per ray: max of its four left-hand sides against its threshold (FMNMX3 + FSETP)
+          const float m = fmaxf(fmaxf(g0.x, g0.y), fmaxf(g1.x, g1.y));
+          any = any || (m >= thr);
+        }
+        if (any) {  // some test passed (rare): re-evaluate and emit
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            if (int(__float_as_uint(g[r][j].x)) >= 0) {
-              const uint32_t slot = atomicAdd(a.prectr, 1u);
-              if (slot < a.preCap) { a.preRay[slot] = ridx[r]; a.preRec[slot] = base + 4 * t + 2 * j; }
-            }
-            if (int(__float_as_uint(g[r][j].y)) >= 0) {
-              const uint32_t slot = atomicAdd(a.prectr, 1u);
-              if (slot < a.preCap) { a.preRay[slot] = ridx[r]; a.preRec[slot] = base + 4 * t + 2 * j + 1; }
+          for (int r = 0; r < R; ++r) {
+            if (ridx[r] == kInvalidRef) continue;
+#pragma unroll
+            const float thr = (MODE == FM_GENERAL) ? ra3[r] : ra2[r];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float2 g = prefilterPair<MODE>(q + j * NH, ra0[r], ra1[r], ra2[r], rb0[r], rb1[r], rb2[r]);
+              if (g.x >= thr) {
+                const uint32_t slot = atomicAdd(a.prectr, 1u);
+                if (slot < a.preCap) { a.preRay[slot] = ridx[r]; a.preRec[slot] = base + 4 * t + 2 * j; }
+              }
+              if (g.y >= thr) {
+                const uint32_t slot = atomicAdd(a.prectr, 1u);
+                if (slot < a.preCap) { a.preRay[slot] = ridx[r]; a.preRec[slot] = base + 4 * t + 2 * j + 1; }
+              }
             }
           }
         }
       }
     }
-    __syncthreads();   // everyone is done with `tile` and `s_item` before the next item overwrites them
+    __syncthreads();   // everyone is done with both tiles and `s_item` before the next item
   }
 }
 
@@ -311,7 +333,7 @@ struct CudaBackend {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> filterEvents;
   size_t filterUsed = 0;
   std::vector<int> filterModes;
-  int gridPerSm = 4;   // resident prefilter CTAs per SM (NRT_PREFILTER_CTAS_PER_SM)
+  int gridPerSm = 3;   // resident prefilter CTAs per SM (NRT_PREFILTER_CTAS_PER_SM)
 
   struct Atom {
     static __device__ __forceinline__ void min64(uint64_t* p, uint64_t v) {

@@ -67,7 +67,7 @@ struct DObject {
   int32_t kind;
   int32_t mesh;        // index into DScene.meshes, or -1
   int32_t mesh_obj;    // index among the scene's MESH objects, or -1
-  int32_t _pad;
+  int32_t xlate_only;  // worldToObject is exactly [I | t] (all reference scenes): see toObject()
   double o2w[16];
   double w2o[16];
   double radius;
@@ -144,10 +144,10 @@ NRT_HD double aabbIntersect(const double* bmin, const double* bmax, const Ray& r
 }
 
 // geom.nim:215-237 ((x / 2) * a, min(t1, t2) even if negative)
-NRT_HD double sphereIntersect(double radius, const Ray& r) {
-  const double a = r.dir.x * r.dir.x + r.dir.y * r.dir.y + r.dir.z * r.dir.z;
-  const double b = 2 * (r.dir.x * r.orig.x + r.dir.y * r.orig.y + r.dir.z * r.orig.z);
-  const double c = r.orig.x * r.orig.x + r.orig.y * r.orig.y + r.orig.z * r.orig.z - radius * radius;
+NRT_HD double sphereIntersect(double radius, V4 orig, V4 dir) {
+  const double a = dir.x * dir.x + dir.y * dir.y + dir.z * dir.z;
+  const double b = 2 * (dir.x * orig.x + dir.y * orig.y + dir.z * orig.z);
+  const double c = orig.x * orig.x + orig.y * orig.y + orig.z * orig.z - radius * radius;
   const double delta = b * b - 4 * a * c;
   if (delta >= 0.0) {
     const double t1 = (-b - signd(b) * sqrt(delta)) / 2 * a;
@@ -158,11 +158,29 @@ NRT_HD double sphereIntersect(double radius, const Ray& r) {
 }
 
 // geom.nim:240-248
-NRT_HD double planeIntersect(const Ray& r) {
+NRT_HD double planeIntersect(V4 orig, V4 dir) {
   const V4 n = v4(0.0, 1.0, 0.0, 0.0);
-  const double denom = dot(n, r.dir);
-  if (fabs(denom) > 1e-6) return -dot(r.orig, n) / denom;
+  const double denom = dot(n, dir);
+  if (fabs(denom) > 1e-6) return -dot(orig, n) / denom;
   return NRT_NEG_INF;
+}
+
+// worldToObject * (orig, dir) of trace() (renderer.nim:54-55).  For a matrix that is exactly
+// [I | t] the glm product ((1*x + 0*y) + 0*z) + t*w equals x + t (points) or x (vectors) bit for
+// bit whenever x, y, z are finite and non-zero (the zero products vanish and one rounding
+// remains), so the 56-flop product is skipped; any other input takes the literal product.
+NRT_HD bool nzFinite3(V4 v) {
+  const double big = 1.7976931348623157e308;
+  return (fabs(v.x) > 0) && (fabs(v.x) <= big) && (fabs(v.y) > 0) && (fabs(v.y) <= big) && (fabs(v.z) > 0) && (fabs(v.z) <= big);
+}
+NRT_HD void toObject(const DObject& ob, V4 o, V4 d, V4& oo, V4& dd) {
+  if (ob.xlate_only && o.w == 1.0 && d.w == 0.0 && nzFinite3(o) && nzFinite3(d)) {
+    oo = v4(o.x + ob.w2o[12], o.y + ob.w2o[13], o.z + ob.w2o[14], 1.0);
+    dd = v4(d.x, d.y, d.z, 0.0);
+  } else {
+    oo = mulm(ob.w2o, o);
+    dd = mulm(ob.w2o, d);
+  }
 }
 
 // geom.nim:283-336 rayTriangleIntersectFast, float64, exact operation order

@@ -234,9 +234,9 @@ NRT_HD uint32_t filterTest(int mode, const float* q, const float* a, const float
 //           direction dh and the point p0 of the line closest to the mesh centre (p0 . dh = 0):
 //           dist^2 = |c - p0|^2 - (c . dh)^2 <= r^2
 // Expanded so that every term is a product of one per-triangle and one per-ray quantity:
-//   2-D:     g = (r^2 - |c|^2) + (-|p|^2) + 2c.p                      1 FADD + 2 FFMA
-//   GENERAL: g = (r^2 - |c|^2) + (-|p0|^2) + 2c.p0 + (c.dh)^2         1 FADD + 7 FFMA (1 FMUL)
-// and the candidate condition is g >= 0 (one sign bit).  Margins that bound the float32
+//   2-D:     (r^2 - |c|^2) + 2c.p                 >=  |p|^2           2 FFMA + 1 compare
+//   GENERAL: (r^2 - |c|^2) + 2c.p0 + (c.dh)^2     >=  |p0|^2          1 FMUL + 6 FFMA + 1 compare
+// (left side per (triangle, ray), right side a per-ray threshold).  Margins that bound the float32
 // evaluation error are folded into the two additive constants at build time:
 //   per triangle  mt = 8u (2|c|^2 + |r^2 - |c|^2|)   (GENERAL: 32u|c|^2 + 8u|K0|)
 //   per ray       mr = 16u |p|^2 (+ float64 slack)
@@ -246,7 +246,7 @@ NRT_HD uint32_t filterTest(int mode, const float* q, const float* a, const float
 
 // floats per hot record (pair-interleaved like the full records)
 NRT_HD constexpr int hotFloats(int mode) { return mode == FM_GENERAL ? 4 : 3; }
-NRT_HD constexpr int prefilterFlops(int mode) { return mode == FM_GENERAL ? 16 : 5; }
+NRT_HD constexpr int prefilterFlops(int mode) { return mode == FM_GENERAL ? 13 : 4; }
 
 // Shared frame of a ray bundle (object space), built on the host in float64.
 struct BundleFrame {
@@ -383,15 +383,16 @@ NRT_HD bool makeHotRay(int mode, const BundleFrame& fr, const Ray& r, HotRay& h)
     const double p2 = x * x + y * y;
     if (!(p2 < big)) return false;
     const double q = -p2 + 16.0 * kFilterU * p2 + 1e-14 * (1.0 + p2);
-    h.a0 = (float)x; h.a1 = (float)y; h.a2 = roundUpSigned(q);
+    h.a0 = (float)x; h.a1 = (float)y; h.a2 = -roundUpSigned(q);   // threshold T = -q, rounded down
     return true;
   }
   if (!(oi < big)) return false;
   if (mode == FM_DIR) {
     const double x = dot3(o, fr.b1), y = dot3(o, fr.b2);
     const double p2 = x * x + y * y;
+    if (!(p2 < 1e29)) return false;
     const double q = -p2 + 16.0 * kFilterU * p2 + 64.0 * kEps64 * oi * oi;
-    h.a0 = (float)x; h.a1 = (float)y; h.a2 = roundUpSigned(q);
+    h.a0 = (float)x; h.a1 = (float)y; h.a2 = -roundUpSigned(q);   // threshold T = -q, rounded down
     return true;
   }
   const double dl2 = dot3(d, d);
@@ -401,21 +402,24 @@ NRT_HD bool makeHotRay(int mode, const BundleFrame& fr, const Ray& r, HotRay& h)
   const double s = dot3(o, dh);
   const double p0[3] = {o[0] - s * dh[0], o[1] - s * dh[1], o[2] - s * dh[2]};
   const double p2 = dot3(p0, p0);
+  if (!(p2 < 1e29)) return false;
   const double q = -p2 + 16.0 * kFilterU * p2 + 64.0 * kEps64 * oi * oi;
-  h.a0 = (float)dh[0]; h.a1 = (float)dh[1]; h.a2 = (float)dh[2]; h.a3 = roundUpSigned(q);
+  h.a0 = (float)dh[0]; h.a1 = (float)dh[1]; h.a2 = (float)dh[2]; h.a3 = -roundUpSigned(q);   // threshold T = -q
   h.b0 = (float)(2.0 * p0[0]); h.b1 = (float)(2.0 * p0[1]); h.b2 = (float)(2.0 * p0[2]);
   return true;
 }
 
 // Scalar statement of one prefilter test (the CUDA kernel evaluates two records per FFMA2 with
-// exactly these operations per component).  Sign bit of the result clear <=> pre-candidate.
-NRT_HD uint32_t prefilterTest(int mode, const float* h, const HotRay& r) {
+// exactly these operations per component).  The per-ray constant is kept on the other side of
+// the comparison (threshold T = -q, stored in the ray) instead of being added: one float32
+// operation less per test and no extra rounding.  true <=> pre-candidate.
+NRT_HD bool prefilterTest(int mode, const float* h, const HotRay& r) {
   if (mode == FM_GENERAL) {
     const float s = fmaf(h[0], r.a0, fmaf(h[1], r.a1, h[2] * r.a2));
-    const float t = fmaf(h[0], r.b0, fmaf(h[1], r.b1, fmaf(h[2], r.b2, h[3] + r.a3)));
-    return fbits(fmaf(s, s, t));
+    const float t = fmaf(h[0], r.b0, fmaf(h[1], r.b1, fmaf(h[2], r.b2, h[3])));
+    return fmaf(s, s, t) >= r.a3;
   }
-  return fbits(fmaf(h[0], r.a0, fmaf(h[1], r.a1, h[2] + r.a2)));
+  return fmaf(h[0], r.a0, fmaf(h[1], r.a1, h[2])) >= r.a2;
 }
 
 // executed float32 flops per test (FFMA = 2): reported next to the roofline

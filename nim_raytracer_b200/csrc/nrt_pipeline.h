@@ -237,7 +237,9 @@ NRT_HD bool waveRay(const DScene& sc, const FrameParams& fp, const ChunkState& c
 }
 
 NRT_HD Ray objectRay(const DObject& ob, V4 o, V4 d) {  // renderer.nim:54-55
-  return initRay(mulm(ob.w2o, o), mulm(ob.w2o, d));
+  V4 oo, dd;
+  toObject(ob, o, d, oo, dd);
+  return initRay(oo, dd);
 }
 
 // ---- gate: TriangleMesh.intersect's AABB test (geom.nim:340) per (ray, mesh object)
@@ -359,10 +361,13 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
       t = bitsd(cs.tBest[int64_t(ob.mesh_obj) * cs.NR + wi]);
       tri = cs.triBest[int64_t(ob.mesh_obj) * cs.NR + wi];
     } else {
-      const Ray ro = objectRay(ob, o, d);
-      t = ob.kind == GEOM_SPHERE ? sphereIntersect(ob.radius, ro)
-          : ob.kind == GEOM_PLANE ? planeIntersect(ro)
-          : ob.kind == GEOM_BOX ? aabbIntersect(ob.bmin, ob.bmax, ro) : NRT_NEG_INF;
+      V4 oo, dd;
+      toObject(ob, o, d, oo, dd);
+      // initRay's 1/dir (geom.nim:42-47) is only read by the AABB test: built for boxes only
+      if (ob.kind == GEOM_SPHERE) t = sphereIntersect(ob.radius, oo, dd);
+      else if (ob.kind == GEOM_PLANE) t = planeIntersect(oo, dd);
+      else if (ob.kind == GEOM_BOX) t = aabbIntersect(ob.bmin, ob.bmax, initRay(oo, dd));
+      else t = NRT_NEG_INF;
     }
     r.tests++;
     if (t >= 0 && t < r.t) { r.t = t; r.obj = i; r.tri = tri; r.hits++; }

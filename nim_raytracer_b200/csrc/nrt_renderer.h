@@ -148,6 +148,17 @@ struct SceneData {
       DObject& dob = objs[i];
       if (o.kind < 0 || o.kind > 3) { err = "bad geometry kind"; return NRT_ERR_INVALID; }
       dob.kind = o.kind; dob.mesh = -1; dob.mesh_obj = -1;
+      {  // exactly [I | t] with finite t?
+        const double* w = o.world_to_object;
+        bool x = true;
+        for (int c = 0; c < 4 && x; ++c)
+          for (int r = 0; r < 4 && x; ++r) {
+            const double v = w[c * 4 + r];
+            if (c < 3 || r == 3) x = (v == ((c == r) ? 1.0 : 0.0));
+            else x = std::isfinite(v);
+          }
+        dob.xlate_only = x ? 1 : 0;
+      }
       std::memcpy(dob.o2w, o.object_to_world, sizeof(dob.o2w));
       std::memcpy(dob.w2o, o.world_to_object, sizeof(dob.w2o));
       dob.radius = o.radius;

@@ -172,3 +172,31 @@ def stress(ntri: int = 1_000_000, nspheres: int = 10_000, seed: int = 20161018) 
                               Material(albedo=vec3(s[i, 4], s[i, 5], s[i, 6]), reflection=refl)))
     return Scene(objects=objects, lights=_bunny_lights(), fov=50.0, cameraToWorld=_camera(0.0, 5.5, 1.5),
                  bgColor=vec3(0.01, 0.03, 0.05))
+
+
+def transformed_objects(stride: int = 16) -> Scene:
+    """Build-defined parity scene: every geometry kind under a NON-translation objectToWorld
+    (rotation + non-uniform scale), so worldToObject*dir is not unit length (the `(x/2)*a` sphere
+    quirk of geom.nim:232 matters) and the literal glm mat*vec path of trace() (renderer.nim:54-55)
+    is exercised; plus a point light (GENERAL shadow bundle) and a mirror."""
+    def xf(t, axis, deg, s):
+        return L.scale(L.rotate(L.translate(L.mat4(1.0), vec3(*t)), axis, L.deg_to_rad(deg)), s)
+    mesh = trianglesToMesh(bunny_triangles(stride=stride))
+    mesh.objectToWorld = xf((1.5, 0.2, -11.0), L.Y_AXIS, 35.0, (0.9, 1.2, 0.8))
+    mesh.worldToObject = L.inverse(mesh.objectToWorld)
+    objects = [
+        Object("mesh", mesh, Material(albedo=vec3(0.6, 0.9, 0.2), reflection=0.3)),
+        Object("ground", initPlane(objectToWorld=xf((0.0, -0.2, 0.0), L.Z_AXIS, 3.0, (1.0, 1.0, 1.0))),
+               Material(albedo=vec3(0.4))),
+        Object("ellipsoid", initSphere(r=1.0, objectToWorld=xf((-3.0, 1.5, -9.0), L.X_AXIS, 20.0, (1.5, 0.7, 1.1))),
+               Material(albedo=vec3(0.9, 0.3, 0.2), reflection=0.6)),
+        Object("box", initBox(objectToWorld=xf((3.5, 1.0, -13.0), L.Y_AXIS, 30.0, (1.0, 1.4, 0.6)),
+                              vmin=vec(-1.0, -1.0, -1.0), vmax=vec(1.0, 1.0, 1.0)),
+               Material(albedo=vec3(0.2, 0.4, 0.9))),
+    ]
+    lights = [
+        PointLight(color=vec3(1.0, 0.9, 0.8), intensity=2500.0, pos=point(2.0, 7.0, -6.0)),
+        DistantLight(color=vec3(0.4, 0.5, 0.7), intensity=1.5, dir=L.normalize(vec(-1.0, -1.0, -0.6))),
+    ]
+    return Scene(objects=objects, lights=lights, fov=55.0, cameraToWorld=_camera(0.5, 4.5, 2.0, -10.0),
+                 bgColor=vec3(0.05, 0.06, 0.1))

@@ -102,7 +102,7 @@ struct LoopBackend {
         float h[4];
         for (int k = 0; k < nh; ++k) h[k] = hot[recIndex(t, k, nh)];
         ++filter_tests;
-        if (int32_t(prefilterTest(mode, h, r)) >= 0) {
+        if (prefilterTest(mode, h, r)) {
           const uint32_t slot = cnt[cntPre(b)]++;
           if (slot < cs.preCap) { cs.preRay[slot] = rq; cs.preRec[slot] = uint32_t(t); }
         }

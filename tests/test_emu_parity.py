@@ -96,6 +96,14 @@ def test_filter_is_conservative_on_random_soup(oracle_mod):
     check(sc, api.Options(120, 68), oracle_mod)
 
 
+def test_general_transforms_point_light_mirror(oracle_mod):
+    # rotation + non-uniform scale on every geometry kind: the literal mat*vec path, non-unit object-space
+    # directions, GENERAL-mode shadow rays (point light) and reflection rays hitting a mesh
+    prof = check(scenes.transformed_objects(), api.Options(120, 68), oracle_mod)
+    assert prof["mesh_rays"] > 500 and prof["exact_rays"] == 0
+    check(scenes.transformed_objects(stride=64), api.Options(64, 36, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
+
+
 def test_degenerate_meshes(oracle_mod):
     from nim_raytracer_b200 import loaders, linalg as L
     # zero-area and needle triangles, duplicated coplanar faces (first index must win)

@@ -90,6 +90,12 @@ def test_jittered_kinds(oracle_mod, kind):
     assert_parity(scenes.spheres_reflection(), o, oracle_mod)
 
 
+def test_general_transforms_point_light_mirror(oracle_mod):
+    # every geometry kind under rotation + non-uniform scale, point light, mirror (GENERAL bundles)
+    assert_parity(scenes.transformed_objects(), api.Options(240, 135), oracle_mod)
+    assert_parity(scenes.transformed_objects(stride=4), api.Options(160, 90, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
+
+
 def test_progressive_refinement(oracle_mod):
     # gui.nim:113-122,254-257: step halves from maxStep to 1; the result is the 1-step frame
     sc, o = scenes.bunny(stride=16), api.Options(128, 72)
