@@ -62,6 +62,30 @@ __global__ void __launch_bounds__(kBlock) k_for_each_stats(F f, int64_t n, unsig
   if (threadIdx.x <= ST_CONT && sh[threadIdx.x]) atomicAdd(&stats[threadIdx.x], sh[threadIdx.x]);
 }
 
+// Same over [0, *count) with a device-resident count (persistent grid, no host sync).
+template <class F>
+__global__ void __launch_bounds__(kBlock) k_for_each_stats_counted(F f, const uint32_t* count, unsigned long long* stats) {
+  const int64_t n = *count;
+  StatDelta d = zeroStats();
+  for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
+    const StatDelta e = f(i);
+#pragma unroll
+    for (int k = 0; k <= ST_CONT; ++k) d.v[k] += e.v[k];
+  }
+  __shared__ unsigned long long sh[ST_COUNT];
+  if (threadIdx.x < ST_COUNT) sh[threadIdx.x] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k <= ST_CONT; ++k) {
+    unsigned long long v = d.v[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x <= ST_CONT && sh[threadIdx.x]) atomicAdd(&stats[threadIdx.x], sh[threadIdx.x]);
+}
+
 // Elements [0, min(*count, cap)) with a device-resident count (no host sync).
 template <class F>
 __global__ void __launch_bounds__(kBlock) k_for_each_counted(F f, const uint32_t* count, int64_t cap) {
@@ -72,12 +96,14 @@ __global__ void __launch_bounds__(kBlock) k_for_each_counted(F f, const uint32_t
 
 // AABB gate + warp-ballot compaction of the rays that enter each mesh's box, one queue
 // per ray bundle (0 = arbitrary / shared-origin rays, 1 + l = shadow rays of DistantLight l).
-__global__ void __launch_bounds__(kBlock) k_gate(Gate g, int64_t n, int nMO, uint32_t* cnt) {
-  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+__global__ void __launch_bounds__(kBlock) k_gate(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO, uint32_t* cnt) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
   const ChunkState& cs = g.cs;
   const int nB = 1 + cs.nL, cst = cntStride(cs.nL);
+  const int64_t n = count ? int64_t(*count) * mult : nHost;
+  const int64_t nPad = (n + 31) / 32 * 32;   // whole warps take part in the ballots
+  for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < nPad; i += int64_t(gridDim.x) * kBlock)
   for (int mo = 0; mo < nMO; ++mo) {
     const GateOut o = g(i, mo);
     uint32_t* c = cnt + mo * cst;
@@ -94,7 +120,7 @@ __global__ void __launch_bounds__(kBlock) k_gate(Gate g, int64_t n, int nMO, uin
         if (mine) {
           const int64_t q = base + __popc(fm & lt);
           const int64_t at = queueBase(cs, mo, b) + q;
-          cs.qref[at] = uint32_t(i);
+          cs.qref[at] = o.wi;
           reinterpret_cast<float4*>(cs.qray0)[at] = make_float4(o.fr.ax, o.fr.ay, o.fr.az, o.fr.rr);
           reinterpret_cast<float4*>(cs.qhot0)[at] = make_float4(o.hr.a0, o.hr.a1, o.hr.a2, o.hr.a3);
           if (b == 0) {
@@ -110,7 +136,7 @@ __global__ void __launch_bounds__(kBlock) k_gate(Gate g, int64_t n, int nMO, uin
       uint32_t base = 0;
       if (int(lane) == leader) base = atomicAdd(&c[CNT_EXACT], uint32_t(__popc(xm)));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (toExact) cs.xref[int64_t(mo) * cs.NR + base + __popc(xm & lt)] = uint32_t(i);
+      if (toExact) cs.xref[int64_t(mo) * cs.NR + base + __popc(xm & lt)] = o.wi;
     }
   }
 }
@@ -163,9 +189,8 @@ __global__ void __launch_bounds__(kBlock) k_pad_recs(float* recs, float* hot, co
 // memory in 16-byte vectors and read back as warp-broadcast LDS.128; each thread keeps R rays
 // in registers.  Survivors (sign bit of g clear) are appended to the pre-candidate list.
 static constexpr int FT_THREADS = 256;
-static constexpr int FT_TC = 256;     // records per shared-memory chunk == records per work item
+static constexpr int FT_TC = 256;     // records per shared-memory chunk
 static_assert(kRecPad % FT_TC == 0, "record padding must cover whole shared-memory chunks");
-template <int MODE> struct PreCfg { static constexpr int R = (MODE == FM_GENERAL) ? 4 : 8; };
 
 struct PreArgs {
   const float4* hot;        // pair-interleaved hot records, padded to a multiple of kRecPad
@@ -178,6 +203,7 @@ struct PreArgs {
   uint32_t* preRay;
   uint32_t* preRec;
   uint32_t preCap;
+  uint32_t group;           // chunks per work item (double-buffered in shared memory)
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
@@ -196,11 +222,9 @@ __device__ __forceinline__ float2 prefilterPair(const float2* h, float a0, float
   return ffma2(h[0], dup2(a0), ffma2(h[1], dup2(a1), h[2]));
 }
 
-static constexpr int FT_GROUP = 4;   // chunks per work item (double-buffered in shared memory)
 
-template <int MODE>
+template <int MODE, int R, int U>
 __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
-  constexpr int R = PreCfg<MODE>::R;
   constexpr int NH = hotFloats(MODE);      // float2 per record pair == float4 per record quad
   constexpr int CH4 = (FT_TC / 4) * NH;    // float4 per chunk
   __shared__ __align__(16) float4 tile[2][CH4];
@@ -212,7 +236,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
   constexpr uint32_t RAYS = FT_THREADS * R;
   const uint32_t nRayTiles = (nq + RAYS - 1) / RAYS;
   const uint32_t nChunks = nrecPadded / FT_TC;
-  const uint32_t nGroups = (nChunks + FT_GROUP - 1) / FT_GROUP;
+  const uint32_t nGroups = (nChunks + a.group - 1) / a.group;
   const uint32_t nItems = nRayTiles * nGroups;
   const int tid = threadIdx.x;
   // asynchronous global -> shared copy of one chunk (cp.async, 16 bytes per thread)
@@ -227,7 +251,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
     const uint32_t item = s_item;
     if (item >= nItems) break;
     const uint32_t rt = item / nGroups, gr = item - rt * nGroups;
-    const uint32_t c0 = gr * FT_GROUP, c1 = min(nChunks, c0 + FT_GROUP);
+    const uint32_t c0 = gr * a.group, c1 = min(nChunks, c0 + a.group);
     stage(c0, 0);
     float ra0[R], ra1[R], ra2[R], ra3[R], rb0[R], rb1[R], rb2[R];
     uint32_t ridx[R];
@@ -250,7 +274,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
       if (ch + 1 < c1) stage(ch + 1, buf ^ 1);
       const uint32_t base = ch * FT_TC;
       const float4* tl = tile[buf];
-#pragma unroll 1
+#pragma unroll U
       for (int t = 0; t < FT_TC / 4; ++t) {
         float2 q[2 * NH];   // two record pairs: q[j * NH + k] = coefficient k of pair j
 #pragma unroll
@@ -273,7 +297,6 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if (ridx[r] == kInvalidRef) continue;
-#pragma unroll
             const float thr = (MODE == FM_GENERAL) ? ra3[r] : ra2[r];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -334,6 +357,8 @@ struct CudaBackend {
   size_t filterUsed = 0;
   std::vector<int> filterModes;
   int gridPerSm = 3;   // resident prefilter CTAs per SM (NRT_PREFILTER_CTAS_PER_SM)
+  int gridGeneral = 2;
+  int chunkGroup = 1;  // NRT_PREFILTER_GROUP: 256-record chunks per work item (small items balance best)
 
   struct Atom {
     static __device__ __forceinline__ void min64(uint64_t* p, uint64_t v) {
@@ -366,10 +391,14 @@ struct CudaBackend {
     k_for_each<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
-  template <class F> void forEachStats(int64_t n, const F& f, unsigned long long* stats) {
-    if (n <= 0) return;
+  // over [0, n) (count == nullptr) or [0, *count) with the count resident on the device
+  template <class F> void forEachStats(const uint32_t* count, int64_t n, const F& f, unsigned long long* stats) {
     use();
-    k_for_each_stats<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, stats);
+    if (count) k_for_each_stats_counted<F><<<unsigned(sms * 8), kBlock, 0, stream>>>(f, count, stats);
+    else {
+      if (n <= 0) return;
+      k_for_each_stats<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, stats);
+    }
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   template <class F> void forEachCounted(const uint32_t* count, int64_t cap, const F& f) {
@@ -377,9 +406,11 @@ struct CudaBackend {
     k_for_each_counted<F><<<unsigned(sms * 8), kBlock, 0, stream>>>(f, count, cap);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
-  void gate(const Gate& g, int64_t n, int nMO, uint32_t* cnt) {
+  void gate(const Gate& g, const uint32_t* count, int64_t n, int mult, int nMO, uint32_t* cnt) {
     use();
-    k_gate<<<blocksFor(n), kBlock, 0, stream>>>(g, n, nMO, cnt);
+    const unsigned grid = count ? unsigned(sms * 8) : blocksFor(n);
+    if (!count && n <= 0) return;
+    k_gate<<<grid, kBlock, 0, stream>>>(g, count, n, mult, nMO, cnt);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   template <class F> void compactRecs(int64_t n, const F& f, float* recs, float* hot, int mode, uint32_t* count) {
@@ -407,6 +438,7 @@ struct CudaBackend {
     a.prectr = cnt + cntPre(b);
     a.preRay = cs.preRay; a.preRec = cs.preRec;
     a.preCap = uint32_t(std::min<int64_t>(cs.preCap, 0xFFFFFFFFll));
+    a.group = uint32_t(chunkGroup);
     if (filterUsed == filterEvents.size()) {
       cudaEvent_t e0, e1;
       NRT_CUDA(cudaEventCreate(&e0)); NRT_CUDA(cudaEventCreate(&e1));
@@ -416,9 +448,10 @@ struct CudaBackend {
     auto& ev = filterEvents[filterUsed];
     filterModes[filterUsed++] = mode;
     NRT_CUDA(cudaEventRecord(ev.first, stream));
-    if (mode == FM_GENERAL) k_mesh_prefilter<FM_GENERAL><<<unsigned(sms * gridPerSm), FT_THREADS, 0, stream>>>(a);
-    else if (mode == FM_ORIGIN) k_mesh_prefilter<FM_ORIGIN><<<unsigned(sms * gridPerSm), FT_THREADS, 0, stream>>>(a);
-    else k_mesh_prefilter<FM_DIR><<<unsigned(sms * gridPerSm), FT_THREADS, 0, stream>>>(a);
+    // tuned on B200 (tools/frame_breakdown.py): 2-D bundles 8 rays/thread, 3 CTAs/SM; GENERAL 4 rays/thread, 2 CTAs/SM
+    if (mode == FM_GENERAL) k_mesh_prefilter<FM_GENERAL, 4, 2><<<unsigned(sms * gridGeneral), FT_THREADS, 0, stream>>>(a);
+    else if (mode == FM_ORIGIN) k_mesh_prefilter<FM_ORIGIN, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, 0, stream>>>(a);
+    else k_mesh_prefilter<FM_DIR, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, 0, stream>>>(a);
     NRT_CUDA(cudaGetLastError()); ++launches;
     NRT_CUDA(cudaEventRecord(ev.second, stream));
   }
@@ -490,6 +523,7 @@ static int initLocked(int ngpu, const int* ids) {
       d->be.device = id;
       d->be.sms = p.multiProcessorCount;
       if (const char* e = std::getenv("NRT_PREFILTER_CTAS_PER_SM")) d->be.gridPerSm = std::max(1, std::atoi(e));
+      if (const char* e = std::getenv("NRT_PREFILTER_GROUP")) d->be.chunkGroup = std::max(1, std::atoi(e));
       NRT_CUDA(cudaSetDevice(id));
       NRT_CUDA(cudaStreamCreateWithFlags(&d->be.stream, cudaStreamNonBlocking));
       NRT_CUDA(cudaEventCreate(&d->ev0)); NRT_CUDA(cudaEventCreate(&d->ev1));

@@ -51,7 +51,8 @@ NRT_HD constexpr int recSlotId(int mode) { return mode == FM_GENERAL ? -1 : (mod
 // floats per queued ray (always stored as float4 planes): GENERAL 8, ORIGIN/DIR 4
 NRT_HD constexpr int rayPlanes(int mode) { return mode == FM_GENERAL ? 2 : 1; }
 
-// Record lists are padded to a multiple of kRecPad with never-hit records (S = -1 => Eb < 0).
+// Record lists are padded to a multiple of kRecPad (the prefilter's shared-memory chunk) with
+// never-hit records (S = -1 => Eb < 0).
 static constexpr int64_t kRecPad = 256;
 NRT_HD int64_t paddedFaces(int64_t nfaces) { return (nfaces + kRecPad - 1) / kRecPad * kRecPad; }
 NRT_HD int64_t recIndex(int64_t r, int k, int nc) { return ((r >> 1) * nc + k) * 2 + (r & 1); }

@@ -85,6 +85,8 @@ struct ChunkState {
   uint32_t* candTri; // candCap
   double* candT;     // candCap
   uint32_t* counters;  // maxWaves*nMO*cntStride(nL)
+  uint32_t* alist;     // 2*S: compacted sample indices of the continuing paths (ping-pong per bounce)
+  uint32_t* acount;    // per bounce: entries of the list consumed by that bounce
   unsigned long long* stats;  // ST_COUNT
   // pixel list of this worker
   const int32_t* rows; // device array of row indices
@@ -96,6 +98,12 @@ struct ChunkState {
   int32_t* aovTri;
   double* aovT;
 };
+
+// The samples a wave works on: all `n` samples of the chunk (bounce 0), or the compacted list of
+// the samples whose path continued (written by Resolve of the previous bounce, count on the device).
+struct ActiveSet { const uint32_t* list; const uint32_t* count; int64_t n; };
+NRT_HD int64_t activeN(const ActiveSet& a) { return a.list ? int64_t(*a.count) : a.n; }
+NRT_HD int64_t sampleOf(const ActiveSet& a, int64_t i) { return a.list ? int64_t(a.list[i]) : i; }
 
 NRT_HD int64_t queueBase(const ChunkState& cs, int mo, int b) {
   return int64_t(mo) * cs.QCAP + (b == 0 ? 0 : cs.NR + int64_t(b - 1) * cs.S);
@@ -243,15 +251,29 @@ NRT_HD Ray objectRay(const DObject& ob, V4 o, V4 d) {  // renderer.nim:54-55
 }
 
 // ---- gate: TriangleMesh.intersect's AABB test (geom.nim:340) per (ray, mesh object)
-struct GateOut { bool pass, safe; int bundle; FilterRay fr; HotRay hr; };
+struct GateOut { bool pass, safe; int bundle; uint32_t wi; FilterRay fr; HotRay hr; };
 struct Gate {
-  const DScene* sc; FrameParams fp; ChunkState cs; int kind; int64_t n; int force_exact;
+  const DScene* sc; FrameParams fp; ChunkState cs; int kind; ActiveSet act; int force_exact;
   int path_mode;   // FM_ORIGIN for the primary wave (all rays share the camera origin), else FM_GENERAL
-  NRT_HD GateOut operator()(int64_t i, int mo) const {
-    GateOut g; g.pass = false; g.safe = false; g.bundle = 0;
+  // i-th ray of the wave: PATH = i-th active sample; SHADOW = (active sample i / nL, light i % nL)
+  NRT_HD GateOut operator()(int64_t idx, int mo) const {
+    GateOut g; g.pass = false; g.safe = false; g.bundle = 0; g.wi = kInvalidRef;
     V4 o, d;
-    const bool valid = (i < n) && waveRay(*sc, fp, cs, kind, i, o, d);
+    const int64_t nS = activeN(act);
+    int64_t i;
+    int lsh = 0;
+    if (kind == WAVE_SHADOW) {
+      if (idx >= nS * cs.nL) return g;
+      const int64_t si = idx / cs.nL;
+      lsh = int(idx - si * cs.nL);
+      i = sampleOf(act, si) * cs.nL + lsh;
+    } else {
+      if (idx >= nS) return g;
+      i = sampleOf(act, idx);
+    }
+    const bool valid = waveRay(*sc, fp, cs, kind, i, o, d);
     if (!valid) return g;
+    g.wi = uint32_t(i);
     const DObject& ob = sc->objects[sc->mesh_obj_index[mo]];
     const DMesh& m = sc->meshes[ob.mesh];
     const Ray r = objectRay(ob, o, d);
@@ -262,7 +284,7 @@ struct Gate {
     if (g.pass && !force_exact) {
       int mode = path_mode, l = 0;
       if (kind == WAVE_SHADOW) {
-        l = int(i % cs.nL);
+        l = lsh;
         mode = (sc->lights[l].kind == LIGHT_DISTANT) ? FM_DIR : FM_GENERAL;
       }
       if (mode != FM_GENERAL && !(sc->frames[frameIndex(sc->nlights, mo, mode, l)].valid > 0)) mode = FM_GENERAL;
@@ -380,9 +402,11 @@ NRT_HD StatDelta zeroStats() { StatDelta s; for (int i = 0; i < ST_COUNT; ++i) s
 
 // ---- shade: nearest hit of the path ray, hit point and normal (renderer.nim:71-88)
 struct Shade {
-  const DScene* sc; FrameParams fp; ChunkState cs;
-  NRT_HD StatDelta operator()(int64_t s) const {
+  const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
+  NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
+    if (idx >= activeN(act)) return st;
+    const int64_t s = sampleOf(act, idx);
     if (!cs.active[s]) return st;
     const V4 o = ld4(cs.rayO, cs.S, s), d = ld4(cs.rayD, cs.S, s);
     const TraceOut tr = traceObjects(*sc, cs, o, d, NRT_INF, s);
@@ -426,10 +450,14 @@ struct Shade {
 };
 
 // ---- resolve: shadow tests + diffuse + reflection set-up (renderer.nim:90-127)
+template <class A>
 struct Resolve {
-  const DScene* sc; FrameParams fp; ChunkState cs;
-  NRT_HD StatDelta operator()(int64_t s) const {
+  const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
+  uint32_t* nextList; uint32_t* nextCount;   // continuing samples for the next bounce
+  NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
+    if (idx >= activeN(act)) return st;
+    const int64_t s = sampleOf(act, idx);
     const int objHit = cs.hitObj[s];
     if (objHit < 0) return st;
     const DObject& ob = sc->objects[objHit];
@@ -468,6 +496,7 @@ struct Resolve {
       cs.bounce[s] = bounce + 1;
       cs.active[s] = 1;
       st.v[ST_CONT] = 1;
+      nextList[A::add32(nextCount, 1u)] = uint32_t(s);
     } else {
       cs.active[s] = 0;
     }

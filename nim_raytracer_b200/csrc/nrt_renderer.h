@@ -305,6 +305,7 @@ struct Renderer {
       cs.preRay = al<uint32_t>(4 * cand); cs.preRec = al<uint32_t>(4 * cand);
       cs.candRef = al<uint32_t>(cand); cs.candTri = al<uint32_t>(cand); cs.candT = al<double>(cand);
       cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * cntStride(nL));
+      cs.alist = al<uint32_t>(2 * S); cs.acount = al<uint32_t>(waves + 2);
       cs.stats = al<unsigned long long>(ST_COUNT);
       dRows = al<int32_t>(nrows);
     }
@@ -312,12 +313,13 @@ struct Renderer {
   }
 
   // One mesh wave: gate + per mesh object { filter per ray bundle, exact, verify }.
-  void meshWave(const SceneData<BE>& sd, const FrameParams& fp, int kind, int64_t n, int wave, bool primary, int force_exact) {
+  void meshWave(const SceneData<BE>& sd, const FrameParams& fp, int kind, const ActiveSet& act, int wave, bool primary, int force_exact) {
     const int nMO = cs.nMO, nL = cs.nL, cst = cntStride(nL);
-    if (nMO == 0 || n == 0) return;
+    if (nMO == 0 || (!act.list && act.n == 0)) return;
     uint32_t* cnt = cs.counters + int64_t(wave) * nMO * cst;
     const int pathMode = primary ? FM_ORIGIN : FM_GENERAL;
-    be->gate(Gate{sd.d, fp, cs, kind, n, force_exact, pathMode}, n, nMO, cnt);
+    const int mult = (kind == WAVE_SHADOW) ? nL : 1;
+    be->gate(Gate{sd.d, fp, cs, kind, act, force_exact, pathMode}, act.list ? act.count : nullptr, act.n * mult, mult, nMO, cnt);
     for (int mo = 0; mo < nMO; ++mo) {
       uint32_t* c = cnt + mo * cst;
       const DMesh& m = sd.meshes[sd.objs[sd.moIndex[mo]].mesh];
@@ -392,21 +394,25 @@ struct Renderer {
         const int64_t ncnt = int64_t(waves) * std::max(nMO, 1) * cntStride(nL);
         be->zero(cs.counters, sizeof(uint32_t) * ncnt);
         be->zero(cs.stats, sizeof(unsigned long long) * ST_COUNT);
+        be->zero(cs.acount, sizeof(uint32_t) * (waves + 2));
         if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
         else be->forEach(nS, GenSimple{sd.d, fp, cs});
         int wave = 0;
-        unsigned long long contPrev = 0;
+        ActiveSet act{nullptr, nullptr, nS};   // bounce 0: every sample of the chunk
         for (int bounce = 0;; ++bounce) {
-          meshWave(sd, fp, WAVE_PATH, nS, wave, bounce == 0, force_exact); ++wave;
-          be->forEachStats(nS, Shade{sd.d, fp, cs}, cs.stats);
-          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, nS * nL, wave, false, force_exact);
+          uint32_t* nextList = cs.alist + int64_t((bounce + 1) & 1) * cs.S;
+          uint32_t* nextCount = cs.acount + bounce + 1;
+          const uint32_t* cnt = act.list ? act.count : nullptr;
+          meshWave(sd, fp, WAVE_PATH, act, wave, bounce == 0, force_exact); ++wave;
+          be->forEachStats(cnt, act.n, Shade{sd.d, fp, cs, act}, cs.stats);
+          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, false, force_exact);
           ++wave;
-          be->forEachStats(nS, Resolve{sd.d, fp, cs}, cs.stats);
+          be->forEachStats(cnt, act.n, Resolve<typename BE::Atom>{sd.d, fp, cs, act, nextList, nextCount}, cs.stats);
           if (bounce >= maxBounces) break;
-          unsigned long long cont = 0;
-          be->download(&cont, cs.stats + ST_CONT, sizeof(cont));
-          if (cont == contPrev) break;  // no sample continued
-          contPrev = cont;
+          uint32_t cont = 0;
+          be->download(&cont, nextCount, sizeof(cont));
+          if (cont == 0) break;  // no sample continued
+          act = ActiveSet{nextList, nextCount, 0};
         }
         be->forEach(npix, Finalize{fp, cs});
         // chunk epilogue: counters (profile + overflow check) and stats

@@ -30,7 +30,8 @@ struct LoopBackend {
   void download(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
   void sync() {}
   template <class F> void forEach(int64_t n, const F& f) { for (int64_t i = 0; i < n; ++i) f(i); ++launches; }
-  template <class F> void forEachStats(int64_t n, const F& f, unsigned long long* st) {
+  template <class F> void forEachStats(const uint32_t* count, int64_t n, const F& f, unsigned long long* st) {
+    if (count) n = *count;
     for (int64_t i = 0; i < n; ++i) { const StatDelta d = f(i); for (int k = 0; k < ST_COUNT; ++k) st[k] += d.v[k]; }
     ++launches;
   }
@@ -57,9 +58,10 @@ struct LoopBackend {
     }
     ++launches;
   }
-  void gate(const Gate& g, int64_t n, int nMO, uint32_t* cnt) {
+  void gate(const Gate& g, const uint32_t* count, int64_t n, int mult, int nMO, uint32_t* cnt) {
     const ChunkState& cs = g.cs;
     const int cst = cntStride(cs.nL);
+    if (count) n = int64_t(*count) * mult;
     for (int64_t i = 0; i < n; ++i)
       for (int mo = 0; mo < nMO; ++mo) {
         const GateOut o = g(i, mo);
@@ -67,7 +69,7 @@ struct LoopBackend {
         if (o.pass && o.safe) {
           const int64_t q = c[cntQueue(o.bundle)]++;
           const int64_t at = queueBase(cs, mo, o.bundle) + q;
-          cs.qref[at] = uint32_t(i);
+          cs.qref[at] = o.wi;
           float* p0 = cs.qray0 + 4 * at;
           p0[0] = o.fr.ax; p0[1] = o.fr.ay; p0[2] = o.fr.az; p0[3] = o.fr.rr;
           float* h0 = cs.qhot0 + 4 * at;
@@ -80,7 +82,7 @@ struct LoopBackend {
           }
         } else if (o.pass) {
           const int64_t q = c[CNT_EXACT]++;
-          cs.xref[int64_t(mo) * cs.NR + q] = uint32_t(i);
+          cs.xref[int64_t(mo) * cs.NR + q] = o.wi;
         }
       }
     ++launches;
