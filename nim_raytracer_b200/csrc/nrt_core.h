@@ -77,6 +77,28 @@ struct DObject {
   double reflection;
 };
 
+// Compact per-object record read by the in-order object scan of trace(): 48 bytes, three
+// 16-byte vector loads (the full DObject, 448 B over four cache lines, is only needed for
+// non-translation transforms, boxes and shading).
+struct alignas(16) CObj {
+  int32_t kind, mesh_obj, xlate_only, _pad;
+  double t[3];     // translation column of worldToObject
+  double radius;
+};
+NRT_HD CObj loadCObj(const CObj* p) {
+#if defined(__CUDA_ARCH__)
+  CObj c;
+  const int4 h = __ldg(reinterpret_cast<const int4*>(p));
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 2);
+  c.kind = h.x; c.mesh_obj = h.y; c.xlate_only = h.z; c._pad = h.w;
+  c.t[0] = a.x; c.t[1] = a.y; c.t[2] = b.x; c.radius = b.y;
+  return c;
+#else
+  return *p;
+#endif
+}
+
 struct DLight {
   int32_t kind;
   int32_t _pad;
@@ -104,6 +126,7 @@ struct BundleFrame;  // nrt_filter.h
 struct DScene {
   int32_t nobjects, nlights, nmeshes, nmesh_objs;
   const DObject* objects;
+  const CObj* cobjs;              // compact mirror of objects[] for the object scan
   const DLight* lights;
   const DMesh* meshes;
   const int32_t* mesh_obj_index;  // mesh object k -> object index

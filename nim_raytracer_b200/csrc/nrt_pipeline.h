@@ -376,19 +376,26 @@ struct Verify2 {  // among candidates attaining the minimum, the lowest face ind
 struct TraceOut { int obj; double t; uint32_t tri; int tests, hits; };
 NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d, double tNear, int64_t wi) {
   TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
+  // the exact shortcut of toObject() for [I | t] matrices applies to this ray?
+  const bool fastRay = (o.w == 1.0) && (d.w == 0.0) && nzFinite3(o) && nzFinite3(d);
   for (int i = 0; i < sc.nobjects; ++i) {
-    const DObject& ob = sc.objects[i];
+    const CObj c = loadCObj(sc.cobjs + i);
     double t; uint32_t tri = kNoTri;
-    if (ob.kind == GEOM_MESH) {
-      t = bitsd(cs.tBest[int64_t(ob.mesh_obj) * cs.NR + wi]);
-      tri = cs.triBest[int64_t(ob.mesh_obj) * cs.NR + wi];
+    if (c.kind == GEOM_MESH) {
+      t = bitsd(cs.tBest[int64_t(c.mesh_obj) * cs.NR + wi]);
+      tri = cs.triBest[int64_t(c.mesh_obj) * cs.NR + wi];
     } else {
       V4 oo, dd;
-      toObject(ob, o, d, oo, dd);
+      if (c.xlate_only && fastRay) {
+        oo = v4(o.x + c.t[0], o.y + c.t[1], o.z + c.t[2], 1.0);
+        dd = v4(d.x, d.y, d.z, 0.0);
+      } else {
+        toObject(sc.objects[i], o, d, oo, dd);
+      }
       // initRay's 1/dir (geom.nim:42-47) is only read by the AABB test: built for boxes only
-      if (ob.kind == GEOM_SPHERE) t = sphereIntersect(ob.radius, oo, dd);
-      else if (ob.kind == GEOM_PLANE) t = planeIntersect(oo, dd);
-      else if (ob.kind == GEOM_BOX) t = aabbIntersect(ob.bmin, ob.bmax, initRay(oo, dd));
+      if (c.kind == GEOM_SPHERE) t = sphereIntersect(c.radius, oo, dd);
+      else if (c.kind == GEOM_PLANE) t = planeIntersect(oo, dd);
+      else if (c.kind == GEOM_BOX) t = aabbIntersect(sc.objects[i].bmin, sc.objects[i].bmax, initRay(oo, dd));
       else t = NRT_NEG_INF;
     }
     r.tests++;

@@ -35,6 +35,7 @@ struct SceneData {
   std::vector<DLight> lights;
   std::vector<DMesh> meshes;  // device pointers inside
   std::vector<int32_t> moIndex;
+  std::vector<CObj> cobjs; CObj* dCObjs = nullptr;
   DObject* dObjs = nullptr; DLight* dLights = nullptr; DMesh* dMeshes = nullptr; int32_t* dMo = nullptr;
   std::vector<void*> owned;
   bool anyReflective = false, anyPointLight = false;
@@ -187,6 +188,14 @@ struct SceneData {
       std::memcpy(dl.dir, l.dir, sizeof(dl.dir));
       std::memcpy(dl.pos, l.pos, sizeof(dl.pos));
     }
+    cobjs.assign(objs.size(), CObj{});
+    for (size_t i = 0; i < objs.size(); ++i) {
+      CObj& c = cobjs[i];
+      c.kind = objs[i].kind; c.mesh_obj = objs[i].mesh_obj; c.xlate_only = objs[i].xlate_only; c._pad = 0;
+      c.t[0] = objs[i].w2o[12]; c.t[1] = objs[i].w2o[13]; c.t[2] = objs[i].w2o[14];
+      c.radius = objs[i].radius;
+    }
+    dCObjs = up(cobjs.data(), int64_t(cobjs.size()), reuse ? dCObjs : nullptr);
     dObjs = up(objs.data(), int64_t(objs.size()), reuse ? dObjs : nullptr);
     dLights = up(lights.data(), int64_t(lights.size()), reuse ? dLights : nullptr);
     dMeshes = up(meshes.data(), int64_t(meshes.size()), reuse ? dMeshes : nullptr);
@@ -226,7 +235,7 @@ struct SceneData {
       }
       dFrames = up(frames.data(), int64_t(frames.size()), reuse ? dFrames : nullptr);
     }
-    h.objects = dObjs; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames;
+    h.objects = dObjs; h.cobjs = dCObjs; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames;
     std::memcpy(h.c2w, desc->camera_to_world, sizeof(h.c2w));
     h.tan_half_fov = std::tan((desc->fov * (kPi / 180.0)) / 2);  // renderer.nim:38; Nim degToRad = d * (PI/180)
     std::memcpy(h.bg, desc->bg_color, sizeof(h.bg));
@@ -368,16 +377,19 @@ struct Renderer {
     if (sd.anyReflective && o.depth_mode == NRT_DEPTH_INTENDED) maxBounces = std::min(maxBounces, std::max(0, o.max_ray_depth));
     const int waves = 2 * (maxBounces + 1);
     const int64_t npixTotal = int64_t(rows.size()) * fp.nx;
-    int64_t S = envInt("NRT_CHUNK_SAMPLES", int64_t(1) << 22);
-    // keep the per-(ray, mesh object) wave arrays within ~8 GB
-    const int64_t perSample = 240 + int64_t(56) * std::max(1, nL) * std::max(1, nMO);
-    S = std::min<int64_t>(S, (int64_t(8) << 30) / perSample);
+    // 16 Mi samples per chunk (~9 GB of state for one mesh object and two lights; sized for 180 GB
+    // of HBM): large chunks amortise launches and the per-bounce host checks
+    int64_t S = envInt("NRT_CHUNK_SAMPLES", int64_t(1) << 24);
+    const int64_t perSample = 260 + int64_t(110) * std::max(1, nL) * std::max(1, nMO);
+    S = std::min<int64_t>(S, (int64_t(32) << 30) / perSample);
     S = std::max<int64_t>(S, fp.spp);
     S = std::min<int64_t>(S, npixTotal * fp.spp);
     int64_t chunkPix = std::max<int64_t>(1, S / fp.spp);
     S = chunkPix * fp.spp;
     int64_t cand = std::max<int64_t>(envInt("NRT_CAND_CAP", 0), 0);
-    if (cand == 0) cand = std::max<int64_t>(int64_t(1) << 20, 8 * S * std::max(1, nL));
+    // observed: ~0.06 candidates and ~0.3 pre-candidates per sample on the bunny scenes; an overflow re-renders
+    // the frame with 4x the capacity
+    if (cand == 0) cand = std::max<int64_t>(int64_t(1) << 20, S * std::max(1, nL) / 2);
     const int force_exact = int(envInt("NRT_FORCE_EXACT", 0));
 
     for (int attempt = 0;; ++attempt) {
