@@ -117,6 +117,28 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows), "power_w_max": max(r[3] for r in self.rows)}
 
 
+def _cpu_sample(scene_desc, opts, target_s):
+    """Bounded, representative CPU sample of the workload: the SAME scene, options and spp at 1/k of
+    the linear resolution (every ray type in the same proportion; scanline sub-sampling is not
+    representative because mesh rows cost ~1000x sky rows).  k is chosen from a probe so that one
+    render takes about `target_s` seconds.  Returns (opts_small, k)."""
+    import copy
+    import oracle
+
+    def small(k):
+        o = copy.copy(opts)
+        o.width, o.height = max(8, opts.width // k), max(8, opts.height // k)
+        return o
+
+    k = 32
+    t = time.time()
+    oracle.render(scene_desc, small(k), fast=True)
+    dt = max(time.time() - t, 1e-3)
+    # time ~ 1/k^2
+    k_new = int(max(1, min(64, round(k * (dt / target_s) ** 0.5))))
+    return small(k_new), k_new
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path timed on the host cores.
     The reference (Nim) cannot be built here, so this is the oracle port (oracle/ref_cpu.cpp,
@@ -129,32 +151,25 @@ def run_reference(args, rank, world):
     scene, opts, desc = workload(args.workload)
     sd = api.SceneDesc(scene)
     cores = oracle.hardware_threads()
-    h = opts.height
-    # bounded sample: every k-th scanline, k chosen from a probe so that one step is ~target seconds
-    probe_rows = list(range(h // 16, h, max(1, h // 8)))   # 8 evenly spread scanlines
-    t = time.time()
-    _, st = oracle.render_rows(sd, opts, probe_rows, fast=True)
-    dt = max(time.time() - t, 1e-3)
-    full_est = dt * h / len(probe_rows)
-    target = float(os.environ.get("NRT_REF_STEP_SECONDS", "5"))
-    k = max(1, int(np.ceil(full_est / target)))
-    rows = list(range(0, h, k))
-    for _ in range(args.warmup if k > 1 else min(args.warmup, 1)):
-        oracle.render_rows(sd, opts, rows, fast=True)
+    so, k = _cpu_sample(sd, opts, float(os.environ.get("NRT_REF_STEP_SECONDS", "5")))
+    for _ in range(args.warmup):
+        oracle.render(sd, so, fast=True)
     rays = 0
     t0 = time.time()
     for _ in range(args.steps):
-        _, st = oracle.render_rows(sd, opts, rows, fast=True)
+        _, st, _ = oracle.render(sd, so, fast=True)
         rays += st.numRays
     el = time.time() - t0
     v = rays / el / 1e6
-    sample = f"every {k}th scanline of the frame ({len(rows)} of {h} lines) per step, all {cores} host threads, float64 -O3 -ffast-math"
+    full_rays_est = (rays / args.steps) * (opts.width * opts.height) / (so.width * so.height)
+    sample = (f"the same scene/options at 1/{k} linear resolution ({so.width}x{so.height}, same spp) per step, "
+              f"all {cores} host threads, float64 -O3 -ffast-math")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "note": "CPU restatement of the reference (Nim toolchain absent); ms_per_step is for the sampled lines only"},
-        "frames_per_s_extrapolated": 1.0 / (el / args.steps * h / len(rows)),
+        "config": {"workload": desc, "note": "CPU restatement of the reference (Nim toolchain absent); a step renders the bounded sample described in cpu_baseline.sample"},
+        "frames_per_s_extrapolated": v * 1e6 / full_rays_est,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -162,22 +177,18 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(scene_desc, opts, budget_s=12.0):
+def cpu_baseline(scene_desc, opts, rays_per_frame, budget_s=12.0):
     import oracle
     cores = oracle.hardware_threads()
-    h = opts.height
-    probe_rows = list(range(h // 16, h, max(1, h // 8)))   # 8 evenly spread scanlines
+    so, k = _cpu_sample(scene_desc, opts, budget_s)
     t = time.time()
-    oracle.render_rows(scene_desc, opts, probe_rows, fast=True)
-    dt = max(time.time() - t, 1e-3)
-    k = max(1, int(np.ceil(dt * h / len(probe_rows) / budget_s)))
-    rows = list(range(0, h, k))
-    t = time.time()
-    _, st = oracle.render_rows(scene_desc, opts, rows, fast=True)
+    _, st, _ = oracle.render(scene_desc, so, fast=True)
     el = time.time() - t
-    return {"value": st.numRays / el / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"every {k}th scanline ({len(rows)} of {h}) of the same frame, {el:.1f} s, oracle -O3 -ffast-math float64, all host threads",
-            "frames_per_s_extrapolated": 1.0 / (el * h / len(rows))}
+    v = st.numRays / el / 1e6
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"the same scene/options at 1/{k} linear resolution ({so.width}x{so.height}, same spp), {el:.1f} s, "
+                      f"oracle -O3 -ffast-math float64, all host threads",
+            "frames_per_s_extrapolated": v * 1e6 / max(rays_per_frame, 1)}
 
 
 def main():
@@ -377,7 +388,7 @@ def main():
             "roofline": roofline, "fb_checksum": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(ds.desc, opts)
+            line["cpu_baseline"] = cpu_baseline(ds.desc, opts, total_rays / args.steps)
         print(json.dumps(line), flush=True)
 
     L.nrt_host_free_pinned(hp)
