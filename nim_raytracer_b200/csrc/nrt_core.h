@@ -180,6 +180,25 @@ NRT_HD double sphereIntersect(double radius, V4 orig, V4 dir) {
   return NRT_NEG_INF;
 }
 
+// Conservative float32 pre-test of the sphere discriminant (geom.nim:216-230): returns true only
+// if delta = b^2 - 4ac is certainly negative, i.e. the reference returns NegInf; the float64
+// evaluation (and its sqrt / divisions) is then skipped.  oc = object-space origin (sphere at 0).
+// |float32 error of b^2 - a c| <= 16u a (|oc|^2 + r^2) with u = 2^-24 covers the roundings of the
+// converted inputs and of the nine float32 operations.
+NRT_HD bool sphereCertainMiss(double radius, V4 oc, V4 dir) {
+  const float ox = (float)oc.x, oy = (float)oc.y, oz = (float)oc.z;
+  const float dx = (float)dir.x, dy = (float)dir.y, dz = (float)dir.z;
+  const float r = (float)radius;
+  const float a = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+  const float b = fmaf(dx, ox, fmaf(dy, oy, dz * oz));           // half of the reference's b
+  const float o2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
+  const float c = o2 - r * r;
+  const float disc = fmaf(b, b, -(a * c));                         // delta / 4
+  const float margin = 9.5367431640625e-7f * (a * (o2 + r * r));  // 16 * 2^-24
+  // NaN / Inf (overflowing inputs) compare false => not a certain miss
+  return disc < -margin;
+}
+
 // geom.nim:240-248
 NRT_HD double planeIntersect(V4 orig, V4 dir) {
   const V4 n = v4(0.0, 1.0, 0.0, 0.0);

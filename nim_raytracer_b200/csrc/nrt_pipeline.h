@@ -393,8 +393,15 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
         toObject(sc.objects[i], o, d, oo, dd);
       }
       // initRay's 1/dir (geom.nim:42-47) is only read by the AABB test: built for boxes only
-      if (c.kind == GEOM_SPHERE) t = sphereIntersect(c.radius, oo, dd);
-      else if (c.kind == GEOM_PLANE) t = planeIntersect(oo, dd);
+      // spheres: most rays miss by far — a float32 discriminant bound proves delta < 0 (=> NegInf) without
+      // the float64 evaluation; planes: orig.y and dir.y of equal sign give t < 0, which trace() rejects
+      // (renderer.nim:60) whatever its value, so the division is skipped
+      if (c.kind == GEOM_SPHERE) t = sphereCertainMiss(c.radius, oo, dd) ? NRT_NEG_INF : sphereIntersect(c.radius, oo, dd);
+      else if (c.kind == GEOM_PLANE) {
+        // (bounded magnitudes: the quotient cannot underflow to -0.0, which `t >= 0` would accept)
+        const bool neg = ((oo.y > 1e-150 && dd.y > 1e-6) || (oo.y < -1e-150 && dd.y < -1e-6)) && fabs(oo.y) < 1e150 && fabs(dd.y) < 1e150;
+        t = neg ? NRT_NEG_INF : planeIntersect(oo, dd);
+      }
       else if (c.kind == GEOM_BOX) t = aabbIntersect(sc.objects[i].bmin, sc.objects[i].bmax, initRay(oo, dd));
       else t = NRT_NEG_INF;
     }

@@ -104,6 +104,11 @@ def test_general_transforms_point_light_mirror(oracle_mod):
     check(scenes.transformed_objects(stride=64), api.Options(64, 36, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
 
 
+def test_stress_scene_small(oracle_mod):
+    # BASELINE config 5 at reduced size (template test/test.nim:29-40)
+    check(scenes.stress(ntri=800, nspheres=30), api.Options(64, 36, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
+
+
 def test_degenerate_meshes(oracle_mod):
     from nim_raytracer_b200 import loaders, linalg as L
     # zero-area and needle triangles, duplicated coplanar faces (first index must win)

@@ -186,6 +186,30 @@ def test_full_size_filter_vs_exact(monkeypatch):
     assert (a_fb.data == b_fb.data).all() and a_st == b_st
 
 
+def test_stress_scene_small(oracle_mod):
+    # BASELINE config 5 at reduced size: random triangle soup as ONE mesh + many spheres (10 % mirrors)
+    sc = scenes.stress(ntri=3000, nspheres=60)
+    assert_parity(sc, api.Options(160, 90, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
+
+
+def test_config4_full_size_properties(monkeypatch):
+    # BASELINE config 4 at its full size (3840x2160, 16 spp, depth 8): size-independent properties —
+    # Stats identities of renderer.nim:58,138,155 and invariance under the chunking of the frame
+    sc = scenes.bunny_spheres()
+    o = api.Options(3840, 2160, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+    ds = api.DeviceScene(sc)
+    fb1 = api.newFramebuf(o.width, o.height)
+    st1 = api.renderFrame(ds, o, fb1)
+    assert st1.numPrimaryRays == 3840 * 2160 * 16
+    assert st1.numIntersectionTests == st1.numRays * len(sc.objects)
+    assert st1.numCappedSamples == 0 and np.isfinite(fb1.data).all()
+    monkeypatch.setenv("NRT_CHUNK_SAMPLES", str(5_000_000))
+    fb2 = api.newFramebuf(o.width, o.height)
+    st2 = api.renderFrame(ds, o, fb2)
+    assert st1 == st2 and digest(fb1.data) == digest(fb2.data)
+    # the 1/4-size frame of the same scene is checked against the oracle in test_golden_config3_reduced
+
+
 def test_error_behaviour():
     import ctypes as C
     L = api.lib()
