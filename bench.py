@@ -191,6 +191,16 @@ def cpu_baseline(scene_desc, opts, rays_per_frame, budget_s=12.0):
             "frames_per_s_extrapolated": v * 1e6 / max(rays_per_frame, 1)}
 
 
+def _traffic(workload_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel launch, from the committed
+    `ncu --set full` capture of this workload (profiles/prefilter_traffic.json); None if not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "prefilter_traffic.json")) as f:
+            return json.load(f).get(workload_name, {}).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -364,7 +374,7 @@ def main():
             "frac": achieved / peak.value if peak.value > 0 else None,
             "peak_source": "FFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
             "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
-            "traffic": None,
+            "traffic": _traffic(args.workload),
             "flops_per_test": prof_acc["flops"] / max(prof_acc["tests"], 1), "tests_per_step": prof_acc["tests"] / args.steps,
             "ref_tests_per_step": prof_acc["tests_ref"] / args.steps,
             "avg_launch_ms": prof_acc["mesh_ms"] / max(prof_acc["launches"], 1),
