@@ -10,6 +10,8 @@
 
 #include <cuda_runtime.h>
 #include <cuda_pipeline.h>
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <atomic>
 #include <cstdio>
@@ -94,74 +96,143 @@ __global__ void __launch_bounds__(kBlock) k_for_each_counted(F f, const uint32_t
   for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) f(i);
 }
 
-// AABB gate + warp-ballot compaction of the rays that enter each mesh's box, one queue
-// per ray bundle (0 = arbitrary / shared-origin rays, 1 + l = shadow rays of DistantLight l).
-__global__ void __launch_bounds__(kBlock) k_gate(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO, uint32_t* cnt) {
+// AABB gate of TriangleMesh.intersect (geom.nim:340) + ORDERED compaction of the rays that enter
+// each mesh's box into one queue per ray bundle (0 = arbitrary / shared-origin rays, 1 + l = shadow
+// rays of DistantLight l) and the float64 brute-force queue.  Three launches:
+//   k_gate_flags  evaluates the gate per (wave position, mesh object), stores a one-byte code and
+//                 counts the codes of every 256-ray block with warp ballots;
+//   k_gate_scan   exclusive scan of the block counts per (mesh object, queue) row -> queue offsets
+//                 and the queue totals;
+//   k_gate_write  re-evaluates the passing rays and stores them at offset + ballot rank.
+// Queue order therefore equals wave order (scanline order of the samples): the 256 consecutive
+// queue entries a prefilter warp works on belong to neighbouring pixels, which is what makes the
+// chunk bounds of the two-level traversal selective.
+__device__ __forceinline__ uint8_t gateCode(const GateOut& o) { return o.pass ? (o.safe ? uint8_t(1 + o.bundle) : uint8_t(255)) : uint8_t(0); }
+__device__ __forceinline__ uint8_t gateWant(int r, int nB) { return r < nB ? uint8_t(1 + r) : uint8_t(255); }
+
+__global__ void __launch_bounds__(kBlock) k_gate_flags(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO) {
+  extern __shared__ uint32_t sh_cnt[];   // nMO * nRow
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt = (1u << lane) - 1u;
   const ChunkState& cs = g.cs;
-  const int nB = 1 + cs.nL, cst = cntStride(cs.nL);
+  const int nB = 1 + cs.nL, nRow = nB + 1, rows = nMO * nRow;
   const int64_t n = count ? int64_t(*count) * mult : nHost;
-  const int64_t nPad = (n + 31) / 32 * 32;   // whole warps take part in the ballots
-  for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < nPad; i += int64_t(gridDim.x) * kBlock)
-  for (int mo = 0; mo < nMO; ++mo) {
-    const GateOut o = g(i, mo);
-    uint32_t* c = cnt + mo * cst;
-    const bool toFilter = o.pass && o.safe, toExact = o.pass && !o.safe;
-    if (__ballot_sync(0xffffffffu, toFilter)) {
-      for (int b = 0; b < nB; ++b) {
-        const bool mine = toFilter && o.bundle == b;
-        const unsigned fm = __ballot_sync(0xffffffffu, mine);
-        if (!fm) continue;
-        const int leader = __ffs(fm) - 1;
-        uint32_t base = 0;
-        if (int(lane) == leader) base = atomicAdd(&c[cntQueue(b)], uint32_t(__popc(fm)));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (mine) {
-          const int64_t q = base + __popc(fm & lt);
-          const int64_t at = queueBase(cs, mo, b) + q;
-          cs.qref[at] = o.wi;
-          reinterpret_cast<float4*>(cs.qray0)[at] = make_float4(o.fr.ax, o.fr.ay, o.fr.az, o.fr.rr);
-          reinterpret_cast<float4*>(cs.qhot0)[at] = make_float4(o.hr.a0, o.hr.a1, o.hr.a2, o.hr.a3);
-          if (b == 0) {
-            reinterpret_cast<float4*>(cs.qray1)[int64_t(mo) * cs.NR + q] = make_float4(o.fr.mx, o.fr.my, o.fr.mz, 0.f);
-            reinterpret_cast<float4*>(cs.qhot1)[int64_t(mo) * cs.NR + q] = make_float4(o.hr.b0, o.hr.b1, o.hr.b2, 0.f);
-          }
+  const int64_t nVB = (n + kBlock - 1) / kBlock;
+  for (int64_t vb = blockIdx.x; vb < nVB; vb += gridDim.x) {
+    for (int k = threadIdx.x; k < rows; k += kBlock) sh_cnt[k] = 0;
+    __syncthreads();
+    const int64_t i = vb * kBlock + threadIdx.x;
+    for (int mo = 0; mo < nMO; ++mo) {
+      uint8_t code = 0;
+      if (i < n) {
+        code = gateCode(g(i, mo));
+        cs.gflag[int64_t(mo) * cs.NR + i] = code;
+      }
+      if (__ballot_sync(0xffffffffu, code != 0)) {
+        for (int r = 0; r < nRow; ++r) {
+          const unsigned m = __ballot_sync(0xffffffffu, code == gateWant(r, nB));
+          if (m && lane == 0) atomicAdd(&sh_cnt[mo * nRow + r], uint32_t(__popc(m)));
         }
       }
     }
-    const unsigned xm = __ballot_sync(0xffffffffu, toExact);
-    if (xm) {
-      const int leader = __ffs(xm) - 1;
-      uint32_t base = 0;
-      if (int(lane) == leader) base = atomicAdd(&c[CNT_EXACT], uint32_t(__popc(xm)));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (toExact) cs.xref[int64_t(mo) * cs.NR + base + __popc(xm & lt)] = o.wi;
+    __syncthreads();
+    for (int k = threadIdx.x; k < rows; k += kBlock) cs.gcnt[int64_t(k) * (cs.gvb + 1) + vb] = sh_cnt[k];
+    __syncthreads();
+  }
+}
+
+// one CTA per (mesh object, queue) row: in-place exclusive scan of the block counts; total -> counter block
+__global__ void __launch_bounds__(1024) k_gate_scan(ChunkState cs, const uint32_t* count, int64_t nHost, int mult, uint32_t* cnt) {
+  __shared__ uint32_t sh[1024];
+  const int nB = 1 + cs.nL, nRow = nB + 1, cst = cntStride(cs.nL);
+  const int row = blockIdx.x, mo = row / nRow, r = row - mo * nRow;
+  uint32_t* p = cs.gcnt + int64_t(row) * (cs.gvb + 1);
+  const int64_t n = count ? int64_t(*count) * mult : nHost;
+  const int64_t nVB = (n + kBlock - 1) / kBlock;
+  const int64_t per = (nVB + 1023) / 1024;
+  const int64_t b0 = min(nVB, int64_t(threadIdx.x) * per), b1 = min(nVB, b0 + per);
+  uint32_t sum = 0;
+  for (int64_t k = b0; k < b1; ++k) sum += p[k];
+  sh[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {   // inclusive Hillis-Steele scan over the 1024 partial sums
+    const uint32_t v = (int(threadIdx.x) >= off) ? sh[threadIdx.x - off] : 0u;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = sh[threadIdx.x] - sum;
+  for (int64_t k = b0; k < b1; ++k) { const uint32_t v = p[k]; p[k] = run; run += v; }
+  if (threadIdx.x == 1023) {
+    const uint32_t total = sh[1023];
+    p[nVB] = total;
+    cnt[mo * cst + (r < nB ? cntQueue(r) : CNT_EXACT)] = total;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_gate_write(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO) {
+  __shared__ uint32_t wc[kBlock / 32];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const ChunkState& cs = g.cs;
+  const int nB = 1 + cs.nL, nRow = nB + 1;
+  const int64_t n = count ? int64_t(*count) * mult : nHost;
+  const int64_t nVB = (n + kBlock - 1) / kBlock;
+  for (int64_t vb = blockIdx.x; vb < nVB; vb += gridDim.x) {
+    const int64_t i = vb * kBlock + threadIdx.x;
+    for (int mo = 0; mo < nMO; ++mo) {
+      const uint8_t code = (i < n) ? cs.gflag[int64_t(mo) * cs.NR + i] : uint8_t(0);
+      for (int r = 0; r < nRow; ++r) {
+        const uint32_t* p = cs.gcnt + int64_t(mo * nRow + r) * (cs.gvb + 1) + vb;
+        const uint32_t base = p[0];
+        if (p[1] == base) continue;          // nothing of this block goes to this queue (block-uniform)
+        const bool mine = code == gateWant(r, nB);
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (lane == 0) wc[warp] = uint32_t(__popc(m));
+        __syncthreads();
+        uint32_t pre = 0;
+        for (unsigned w = 0; w < warp; ++w) pre += wc[w];
+        __syncthreads();
+        if (!mine) continue;
+        const int64_t q = int64_t(base) + pre + __popc(m & lt);
+        const GateOut o = g(i, mo);
+        if (r < nB) {
+          const int64_t at = queueBase(cs, mo, r) + q;
+          cs.qref[at] = o.wi;
+          reinterpret_cast<float4*>(cs.qray0)[at] = make_float4(o.fr.ax, o.fr.ay, o.fr.az, o.fr.rr);
+          reinterpret_cast<float4*>(cs.qhot0)[at] = make_float4(o.hr.a0, o.hr.a1, o.hr.a2, o.hr.a3);
+          if (r == 0) {
+            reinterpret_cast<float4*>(cs.qray1)[int64_t(mo) * cs.NR + q] = make_float4(o.fr.mx, o.fr.my, o.fr.mz, 0.f);
+            reinterpret_cast<float4*>(cs.qhot1)[int64_t(mo) * cs.NR + q] = make_float4(o.hr.b0, o.hr.b1, o.hr.b2, 0.f);
+          }
+        } else {
+          cs.xref[int64_t(mo) * cs.NR + q] = o.wi;
+        }
+      }
     }
   }
 }
 
-// Filter-record build with culling: ballot-compacted, stored pair-interleaved (nrt_filter.h).
+// Filter-record build with culling, order preserving (records stay in the Morton order of the
+// faces): keep flags -> exclusive scan (cub) -> scatter; stored pair-interleaved (nrt_filter.h).
+template <class F>
+__global__ void __launch_bounds__(kBlock) k_rec_flags(F f, int64_t n, uint32_t* flag) {
+  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  if (i < n) flag[i] = f(i).keep ? 1u : 0u;
+}
 template <class F, int MODE>
-__global__ void __launch_bounds__(kBlock) k_compact_recs(F f, int64_t n, float* recs, float* hot, uint32_t* count) {
+__global__ void __launch_bounds__(kBlock) k_rec_scatter(F f, int64_t n, const uint32_t* pos, float* recs, float* hot, uint32_t* count) {
   constexpr int NC = recFloats(MODE), NH = hotFloats(MODE);
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
-  const unsigned lane = threadIdx.x & 31u;
-  RecOut o; o.keep = false;
-  if (i < n) o = f(i);
-  const unsigned m = __ballot_sync(0xffffffffu, o.keep);
-  if (!m) return;
-  const int leader = __ffs(m) - 1;
-  uint32_t base = 0;
-  if (int(lane) == leader) base = atomicAdd(count, uint32_t(__popc(m)));
-  base = __shfl_sync(0xffffffffu, base, leader);
+  if (i >= n) return;
+  const RecOut o = f(i);
+  const int64_t r = pos[i];
   if (o.keep) {
-    const int64_t r = base + __popc(m & ((1u << lane) - 1u));
 #pragma unroll
     for (int k = 0; k < NC; ++k) recs[recIndex(r, k, NC)] = o.c[k];
 #pragma unroll
     for (int k = 0; k < NH; ++k) hot[recIndex(r, k, NH)] = o.h[k];
   }
+  if (i == n - 1) *count = uint32_t(r) + (o.keep ? 1u : 0u);
 }
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_pad_recs(float* recs, float* hot, const uint32_t* count) {
@@ -179,31 +250,45 @@ __global__ void __launch_bounds__(kBlock) k_pad_recs(float* recs, float* hot, co
 }
 
 // ---------------------------------------------------------- mesh prefilter ----
-// The hot kernel: every queued ray of a bundle x every hot record (bounding circle / sphere,
-// nrt_filter.h) of one record set, float32.  Two triangles are evaluated per FFMA2
-// (fma.rn.f32x2): records are pair-interleaved; ray components are scalar operands that the
-// hardware broadcasts to both halves.  Per (ray, triangle) test:
-//   ORIGIN / DIR  1 FADD + 2 FFMA  (2-D point in circle),   GENERAL  1 FADD + 1 FMUL + 6 FFMA
-// plus 0.5 LOP3 (sign accumulation) on the ALU pipe.  Persistent CTAs pull (ray tile x
-// record chunk) work items from an atomic counter; a chunk of hot records is staged in shared
-// memory in 16-byte vectors and read back as warp-broadcast LDS.128; each thread keeps R rays
-// in registers.  Survivors (sign bit of g clear) are appended to the pre-candidate list.
+// The hot kernel: the queued rays of a bundle x the hot records (bounding circle / sphere,
+// nrt_filter.h) of one record set, float32 — a flattened two-level traversal of the mesh.
+//
+// Level 1  Records are stored in Morton order of the face centroids, so the 256 records of a
+//          chunk are a compact patch of the surface with one bound (circle / sphere around the
+//          chunk's circles, same record format and same test).  A warp keeps a RUN of 32 x R
+//          consecutive queue entries (neighbouring pixels) in registers and tests them against
+//          the bounds of a group of <= 32 chunks: R tests per lane per bound, the per-lane pass
+//          bits are OR-reduced across the warp once per group (redux.sync).
+// Level 2  For every chunk some ray of the run can reach, the warp stages the chunk's hot records
+//          into its own shared-memory slice (cp.async, 16-byte vectors, double buffered: the next
+//          admitted chunk is in flight while the current one is evaluated) and evaluates
+//          run x chunk in full: two faces per FFMA2 (fma.rn.f32x2; records are pair-interleaved,
+//          ray components are scalar operands broadcast to both halves), records read back as
+//          warp-broadcast LDS.128.  Per (ray, face) test:
+//            ORIGIN / DIR  2 FFMA (2-D point in circle),   GENERAL  1 FMUL + 6 FFMA
+//          plus the shared compare: max of four left-hand sides against the ray's threshold.
+// Survivors are appended to the pre-candidate list.  Warps are autonomous (no CTA barrier): work
+// items (run, chunk group) come from an atomic counter, run-major so that concurrently running
+// warps touch the same chunks.
 static constexpr int FT_THREADS = 256;
-static constexpr int FT_TC = 256;     // records per shared-memory chunk
-static_assert(kRecPad % FT_TC == 0, "record padding must cover whole shared-memory chunks");
+static constexpr int FT_WARPS = FT_THREADS / 32;
+static constexpr int FT_TC = 256;     // records per chunk
+static_assert(kRecPad == FT_TC, "one bound per shared-memory chunk");
 
 struct PreArgs {
   const float4* hot;        // pair-interleaved hot records, padded to a multiple of kRecPad
+  const float4* bounds;     // one hot-format record per chunk
   const uint32_t* nrec;     // number of records (device)
-  const float4* h0;         // ray plane H0: (x, y, q, 0) | (dh, q)
+  const float4* h0;         // ray plane H0: (x, y, T, 0) | (dh, T)
   const float4* h1;         // ray plane H1: (2 p0, 0)   (GENERAL)
   const uint32_t* qcount;   // queued rays (device)
-  uint32_t* tilectr;        // work-item counter
+  uint32_t* itemctr;        // work-item counter
   uint32_t* prectr;         // pre-candidate counter
+  uint32_t* workctr;        // (run, chunk) pairs evaluated in full
   uint32_t* preRay;
   uint32_t* preRec;
   uint32_t preCap;
-  uint32_t group;           // chunks per work item (double-buffered in shared memory)
+  uint32_t cull;            // 0: every chunk is evaluated (brute force over the record set)
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
@@ -222,42 +307,48 @@ __device__ __forceinline__ float2 prefilterPair(const float2* h, float a0, float
   return ffma2(h[0], dup2(a0), ffma2(h[1], dup2(a1), h[2]));
 }
 
-
 template <int MODE, int R, int U>
 __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
   constexpr int NH = hotFloats(MODE);      // float2 per record pair == float4 per record quad
   constexpr int CH4 = (FT_TC / 4) * NH;    // float4 per chunk
-  __shared__ __align__(16) float4 tile[2][CH4];
-  __shared__ uint32_t s_item;
+  constexpr uint32_t RUN = 32 * R;
+  static_assert(RUN == uint32_t(prefilterRunRays(MODE)), "run size is part of the executed-test accounting");
+  extern __shared__ __align__(16) float4 smem_tiles[];   // [FT_WARPS][2][CH4]
   const uint32_t nq = *a.qcount;
   if (nq == 0) return;
   const uint32_t nrecPadded = uint32_t(paddedFaces(int64_t(*a.nrec)));
   if (nrecPadded == 0) return;
-  constexpr uint32_t RAYS = FT_THREADS * R;
-  const uint32_t nRayTiles = (nq + RAYS - 1) / RAYS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* const tile = smem_tiles + size_t(warp) * 2 * CH4;
+  const uint32_t nRuns = (nq + RUN - 1) / RUN;
   const uint32_t nChunks = nrecPadded / FT_TC;
-  const uint32_t nGroups = (nChunks + a.group - 1) / a.group;
-  const uint32_t nItems = nRayTiles * nGroups;
-  const int tid = threadIdx.x;
-  // asynchronous global -> shared copy of one chunk (cp.async, 16 bytes per thread)
+  // chunk groups of <= 32 chunks (one pass mask); smaller groups when there are too few runs to fill the GPU
+  uint32_t G = 32;
+  const uint32_t totalWarps = gridDim.x * FT_WARPS;
+  while (G > 4 && uint64_t(nRuns) * ((nChunks + G - 1) / G) < 4ull * totalWarps) G >>= 1;
+  const uint32_t nGroups = (nChunks + G - 1) / G;
+  const uint32_t nItems = nRuns * nGroups;
+  uint32_t work = 0;
+  // asynchronous global -> shared copy of one chunk into the warp's slice (16 bytes per lane and step)
   auto stage = [&](uint32_t chunk, int buf) {
     const float4* src = a.hot + size_t(chunk) * CH4;
-    for (int k = tid; k < CH4; k += FT_THREADS) __pipeline_memcpy_async(&tile[buf][k], src + k, 16);
+    float4* dst = tile + buf * CH4;
+#pragma unroll
+    for (int k = 0; k < CH4 / 32; ++k) __pipeline_memcpy_async(dst + k * 32 + lane, src + k * 32 + lane, 16);
     __pipeline_commit();
   };
   for (;;) {
-    if (tid == 0) s_item = atomicAdd(a.tilectr, 1u);
-    __syncthreads();
-    const uint32_t item = s_item;
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(a.itemctr, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= nItems) break;
-    const uint32_t rt = item / nGroups, gr = item - rt * nGroups;
-    const uint32_t c0 = gr * a.group, c1 = min(nChunks, c0 + a.group);
-    stage(c0, 0);
+    const uint32_t run = item / nGroups, gr = item - run * nGroups;
+    const uint32_t c0 = gr * G, c1 = min(nChunks, c0 + G);
     float ra0[R], ra1[R], ra2[R], ra3[R], rb0[R], rb1[R], rb2[R];
     uint32_t ridx[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const uint32_t idx = rt * RAYS + r * FT_THREADS + tid;
+      const uint32_t idx = run * RUN + r * 32 + lane;
       const uint32_t ic = idx < nq ? idx : nq - 1;  // tail: duplicate a real ray, never emit for it
       const float4 p0 = __ldg(a.h0 + ic);
       ra0[r] = p0.x; ra1[r] = p0.y; ra2[r] = p0.z; ra3[r] = p0.w;
@@ -267,13 +358,46 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
       } else { rb0[r] = rb1[r] = rb2[r] = 0.f; }
       ridx[r] = idx < nq ? idx : kInvalidRef;
     }
-    for (uint32_t ch = c0; ch < c1; ++ch) {
-      const int buf = int(ch - c0) & 1;
-      __pipeline_wait_prior(0);
-      __syncthreads();                       // chunk `ch` is in tile[buf]; everyone left tile[buf ^ 1]
-      if (ch + 1 < c1) stage(ch + 1, buf ^ 1);
-      const uint32_t base = ch * FT_TC;
-      const float4* tl = tile[buf];
+    // ---- level 1: chunk bounds ----
+    uint32_t mask;
+    if (a.cull) {
+      uint32_t mine = 0;
+      for (uint32_t c = c0; c < c1; ++c) {
+        const float4 bd = __ldg(a.bounds + c);
+        bool p = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (MODE == FM_GENERAL) {
+            const float sdot = fmaf(bd.x, ra0[r], fmaf(bd.y, ra1[r], bd.z * ra2[r]));
+            const float tt = fmaf(bd.x, rb0[r], fmaf(bd.y, rb1[r], fmaf(bd.z, rb2[r], bd.w)));
+            p = p || (fmaf(sdot, sdot, tt) >= ra3[r]);
+          } else {
+            p = p || (fmaf(bd.x, ra0[r], fmaf(bd.y, ra1[r], bd.z)) >= ra2[r]);
+          }
+        }
+        mine |= uint32_t(p) << (c - c0);
+      }
+      mask = __reduce_or_sync(0xffffffffu, mine);
+    } else {
+      mask = (c1 - c0 >= 32) ? 0xffffffffu : ((1u << (c1 - c0)) - 1u);
+    }
+    work += uint32_t(__popc(mask));
+    // ---- level 2: run x admitted chunks ----
+    int buf = 0;
+    int cur = -1;
+    if (mask) { cur = __ffs(mask) - 1; mask &= mask - 1; stage(c0 + cur, 0); }
+    while (cur >= 0) {
+      int nxt = -1;
+      if (mask) {
+        nxt = __ffs(mask) - 1; mask &= mask - 1;
+        stage(c0 + nxt, buf ^ 1);
+        __pipeline_wait_prior(1);
+      } else {
+        __pipeline_wait_prior(0);
+      }
+      __syncwarp();                            // chunk `cur` is in the slice for every lane
+      const uint32_t base = (c0 + cur) * FT_TC;
+      const float4* tl = tile + buf * CH4;
 #pragma unroll U
       for (int t = 0; t < FT_TC / 4; ++t) {
         float2 q[2 * NH];   // two record pairs: q[j * NH + k] = coefficient k of pair j
@@ -313,9 +437,12 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
           }
         }
       }
+      __syncwarp();                            // every lane left the slice before it is staged again
+      buf ^= 1;
+      cur = nxt;
     }
-    __syncthreads();   // everyone is done with both tiles and `s_item` before the next item
   }
+  if (lane == 0 && work) atomicAdd(a.workctr, work);
 }
 
 // clamp -> sRGB -> 8 bit (utils/framebuf.nim:74-78, utils/color.nim:17-22)
@@ -358,7 +485,10 @@ struct CudaBackend {
   std::vector<int> filterModes;
   int gridPerSm = 3;   // resident prefilter CTAs per SM (NRT_PREFILTER_CTAS_PER_SM)
   int gridGeneral = 2;
-  int chunkGroup = 1;  // NRT_PREFILTER_GROUP: 256-record chunks per work item (small items balance best)
+  bool cull = true;    // NRT_PREFILTER_CULL=0: evaluate every chunk (brute force over the record set)
+  bool smemOptIn = false;
+  void* scratchPtr[2] = {nullptr, nullptr};
+  size_t scratchBytes[2] = {0, 0};
 
   struct Atom {
     static __device__ __forceinline__ void min64(uint64_t* p, uint64_t v) {
@@ -406,39 +536,88 @@ struct CudaBackend {
     k_for_each_counted<F><<<unsigned(sms * 8), kBlock, 0, stream>>>(f, count, cap);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
+  // grow-only scratch buffers (temp storage of cub, keep flags, sort keys)
+  void* scratch(int slot, size_t bytes) {
+    if (scratchBytes[slot] < bytes) {
+      use();
+      NRT_CUDA(cudaStreamSynchronize(stream));
+      if (scratchPtr[slot]) NRT_CUDA(cudaFree(scratchPtr[slot]));
+      scratchPtr[slot] = nullptr; scratchBytes[slot] = 0;
+      const size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 16);
+      NRT_CUDA(cudaMalloc(&scratchPtr[slot], want));
+      scratchBytes[slot] = want;
+    }
+    return scratchPtr[slot];
+  }
   void gate(const Gate& g, const uint32_t* count, int64_t n, int mult, int nMO, uint32_t* cnt) {
     use();
-    const unsigned grid = count ? unsigned(sms * 8) : blocksFor(n);
     if (!count && n <= 0) return;
-    k_gate<<<grid, kBlock, 0, stream>>>(g, count, n, mult, nMO, cnt);
-    NRT_CUDA(cudaGetLastError()); ++launches;
+    const ChunkState& cs = g.cs;
+    const int rows = nMO * (2 + cs.nL);
+    const unsigned grid = count ? unsigned(sms * 8) : blocksFor(n);
+    k_gate_flags<<<grid, kBlock, sizeof(uint32_t) * rows, stream>>>(g, count, n, mult, nMO);
+    k_gate_scan<<<unsigned(rows), 1024, 0, stream>>>(cs, count, n, mult, cnt);
+    k_gate_write<<<grid, kBlock, 0, stream>>>(g, count, n, mult, nMO);
+    NRT_CUDA(cudaGetLastError()); launches += 3;
+  }
+  // Morton order of the face centroids -> m.order (stable: ties keep face order)
+  void sortFaces(const DMesh& m) {
+    use();
+    const int64_t n = m.nfaces;
+    uint32_t* keys = static_cast<uint32_t*>(scratch(1, sizeof(uint32_t) * 3 * n));
+    uint32_t* keys2 = keys + n; uint32_t* idx = keys + 2 * n;
+    k_for_each<FaceKeys><<<blocksFor(n), kBlock, 0, stream>>>(FaceKeys{m, keys, idx}, n);
+    size_t tb = 0;
+    NRT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, idx, m.order, int(n), 0, 30, stream));
+    void* tmp = scratch(0, tb);
+    NRT_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, idx, m.order, int(n), 0, 30, stream));
+    NRT_CUDA(cudaGetLastError()); launches += 2;
   }
   template <class F> void compactRecs(int64_t n, const F& f, float* recs, float* hot, int mode, uint32_t* count) {
     use();
+    uint32_t* flag = static_cast<uint32_t*>(scratch(1, sizeof(uint32_t) * 2 * n));
+    uint32_t* pos = flag + n;
+    k_rec_flags<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, flag);
+    size_t tb = 0;
+    NRT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flag, pos, int(n), stream));
+    void* tmp = scratch(0, tb);
+    NRT_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, flag, pos, int(n), stream));
     if (mode == FM_ORIGIN) {
-      k_compact_recs<F, FM_ORIGIN><<<blocksFor(n), kBlock, 0, stream>>>(f, n, recs, hot, count);
+      k_rec_scatter<F, FM_ORIGIN><<<blocksFor(n), kBlock, 0, stream>>>(f, n, pos, recs, hot, count);
       k_pad_recs<FM_ORIGIN><<<1, kBlock, 0, stream>>>(recs, hot, count);
     } else {
-      k_compact_recs<F, FM_DIR><<<blocksFor(n), kBlock, 0, stream>>>(f, n, recs, hot, count);
+      k_rec_scatter<F, FM_DIR><<<blocksFor(n), kBlock, 0, stream>>>(f, n, pos, recs, hot, count);
       k_pad_recs<FM_DIR><<<1, kBlock, 0, stream>>>(recs, hot, count);
     }
-    NRT_CUDA(cudaGetLastError()); launches += 2;
+    NRT_CUDA(cudaGetLastError()); launches += 4;
+  }
+  // next bounce's active list: samples with active == 1, in sample order (count on the device)
+  void compactActive(const ChunkState& cs, int64_t nS, uint32_t* list, uint32_t* count) {
+    use();
+    thrust::counting_iterator<uint32_t> ids(0u);
+    size_t tb = 0;
+    NRT_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids, cs.active, list, count, int(nS), stream));
+    void* tmp = scratch(0, tb);
+    NRT_CUDA(cub::DeviceSelect::Flagged(tmp, tb, ids, cs.active, list, count, int(nS), stream));
+    ++launches;
   }
   // prefilter launch for one ray bundle of one mesh object
-  void filter(int mode, const float* hot, const uint32_t* nrec, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
+  void filter(int mode, const float* hot, const float* bounds, const uint32_t* nrec, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
     use();
     PreArgs a;
     a.hot = reinterpret_cast<const float4*>(hot);
+    a.bounds = reinterpret_cast<const float4*>(bounds);
     a.nrec = nrec;
     const int64_t base = queueBase(cs, mo, b);
     a.h0 = reinterpret_cast<const float4*>(cs.qhot0) + base;
     a.h1 = reinterpret_cast<const float4*>(cs.qhot1) + int64_t(mo) * cs.NR;
     a.qcount = cnt + cntQueue(b);
-    a.tilectr = cnt + cntTile(b);
+    a.itemctr = cnt + cntTile(b);
     a.prectr = cnt + cntPre(b);
+    a.workctr = cnt + cntWork(b);
     a.preRay = cs.preRay; a.preRec = cs.preRec;
     a.preCap = uint32_t(std::min<int64_t>(cs.preCap, 0xFFFFFFFFll));
-    a.group = uint32_t(chunkGroup);
+    a.cull = cull ? 1u : 0u;
     if (filterUsed == filterEvents.size()) {
       cudaEvent_t e0, e1;
       NRT_CUDA(cudaEventCreate(&e0)); NRT_CUDA(cudaEventCreate(&e1));
@@ -448,10 +627,18 @@ struct CudaBackend {
     auto& ev = filterEvents[filterUsed];
     filterModes[filterUsed++] = mode;
     NRT_CUDA(cudaEventRecord(ev.first, stream));
-    // tuned on B200 (tools/frame_breakdown.py): 2-D bundles 8 rays/thread, 3 CTAs/SM; GENERAL 4 rays/thread, 2 CTAs/SM
-    if (mode == FM_GENERAL) k_mesh_prefilter<FM_GENERAL, 4, 2><<<unsigned(sms * gridGeneral), FT_THREADS, 0, stream>>>(a);
-    else if (mode == FM_ORIGIN) k_mesh_prefilter<FM_ORIGIN, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, 0, stream>>>(a);
-    else k_mesh_prefilter<FM_DIR, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, 0, stream>>>(a);
+    // per-warp double-buffered chunk slices: 2-D bundles 8 rays/lane (48 KiB/CTA, 3 CTAs/SM); GENERAL 4 rays/lane (64 KiB/CTA, 2 CTAs/SM)
+    constexpr size_t sm2d = size_t(FT_WARPS) * 2 * (FT_TC / 4) * 3 * sizeof(float4);
+    constexpr size_t smGen = size_t(FT_WARPS) * 2 * (FT_TC / 4) * 4 * sizeof(float4);
+    if (!smemOptIn) {
+      NRT_CUDA(cudaFuncSetAttribute(k_mesh_prefilter<FM_GENERAL, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smGen)));
+      NRT_CUDA(cudaFuncSetAttribute(k_mesh_prefilter<FM_ORIGIN, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2d)));
+      NRT_CUDA(cudaFuncSetAttribute(k_mesh_prefilter<FM_DIR, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2d)));
+      smemOptIn = true;
+    }
+    if (mode == FM_GENERAL) k_mesh_prefilter<FM_GENERAL, 4, 2><<<unsigned(sms * gridGeneral), FT_THREADS, smGen, stream>>>(a);
+    else if (mode == FM_ORIGIN) k_mesh_prefilter<FM_ORIGIN, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, sm2d, stream>>>(a);
+    else k_mesh_prefilter<FM_DIR, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, sm2d, stream>>>(a);
     NRT_CUDA(cudaGetLastError()); ++launches;
     NRT_CUDA(cudaEventRecord(ev.second, stream));
   }
@@ -470,6 +657,7 @@ struct CudaBackend {
     cudaSetDevice(device);
     for (auto& e : filterEvents) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     filterEvents.clear();
+    for (int k = 0; k < 2; ++k) { if (scratchPtr[k]) cudaFree(scratchPtr[k]); scratchPtr[k] = nullptr; scratchBytes[k] = 0; }
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -523,7 +711,7 @@ static int initLocked(int ngpu, const int* ids) {
       d->be.device = id;
       d->be.sms = p.multiProcessorCount;
       if (const char* e = std::getenv("NRT_PREFILTER_CTAS_PER_SM")) d->be.gridPerSm = std::max(1, std::atoi(e));
-      if (const char* e = std::getenv("NRT_PREFILTER_GROUP")) d->be.chunkGroup = std::max(1, std::atoi(e));
+      if (const char* e = std::getenv("NRT_PREFILTER_CULL")) d->be.cull = std::atoi(e) != 0;
       NRT_CUDA(cudaSetDevice(id));
       NRT_CUDA(cudaStreamCreateWithFlags(&d->be.stream, cudaStreamNonBlocking));
       NRT_CUDA(cudaEventCreate(&d->ev0)); NRT_CUDA(cudaEventCreate(&d->ev1));

@@ -119,6 +119,8 @@ struct DMesh {
   double L;                 // filter length scale (max AABB half extent)
   float* recs;              // GENERAL-mode full filter records (nrt_filter.h), pair-interleaved
   float* hot;               // GENERAL-mode hot (bounding sphere) records, pair-interleaved
+  float* bounds;            // GENERAL-mode chunk bounds (one hot-format record per 256 records)
+  uint32_t* order;          // faces in Morton order of their centroids: record r <-> face order[r]
 };
 
 struct BundleFrame;  // nrt_filter.h

@@ -248,6 +248,9 @@ NRT_HD uint32_t filterTest(int mode, const float* q, const float* a, const float
 // floats per hot record (pair-interleaved like the full records)
 NRT_HD constexpr int hotFloats(int mode) { return mode == FM_GENERAL ? 4 : 3; }
 NRT_HD constexpr int prefilterFlops(int mode) { return mode == FM_GENERAL ? 13 : 4; }
+// Rays of one prefilter "run": the consecutive queue entries one warp keeps in registers (32 lanes x
+// 8 or 4 rays) and decides chunk culling for (nrt.cu: k_mesh_prefilter; mirrored by the emulation).
+NRT_HD constexpr int prefilterRunRays(int mode) { return mode == FM_GENERAL ? 128 : 256; }
 
 // Shared frame of a ray bundle (object space), built on the host in float64.
 struct BundleFrame {
@@ -408,6 +411,81 @@ NRT_HD bool makeHotRay(int mode, const BundleFrame& fr, const Ray& r, HotRay& h)
   h.a0 = (float)dh[0]; h.a1 = (float)dh[1]; h.a2 = (float)dh[2]; h.a3 = -roundUpSigned(q);   // threshold T = -q
   h.b0 = (float)(2.0 * p0[0]); h.b1 = (float)(2.0 * p0[1]); h.b2 = (float)(2.0 * p0[2]);
   return true;
+}
+
+// ---- spatial order + chunk bounds (two-level flattened traversal of a record set) ----
+// Records are stored in Morton order of the face centroids, so the kRecPad (256) consecutive
+// records of a shared-memory chunk are spatially compact; one extra hot-format record per chunk
+// encloses all of the chunk's circles / spheres.  A warp tests its rays against the chunk bound
+// first and skips the chunk when none of them can reach it.
+NRT_HD uint32_t expandBits10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+NRT_HD uint32_t mortonKey(const DMesh& m, const double* p0, const double* p1, const double* p2) {
+  uint32_t q[3];
+  for (int k = 0; k < 3; ++k) {
+    const double c = (p0[k] + p1[k] + p2[k]) * (1.0 / 3.0), ext = m.bmax[k] - m.bmin[k];
+    double t = (ext > 0) ? (c - m.bmin[k]) / ext : 0.0;
+    if (!(t > 0)) t = 0;          // also NaN
+    if (t > 0.999999) t = 0.999999;
+    q[k] = uint32_t(t * 1024.0);
+  }
+  return (expandBits10(q[0]) << 2) | (expandBits10(q[1]) << 1) | expandBits10(q[2]);
+}
+
+// Bound of chunk `ch` (records [ch*kRecPad, (ch+1)*kRecPad)) of a hot record array, in hot-record
+// format: a circle / sphere (C, R) around the records' own circles {centre c, rho^2 = c0m + |c|^2}
+// (2-D: c = (h0, h1)/2; GENERAL: c = h[0..2], rho^2 = K0m + |c|^2; rho >= the face's true radius
+// because c0m carries the face margin).  A ray that truly hits a face of the chunk lies within
+// d + rho <= R / (1 + 1e-6) of C, and the float32 evaluation of the bound test carries the same
+// margins as a record's, so it passes: culling by the bound never loses a hit.
+NRT_HD void chunkBound(int mode, const float* hot, int64_t ch, float* b) {
+  const int nh = hotFloats(mode), dim = (mode == FM_GENERAL) ? 3 : 2, last = nh - 1;
+  const double half = (mode == FM_GENERAL) ? 1.0 : 0.5;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  int64_t n = 0;
+  bool always = false;
+  for (int64_t r = ch * kRecPad; r < (ch + 1) * kRecPad; ++r) {
+    const float k0 = hot[recIndex(r, last, nh)];
+    if (k0 <= -1e29f) continue;             // never-hit padding
+    if (k0 >= 1e29f) { always = true; break; }
+    double c[3] = {0, 0, 0}, c2 = 0;
+    for (int k = 0; k < dim; ++k) { c[k] = half * double(hot[recIndex(r, k, nh)]); c2 += c[k] * c[k]; }
+    const double rho2 = double(k0) + c2, rho = rho2 > 0 ? sqrt(rho2) : 0.0;
+    for (int k = 0; k < dim; ++k) { lo[k] = fmin(lo[k], c[k] - rho); hi[k] = fmax(hi[k], c[k] + rho); }
+    ++n;
+  }
+  if (always) { alwaysHot(mode, b); return; }
+  if (n == 0) { neverHitHot(mode, b); return; }
+  // centre of the box around the circles (tighter than their mean for elongated chunks)
+  double C[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), dim == 3 ? 0.5 * (lo[2] + hi[2]) : 0.0};
+  double R = 0;
+  for (int64_t r = ch * kRecPad; r < (ch + 1) * kRecPad; ++r) {
+    const float k0 = hot[recIndex(r, last, nh)];
+    if (k0 <= -1e29f) continue;
+    double c2 = 0, d2 = 0;
+    for (int k = 0; k < dim; ++k) {
+      const double c = half * double(hot[recIndex(r, k, nh)]);
+      c2 += c * c; d2 += (c - C[k]) * (c - C[k]);
+    }
+    const double rho2 = double(k0) + c2;
+    const double rho = rho2 > 0 ? sqrt(rho2) : 0.0;
+    R = fmax(R, sqrt(d2) + rho);
+  }
+  R *= 1.0 + 1e-6;
+  const double C2 = C[0] * C[0] + C[1] * C[1] + (dim == 3 ? C[2] * C[2] : 0.0), r2 = R * R, k0 = r2 - C2;
+  if (!(C2 < 1e29) || !(r2 < 1e29)) { alwaysHot(mode, b); return; }
+  if (mode == FM_GENERAL) {
+    const double mt = 32.0 * kFilterU * C2 + 8.0 * kFilterU * fabs(k0) + 8.0 * kFilterU * r2;
+    b[0] = (float)C[0]; b[1] = (float)C[1]; b[2] = (float)C[2]; b[3] = roundUpSigned(k0 + mt);
+  } else {
+    const double mt = 8.0 * kFilterU * (2.0 * C2 + fabs(k0)) + 8.0 * kFilterU * r2;
+    b[0] = (float)(2.0 * C[0]); b[1] = (float)(2.0 * C[1]); b[2] = roundUpSigned(k0 + mt);
+  }
 }
 
 // Scalar statement of one prefilter test (the CUDA kernel evaluates two records per FFMA2 with

@@ -26,14 +26,15 @@ namespace nrt {
 
 enum WaveKind { WAVE_PATH = 0, WAVE_SHADOW = 1 };
 
-// Counter block per (wave, mesh object): [EXACT, CAND, then (QUEUE_b, TILE_b, PRE_b) per ray bundle b].
+// Counter block per (wave, mesh object): [EXACT, CAND, then (QUEUE_b, TILE_b, PRE_b, WORK_b) per ray bundle b].
 // Bundle 0 holds arbitrary rays (GENERAL mode; ORIGIN mode for the primary wave, whose rays share
 // the camera origin); bundle 1 + l holds the shadow rays of DistantLight l (DIR mode).
 enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_BUNDLE0 = 2 };
-NRT_HD int cntStride(int nL) { return CNT_BUNDLE0 + 3 * (1 + nL); }
-NRT_HD int cntQueue(int b) { return CNT_BUNDLE0 + 3 * b; }      // rays queued for the bundle
-NRT_HD int cntTile(int b) { return CNT_BUNDLE0 + 3 * b + 1; }   // prefilter work-item counter
-NRT_HD int cntPre(int b) { return CNT_BUNDLE0 + 3 * b + 2; }    // pre-candidates (prefilter survivors)
+NRT_HD int cntStride(int nL) { return CNT_BUNDLE0 + 4 * (1 + nL); }
+NRT_HD int cntQueue(int b) { return CNT_BUNDLE0 + 4 * b; }      // rays queued for the bundle
+NRT_HD int cntTile(int b) { return CNT_BUNDLE0 + 4 * b + 1; }   // prefilter work-item counter
+NRT_HD int cntPre(int b) { return CNT_BUNDLE0 + 4 * b + 2; }    // pre-candidates (prefilter survivors)
+NRT_HD int cntWork(int b) { return CNT_BUNDLE0 + 4 * b + 3; }   // (ray run, chunk) pairs the prefilter evaluated in full
 // Stats slots
 enum { ST_PRIMARY = 0, ST_TESTS = 1, ST_HITS = 2, ST_RAYS = 3, ST_CAPPED = 4, ST_CONT = 5, ST_COUNT = 8 };
 
@@ -80,6 +81,12 @@ struct ChunkState {
   uint32_t* preRay;  // preCap
   uint32_t* preRec;  // preCap
   uint32_t* xref;    // nMO*NR     exact (float64 brute force) queue
+  // ordered queue compaction (CUDA backend): gate pass 1 writes a code per (mesh object, wave
+  // position) and per-block counts; a scan turns the counts into queue offsets; pass 2 writes the
+  // rays, so queue order == wave order (scanline order): consecutive queue entries are neighbours.
+  uint8_t* gflag;    // nMO*NR     0 none, 1 + b filter bundle b, 255 exact
+  uint32_t* gcnt;    // nMO*(2+nL) rows x (gvb + 1): per 256-ray block counts, then their exclusive scan
+  int64_t gvb;       // blocks per row (capacity)
   // candidates of the current (wave, mesh object)
   uint32_t* candRef; // candCap
   uint32_t* candTri; // candCap
@@ -321,7 +328,7 @@ struct ExactMesh {
 // ---- refine: float32 sign test (nrt_filter.h: filterTest) on the prefilter survivors ----
 template <class A>
 struct Refine {
-  ChunkState cs; int mode; const float* recs; int mo; int b; uint32_t* candCount;
+  ChunkState cs; int mode; const float* recs; const uint32_t* ids; int mo; int b; uint32_t* candCount;
   NRT_HD void operator()(int64_t i) const {
     const uint32_t rq = cs.preRay[i], pos = cs.preRec[i];
     const int nc = recFloats(mode);
@@ -332,7 +339,7 @@ struct Refine {
     const float* p1 = cs.qray1 + 4 * (int64_t(mo) * cs.NR + rq);   // read only in GENERAL mode (b == 0)
     const uint32_t x = filterTest(mode, q, p0, p1, p0[3]);
     if (int32_t(x) < 0) return;
-    uint32_t tri = pos;
+    uint32_t tri = ids ? ids[pos] : pos;   // GENERAL: record position -> face through the Morton order
     if (recSlotId(mode) >= 0) tri = fbits(q[recSlotId(mode)]);
     const uint32_t slot = A::add32(candCount, 1u);
     if (slot < cs.candCap) { cs.candRef[slot] = cs.qref[at]; cs.candTri[slot] = tri; }
@@ -464,10 +471,11 @@ struct Shade {
 };
 
 // ---- resolve: shadow tests + diffuse + reflection set-up (renderer.nim:90-127)
-template <class A>
+// Samples whose path continues keep active == 1; the backend compacts them IN SAMPLE ORDER into
+// the next bounce's active list (compactActive), so reflection rays of neighbouring pixels stay
+// neighbours in the queues.
 struct Resolve {
   const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
-  uint32_t* nextList; uint32_t* nextCount;   // continuing samples for the next bounce
   NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
     if (idx >= activeN(act)) return st;
@@ -510,7 +518,6 @@ struct Resolve {
       cs.bounce[s] = bounce + 1;
       cs.active[s] = 1;
       st.v[ST_CONT] = 1;
-      nextList[A::add32(nextCount, 1u)] = uint32_t(s);
     } else {
       cs.active[s] = 0;
     }
@@ -550,12 +557,22 @@ struct Finalize {
 // ---- filter records (nrt_filter.h), one element per face (or per padding slot) ----
 struct RecOut { bool keep; float c[16]; float h[4]; };
 
-// GENERAL: depends on the mesh only; stored at its own index (face id == record index).
+// Morton keys of the faces (record order).
+struct FaceKeys {
+  DMesh m; uint32_t* keys; uint32_t* idx;
+  NRT_HD void operator()(int64_t f) const {
+    keys[f] = mortonKey(m, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2]);
+    idx[f] = uint32_t(f);
+  }
+};
+
+// GENERAL: depends on the mesh only; record r holds face order[r] (no culling).
 struct BuildRecsGeneral {
   DMesh m;
-  NRT_HD void operator()(int64_t f) const {
+  NRT_HD void operator()(int64_t r) const {
     float c[16], h[4];
-    if (f < m.nfaces) {
+    if (r < m.nfaces) {
+      const int64_t f = m.order[r];
       const double *p0 = m.verts + 4 * m.vidx[3 * f], *p1 = m.verts + 4 * m.vidx[3 * f + 1], *p2 = m.verts + 4 * m.vidx[3 * f + 2];
       makeRecGeneral(m, p0, p1, p2, c);
       BundleFrame fr;
@@ -566,18 +583,20 @@ struct BuildRecsGeneral {
       neverHitRecord(FM_GENERAL, c);
       neverHitHot(FM_GENERAL, h);
     }
-    for (int k = 0; k < 16; ++k) m.recs[recIndex(f, k, 16)] = c[k];
-    for (int k = 0; k < 4; ++k) m.hot[recIndex(f, k, 4)] = h[k];
+    for (int k = 0; k < 16; ++k) m.recs[recIndex(r, k, 16)] = c[k];
+    for (int k = 0; k < 4; ++k) m.hot[recIndex(r, k, 4)] = h[k];
   }
 };
 
-// ORIGIN: per (mesh object, camera): culled against the shared origin; compacted by the backend.
+// ORIGIN: per (mesh object, camera): culled against the shared origin.  Called with the Morton
+// rank r; the backend compacts the kept records preserving that order.
 struct BuildRecsOrigin {
   const DScene* sc; int mo;
-  NRT_HD RecOut operator()(int64_t f) const {
+  NRT_HD RecOut operator()(int64_t r) const {
     RecOut o;
     const DObject& ob = sc->objects[sc->mesh_obj_index[mo]];
     const DMesh& m = sc->meshes[ob.mesh];
+    const int64_t f = m.order[r];
     const V4 ow = mulm(sc->c2w, v4(0.0, 0.0, 0.0, 1.0));   // castPrimaryRay's origin (renderer.nim:42)
     const V4 oo = mulm(ob.w2o, ow);                        // trace()'s object-space origin (renderer.nim:54)
     const double O[3] = {oo.x, oo.y, oo.z};
@@ -598,10 +617,11 @@ struct BuildRecsOrigin {
 // DIR: per (mesh object, DistantLight l): culled by det < 1e-6 for the shared direction.
 struct BuildRecsDir {
   const DScene* sc; int mo; int l;
-  NRT_HD RecOut operator()(int64_t f) const {
+  NRT_HD RecOut operator()(int64_t r) const {
     RecOut o;
     const DObject& ob = sc->objects[sc->mesh_obj_index[mo]];
     const DMesh& m = sc->meshes[ob.mesh];
+    const int64_t f = m.order[r];
     const DLight& li = sc->lights[l];
     const V4 dw = scale(v4(li.dir[0], li.dir[1], li.dir[2], li.dir[3]), -1.0);   // renderer.nim:96
     const V4 dobj = mulm(ob.w2o, dw);                                             // renderer.nim:55
@@ -612,6 +632,17 @@ struct BuildRecsDir {
     makeHotRec(FM_DIR, sc->frames[frameIndex(sc->nlights, mo, FM_DIR, l)], p0, p1, p2, o.h);
     if (!(o.c[8] < 1e29f)) alwaysHot(FM_DIR, o.h);
     return o;
+  }
+};
+
+// Chunk bounds of a record set (one element per chunk of the padded record list).
+struct BuildBounds {
+  int mode; const float* hot; const uint32_t* count; float* bounds;
+  NRT_HD void operator()(int64_t ch) const {
+    float b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ch * kRecPad < paddedFaces(int64_t(*count))) chunkBound(mode, hot, ch, b);
+    else neverHitHot(mode, b);
+    for (int k = 0; k < 4; ++k) bounds[4 * ch + k] = b[k];
   }
 };
 

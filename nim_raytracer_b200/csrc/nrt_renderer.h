@@ -41,7 +41,7 @@ struct SceneData {
   bool anyReflective = false, anyPointLight = false;
   int64_t bytes_uploaded = 0;
   // Filter record sets per mesh object (device): ORIGIN (camera) and DIR per DistantLight.
-  struct MoRecs { float* origin = nullptr; float* originHot = nullptr; std::vector<float*> dir, dirHot; };
+  struct MoRecs { float* origin = nullptr; float* originHot = nullptr; float* originBounds = nullptr; std::vector<float*> dir, dirHot, dirBounds; };
   std::vector<BundleFrame> frames;        // host copy, [mo * recStride() + j]
   BundleFrame* dFrames = nullptr;
   bool anyGeneralShadow = false;          // some shadow rays need the GENERAL bundle (point light / unusable frame)
@@ -55,6 +55,10 @@ struct SceneData {
   const float* hotOf(int mo, int mode, int l) const {
     return mode == FM_GENERAL ? meshes[objs[moIndex[mo]].mesh].hot : (mode == FM_ORIGIN ? moRecs[mo].originHot : moRecs[mo].dirHot[l]);
   }
+  const float* boundsOf(int mo, int mode, int l) const {
+    return mode == FM_GENERAL ? meshes[objs[moIndex[mo]].mesh].bounds : (mode == FM_ORIGIN ? moRecs[mo].originBounds : moRecs[mo].dirBounds[l]);
+  }
+  static int64_t numChunks(int64_t nfaces) { return paddedFaces(nfaces) / kRecPad; }
   bool frameValid(int mo, int mode, int l) const { return frames[frameIndex(h.nlights, mo, mode, l)].valid > 0; }
 
   static bool makeBasis(const double* axis, BundleFrame& fr) {
@@ -134,6 +138,8 @@ struct SceneData {
       dm.nidx = up(m.normal_idx, m.nfaces * 3, reuse ? const_cast<int64_t*>(old[i].nidx) : nullptr);
       dm.recs = up<float>(nullptr, paddedFaces(m.nfaces) * recFloats(FM_GENERAL), reuse ? old[i].recs : nullptr);
       dm.hot = up<float>(nullptr, paddedFaces(m.nfaces) * hotFloats(FM_GENERAL), reuse ? old[i].hot : nullptr);
+      dm.bounds = up<float>(nullptr, std::max<int64_t>(1, numChunks(m.nfaces)) * 4, reuse ? old[i].bounds : nullptr);
+      dm.order = up<uint32_t>(nullptr, std::max<int64_t>(1, m.nfaces), reuse ? old[i].order : nullptr);
       calcAABB(m.vertices, m.nverts, dm.bmin, dm.bmax);
       double L = 0;
       for (int k = 0; k < 3; ++k) {
@@ -242,6 +248,9 @@ struct SceneData {
     d = up(&h, 1, reuse ? d : nullptr);
     // ---- filter records: GENERAL per mesh; ORIGIN / DIR per mesh object (device-side build) ----
     for (auto& m : meshes)
+      if (m.nfaces > 0) be->sortFaces(m);   // fills m.order (Morton order of the face centroids)
+    dMeshes = up(meshes.data(), int64_t(meshes.size()), dMeshes);   // (the device copy was uploaded above with the same pointers)
+    for (auto& m : meshes)
       if (m.nfaces > 0) be->forEach(paddedFaces(m.nfaces), BuildRecsGeneral{m});
     const int nMO = int(moIndex.size()), rs = recStride();
     moRecs.assign(nMO, MoRecs{});
@@ -253,6 +262,8 @@ struct SceneData {
       MoRecs& r = moRecs[mo];
       r.origin = up<float>(nullptr, paddedFaces(nf) * recFloats(FM_ORIGIN), reuse ? oldRecs[mo].origin : nullptr);
       r.originHot = up<float>(nullptr, paddedFaces(nf) * hotFloats(FM_ORIGIN), reuse ? oldRecs[mo].originHot : nullptr);
+      r.originBounds = up<float>(nullptr, std::max<int64_t>(1, numChunks(nf)) * 4, reuse ? oldRecs[mo].originBounds : nullptr);
+      r.dirBounds.assign(size_t(desc->nlights), nullptr);
       r.dir.assign(size_t(desc->nlights), nullptr);
       r.dirHot.assign(size_t(desc->nlights), nullptr);
       if (nf > 0 && frameValid(mo, FM_ORIGIN, 0))
@@ -261,8 +272,19 @@ struct SceneData {
         if (lights[l].kind != NRT_LIGHT_DISTANT || !frameValid(mo, FM_DIR, l)) continue;
         r.dir[l] = up<float>(nullptr, paddedFaces(nf) * recFloats(FM_DIR), reuse ? oldRecs[mo].dir[l] : nullptr);
         r.dirHot[l] = up<float>(nullptr, paddedFaces(nf) * hotFloats(FM_DIR), reuse ? oldRecs[mo].dirHot[l] : nullptr);
+        r.dirBounds[l] = up<float>(nullptr, std::max<int64_t>(1, numChunks(nf)) * 4, reuse ? oldRecs[mo].dirBounds[l] : nullptr);
         if (nf > 0) be->compactRecs(nf, BuildRecsDir{d, mo, l}, r.dir[l], r.dirHot[l], FM_DIR, dRecCount + mo * rs + 2 + l);
       }
+    }
+    // chunk bounds of every record set (after the records exist)
+    for (int mo = 0; mo < nMO; ++mo) {
+      const DMesh& m = meshes[objs[moIndex[mo]].mesh];
+      const int64_t nch = numChunks(m.nfaces);
+      if (nch == 0) continue;
+      be->forEach(nch, BuildBounds{FM_GENERAL, m.hot, dRecCount + mo * rs, m.bounds});
+      if (frameValid(mo, FM_ORIGIN, 0)) be->forEach(nch, BuildBounds{FM_ORIGIN, moRecs[mo].originHot, dRecCount + mo * rs + 1, moRecs[mo].originBounds});
+      for (int l = 0; l < desc->nlights; ++l)
+        if (moRecs[mo].dirHot[l]) be->forEach(nch, BuildBounds{FM_DIR, moRecs[mo].dirHot[l], dRecCount + mo * rs + 2 + l, moRecs[mo].dirBounds[l]});
     }
     be->download(hRecCount.data(), dRecCount, sizeof(uint32_t) * hRecCount.size());
     return NRT_OK;
@@ -316,6 +338,9 @@ struct Renderer {
       cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * cntStride(nL));
       cs.alist = al<uint32_t>(2 * S); cs.acount = al<uint32_t>(waves + 2);
       cs.stats = al<unsigned long long>(ST_COUNT);
+      cs.gvb = (NR + 255) / 256 + 1;
+      cs.gflag = al<uint8_t>(m);
+      cs.gcnt = al<uint32_t>(int64_t(std::max(nMO, 1)) * (2 + nL) * (cs.gvb + 1));
       dRows = al<int32_t>(nrows);
     }
     cs.S = capS; cs.NR = capNR; cs.QCAP = capNR + int64_t(nL) * capS; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.preCap = 4 * capCand; cs.rows = dRows;
@@ -336,9 +361,10 @@ struct Renderer {
       if (!force_exact) {
         // prefilter (hot) -> refine (float32 sign test) per ray bundle; both feed the candidate list of (wave, mo)
         auto run = [&](int mode, int l, int b) {
-          be->filter(mode, sd.hotOf(mo, mode, l), sd.recCountOf(mo, mode, l), cs, mo, b, c);
+          be->filter(mode, sd.hotOf(mo, mode, l), sd.boundsOf(mo, mode, l), sd.recCountOf(mo, mode, l), cs, mo, b, c);
           be->forEachCounted(c + cntPre(b), cs.preCap,
-                             Refine<typename BE::Atom>{cs, mode, sd.recsOf(mo, mode, l), mo, b, c + CNT_CAND});
+                             Refine<typename BE::Atom>{cs, mode, sd.recsOf(mo, mode, l), mode == FM_GENERAL ? m.order : nullptr,
+                                                       mo, b, c + CNT_CAND});
         };
         if (kind == WAVE_PATH) {
           const int mode = (primary && sd.frameValid(mo, FM_ORIGIN, 0)) ? FM_ORIGIN : FM_GENERAL;
@@ -419,8 +445,9 @@ struct Renderer {
           be->forEachStats(cnt, act.n, Shade{sd.d, fp, cs, act}, cs.stats);
           if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, false, force_exact);
           ++wave;
-          be->forEachStats(cnt, act.n, Resolve<typename BE::Atom>{sd.d, fp, cs, act, nextList, nextCount}, cs.stats);
+          be->forEachStats(cnt, act.n, Resolve{sd.d, fp, cs, act}, cs.stats);
           if (bounce >= maxBounces) break;
+          be->compactActive(cs, nS, nextList, nextCount);
           uint32_t cont = 0;
           be->download(&cont, nextCount, sizeof(cont));
           if (cont == 0) break;  // no sample continued
@@ -446,7 +473,11 @@ struct Renderer {
               if (!q) continue;
               // wave parity: even = path wave (primary for w == 0), odd = shadow wave
               const int mode = b > 0 ? FM_DIR : ((w & 1) ? FM_GENERAL : ((w == 0 && sd.frameValid(mo, FM_ORIGIN, 0)) ? FM_ORIGIN : FM_GENERAL));
-              const int64_t t = q * int64_t(sd.hostRecCount(mo, mode, b > 0 ? b - 1 : 0));
+              // executed prefilter tests: fully evaluated (ray run x 256-record chunk) pairs + one bound test
+              // per (ray, chunk); a run is the prefilterRunRays(mode) consecutive queue entries of one warp
+              const int64_t nch = SceneData<BE>::numChunks(int64_t(sd.hostRecCount(mo, mode, b > 0 ? b - 1 : 0)));
+              const int64_t run = prefilterRunRays(mode), nruns = (q + run - 1) / run;
+              const int64_t t = int64_t(c[cntWork(b)]) * run * kRecPad + nruns * run * nch;
               pacc.mesh_tests += t; pacc.tests_by_mode[mode] += t;
               queued += q;
             }

@@ -8,8 +8,11 @@
 // This is NOT a CPU fallback of the product: it is built only by tests/ into
 // tests/emu/libnrt_emu.so, exports `emu_*` symbols only, and nothing in
 // nim_raytracer_b200/ or include/nrt.h can load or reach it.
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "../../nim_raytracer_b200/csrc/nrt_renderer.h"
 
@@ -38,6 +41,14 @@ struct LoopBackend {
   template <class F> void forEachCounted(const uint32_t* c, int64_t cap, const F& f) {
     const int64_t n = std::min<int64_t>(*c, cap);
     for (int64_t i = 0; i < n; ++i) f(i);
+    ++launches;
+  }
+  void sortFaces(const DMesh& m) {
+    std::vector<uint32_t> keys(m.nfaces), idx(m.nfaces);
+    FaceKeys fk{m, keys.data(), idx.data()};
+    for (int64_t f = 0; f < m.nfaces; ++f) fk(f);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::memcpy(m.order, idx.data(), sizeof(uint32_t) * m.nfaces);
     ++launches;
   }
   template <class F> void compactRecs(int64_t n, const F& f, float* recs, float* hot, int mode, uint32_t* count) {
@@ -87,29 +98,54 @@ struct LoopBackend {
       }
     ++launches;
   }
-  // Prefilter: every queued ray of the bundle x every hot record (bounding circle / sphere).
-  void filter(int mode, const float* hot, const uint32_t* count, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
+  // Prefilter, two-level like the CUDA kernel: the queue is cut into runs of prefilterRunRays(mode)
+  // consecutive rays (one warp's registers); a run evaluates the 256 hot records of a chunk in full
+  // iff at least one of its rays passes the chunk's bound test.
+  void filter(int mode, const float* hot, const float* bounds, const uint32_t* count, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
     const uint32_t nq = cnt[cntQueue(b)];
     const int64_t base = queueBase(cs, mo, b);
     const float* h0 = cs.qhot0 + 4 * base;
     const float* h1 = cs.qhot1 + 4 * (int64_t(mo) * cs.NR);
-    const int64_t np = paddedFaces(*count);
+    const int64_t np = paddedFaces(*count), nch = np / kRecPad;
     const int nh = hotFloats(mode);
-    for (uint32_t rq = 0; rq < nq; ++rq) {
+    const bool cull = std::getenv("NRT_PREFILTER_CULL") ? std::atoi(std::getenv("NRT_PREFILTER_CULL")) != 0 : true;
+    const uint32_t run = uint32_t(prefilterRunRays(mode));
+    auto rayAt = [&](uint32_t rq) {
       HotRay r;
       r.a0 = h0[4 * rq]; r.a1 = h0[4 * rq + 1]; r.a2 = h0[4 * rq + 2]; r.a3 = h0[4 * rq + 3];
       r.b0 = r.b1 = r.b2 = r.b3 = 0.f;
       if (mode == FM_GENERAL) { r.b0 = h1[4 * rq]; r.b1 = h1[4 * rq + 1]; r.b2 = h1[4 * rq + 2]; }
-      for (int64_t t = 0; t < np; ++t) {
-        float h[4];
-        for (int k = 0; k < nh; ++k) h[k] = hot[recIndex(t, k, nh)];
-        ++filter_tests;
-        if (prefilterTest(mode, h, r)) {
-          const uint32_t slot = cnt[cntPre(b)]++;
-          if (slot < cs.preCap) { cs.preRay[slot] = rq; cs.preRec[slot] = uint32_t(t); }
+      return r;
+    };
+    for (uint32_t r0 = 0; r0 < nq; r0 += run) {
+      const uint32_t r1 = std::min(nq, r0 + run);
+      for (int64_t ch = 0; ch < nch; ++ch) {
+        bool any = !cull;
+        for (uint32_t rq = r0; rq < r1 && !any; ++rq) any = prefilterTest(mode, bounds + 4 * ch, rayAt(rq));
+        if (!any) continue;
+        ++cnt[cntWork(b)];
+        for (uint32_t rq = r0; rq < r1; ++rq) {
+          const HotRay r = rayAt(rq);
+          for (int64_t t = ch * kRecPad; t < (ch + 1) * kRecPad; ++t) {
+            float h[4];
+            for (int k = 0; k < nh; ++k) h[k] = hot[recIndex(t, k, nh)];
+            ++filter_tests;
+            if (prefilterTest(mode, h, r)) {
+              const uint32_t slot = cnt[cntPre(b)]++;
+              if (slot < cs.preCap) { cs.preRay[slot] = rq; cs.preRec[slot] = uint32_t(t); }
+            }
+          }
         }
       }
     }
+    ++launches;
+  }
+  // next bounce's active list: the samples with active == 1, in sample order
+  void compactActive(const ChunkState& cs, int64_t nS, uint32_t* list, uint32_t* count) {
+    uint32_t n = 0;
+    for (int64_t s = 0; s < nS; ++s)
+      if (cs.active[s]) list[n++] = uint32_t(s);
+    *count = n;
     ++launches;
   }
 };

@@ -31,13 +31,20 @@ def test_one_triangle_mesh(oracle_mod):
     assert prof["mesh_rays"] > 0
 
 
-def test_bunny_full_mesh(oracle_mod):
+def test_bunny_full_mesh(oracle_mod, monkeypatch):
+    monkeypatch.setenv("NRT_PREFILTER_CULL", "0")
     prof = check(scenes.bunny(), api.Options(160, 90), oracle_mod)
     # shared-origin (primary) and shared-direction (distant-light shadow) bundles drop the faces
     # that can never be hit (plane faces away / det < 1e-6): roughly half of the 69,451
     assert prof["exact_rays"] == 0 and 0.4 * 69451 < prof["mesh_tests"] / prof["mesh_rays"] < 0.6 * 69451
     # the filter is selective: ~1 float64 re-evaluation per ray that enters the box
     assert prof["candidates"] < 2 * prof["mesh_rays"]
+    # two-level traversal (Morton-ordered 256-record chunks + chunk bounds): same image, ids and
+    # stats, same candidates, fewer tests even at this tiny resolution (a 256-ray run spans 1.6 rows)
+    monkeypatch.setenv("NRT_PREFILTER_CULL", "1")
+    prof2 = check(scenes.bunny(), api.Options(160, 90), oracle_mod)
+    assert prof2["candidates"] == prof["candidates"] and prof2["pre_candidates"] == prof["pre_candidates"]
+    assert prof2["mesh_tests"] < 0.7 * prof["mesh_tests"]
 
 
 def test_bunny_native_winding(oracle_mod):
