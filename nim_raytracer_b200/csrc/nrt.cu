@@ -45,47 +45,43 @@ __global__ void __launch_bounds__(kBlock) k_for_each(F f, int64_t n) {
   if (i < n) f(i);
 }
 
-template <class F>
-__global__ void __launch_bounds__(kBlock) k_for_each_stats(F f, int64_t n, unsigned long long* stats) {
-  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
-  StatDelta d = zeroStats();
-  if (i < n) d = f(i);
+// Block-wide sum of the per-thread Stats deltas into the global counters: two redux.sync per
+// counter (26-bit halves, so the warp sums cannot overflow), shared-memory atomics across the
+// warps, one global atomic per counter and block.
+__device__ __forceinline__ void blockStatsAdd(const StatDelta& d, unsigned long long* stats) {
   __shared__ unsigned long long sh[ST_COUNT];
   if (threadIdx.x < ST_COUNT) sh[threadIdx.x] = 0;
   __syncthreads();
 #pragma unroll
   for (int k = 0; k <= ST_CONT; ++k) {
-    unsigned long long v = d.v[k];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[k], v);
+    const unsigned lo = __reduce_add_sync(0xffffffffu, unsigned(d.v[k] & 0x3FFFFFFull));
+    const unsigned hi = __reduce_add_sync(0xffffffffu, unsigned(d.v[k] >> 26));
+    if ((threadIdx.x & 31) == 0 && (lo | hi)) atomicAdd(&sh[k], (unsigned long long)lo + ((unsigned long long)hi << 26));
   }
   __syncthreads();
   if (threadIdx.x <= ST_CONT && sh[threadIdx.x]) atomicAdd(&stats[threadIdx.x], sh[threadIdx.x]);
+}
+
+template <class F>
+__global__ void __launch_bounds__(kBlock) k_for_each_stats(F f, int64_t n, unsigned long long* stats) {
+  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  StatDelta d = zeroStats();
+  if (i < n) d = f(i);
+  blockStatsAdd(d, stats);
 }
 
 // Same over [0, *count) with a device-resident count (persistent grid, no host sync).
 template <class F>
 __global__ void __launch_bounds__(kBlock) k_for_each_stats_counted(F f, const uint32_t* count, unsigned long long* stats) {
   const int64_t n = *count;
+  if (int64_t(blockIdx.x) * kBlock >= n) return;   // nothing for this block (block-uniform)
   StatDelta d = zeroStats();
   for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
     const StatDelta e = f(i);
 #pragma unroll
     for (int k = 0; k <= ST_CONT; ++k) d.v[k] += e.v[k];
   }
-  __shared__ unsigned long long sh[ST_COUNT];
-  if (threadIdx.x < ST_COUNT) sh[threadIdx.x] = 0;
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k <= ST_CONT; ++k) {
-    unsigned long long v = d.v[k];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[k], v);
-  }
-  __syncthreads();
-  if (threadIdx.x <= ST_CONT && sh[threadIdx.x]) atomicAdd(&stats[threadIdx.x], sh[threadIdx.x]);
+  blockStatsAdd(d, stats);
 }
 
 // Elements [0, min(*count, cap)) with a device-resident count (no host sync).
@@ -93,24 +89,29 @@ template <class F>
 __global__ void __launch_bounds__(kBlock) k_for_each_counted(F f, const uint32_t* count, int64_t cap) {
   int64_t n = *count;
   if (n > cap) n = cap;
+  if (int64_t(blockIdx.x) * kBlock >= n) return;
   for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) f(i);
 }
 
 // AABB gate of TriangleMesh.intersect (geom.nim:340) + ORDERED compaction of the rays that enter
 // each mesh's box into one queue per ray bundle (0 = arbitrary / shared-origin rays, 1 + l = shadow
 // rays of DistantLight l) and the float64 brute-force queue.  Three launches:
-//   k_gate_flags  evaluates the gate per (wave position, mesh object), stores a one-byte code and
-//                 counts the codes of every 256-ray block with warp ballots;
-//   k_gate_scan   exclusive scan of the block counts per (mesh object, queue) row -> queue offsets
-//                 and the queue totals;
-//   k_gate_write  re-evaluates the passing rays and stores them at offset + ballot rank.
+//   k_gate_flags  evaluates the gate per (wave position, mesh object) — a float32 certain-miss test
+//                 first, the reference's float64 slab test only for rays near the box — stores a
+//                 one-byte code, counts the codes of every 256-ray block with warp ballots, adds
+//                 the counts to their segment (256 blocks) and lists the non-empty blocks;
+//   k_gate_scan   exclusive scan of the (few) segment totals per (mesh object, queue) row ->
+//                 segment offsets and the queue totals;
+//   k_gate_write  only over the non-empty blocks: offset = segment offset + counts of the preceding
+//                 blocks of the segment + ballot rank; re-evaluates the passing rays and stores them.
 // Queue order therefore equals wave order (scanline order of the samples): the 256 consecutive
 // queue entries a prefilter warp works on belong to neighbouring pixels, which is what makes the
 // chunk bounds of the two-level traversal selective.
+static constexpr int kSegBlocks = 256;   // 256-ray blocks per segment
 __device__ __forceinline__ uint8_t gateCode(const GateOut& o) { return o.pass ? (o.safe ? uint8_t(1 + o.bundle) : uint8_t(255)) : uint8_t(0); }
 __device__ __forceinline__ uint8_t gateWant(int r, int nB) { return r < nB ? uint8_t(1 + r) : uint8_t(255); }
 
-__global__ void __launch_bounds__(kBlock) k_gate_flags(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO) {
+__global__ void __launch_bounds__(kBlock) k_gate_flags(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO, uint32_t* neCount) {
   extern __shared__ uint32_t sh_cnt[];   // nMO * nRow
   const unsigned lane = threadIdx.x & 31u;
   const ChunkState& cs = g.cs;
@@ -135,65 +136,85 @@ __global__ void __launch_bounds__(kBlock) k_gate_flags(Gate g, const uint32_t* c
       }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < rows; k += kBlock) cs.gcnt[int64_t(k) * (cs.gvb + 1) + vb] = sh_cnt[k];
-    __syncthreads();
+    bool any = false;
+    for (int k = threadIdx.x; k < rows; k += kBlock) {
+      const uint32_t c = sh_cnt[k];
+      cs.gcnt[int64_t(k) * cs.gvb + vb] = c;
+      if (c) { atomicAdd(&cs.gseg[int64_t(k) * cs.gsn + vb / kSegBlocks], c); any = true; }
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) cs.gne[atomicAdd(neCount, 1u)] = uint32_t(vb);
   }
 }
 
-// one CTA per (mesh object, queue) row: in-place exclusive scan of the block counts; total -> counter block
+// one CTA per (mesh object, queue) row: exclusive scan of the segment totals (and their reset for the
+// next gate); queue total -> counter block
 __global__ void __launch_bounds__(1024) k_gate_scan(ChunkState cs, const uint32_t* count, int64_t nHost, int mult, uint32_t* cnt) {
   __shared__ uint32_t sh[1024];
   const int nB = 1 + cs.nL, nRow = nB + 1, cst = cntStride(cs.nL);
   const int row = blockIdx.x, mo = row / nRow, r = row - mo * nRow;
-  uint32_t* p = cs.gcnt + int64_t(row) * (cs.gvb + 1);
+  uint32_t* seg = cs.gseg + int64_t(row) * cs.gsn;
+  uint32_t* base = cs.gsegBase + int64_t(row) * cs.gsn;
   const int64_t n = count ? int64_t(*count) * mult : nHost;
-  const int64_t nVB = (n + kBlock - 1) / kBlock;
-  const int64_t per = (nVB + 1023) / 1024;
-  const int64_t b0 = min(nVB, int64_t(threadIdx.x) * per), b1 = min(nVB, b0 + per);
-  uint32_t sum = 0;
-  for (int64_t k = b0; k < b1; ++k) sum += p[k];
-  sh[threadIdx.x] = sum;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {   // inclusive Hillis-Steele scan over the 1024 partial sums
-    const uint32_t v = (int(threadIdx.x) >= off) ? sh[threadIdx.x - off] : 0u;
+  const int64_t nSeg = ((n + kBlock - 1) / kBlock + kSegBlocks - 1) / kSegBlocks;
+  uint32_t carry = 0;
+  for (int64_t s0 = 0; s0 < nSeg; s0 += 1024) {   // one pass unless a wave has more than 67 M rays
+    const int64_t k = s0 + threadIdx.x;
+    const uint32_t v = (k < nSeg) ? seg[k] : 0u;
+    sh[threadIdx.x] = v;
     __syncthreads();
-    sh[threadIdx.x] += v;
+    for (int off = 1; off < 1024; off <<= 1) {
+      const uint32_t a = (int(threadIdx.x) >= off) ? sh[threadIdx.x - off] : 0u;
+      __syncthreads();
+      sh[threadIdx.x] += a;
+      __syncthreads();
+    }
+    if (k < nSeg) { base[k] = carry + sh[threadIdx.x] - v; seg[k] = 0; }
+    carry += sh[1023];
     __syncthreads();
   }
-  uint32_t run = sh[threadIdx.x] - sum;
-  for (int64_t k = b0; k < b1; ++k) { const uint32_t v = p[k]; p[k] = run; run += v; }
-  if (threadIdx.x == 1023) {
-    const uint32_t total = sh[1023];
-    p[nVB] = total;
-    cnt[mo * cst + (r < nB ? cntQueue(r) : CNT_EXACT)] = total;
-  }
+  if (threadIdx.x == 0) cnt[mo * cst + (r < nB ? cntQueue(r) : CNT_EXACT)] = carry;
 }
 
-__global__ void __launch_bounds__(kBlock) k_gate_write(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO) {
+__global__ void __launch_bounds__(kBlock) k_gate_write(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO, const uint32_t* neCount) {
   __shared__ uint32_t wc[kBlock / 32];
+  __shared__ uint32_t sh_pre;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const ChunkState& cs = g.cs;
   const int nB = 1 + cs.nL, nRow = nB + 1;
   const int64_t n = count ? int64_t(*count) * mult : nHost;
-  const int64_t nVB = (n + kBlock - 1) / kBlock;
-  for (int64_t vb = blockIdx.x; vb < nVB; vb += gridDim.x) {
+  const uint32_t nNE = *neCount;
+  for (uint32_t e = blockIdx.x; e < nNE; e += gridDim.x) {
+    const int64_t vb = cs.gne[e];
     const int64_t i = vb * kBlock + threadIdx.x;
+    const int64_t sg = vb / kSegBlocks, inSeg = vb - sg * kSegBlocks;
     for (int mo = 0; mo < nMO; ++mo) {
       const uint8_t code = (i < n) ? cs.gflag[int64_t(mo) * cs.NR + i] : uint8_t(0);
+      if (code != 0) {   // passing rays start from "box hit, no face yet" (geom.nim:343: tMin = Inf)
+        const uint32_t wi = g.waveIndex(i);
+        cs.tBest[int64_t(mo) * cs.NR + wi] = dbits(NRT_INF);
+        cs.triBest[int64_t(mo) * cs.NR + wi] = kNoTri;
+      }
       for (int r = 0; r < nRow; ++r) {
-        const uint32_t* p = cs.gcnt + int64_t(mo * nRow + r) * (cs.gvb + 1) + vb;
-        const uint32_t base = p[0];
-        if (p[1] == base) continue;          // nothing of this block goes to this queue (block-uniform)
+        const int64_t row = int64_t(mo) * nRow + r;
+        const uint32_t* pc = cs.gcnt + row * cs.gvb;
+        if (pc[vb] == 0) continue;           // nothing of this block goes to this queue (block-uniform)
+        // queue offset of the block: segment offset + the counts of the segment's preceding blocks
+        if (threadIdx.x == 0) sh_pre = 0;
+        __syncthreads();
+        uint32_t v = (int64_t(threadIdx.x) < inSeg) ? pc[sg * kSegBlocks + threadIdx.x] : 0u;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0 && v) atomicAdd(&sh_pre, v);
         const bool mine = code == gateWant(r, nB);
         const unsigned m = __ballot_sync(0xffffffffu, mine);
         if (lane == 0) wc[warp] = uint32_t(__popc(m));
         __syncthreads();
-        uint32_t pre = 0;
+        uint32_t pre = cs.gsegBase[row * cs.gsn + sg] + sh_pre;
         for (unsigned w = 0; w < warp; ++w) pre += wc[w];
         __syncthreads();
         if (!mine) continue;
-        const int64_t q = int64_t(base) + pre + __popc(m & lt);
+        const int64_t q = int64_t(pre) + __popc(m & lt);
         const GateOut o = g(i, mo);
         if (r < nB) {
           const int64_t at = queueBase(cs, mo, r) + q;
@@ -273,6 +294,7 @@ __global__ void __launch_bounds__(kBlock) k_pad_recs(float* recs, float* hot, co
 static constexpr int FT_THREADS = 256;
 static constexpr int FT_WARPS = FT_THREADS / 32;
 static constexpr int FT_TC = 256;     // records per chunk
+static constexpr int FT_WB = 256;     // per-warp survivor buffer entries (flushed after every chunk)
 static_assert(kRecPad == FT_TC, "one bound per shared-memory chunk");
 
 struct PreArgs {
@@ -320,6 +342,19 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
   if (nrecPadded == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* const tile = smem_tiles + size_t(warp) * 2 * CH4;
+  // per-warp survivor buffer behind the tiles: FT_WB (ray, record) pairs + a counter
+  uint2* const wbuf = reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * 2 * CH4) + size_t(warp) * FT_WB;
+  uint32_t* const wcnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * 2 * CH4) + size_t(FT_WARPS) * FT_WB) + warp;
+  if (lane == 0) *wcnt = 0;
+  __syncwarp();
+  auto emit = [&](uint32_t ray, uint32_t rec) {
+    const uint32_t slot = atomicAdd(wcnt, 1u);
+    if (slot < uint32_t(FT_WB)) wbuf[slot] = make_uint2(ray, rec);
+    else {  // buffer full (dense hits, e.g. always-candidate records): straight to the global list
+      const uint32_t gs = atomicAdd(a.prectr, 1u);
+      if (gs < a.preCap) { a.preRay[gs] = ray; a.preRec[gs] = rec; }
+    }
+  };
   const uint32_t nRuns = (nq + RUN - 1) / RUN;
   const uint32_t nChunks = nrecPadded / FT_TC;
   // chunk groups of <= 32 chunks (one pass mask); smaller groups when there are too few runs to fill the GPU
@@ -407,7 +442,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
           q[2 * c] = make_float2(v4.x, v4.y);
           q[2 * c + 1] = make_float2(v4.z, v4.w);
         }
-        bool any = false;
+        uint32_t hm = 0;   // bit r: ray r passed one of the four tests
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const float thr = (MODE == FM_GENERAL) ? ra3[r] : ra2[r];
@@ -415,26 +450,36 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
           const float2 g1 = prefilterPair<MODE>(q + NH, ra0[r], ra1[r], ra2[r], rb0[r], rb1[r], rb2[r]);
           // one compare per ray: max of its four left-hand sides against its threshold (FMNMX3 + FSETP)
           const float m = fmaxf(fmaxf(g0.x, g0.y), fmaxf(g1.x, g1.y));
-          any = any || (m >= thr);
+          if (m >= thr) hm |= 1u << r;
         }
-        if (any) {  // some test passed (rare): re-evaluate and emit
+        if (hm) {  // re-evaluate the rays that passed and emit their survivors
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            if (ridx[r] == kInvalidRef) continue;
+            if (!(hm & (1u << r)) || ridx[r] == kInvalidRef) continue;
             const float thr = (MODE == FM_GENERAL) ? ra3[r] : ra2[r];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const float2 g = prefilterPair<MODE>(q + j * NH, ra0[r], ra1[r], ra2[r], rb0[r], rb1[r], rb2[r]);
-              if (g.x >= thr) {
-                const uint32_t slot = atomicAdd(a.prectr, 1u);
-                if (slot < a.preCap) { a.preRay[slot] = ridx[r]; a.preRec[slot] = base + 4 * t + 2 * j; }
-              }
-              if (g.y >= thr) {
-                const uint32_t slot = atomicAdd(a.prectr, 1u);
-                if (slot < a.preCap) { a.preRay[slot] = ridx[r]; a.preRec[slot] = base + 4 * t + 2 * j + 1; }
-              }
+              if (g.x >= thr) emit(ridx[r], base + 4 * t + 2 * j);
+              if (g.y >= thr) emit(ridx[r], base + 4 * t + 2 * j + 1);
             }
           }
+        }
+      }
+      // flush the warp's survivors: one global atomic per (warp, chunk), coalesced stores
+      __syncwarp();
+      {
+        const uint32_t nb = min(*wcnt, uint32_t(FT_WB));
+        if (nb) {
+          uint32_t gb = 0;
+          if (lane == 0) gb = atomicAdd(a.prectr, nb);
+          gb = __shfl_sync(0xffffffffu, gb, 0);
+          for (uint32_t k = lane; k < nb; k += 32) {
+            const uint2 e = wbuf[k];
+            if (gb + k < a.preCap) { a.preRay[gb + k] = e.x; a.preRec[gb + k] = e.y; }
+          }
+          __syncwarp();
+          if (lane == 0) *wcnt = 0;
         }
       }
       __syncwarp();                            // every lane left the slice before it is staged again
@@ -555,9 +600,10 @@ struct CudaBackend {
     const ChunkState& cs = g.cs;
     const int rows = nMO * (2 + cs.nL);
     const unsigned grid = count ? unsigned(sms * 8) : blocksFor(n);
-    k_gate_flags<<<grid, kBlock, sizeof(uint32_t) * rows, stream>>>(g, count, n, mult, nMO);
+    uint32_t* ne = cnt + CNT_NE;   // zeroed with the counter blocks at the start of the chunk
+    k_gate_flags<<<grid, kBlock, sizeof(uint32_t) * rows, stream>>>(g, count, n, mult, nMO, ne);
     k_gate_scan<<<unsigned(rows), 1024, 0, stream>>>(cs, count, n, mult, cnt);
-    k_gate_write<<<grid, kBlock, 0, stream>>>(g, count, n, mult, nMO);
+    k_gate_write<<<unsigned(sms * 8), kBlock, 0, stream>>>(g, count, n, mult, nMO, ne);
     NRT_CUDA(cudaGetLastError()); launches += 3;
   }
   // Morton order of the face centroids -> m.order (stable: ties keep face order)
@@ -628,8 +674,9 @@ struct CudaBackend {
     filterModes[filterUsed++] = mode;
     NRT_CUDA(cudaEventRecord(ev.first, stream));
     // per-warp double-buffered chunk slices: 2-D bundles 8 rays/lane (48 KiB/CTA, 3 CTAs/SM); GENERAL 4 rays/lane (64 KiB/CTA, 2 CTAs/SM)
-    constexpr size_t sm2d = size_t(FT_WARPS) * 2 * (FT_TC / 4) * 3 * sizeof(float4);
-    constexpr size_t smGen = size_t(FT_WARPS) * 2 * (FT_TC / 4) * 4 * sizeof(float4);
+    constexpr size_t smBuf = size_t(FT_WARPS) * FT_WB * sizeof(uint2) + FT_WARPS * sizeof(uint32_t);
+    constexpr size_t sm2d = size_t(FT_WARPS) * 2 * (FT_TC / 4) * 3 * sizeof(float4) + smBuf;
+    constexpr size_t smGen = size_t(FT_WARPS) * 2 * (FT_TC / 4) * 4 * sizeof(float4) + smBuf;
     if (!smemOptIn) {
       NRT_CUDA(cudaFuncSetAttribute(k_mesh_prefilter<FM_GENERAL, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smGen)));
       NRT_CUDA(cudaFuncSetAttribute(k_mesh_prefilter<FM_ORIGIN, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2d)));

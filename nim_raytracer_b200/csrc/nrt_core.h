@@ -75,6 +75,7 @@ struct DObject {
   double bmax[4];
   double albedo[3];
   double reflection;
+  double albedo_pi[3]; // albedo / PI (shader.nim:15), the same IEEE division done once at scene build
 };
 
 // Compact per-object record read by the in-order object scan of trace(): 48 bytes, three
@@ -117,6 +118,8 @@ struct DMesh {
   double bmin[4], bmax[4];  // calcAABB (geom.nim:175-188)
   double center[3];         // filter frame origin (AABB centre)
   double L;                 // filter length scale (max AABB half extent)
+  float rb2f;               // squared half diagonal of the AABB, rounded up (boxCertainMiss); Inf disables the pre-test
+  float _padf;
   float* recs;              // GENERAL-mode full filter records (nrt_filter.h), pair-interleaved
   float* hot;               // GENERAL-mode hot (bounding sphere) records, pair-interleaved
   float* bounds;            // GENERAL-mode chunk bounds (one hot-format record per 256 records)
@@ -210,17 +213,30 @@ NRT_HD double planeIntersect(V4 orig, V4 dir) {
 }
 
 // worldToObject * (orig, dir) of trace() (renderer.nim:54-55).  For a matrix that is exactly
-// [I | t] the glm product ((1*x + 0*y) + 0*z) + t*w equals x + t (points) or x (vectors) bit for
-// bit whenever x, y, z are finite and non-zero (the zero products vanish and one rounding
-// remains), so the 56-flop product is skipped; any other input takes the literal product.
-NRT_HD bool nzFinite3(V4 v) {
+// [I | t] (entries == 1.0 / == 0.0, t finite) and finite x, y, z the glm product
+//   ((1*x + 0*y) + 0*z) + t*w
+// has zero products that vanish, so per component
+//   points  (w == 1): x + t  (one rounding)  unless x == 0 and t == 0 (a zero whose sign depends on
+//                     the products: evaluated literally),
+//   vectors (w == 0): x                       unless x == 0 (same).
+// Bit for bit the literal product at a fraction of its 56 flops and 16 loads; any other input
+// (w not exactly 1 / 0, non-finite components) takes the literal product.
+NRT_HD bool finite3(V4 v) {
   const double big = 1.7976931348623157e308;
-  return (fabs(v.x) > 0) && (fabs(v.x) <= big) && (fabs(v.y) > 0) && (fabs(v.y) <= big) && (fabs(v.z) > 0) && (fabs(v.z) <= big);
+  return (fabs(v.x) <= big) && (fabs(v.y) <= big) && (fabs(v.z) <= big);   // false for NaN
 }
+NRT_HD double mulmRow(const double* m, int r, V4 v) { return ((m[r] * v.x + m[4 + r] * v.y) + m[8 + r] * v.z) + m[12 + r] * v.w; }
 NRT_HD void toObject(const DObject& ob, V4 o, V4 d, V4& oo, V4& dd) {
-  if (ob.xlate_only && o.w == 1.0 && d.w == 0.0 && nzFinite3(o) && nzFinite3(d)) {
-    oo = v4(o.x + ob.w2o[12], o.y + ob.w2o[13], o.z + ob.w2o[14], 1.0);
-    dd = v4(d.x, d.y, d.z, 0.0);
+  if (ob.xlate_only && o.w == 1.0 && d.w == 0.0 && finite3(o) && finite3(d)) {
+    const double* m = ob.w2o;
+    oo.x = (o.x != 0.0 || m[12] != 0.0) ? o.x + m[12] : mulmRow(m, 0, o);
+    oo.y = (o.y != 0.0 || m[13] != 0.0) ? o.y + m[13] : mulmRow(m, 1, o);
+    oo.z = (o.z != 0.0 || m[14] != 0.0) ? o.z + m[14] : mulmRow(m, 2, o);
+    oo.w = 1.0;
+    dd.x = (d.x != 0.0) ? d.x : mulmRow(m, 0, d);
+    dd.y = (d.y != 0.0) ? d.y : mulmRow(m, 1, d);
+    dd.z = (d.z != 0.0) ? d.z : mulmRow(m, 2, d);
+    dd.w = 0.0;
   } else {
     oo = mulm(ob.w2o, o);
     dd = mulm(ob.w2o, d);
@@ -287,9 +303,9 @@ NRT_HD ShadingInfo getShadingInfo(const DLight& l, V4 p) {
 
 // shader.nim:12-17
 NRT_HD V3 shadeDiffuse(const DObject& o, const ShadingInfo& si, V4 hitNormal) {
-  const V3 albedo = v3(o.albedo[0], o.albedo[1], o.albedo[2]);
+  const V3 albedoPi = v3(o.albedo_pi[0], o.albedo_pi[1], o.albedo_pi[2]);   // divs(albedo, kPi)
   const double c = nim_max(0.0, dot(hitNormal, scale(si.lightDir, -1.0)));
-  return scale(mul(divs(albedo, kPi), si.lightIntensity), c);
+  return scale(mul(albedoPi, si.lightIntensity), c);
 }
 
 // renderer.nim:31-44 (orig/dir only; initRay is applied per object in trace)

@@ -26,10 +26,11 @@ namespace nrt {
 
 enum WaveKind { WAVE_PATH = 0, WAVE_SHADOW = 1 };
 
-// Counter block per (wave, mesh object): [EXACT, CAND, then (QUEUE_b, TILE_b, PRE_b, WORK_b) per ray bundle b].
+// Counter block per (wave, mesh object): [EXACT, CAND, NE, then (QUEUE_b, TILE_b, PRE_b, WORK_b) per ray bundle b].
 // Bundle 0 holds arbitrary rays (GENERAL mode; ORIGIN mode for the primary wave, whose rays share
 // the camera origin); bundle 1 + l holds the shadow rays of DistantLight l (DIR mode).
-enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_BUNDLE0 = 2 };
+// NE (mesh object 0's block only): 256-ray blocks of the wave with at least one ray entering a mesh box.
+enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_NE = 2, CNT_BUNDLE0 = 3 };
 NRT_HD int cntStride(int nL) { return CNT_BUNDLE0 + 4 * (1 + nL); }
 NRT_HD int cntQueue(int b) { return CNT_BUNDLE0 + 4 * b; }      // rays queued for the bundle
 NRT_HD int cntTile(int b) { return CNT_BUNDLE0 + 4 * b + 1; }   // prefilter work-item counter
@@ -84,9 +85,13 @@ struct ChunkState {
   // ordered queue compaction (CUDA backend): gate pass 1 writes a code per (mesh object, wave
   // position) and per-block counts; a scan turns the counts into queue offsets; pass 2 writes the
   // rays, so queue order == wave order (scanline order): consecutive queue entries are neighbours.
-  uint8_t* gflag;    // nMO*NR     0 none, 1 + b filter bundle b, 255 exact
-  uint32_t* gcnt;    // nMO*(2+nL) rows x (gvb + 1): per 256-ray block counts, then their exclusive scan
+  uint8_t* gflag;    // nMO*NR     by wave position: 0 none, 1 + b filter bundle b, 255 exact
+  uint32_t* gcnt;    // nMO*(2+nL) rows x gvb: rays of each 256-ray block that go to the row's queue
+  uint32_t* gseg;    // rows x gsn: the same summed per segment of 256 blocks (zero between gates)
+  uint32_t* gsegBase;// rows x gsn: exclusive scan of gseg = queue offset of the segment
+  uint32_t* gne;     // gvb: blocks with at least one entering ray (unordered)
   int64_t gvb;       // blocks per row (capacity)
+  int64_t gsn;       // segments per row (capacity)
   // candidates of the current (wave, mesh object)
   uint32_t* candRef; // candCap
   uint32_t* candTri; // candCap
@@ -251,6 +256,25 @@ NRT_HD bool waveRay(const DScene& sc, const FrameParams& fp, const ChunkState& c
   return true;
 }
 
+// Conservative float32 pre-test of the AABB gate (geom.nim:340): true only if the ray (t >= 0)
+// certainly stays outside the bounding sphere of the mesh box — its line misses the sphere, or its
+// origin is outside and it moves away from the centre.  The reference's slab test (geom.nim:76-96)
+// then returns NegInf or a negative tmin, both "no hit", so the float64 evaluation (three
+// divisions in initRay) is skipped.  Slack: 1e-5 |w|^2 |d|^2 >> the float32 cancellation error
+// 12u |w|^2 |d|^2 of |w x d|^2; the sphere is inflated by 0.1 %.  NaN / overflow compare false.
+NRT_HD bool boxCertainMiss(const DMesh& m, V4 oo, V4 dd) {
+  const float wx = float(oo.x - m.center[0]), wy = float(oo.y - m.center[1]), wz = float(oo.z - m.center[2]);
+  const float dx = float(dd.x), dy = float(dd.y), dz = float(dd.z);
+  const float w2 = fmaf(wx, wx, fmaf(wy, wy, wz * wz)), d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+  if (!(w2 < 1e30f) || !(d2 < 1e30f) || !(d2 > 1e-30f) || !(m.rb2f < 1e30f)) return false;
+  const float cx = wy * dz - wz * dy, cy = wz * dx - wx * dz, cz = wx * dy - wy * dx;
+  const float c2 = fmaf(cx, cx, fmaf(cy, cy, cz * cz));
+  const float slack = 1e-5f * (w2 * d2);
+  if (c2 > fmaf(m.rb2f, d2, slack)) return true;
+  const float wd = fmaf(wx, dx, fmaf(wy, dy, wz * dz));
+  return (w2 > m.rb2f * 1.001f) && (wd > 0.f) && (wd * wd > slack);
+}
+
 NRT_HD Ray objectRay(const DObject& ob, V4 o, V4 d) {  // renderer.nim:54-55
   V4 oo, dd;
   toObject(ob, o, d, oo, dd);
@@ -262,6 +286,14 @@ struct GateOut { bool pass, safe; int bundle; uint32_t wi; FilterRay fr; HotRay 
 struct Gate {
   const DScene* sc; FrameParams fp; ChunkState cs; int kind; ActiveSet act; int force_exact;
   int path_mode;   // FM_ORIGIN for the primary wave (all rays share the camera origin), else FM_GENERAL
+  // wave-ray index (the slot of the ray's mesh results) of wave position idx < wave size
+  NRT_HD uint32_t waveIndex(int64_t idx) const {
+    if (kind == WAVE_SHADOW) {
+      const int64_t si = idx / cs.nL;
+      return uint32_t(sampleOf(act, si) * cs.nL + (idx - si * cs.nL));
+    }
+    return uint32_t(sampleOf(act, idx));
+  }
   // i-th ray of the wave: PATH = i-th active sample; SHADOW = (active sample i / nL, light i % nL)
   NRT_HD GateOut operator()(int64_t idx, int mo) const {
     GateOut g; g.pass = false; g.safe = false; g.bundle = 0; g.wi = kInvalidRef;
@@ -283,11 +315,12 @@ struct Gate {
     g.wi = uint32_t(i);
     const DObject& ob = sc->objects[sc->mesh_obj_index[mo]];
     const DMesh& m = sc->meshes[ob.mesh];
-    const Ray r = objectRay(ob, o, d);
+    V4 oo, dd;
+    toObject(ob, o, d, oo, dd);                      // renderer.nim:54-55
+    if (boxCertainMiss(m, oo, dd)) return g;         // float32: the ray stays clear of the box's bounding sphere
+    const Ray r = initRay(oo, dd);
     const double tmin = aabbIntersect(m.bmin, m.bmax, r);
     g.pass = !(tmin < 0);
-    cs.tBest[int64_t(mo) * cs.NR + i] = dbits(g.pass ? NRT_INF : NRT_NEG_INF);
-    cs.triBest[int64_t(mo) * cs.NR + i] = kNoTri;
     if (g.pass && !force_exact) {
       int mode = path_mode, l = 0;
       if (kind == WAVE_SHADOW) {
@@ -381,19 +414,25 @@ struct Verify2 {  // among candidates attaining the minimum, the lowest face ind
 
 // trace(): renderer.nim:47-67 with the mesh results looked up.  `wi` = wave-ray index.
 struct TraceOut { int obj; double t; uint32_t tri; int tests, hits; };
-NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d, double tNear, int64_t wi) {
+// `pos` = wave position of the ray (index of its gate code): a ray that did not enter a mesh's box
+// (code 0) has t = NegInf for that mesh without touching the per-ray mesh results.
+NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d, double tNear, int64_t wi, int64_t pos) {
   TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
-  // the exact shortcut of toObject() for [I | t] matrices applies to this ray?
-  const bool fastRay = (o.w == 1.0) && (d.w == 0.0) && nzFinite3(o) && nzFinite3(d);
+  // the exact shortcut of toObject() for [I | t] matrices applies to this ray?  (zero components
+  // need toObject()'s per-component treatment)
+  const bool fastRay = (o.w == 1.0) && (d.w == 0.0) && finite3(o) && finite3(d) && d.x != 0.0 && d.y != 0.0 && d.z != 0.0;
   for (int i = 0; i < sc.nobjects; ++i) {
     const CObj c = loadCObj(sc.cobjs + i);
     double t; uint32_t tri = kNoTri;
     if (c.kind == GEOM_MESH) {
-      t = bitsd(cs.tBest[int64_t(c.mesh_obj) * cs.NR + wi]);
-      tri = cs.triBest[int64_t(c.mesh_obj) * cs.NR + wi];
+      t = NRT_NEG_INF;
+      if (cs.gflag[int64_t(c.mesh_obj) * cs.NR + pos]) {
+        t = bitsd(cs.tBest[int64_t(c.mesh_obj) * cs.NR + wi]);
+        tri = cs.triBest[int64_t(c.mesh_obj) * cs.NR + wi];
+      }
     } else {
       V4 oo, dd;
-      if (c.xlate_only && fastRay) {
+      if (c.xlate_only && fastRay && (o.x != 0.0 || c.t[0] != 0.0) && (o.y != 0.0 || c.t[1] != 0.0) && (o.z != 0.0 || c.t[2] != 0.0)) {
         oo = v4(o.x + c.t[0], o.y + c.t[1], o.z + c.t[2], 1.0);
         dd = v4(d.x, d.y, d.z, 0.0);
       } else {
@@ -430,7 +469,7 @@ struct Shade {
     const int64_t s = sampleOf(act, idx);
     if (!cs.active[s]) return st;
     const V4 o = ld4(cs.rayO, cs.S, s), d = ld4(cs.rayD, cs.S, s);
-    const TraceOut tr = traceObjects(*sc, cs, o, d, NRT_INF, s);
+    const TraceOut tr = traceObjects(*sc, cs, o, d, NRT_INF, s, idx);
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     const int bounce = cs.bounce[s];
     if (bounce == 0) {
@@ -488,7 +527,7 @@ struct Resolve {
     for (int l = 0; l < cs.nL; ++l) {
       const ShadingInfo si = getShadingInfo(sc->lights[l], hitW);
       const V4 so = add(hitW, scale(n, fp.bias)), sd = scale(si.lightDir, -1.0);
-      const TraceOut tr = traceObjects(*sc, cs, so, sd, si.lightDistance, s * cs.nL + l);
+      const TraceOut tr = traceObjects(*sc, cs, so, sd, si.lightDistance, s * cs.nL + l, idx * cs.nL + l);
       st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
       if (tr.obj < 0) local = add(local, shadeDiffuse(ob, si, n));
     }

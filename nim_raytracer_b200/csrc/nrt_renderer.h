@@ -148,6 +148,13 @@ struct SceneData {
       }
       if (!(L > 0) || !std::isfinite(L)) { L = 0; for (int k = 0; k < 3; ++k) dm.center[k] = 0; }  // => every ray takes the exact path
       dm.L = L;
+      {
+        double rb2 = 0;
+        for (int k = 0; k < 3; ++k) { const double hk = 0.5 * (dm.bmax[k] - dm.bmin[k]); rb2 += hk * hk; }
+        rb2 *= 1.0 + 1e-6;   // covers the rounding of center[] and of the sum
+        dm.rb2f = (std::isfinite(rb2) && rb2 < 1e30 && L > 0) ? roundUpF(rb2) : float(NRT_INF);
+        dm._padf = 0.f;
+      }
     }
     anyReflective = false; anyPointLight = false;
     for (int i = 0; i < desc->nobjects; ++i) {
@@ -172,6 +179,7 @@ struct SceneData {
       std::memcpy(dob.bmin, o.vmin, sizeof(dob.bmin));
       std::memcpy(dob.bmax, o.vmax, sizeof(dob.bmax));
       std::memcpy(dob.albedo, o.albedo, sizeof(dob.albedo));
+      for (int k = 0; k < 3; ++k) dob.albedo_pi[k] = o.albedo[k] / kPi;
       dob.reflection = o.reflection;
       if (o.reflection > 0.0) anyReflective = true;
       if (o.kind == NRT_GEOM_MESH) {
@@ -339,8 +347,14 @@ struct Renderer {
       cs.alist = al<uint32_t>(2 * S); cs.acount = al<uint32_t>(waves + 2);
       cs.stats = al<unsigned long long>(ST_COUNT);
       cs.gvb = (NR + 255) / 256 + 1;
+      cs.gsn = (cs.gvb + 255) / 256;
       cs.gflag = al<uint8_t>(m);
-      cs.gcnt = al<uint32_t>(int64_t(std::max(nMO, 1)) * (2 + nL) * (cs.gvb + 1));
+      const int64_t grows = int64_t(std::max(nMO, 1)) * (2 + nL);
+      cs.gcnt = al<uint32_t>(grows * cs.gvb);
+      cs.gseg = al<uint32_t>(grows * cs.gsn);
+      cs.gsegBase = al<uint32_t>(grows * cs.gsn);
+      cs.gne = al<uint32_t>(cs.gvb);
+      be->zero(cs.gseg, sizeof(uint32_t) * grows * cs.gsn);
       dRows = al<int32_t>(nrows);
     }
     cs.S = capS; cs.NR = capNR; cs.QCAP = capNR + int64_t(nL) * capS; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.preCap = 4 * capCand; cs.rows = dRows;

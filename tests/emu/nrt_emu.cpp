@@ -77,6 +77,11 @@ struct LoopBackend {
       for (int mo = 0; mo < nMO; ++mo) {
         const GateOut o = g(i, mo);
         uint32_t* c = cnt + mo * cst;
+        cs.gflag[int64_t(mo) * cs.NR + i] = o.pass ? (o.safe ? uint8_t(1 + o.bundle) : uint8_t(255)) : uint8_t(0);
+        if (o.pass) {
+          cs.tBest[int64_t(mo) * cs.NR + o.wi] = dbits(NRT_INF);
+          cs.triBest[int64_t(mo) * cs.NR + o.wi] = kNoTri;
+        }
         if (o.pass && o.safe) {
           const int64_t q = c[cntQueue(o.bundle)]++;
           const int64_t at = queueBase(cs, mo, o.bundle) + q;
