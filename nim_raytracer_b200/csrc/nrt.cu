@@ -12,6 +12,7 @@
 #include <cuda_pipeline.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/permutation_iterator.h>
 
 #include <atomic>
 #include <cstdio>
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
   // chunk groups of <= 32 chunks (one pass mask); smaller groups when there are too few runs to fill the GPU
   uint32_t G = 32;
   const uint32_t totalWarps = gridDim.x * FT_WARPS;
-  while (G > 4 && uint64_t(nRuns) * ((nChunks + G - 1) / G) < 4ull * totalWarps) G >>= 1;
+  while (G > 1 && uint64_t(nRuns) * ((nChunks + G - 1) / G) < 4ull * totalWarps) G >>= 1;
   const uint32_t nGroups = (nChunks + G - 1) / G;
   const uint32_t nItems = nRuns * nGroups;
   uint32_t work = 0;
@@ -558,6 +559,13 @@ struct CudaBackend {
     NRT_CUDA(cudaStreamSynchronize(stream));
   }
   void sync() { use(); NRT_CUDA(cudaStreamSynchronize(stream)); }
+  // free device memory + what the caller already holds (its buffers are reused or replaced)
+  int64_t memAvailable(int64_t held) {
+    use();
+    size_t fr = 0, tot = 0;
+    NRT_CUDA(cudaMemGetInfo(&fr, &tot));
+    return int64_t(fr) + held;
+  }
   static unsigned blocksFor(int64_t n) { return unsigned((n + kBlock - 1) / kBlock); }
 
   template <class F> void forEach(int64_t n, const F& f) {
@@ -637,14 +645,21 @@ struct CudaBackend {
     }
     NRT_CUDA(cudaGetLastError()); launches += 4;
   }
-  // next bounce's active list: samples with active == 1, in sample order (count on the device)
-  void compactActive(const ChunkState& cs, int64_t nS, uint32_t* list, uint32_t* count) {
+  // next bounce's active list: the samples of the current set with active == 1, in sample order
+  void compactActive(const ChunkState& cs, const ActiveSet& act, uint32_t* list, uint32_t* count) {
     use();
-    thrust::counting_iterator<uint32_t> ids(0u);
     size_t tb = 0;
-    NRT_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids, cs.active, list, count, int(nS), stream));
-    void* tmp = scratch(0, tb);
-    NRT_CUDA(cub::DeviceSelect::Flagged(tmp, tb, ids, cs.active, list, count, int(nS), stream));
+    if (!act.list) {
+      thrust::counting_iterator<uint32_t> ids(0u);
+      NRT_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids, cs.active, list, count, int(act.n), stream));
+      void* tmp = scratch(0, tb);
+      NRT_CUDA(cub::DeviceSelect::Flagged(tmp, tb, ids, cs.active, list, count, int(act.n), stream));
+    } else {
+      auto flags = thrust::make_permutation_iterator(cs.active, act.list);
+      NRT_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, act.list, flags, list, count, int(act.n), stream));
+      void* tmp = scratch(0, tb);
+      NRT_CUDA(cub::DeviceSelect::Flagged(tmp, tb, act.list, flags, list, count, int(act.n), stream));
+    }
     ++launches;
   }
   // prefilter launch for one ray bundle of one mesh object

@@ -100,6 +100,28 @@ NRT_HD CObj loadCObj(const CObj* p) {
 #endif
 }
 
+// float32 mirror for the object scan's first look at a sphere (32 bytes, two 16-byte loads, the
+// same address for every lane of a warp): see sphereCertainMissF().
+struct alignas(16) CObjF {
+  float tx, ty, tz;   // translation column of worldToObject, rounded to float32
+  float r2;           // radius^2, rounded to float32
+  float mconst;       // object part of the error margin: 2e-6 r^2 + 2e-7 |t|_inf^2, rounded up
+  int32_t kind, mesh_obj;
+  int32_t fast;       // sphere, worldToObject exactly [I | t], everything finite and of sane magnitude
+};
+NRT_HD CObjF loadCObjF(const CObjF* p) {
+#if defined(__CUDA_ARCH__)
+  CObjF c;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+  c.tx = a.x; c.ty = a.y; c.tz = a.z; c.r2 = a.w;
+  c.mconst = __int_as_float(b.x); c.kind = b.y; c.mesh_obj = b.z; c.fast = b.w;
+  return c;
+#else
+  return *p;
+#endif
+}
+
 struct DLight {
   int32_t kind;
   int32_t _pad;
@@ -132,6 +154,7 @@ struct DScene {
   int32_t nobjects, nlights, nmeshes, nmesh_objs;
   const DObject* objects;
   const CObj* cobjs;              // compact mirror of objects[] for the object scan
+  const CObjF* cobjf;             // float32 mirror (first look at spheres)
   const DLight* lights;
   const DMesh* meshes;
   const int32_t* mesh_obj_index;  // mesh object k -> object index
@@ -202,6 +225,34 @@ NRT_HD bool sphereCertainMiss(double radius, V4 oc, V4 dir) {
   const float margin = 9.5367431640625e-7f * (a * (o2 + r * r));  // 16 * 2^-24
   // NaN / Inf (overflowing inputs) compare false => not a certain miss
   return disc < -margin;
+}
+
+// The same decision from float32 copies of the WORLD-space ray (converted once per ray, not per
+// object) and of the object's translation: oc = o + t is formed in float32.  With u = 2^-24,
+// M = |o|_inf + |t|_inf and delta = 2.01 u M bounding the error of each component of oc, the
+// float32 value of delta/4 = b^2 - a c differs from the exact one by at most
+//   16u a (|oc|^2 + r^2)                    conversions of d and r^2, the float32 operations
+// + a (7 |oc| delta + 6 delta^2)             perturbation of oc
+//   <= a (3.4e-6 |oc|^2 + 1.1e-7 (|o|_inf^2 + |t|_inf^2))   (7 |oc| delta <= 3.5 (2^-20 |oc|^2 + 2^20 delta^2)).
+// The margin used is a (5e-6 |oc|^2 + [2e-6 r^2 + 2e-7 |t|_inf^2] + [2e-7 |o|_inf^2]): object part in
+// CObjF.mconst, ray part in `mray`.  true => the reference's delta is negative (NegInf).
+struct RayF { float ox, oy, oz, dx, dy, dz, a, mray; };
+NRT_HD RayF makeRayF(V4 o, V4 d) {
+  RayF r;
+  r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
+  r.dx = (float)d.x; r.dy = (float)d.y; r.dz = (float)d.z;
+  r.a = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
+  const float mo = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
+  r.mray = 2e-7f * (mo * mo);
+  return r;
+}
+NRT_HD bool sphereCertainMissF(const CObjF& c, const RayF& r) {
+  const float ox = r.ox + c.tx, oy = r.oy + c.ty, oz = r.oz + c.tz;
+  const float b = fmaf(r.dx, ox, fmaf(r.dy, oy, r.dz * oz));
+  const float o2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
+  const float disc = fmaf(b, b, -(r.a * (o2 - c.r2)));
+  const float margin = r.a * fmaf(5e-6f, o2, c.mconst + r.mray);
+  return disc < -margin;   // NaN / Inf compare false => not a certain miss
 }
 
 // geom.nim:240-248

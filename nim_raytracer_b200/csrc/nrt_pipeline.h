@@ -124,8 +124,12 @@ NRT_HD int64_t queueBase(const ChunkState& cs, int mo, int b) {
 NRT_HD V4 ld4(const double* a, int64_t n, int64_t i) { return v4(a[i], a[n + i], a[2 * n + i], a[3 * n + i]); }
 NRT_HD void st4(double* a, int64_t n, int64_t i, V4 v) { a[i] = v.x; a[n + i] = v.y; a[2 * n + i] = v.z; a[3 * n + i] = v.w; }
 
+// 64-bit integer division is a long instruction sequence on the GPU; every index on this path fits 32 bits
+NRT_HD int64_t divFast(int64_t a, int32_t b) {
+  return ((uint64_t(a) >> 32) == 0) ? int64_t(uint32_t(a) / uint32_t(b)) : a / b;
+}
 NRT_HD void pixelOf(const FrameParams& fp, const ChunkState& cs, int64_t p, int& x, int& y) {
-  const int64_t ri = p / fp.nx;
+  const int64_t ri = divFast(p, fp.nx);
   x = int(p - ri * fp.nx) * fp.step;
   y = cs.rows[ri];
 }
@@ -201,8 +205,9 @@ NRT_HD void initSample(const ChunkState& cs, int64_t s, bool alive, V4 o, V4 d) 
 struct GenSimple {
   const DScene* sc; FrameParams fp; ChunkState cs;
   NRT_HD void operator()(int64_t s) const {
-    const int64_t p = cs.p0 + s / fp.spp;
-    const int k = int(s % fp.spp);
+    const int64_t sp = divFast(s, fp.spp);
+    const int64_t p = cs.p0 + sp;
+    const int k = int(s - sp * fp.spp);
     int x, y; pixelOf(fp, cs, p, x, y);
     const bool alive = !pixelSkipped(fp, x, y);
     double sx = 0.0, sy = 0.0;
@@ -246,7 +251,7 @@ NRT_HD bool waveRay(const DScene& sc, const FrameParams& fp, const ChunkState& c
     o = ld4(cs.rayO, cs.S, i); d = ld4(cs.rayD, cs.S, i);
     return true;
   }
-  const int64_t s = i / cs.nL;
+  const int64_t s = divFast(i, cs.nL);
   const int l = int(i - s * cs.nL);
   if (cs.hitObj[s] < 0) return false;
   const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
@@ -289,7 +294,7 @@ struct Gate {
   // wave-ray index (the slot of the ray's mesh results) of wave position idx < wave size
   NRT_HD uint32_t waveIndex(int64_t idx) const {
     if (kind == WAVE_SHADOW) {
-      const int64_t si = idx / cs.nL;
+      const int64_t si = divFast(idx, cs.nL);
       return uint32_t(sampleOf(act, si) * cs.nL + (idx - si * cs.nL));
     }
     return uint32_t(sampleOf(act, idx));
@@ -303,7 +308,7 @@ struct Gate {
     int lsh = 0;
     if (kind == WAVE_SHADOW) {
       if (idx >= nS * cs.nL) return g;
-      const int64_t si = idx / cs.nL;
+      const int64_t si = divFast(idx, cs.nL);
       lsh = int(idx - si * cs.nL);
       i = sampleOf(act, si) * cs.nL + lsh;
     } else {
@@ -420,8 +425,13 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
   TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
   // the exact shortcut of toObject() for [I | t] matrices applies to this ray?  (zero components
   // need toObject()'s per-component treatment)
-  const bool fastRay = (o.w == 1.0) && (d.w == 0.0) && finite3(o) && finite3(d) && d.x != 0.0 && d.y != 0.0 && d.z != 0.0;
+  const bool f32ok = (o.w == 1.0) && (d.w == 0.0) && finite3(o) && finite3(d);
+  const bool fastRay = f32ok && d.x != 0.0 && d.y != 0.0 && d.z != 0.0;
+  const RayF rf = makeRayF(o, d);
   for (int i = 0; i < sc.nobjects; ++i) {
+    const CObjF cf = loadCObjF(sc.cobjf + i);
+    // most (ray, sphere) pairs miss by far: decided from float32 copies without touching float64
+    if (cf.fast && f32ok && sphereCertainMissF(cf, rf)) { r.tests++; continue; }
     const CObj c = loadCObj(sc.cobjs + i);
     double t; uint32_t tri = kNoTri;
     if (c.kind == GEOM_MESH) {
@@ -474,8 +484,8 @@ struct Shade {
     const int bounce = cs.bounce[s];
     if (bounce == 0) {
       st.v[ST_PRIMARY] = 1;
-      if (s % fp.spp == 0 && (cs.aovObj || cs.aovTri || cs.aovT)) {
-        int x, y; pixelOf(fp, cs, cs.p0 + s / fp.spp, x, y);
+      if ((cs.aovObj || cs.aovTri || cs.aovT) && s == divFast(s, fp.spp) * fp.spp) {
+        int x, y; pixelOf(fp, cs, cs.p0 + divFast(s, fp.spp), x, y);
         const int64_t pi = int64_t(y) * fp.width + x;
         if (cs.aovObj) cs.aovObj[pi] = tr.obj;
         if (cs.aovTri) cs.aovTri[pi] = (tr.obj >= 0 && tr.tri != kNoTri) ? int32_t(tr.tri) : -1;

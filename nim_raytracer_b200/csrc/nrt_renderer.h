@@ -36,6 +36,7 @@ struct SceneData {
   std::vector<DMesh> meshes;  // device pointers inside
   std::vector<int32_t> moIndex;
   std::vector<CObj> cobjs; CObj* dCObjs = nullptr;
+  std::vector<CObjF> cobjf; CObjF* dCObjF = nullptr;
   DObject* dObjs = nullptr; DLight* dLights = nullptr; DMesh* dMeshes = nullptr; int32_t* dMo = nullptr;
   std::vector<void*> owned;
   bool anyReflective = false, anyPointLight = false;
@@ -209,6 +210,19 @@ struct SceneData {
       c.t[0] = objs[i].w2o[12]; c.t[1] = objs[i].w2o[13]; c.t[2] = objs[i].w2o[14];
       c.radius = objs[i].radius;
     }
+    cobjf.assign(objs.size(), CObjF{});
+    for (size_t i = 0; i < objs.size(); ++i) {
+      CObjF& f = cobjf[i];
+      const CObj& c = cobjs[i];
+      const double mt = std::max(std::fabs(c.t[0]), std::max(std::fabs(c.t[1]), std::fabs(c.t[2])));
+      const double r2 = c.radius * c.radius;
+      f.tx = float(c.t[0]); f.ty = float(c.t[1]); f.tz = float(c.t[2]);
+      f.r2 = float(r2);
+      f.mconst = roundUpF(2e-6 * r2 + 2e-7 * mt * mt);
+      f.kind = c.kind; f.mesh_obj = c.mesh_obj;
+      f.fast = (c.kind == NRT_GEOM_SPHERE && c.xlate_only && std::isfinite(c.radius) && mt < 1e15 && r2 < 1e30 && r2 > 1e-30) ? 1 : 0;
+    }
+    dCObjF = up(cobjf.data(), int64_t(cobjf.size()), reuse ? dCObjF : nullptr);
     dCObjs = up(cobjs.data(), int64_t(cobjs.size()), reuse ? dCObjs : nullptr);
     dObjs = up(objs.data(), int64_t(objs.size()), reuse ? dObjs : nullptr);
     dLights = up(lights.data(), int64_t(lights.size()), reuse ? dLights : nullptr);
@@ -249,7 +263,7 @@ struct SceneData {
       }
       dFrames = up(frames.data(), int64_t(frames.size()), reuse ? dFrames : nullptr);
     }
-    h.objects = dObjs; h.cobjs = dCObjs; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames;
+    h.objects = dObjs; h.cobjs = dCObjs; h.cobjf = dCObjF; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames;
     std::memcpy(h.c2w, desc->camera_to_world, sizeof(h.c2w));
     h.tan_half_fov = std::tan((desc->fov * (kPi / 180.0)) / 2);  // renderer.nim:38; Nim degToRad = d * (PI/180)
     std::memcpy(h.bg, desc->bg_color, sizeof(h.bg));
@@ -310,6 +324,7 @@ struct Renderer {
   BE* be = nullptr;
   ChunkState cs{};
   int64_t capS = 0, capNR = 0, capCand = 0;
+  int64_t wantedS = 0;   // the chunk-size request the current buffers were sized for (before the memory cap)
   int capMO = -1, capNL = -1, capWaves = 0, capRows = 0;
   std::vector<void*> owned;
   int32_t* dRows = nullptr;
@@ -320,6 +335,7 @@ struct Renderer {
     for (void* p : owned) be->dfree(p);
     owned.clear();
     capS = capNR = capCand = 0; capMO = -1; capNL = -1; capWaves = 0; capRows = 0; dRows = nullptr;
+    wantedS = 0;
   }
   template <class T> T* al(int64_t n) { T* p = static_cast<T*>(be->dalloc(sizeof(T) * std::max<int64_t>(n, 1))); owned.push_back(p); return p; }
 
@@ -367,7 +383,7 @@ struct Renderer {
     uint32_t* cnt = cs.counters + int64_t(wave) * nMO * cst;
     const int pathMode = primary ? FM_ORIGIN : FM_GENERAL;
     const int mult = (kind == WAVE_SHADOW) ? nL : 1;
-    be->gate(Gate{sd.d, fp, cs, kind, act, force_exact, pathMode}, act.list ? act.count : nullptr, act.n * mult, mult, nMO, cnt);
+    be->gate(Gate{sd.d, fp, cs, kind, act, force_exact, pathMode}, nullptr, act.n * mult, mult, nMO, cnt);
     for (int mo = 0; mo < nMO; ++mo) {
       uint32_t* c = cnt + mo * cst;
       const DMesh& m = sd.meshes[sd.objs[sd.moIndex[mo]].mesh];
@@ -417,11 +433,21 @@ struct Renderer {
     if (sd.anyReflective && o.depth_mode == NRT_DEPTH_INTENDED) maxBounces = std::min(maxBounces, std::max(0, o.max_ray_depth));
     const int waves = 2 * (maxBounces + 1);
     const int64_t npixTotal = int64_t(rows.size()) * fp.nx;
-    // 16 Mi samples per chunk (~9 GB of state for one mesh object and two lights; sized for 180 GB
-    // of HBM): large chunks amortise launches and the per-bounce host checks
-    int64_t S = envInt("NRT_CHUNK_SAMPLES", int64_t(1) << 24);
+    // Samples per chunk: as many as fit in 96 GB or 60 % of the free device memory (~470 B of state per
+    // sample for one mesh object and two lights; a 3840x2160x16 frame is ONE chunk of 62 GB on a 180 GB
+    // B200).  Every bounce costs ~25 launches and a host check whatever the chunk size, so large chunks pay.
+    int64_t S = envInt("NRT_CHUNK_SAMPLES", int64_t(1) << 28);
     const int64_t perSample = 260 + int64_t(110) * std::max(1, nL) * std::max(1, nMO);
-    S = std::min<int64_t>(S, (int64_t(32) << 30) / perSample);
+    S = std::min<int64_t>(S, (int64_t(1) << 31) / std::max(1, nL));   // wave-ray indices are 32-bit
+    S = std::min<int64_t>(S, npixTotal * fp.spp);
+    if (S <= wantedS && capS > 0) {
+      S = std::min(S, capS);          // the existing buffers (sized for a request at least this large) serve
+    } else {
+      // (re)allocation ahead: ask the device (cudaMemGetInfo is far too slow to call every frame)
+      wantedS = S;
+      const int64_t memCap = std::min<int64_t>(int64_t(96) << 30, int64_t(0.6 * double(be->memAvailable(capS * perSample))));
+      S = std::min<int64_t>(S, std::max<int64_t>(memCap, int64_t(64) << 20) / perSample);
+    }
     S = std::max<int64_t>(S, fp.spp);
     S = std::min<int64_t>(S, npixTotal * fp.spp);
     int64_t chunkPix = std::max<int64_t>(1, S / fp.spp);
@@ -454,18 +480,18 @@ struct Renderer {
         for (int bounce = 0;; ++bounce) {
           uint32_t* nextList = cs.alist + int64_t((bounce + 1) & 1) * cs.S;
           uint32_t* nextCount = cs.acount + bounce + 1;
-          const uint32_t* cnt = act.list ? act.count : nullptr;
+          // (act.n is exact on the host for every bounce: launches are sized to it)
           meshWave(sd, fp, WAVE_PATH, act, wave, bounce == 0, force_exact); ++wave;
-          be->forEachStats(cnt, act.n, Shade{sd.d, fp, cs, act}, cs.stats);
+          be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act}, cs.stats);
           if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, false, force_exact);
           ++wave;
-          be->forEachStats(cnt, act.n, Resolve{sd.d, fp, cs, act}, cs.stats);
+          be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act}, cs.stats);
           if (bounce >= maxBounces) break;
-          be->compactActive(cs, nS, nextList, nextCount);
+          be->compactActive(cs, act, nextList, nextCount);
           uint32_t cont = 0;
           be->download(&cont, nextCount, sizeof(cont));
           if (cont == 0) break;  // no sample continued
-          act = ActiveSet{nextList, nextCount, 0};
+          act = ActiveSet{nextList, nextCount, int64_t(cont)};
         }
         be->forEach(npix, Finalize{fp, cs});
         // chunk epilogue: counters (profile + overflow check) and stats

@@ -32,6 +32,7 @@ struct LoopBackend {
   void upload(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
   void download(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
   void sync() {}
+  int64_t memAvailable(int64_t) { return int64_t(1) << 40; }
   template <class F> void forEach(int64_t n, const F& f) { for (int64_t i = 0; i < n; ++i) f(i); ++launches; }
   template <class F> void forEachStats(const uint32_t* count, int64_t n, const F& f, unsigned long long* st) {
     if (count) n = *count;
@@ -145,11 +146,13 @@ struct LoopBackend {
     }
     ++launches;
   }
-  // next bounce's active list: the samples with active == 1, in sample order
-  void compactActive(const ChunkState& cs, int64_t nS, uint32_t* list, uint32_t* count) {
+  // next bounce's active list: the samples of the current set with active == 1, in sample order
+  void compactActive(const ChunkState& cs, const ActiveSet& act, uint32_t* list, uint32_t* count) {
     uint32_t n = 0;
-    for (int64_t s = 0; s < nS; ++s)
+    for (int64_t i = 0; i < act.n; ++i) {
+      const int64_t s = act.list ? int64_t(act.list[i]) : i;
       if (cs.active[s]) list[n++] = uint32_t(s);
+    }
     *count = n;
     ++launches;
   }
