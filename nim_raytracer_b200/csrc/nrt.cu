@@ -50,17 +50,25 @@ __global__ void __launch_bounds__(kBlock) k_for_each(F f, int64_t n) {
 // counter (26-bit halves, so the warp sums cannot overflow), shared-memory atomics across the
 // warps, one global atomic per counter and block.
 __device__ __forceinline__ void blockStatsAdd(const StatDelta& d, unsigned long long* stats) {
-  __shared__ unsigned long long sh[ST_COUNT];
-  if (threadIdx.x < ST_COUNT) sh[threadIdx.x] = 0;
+  // 24-bit halves: a warp sum stays below 2^29 and a block sum below 2^32, so native 32-bit
+  // shared-memory atomics serve (64-bit ones are compare-and-swap loops); per-thread values < 2^48
+  __shared__ unsigned sh[2 * ST_COUNT];
+  if (threadIdx.x < 2 * ST_COUNT) sh[threadIdx.x] = 0;
   __syncthreads();
 #pragma unroll
   for (int k = 0; k <= ST_CONT; ++k) {
-    const unsigned lo = __reduce_add_sync(0xffffffffu, unsigned(d.v[k] & 0x3FFFFFFull));
-    const unsigned hi = __reduce_add_sync(0xffffffffu, unsigned(d.v[k] >> 26));
-    if ((threadIdx.x & 31) == 0 && (lo | hi)) atomicAdd(&sh[k], (unsigned long long)lo + ((unsigned long long)hi << 26));
+    const unsigned lo = __reduce_add_sync(0xffffffffu, unsigned(d.v[k] & 0xFFFFFFull));
+    const unsigned hi = __reduce_add_sync(0xffffffffu, unsigned(d.v[k] >> 24));
+    if ((threadIdx.x & 31) == 0) {
+      if (lo) atomicAdd(&sh[2 * k], lo);
+      if (hi) atomicAdd(&sh[2 * k + 1], hi);
+    }
   }
   __syncthreads();
-  if (threadIdx.x <= ST_CONT && sh[threadIdx.x]) atomicAdd(&stats[threadIdx.x], sh[threadIdx.x]);
+  if (threadIdx.x <= ST_CONT) {
+    const unsigned long long v = (unsigned long long)sh[2 * threadIdx.x] + ((unsigned long long)sh[2 * threadIdx.x + 1] << 24);
+    if (v) atomicAdd(&stats[threadIdx.x], v);
+  }
 }
 
 template <class F>

@@ -100,22 +100,18 @@ NRT_HD CObj loadCObj(const CObj* p) {
 #endif
 }
 
-// float32 mirror for the object scan's first look at a sphere (32 bytes, two 16-byte loads, the
-// same address for every lane of a warp): see sphereCertainMissF().
+// float32 mirror for the object scan's first look at an object (16 bytes, one vector load, the
+// same address for every lane of a warp): see certainMissF().
 struct alignas(16) CObjF {
   float tx, ty, tz;   // translation column of worldToObject, rounded to float32
-  float r2;           // radius^2, rounded to float32
-  float mconst;       // object part of the error margin: 2e-6 r^2 + 2e-7 |t|_inf^2, rounded up
-  int32_t kind, mesh_obj;
-  int32_t fast;       // sphere, worldToObject exactly [I | t], everything finite and of sane magnitude
+  float r2m;          // radius^2 + the object part of the error margin, rounded up; +Inf for every
+                      // object the float32 test does not apply to (not a sphere, general matrix, ...)
 };
 NRT_HD CObjF loadCObjF(const CObjF* p) {
 #if defined(__CUDA_ARCH__)
   CObjF c;
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
-  c.tx = a.x; c.ty = a.y; c.tz = a.z; c.r2 = a.w;
-  c.mconst = __int_as_float(b.x); c.kind = b.y; c.mesh_obj = b.z; c.fast = b.w;
+  c.tx = a.x; c.ty = a.y; c.tz = a.z; c.r2m = a.w;
   return c;
 #else
   return *p;
@@ -234,8 +230,10 @@ NRT_HD bool sphereCertainMiss(double radius, V4 oc, V4 dir) {
 //   16u a (|oc|^2 + r^2)                    conversions of d and r^2, the float32 operations
 // + a (7 |oc| delta + 6 delta^2)             perturbation of oc
 //   <= a (3.4e-6 |oc|^2 + 1.1e-7 (|o|_inf^2 + |t|_inf^2))   (7 |oc| delta <= 3.5 (2^-20 |oc|^2 + 2^20 delta^2)).
-// The margin used is a (5e-6 |oc|^2 + [2e-6 r^2 + 2e-7 |t|_inf^2] + [2e-7 |o|_inf^2]): object part in
-// CObjF.mconst, ray part in `mray`.  true => the reference's delta is negative (NegInf).
+// The test is b^2 - a c < -a (5e-6 |oc|^2 + [2e-6 r^2 + 2e-7 |t|_inf^2] + [2e-7 |o|_inf^2]), evaluated as
+//   b^2 < a (|oc|^2 (1 - 5e-6) - r2m - mray)     r2m = r^2 + object part (CObjF), mray = ray part
+// (the rearrangement costs another ~3u a |oc|^2, inside the slack between 4.3e-6 and 5e-6).
+// true => the reference's delta is negative (NegInf).  NaN / Inf compare false.
 struct RayF { float ox, oy, oz, dx, dy, dz, a, mray; };
 NRT_HD RayF makeRayF(V4 o, V4 d) {
   RayF r;
@@ -246,13 +244,11 @@ NRT_HD RayF makeRayF(V4 o, V4 d) {
   r.mray = 2e-7f * (mo * mo);
   return r;
 }
-NRT_HD bool sphereCertainMissF(const CObjF& c, const RayF& r) {
+NRT_HD bool certainMissF(const CObjF& c, const RayF& r) {
   const float ox = r.ox + c.tx, oy = r.oy + c.ty, oz = r.oz + c.tz;
   const float b = fmaf(r.dx, ox, fmaf(r.dy, oy, r.dz * oz));
   const float o2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
-  const float disc = fmaf(b, b, -(r.a * (o2 - c.r2)));
-  const float margin = r.a * fmaf(5e-6f, o2, c.mconst + r.mray);
-  return disc < -margin;   // NaN / Inf compare false => not a certain miss
+  return b * b < r.a * fmaf(o2, 0.999995f, -(c.r2m + r.mray));
 }
 
 // geom.nim:240-248

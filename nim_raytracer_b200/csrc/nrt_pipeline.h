@@ -82,6 +82,7 @@ struct ChunkState {
   uint32_t* preRay;  // preCap
   uint32_t* preRec;  // preCap
   uint32_t* xref;    // nMO*NR     exact (float64 brute force) queue
+  uint8_t* occ;      // NR         shadow ray (sample, light) found an occluder (ShadowTrace -> Resolve)
   // ordered queue compaction (CUDA backend): gate pass 1 writes a code per (mesh object, wave
   // position) and per-block counts; a scan turns the counts into queue offsets; pass 2 writes the
   // rays, so queue order == wave order (scanline order): consecutive queue entries are neighbours.
@@ -428,10 +429,22 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
   const bool f32ok = (o.w == 1.0) && (d.w == 0.0) && finite3(o) && finite3(d);
   const bool fastRay = f32ok && d.x != 0.0 && d.y != 0.0 && d.z != 0.0;
   const RayF rf = makeRayF(o, d);
-  for (int i = 0; i < sc.nobjects; ++i) {
-    const CObjF cf = loadCObjF(sc.cobjf + i);
-    // most (ray, sphere) pairs miss by far: decided from float32 copies without touching float64
-    if (cf.fast && f32ok && sphereCertainMissF(cf, rf)) { r.tests++; continue; }
+  // Two phases per batch of 32 objects, both in list order: a branch-free float32 pass marks the
+  // objects that are not certain misses (most (ray, sphere) pairs miss by far); the float64
+  // evaluation of the reference then runs for the marked ones only.
+  for (int base = 0; base < sc.nobjects; base += 32) {
+    const int nb = (sc.nobjects - base < 32) ? sc.nobjects - base : 32;
+    uint32_t need = (nb == 32) ? 0xFFFFFFFFu : ((1u << nb) - 1u);
+    if (f32ok) {
+      uint32_t miss = 0;
+#pragma unroll 4
+      for (int j = 0; j < nb; ++j) miss |= uint32_t(certainMissF(loadCObjF(sc.cobjf + base + j), rf)) << j;
+      need &= ~miss;
+    }
+    r.tests += nb;
+    while (need) {
+    const int i = base + (__builtin_ffs(int(need)) - 1);
+    need &= need - 1;
     const CObj c = loadCObj(sc.cobjs + i);
     double t; uint32_t tri = kNoTri;
     if (c.kind == GEOM_MESH) {
@@ -461,8 +474,8 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
       else if (c.kind == GEOM_BOX) t = aabbIntersect(sc.objects[i].bmin, sc.objects[i].bmax, initRay(oo, dd));
       else t = NRT_NEG_INF;
     }
-    r.tests++;
     if (t >= 0 && t < r.t) { r.t = t; r.obj = i; r.tri = tri; r.hits++; }
+    }
   }
   return r;
 }
@@ -519,7 +532,28 @@ struct Shade {
   }
 };
 
-// ---- resolve: shadow tests + diffuse + reflection set-up (renderer.nim:90-127)
+// ---- shadow trace: one element per shadow ray (active sample i / nL, light i % nL): the trace()
+// call of renderer.nim:101-102; only "some object hit before the light" is kept (renderer.nim:103)
+struct ShadowTrace {
+  const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
+  NRT_HD StatDelta operator()(int64_t idx) const {
+    StatDelta st = zeroStats();
+    const int64_t si = divFast(idx, cs.nL);
+    if (si >= activeN(act)) return st;
+    const int l = int(idx - si * cs.nL);
+    const int64_t s = sampleOf(act, si);
+    if (cs.hitObj[s] < 0) return st;
+    const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
+    const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
+    const V4 so = add(hitW, scale(n, fp.bias)), sd = scale(li.lightDir, -1.0);   // renderer.nim:98-99
+    const TraceOut tr = traceObjects(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx);
+    st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
+    cs.occ[s * cs.nL + l] = tr.obj >= 0 ? 1 : 0;
+    return st;
+  }
+};
+
+// ---- resolve: shadeDiffuse of the unoccluded lights + reflection set-up (renderer.nim:90-127)
 // Samples whose path continues keep active == 1; the backend compacts them IN SAMPLE ORDER into
 // the next bounce's active list (compactActive), so reflection rays of neighbouring pixels stay
 // neighbours in the queues.
@@ -535,11 +569,9 @@ struct Resolve {
     const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
     V3 local = v3(0.0, 0.0, 0.0);
     for (int l = 0; l < cs.nL; ++l) {
+      if (cs.occ[s * cs.nL + l]) continue;
       const ShadingInfo si = getShadingInfo(sc->lights[l], hitW);
-      const V4 so = add(hitW, scale(n, fp.bias)), sd = scale(si.lightDir, -1.0);
-      const TraceOut tr = traceObjects(*sc, cs, so, sd, si.lightDistance, s * cs.nL + l, idx * cs.nL + l);
-      st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
-      if (tr.obj < 0) local = add(local, shadeDiffuse(ob, si, n));
+      local = add(local, shadeDiffuse(ob, si, n));
     }
     const double k = ob.reflection, w = cs.weight[s];
     const int bounce = cs.bounce[s];

@@ -217,10 +217,8 @@ struct SceneData {
       const double mt = std::max(std::fabs(c.t[0]), std::max(std::fabs(c.t[1]), std::fabs(c.t[2])));
       const double r2 = c.radius * c.radius;
       f.tx = float(c.t[0]); f.ty = float(c.t[1]); f.tz = float(c.t[2]);
-      f.r2 = float(r2);
-      f.mconst = roundUpF(2e-6 * r2 + 2e-7 * mt * mt);
-      f.kind = c.kind; f.mesh_obj = c.mesh_obj;
-      f.fast = (c.kind == NRT_GEOM_SPHERE && c.xlate_only && std::isfinite(c.radius) && mt < 1e15 && r2 < 1e30 && r2 > 1e-30) ? 1 : 0;
+      const bool fast = c.kind == NRT_GEOM_SPHERE && c.xlate_only && std::isfinite(c.radius) && mt < 1e15 && r2 < 1e30 && r2 > 1e-30;
+      f.r2m = fast ? roundUpF(r2 + 2e-6 * r2 + 2e-7 * mt * mt) : float(NRT_INF);
     }
     dCObjF = up(cobjf.data(), int64_t(cobjf.size()), reuse ? dCObjF : nullptr);
     dCObjs = up(cobjs.data(), int64_t(cobjs.size()), reuse ? dCObjs : nullptr);
@@ -365,6 +363,7 @@ struct Renderer {
       cs.gvb = (NR + 255) / 256 + 1;
       cs.gsn = (cs.gvb + 255) / 256;
       cs.gflag = al<uint8_t>(m);
+      cs.occ = al<uint8_t>(NR);
       const int64_t grows = int64_t(std::max(nMO, 1)) * (2 + nL);
       cs.gcnt = al<uint32_t>(grows * cs.gvb);
       cs.gseg = al<uint32_t>(grows * cs.gsn);
@@ -485,6 +484,7 @@ struct Renderer {
           be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act}, cs.stats);
           if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, false, force_exact);
           ++wave;
+          if (nL > 0) be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
           be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act}, cs.stats);
           if (bounce >= maxBounces) break;
           be->compactActive(cs, act, nextList, nextCount);
