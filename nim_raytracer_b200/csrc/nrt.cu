@@ -15,6 +15,7 @@
 #include <thrust/iterator/permutation_iterator.h>
 
 #include <atomic>
+#include <type_traits>
 #include <cstdio>
 #include <stdexcept>
 #include <mutex>
@@ -117,7 +118,6 @@ __global__ void __launch_bounds__(kBlock) k_for_each_counted(F f, const uint32_t
 // queue entries a prefilter warp works on belong to neighbouring pixels, which is what makes the
 // chunk bounds of the two-level traversal selective.
 static constexpr int kSegBlocks = 256;   // 256-ray blocks per segment
-__device__ __forceinline__ uint8_t gateCode(const GateOut& o) { return o.pass ? (o.safe ? uint8_t(1 + o.bundle) : uint8_t(255)) : uint8_t(0); }
 __device__ __forceinline__ uint8_t gateWant(int r, int nB) { return r < nB ? uint8_t(1 + r) : uint8_t(255); }
 
 __global__ void __launch_bounds__(kBlock) k_gate_flags(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO, uint32_t* neCount) {
@@ -155,6 +155,55 @@ __global__ void __launch_bounds__(kBlock) k_gate_flags(Gate g, const uint32_t* c
   }
 }
 
+// Fused producer + gate flags (nrt_pipeline.h: GenGate, ShadeGate): thread i creates `mult` wave
+// positions i * mult + k, evaluates their gate codes while the rays are in registers and counts
+// them for the 256-position blocks it overlaps (a CTA of 256 threads covers exactly `mult` of them).
+template <class P>
+struct ProduceEmit {
+  const ChunkState& cs; uint8_t* flags; uint32_t* sh; int64_t i; int mult, rows, nRow, nB;
+  __device__ __forceinline__ void operator()(int k, int mo, uint8_t code) const {
+    const int64_t pos = i * mult + k;
+    flags[int64_t(mo) * cs.NR + pos] = code;
+    // warp-aggregated shared-memory count: lanes with the same (block, row) key elect one adder
+    const unsigned act = __activemask();
+    if (!__any_sync(act, code != 0)) return;
+    const int vbl = int((int64_t(threadIdx.x) * mult + k) >> 8);
+    const int r = (code == 255) ? nB : int(code) - 1;
+    const int key = code ? vbl * rows + mo * nRow + r : -1;
+    const unsigned peers = __match_any_sync(act, key);
+    if (key >= 0 && (threadIdx.x & 31) == unsigned(__ffs(peers) - 1)) atomicAdd(&sh[key], uint32_t(__popc(peers)));
+  }
+};
+__device__ __forceinline__ void produceCounts(const ChunkState& cs, const uint32_t* sh, int64_t n, int mult, int rows, uint32_t* neCount) {
+  const int64_t nVB = (n * mult + kBlock - 1) / kBlock;
+  for (int k = threadIdx.x; k < mult * rows; k += kBlock) {
+    const int vbl = k / rows, row = k - vbl * rows;
+    const int64_t vb = int64_t(blockIdx.x) * mult + vbl;
+    if (vb >= nVB) continue;
+    const uint32_t c = sh[k];
+    cs.gcnt[int64_t(row) * cs.gvb + vb] = c;
+    if (c) atomicAdd(&cs.gseg[int64_t(row) * cs.gsn + vb / kSegBlocks], c);
+  }
+  for (int vbl = threadIdx.x; vbl < mult; vbl += kBlock) {
+    const int64_t vb = int64_t(blockIdx.x) * mult + vbl;
+    if (vb >= nVB) continue;
+    uint32_t any = 0;
+    for (int row = 0; row < rows; ++row) any |= sh[vbl * rows + row];
+    if (any) cs.gne[atomicAdd(neCount, 1u)] = uint32_t(vb);
+  }
+}
+template <class P>
+__global__ void __launch_bounds__(kBlock) k_produce_gate(P p, ChunkState cs, int64_t n, int mult, int nMO, uint32_t* neCount) {
+  extern __shared__ uint32_t sh_pc[];   // mult * rows
+  const int nB = 1 + cs.nL, nRow = nB + 1, rows = nMO * nRow;
+  for (int k = threadIdx.x; k < mult * rows; k += kBlock) sh_pc[k] = 0;
+  __syncthreads();
+  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  ProduceEmit<P> emit{cs, cs.gflag, sh_pc, i, mult, rows, nRow, nB};
+  if (i < n) p(i, emit);
+  __syncthreads();
+  produceCounts(cs, sh_pc, n, mult, rows, neCount);
+}
 // one CTA per (mesh object, queue) row: exclusive scan of the segment totals (and their reset for the
 // next gate); queue total -> counter block
 __global__ void __launch_bounds__(1024) k_gate_scan(ChunkState cs, const uint32_t* count, int64_t nHost, int mult, uint32_t* cnt) {
@@ -304,6 +353,7 @@ static constexpr int FT_THREADS = 256;
 static constexpr int FT_WARPS = FT_THREADS / 32;
 static constexpr int FT_TC = 256;     // records per chunk
 static constexpr int FT_WB = 256;     // per-warp survivor buffer entries (flushed after every chunk)
+static constexpr uint32_t kGroupMax = 4;   // chunks per work item: admitted chunks cluster in Morton order, so large groups make a few items very long
 static_assert(kRecPad == FT_TC, "one bound per shared-memory chunk");
 
 struct PreArgs {
@@ -339,7 +389,7 @@ __device__ __forceinline__ float2 prefilterPair(const float2* h, float a0, float
 }
 
 template <int MODE, int R, int U>
-__global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
+__global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? 2 : 3) k_mesh_prefilter(PreArgs a) {
   constexpr int NH = hotFloats(MODE);      // float2 per record pair == float4 per record quad
   constexpr int CH4 = (FT_TC / 4) * NH;    // float4 per chunk
   constexpr uint32_t RUN = 32 * R;
@@ -367,7 +417,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_mesh_prefilter(PreArgs a) {
   const uint32_t nRuns = (nq + RUN - 1) / RUN;
   const uint32_t nChunks = nrecPadded / FT_TC;
   // chunk groups of <= 32 chunks (one pass mask); smaller groups when there are too few runs to fill the GPU
-  uint32_t G = 32;
+  uint32_t G = kGroupMax;
   const uint32_t totalWarps = gridDim.x * FT_WARPS;
   while (G > 1 && uint64_t(nRuns) * ((nChunks + G - 1) / G) < 4ull * totalWarps) G >>= 1;
   const uint32_t nGroups = (nChunks + G - 1) / G;
@@ -622,6 +672,23 @@ struct CudaBackend {
     k_gate_write<<<unsigned(sms * 8), kBlock, 0, stream>>>(g, count, n, mult, nMO, ne);
     NRT_CUDA(cudaGetLastError()); launches += 3;
   }
+  // fused producer + gate flags (GenGate: mult 1; ShadeGate: mult nL, with Stats); gateFinish() completes the gate
+  template <class P> void produceGate(int64_t n, int mult, const P& p, const ChunkState& cs, int nMO, uint32_t* cnt, unsigned long long* stats) {
+    use();
+    if (n <= 0) return;
+    const size_t sm = sizeof(uint32_t) * size_t(mult) * nMO * (2 + cs.nL);
+    (void)stats;
+    k_produce_gate<P><<<blocksFor(n), kBlock, sm, stream>>>(p, cs, n, mult, nMO, cnt + CNT_NE);
+    NRT_CUDA(cudaGetLastError()); ++launches;
+  }
+  void gateFinish(const Gate& g, int64_t n, int nMO, uint32_t* cnt) {
+    use();
+    if (n <= 0) return;
+    const int rows = nMO * (2 + g.cs.nL);
+    k_gate_scan<<<unsigned(rows), 1024, 0, stream>>>(g.cs, nullptr, n, 1, cnt);
+    k_gate_write<<<unsigned(sms * 8), kBlock, 0, stream>>>(g, nullptr, n, 1, nMO, cnt + CNT_NE);
+    NRT_CUDA(cudaGetLastError()); launches += 2;
+  }
   // Morton order of the face centroids -> m.order (stable: ties keep face order)
   void sortFaces(const DMesh& m) {
     use();
@@ -713,11 +780,12 @@ struct CudaBackend {
     NRT_CUDA(cudaEventRecord(ev.second, stream));
   }
   // call after a stream sync
-  double filterMs(int64_t* n, double* byMode) {
+  double filterMs(int64_t* n, double* byMode, std::vector<float>* each = nullptr) {
     double ms = 0;
     for (size_t i = 0; i < filterUsed; ++i) {
       float t = 0;
       if (cudaEventElapsedTime(&t, filterEvents[i].first, filterEvents[i].second) == cudaSuccess) { ms += t; byMode[filterModes[i]] += t; }
+      if (each) each->push_back(t);
     }
     *n = int64_t(filterUsed);
     filterUsed = 0;
@@ -928,7 +996,18 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     p.total_ms = std::max(p.total_ms, double(ms));
     int64_t nl = 0;
     double byMode[4] = {0, 0, 0, 0};
-    const double fms = dc->be.filterMs(&nl, byMode);
+    std::vector<float> each;
+    const bool traceP = std::getenv("NRT_TRACE_PREFILTER") != nullptr;
+    const double fms = dc->be.filterMs(&nl, byMode, traceP ? &each : nullptr);
+    if (traceP) {
+      const auto& lg = sc->dev[d].rn.preLog;
+      for (size_t i = 0; i < lg.size() && i < each.size(); ++i)
+        fprintf(stderr, "[prefilter] dev %d wave %2d mo %d bundle %d mode %d rays %9lld runs %7lld chunks %4lld work %9lld (%.2f per run) pre %9lld  %8.1f us\n",
+                d, lg[i].wave, lg[i].mo, lg[i].b, lg[i].mode, (long long)lg[i].rays,
+                (long long)((lg[i].rays + prefilterRunRays(lg[i].mode) - 1) / prefilterRunRays(lg[i].mode)), (long long)lg[i].nch,
+                (long long)lg[i].work, double(lg[i].work) / std::max<double>(1.0, double((lg[i].rays + prefilterRunRays(lg[i].mode) - 1) / prefilterRunRays(lg[i].mode))),
+                (long long)lg[i].pre, each[i] * 1e3);
+    }
     p.mesh_filter_ms = std::max(p.mesh_filter_ms, fms);
     p.mesh_filter_launches += nl;
     const ProfileAcc& a = sc->dev[d].rn.prof;

@@ -203,9 +203,11 @@ NRT_HD void initSample(const ChunkState& cs, int64_t s, bool alive, V4 o, V4 d) 
 }
 
 // ---- gen: one element per SAMPLE (akNone / akGrid) ---------------------------
+struct GenOut { bool alive; V4 o, d; };
 struct GenSimple {
   const DScene* sc; FrameParams fp; ChunkState cs;
-  NRT_HD void operator()(int64_t s) const {
+  NRT_HD void operator()(int64_t s) const { GenOut out; run(s, out); }
+  NRT_HD void run(int64_t s, GenOut& out) const {
     const int64_t sp = divFast(s, fp.spp);
     const int64_t p = cs.p0 + sp;
     const int k = int(s - sp * fp.spp);
@@ -223,6 +225,7 @@ struct GenSimple {
     castPrimaryRay(*sc, fp.width, fp.height, fp.aa_kind == AA_NONE ? double(x) : double(x) + sx,
                    fp.aa_kind == AA_NONE ? double(y) : double(y) + sy, o, d);
     initSample(cs, s, alive, o, d);
+    out.alive = alive; out.o = o; out.d = d;
   }
 };
 
@@ -318,7 +321,12 @@ struct Gate {
     }
     const bool valid = waveRay(*sc, fp, cs, kind, i, o, d);
     if (!valid) return g;
-    g.wi = uint32_t(i);
+    return evalRay(o, d, uint32_t(i), mo, lsh);
+  }
+  // the gate of one world-space ray (o, d) with wave-ray index wi (lsh = light of a shadow ray)
+  NRT_HD GateOut evalRay(V4 o, V4 d, uint32_t wi, int mo, int lsh) const {
+    GateOut g; g.pass = false; g.safe = false; g.bundle = 0;
+    g.wi = wi;
     const DObject& ob = sc->objects[sc->mesh_obj_index[mo]];
     const DMesh& m = sc->meshes[ob.mesh];
     V4 oo, dd;
@@ -342,6 +350,7 @@ struct Gate {
     return g;
   }
 };
+NRT_HD uint8_t gateCode(const GateOut& o) { return o.pass ? (o.safe ? uint8_t(1 + o.bundle) : uint8_t(255)) : uint8_t(0); }
 
 // ---- exact: float64 brute force over ALL faces for rays the filter cannot take
 struct ExactMesh {
@@ -484,10 +493,13 @@ struct StatDelta { unsigned long long v[ST_COUNT]; };
 NRT_HD StatDelta zeroStats() { StatDelta s; for (int i = 0; i < ST_COUNT; ++i) s.v[i] = 0; return s; }
 
 // ---- shade: nearest hit of the path ray, hit point and normal (renderer.nim:71-88)
+struct ShadeOut { bool hit; int64_t s; V4 hitW, n; };
 struct Shade {
   const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
-  NRT_HD StatDelta operator()(int64_t idx) const {
+  NRT_HD StatDelta operator()(int64_t idx) const { ShadeOut out; return run(idx, out); }
+  NRT_HD StatDelta run(int64_t idx, ShadeOut& out) const {
     StatDelta st = zeroStats();
+    out.hit = false; out.s = 0;
     if (idx >= activeN(act)) return st;
     const int64_t s = sampleOf(act, idx);
     if (!cs.active[s]) return st;
@@ -528,7 +540,22 @@ struct Shade {
     st4(cs.hitW, cs.S, s, hitW);
     st4(cs.nrm, cs.S, s, n);
     cs.hitObj[s] = tr.obj;
+    out.hit = true; out.s = s; out.hitW = hitW; out.n = n;
     return st;
+  }
+};
+
+// ---- fused producer: the kernel that creates the primary rays also evaluates their gate codes while
+// the rays are in registers (the CUDA backend counts the codes per 256-position block in the same
+// kernel, so the separate flags pass over the sample state disappears).  `emit(k, mo, code)` receives
+// the code of wave position i * mult + k for mesh object mo.  (The same fusion of Shade with the
+// shadow-ray gate was measured slower on B200: 98 registers, two shadow rays per thread in sequence.)
+struct GenGate {      // primary rays: position == sample, mult == 1
+  GenSimple gen; Gate gate; int nMO;
+  template <class E> NRT_HD void operator()(int64_t s, E& emit) const {
+    GenOut out; gen.run(s, out);
+    for (int mo = 0; mo < nMO; ++mo)
+      emit(0, mo, out.alive ? gateCode(gate.evalRay(out.o, out.d, uint32_t(s), mo, 0)) : uint8_t(0));
   }
 };
 

@@ -328,6 +328,9 @@ struct Renderer {
   int32_t* dRows = nullptr;
   ProfileAcc prof;
   int64_t launches_hint = 0;
+  // one entry per prefilter launch of the last frame, in launch order (NRT_TRACE_PREFILTER)
+  struct PreLaunch { int wave, mo, b, mode; int64_t rays, work, pre, nch; };
+  std::vector<PreLaunch> preLog;
 
   void freeAll() {
     for (void* p : owned) be->dfree(p);
@@ -375,14 +378,21 @@ struct Renderer {
     cs.S = capS; cs.NR = capNR; cs.QCAP = capNR + int64_t(nL) * capS; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.preCap = 4 * capCand; cs.rows = dRows;
   }
 
-  // One mesh wave: gate + per mesh object { filter per ray bundle, exact, verify }.
-  void meshWave(const SceneData<BE>& sd, const FrameParams& fp, int kind, const ActiveSet& act, int wave, bool primary, int force_exact) {
+  Gate makeGate(const SceneData<BE>& sd, const FrameParams& fp, int kind, const ActiveSet& act, bool primary, int force_exact) const {
+    return Gate{sd.d, fp, cs, kind, act, force_exact, primary ? FM_ORIGIN : FM_GENERAL};
+  }
+  uint32_t* waveCounters(int wave) const { return cs.counters + int64_t(wave) * cs.nMO * cntStride(cs.nL); }
+
+  // One mesh wave: gate + per mesh object { filter per ray bundle, exact, verify }.  `gated`: the
+  // kernel that produced the wave's rays already evaluated and counted the gate codes (produceGate).
+  void meshWave(const SceneData<BE>& sd, const FrameParams& fp, int kind, const ActiveSet& act, int wave, bool primary, int force_exact, bool gated) {
     const int nMO = cs.nMO, nL = cs.nL, cst = cntStride(nL);
     if (nMO == 0 || (!act.list && act.n == 0)) return;
-    uint32_t* cnt = cs.counters + int64_t(wave) * nMO * cst;
-    const int pathMode = primary ? FM_ORIGIN : FM_GENERAL;
+    uint32_t* cnt = waveCounters(wave);
     const int mult = (kind == WAVE_SHADOW) ? nL : 1;
-    be->gate(Gate{sd.d, fp, cs, kind, act, force_exact, pathMode}, nullptr, act.n * mult, mult, nMO, cnt);
+    const Gate g = makeGate(sd, fp, kind, act, primary, force_exact);
+    if (gated) be->gateFinish(g, act.n * mult, nMO, cnt);
+    else be->gate(g, nullptr, act.n * mult, mult, nMO, cnt);
     for (int mo = 0; mo < nMO; ++mo) {
       uint32_t* c = cnt + mo * cst;
       const DMesh& m = sd.meshes[sd.objs[sd.moIndex[mo]].mesh];
@@ -390,6 +400,7 @@ struct Renderer {
       if (!force_exact) {
         // prefilter (hot) -> refine (float32 sign test) per ray bundle; both feed the candidate list of (wave, mo)
         auto run = [&](int mode, int l, int b) {
+          preLog.push_back(PreLaunch{wave, mo, b, mode, 0, 0, 0, 0});
           be->filter(mode, sd.hotOf(mo, mode, l), sd.boundsOf(mo, mode, l), sd.recCountOf(mo, mode, l), cs, mo, b, c);
           be->forEachCounted(c + cntPre(b), cs.preCap,
                              Refine<typename BE::Atom>{cs, mode, sd.recsOf(mo, mode, l), mode == FM_GENERAL ? m.order : nullptr,
@@ -461,6 +472,7 @@ struct Renderer {
       ensure(S, nL, nMO, waves, cand, int(rows.size()));
       cs.fb = fb; cs.aovObj = aovObj; cs.aovTri = aovTri; cs.aovT = aovT;
       be->upload(dRows, rows.data(), sizeof(int32_t) * rows.size());
+      preLog.clear();
       bool overflow = false;
       unsigned long long total[ST_COUNT] = {0};
       ProfileAcc pacc;
@@ -472,17 +484,20 @@ struct Renderer {
         be->zero(cs.counters, sizeof(uint32_t) * ncnt);
         be->zero(cs.stats, sizeof(unsigned long long) * ST_COUNT);
         be->zero(cs.acount, sizeof(uint32_t) * (waves + 2));
-        if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
-        else be->forEach(nS, GenSimple{sd.d, fp, cs});
         int wave = 0;
         ActiveSet act{nullptr, nullptr, nS};   // bounce 0: every sample of the chunk
+        // primary rays: generated and gated in one kernel (the jittered kinds generate per pixel: separate gate)
+        const bool fuseGen = !jitter && nMO > 0;
+        if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
+        else if (fuseGen) be->produceGate(nS, 1, GenGate{GenSimple{sd.d, fp, cs}, makeGate(sd, fp, WAVE_PATH, act, true, force_exact), nMO}, cs, nMO, waveCounters(0), nullptr);
+        else be->forEach(nS, GenSimple{sd.d, fp, cs});
         for (int bounce = 0;; ++bounce) {
           uint32_t* nextList = cs.alist + int64_t((bounce + 1) & 1) * cs.S;
           uint32_t* nextCount = cs.acount + bounce + 1;
           // (act.n is exact on the host for every bounce: launches are sized to it)
-          meshWave(sd, fp, WAVE_PATH, act, wave, bounce == 0, force_exact); ++wave;
+          meshWave(sd, fp, WAVE_PATH, act, wave, bounce == 0, force_exact, bounce == 0 && fuseGen); ++wave;
           be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act}, cs.stats);
-          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, false, force_exact);
+          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, false, force_exact, false);
           ++wave;
           if (nL > 0) be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
           be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act}, cs.stats);
@@ -527,6 +542,12 @@ struct Renderer {
             pacc.candidates += c[CNT_CAND];
           }
         for (int k = 0; k < ST_COUNT; ++k) total[k] += hs[k];
+        for (auto& e : preLog)
+          if (e.nch == 0 && e.wave < wave) {   // entries of this chunk (filled once)
+            const uint32_t* c = hc.data() + (int64_t(e.wave) * nMO + e.mo) * cst;
+            e.rays = c[cntQueue(e.b)]; e.work = c[cntWork(e.b)]; e.pre = c[cntPre(e.b)];
+            e.nch = std::max<int64_t>(1, SceneData<BE>::numChunks(int64_t(sd.hostRecCount(e.mo, e.mode, e.b > 0 ? e.b - 1 : 0))));
+          }
       }
       if (!overflow) {
         for (int k = 0; k < ST_COUNT; ++k) statsOut[k] = total[k];

@@ -104,6 +104,14 @@ struct LoopBackend {
       }
     ++launches;
   }
+  // fused producer + gate flags: here the producer runs first and the ordinary gate follows
+  struct NoEmit { void operator()(int, int, uint8_t) const {} };
+  void produceGate(int64_t n, int, const GenGate& p, const ChunkState&, int, uint32_t*, unsigned long long*) {
+    NoEmit e;
+    for (int64_t i = 0; i < n; ++i) p(i, e);
+    ++launches;
+  }
+  void gateFinish(const Gate& g, int64_t n, int nMO, uint32_t* cnt) { gate(g, nullptr, n, 1, nMO, cnt); --launches; }
   // Prefilter, two-level like the CUDA kernel: the queue is cut into runs of prefilterRunRays(mode)
   // consecutive rays (one warp's registers); a run evaluates the 256 hot records of a chunk in full
   // iff at least one of its rays passes the chunk's bound test.

@@ -5,6 +5,10 @@ import bench
 from nim_raytracer_b200 import api
 L = api.lib()
 api.initRenderer(devices=[0])
+import os
+if os.environ.get('NRT_PART'):
+    i, c = map(int, os.environ['NRT_PART'].split(','))
+    api.setPartition(i, c)
 for wl in sys.argv[1:] or ["config2"]:
     sc, o, desc = bench.workload(wl)
     co = o.to_c()
