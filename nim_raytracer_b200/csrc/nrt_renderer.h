@@ -352,7 +352,7 @@ struct Renderer {
       capS = S; capNR = NR; capMO = nMO; capNL = nL; capWaves = waves; capCand = cand; capRows = nrows;
       cs.rayO = al<double>(4 * S); cs.rayD = al<double>(4 * S); cs.hitW = al<double>(4 * S); cs.nrm = al<double>(4 * S);
       cs.accum = al<double>(3 * S); cs.weight = al<double>(S);
-      cs.hitObj = al<int32_t>(S); cs.bounce = al<int32_t>(S); cs.active = al<uint8_t>(S);
+      cs.hitObj = al<int32_t>(S); cs.active = al<uint8_t>(S);
       const int64_t m = int64_t(std::max(nMO, 1)) * NR;
       const int64_t qcap = NR + int64_t(nL) * S, mq = int64_t(std::max(nMO, 1)) * qcap;
       cs.tBest = al<uint64_t>(m); cs.triBest = al<uint32_t>(m);
@@ -378,19 +378,20 @@ struct Renderer {
     cs.S = capS; cs.NR = capNR; cs.QCAP = capNR + int64_t(nL) * capS; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.preCap = 4 * capCand; cs.rows = dRows;
   }
 
-  Gate makeGate(const SceneData<BE>& sd, const FrameParams& fp, int kind, const ActiveSet& act, bool primary, int force_exact) const {
-    return Gate{sd.d, fp, cs, kind, act, force_exact, primary ? FM_ORIGIN : FM_GENERAL};
+  Gate makeGate(const SceneData<BE>& sd, const FrameParams& fp, int kind, const ActiveSet& act, int bounce, int force_exact) const {
+    return Gate{sd.d, fp, cs, kind, act, force_exact, (bounce == 0 && kind == WAVE_PATH) ? FM_ORIGIN : FM_GENERAL, bounce};
   }
   uint32_t* waveCounters(int wave) const { return cs.counters + int64_t(wave) * cs.nMO * cntStride(cs.nL); }
 
   // One mesh wave: gate + per mesh object { filter per ray bundle, exact, verify }.  `gated`: the
   // kernel that produced the wave's rays already evaluated and counted the gate codes (produceGate).
-  void meshWave(const SceneData<BE>& sd, const FrameParams& fp, int kind, const ActiveSet& act, int wave, bool primary, int force_exact, bool gated) {
+  void meshWave(const SceneData<BE>& sd, const FrameParams& fp, int kind, const ActiveSet& act, int wave, int bounce, int force_exact, bool gated) {
+    const bool primary = bounce == 0 && kind == WAVE_PATH;
     const int nMO = cs.nMO, nL = cs.nL, cst = cntStride(nL);
     if (nMO == 0 || (!act.list && act.n == 0)) return;
     uint32_t* cnt = waveCounters(wave);
     const int mult = (kind == WAVE_SHADOW) ? nL : 1;
-    const Gate g = makeGate(sd, fp, kind, act, primary, force_exact);
+    const Gate g = makeGate(sd, fp, kind, act, bounce, force_exact);
     if (gated) be->gateFinish(g, act.n * mult, nMO, cnt);
     else be->gate(g, nullptr, act.n * mult, mult, nMO, cnt);
     for (int mo = 0; mo < nMO; ++mo) {
@@ -415,8 +416,8 @@ struct Renderer {
             if (sd.lights[l].kind == NRT_LIGHT_DISTANT && sd.frameValid(mo, FM_DIR, l)) run(FM_DIR, l, 1 + l);
         }
       }
-      be->forEachCounted(c + CNT_EXACT, cs.NR, ExactMesh{sd.d, fp, cs, kind, mo, c + CNT_EXACT});
-      be->forEachCounted(c + CNT_CAND, cs.candCap, Verify1<typename BE::Atom>{sd.d, fp, cs, kind, mo});
+      be->forEachCounted(c + CNT_EXACT, cs.NR, ExactMesh{sd.d, fp, cs, kind, mo, c + CNT_EXACT, bounce});
+      be->forEachCounted(c + CNT_CAND, cs.candCap, Verify1<typename BE::Atom>{sd.d, fp, cs, kind, mo, bounce});
       be->forEachCounted(c + CNT_CAND, cs.candCap, Verify2<typename BE::Atom>{cs, mo});
     }
   }
@@ -489,18 +490,18 @@ struct Renderer {
         // primary rays: generated and gated in one kernel (the jittered kinds generate per pixel: separate gate)
         const bool fuseGen = !jitter && nMO > 0;
         if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
-        else if (fuseGen) be->produceGate(nS, 1, GenGate{GenSimple{sd.d, fp, cs}, makeGate(sd, fp, WAVE_PATH, act, true, force_exact), nMO}, cs, nMO, waveCounters(0), nullptr);
+        else if (fuseGen) be->produceGate(nS, 1, GenGate{GenSimple{sd.d, fp, cs}, makeGate(sd, fp, WAVE_PATH, act, 0, force_exact), nMO}, cs, nMO, waveCounters(0), nullptr);
         else be->forEach(nS, GenSimple{sd.d, fp, cs});
         for (int bounce = 0;; ++bounce) {
           uint32_t* nextList = cs.alist + int64_t((bounce + 1) & 1) * cs.S;
           uint32_t* nextCount = cs.acount + bounce + 1;
           // (act.n is exact on the host for every bounce: launches are sized to it)
-          meshWave(sd, fp, WAVE_PATH, act, wave, bounce == 0, force_exact, bounce == 0 && fuseGen); ++wave;
-          be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act}, cs.stats);
-          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, false, force_exact, false);
+          meshWave(sd, fp, WAVE_PATH, act, wave, bounce, force_exact, bounce == 0 && fuseGen); ++wave;
+          be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act, bounce}, cs.stats);
+          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, bounce, force_exact, false);
           ++wave;
           if (nL > 0) be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
-          be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act}, cs.stats);
+          be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act, bounce}, cs.stats);
           if (bounce >= maxBounces) break;
           be->compactActive(cs, act, nextList, nextCount);
           uint32_t cont = 0;
