@@ -191,6 +191,27 @@ def cpu_baseline(scene_desc, opts, rays_per_frame, budget_s=12.0):
             "frames_per_s_extrapolated": v * 1e6 / max(rays_per_frame, 1)}
 
 
+# Modelled algorithmic bytes per primary sample of the streaming kernels over the per-sample state
+# (float64 SoA; two lights, one mesh object, bounce 0 only - later bounces add
+# ~15 % more launches of the same kernels, so the achieved figures are slightly understated).
+STATE_BYTES_PER_SAMPLE = {
+    "gen+gate": 34,        # W rayD 32 + active 1 + gate code 1
+    "Shade": 102,          # R rayD 32 + active 1 + code 1;  W hitObj 4 + hitW 32 + nrm 32 (hit) | accum 24 (miss)
+    "k_gate_flags": 70,    # R hitObj 4 + hitW 32 + nrm 32;  W 2 codes (one per light)
+    "ShadowTrace": 72,     # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W 2 occlusion flags
+    "Resolve": 94,         # R hitObj 4 + hitW 32 + nrm 32 + 2 flags;  W accum 24
+    "Finalize": 25,        # R accum 24;  W 12 bytes per pixel (16 samples)
+}
+
+
+def _hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:  # noqa: BLE001
+        return 6459.0   # the pool's measured copy bandwidth (B200_PROFILING.md fallback)
+
+
 def _traffic(workload_name):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel launch, from the committed
     `ncu --set full` capture of this workload (profiles/prefilter_traffic.json); None if not captured."""
@@ -365,6 +386,14 @@ def main():
            "ms_per_step": e_ms / args.steps, "frames_per_s": args.steps / (e_ms * 1e-3)}
     checksum = float(np.asarray(host_fb, dtype=np.float64).sum()) if rank == 0 else 0.0
 
+    # ---- per-kernel-family shares: one untimed frame with every launch bracketed by CUDA events ----
+    api.setKernelTiming(True)
+    step_resident()
+    barrier()
+    ktimes = ds.kernelTimes()
+    kframe_ms = ds.profile().total_ms
+    api.setKernelTiming(False)
+
     if rank == 0:
         peak = C.c_double(); clk = C.c_double()
         api.check(L.nrt_measure_fp32_peak(C.byref(peak), C.byref(clk)), "nrt_measure_fp32_peak")
@@ -385,6 +414,20 @@ def main():
             "note": "achieved = executed float32 flops of the prefilter launches (FFMA = 2) / their CUDA-event time; "
                     "ref_tests = rays x all faces, what geom.nim:346 would evaluate (reported, never used for the fraction)",
         }
+        ksum = sum(ms for ms, _ in ktimes.values()) or 1.0
+        samples = float(cs.num_primary_rays)   # primary samples this rank rendered in the last frame
+        hbm_peak = _hbm_peak()
+        kernels = []
+        for name, (ms, nl) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
+            k = {"kernel": name, "ms": ms, "share": ms / ksum, "launches": nl}
+            bps = next((v for key, v in STATE_BYTES_PER_SAMPLE.items() if name.startswith(key)), None)
+            if bps is not None:   # streaming kernels over the per-sample state: modelled algorithmic bytes
+                gbs = bps * samples / max(ms * 1e-3, 1e-12) / 1e9
+                k.update({"bound": "hbm", "algorithmic_bytes": bps * samples, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
+            kernels.append(k)
+        pre_ms = ktimes.get("k_mesh_prefilter", (0.0, 0))[0]
+        roofline["kernel_share_of_step"] = pre_ms / ksum
+        roofline["share_source"] = "CUDA events around every launch of one untimed frame (nrt_set_kernel_timing); 'kernels' lists every family"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -395,7 +438,7 @@ def main():
             "frames_per_s": args.steps / (t_ms * 1e-3), "rays_per_frame": total_rays / args.steps,
             "device_ms_per_step": ms_dev.value / args.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(klaunches),
-            "roofline": roofline, "fb_checksum": checksum,
+            "roofline": roofline, "kernels": kernels, "kernel_timing_frame_ms": kframe_ms, "fb_checksum": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(ds.desc, opts, total_rays / args.steps)

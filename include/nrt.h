@@ -178,6 +178,13 @@ typedef struct nrt_profile {
   double mesh_ms_by_mode[4];
 } nrt_profile;
 
+/* Device time per kernel family of one frame (measurement hook, see nrt_set_kernel_timing). */
+#define NRT_KERNEL_CATEGORIES 16
+typedef struct nrt_kernel_times {
+  double ms[NRT_KERNEL_CATEGORIES];        /* summed CUDA-event time of the category's launches */
+  int64_t launches[NRT_KERNEL_CATEGORIES];
+} nrt_kernel_times;
+
 typedef struct nrt_scene nrt_scene;
 
 /* 64-byte opaque handle for sharing a device allocation across processes
@@ -240,6 +247,14 @@ int nrt_framebuf_to_srgb8(const float* fb_host, int width, int height,
                           int srgb, unsigned char* rgb8);
 
 int nrt_get_profile(const nrt_scene* scene, nrt_profile* out);
+
+/* Per-kernel-family timing (no reference counterpart; the reference only prints a wall-clock total,
+ * src/utils/progress.nim:27-28).  While enabled every kernel launch of nrt_render* is bracketed by
+ * two CUDA events; nrt_get_kernel_times returns the sums of the last frame rendered on `scene`
+ * (first device of the group).  nrt_kernel_category_name(i) names slot i ("" past the last one). */
+int nrt_set_kernel_timing(int enable);
+int nrt_get_kernel_times(const nrt_scene* scene, nrt_kernel_times* out);
+const char* nrt_kernel_category_name(int category);
 
 /* Device buffers + cross-process sharing for the one-process-per-GPU launch. */
 int nrt_device_alloc(int64_t bytes, void** dev_ptr);         /* on group device 0 */

@@ -106,6 +106,13 @@ class nrt_aov(C.Structure):
     ]
 
 
+NRT_KERNEL_CATEGORIES = 16
+
+
+class nrt_kernel_times(C.Structure):
+    _fields_ = [("ms", C.c_double * NRT_KERNEL_CATEGORIES), ("launches", C.c_int64 * NRT_KERNEL_CATEGORIES)]
+
+
 class nrt_profile(C.Structure):
     _fields_ = [
         ("total_ms", C.c_double), ("mesh_filter_ms", C.c_double),
@@ -153,6 +160,10 @@ def lib() -> C.CDLL:
     L.nrt_render_device.argtypes = L.nrt_render.argtypes
     L.nrt_framebuf_to_srgb8.argtypes = [vp, i32, i32, i32, vp]
     L.nrt_get_profile.argtypes = [vp, C.POINTER(nrt_profile)]
+    L.nrt_set_kernel_timing.argtypes = [i32]
+    L.nrt_get_kernel_times.argtypes = [vp, C.POINTER(nrt_kernel_times)]
+    L.nrt_kernel_category_name.argtypes = [i32]
+    L.nrt_kernel_category_name.restype = C.c_char_p
     L.nrt_device_alloc.argtypes = [i64, C.POINTER(vp)]
     L.nrt_device_free.argtypes = [vp]
     L.nrt_device_memset.argtypes = [vp, i32, i64]
@@ -424,6 +435,10 @@ def shutdown() -> None:
     _initialised = False
 
 
+def setKernelTiming(enable: bool) -> None:
+    check(lib().nrt_set_kernel_timing(1 if enable else 0), "nrt_set_kernel_timing")
+
+
 def setPartition(index: int, count: int) -> None:
     check(lib().nrt_set_partition(index, count), "nrt_set_partition")
 
@@ -447,6 +462,17 @@ class DeviceScene:
         p = nrt_profile()
         check(lib().nrt_get_profile(self.handle, C.byref(p)), "nrt_get_profile")
         return p
+
+    def kernelTimes(self) -> dict:
+        """{kernel family: (ms, launches)} of the last frame rendered with setKernelTiming(True)."""
+        t = nrt_kernel_times()
+        check(lib().nrt_get_kernel_times(self.handle, C.byref(t)), "nrt_get_kernel_times")
+        out = {}
+        for i in range(NRT_KERNEL_CATEGORIES):
+            name = lib().nrt_kernel_category_name(i).decode()
+            if name and t.launches[i]:
+                out[name] = (t.ms[i], int(t.launches[i]))
+        return out
 
     def close(self) -> None:
         if self.handle:

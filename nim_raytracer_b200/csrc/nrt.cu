@@ -577,6 +577,29 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float 
   if (s == 12345.678f) out[0] = s;
 }
 
+// ------------------------------------------------------- kernel categories ----
+// Per-category device time of a frame (nrt_set_kernel_timing): every launch is bracketed by two
+// CUDA events on the render stream.  Off by default (the events cost a little); bench.py turns it on
+// for an untimed frame to report each kernel family's share of the step.
+enum KernelCat { KC_GEN = 0, KC_GATE_FLAGS, KC_GATE_SCAN, KC_GATE_WRITE, KC_PREFILTER, KC_REFINE, KC_EXACT, KC_VERIFY,
+                 KC_SHADE, KC_SHADOW_TRACE, KC_RESOLVE, KC_COMPACT, KC_FINALIZE, KC_OTHER, KC_COUNT };
+static const char* const kKernelCatNames[KC_COUNT] = {
+  "gen+gate (GenGate / GenSimple / GenJittered)", "k_gate_flags", "k_gate_scan", "k_gate_write", "k_mesh_prefilter", "Refine",
+  "ExactMesh", "Verify1+Verify2", "Shade", "ShadowTrace", "Resolve", "compactActive (cub select)", "Finalize", "other"};
+static_assert(KC_COUNT <= NRT_KERNEL_CATEGORIES, "nrt_kernel_times is too small");
+template <class F> struct CatOf { static constexpr int v = KC_OTHER; };
+template <> struct CatOf<GenSimple> { static constexpr int v = KC_GEN; };
+template <> struct CatOf<GenJittered> { static constexpr int v = KC_GEN; };
+template <> struct CatOf<GenGate> { static constexpr int v = KC_GEN; };
+template <> struct CatOf<Shade> { static constexpr int v = KC_SHADE; };
+template <> struct CatOf<ShadowTrace> { static constexpr int v = KC_SHADOW_TRACE; };
+template <> struct CatOf<Resolve> { static constexpr int v = KC_RESOLVE; };
+template <> struct CatOf<Finalize> { static constexpr int v = KC_FINALIZE; };
+template <> struct CatOf<ExactMesh> { static constexpr int v = KC_EXACT; };
+template <class A> struct CatOf<Refine<A>> { static constexpr int v = KC_REFINE; };
+template <class A> struct CatOf<Verify1<A>> { static constexpr int v = KC_VERIFY; };
+template <class A> struct CatOf<Verify2<A>> { static constexpr int v = KC_VERIFY; };
+
 // ----------------------------------------------------------------- backend ----
 struct CudaBackend {
   int device = 0;
@@ -601,6 +624,35 @@ struct CudaBackend {
     static __device__ __forceinline__ void min32(uint32_t* p, uint32_t v) { atomicMin(p, v); }
     static __device__ __forceinline__ uint32_t add32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
   };
+
+  // ---- optional per-category timing ----
+  bool timing = false;
+  std::vector<cudaEvent_t> tEvents;     // pairs (start, stop)
+  std::vector<int> tCats;
+  size_t tUsed = 0;
+  struct Timed {
+    CudaBackend* be; size_t slot;
+    Timed(CudaBackend* b, int cat) : be(b), slot(size_t(-1)) {
+      if (!be->timing) return;
+      if (be->tUsed == be->tCats.size()) {
+        cudaEvent_t a, c;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&c) != cudaSuccess) return;
+        be->tEvents.push_back(a); be->tEvents.push_back(c); be->tCats.push_back(0);
+      }
+      slot = be->tUsed++;
+      be->tCats[slot] = cat;
+      cudaEventRecord(be->tEvents[2 * slot], be->stream);
+    }
+    ~Timed() { if (slot != size_t(-1)) cudaEventRecord(be->tEvents[2 * slot + 1], be->stream); }
+  };
+  // call after a stream sync; adds this frame's per-category times and launch counts
+  void collectTimes(double* ms, int64_t* n) {
+    for (size_t i = 0; i < tUsed; ++i) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, tEvents[2 * i], tEvents[2 * i + 1]) == cudaSuccess) { ms[tCats[i]] += t; n[tCats[i]] += 1; }
+    }
+    tUsed = 0;
+  }
 
   void use() { NRT_CUDA(cudaSetDevice(device)); }
   void* dalloc(size_t bytes) { use(); void* p = nullptr; NRT_CUDA(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
@@ -629,21 +681,24 @@ struct CudaBackend {
   template <class F> void forEach(int64_t n, const F& f) {
     if (n <= 0) return;
     use();
+    Timed tm(this, CatOf<F>::v);
     k_for_each<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   // over [0, n) (count == nullptr) or [0, *count) with the count resident on the device
   template <class F> void forEachStats(const uint32_t* count, int64_t n, const F& f, unsigned long long* stats) {
     use();
+    if (!count && n <= 0) return;
+    Timed tm(this, CatOf<F>::v);
     if (count) k_for_each_stats_counted<F><<<unsigned(sms * 8), kBlock, 0, stream>>>(f, count, stats);
     else {
-      if (n <= 0) return;
       k_for_each_stats<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, stats);
     }
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   template <class F> void forEachCounted(const uint32_t* count, int64_t cap, const F& f) {
     use();
+    Timed tm(this, CatOf<F>::v);
     k_for_each_counted<F><<<unsigned(sms * 8), kBlock, 0, stream>>>(f, count, cap);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
@@ -667,9 +722,9 @@ struct CudaBackend {
     const int rows = nMO * (2 + cs.nL);
     const unsigned grid = count ? unsigned(sms * 8) : blocksFor(n);
     uint32_t* ne = cnt + CNT_NE;   // zeroed with the counter blocks at the start of the chunk
-    k_gate_flags<<<grid, kBlock, sizeof(uint32_t) * rows, stream>>>(g, count, n, mult, nMO, ne);
-    k_gate_scan<<<unsigned(rows), 1024, 0, stream>>>(cs, count, n, mult, cnt);
-    k_gate_write<<<unsigned(sms * 8), kBlock, 0, stream>>>(g, count, n, mult, nMO, ne);
+    { Timed tm(this, KC_GATE_FLAGS); k_gate_flags<<<grid, kBlock, sizeof(uint32_t) * rows, stream>>>(g, count, n, mult, nMO, ne); }
+    { Timed tm(this, KC_GATE_SCAN); k_gate_scan<<<unsigned(rows), 1024, 0, stream>>>(cs, count, n, mult, cnt); }
+    { Timed tm(this, KC_GATE_WRITE); k_gate_write<<<unsigned(sms * 8), kBlock, 0, stream>>>(g, count, n, mult, nMO, ne); }
     NRT_CUDA(cudaGetLastError()); launches += 3;
   }
   // fused producer + gate flags (GenGate: mult 1; ShadeGate: mult nL, with Stats); gateFinish() completes the gate
@@ -678,6 +733,7 @@ struct CudaBackend {
     if (n <= 0) return;
     const size_t sm = sizeof(uint32_t) * size_t(mult) * nMO * (2 + cs.nL);
     (void)stats;
+    Timed tm(this, CatOf<P>::v);
     k_produce_gate<P><<<blocksFor(n), kBlock, sm, stream>>>(p, cs, n, mult, nMO, cnt + CNT_NE);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
@@ -685,8 +741,8 @@ struct CudaBackend {
     use();
     if (n <= 0) return;
     const int rows = nMO * (2 + g.cs.nL);
-    k_gate_scan<<<unsigned(rows), 1024, 0, stream>>>(g.cs, nullptr, n, 1, cnt);
-    k_gate_write<<<unsigned(sms * 8), kBlock, 0, stream>>>(g, nullptr, n, 1, nMO, cnt + CNT_NE);
+    { Timed tm(this, KC_GATE_SCAN); k_gate_scan<<<unsigned(rows), 1024, 0, stream>>>(g.cs, nullptr, n, 1, cnt); }
+    { Timed tm(this, KC_GATE_WRITE); k_gate_write<<<unsigned(sms * 8), kBlock, 0, stream>>>(g, nullptr, n, 1, nMO, cnt + CNT_NE); }
     NRT_CUDA(cudaGetLastError()); launches += 2;
   }
   // Morton order of the face centroids -> m.order (stable: ties keep face order)
@@ -723,6 +779,7 @@ struct CudaBackend {
   // next bounce's active list: the samples of the current set with active == 1, in sample order
   void compactActive(const ChunkState& cs, const ActiveSet& act, uint32_t* list, uint32_t* count) {
     use();
+    Timed tm(this, KC_COMPACT);
     size_t tb = 0;
     if (!act.list) {
       thrust::counting_iterator<uint32_t> ids(0u);
@@ -762,6 +819,7 @@ struct CudaBackend {
     }
     auto& ev = filterEvents[filterUsed];
     filterModes[filterUsed++] = mode;
+    Timed tm(this, KC_PREFILTER);
     NRT_CUDA(cudaEventRecord(ev.first, stream));
     // per-warp double-buffered chunk slices: 2-D bundles 8 rays/lane (48 KiB/CTA, 3 CTAs/SM); GENERAL 4 rays/lane (64 KiB/CTA, 2 CTAs/SM)
     constexpr size_t smBuf = size_t(FT_WARPS) * FT_WB * sizeof(uint2) + FT_WARPS * sizeof(uint32_t);
@@ -795,6 +853,8 @@ struct CudaBackend {
     cudaSetDevice(device);
     for (auto& e : filterEvents) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     filterEvents.clear();
+    for (auto& e : tEvents) cudaEventDestroy(e);
+    tEvents.clear(); tCats.clear(); tUsed = 0;
     for (int k = 0; k < 2; ++k) { if (scratchPtr[k]) cudaFree(scratchPtr[k]); scratchPtr[k] = nullptr; scratchBytes[k] = 0; }
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
@@ -824,6 +884,7 @@ struct PerDevice {
 struct nrt_scene {
   std::vector<nrt::PerDevice> dev;
   nrt_profile prof{};
+  nrt_kernel_times ktimes{};   // last frame rendered with kernel timing on (device 0 of the group)
 };
 
 namespace nrt {
@@ -1015,6 +1076,13 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     p.candidates += a.candidates;
     p.pre_candidates += a.pre_candidates;
     p.kernel_launches += dc->be.launches;
+    if (dc->be.timing && d == 0) {
+      sc->ktimes = nrt_kernel_times{};
+      dc->be.collectTimes(sc->ktimes.ms, sc->ktimes.launches);
+    } else if (dc->be.timing) {
+      nrt_kernel_times scratchT{};
+      dc->be.collectTimes(scratchT.ms, scratchT.launches);
+    }
     for (int m = 0; m < 3; ++m) {
       p.mesh_tests_by_mode[m] += a.tests_by_mode[m];
       p.mesh_ms_by_mode[m] = std::max(p.mesh_ms_by_mode[m], byMode[m]);
@@ -1135,6 +1203,21 @@ int nrt_render(nrt_scene* scene, const nrt_options* opts, int y0, int y1, int st
 int nrt_render_device(nrt_scene* scene, const nrt_options* opts, int y0, int y1, int step, int max_step, float* fb_dev,
                       nrt_stats* stats, const nrt_aov* aov_dev) {
   return renderImpl(scene, opts, y0, y1, step, max_step, fb_dev, stats, aov_dev, true);
+}
+
+int nrt_set_kernel_timing(int enable) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called");
+  for (auto* d : g_devs) { d->be.timing = enable != 0; d->be.tUsed = 0; }
+  return NRT_OK;
+}
+int nrt_get_kernel_times(const nrt_scene* scene, nrt_kernel_times* out) {
+  if (!scene || !out) return fail(NRT_ERR_INVALID, "null argument");
+  *out = scene->ktimes;
+  return NRT_OK;
+}
+const char* nrt_kernel_category_name(int category) {
+  return (category >= 0 && category < KC_COUNT) ? kKernelCatNames[category] : "";
 }
 
 int nrt_get_profile(const nrt_scene* scene, nrt_profile* out) {
