@@ -47,27 +47,23 @@ __global__ void __launch_bounds__(kBlock) k_for_each(F f, int64_t n) {
   if (i < n) f(i);
 }
 
-// Block-wide sum of the per-thread Stats deltas into the global counters: two redux.sync per
-// counter (26-bit halves, so the warp sums cannot overflow), shared-memory atomics across the
-// warps, one global atomic per counter and block.
+// Block-wide sum of the per-thread Stats deltas into the global counters: one redux.sync per counter
+// and warp (per-thread values are below 2^27: one trace() call tests each object once), the warp sums
+// go to shared memory with plain stores, and one thread per counter adds them up in 64 bits for a
+// single global atomic per counter and block.
 __device__ __forceinline__ void blockStatsAdd(const StatDelta& d, unsigned long long* stats) {
-  // 24-bit halves: a warp sum stays below 2^29 and a block sum below 2^32, so native 32-bit
-  // shared-memory atomics serve (64-bit ones are compare-and-swap loops); per-thread values < 2^48
-  __shared__ unsigned sh[2 * ST_COUNT];
-  if (threadIdx.x < 2 * ST_COUNT) sh[threadIdx.x] = 0;
-  __syncthreads();
+  __shared__ unsigned sh[kBlock / 32][ST_COUNT];
+  const unsigned warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k <= ST_CONT; ++k) {
-    const unsigned lo = __reduce_add_sync(0xffffffffu, unsigned(d.v[k] & 0xFFFFFFull));
-    const unsigned hi = __reduce_add_sync(0xffffffffu, unsigned(d.v[k] >> 24));
-    if ((threadIdx.x & 31) == 0) {
-      if (lo) atomicAdd(&sh[2 * k], lo);
-      if (hi) atomicAdd(&sh[2 * k + 1], hi);
-    }
+    const unsigned v = __reduce_add_sync(0xffffffffu, unsigned(d.v[k]));
+    if ((threadIdx.x & 31) == 0) sh[warp][k] = v;
   }
   __syncthreads();
   if (threadIdx.x <= ST_CONT) {
-    const unsigned long long v = (unsigned long long)sh[2 * threadIdx.x] + ((unsigned long long)sh[2 * threadIdx.x + 1] << 24);
+    unsigned long long v = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) v += sh[w][threadIdx.x];
     if (v) atomicAdd(&stats[threadIdx.x], v);
   }
 }
@@ -77,20 +73,6 @@ __global__ void __launch_bounds__(kBlock) k_for_each_stats(F f, int64_t n, unsig
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
   StatDelta d = zeroStats();
   if (i < n) d = f(i);
-  blockStatsAdd(d, stats);
-}
-
-// Same over [0, *count) with a device-resident count (persistent grid, no host sync).
-template <class F>
-__global__ void __launch_bounds__(kBlock) k_for_each_stats_counted(F f, const uint32_t* count, unsigned long long* stats) {
-  const int64_t n = *count;
-  if (int64_t(blockIdx.x) * kBlock >= n) return;   // nothing for this block (block-uniform)
-  StatDelta d = zeroStats();
-  for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
-    const StatDelta e = f(i);
-#pragma unroll
-    for (int k = 0; k <= ST_CONT; ++k) d.v[k] += e.v[k];
-  }
   blockStatsAdd(d, stats);
 }
 
@@ -685,15 +667,12 @@ struct CudaBackend {
     k_for_each<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
-  // over [0, n) (count == nullptr) or [0, *count) with the count resident on the device
-  template <class F> void forEachStats(const uint32_t* count, int64_t n, const F& f, unsigned long long* stats) {
+  // over [0, n) (every count on this path is known on the host: the first argument is kept for the backend interface)
+  template <class F> void forEachStats(const uint32_t*, int64_t n, const F& f, unsigned long long* stats) {
     use();
-    if (!count && n <= 0) return;
+    if (n <= 0) return;
     Timed tm(this, CatOf<F>::v);
-    if (count) k_for_each_stats_counted<F><<<unsigned(sms * 8), kBlock, 0, stream>>>(f, count, stats);
-    else {
-      k_for_each_stats<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, stats);
-    }
+    k_for_each_stats<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, stats);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   template <class F> void forEachCounted(const uint32_t* count, int64_t cap, const F& f) {

@@ -101,11 +101,17 @@ NRT_HD CObj loadCObj(const CObj* p) {
 }
 
 // float32 mirror for the object scan's first look at an object (16 bytes, one vector load, the
-// same address for every lane of a warp): see certainMissF().
+// same address for every lane of a warp): see certainMissF() / planeMissF().
+//   sphere the float32 test applies to:  (tx, ty, tz) = translation column of worldToObject rounded to
+//                                        float32, r2m = radius^2 + object part of the margin (rounded up)
+//   anything else: r2m = +Inf and tx carries a tag (bit pattern of an int):
+//     COF_PLANE  plane with an exact [I | t] worldToObject: ty = t.y, tz = object part of the margin
+//     COF_MESH   triangle mesh: ty = bit pattern of its mesh-object index (its gate code decides)
+//     COF_SLOW   no float32 shortcut (boxes, general matrices, non-finite values)
+enum { COF_SLOW = 0, COF_PLANE = 1, COF_MESH = 2 };
 struct alignas(16) CObjF {
-  float tx, ty, tz;   // translation column of worldToObject, rounded to float32
-  float r2m;          // radius^2 + the object part of the error margin, rounded up; +Inf for every
-                      // object the float32 test does not apply to (not a sphere, general matrix, ...)
+  float tx, ty, tz;
+  float r2m;
 };
 NRT_HD CObjF loadCObjF(const CObjF* p) {
 #if defined(__CUDA_ARCH__)
@@ -234,7 +240,7 @@ NRT_HD bool sphereCertainMiss(double radius, V4 oc, V4 dir) {
 //   b^2 < a (|oc|^2 (1 - 5e-6) - r2m - mray)     r2m = r^2 + object part (CObjF), mray = ray part
 // (the rearrangement costs another ~3u a |oc|^2, inside the slack between 4.3e-6 and 5e-6).
 // true => the reference's delta is negative (NegInf).  NaN / Inf compare false.
-struct RayF { float ox, oy, oz, dx, dy, dz, a, mray; };
+struct RayF { float ox, oy, oz, dx, dy, dz, a, mray, mo; };
 NRT_HD RayF makeRayF(V4 o, V4 d) {
   RayF r;
   r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
@@ -242,6 +248,7 @@ NRT_HD RayF makeRayF(V4 o, V4 d) {
   r.a = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
   const float mo = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
   r.mray = 2e-7f * (mo * mo);
+  r.mo = mo;
   return r;
 }
 NRT_HD bool certainMissF(const CObjF& c, const RayF& r) {
@@ -249,6 +256,17 @@ NRT_HD bool certainMissF(const CObjF& c, const RayF& r) {
   const float b = fmaf(r.dx, ox, fmaf(r.dy, oy, r.dz * oz));
   const float o2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
   return b * b < r.a * fmaf(o2, 0.999995f, -(c.r2m + r.mray));
+}
+
+// Plane (object space y = 0, geom.nim:240-248) with worldToObject = [I | t]: when the object-space
+// origin height o.y + t.y and the direction's y have the same strict sign the reference returns either
+// NegInf (|d.y| <= 1e-6) or t = -o.y / d.y < 0, both rejected by trace() (renderer.nim:60).  Decided in
+// float32: |oy - (o.y + t.y)| <= 2.01 u (|o|_inf + |t|_inf) < 2.5e-7 (|o|_inf + |t|_inf) =: margin
+// (ray part 2.5e-7 mo, object part in c.tz, which also adds 1e-30 so that the true height is far from
+// the underflow range where -o.y / d.y could round to -0.0).  float(d.y) keeps the sign of d.y.
+NRT_HD bool planeMissF(const CObjF& c, const RayF& r) {
+  const float oy = r.oy + c.ty, m = fmaf(2.5e-7f, r.mo, c.tz);
+  return (oy > m && r.dy > 0.f) || (oy < -m && r.dy < 0.f);
 }
 
 // geom.nim:240-248
@@ -276,14 +294,19 @@ NRT_HD double mulmRow(const double* m, int r, V4 v) { return ((m[r] * v.x + m[4 
 NRT_HD void toObject(const DObject& ob, V4 o, V4 d, V4& oo, V4& dd) {
   if (ob.xlate_only && o.w == 1.0 && d.w == 0.0 && finite3(o) && finite3(d)) {
     const double* m = ob.w2o;
-    oo.x = (o.x != 0.0 || m[12] != 0.0) ? o.x + m[12] : mulmRow(m, 0, o);
-    oo.y = (o.y != 0.0 || m[13] != 0.0) ? o.y + m[13] : mulmRow(m, 1, o);
-    oo.z = (o.z != 0.0 || m[14] != 0.0) ? o.z + m[14] : mulmRow(m, 2, o);
-    oo.w = 1.0;
-    dd.x = (d.x != 0.0) ? d.x : mulmRow(m, 0, d);
-    dd.y = (d.y != 0.0) ? d.y : mulmRow(m, 1, d);
-    dd.z = (d.z != 0.0) ? d.z : mulmRow(m, 2, d);
-    dd.w = 0.0;
+    oo = v4(o.x + m[12], o.y + m[13], o.z + m[14], 1.0);
+    dd = v4(d.x, d.y, d.z, 0.0);
+    // components whose literal value is a zero of product-dependent sign (rare: one real branch)
+    const bool rare = (o.x == 0.0 && m[12] == 0.0) || (o.y == 0.0 && m[13] == 0.0) || (o.z == 0.0 && m[14] == 0.0) ||
+                      d.x == 0.0 || d.y == 0.0 || d.z == 0.0;
+    if (rare) {
+      if (o.x == 0.0 && m[12] == 0.0) oo.x = mulmRow(m, 0, o);
+      if (o.y == 0.0 && m[13] == 0.0) oo.y = mulmRow(m, 1, o);
+      if (o.z == 0.0 && m[14] == 0.0) oo.z = mulmRow(m, 2, o);
+      if (d.x == 0.0) dd.x = mulmRow(m, 0, d);
+      if (d.y == 0.0) dd.y = mulmRow(m, 1, d);
+      if (d.z == 0.0) dd.z = mulmRow(m, 2, d);
+    }
   } else {
     oo = mulm(ob.w2o, o);
     dd = mulm(ob.w2o, d);

@@ -126,6 +126,9 @@ NRT_HD void st4(double* a, int64_t n, int64_t i, V4 v) { a[i] = v.x; a[n + i] = 
 
 // 64-bit integer division is a long instruction sequence on the GPU; every index on this path fits 32 bits
 NRT_HD int64_t divFast(int64_t a, int32_t b) {
+  if (b == 1) return a;
+  if (b == 2) return a >> 1;          // a >= 0 on every call site
+  if (b == 16) return a >> 4;
   return ((uint64_t(a) >> 32) == 0) ? int64_t(uint32_t(a) / uint32_t(b)) : a / b;
 }
 NRT_HD void pixelOf(const FrameParams& fp, const ChunkState& cs, int64_t p, int& x, int& y) {
@@ -444,10 +447,20 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
   for (int base = 0; base < sc.nobjects; base += 32) {
     const int nb = (sc.nobjects - base < 32) ? sc.nobjects - base : 32;
     uint32_t need = (nb == 32) ? 0xFFFFFFFFu : ((1u << nb) - 1u);
-    if (f32ok) {
+    {
       uint32_t miss = 0;
 #pragma unroll 4
-      for (int j = 0; j < nb; ++j) miss |= uint32_t(certainMissF(loadCObjF(sc.cobjf + base + j), rf)) << j;
+      for (int j = 0; j < nb; ++j) {
+        const CObjF c = loadCObjF(sc.cobjf + base + j);   // the same record for every lane: the branches are uniform
+        bool m;
+        if (c.r2m < 3.0e38f) m = f32ok && certainMissF(c, rf);
+        else {
+          const uint32_t tag = fbits(c.tx);
+          if (tag == COF_MESH) m = cs.gflag[int64_t(fbits(c.ty)) * cs.NR + pos] == 0;   // the ray did not enter the mesh's box
+          else m = (tag == COF_PLANE) && f32ok && planeMissF(c, rf);
+        }
+        miss |= uint32_t(m) << j;
+      }
       need &= ~miss;
     }
     r.tests += nb;

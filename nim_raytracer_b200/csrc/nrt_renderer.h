@@ -216,9 +216,16 @@ struct SceneData {
       const CObj& c = cobjs[i];
       const double mt = std::max(std::fabs(c.t[0]), std::max(std::fabs(c.t[1]), std::fabs(c.t[2])));
       const double r2 = c.radius * c.radius;
-      f.tx = float(c.t[0]); f.ty = float(c.t[1]); f.tz = float(c.t[2]);
-      const bool fast = c.kind == NRT_GEOM_SPHERE && c.xlate_only && std::isfinite(c.radius) && mt < 1e15 && r2 < 1e30 && r2 > 1e-30;
-      f.r2m = fast ? roundUpF(r2 + 2e-6 * r2 + 2e-7 * mt * mt) : float(NRT_INF);
+      const bool finiteT = std::isfinite(c.t[0]) && std::isfinite(c.t[1]) && std::isfinite(c.t[2]) && mt < 1e15;
+      f.tx = bitsToFloat(uint32_t(COF_SLOW)); f.ty = 0.f; f.tz = 0.f; f.r2m = float(NRT_INF);
+      if (c.kind == NRT_GEOM_SPHERE && c.xlate_only && finiteT && std::isfinite(c.radius) && r2 < 1e30 && r2 > 1e-30) {
+        f.tx = float(c.t[0]); f.ty = float(c.t[1]); f.tz = float(c.t[2]);
+        f.r2m = roundUpF(r2 + 2e-6 * r2 + 2e-7 * mt * mt);
+      } else if (c.kind == NRT_GEOM_PLANE && c.xlate_only && finiteT) {
+        f.tx = bitsToFloat(uint32_t(COF_PLANE)); f.ty = float(c.t[1]); f.tz = roundUpF(2.5e-7 * mt + 1e-30);
+      } else if (c.kind == NRT_GEOM_MESH) {
+        f.tx = bitsToFloat(uint32_t(COF_MESH)); f.ty = bitsToFloat(uint32_t(c.mesh_obj));
+      }
     }
     dCObjF = up(cobjf.data(), int64_t(cobjf.size()), reuse ? dCObjF : nullptr);
     dCObjs = up(cobjs.data(), int64_t(cobjs.size()), reuse ? dCObjs : nullptr);
