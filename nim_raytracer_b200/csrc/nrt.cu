@@ -311,31 +311,29 @@ __global__ void __launch_bounds__(kBlock) k_pad_recs(float* recs, float* hot, co
 }
 
 // ---------------------------------------------------------- mesh prefilter ----
-// The hot kernel: the queued rays of a bundle x the hot records (bounding circle / sphere,
+// The hot path: the queued rays of a bundle x the hot records (bounding circle / sphere,
 // nrt_filter.h) of one record set, float32 — a flattened two-level traversal of the mesh.
 //
-// Level 1  Records are stored in Morton order of the face centroids, so the 256 records of a
-//          chunk are a compact patch of the surface with one bound (circle / sphere around the
-//          chunk's circles, same record format and same test).  A warp keeps a RUN of 32 x R
-//          consecutive queue entries (neighbouring pixels) in registers and tests them against
-//          the bounds of a group of <= 32 chunks: R tests per lane per bound, the per-lane pass
-//          bits are OR-reduced across the warp once per group (redux.sync).
-// Level 2  For every chunk some ray of the run can reach, the warp stages the chunk's hot records
-//          into its own shared-memory slice (cp.async, 16-byte vectors, double buffered: the next
-//          admitted chunk is in flight while the current one is evaluated) and evaluates
-//          run x chunk in full: two faces per FFMA2 (fma.rn.f32x2; records are pair-interleaved,
-//          ray components are scalar operands broadcast to both halves), records read back as
-//          warp-broadcast LDS.128.  Per (ray, face) test:
+// Level 1 (k_prefilter_bounds)  Records are stored in Morton order of the face centroids, so the
+//          256 records of a chunk are a compact patch of the surface with one bound (circle / sphere
+//          around the chunk's circles, same record format and same test).  A warp keeps a RUN of
+//          32 x R consecutive queue entries (neighbouring pixels) in registers and tests them against
+//          the bounds of 32 chunks: R tests per lane per bound, the per-lane pass bits are OR-reduced
+//          across the warp (redux.sync), and every admitted (run, chunk) pair is appended to a work list.
+// Level 2 (k_mesh_prefilter)  Persistent warps pop pairs from the list — uniform work items, so a
+//          launch ends within one item of its last warp (short lists are split into half / quarter
+//          chunks).  The warp stages the chunk's hot records into its shared-memory slice (cp.async,
+//          16-byte vectors) and evaluates run x chunk in full: two faces per FFMA2 (fma.rn.f32x2;
+//          records are pair-interleaved, ray components are scalar operands broadcast to both
+//          halves), records read back as warp-broadcast LDS.128.  Per (ray, face) test:
 //            ORIGIN / DIR  2 FFMA (2-D point in circle),   GENERAL  1 FMUL + 6 FFMA
 //          plus the shared compare: max of four left-hand sides against the ray's threshold.
-// Survivors are appended to the pre-candidate list.  Warps are autonomous (no CTA barrier): work
-// items (run, chunk group) come from an atomic counter, run-major so that concurrently running
-// warps touch the same chunks.
+//          Survivors go through a per-warp shared-memory buffer to the pre-candidate list
+//          (one global atomic per item, coalesced stores).
 static constexpr int FT_THREADS = 256;
 static constexpr int FT_WARPS = FT_THREADS / 32;
 static constexpr int FT_TC = 256;     // records per chunk
-static constexpr int FT_WB = 256;     // per-warp survivor buffer entries (flushed after every chunk)
-static constexpr uint32_t kGroupMax = 4;   // chunks per work item: admitted chunks cluster in Morton order, so large groups make a few items very long
+static constexpr int FT_WB = 256;     // per-warp survivor buffer entries (flushed after every item)
 static_assert(kRecPad == FT_TC, "one bound per shared-memory chunk");
 
 struct PreArgs {
@@ -345,9 +343,11 @@ struct PreArgs {
   const float4* h0;         // ray plane H0: (x, y, T, 0) | (dh, T)
   const float4* h1;         // ray plane H1: (2 p0, 0)   (GENERAL)
   const uint32_t* qcount;   // queued rays (device)
-  uint32_t* itemctr;        // work-item counter
+  uint32_t* itemctr;        // level 2 work-item counter
   uint32_t* prectr;         // pre-candidate counter
-  uint32_t* workctr;        // (run, chunk) pairs evaluated in full
+  uint32_t* workctr;        // (run, chunk) pairs admitted by level 1 (may exceed pairCap: the host re-renders)
+  uint2* pairs;             // the work list
+  uint32_t pairCap;
   uint32_t* preRay;
   uint32_t* preRec;
   uint32_t preCap;
@@ -370,22 +370,89 @@ __device__ __forceinline__ float2 prefilterPair(const float2* h, float a0, float
   return ffma2(h[0], dup2(a0), ffma2(h[1], dup2(a1), h[2]));
 }
 
+// the R rays of this lane in run `run` (tail entries duplicate the last real ray and are never emitted)
+template <int MODE, int R>
+struct LaneRays {
+  float a0[R], a1[R], a2[R], a3[R], b0[R], b1[R], b2[R];
+  uint32_t idx[R];
+  __device__ __forceinline__ void load(const PreArgs& a, uint32_t run, uint32_t nq, int lane) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint32_t i = run * (32u * R) + r * 32 + lane;
+      const uint32_t ic = i < nq ? i : nq - 1;
+      const float4 p0 = __ldg(a.h0 + ic);
+      a0[r] = p0.x; a1[r] = p0.y; a2[r] = p0.z; a3[r] = p0.w;
+      if (MODE == FM_GENERAL) {
+        const float4 p1 = __ldg(a.h1 + ic);
+        b0[r] = p1.x; b1[r] = p1.y; b2[r] = p1.z;
+      } else { b0[r] = b1[r] = b2[r] = 0.f; }
+      idx[r] = i < nq ? i : kInvalidRef;
+    }
+  }
+};
+
+template <int MODE, int R>
+__global__ void __launch_bounds__(FT_THREADS) k_prefilter_bounds(PreArgs a) {
+  constexpr uint32_t RUN = 32 * R;
+  static_assert(RUN == uint32_t(prefilterRunRays(MODE)), "run size is part of the executed-test accounting");
+  const uint32_t nq = *a.qcount;
+  if (nq == 0) return;
+  const uint32_t nChunks = uint32_t(paddedFaces(int64_t(*a.nrec))) / FT_TC;
+  if (nChunks == 0) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nRuns = (nq + RUN - 1) / RUN, nGroups = (nChunks + 31) / 32;
+  const uint32_t totalWarps = gridDim.x * FT_WARPS, gw = blockIdx.x * FT_WARPS + (threadIdx.x >> 5);
+  for (uint64_t item = gw; item < uint64_t(nRuns) * nGroups; item += totalWarps) {
+    const uint32_t run = uint32_t(item / nGroups), gr = uint32_t(item - uint64_t(run) * nGroups);
+    const uint32_t c0 = gr * 32, c1 = min(nChunks, c0 + 32);
+    uint32_t mask;
+    if (a.cull) {
+      LaneRays<MODE, R> ry;
+      ry.load(a, run, nq, lane);
+      uint32_t mine = 0;
+      for (uint32_t c = c0; c < c1; ++c) {
+        const float4 bd = __ldg(a.bounds + c);
+        bool p = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (MODE == FM_GENERAL) {
+            const float sdot = fmaf(bd.x, ry.a0[r], fmaf(bd.y, ry.a1[r], bd.z * ry.a2[r]));
+            const float tt = fmaf(bd.x, ry.b0[r], fmaf(bd.y, ry.b1[r], fmaf(bd.z, ry.b2[r], bd.w)));
+            p = p || (fmaf(sdot, sdot, tt) >= ry.a3[r]);
+          } else {
+            p = p || (fmaf(bd.x, ry.a0[r], fmaf(bd.y, ry.a1[r], bd.z)) >= ry.a2[r]);
+          }
+        }
+        mine |= uint32_t(p) << (c - c0);
+      }
+      mask = __reduce_or_sync(0xffffffffu, mine);
+    } else {
+      mask = (c1 - c0 >= 32) ? 0xffffffffu : ((1u << (c1 - c0)) - 1u);
+    }
+    if (mask) {
+      const uint32_t n = uint32_t(__popc(mask));
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(a.workctr, n);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (uint32_t(lane) < n && base + lane < a.pairCap) a.pairs[base + lane] = make_uint2(run, c0 + __fns(mask, 0, lane + 1));
+    }
+  }
+}
+
 template <int MODE, int R, int U>
 __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? 2 : 3) k_mesh_prefilter(PreArgs a) {
   constexpr int NH = hotFloats(MODE);      // float2 per record pair == float4 per record quad
   constexpr int CH4 = (FT_TC / 4) * NH;    // float4 per chunk
-  constexpr uint32_t RUN = 32 * R;
-  static_assert(RUN == uint32_t(prefilterRunRays(MODE)), "run size is part of the executed-test accounting");
-  extern __shared__ __align__(16) float4 smem_tiles[];   // [FT_WARPS][2][CH4]
+  extern __shared__ __align__(16) float4 smem_tiles[];   // [FT_WARPS][CH4]
   const uint32_t nq = *a.qcount;
   if (nq == 0) return;
-  const uint32_t nrecPadded = uint32_t(paddedFaces(int64_t(*a.nrec)));
-  if (nrecPadded == 0) return;
+  const uint32_t nPairs = min(*a.workctr, a.pairCap);
+  if (nPairs == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4* const tile = smem_tiles + size_t(warp) * 2 * CH4;
+  float4* const tile = smem_tiles + size_t(warp) * CH4;
   // per-warp survivor buffer behind the tiles: FT_WB (ray, record) pairs + a counter
-  uint2* const wbuf = reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * 2 * CH4) + size_t(warp) * FT_WB;
-  uint32_t* const wcnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * 2 * CH4) + size_t(FT_WARPS) * FT_WB) + warp;
+  uint2* const wbuf = reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * CH4) + size_t(warp) * FT_WB;
+  uint32_t* const wcnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * CH4) + size_t(FT_WARPS) * FT_WB) + warp;
   if (lane == 0) *wcnt = 0;
   __syncwarp();
   auto emit = [&](uint32_t ray, uint32_t rec) {
@@ -396,139 +463,81 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? 2 : 3) k_mesh
       if (gs < a.preCap) { a.preRay[gs] = ray; a.preRec[gs] = rec; }
     }
   };
-  const uint32_t nRuns = (nq + RUN - 1) / RUN;
-  const uint32_t nChunks = nrecPadded / FT_TC;
-  // chunk groups of <= 32 chunks (one pass mask); smaller groups when there are too few runs to fill the GPU
-  uint32_t G = kGroupMax;
+  // short lists: items of half / quarter chunks so that the launch still fills the GPU
   const uint32_t totalWarps = gridDim.x * FT_WARPS;
-  while (G > 1 && uint64_t(nRuns) * ((nChunks + G - 1) / G) < 4ull * totalWarps) G >>= 1;
-  const uint32_t nGroups = (nChunks + G - 1) / G;
-  const uint32_t nItems = nRuns * nGroups;
-  uint32_t work = 0;
-  // asynchronous global -> shared copy of one chunk into the warp's slice (16 bytes per lane and step)
-  auto stage = [&](uint32_t chunk, int buf) {
-    const float4* src = a.hot + size_t(chunk) * CH4;
-    float4* dst = tile + buf * CH4;
-#pragma unroll
-    for (int k = 0; k < CH4 / 32; ++k) __pipeline_memcpy_async(dst + k * 32 + lane, src + k * 32 + lane, 16);
-    __pipeline_commit();
-  };
+  uint32_t SP = 1;
+  while (SP < 4 && uint64_t(nPairs) * SP < 2ull * totalWarps) SP <<= 1;
+  const uint32_t QN = (FT_TC / 4) / SP;                // record quads per item
+  const uint64_t nItems = uint64_t(nPairs) * SP;
   for (;;) {
     uint32_t item = 0;
     if (lane == 0) item = atomicAdd(a.itemctr, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= nItems) break;
-    const uint32_t run = item / nGroups, gr = item - run * nGroups;
-    const uint32_t c0 = gr * G, c1 = min(nChunks, c0 + G);
-    float ra0[R], ra1[R], ra2[R], ra3[R], rb0[R], rb1[R], rb2[R];
-    uint32_t ridx[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const uint32_t idx = run * RUN + r * 32 + lane;
-      const uint32_t ic = idx < nq ? idx : nq - 1;  // tail: duplicate a real ray, never emit for it
-      const float4 p0 = __ldg(a.h0 + ic);
-      ra0[r] = p0.x; ra1[r] = p0.y; ra2[r] = p0.z; ra3[r] = p0.w;
-      if (MODE == FM_GENERAL) {
-        const float4 p1 = __ldg(a.h1 + ic);
-        rb0[r] = p1.x; rb1[r] = p1.y; rb2[r] = p1.z;
-      } else { rb0[r] = rb1[r] = rb2[r] = 0.f; }
-      ridx[r] = idx < nq ? idx : kInvalidRef;
+    const uint32_t pi = item / SP, part = item - pi * SP;
+    const uint2 pr = a.pairs[pi];
+    // stage this item's part of the chunk (16 bytes per lane and step), rays meanwhile
+    {
+      const float4* src = a.hot + size_t(pr.y) * CH4 + size_t(part) * QN * NH;
+      for (uint32_t k = lane; k < QN * NH; k += 32) __pipeline_memcpy_async(tile + k, src + k, 16);
+      __pipeline_commit();
     }
-    // ---- level 1: chunk bounds ----
-    uint32_t mask;
-    if (a.cull) {
-      uint32_t mine = 0;
-      for (uint32_t c = c0; c < c1; ++c) {
-        const float4 bd = __ldg(a.bounds + c);
-        bool p = false;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (MODE == FM_GENERAL) {
-            const float sdot = fmaf(bd.x, ra0[r], fmaf(bd.y, ra1[r], bd.z * ra2[r]));
-            const float tt = fmaf(bd.x, rb0[r], fmaf(bd.y, rb1[r], fmaf(bd.z, rb2[r], bd.w)));
-            p = p || (fmaf(sdot, sdot, tt) >= ra3[r]);
-          } else {
-            p = p || (fmaf(bd.x, ra0[r], fmaf(bd.y, ra1[r], bd.z)) >= ra2[r]);
-          }
-        }
-        mine |= uint32_t(p) << (c - c0);
-      }
-      mask = __reduce_or_sync(0xffffffffu, mine);
-    } else {
-      mask = (c1 - c0 >= 32) ? 0xffffffffu : ((1u << (c1 - c0)) - 1u);
-    }
-    work += uint32_t(__popc(mask));
-    // ---- level 2: run x admitted chunks ----
-    int buf = 0;
-    int cur = -1;
-    if (mask) { cur = __ffs(mask) - 1; mask &= mask - 1; stage(c0 + cur, 0); }
-    while (cur >= 0) {
-      int nxt = -1;
-      if (mask) {
-        nxt = __ffs(mask) - 1; mask &= mask - 1;
-        stage(c0 + nxt, buf ^ 1);
-        __pipeline_wait_prior(1);
-      } else {
-        __pipeline_wait_prior(0);
-      }
-      __syncwarp();                            // chunk `cur` is in the slice for every lane
-      const uint32_t base = (c0 + cur) * FT_TC;
-      const float4* tl = tile + buf * CH4;
+    LaneRays<MODE, R> ry;
+    ry.load(a, pr.x, nq, lane);
+    __pipeline_wait_prior(0);
+    __syncwarp();                            // the records are in the slice for every lane
+    const uint32_t base = pr.y * FT_TC + part * QN * 4;
 #pragma unroll U
-      for (int t = 0; t < FT_TC / 4; ++t) {
-        float2 q[2 * NH];   // two record pairs: q[j * NH + k] = coefficient k of pair j
+    for (uint32_t t = 0; t < QN; ++t) {
+      float2 q[2 * NH];   // two record pairs: q[j * NH + k] = coefficient k of pair j
 #pragma unroll
-        for (int c = 0; c < NH; ++c) {
-          const float4 v4 = tl[t * NH + c];
-          q[2 * c] = make_float2(v4.x, v4.y);
-          q[2 * c + 1] = make_float2(v4.z, v4.w);
-        }
-        uint32_t hm = 0;   // bit r: ray r passed one of the four tests
+      for (int c = 0; c < NH; ++c) {
+        const float4 v4 = tile[t * NH + c];
+        q[2 * c] = make_float2(v4.x, v4.y);
+        q[2 * c + 1] = make_float2(v4.z, v4.w);
+      }
+      uint32_t hm = 0;   // bit r: ray r passed one of the four tests
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float thr = (MODE == FM_GENERAL) ? ry.a3[r] : ry.a2[r];
+        const float2 g0 = prefilterPair<MODE>(q, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
+        const float2 g1 = prefilterPair<MODE>(q + NH, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
+        // one compare per ray: max of its four left-hand sides against its threshold (FMNMX3 + FSETP)
+        const float m = fmaxf(fmaxf(g0.x, g0.y), fmaxf(g1.x, g1.y));
+        if (m >= thr) hm |= 1u << r;
+      }
+      if (hm) {  // re-evaluate the rays that passed and emit their survivors
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const float thr = (MODE == FM_GENERAL) ? ra3[r] : ra2[r];
-          const float2 g0 = prefilterPair<MODE>(q, ra0[r], ra1[r], ra2[r], rb0[r], rb1[r], rb2[r]);
-          const float2 g1 = prefilterPair<MODE>(q + NH, ra0[r], ra1[r], ra2[r], rb0[r], rb1[r], rb2[r]);
-          // one compare per ray: max of its four left-hand sides against its threshold (FMNMX3 + FSETP)
-          const float m = fmaxf(fmaxf(g0.x, g0.y), fmaxf(g1.x, g1.y));
-          if (m >= thr) hm |= 1u << r;
-        }
-        if (hm) {  // re-evaluate the rays that passed and emit their survivors
+          if (!(hm & (1u << r)) || ry.idx[r] == kInvalidRef) continue;
+          const float thr = (MODE == FM_GENERAL) ? ry.a3[r] : ry.a2[r];
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            if (!(hm & (1u << r)) || ridx[r] == kInvalidRef) continue;
-            const float thr = (MODE == FM_GENERAL) ? ra3[r] : ra2[r];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float2 g = prefilterPair<MODE>(q + j * NH, ra0[r], ra1[r], ra2[r], rb0[r], rb1[r], rb2[r]);
-              if (g.x >= thr) emit(ridx[r], base + 4 * t + 2 * j);
-              if (g.y >= thr) emit(ridx[r], base + 4 * t + 2 * j + 1);
-            }
+          for (int j = 0; j < 2; ++j) {
+            const float2 g = prefilterPair<MODE>(q + j * NH, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
+            if (g.x >= thr) emit(ry.idx[r], base + 4 * t + 2 * j);
+            if (g.y >= thr) emit(ry.idx[r], base + 4 * t + 2 * j + 1);
           }
         }
       }
-      // flush the warp's survivors: one global atomic per (warp, chunk), coalesced stores
-      __syncwarp();
-      {
-        const uint32_t nb = min(*wcnt, uint32_t(FT_WB));
-        if (nb) {
-          uint32_t gb = 0;
-          if (lane == 0) gb = atomicAdd(a.prectr, nb);
-          gb = __shfl_sync(0xffffffffu, gb, 0);
-          for (uint32_t k = lane; k < nb; k += 32) {
-            const uint2 e = wbuf[k];
-            if (gb + k < a.preCap) { a.preRay[gb + k] = e.x; a.preRec[gb + k] = e.y; }
-          }
-          __syncwarp();
-          if (lane == 0) *wcnt = 0;
-        }
-      }
-      __syncwarp();                            // every lane left the slice before it is staged again
-      buf ^= 1;
-      cur = nxt;
     }
+    // flush the warp's survivors: one global atomic per item, coalesced stores
+    __syncwarp();
+    {
+      const uint32_t nb = min(*wcnt, uint32_t(FT_WB));
+      if (nb) {
+        uint32_t gb = 0;
+        if (lane == 0) gb = atomicAdd(a.prectr, nb);
+        gb = __shfl_sync(0xffffffffu, gb, 0);
+        for (uint32_t k = lane; k < nb; k += 32) {
+          const uint2 e = wbuf[k];
+          if (gb + k < a.preCap) { a.preRay[gb + k] = e.x; a.preRec[gb + k] = e.y; }
+        }
+        __syncwarp();
+        if (lane == 0) *wcnt = 0;
+      }
+    }
+    __syncwarp();                            // every lane left the slice before it is staged again
   }
-  if (lane == 0 && work) atomicAdd(a.workctr, work);
 }
 
 // clamp -> sRGB -> 8 bit (utils/framebuf.nim:74-78, utils/color.nim:17-22)
@@ -787,6 +796,8 @@ struct CudaBackend {
     a.itemctr = cnt + cntTile(b);
     a.prectr = cnt + cntPre(b);
     a.workctr = cnt + cntWork(b);
+    a.pairs = reinterpret_cast<uint2*>(cs.pairs);
+    a.pairCap = uint32_t(std::min<int64_t>(cs.pairCap, 0xFFFFFFFFll));
     a.preRay = cs.preRay; a.preRec = cs.preRec;
     a.preCap = uint32_t(std::min<int64_t>(cs.preCap, 0xFFFFFFFFll));
     a.cull = cull ? 1u : 0u;
@@ -800,19 +811,28 @@ struct CudaBackend {
     filterModes[filterUsed++] = mode;
     Timed tm(this, KC_PREFILTER);
     NRT_CUDA(cudaEventRecord(ev.first, stream));
-    // per-warp double-buffered chunk slices: 2-D bundles 8 rays/lane (48 KiB/CTA, 3 CTAs/SM); GENERAL 4 rays/lane (64 KiB/CTA, 2 CTAs/SM)
+    // per-warp chunk slice + survivor buffer: 2-D bundles 8 rays/lane (40 KiB/CTA, 3 CTAs/SM); GENERAL 4 rays/lane (48 KiB/CTA, 2 CTAs/SM)
     constexpr size_t smBuf = size_t(FT_WARPS) * FT_WB * sizeof(uint2) + FT_WARPS * sizeof(uint32_t);
-    constexpr size_t sm2d = size_t(FT_WARPS) * 2 * (FT_TC / 4) * 3 * sizeof(float4) + smBuf;
-    constexpr size_t smGen = size_t(FT_WARPS) * 2 * (FT_TC / 4) * 4 * sizeof(float4) + smBuf;
+    constexpr size_t sm2d = size_t(FT_WARPS) * (FT_TC / 4) * 3 * sizeof(float4) + smBuf;
+    constexpr size_t smGen = size_t(FT_WARPS) * (FT_TC / 4) * 4 * sizeof(float4) + smBuf;
     if (!smemOptIn) {
       NRT_CUDA(cudaFuncSetAttribute(k_mesh_prefilter<FM_GENERAL, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smGen)));
       NRT_CUDA(cudaFuncSetAttribute(k_mesh_prefilter<FM_ORIGIN, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2d)));
       NRT_CUDA(cudaFuncSetAttribute(k_mesh_prefilter<FM_DIR, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2d)));
       smemOptIn = true;
     }
-    if (mode == FM_GENERAL) k_mesh_prefilter<FM_GENERAL, 4, 2><<<unsigned(sms * gridGeneral), FT_THREADS, smGen, stream>>>(a);
-    else if (mode == FM_ORIGIN) k_mesh_prefilter<FM_ORIGIN, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, sm2d, stream>>>(a);
-    else k_mesh_prefilter<FM_DIR, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, sm2d, stream>>>(a);
+    const unsigned gb = unsigned(sms * 8);
+    if (mode == FM_GENERAL) {
+      k_prefilter_bounds<FM_GENERAL, 4><<<gb, FT_THREADS, 0, stream>>>(a);
+      k_mesh_prefilter<FM_GENERAL, 4, 2><<<unsigned(sms * gridGeneral), FT_THREADS, smGen, stream>>>(a);
+    } else if (mode == FM_ORIGIN) {
+      k_prefilter_bounds<FM_ORIGIN, 8><<<gb, FT_THREADS, 0, stream>>>(a);
+      k_mesh_prefilter<FM_ORIGIN, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, sm2d, stream>>>(a);
+    } else {
+      k_prefilter_bounds<FM_DIR, 8><<<gb, FT_THREADS, 0, stream>>>(a);
+      k_mesh_prefilter<FM_DIR, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, sm2d, stream>>>(a);
+    }
+    launches += 2;
     NRT_CUDA(cudaGetLastError()); ++launches;
     NRT_CUDA(cudaEventRecord(ev.second, stream));
   }

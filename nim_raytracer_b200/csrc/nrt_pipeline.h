@@ -81,6 +81,9 @@ struct ChunkState {
   uint32_t* preRay;  // preCap
   uint32_t* preRec;  // preCap
   uint32_t* xref;    // nMO*NR     exact (float64 brute force) queue
+  // (run, chunk) pairs admitted by the chunk bounds of the current bundle (CUDA backend)
+  int64_t pairCap;
+  uint32_t* pairs;   // 2*pairCap
   uint8_t* occ;      // NR         shadow ray (sample, light) found an occluder (ShadowTrace -> Resolve)
   // ordered queue compaction (CUDA backend): gate pass 1 writes a code per (mesh object, wave
   // position) and per-block counts; a scan turns the counts into queue offsets; pass 2 writes the

@@ -328,7 +328,7 @@ template <class BE>
 struct Renderer {
   BE* be = nullptr;
   ChunkState cs{};
-  int64_t capS = 0, capNR = 0, capCand = 0;
+  int64_t capS = 0, capNR = 0, capCand = 0, capPairs = 0;
   int64_t wantedS = 0;   // the chunk-size request the current buffers were sized for (before the memory cap)
   int capMO = -1, capNL = -1, capWaves = 0, capRows = 0;
   std::vector<void*> owned;
@@ -366,6 +366,8 @@ struct Renderer {
       cs.qref = al<uint32_t>(mq); cs.qray0 = al<float>(mq * 4); cs.qray1 = al<float>(m * 4); cs.xref = al<uint32_t>(m);
       cs.qhot0 = al<float>(mq * 4); cs.qhot1 = al<float>(m * 4);
       cs.preRay = al<uint32_t>(4 * cand); cs.preRec = al<uint32_t>(4 * cand);
+      capPairs = std::max<int64_t>(int64_t(1) << 20, cand / 8);   // ~0.03 pairs per queued ray on the bunny scenes
+      cs.pairs = al<uint32_t>(2 * capPairs);
       cs.candRef = al<uint32_t>(cand); cs.candTri = al<uint32_t>(cand); cs.candT = al<double>(cand);
       cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * cntStride(nL));
       cs.alist = al<uint32_t>(2 * S); cs.acount = al<uint32_t>(waves + 2);
@@ -382,6 +384,7 @@ struct Renderer {
       be->zero(cs.gseg, sizeof(uint32_t) * grows * cs.gsn);
       dRows = al<int32_t>(nrows);
     }
+    cs.pairCap = capPairs;
     cs.S = capS; cs.NR = capNR; cs.QCAP = capNR + int64_t(nL) * capS; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.preCap = 4 * capCand; cs.rows = dRows;
   }
 
@@ -531,7 +534,7 @@ struct Renderer {
             int64_t queued = 0;
             for (int b = 0; b <= nL; ++b) {
               const int64_t q = c[cntQueue(b)];
-              if (c[cntPre(b)] > uint64_t(cs.preCap)) overflow = true;
+              if (c[cntPre(b)] > uint64_t(cs.preCap) || c[cntWork(b)] > uint64_t(cs.pairCap)) overflow = true;
               pacc.pre_candidates += c[cntPre(b)];
               if (!q) continue;
               // wave parity: even = path wave (primary for w == 0), odd = shadow wave

@@ -24,4 +24,7 @@ for wl in sys.argv[1:] or ["config2"]:
     p = ds.profile()
     print(f"{wl}: wall {wall:.3f} ms frame {p.total_ms:.3f} ms prefilter {p.mesh_filter_ms:.3f} ms by_mode {[round(x,3) for x in p.mesh_ms_by_mode[:3]]} "
           f"tests {list(p.mesh_tests_by_mode)[:3]} pre {p.pre_candidates} cand {p.candidates} launches {p.kernel_launches} Mrays/s {cs.num_rays / wall / 1e3:.0f}")
+    api.setKernelTiming(True); step(); kt = ds.kernelTimes(); api.setKernelTiming(False)
+    tot = sum(ms for ms, _ in kt.values())
+    print("   " + " | ".join(f"{k.split(' ')[0]} {ms:.2f}" for k, (ms, n) in sorted(kt.items(), key=lambda kv: -kv[1][0])) + f" | sum {tot:.2f}")
     L.nrt_device_free(fb); ds.close()
