@@ -85,6 +85,16 @@ __global__ void __launch_bounds__(kBlock) k_for_each_counted(F f, const uint32_t
   for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) f(i);
 }
 
+// Two counted lists in one launch (fa over [0, min(*ca, capA)), then fb over [0, min(*cb, capB))).
+template <class FA, class FB>
+__global__ void __launch_bounds__(kBlock) k_for_each_counted2(FA fa, const uint32_t* ca, int64_t capA, FB fb, const uint32_t* cb, int64_t capB) {
+  int64_t na = *ca, nb = *cb;
+  if (na > capA) na = capA;
+  if (nb > capB) nb = capB;
+  for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < na; i += int64_t(gridDim.x) * kBlock) fa(i);
+  for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < nb; i += int64_t(gridDim.x) * kBlock) fb(i);
+}
+
 // AABB gate of TriangleMesh.intersect (geom.nim:340) + ORDERED compaction of the rays that enter
 // each mesh's box into one queue per ray bundle (0 = arbitrary / shared-origin rays, 1 + l = shadow
 // rays of DistantLight l) and the float64 brute-force queue.  Three launches:
@@ -688,6 +698,12 @@ struct CudaBackend {
     use();
     Timed tm(this, CatOf<F>::v);
     k_for_each_counted<F><<<unsigned(sms * 8), kBlock, 0, stream>>>(f, count, cap);
+    NRT_CUDA(cudaGetLastError()); ++launches;
+  }
+  template <class FA, class FB> void forEachCounted2(const uint32_t* ca, int64_t capA, const FA& fa, const uint32_t* cb, int64_t capB, const FB& fb) {
+    use();
+    Timed tm(this, CatOf<FB>::v);
+    k_for_each_counted2<FA, FB><<<unsigned(sms * 8), kBlock, 0, stream>>>(fa, ca, capA, fb, cb, capB);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   // grow-only scratch buffers (temp storage of cub, keep flags, sort keys)

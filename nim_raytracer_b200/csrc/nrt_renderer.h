@@ -426,8 +426,9 @@ struct Renderer {
             if (sd.lights[l].kind == NRT_LIGHT_DISTANT && sd.frameValid(mo, FM_DIR, l)) run(FM_DIR, l, 1 + l);
         }
       }
-      be->forEachCounted(c + CNT_EXACT, cs.NR, ExactMesh{sd.d, fp, cs, kind, mo, c + CNT_EXACT, bounce});
-      be->forEachCounted(c + CNT_CAND, cs.candCap, Verify1<typename BE::Atom>{sd.d, fp, cs, kind, mo, bounce});
+      // (one launch: the float64 brute-force queue is empty on every scene seen so far)
+      be->forEachCounted2(c + CNT_EXACT, cs.NR, ExactMesh{sd.d, fp, cs, kind, mo, c + CNT_EXACT, bounce},
+                          c + CNT_CAND, cs.candCap, Verify1<typename BE::Atom>{sd.d, fp, cs, kind, mo, bounce});
       be->forEachCounted(c + CNT_CAND, cs.candCap, Verify2<typename BE::Atom>{cs, mo});
     }
   }

@@ -44,6 +44,11 @@ struct LoopBackend {
     for (int64_t i = 0; i < n; ++i) f(i);
     ++launches;
   }
+  template <class FA, class FB> void forEachCounted2(const uint32_t* ca, int64_t capA, const FA& fa, const uint32_t* cb, int64_t capB, const FB& fb) {
+    forEachCounted(ca, capA, fa);
+    forEachCounted(cb, capB, fb);
+    --launches;
+  }
   void sortFaces(const DMesh& m) {
     std::vector<uint32_t> keys(m.nfaces), idx(m.nfaces);
     FaceKeys fk{m, keys.data(), idx.data()};
