@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kBlock) k_rec_scatter(F f, int64_t n, const ui
   const int64_t r = pos[i];
   if (o.keep) {
 #pragma unroll
-    for (int k = 0; k < NC; ++k) recs[recIndex(r, k, NC)] = o.c[k];
+    for (int k = 0; k < NC; ++k) recs[fullIndex(r, k)] = o.c[k];
 #pragma unroll
     for (int k = 0; k < NH; ++k) hot[recIndex(r, k, NH)] = o.h[k];
   }
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kBlock) k_pad_recs(float* recs, float* hot, co
   neverHitHot(MODE, h);
   for (int64_t r = n + threadIdx.x; r < np; r += kBlock) {
 #pragma unroll
-    for (int k = 0; k < NC; ++k) recs[recIndex(r, k, NC)] = c[k];
+    for (int k = 0; k < NC; ++k) recs[fullIndex(r, k)] = c[k];
 #pragma unroll
     for (int k = 0; k < NH; ++k) hot[recIndex(r, k, NH)] = h[k];
   }
@@ -550,6 +550,34 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? 2 : 3) k_mesh
   }
 }
 
+// Finalize with coalesced reads: a pixel's samples are contiguous in the accumulator planes, so one
+// thread per pixel would read 8-byte words 8*spp bytes apart.  The CTA copies a tile of
+// pixels x spp samples into shared memory with coalesced loads (rows padded by one double: no bank
+// conflicts), then every thread adds its pixel's row in sample order (renderer.nim:147-159).
+static constexpr int kFinSmemDoubles = 5120;   // 40 KiB
+__global__ void __launch_bounds__(kBlock) k_finalize_tiled(Finalize f, int64_t npix, int tilePix) {
+  extern __shared__ double sh_fin[];
+  const int spp = f.fp.spp, row = spp + 1;
+  const ChunkState& cs = f.cs;
+  for (int64_t p0 = int64_t(blockIdx.x) * tilePix; p0 < npix; p0 += int64_t(gridDim.x) * tilePix) {
+    const int np = (npix - p0 < int64_t(tilePix)) ? int(npix - p0) : tilePix;
+    double sum[3] = {0.0, 0.0, 0.0};
+    for (int ch = 0; ch < 3; ++ch) {
+      const double* src = cs.accum + int64_t(ch) * cs.S + p0 * spp;
+      __syncthreads();
+      for (int k = threadIdx.x; k < np * spp; k += kBlock) { const int p = k / spp; sh_fin[p * row + (k - p * spp)] = src[k]; }
+      __syncthreads();
+      if (int(threadIdx.x) < np) {
+        double a = 0.0;
+        const double* r = sh_fin + threadIdx.x * row;
+        for (int k = 0; k < spp; ++k) a = a + r[k];
+        sum[ch] = a;
+      }
+    }
+    if (int(threadIdx.x) < np) f.store(p0 + threadIdx.x, sum[0], sum[1], sum[2]);
+  }
+}
+
 // clamp -> sRGB -> 8 bit (utils/framebuf.nim:74-78, utils/color.nim:17-22)
 __global__ void __launch_bounds__(kBlock) k_srgb8(const float* fb, unsigned char* out, int64_t n, int srgb) {
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
@@ -698,6 +726,17 @@ struct CudaBackend {
     use();
     Timed tm(this, CatOf<F>::v);
     k_for_each_counted<F><<<unsigned(sms * 8), kBlock, 0, stream>>>(f, count, cap);
+    NRT_CUDA(cudaGetLastError()); ++launches;
+  }
+  void finalize(int64_t npix, const Finalize& f) {
+    if (npix <= 0) return;
+    use();
+    const int spp = f.fp.spp;
+    if (f.fp.aa_kind == AA_NONE || spp < 2 || spp + 1 > kFinSmemDoubles / 8) { forEach(npix, f); return; }
+    Timed tm(this, KC_FINALIZE);
+    const int tilePix = std::min<int>(kBlock, kFinSmemDoubles / (spp + 1));
+    const int64_t tiles = (npix + tilePix - 1) / tilePix;
+    k_finalize_tiled<<<unsigned(std::min<int64_t>(tiles, int64_t(sms) * 16)), kBlock, sizeof(double) * kFinSmemDoubles, stream>>>(f, npix, tilePix);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   template <class FA, class FB> void forEachCounted2(const uint32_t* ca, int64_t capA, const FA& fa, const uint32_t* cb, int64_t capB, const FB& fb) {

@@ -55,7 +55,10 @@ NRT_HD constexpr int rayPlanes(int mode) { return mode == FM_GENERAL ? 2 : 1; }
 // never-hit records (S = -1 => Eb < 0).
 static constexpr int64_t kRecPad = 256;
 NRT_HD int64_t paddedFaces(int64_t nfaces) { return (nfaces + kRecPad - 1) / kRecPad * kRecPad; }
-NRT_HD int64_t recIndex(int64_t r, int k, int nc) { return ((r >> 1) * nc + k) * 2 + (r & 1); }
+NRT_HD int64_t recIndex(int64_t r, int k, int nc) { return ((r >> 1) * nc + k) * 2 + (r & 1); }   // hot records (FFMA2 pairs)
+// Full records (read one at a time by the refine stage) are plain 64-byte rows: four 16-byte loads.
+static constexpr int kFullStride = 16;
+NRT_HD int64_t fullIndex(int64_t r, int k) { return r * kFullStride + k; }
 
 static constexpr double kFilterU = 5.9604644775390625e-8;    // 2^-24
 static constexpr double kEps64 = 2.220446049250313e-16;       // 2^-52

@@ -387,7 +387,17 @@ struct Refine {
     const uint32_t rq = cs.preRay[i], pos = cs.preRec[i];
     const int nc = recFloats(mode);
     float q[16];
-    for (int k = 0; k < nc; ++k) q[k] = recs[recIndex(pos, k, nc)];
+#if defined(__CUDA_ARCH__)
+    {
+      const float4* p4 = reinterpret_cast<const float4*>(recs + fullIndex(pos, 0));
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        if (4 * k4 < nc) { const float4 v = __ldg(p4 + k4); q[4 * k4] = v.x; q[4 * k4 + 1] = v.y; q[4 * k4 + 2] = v.z; q[4 * k4 + 3] = v.w; }
+      }
+    }
+#else
+    for (int k = 0; k < nc; ++k) q[k] = recs[fullIndex(pos, k)];
+#endif
     const int64_t at = queueBase(cs, mo, b) + rq;
     const float* p0 = cs.qray0 + 4 * at;
     const float* p1 = cs.qray1 + 4 * (int64_t(mo) * cs.NR + rq);   // read only in GENERAL mode (b == 0)
@@ -664,6 +674,14 @@ struct Finalize {
       for (int k = 0; k < fp.spp; ++k) {
         r = r + cs.accum[s0 + k]; g = g + cs.accum[cs.S + s0 + k]; b = b + cs.accum[2 * cs.S + s0 + k];
       }
+    }
+    store(pl, r, g, b);
+  }
+  // (r, g, b) = the pixel's sample sums in sample order (its single sample for akNone)
+  NRT_HD void store(int64_t pl, double r, double g, double b) const {
+    int x, y; pixelOf(fp, cs, cs.p0 + pl, x, y);
+    if (pixelSkipped(fp, x, y)) return;
+    if (fp.aa_kind != AA_NONE) {
       const double inv = 1 / double(fp.spp);  // renderer.nim:159
       r = r * inv; g = g * inv; b = b * inv;
     }
@@ -707,7 +725,7 @@ struct BuildRecsGeneral {
       neverHitRecord(FM_GENERAL, c);
       neverHitHot(FM_GENERAL, h);
     }
-    for (int k = 0; k < 16; ++k) m.recs[recIndex(r, k, 16)] = c[k];
+    for (int k = 0; k < 16; ++k) m.recs[fullIndex(r, k)] = c[k];
     for (int k = 0; k < 4; ++k) m.hot[recIndex(r, k, 4)] = h[k];
   }
 };

@@ -137,7 +137,7 @@ struct SceneData {
       dm.normals = up(m.normals, m.nnormals * 4, reuse ? const_cast<double*>(old[i].normals) : nullptr);
       dm.vidx = up(m.vertex_idx, m.nfaces * 3, reuse ? const_cast<int64_t*>(old[i].vidx) : nullptr);
       dm.nidx = up(m.normal_idx, m.nfaces * 3, reuse ? const_cast<int64_t*>(old[i].nidx) : nullptr);
-      dm.recs = up<float>(nullptr, paddedFaces(m.nfaces) * recFloats(FM_GENERAL), reuse ? old[i].recs : nullptr);
+      dm.recs = up<float>(nullptr, paddedFaces(m.nfaces) * kFullStride, reuse ? old[i].recs : nullptr);
       dm.hot = up<float>(nullptr, paddedFaces(m.nfaces) * hotFloats(FM_GENERAL), reuse ? old[i].hot : nullptr);
       dm.bounds = up<float>(nullptr, std::max<int64_t>(1, numChunks(m.nfaces)) * 4, reuse ? old[i].bounds : nullptr);
       dm.order = up<uint32_t>(nullptr, std::max<int64_t>(1, m.nfaces), reuse ? old[i].order : nullptr);
@@ -287,7 +287,7 @@ struct SceneData {
     for (int mo = 0; mo < nMO; ++mo) {
       const int64_t nf = meshes[objs[moIndex[mo]].mesh].nfaces;
       MoRecs& r = moRecs[mo];
-      r.origin = up<float>(nullptr, paddedFaces(nf) * recFloats(FM_ORIGIN), reuse ? oldRecs[mo].origin : nullptr);
+      r.origin = up<float>(nullptr, paddedFaces(nf) * kFullStride, reuse ? oldRecs[mo].origin : nullptr);
       r.originHot = up<float>(nullptr, paddedFaces(nf) * hotFloats(FM_ORIGIN), reuse ? oldRecs[mo].originHot : nullptr);
       r.originBounds = up<float>(nullptr, std::max<int64_t>(1, numChunks(nf)) * 4, reuse ? oldRecs[mo].originBounds : nullptr);
       r.dirBounds.assign(size_t(desc->nlights), nullptr);
@@ -297,7 +297,7 @@ struct SceneData {
         be->compactRecs(nf, BuildRecsOrigin{d, mo}, r.origin, r.originHot, FM_ORIGIN, dRecCount + mo * rs + 1);
       for (int l = 0; l < desc->nlights; ++l) {
         if (lights[l].kind != NRT_LIGHT_DISTANT || !frameValid(mo, FM_DIR, l)) continue;
-        r.dir[l] = up<float>(nullptr, paddedFaces(nf) * recFloats(FM_DIR), reuse ? oldRecs[mo].dir[l] : nullptr);
+        r.dir[l] = up<float>(nullptr, paddedFaces(nf) * kFullStride, reuse ? oldRecs[mo].dir[l] : nullptr);
         r.dirHot[l] = up<float>(nullptr, paddedFaces(nf) * hotFloats(FM_DIR), reuse ? oldRecs[mo].dirHot[l] : nullptr);
         r.dirBounds[l] = up<float>(nullptr, std::max<int64_t>(1, numChunks(nf)) * 4, reuse ? oldRecs[mo].dirBounds[l] : nullptr);
         if (nf > 0) be->compactRecs(nf, BuildRecsDir{d, mo, l}, r.dir[l], r.dirHot[l], FM_DIR, dRecCount + mo * rs + 2 + l);
@@ -520,7 +520,7 @@ struct Renderer {
           if (cont == 0) break;  // no sample continued
           act = ActiveSet{nextList, nextCount, int64_t(cont)};
         }
-        be->forEach(npix, Finalize{fp, cs});
+        be->finalize(npix, Finalize{fp, cs});
         // chunk epilogue: counters (profile + overflow check) and stats
         std::vector<uint32_t> hc(ncnt);
         unsigned long long hs[ST_COUNT];

@@ -49,6 +49,7 @@ struct LoopBackend {
     forEachCounted(cb, capB, fb);
     --launches;
   }
+  void finalize(int64_t npix, const Finalize& f) { forEach(npix, f); }
   void sortFaces(const DMesh& m) {
     std::vector<uint32_t> keys(m.nfaces), idx(m.nfaces);
     FaceKeys fk{m, keys.data(), idx.data()};
@@ -63,14 +64,14 @@ struct LoopBackend {
       const RecOut o = f(i);
       if (!o.keep) continue;
       const int64_t r = (*count)++;
-      for (int k = 0; k < nc; ++k) recs[recIndex(r, k, nc)] = o.c[k];
+      for (int k = 0; k < nc; ++k) recs[fullIndex(r, k)] = o.c[k];
       for (int k = 0; k < nh; ++k) hot[recIndex(r, k, nh)] = o.h[k];
     }
     float c[16], h[4];
     neverHitRecord(mode, c);
     neverHitHot(mode, h);
     for (int64_t r = *count; r < paddedFaces(*count); ++r) {
-      for (int k = 0; k < nc; ++k) recs[recIndex(r, k, nc)] = c[k];
+      for (int k = 0; k < nc; ++k) recs[fullIndex(r, k)] = c[k];
       for (int k = 0; k < nh; ++k) hot[recIndex(r, k, nh)] = h[k];
     }
     ++launches;
