@@ -1048,6 +1048,7 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
         aObj = aov->obj_id; aTri = aov->tri_id; aT = aov->t_hit;
       }
       be.launches = 0;
+      if (const char* e = std::getenv("NRT_PREFILTER_CULL")) be.cull = std::atoi(e) != 0; else be.cull = true;
       NRT_CUDA(cudaEventRecord(dc->ev0, be.stream));
       // Host <-> staging copies of exactly the rows this worker renders (and their step x step
       // fill rows); equally spaced rows (scanline interleave) go out as one 2D copy.

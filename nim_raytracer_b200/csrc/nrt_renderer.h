@@ -342,7 +342,7 @@ struct Renderer {
   void freeAll() {
     for (void* p : owned) be->dfree(p);
     owned.clear();
-    capS = capNR = capCand = 0; capMO = -1; capNL = -1; capWaves = 0; capRows = 0; dRows = nullptr;
+    capS = capNR = capCand = capPairs = 0; capMO = -1; capNL = -1; capWaves = 0; capRows = 0; dRows = nullptr;
     wantedS = 0;
   }
   template <class T> T* al(int64_t n) { T* p = static_cast<T*>(be->dalloc(sizeof(T) * std::max<int64_t>(n, 1))); owned.push_back(p); return p; }
@@ -352,9 +352,11 @@ struct Renderer {
     return (v && *v) ? std::atoll(v) : dflt;
   }
 
-  void ensure(int64_t S, int nL, int nMO, int waves, int64_t cand, int nrows) {
+  void ensure(int64_t S, int nL, int nMO, int waves, int64_t cand, int nrows, int64_t pairsReq) {
     const int64_t NR = S * std::max(1, nL);
-    if (S > capS || NR > capNR || nMO > capMO || nL != capNL || waves > capWaves || cand > capCand || nrows > capRows) {
+    const int64_t pairsWant = pairsReq > 0 ? pairsReq : std::max<int64_t>(int64_t(1) << 20, cand / 8);   // ~0.03 pairs per queued ray on the bunny scenes
+    if (S > capS || NR > capNR || nMO > capMO || nL != capNL || waves > capWaves || cand > capCand || nrows > capRows || pairsWant > capPairs ||
+        (pairsReq > 0 && pairsReq != capPairs)) {
       freeAll();
       capS = S; capNR = NR; capMO = nMO; capNL = nL; capWaves = waves; capCand = cand; capRows = nrows;
       cs.rayO = al<double>(4 * S); cs.rayD = al<double>(4 * S); cs.hitW = al<double>(4 * S); cs.nrm = al<double>(4 * S);
@@ -366,7 +368,7 @@ struct Renderer {
       cs.qref = al<uint32_t>(mq); cs.qray0 = al<float>(mq * 4); cs.qray1 = al<float>(m * 4); cs.xref = al<uint32_t>(m);
       cs.qhot0 = al<float>(mq * 4); cs.qhot1 = al<float>(m * 4);
       cs.preRay = al<uint32_t>(4 * cand); cs.preRec = al<uint32_t>(4 * cand);
-      capPairs = std::max<int64_t>(int64_t(1) << 20, cand / 8);   // ~0.03 pairs per queued ray on the bunny scenes
+      capPairs = pairsWant;
       cs.pairs = al<uint32_t>(2 * capPairs);
       cs.candRef = al<uint32_t>(cand); cs.candTri = al<uint32_t>(cand); cs.candT = al<double>(cand);
       cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * cntStride(nL));
@@ -479,9 +481,10 @@ struct Renderer {
     // the frame with 4x the capacity
     if (cand == 0) cand = std::max<int64_t>(int64_t(1) << 20, S * std::max(1, nL) / 2);
     const int force_exact = int(envInt("NRT_FORCE_EXACT", 0));
+    int64_t pairsReq = std::max<int64_t>(envInt("NRT_PAIR_CAP", 0), 0);   // (run, chunk) work-list capacity; 0: sized from cand
 
     for (int attempt = 0;; ++attempt) {
-      ensure(S, nL, nMO, waves, cand, int(rows.size()));
+      ensure(S, nL, nMO, waves, cand, int(rows.size()), pairsReq);
       cs.fb = fb; cs.aovObj = aovObj; cs.aovTri = aovTri; cs.aovT = aovT;
       be->upload(dRows, rows.data(), sizeof(int32_t) * rows.size());
       preLog.clear();
@@ -567,7 +570,8 @@ struct Renderer {
         return NRT_OK;
       }
       if (attempt >= 3) { err = "candidate buffer overflow"; return NRT_ERR_OVERFLOW; }
-      cand *= 4;  // re-render the frame with a larger candidate buffer (outputs are simply overwritten)
+      cand *= 4;  // re-render the frame with larger candidate / pair buffers (outputs are simply overwritten)
+      pairsReq *= 8;
     }
   }
 };

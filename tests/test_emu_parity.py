@@ -86,6 +86,9 @@ def test_chunking_overflow_retry_and_exact_path(oracle_mod, monkeypatch):
     monkeypatch.setenv("NRT_CAND_CAP", "8")
     check(sc, o, oracle_mod)
     monkeypatch.delenv("NRT_CAND_CAP")
+    monkeypatch.setenv("NRT_PAIR_CAP", "4")      # (run, chunk) work list overflows -> re-render with 8x
+    check(sc, o, oracle_mod)
+    monkeypatch.delenv("NRT_PAIR_CAP")
     monkeypatch.setenv("NRT_FORCE_EXACT", "1")
     prof = check(sc, o, oracle_mod)
     assert prof["mesh_tests"] == 0 and prof["exact_rays"] == prof["mesh_rays"]

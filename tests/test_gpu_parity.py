@@ -140,6 +140,45 @@ def test_chunked_and_exact_paths_agree(oracle_mod, monkeypatch):
     assert (fb.data == ref.data).all() and st == rst
 
 
+def test_two_level_traversal_equals_brute_force(monkeypatch):
+    # chunk bounds + (run, chunk) work list vs every chunk of the record set: same ids, image, stats and
+    # candidates; far fewer executed tests.  Then the work list overflows on purpose: re-render path.
+    sc, o = scenes.bunny_spheres(stride=2), api.Options(480, 270, antialias=api.Antialias(api.akGrid, 2))
+    ds = api.DeviceScene(sc)
+
+    def run():
+        fb, aov = api.newFramebuf(o.width, o.height), api.Aov(o.width, o.height)
+        st = api.renderFrame(ds, o, fb, aov=aov)
+        return fb, st, aov, ds.profile()
+
+    monkeypatch.setenv("NRT_PREFILTER_CULL", "0")
+    b_fb, b_st, b_aov, b_p = run()
+    monkeypatch.setenv("NRT_PREFILTER_CULL", "1")
+    c_fb, c_st, c_aov, c_p = run()
+    assert (b_fb.data == c_fb.data).all() and b_st == c_st
+    assert (b_aov.tri_id == c_aov.tri_id).all() and (b_aov.obj_id == c_aov.obj_id).all() and (b_aov.t_hit == c_aov.t_hit).all()
+    assert b_p.candidates == c_p.candidates and b_p.pre_candidates == c_p.pre_candidates
+    assert c_p.mesh_tests < 0.5 * b_p.mesh_tests          # (a 256-ray run spans 8 pixels x 4 spp here; ~1/16 at 4K x 16 spp)
+    monkeypatch.setenv("NRT_PAIR_CAP", "64")
+    d_fb, d_st, d_aov, _ = run()
+    assert (d_fb.data == c_fb.data).all() and d_st == c_st and (d_aov.tri_id == c_aov.tri_id).all()
+
+
+def test_kernel_timing_hook():
+    sc, o = scenes.bunny(stride=8), api.Options(320, 180)
+    ds = api.DeviceScene(sc)
+    fb = api.newFramebuf(o.width, o.height)
+    api.setKernelTiming(True)
+    try:
+        api.renderFrame(ds, o, fb)
+        kt = ds.kernelTimes()
+    finally:
+        api.setKernelTiming(False)
+    assert "k_mesh_prefilter" in kt and "Shade" in kt and "Resolve" in kt
+    assert all(ms >= 0 and n > 0 for ms, n in kt.values())
+    assert abs(sum(ms for ms, _ in kt.values()) - ds.profile().total_ms) < max(1.0, ds.profile().total_ms)
+
+
 def _check_golden(name, scene, opts):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     fb, st, aov = gpu_render(scene, opts)
