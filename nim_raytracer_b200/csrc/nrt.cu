@@ -23,6 +23,23 @@
 
 #include "nrt_renderer.h"
 
+// Resident CTAs per SM the register allocation of the per-sample kernels aims at (0 = the compiler's
+// choice).  Measured on B200, BASELINE config 4: k_gate_flags 5.87 ms at 56 registers -> 4.52 ms at 40
+// (6 CTAs/SM, 116 bytes of spills); Resolve 3.16 -> 2.95 ms at 64; Shade and ShadowTrace are fastest at
+// the compiler's 64 registers without spills (48 registers: +7 %, 40: +15 %).
+#ifndef NRT_OCC_ST
+#define NRT_OCC_ST 0
+#endif
+#ifndef NRT_OCC_SHADE
+#define NRT_OCC_SHADE 0
+#endif
+#ifndef NRT_OCC_DEFAULT
+#define NRT_OCC_DEFAULT 4
+#endif
+#ifndef NRT_OCC_GATE
+#define NRT_OCC_GATE 6
+#endif
+
 namespace nrt {
 
 // ------------------------------------------------------------------ errors ----
@@ -68,8 +85,12 @@ __device__ __forceinline__ void blockStatsAdd(const StatDelta& d, unsigned long 
   }
 }
 
+// resident CTAs per SM the register allocation aims at (measured on B200: see DESIGN.md)
+template <class F> struct MinBlocks { static constexpr int v = NRT_OCC_DEFAULT; };
+template <> struct MinBlocks<ShadowTrace> { static constexpr int v = NRT_OCC_ST; };
+template <> struct MinBlocks<Shade> { static constexpr int v = NRT_OCC_SHADE; };
 template <class F>
-__global__ void __launch_bounds__(kBlock) k_for_each_stats(F f, int64_t n, unsigned long long* stats) {
+__global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats(F f, int64_t n, unsigned long long* stats) {
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
   StatDelta d = zeroStats();
   if (i < n) d = f(i);
@@ -112,7 +133,7 @@ __global__ void __launch_bounds__(kBlock) k_for_each_counted2(FA fa, const uint3
 static constexpr int kSegBlocks = 256;   // 256-ray blocks per segment
 __device__ __forceinline__ uint8_t gateWant(int r, int nB) { return r < nB ? uint8_t(1 + r) : uint8_t(255); }
 
-__global__ void __launch_bounds__(kBlock) k_gate_flags(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO, uint32_t* neCount) {
+__global__ void __launch_bounds__(kBlock, NRT_OCC_GATE) k_gate_flags(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO, uint32_t* neCount) {
   extern __shared__ uint32_t sh_cnt[];   // nMO * nRow
   const unsigned lane = threadIdx.x & 31u;
   const ChunkState& cs = g.cs;

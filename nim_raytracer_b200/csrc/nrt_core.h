@@ -76,6 +76,7 @@ struct DObject {
   double albedo[3];
   double reflection;
   double albedo_pi[3]; // albedo / PI (shader.nim:15), the same IEEE division done once at scene build
+  double plane_nw[4];  // objectToWorld * (0,1,0,0): the world-space normal of a Plane (geom.nim:367-368, renderer.nim:85), done once
 };
 
 // Compact per-object record read by the in-order object scan of trace(): 48 bytes, three
@@ -162,6 +163,7 @@ struct DScene {
   const int32_t* mesh_obj_index;  // mesh object k -> object index
   const BundleFrame* frames;      // [mo * (2 + nlights) + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
   double c2w[16];
+  double cam_orig[4];             // c2w * (0,0,0,1): castPrimaryRay's origin (renderer.nim:42), the same product done once on the host
   double tan_half_fov;            // f of renderer.nim:38 (host libm, shared with nothing else)
   double bg[3];
 };
@@ -384,7 +386,7 @@ NRT_HD void castPrimaryRay(const DScene& sc, int w, int h, double x, double y, V
   const double f = sc.tan_half_fov;
   const double cx = ((2 * x * r) / double(w) - r) * f;
   const double cy = (1 - 2 * y / double(h)) * f;
-  orig = mulm(sc.c2w, v4(0.0, 0.0, 0.0, 1.0));
+  orig = v4(sc.cam_orig[0], sc.cam_orig[1], sc.cam_orig[2], sc.cam_orig[3]);
   dir = mulm(sc.c2w, normalize(v4(cx, cy, -1, 0.0)));
 }
 

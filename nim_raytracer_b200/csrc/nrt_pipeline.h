@@ -200,7 +200,7 @@ NRT_HD void makeSamples(int kind, int m, PixelRng& rng, double* px, double* py) 
 // Bounce-0 state that every sample shares is not stored: the ray origin is the camera origin
 // (primaryOrigin), the path weight is 1, the colour accumulator starts at 0 and the bounce number
 // is the host loop's — Gen writes 33 bytes per sample instead of 105.
-NRT_HD V4 primaryOrigin(const DScene& sc) { return mulm(sc.c2w, v4(0.0, 0.0, 0.0, 1.0)); }   // renderer.nim:42
+NRT_HD V4 primaryOrigin(const DScene& sc) { return v4(sc.cam_orig[0], sc.cam_orig[1], sc.cam_orig[2], sc.cam_orig[3]); }   // renderer.nim:42
 NRT_HD void initSample(const ChunkState& cs, int64_t s, bool alive, V4 d) {
   st4(cs.rayD, cs.S, s, d);
   cs.active[s] = alive ? 1 : 0;
@@ -557,8 +557,12 @@ struct Shade {
     const V4 hitW = add(o, scale(d, tr.t));
     V4 n;
     if (tr.tri == kNoTri) {
-      const V4 hitO = mulm(ob.w2o, hitW);
-      n = mulm(ob.o2w, geomNormal(ob, hitO));
+      if (ob.kind == GEOM_PLANE) {   // constant normal: the product was done at scene build
+        n = v4(ob.plane_nw[0], ob.plane_nw[1], ob.plane_nw[2], ob.plane_nw[3]);
+      } else {
+        const V4 hitO = mulm(ob.w2o, hitW);
+        n = mulm(ob.o2w, geomNormal(ob, hitO));
+      }
     } else {
       const DMesh& m = sc->meshes[ob.mesh];
       const double* nn = m.normals + 4 * m.nidx[3 * int64_t(tr.tri)];

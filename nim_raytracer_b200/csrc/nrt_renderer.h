@@ -181,6 +181,7 @@ struct SceneData {
       std::memcpy(dob.bmax, o.vmax, sizeof(dob.bmax));
       std::memcpy(dob.albedo, o.albedo, sizeof(dob.albedo));
       for (int k = 0; k < 3; ++k) dob.albedo_pi[k] = o.albedo[k] / kPi;
+      { const V4 nw = mulm(dob.o2w, v4(0.0, 1.0, 0.0, 0.0)); dob.plane_nw[0] = nw.x; dob.plane_nw[1] = nw.y; dob.plane_nw[2] = nw.z; dob.plane_nw[3] = nw.w; }
       dob.reflection = o.reflection;
       if (o.reflection > 0.0) anyReflective = true;
       if (o.kind == NRT_GEOM_MESH) {
@@ -270,6 +271,7 @@ struct SceneData {
     }
     h.objects = dObjs; h.cobjs = dCObjs; h.cobjf = dCObjF; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames;
     std::memcpy(h.c2w, desc->camera_to_world, sizeof(h.c2w));
+    { const V4 co = mulm(h.c2w, v4(0.0, 0.0, 0.0, 1.0)); h.cam_orig[0] = co.x; h.cam_orig[1] = co.y; h.cam_orig[2] = co.z; h.cam_orig[3] = co.w; }
     h.tan_half_fov = std::tan((desc->fov * (kPi / 180.0)) / 2);  // renderer.nim:38; Nim degToRad = d * (PI/180)
     std::memcpy(h.bg, desc->bg_color, sizeof(h.bg));
     d = up(&h, 1, reuse ? d : nullptr);
