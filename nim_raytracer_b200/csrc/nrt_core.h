@@ -242,7 +242,7 @@ NRT_HD bool sphereCertainMiss(double radius, V4 oc, V4 dir) {
 //   b^2 < a (|oc|^2 (1 - 5e-6) - r2m - mray)     r2m = r^2 + object part (CObjF), mray = ray part
 // (the rearrangement costs another ~3u a |oc|^2, inside the slack between 4.3e-6 and 5e-6).
 // true => the reference's delta is negative (NegInf).  NaN / Inf compare false.
-struct RayF { float ox, oy, oz, dx, dy, dz, a, mray, mo; };
+struct RayF { float ox, oy, oz, dx, dy, dz, a, mray; };
 NRT_HD RayF makeRayF(V4 o, V4 d) {
   RayF r;
   r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
@@ -250,7 +250,6 @@ NRT_HD RayF makeRayF(V4 o, V4 d) {
   r.a = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
   const float mo = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
   r.mray = 2e-7f * (mo * mo);
-  r.mo = mo;
   return r;
 }
 NRT_HD bool certainMissF(const CObjF& c, const RayF& r) {
@@ -263,11 +262,12 @@ NRT_HD bool certainMissF(const CObjF& c, const RayF& r) {
 // Plane (object space y = 0, geom.nim:240-248) with worldToObject = [I | t]: when the object-space
 // origin height o.y + t.y and the direction's y have the same strict sign the reference returns either
 // NegInf (|d.y| <= 1e-6) or t = -o.y / d.y < 0, both rejected by trace() (renderer.nim:60).  Decided in
-// float32: |oy - (o.y + t.y)| <= 2.01 u (|o|_inf + |t|_inf) < 2.5e-7 (|o|_inf + |t|_inf) =: margin
-// (ray part 2.5e-7 mo, object part in c.tz, which also adds 1e-30 so that the true height is far from
-// the underflow range where -o.y / d.y could round to -0.0).  float(d.y) keeps the sign of d.y.
+// float32 from the y components alone: |oy - (o.y + t.y)| <= 2u (1 + u) (|o.y| + |t.y|) < 2.5e-7 (|o.y| + |t.y|)
+// =: margin (ray part from |oy|, object part in c.tz, which also adds 1e-30 so that the true height is
+// far from the range where -o.y / d.y could round to -0.0).  float(d.y) keeps the sign of d.y.  A
+// shadow ray that leaves the plane itself (height = bias = 1e-8, towards the light) is decided here too.
 NRT_HD bool planeMissF(const CObjF& c, const RayF& r) {
-  const float oy = r.oy + c.ty, m = fmaf(2.5e-7f, r.mo, c.tz);
+  const float oy = r.oy + c.ty, m = fmaf(2.5e-7f, fabsf(r.oy), c.tz);
   return (oy > m && r.dy > 0.f) || (oy < -m && r.dy < 0.f);
 }
 

@@ -223,7 +223,7 @@ struct SceneData {
         f.tx = float(c.t[0]); f.ty = float(c.t[1]); f.tz = float(c.t[2]);
         f.r2m = roundUpF(r2 + 2e-6 * r2 + 2e-7 * mt * mt);
       } else if (c.kind == NRT_GEOM_PLANE && c.xlate_only && finiteT) {
-        f.tx = bitsToFloat(uint32_t(COF_PLANE)); f.ty = float(c.t[1]); f.tz = roundUpF(2.5e-7 * mt + 1e-30);
+        f.tx = bitsToFloat(uint32_t(COF_PLANE)); f.ty = float(c.t[1]); f.tz = roundUpF(2.5e-7 * std::fabs(c.t[1]) + 1e-30);
       } else if (c.kind == NRT_GEOM_MESH) {
         f.tx = bitsToFloat(uint32_t(COF_MESH)); f.ty = bitsToFloat(uint32_t(c.mesh_obj));
       }
