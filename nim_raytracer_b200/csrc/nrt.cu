@@ -383,6 +383,7 @@ struct PreArgs {
   uint32_t* preRec;
   uint32_t preCap;
   uint32_t cull;            // 0: every chunk is evaluated (brute force over the record set)
+  uint32_t splitBelow;      // lists shorter than splitBelow x (resident warps) are split into half / quarter chunk items
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? 2 : 3) k_mesh
   // short lists: items of half / quarter chunks so that the launch still fills the GPU
   const uint32_t totalWarps = gridDim.x * FT_WARPS;
   uint32_t SP = 1;
-  while (SP < 4 && uint64_t(nPairs) * SP < 2ull * totalWarps) SP <<= 1;
+  while (SP < 4 && uint64_t(nPairs) * SP < uint64_t(a.splitBelow) * totalWarps) SP <<= 1;
   const uint32_t QN = (FT_TC / 4) / SP;                // record quads per item
   const uint64_t nItems = uint64_t(nPairs) * SP;
   for (;;) {
@@ -663,6 +664,7 @@ struct CudaBackend {
   int gridPerSm = 3;   // resident prefilter CTAs per SM (NRT_PREFILTER_CTAS_PER_SM)
   int gridGeneral = 2;
   bool cull = true;    // NRT_PREFILTER_CULL=0: evaluate every chunk (brute force over the record set)
+  int splitBelow = 8;  // NRT_PREFILTER_SPLIT: measured on the 1/8-frame partitions of an 8-GPU run (2: 1.08 ms of prefilter, 8: 1.04, 32: 1.01; full frame unchanged)
   bool smemOptIn = false;
   void* scratchPtr[2] = {nullptr, nullptr};
   size_t scratchBytes[2] = {0, 0};
@@ -877,6 +879,7 @@ struct CudaBackend {
     a.preRay = cs.preRay; a.preRec = cs.preRec;
     a.preCap = uint32_t(std::min<int64_t>(cs.preCap, 0xFFFFFFFFll));
     a.cull = cull ? 1u : 0u;
+    a.splitBelow = uint32_t(splitBelow);
     if (filterUsed == filterEvents.size()) {
       cudaEvent_t e0, e1;
       NRT_CUDA(cudaEventCreate(&e0)); NRT_CUDA(cudaEventCreate(&e1));
@@ -1070,6 +1073,7 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
       }
       be.launches = 0;
       if (const char* e = std::getenv("NRT_PREFILTER_CULL")) be.cull = std::atoi(e) != 0; else be.cull = true;
+      if (const char* e = std::getenv("NRT_PREFILTER_SPLIT")) be.splitBelow = std::max(0, std::atoi(e));
       NRT_CUDA(cudaEventRecord(dc->ev0, be.stream));
       // Host <-> staging copies of exactly the rows this worker renders (and their step x step
       // fill rows); equally spaced rows (scanline interleave) go out as one 2D copy.
