@@ -370,6 +370,7 @@ static_assert(kRecPad == FT_TC, "one bound per shared-memory chunk");
 struct PreArgs {
   const float4* hot;        // pair-interleaved hot records, padded to a multiple of kRecPad
   const float4* bounds;     // one hot-format record per chunk
+  const float4* sub;        // one hot-format record per sub-chunk (kSubRecs records)
   const uint32_t* nrec;     // number of records (device)
   const float4* h0;         // ray plane H0: (x, y, T, 0) | (dh, T)
   const float4* h1;         // ray plane H1: (2 p0, 0)   (GENERAL)
@@ -377,6 +378,7 @@ struct PreArgs {
   uint32_t* itemctr;        // level 2 work-item counter
   uint32_t* prectr;         // pre-candidate counter
   uint32_t* workctr;        // (run, chunk) pairs admitted by level 1 (may exceed pairCap: the host re-renders)
+  uint32_t* subctr;         // (run, sub-chunk) pairs evaluated in full
   uint2* pairs;             // the work list
   uint32_t pairCap;
   uint32_t* preRay;
@@ -475,16 +477,18 @@ template <int MODE, int R, int U>
 __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? 2 : 3) k_mesh_prefilter(PreArgs a) {
   constexpr int NH = hotFloats(MODE);      // float2 per record pair == float4 per record quad
   constexpr int CH4 = (FT_TC / 4) * NH;    // float4 per chunk
-  extern __shared__ __align__(16) float4 smem_tiles[];   // [FT_WARPS][CH4]
+  constexpr int SQ = kSubRecs / 4;         // record quads per sub-chunk
+  extern __shared__ __align__(16) float4 smem_tiles[];   // [FT_WARPS][CH4 + kSubPerChunk]
   const uint32_t nq = *a.qcount;
   if (nq == 0) return;
   const uint32_t nPairs = min(*a.workctr, a.pairCap);
   if (nPairs == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4* const tile = smem_tiles + size_t(warp) * CH4;
+  float4* const tile = smem_tiles + size_t(warp) * (CH4 + kSubPerChunk);
+  float4* const stile = tile + CH4;        // the chunk's sub-chunk bounds
   // per-warp survivor buffer behind the tiles: FT_WB (ray, record) pairs + a counter
-  uint2* const wbuf = reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * CH4) + size_t(warp) * FT_WB;
-  uint32_t* const wcnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * CH4) + size_t(FT_WARPS) * FT_WB) + warp;
+  uint2* const wbuf = reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * (CH4 + kSubPerChunk)) + size_t(warp) * FT_WB;
+  uint32_t* const wcnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * (CH4 + kSubPerChunk)) + size_t(FT_WARPS) * FT_WB) + warp;
   if (lane == 0) *wcnt = 0;
   __syncwarp();
   auto emit = [&](uint32_t ray, uint32_t rec) {
@@ -499,8 +503,9 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? 2 : 3) k_mesh
   const uint32_t totalWarps = gridDim.x * FT_WARPS;
   uint32_t SP = 1;
   while (SP < 4 && uint64_t(nPairs) * SP < uint64_t(a.splitBelow) * totalWarps) SP <<= 1;
-  const uint32_t QN = (FT_TC / 4) / SP;                // record quads per item
+  const uint32_t SN = kSubPerChunk / SP;               // sub-chunks per item
   const uint64_t nItems = uint64_t(nPairs) * SP;
+  uint32_t subWork = 0;
   for (;;) {
     uint32_t item = 0;
     if (lane == 0) item = atomicAdd(a.itemctr, 1u);
@@ -508,46 +513,68 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? 2 : 3) k_mesh
     if (item >= nItems) break;
     const uint32_t pi = item / SP, part = item - pi * SP;
     const uint2 pr = a.pairs[pi];
-    // stage this item's part of the chunk (16 bytes per lane and step), rays meanwhile
+    // stage this item's part of the chunk and its sub-chunk bounds (16 bytes per lane and step), rays meanwhile
     {
-      const float4* src = a.hot + size_t(pr.y) * CH4 + size_t(part) * QN * NH;
-      for (uint32_t k = lane; k < QN * NH; k += 32) __pipeline_memcpy_async(tile + k, src + k, 16);
+      const float4* src = a.hot + size_t(pr.y) * CH4 + size_t(part) * SN * SQ * NH;
+      for (uint32_t k = lane; k < SN * SQ * NH; k += 32) __pipeline_memcpy_async(tile + k, src + k, 16);
+      if (uint32_t(lane) < SN) __pipeline_memcpy_async(stile + lane, a.sub + size_t(pr.y) * kSubPerChunk + part * SN + lane, 16);
       __pipeline_commit();
     }
     LaneRays<MODE, R> ry;
     ry.load(a, pr.x, nq, lane);
     __pipeline_wait_prior(0);
     __syncwarp();                            // the records are in the slice for every lane
-    const uint32_t base = pr.y * FT_TC + part * QN * 4;
-#pragma unroll U
-    for (uint32_t t = 0; t < QN; ++t) {
-      float2 q[2 * NH];   // two record pairs: q[j * NH + k] = coefficient k of pair j
-#pragma unroll
-      for (int c = 0; c < NH; ++c) {
-        const float4 v4 = tile[t * NH + c];
-        q[2 * c] = make_float2(v4.x, v4.y);
-        q[2 * c + 1] = make_float2(v4.z, v4.w);
-      }
-      uint32_t hm = 0;   // bit r: ray r passed one of the four tests
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float thr = (MODE == FM_GENERAL) ? ry.a3[r] : ry.a2[r];
-        const float2 g0 = prefilterPair<MODE>(q, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
-        const float2 g1 = prefilterPair<MODE>(q + NH, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
-        // one compare per ray: max of its four left-hand sides against its threshold (FMNMX3 + FSETP)
-        const float m = fmaxf(fmaxf(g0.x, g0.y), fmaxf(g1.x, g1.y));
-        if (m >= thr) hm |= 1u << r;
-      }
-      if (hm) {  // re-evaluate the rays that passed and emit their survivors
+    const uint32_t base = pr.y * FT_TC + part * SN * kSubRecs;
+    for (uint32_t sb = 0; sb < SN; ++sb) {
+      // ---- level 2: can any ray of the run reach this sub-chunk? ----
+      if (a.cull) {
+        const float4 bd = stile[sb];
+        bool p = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (!(hm & (1u << r)) || ry.idx[r] == kInvalidRef) continue;
-          const float thr = (MODE == FM_GENERAL) ? ry.a3[r] : ry.a2[r];
+          if (MODE == FM_GENERAL) {
+            const float sdot = fmaf(bd.x, ry.a0[r], fmaf(bd.y, ry.a1[r], bd.z * ry.a2[r]));
+            const float tt = fmaf(bd.x, ry.b0[r], fmaf(bd.y, ry.b1[r], fmaf(bd.z, ry.b2[r], bd.w)));
+            p = p || (fmaf(sdot, sdot, tt) >= ry.a3[r]);
+          } else {
+            p = p || (fmaf(bd.x, ry.a0[r], fmaf(bd.y, ry.a1[r], bd.z)) >= ry.a2[r]);
+          }
+        }
+        if (!__any_sync(0xffffffffu, p)) continue;
+      }
+      ++subWork;
+      // ---- level 3: run x the sub-chunk's records ----
+#pragma unroll U
+      for (uint32_t tq = 0; tq < uint32_t(SQ); ++tq) {
+        const uint32_t t = sb * SQ + tq;
+        float2 q[2 * NH];   // two record pairs: q[j * NH + k] = coefficient k of pair j
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float2 g = prefilterPair<MODE>(q + j * NH, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
-            if (g.x >= thr) emit(ry.idx[r], base + 4 * t + 2 * j);
-            if (g.y >= thr) emit(ry.idx[r], base + 4 * t + 2 * j + 1);
+        for (int c = 0; c < NH; ++c) {
+          const float4 v4 = tile[t * NH + c];
+          q[2 * c] = make_float2(v4.x, v4.y);
+          q[2 * c + 1] = make_float2(v4.z, v4.w);
+        }
+        uint32_t hm = 0;   // bit r: ray r passed one of the four tests
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float thr = (MODE == FM_GENERAL) ? ry.a3[r] : ry.a2[r];
+          const float2 g0 = prefilterPair<MODE>(q, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
+          const float2 g1 = prefilterPair<MODE>(q + NH, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
+          // one compare per ray: max of its four left-hand sides against its threshold (FMNMX3 + FSETP)
+          const float m = fmaxf(fmaxf(g0.x, g0.y), fmaxf(g1.x, g1.y));
+          if (m >= thr) hm |= 1u << r;
+        }
+        if (hm) {  // re-evaluate the rays that passed and emit their survivors
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (!(hm & (1u << r)) || ry.idx[r] == kInvalidRef) continue;
+            const float thr = (MODE == FM_GENERAL) ? ry.a3[r] : ry.a2[r];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float2 g = prefilterPair<MODE>(q + j * NH, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
+              if (g.x >= thr) emit(ry.idx[r], base + 4 * t + 2 * j);
+              if (g.y >= thr) emit(ry.idx[r], base + 4 * t + 2 * j + 1);
+            }
           }
         }
       }
@@ -570,6 +597,7 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? 2 : 3) k_mesh
     }
     __syncwarp();                            // every lane left the slice before it is staged again
   }
+  if (lane == 0 && subWork) atomicAdd(a.subctr, subWork);
 }
 
 // Finalize with coalesced reads: a pixel's samples are contiguous in the accumulator planes, so one
@@ -861,11 +889,12 @@ struct CudaBackend {
     ++launches;
   }
   // prefilter launch for one ray bundle of one mesh object
-  void filter(int mode, const float* hot, const float* bounds, const uint32_t* nrec, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
+  void filter(int mode, const float* hot, const float* bounds, const float* sub, const uint32_t* nrec, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
     use();
     PreArgs a;
     a.hot = reinterpret_cast<const float4*>(hot);
     a.bounds = reinterpret_cast<const float4*>(bounds);
+    a.sub = reinterpret_cast<const float4*>(sub);
     a.nrec = nrec;
     const int64_t base = queueBase(cs, mo, b);
     a.h0 = reinterpret_cast<const float4*>(cs.qhot0) + base;
@@ -874,6 +903,7 @@ struct CudaBackend {
     a.itemctr = cnt + cntTile(b);
     a.prectr = cnt + cntPre(b);
     a.workctr = cnt + cntWork(b);
+    a.subctr = cnt + cntSub(b);
     a.pairs = reinterpret_cast<uint2*>(cs.pairs);
     a.pairCap = uint32_t(std::min<int64_t>(cs.pairCap, 0xFFFFFFFFll));
     a.preRay = cs.preRay; a.preRec = cs.preRec;
@@ -892,8 +922,8 @@ struct CudaBackend {
     NRT_CUDA(cudaEventRecord(ev.first, stream));
     // per-warp chunk slice + survivor buffer: 2-D bundles 8 rays/lane (40 KiB/CTA, 3 CTAs/SM); GENERAL 4 rays/lane (48 KiB/CTA, 2 CTAs/SM)
     constexpr size_t smBuf = size_t(FT_WARPS) * FT_WB * sizeof(uint2) + FT_WARPS * sizeof(uint32_t);
-    constexpr size_t sm2d = size_t(FT_WARPS) * (FT_TC / 4) * 3 * sizeof(float4) + smBuf;
-    constexpr size_t smGen = size_t(FT_WARPS) * (FT_TC / 4) * 4 * sizeof(float4) + smBuf;
+    constexpr size_t sm2d = size_t(FT_WARPS) * ((FT_TC / 4) * 3 + kSubPerChunk) * sizeof(float4) + smBuf;
+    constexpr size_t smGen = size_t(FT_WARPS) * ((FT_TC / 4) * 4 + kSubPerChunk) * sizeof(float4) + smBuf;
     if (!smemOptIn) {
       NRT_CUDA(cudaFuncSetAttribute(k_mesh_prefilter<FM_GENERAL, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smGen)));
       NRT_CUDA(cudaFuncSetAttribute(k_mesh_prefilter<FM_ORIGIN, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2d)));

@@ -446,13 +446,13 @@ NRT_HD uint32_t mortonKey(const DMesh& m, const double* p0, const double* p1, co
 // because c0m carries the face margin).  A ray that truly hits a face of the chunk lies within
 // d + rho <= R / (1 + 1e-6) of C, and the float32 evaluation of the bound test carries the same
 // margins as a record's, so it passes: culling by the bound never loses a hit.
-NRT_HD void chunkBound(int mode, const float* hot, int64_t ch, float* b) {
+NRT_HD void rangeBound(int mode, const float* hot, int64_t first, int64_t count, float* b) {
   const int nh = hotFloats(mode), dim = (mode == FM_GENERAL) ? 3 : 2, last = nh - 1;
   const double half = (mode == FM_GENERAL) ? 1.0 : 0.5;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   int64_t n = 0;
   bool always = false;
-  for (int64_t r = ch * kRecPad; r < (ch + 1) * kRecPad; ++r) {
+  for (int64_t r = first; r < first + count; ++r) {
     const float k0 = hot[recIndex(r, last, nh)];
     if (k0 <= -1e29f) continue;             // never-hit padding
     if (k0 >= 1e29f) { always = true; break; }
@@ -467,7 +467,7 @@ NRT_HD void chunkBound(int mode, const float* hot, int64_t ch, float* b) {
   // centre of the box around the circles (tighter than their mean for elongated chunks)
   double C[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), dim == 3 ? 0.5 * (lo[2] + hi[2]) : 0.0};
   double R = 0;
-  for (int64_t r = ch * kRecPad; r < (ch + 1) * kRecPad; ++r) {
+  for (int64_t r = first; r < first + count; ++r) {
     const float k0 = hot[recIndex(r, last, nh)];
     if (k0 <= -1e29f) continue;
     double c2 = 0, d2 = 0;
@@ -490,6 +490,13 @@ NRT_HD void chunkBound(int mode, const float* hot, int64_t ch, float* b) {
     b[0] = (float)(2.0 * C[0]); b[1] = (float)(2.0 * C[1]); b[2] = roundUpSigned(k0 + mt);
   }
 }
+
+NRT_HD void chunkBound(int mode, const float* hot, int64_t ch, float* b) { rangeBound(mode, hot, ch * kRecPad, kRecPad, b); }
+// Third level: every chunk is cut into kSubPerChunk runs of kSubRecs consecutive records (sub-patches of
+// the chunk's patch, still in Morton order) with their own bounds; a (ray run, chunk) pair evaluates only
+// the sub-chunks some ray of the run can reach.
+static constexpr int kSubRecs = 16, kSubPerChunk = int(kRecPad) / kSubRecs;
+NRT_HD void subChunkBound(int mode, const float* hot, int64_t sub, float* b) { rangeBound(mode, hot, sub * kSubRecs, kSubRecs, b); }
 
 // Scalar statement of one prefilter test (the CUDA kernel evaluates two records per FFMA2 with
 // exactly these operations per component).  The per-ray constant is kept on the other side of

@@ -26,16 +26,17 @@ namespace nrt {
 
 enum WaveKind { WAVE_PATH = 0, WAVE_SHADOW = 1 };
 
-// Counter block per (wave, mesh object): [EXACT, CAND, NE, then (QUEUE_b, TILE_b, PRE_b, WORK_b) per ray bundle b].
+// Counter block per (wave, mesh object): [EXACT, CAND, NE, then (QUEUE_b, TILE_b, PRE_b, WORK_b, SUB_b) per ray bundle b].
 // Bundle 0 holds arbitrary rays (GENERAL mode; ORIGIN mode for the primary wave, whose rays share
 // the camera origin); bundle 1 + l holds the shadow rays of DistantLight l (DIR mode).
 // NE (mesh object 0's block only): 256-ray blocks of the wave with at least one ray entering a mesh box.
 enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_NE = 2, CNT_BUNDLE0 = 3 };
-NRT_HD int cntStride(int nL) { return CNT_BUNDLE0 + 4 * (1 + nL); }
-NRT_HD int cntQueue(int b) { return CNT_BUNDLE0 + 4 * b; }      // rays queued for the bundle
-NRT_HD int cntTile(int b) { return CNT_BUNDLE0 + 4 * b + 1; }   // prefilter work-item counter
-NRT_HD int cntPre(int b) { return CNT_BUNDLE0 + 4 * b + 2; }    // pre-candidates (prefilter survivors)
-NRT_HD int cntWork(int b) { return CNT_BUNDLE0 + 4 * b + 3; }   // (ray run, chunk) pairs the prefilter evaluated in full
+NRT_HD int cntStride(int nL) { return CNT_BUNDLE0 + 5 * (1 + nL); }
+NRT_HD int cntQueue(int b) { return CNT_BUNDLE0 + 5 * b; }      // rays queued for the bundle
+NRT_HD int cntTile(int b) { return CNT_BUNDLE0 + 5 * b + 1; }   // prefilter work-item counter
+NRT_HD int cntPre(int b) { return CNT_BUNDLE0 + 5 * b + 2; }    // pre-candidates (prefilter survivors)
+NRT_HD int cntWork(int b) { return CNT_BUNDLE0 + 5 * b + 3; }   // (ray run, chunk) pairs admitted by the chunk bounds
+NRT_HD int cntSub(int b) { return CNT_BUNDLE0 + 5 * b + 4; }    // (ray run, sub-chunk) pairs evaluated in full
 // Stats slots
 enum { ST_PRIMARY = 0, ST_TESTS = 1, ST_HITS = 2, ST_RAYS = 3, ST_CAPPED = 4, ST_CONT = 5, ST_COUNT = 8 };
 
@@ -781,14 +782,20 @@ struct BuildRecsDir {
   }
 };
 
-// Chunk bounds of a record set (one element per chunk of the padded record list).
+// Bounds of a record set: elements [0, nch) are the chunk bounds, elements [nch, nch * (1 + kSubPerChunk))
+// the sub-chunk bounds, stored behind them (nch = chunks of the mesh's padded face count).
 struct BuildBounds {
-  int mode; const float* hot; const uint32_t* count; float* bounds;
-  NRT_HD void operator()(int64_t ch) const {
+  int mode; const float* hot; const uint32_t* count; float* bounds; int64_t nch;
+  NRT_HD void operator()(int64_t e) const {
     float b[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ch * kRecPad < paddedFaces(int64_t(*count))) chunkBound(mode, hot, ch, b);
-    else neverHitHot(mode, b);
-    for (int k = 0; k < 4; ++k) bounds[4 * ch + k] = b[k];
+    const int64_t np = paddedFaces(int64_t(*count));
+    if (e < nch) {
+      if (e * kRecPad < np) chunkBound(mode, hot, e, b); else neverHitHot(mode, b);
+    } else {
+      const int64_t sub = e - nch;
+      if (sub * kSubRecs < np) subChunkBound(mode, hot, sub, b); else neverHitHot(mode, b);
+    }
+    for (int k = 0; k < 4; ++k) bounds[4 * e + k] = b[k];
   }
 };
 

@@ -139,7 +139,7 @@ struct SceneData {
       dm.nidx = up(m.normal_idx, m.nfaces * 3, reuse ? const_cast<int64_t*>(old[i].nidx) : nullptr);
       dm.recs = up<float>(nullptr, paddedFaces(m.nfaces) * kFullStride, reuse ? old[i].recs : nullptr);
       dm.hot = up<float>(nullptr, paddedFaces(m.nfaces) * hotFloats(FM_GENERAL), reuse ? old[i].hot : nullptr);
-      dm.bounds = up<float>(nullptr, std::max<int64_t>(1, numChunks(m.nfaces)) * 4, reuse ? old[i].bounds : nullptr);
+      dm.bounds = up<float>(nullptr, std::max<int64_t>(1, numChunks(m.nfaces)) * 4 * (1 + kSubPerChunk), reuse ? old[i].bounds : nullptr);
       dm.order = up<uint32_t>(nullptr, std::max<int64_t>(1, m.nfaces), reuse ? old[i].order : nullptr);
       calcAABB(m.vertices, m.nverts, dm.bmin, dm.bmax);
       double L = 0;
@@ -291,7 +291,7 @@ struct SceneData {
       MoRecs& r = moRecs[mo];
       r.origin = up<float>(nullptr, paddedFaces(nf) * kFullStride, reuse ? oldRecs[mo].origin : nullptr);
       r.originHot = up<float>(nullptr, paddedFaces(nf) * hotFloats(FM_ORIGIN), reuse ? oldRecs[mo].originHot : nullptr);
-      r.originBounds = up<float>(nullptr, std::max<int64_t>(1, numChunks(nf)) * 4, reuse ? oldRecs[mo].originBounds : nullptr);
+      r.originBounds = up<float>(nullptr, std::max<int64_t>(1, numChunks(nf)) * 4 * (1 + kSubPerChunk), reuse ? oldRecs[mo].originBounds : nullptr);
       r.dirBounds.assign(size_t(desc->nlights), nullptr);
       r.dir.assign(size_t(desc->nlights), nullptr);
       r.dirHot.assign(size_t(desc->nlights), nullptr);
@@ -301,7 +301,7 @@ struct SceneData {
         if (lights[l].kind != NRT_LIGHT_DISTANT || !frameValid(mo, FM_DIR, l)) continue;
         r.dir[l] = up<float>(nullptr, paddedFaces(nf) * kFullStride, reuse ? oldRecs[mo].dir[l] : nullptr);
         r.dirHot[l] = up<float>(nullptr, paddedFaces(nf) * hotFloats(FM_DIR), reuse ? oldRecs[mo].dirHot[l] : nullptr);
-        r.dirBounds[l] = up<float>(nullptr, std::max<int64_t>(1, numChunks(nf)) * 4, reuse ? oldRecs[mo].dirBounds[l] : nullptr);
+        r.dirBounds[l] = up<float>(nullptr, std::max<int64_t>(1, numChunks(nf)) * 4 * (1 + kSubPerChunk), reuse ? oldRecs[mo].dirBounds[l] : nullptr);
         if (nf > 0) be->compactRecs(nf, BuildRecsDir{d, mo, l}, r.dir[l], r.dirHot[l], FM_DIR, dRecCount + mo * rs + 2 + l);
       }
     }
@@ -310,10 +310,10 @@ struct SceneData {
       const DMesh& m = meshes[objs[moIndex[mo]].mesh];
       const int64_t nch = numChunks(m.nfaces);
       if (nch == 0) continue;
-      be->forEach(nch, BuildBounds{FM_GENERAL, m.hot, dRecCount + mo * rs, m.bounds});
-      if (frameValid(mo, FM_ORIGIN, 0)) be->forEach(nch, BuildBounds{FM_ORIGIN, moRecs[mo].originHot, dRecCount + mo * rs + 1, moRecs[mo].originBounds});
+      be->forEach(nch * (1 + kSubPerChunk), BuildBounds{FM_GENERAL, m.hot, dRecCount + mo * rs, m.bounds, nch});
+      if (frameValid(mo, FM_ORIGIN, 0)) be->forEach(nch * (1 + kSubPerChunk), BuildBounds{FM_ORIGIN, moRecs[mo].originHot, dRecCount + mo * rs + 1, moRecs[mo].originBounds, nch});
       for (int l = 0; l < desc->nlights; ++l)
-        if (moRecs[mo].dirHot[l]) be->forEach(nch, BuildBounds{FM_DIR, moRecs[mo].dirHot[l], dRecCount + mo * rs + 2 + l, moRecs[mo].dirBounds[l]});
+        if (moRecs[mo].dirHot[l]) be->forEach(nch * (1 + kSubPerChunk), BuildBounds{FM_DIR, moRecs[mo].dirHot[l], dRecCount + mo * rs + 2 + l, moRecs[mo].dirBounds[l], nch});
     }
     be->download(hRecCount.data(), dRecCount, sizeof(uint32_t) * hRecCount.size());
     return NRT_OK;
@@ -416,7 +416,7 @@ struct Renderer {
         // prefilter (hot) -> refine (float32 sign test) per ray bundle; both feed the candidate list of (wave, mo)
         auto run = [&](int mode, int l, int b) {
           preLog.push_back(PreLaunch{wave, mo, b, mode, 0, 0, 0, 0});
-          be->filter(mode, sd.hotOf(mo, mode, l), sd.boundsOf(mo, mode, l), sd.recCountOf(mo, mode, l), cs, mo, b, c);
+          be->filter(mode, sd.hotOf(mo, mode, l), sd.boundsOf(mo, mode, l), sd.boundsOf(mo, mode, l) + 4 * SceneData<BE>::numChunks(m.nfaces), sd.recCountOf(mo, mode, l), cs, mo, b, c);
           be->forEachCounted(c + cntPre(b), cs.preCap,
                              Refine<typename BE::Atom>{cs, mode, sd.recsOf(mo, mode, l), mode == FM_GENERAL ? m.order : nullptr,
                                                        mo, b, c + CNT_CAND});
@@ -549,7 +549,9 @@ struct Renderer {
               // per (ray, chunk); a run is the prefilterRunRays(mode) consecutive queue entries of one warp
               const int64_t nch = SceneData<BE>::numChunks(int64_t(sd.hostRecCount(mo, mode, b > 0 ? b - 1 : 0)));
               const int64_t run = prefilterRunRays(mode), nruns = (q + run - 1) / run;
-              const int64_t t = int64_t(c[cntWork(b)]) * run * kRecPad + nruns * run * nch;
+              // executed tests: chunk bounds (every run x every chunk), sub-chunk bounds of the admitted pairs,
+              // and the records of the admitted sub-chunks
+              const int64_t t = nruns * run * nch + int64_t(c[cntWork(b)]) * run * kSubPerChunk + int64_t(c[cntSub(b)]) * run * kSubRecs;
               pacc.mesh_tests += t; pacc.tests_by_mode[mode] += t;
               queued += q;
             }

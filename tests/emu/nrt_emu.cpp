@@ -121,7 +121,7 @@ struct LoopBackend {
   // Prefilter, two-level like the CUDA kernel: the queue is cut into runs of prefilterRunRays(mode)
   // consecutive rays (one warp's registers); a run evaluates the 256 hot records of a chunk in full
   // iff at least one of its rays passes the chunk's bound test.
-  void filter(int mode, const float* hot, const float* bounds, const uint32_t* count, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
+  void filter(int mode, const float* hot, const float* bounds, const float* sub, const uint32_t* count, const ChunkState& cs, int mo, int b, uint32_t* cnt) {
     const uint32_t nq = cnt[cntQueue(b)];
     const int64_t base = queueBase(cs, mo, b);
     const float* h0 = cs.qhot0 + 4 * base;
@@ -144,15 +144,21 @@ struct LoopBackend {
         for (uint32_t rq = r0; rq < r1 && !any; ++rq) any = prefilterTest(mode, bounds + 4 * ch, rayAt(rq));
         if (!any) continue;
         ++cnt[cntWork(b)];
-        for (uint32_t rq = r0; rq < r1; ++rq) {
-          const HotRay r = rayAt(rq);
-          for (int64_t t = ch * kRecPad; t < (ch + 1) * kRecPad; ++t) {
-            float h[4];
-            for (int k = 0; k < nh; ++k) h[k] = hot[recIndex(t, k, nh)];
-            ++filter_tests;
-            if (prefilterTest(mode, h, r)) {
-              const uint32_t slot = cnt[cntPre(b)]++;
-              if (slot < cs.preCap) { cs.preRay[slot] = rq; cs.preRec[slot] = uint32_t(t); }
+        for (int64_t sb = ch * kSubPerChunk; sb < (ch + 1) * kSubPerChunk; ++sb) {
+          bool anyS = !cull;
+          for (uint32_t rq = r0; rq < r1 && !anyS; ++rq) anyS = prefilterTest(mode, sub + 4 * sb, rayAt(rq));
+          if (!anyS) continue;
+          ++cnt[cntSub(b)];
+          for (uint32_t rq = r0; rq < r1; ++rq) {
+            const HotRay r = rayAt(rq);
+            for (int64_t t = sb * kSubRecs; t < (sb + 1) * kSubRecs; ++t) {
+              float h[4];
+              for (int k = 0; k < nh; ++k) h[k] = hot[recIndex(t, k, nh)];
+              ++filter_tests;
+              if (prefilterTest(mode, h, r)) {
+                const uint32_t slot = cnt[cntPre(b)]++;
+                if (slot < cs.preCap) { cs.preRay[slot] = rq; cs.preRec[slot] = uint32_t(t); }
+              }
             }
           }
         }
