@@ -212,12 +212,13 @@ def _hbm_peak():
         return 6459.0   # the pool's measured copy bandwidth (B200_PROFILING.md fallback)
 
 
-def _traffic(workload_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel launch, from the committed
-    `ncu --set full` capture of this workload (profiles/prefilter_traffic.json); None if not captured."""
+def _traffic(workload_name, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed
+    `ncu --set full` capture of this workload (profiles/kernel_traffic.json); None if not captured."""
     try:
-        with open(os.path.join(ROOT, "profiles", "prefilter_traffic.json")) as f:
-            return json.load(f).get(workload_name, {}).get("dram_bytes_per_launch")
+        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+            tab = json.load(f).get(workload_name, {})
+        return next((v.get("dram_bytes_per_launch") for k, v in tab.items() if kernel.startswith(k)), None)
     except Exception:  # noqa: BLE001
         return None
 
@@ -398,12 +399,12 @@ def main():
         peak = C.c_double(); clk = C.c_double()
         api.check(L.nrt_measure_fp32_peak(C.byref(peak), C.byref(clk)), "nrt_measure_fp32_peak")
         achieved = prof_acc["flops"] / max(prof_acc["mesh_ms"] * 1e-3, 1e-12) / 1e12
-        roofline = {
+        intersection = {
             "bound": "fp32", "kernel": "k_mesh_prefilter", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
             "frac": achieved / peak.value if peak.value > 0 else None,
             "peak_source": "FFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
             "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
-            "traffic": _traffic(args.workload),
+            "traffic": _traffic(args.workload, "k_mesh_prefilter"),
             "flops_per_test": prof_acc["flops"] / max(prof_acc["tests"], 1), "tests_per_step": prof_acc["tests"] / args.steps,
             "ref_tests_per_step": prof_acc["tests_ref"] / args.steps,
             "avg_launch_ms": prof_acc["mesh_ms"] / max(prof_acc["launches"], 1),
@@ -426,8 +427,23 @@ def main():
                 k.update({"bound": "hbm", "algorithmic_bytes": bps * samples, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
             kernels.append(k)
         pre_ms = ktimes.get("k_mesh_prefilter", (0.0, 0))[0]
-        roofline["kernel_share_of_step"] = pre_ms / ksum
-        roofline["share_source"] = "CUDA events around every launch of one untimed frame (nrt_set_kernel_timing); 'kernels' lists every family"
+        intersection["kernel_share_of_step"] = pre_ms / ksum
+        intersection["share_source"] = "CUDA events around every launch of one untimed frame (nrt_set_kernel_timing); 'kernels' lists every family"
+        # `roofline` = the dominant kernel family of the step by measured share
+        dom = kernels[0]
+        if dom["kernel"].startswith("k_mesh_prefilter"):
+            roofline = dict(intersection)
+        else:
+            roofline = {
+                "bound": "hbm", "kernel": dom["kernel"], "achieved": dom.get("achieved_GBps"), "peak": hbm_peak, "unit": "GB/s",
+                "frac": dom.get("frac_of_hbm_peak"), "traffic": _traffic(args.workload, dom["kernel"]),
+                "algorithmic_bytes_per_launch": dom.get("algorithmic_bytes", 0) / max(dom["launches"], 1),
+                "avg_launch_ms": dom["ms"] / max(dom["launches"], 1), "kernel_share_of_step": dom["share"],
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth measured on this pool)",
+                "note": "streaming kernel over the float64 per-sample state; achieved = modelled algorithmic bytes (STATE_BYTES_PER_SAMPLE in "
+                        "bench.py, DESIGN.md section 6) x primary samples / the family's CUDA-event time; the kernel is issue/latency bound "
+                        "below the HBM roofline (profiles/)",
+            }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -438,7 +454,7 @@ def main():
             "frames_per_s": args.steps / (t_ms * 1e-3), "rays_per_frame": total_rays / args.steps,
             "device_ms_per_step": ms_dev.value / args.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(klaunches),
-            "roofline": roofline, "kernels": kernels, "kernel_timing_frame_ms": kframe_ms, "fb_checksum": checksum,
+            "roofline": roofline, "intersection_kernel": intersection, "kernels": kernels, "kernel_timing_frame_ms": kframe_ms, "fb_checksum": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(ds.desc, opts, total_rays / args.steps)
