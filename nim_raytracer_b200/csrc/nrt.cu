@@ -670,6 +670,7 @@ template <class F> struct CatOf { static constexpr int v = KC_OTHER; };
 template <> struct CatOf<GenSimple> { static constexpr int v = KC_GEN; };
 template <> struct CatOf<GenJittered> { static constexpr int v = KC_GEN; };
 template <> struct CatOf<GenGate> { static constexpr int v = KC_GEN; };
+template <> struct CatOf<ShadowGate> { static constexpr int v = KC_GATE_FLAGS; };
 template <> struct CatOf<Shade> { static constexpr int v = KC_SHADE; };
 template <> struct CatOf<ShadowTrace> { static constexpr int v = KC_SHADOW_TRACE; };
 template <> struct CatOf<Resolve> { static constexpr int v = KC_RESOLVE; };

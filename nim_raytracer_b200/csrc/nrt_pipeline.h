@@ -591,6 +591,28 @@ struct GenGate {      // primary rays: position == sample, mult == 1
   }
 };
 
+// Shadow rays: one element per ACTIVE SAMPLE evaluates the gate of its nL shadow rays (positions
+// idx * nL + l): the hit record is loaded once and the shared origin hitW + n * bias is formed once.
+struct ShadowGate {   // gate.kind == WAVE_SHADOW, mult == nL
+  Gate gate; int nMO;
+  template <class E> NRT_HD void operator()(int64_t idx, E& emit) const {
+    const ChunkState& cs = gate.cs;
+    const int64_t s = sampleOf(gate.act, idx);
+    const bool hit = cs.hitObj[s] >= 0;
+    V4 hitW = v4(0.0, 0.0, 0.0, 1.0), o = hitW;
+    if (hit) {
+      hitW = ld4(cs.hitW, cs.S, s);
+      o = add(hitW, scale(ld4(cs.nrm, cs.S, s), gate.fp.bias));   // renderer.nim:98
+    }
+    for (int l = 0; l < cs.nL; ++l) {
+      V4 d = o;
+      if (hit) d = scale(getShadingInfo(gate.sc->lights[l], hitW).lightDir, -1.0);   // renderer.nim:99
+      for (int mo = 0; mo < nMO; ++mo)
+        emit(l, mo, hit ? gateCode(gate.evalRay(o, d, uint32_t(s * cs.nL + l), mo, l)) : uint8_t(0));
+    }
+  }
+};
+
 // ---- shadow trace: one element per shadow ray (active sample i / nL, light i % nL): the trace()
 // call of renderer.nim:101-102; only "some object hit before the light" is kept (renderer.nim:103)
 struct ShadowTrace {

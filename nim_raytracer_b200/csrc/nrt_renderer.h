@@ -337,6 +337,7 @@ struct Renderer {
   int32_t* dRows = nullptr;
   ProfileAcc prof;
   int64_t launches_hint = 0;
+  bool shadowGatePerSample = envInt("NRT_SHADOW_GATE_PER_SAMPLE", 1) != 0;
   // one entry per prefilter launch of the last frame, in launch order (NRT_TRACE_PREFILTER)
   struct PreLaunch { int wave, mo, b, mode; int64_t rays, work, pre, nch; };
   std::vector<PreLaunch> preLog;
@@ -407,6 +408,10 @@ struct Renderer {
     const int mult = (kind == WAVE_SHADOW) ? nL : 1;
     const Gate g = makeGate(sd, fp, kind, act, bounce, force_exact);
     if (gated) be->gateFinish(g, act.n * mult, nMO, cnt);
+    else if (kind == WAVE_SHADOW && shadowGatePerSample) {
+      be->produceGate(act.n, nL, ShadowGate{g, nMO}, cs, nMO, cnt, nullptr);
+      be->gateFinish(g, act.n * mult, nMO, cnt);
+    }
     else be->gate(g, nullptr, act.n * mult, mult, nMO, cnt);
     for (int mo = 0; mo < nMO; ++mo) {
       uint32_t* c = cnt + mo * cst;

@@ -112,7 +112,7 @@ struct LoopBackend {
   }
   // fused producer + gate flags: here the producer runs first and the ordinary gate follows
   struct NoEmit { void operator()(int, int, uint8_t) const {} };
-  void produceGate(int64_t n, int, const GenGate& p, const ChunkState&, int, uint32_t*, unsigned long long*) {
+  template <class P> void produceGate(int64_t n, int, const P& p, const ChunkState&, int, uint32_t*, unsigned long long*) {
     NoEmit e;
     for (int64_t i = 0; i < n; ++i) p(i, e);
     ++launches;
