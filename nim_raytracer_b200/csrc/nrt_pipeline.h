@@ -634,6 +634,27 @@ struct ShadowTrace {
   }
 };
 
+// The same per ACTIVE SAMPLE: its nL shadow rays share the loads of the hit record and the origin.
+struct ShadowTraceSample {
+  const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
+  NRT_HD StatDelta operator()(int64_t idx) const {
+    StatDelta st = zeroStats();
+    if (idx >= activeN(act)) return st;
+    const int64_t s = sampleOf(act, idx);
+    if (cs.hitObj[s] < 0) return st;
+    const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
+    const V4 so = add(hitW, scale(n, fp.bias));                                   // renderer.nim:98
+    for (int l = 0; l < cs.nL; ++l) {
+      const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
+      const V4 sd = scale(li.lightDir, -1.0);                                      // renderer.nim:99
+      const TraceOut tr = traceObjects(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx * cs.nL + l);
+      st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
+      cs.occ[s * cs.nL + l] = tr.obj >= 0 ? 1 : 0;
+    }
+    return st;
+  }
+};
+
 // ---- resolve: shadeDiffuse of the unoccluded lights + reflection set-up (renderer.nim:90-127)
 // Samples whose path continues keep active == 1; the backend compacts them IN SAMPLE ORDER into
 // the next bounce's active list (compactActive), so reflection rays of neighbouring pixels stay

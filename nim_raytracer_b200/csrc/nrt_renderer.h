@@ -338,6 +338,7 @@ struct Renderer {
   ProfileAcc prof;
   int64_t launches_hint = 0;
   bool shadowGatePerSample = envInt("NRT_SHADOW_GATE_PER_SAMPLE", 1) != 0;
+  bool shadowTracePerSample = envInt("NRT_SHADOW_TRACE_PER_SAMPLE", 1) != 0;
   // one entry per prefilter launch of the last frame, in launch order (NRT_TRACE_PREFILTER)
   struct PreLaunch { int wave, mo, b, mode; int64_t rays, work, pre, nch; };
   std::vector<PreLaunch> preLog;
@@ -521,7 +522,10 @@ struct Renderer {
           be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act, bounce}, cs.stats);
           if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, bounce, force_exact, false);
           ++wave;
-          if (nL > 0) be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
+          if (nL > 0) {
+            if (shadowTracePerSample) be->forEachStats(nullptr, act.n, ShadowTraceSample{sd.d, fp, cs, act}, cs.stats);
+            else be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
+          }
           be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act, bounce}, cs.stats);
           if (bounce >= maxBounces) break;
           be->compactActive(cs, act, nextList, nextCount);
