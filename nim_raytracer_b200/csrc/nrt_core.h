@@ -21,6 +21,14 @@
 #define NRT_HD inline
 #endif
 
+// Keeps a loaded value materialised where it is written (the compiler would otherwise sink the load
+// below the branch that decides whether it is needed, serialising two memory round trips).
+#if defined(__CUDA_ARCH__)
+#define NRT_KEEP_D(x) asm volatile("" : "+d"(x))
+#else
+#define NRT_KEEP_D(x) ((void)0)
+#endif
+
 namespace nrt {
 
 // ---------------------------------------------------------------- constants --

@@ -455,6 +455,8 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
   const bool f32ok = (o.w == 1.0) && (d.w == 0.0) && finite3(o) && finite3(d);
   const bool fastRay = f32ok && d.x != 0.0 && d.y != 0.0 && d.z != 0.0;
   const RayF rf = makeRayF(o, d);
+  // the gate code of the first mesh object is requested now: its latency overlaps the float32 pass below
+  const uint8_t code0 = (cs.nMO > 0) ? cs.gflag[pos] : uint8_t(0);
   // Two phases per batch of 32 objects, both in list order: a branch-free float32 pass marks the
   // objects that are not certain misses (most (ray, sphere) pairs miss by far); the float64
   // evaluation of the reference then runs for the marked ones only.
@@ -470,7 +472,10 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
         if (c.r2m < 3.0e38f) m = f32ok && certainMissF(c, rf);
         else {
           const uint32_t tag = fbits(c.tx);
-          if (tag == COF_MESH) m = cs.gflag[int64_t(fbits(c.ty)) * cs.NR + pos] == 0;   // the ray did not enter the mesh's box
+          if (tag == COF_MESH) {   // code 0: the ray did not enter the mesh's box
+            const uint32_t mo = fbits(c.ty);
+            m = (mo == 0 ? code0 : cs.gflag[int64_t(mo) * cs.NR + pos]) == 0;
+          }
           else m = (tag == COF_PLANE) && f32ok && planeMissF(c, rf);
         }
         miss |= uint32_t(m) << j;
@@ -529,8 +534,11 @@ struct Shade {
     out.hit = false; out.s = 0;
     if (idx >= activeN(act)) return st;
     const int64_t s = sampleOf(act, idx);
-    if (!cs.active[s]) { cs.hitObj[s] = -1; return st; }
-    const V4 o = (bounce == 0) ? primaryOrigin(*sc) : ld4(cs.rayO, cs.S, s), d = ld4(cs.rayD, cs.S, s);
+    // (the ray is loaded before the activity flag is looked at: both requests are in flight together)
+    const V4 d = ld4(cs.rayD, cs.S, s);
+    const uint8_t alive = cs.active[s];
+    const V4 o = (bounce == 0) ? primaryOrigin(*sc) : ld4(cs.rayO, cs.S, s);
+    if (!alive) { cs.hitObj[s] = -1; return st; }
     const TraceOut tr = traceObjects(*sc, cs, o, d, NRT_INF, s, idx);
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     if (bounce == 0) {
@@ -598,12 +606,13 @@ struct ShadowGate {   // gate.kind == WAVE_SHADOW, mult == nL
   template <class E> NRT_HD void operator()(int64_t idx, E& emit) const {
     const ChunkState& cs = gate.cs;
     const int64_t s = sampleOf(gate.act, idx);
+    // (hit record requested together with the hit flag: one memory round trip instead of two)
+    V4 hitW = ld4(cs.hitW, cs.S, s), nrm = ld4(cs.nrm, cs.S, s);
     const bool hit = cs.hitObj[s] >= 0;
-    V4 hitW = v4(0.0, 0.0, 0.0, 1.0), o = hitW;
-    if (hit) {
-      hitW = ld4(cs.hitW, cs.S, s);
-      o = add(hitW, scale(ld4(cs.nrm, cs.S, s), gate.fp.bias));   // renderer.nim:98
-    }
+    NRT_KEEP_D(hitW.x); NRT_KEEP_D(hitW.y); NRT_KEEP_D(hitW.z); NRT_KEEP_D(hitW.w);
+    NRT_KEEP_D(nrm.x); NRT_KEEP_D(nrm.y); NRT_KEEP_D(nrm.z); NRT_KEEP_D(nrm.w);
+    V4 o = hitW;
+    if (hit) o = add(hitW, scale(nrm, gate.fp.bias));   // renderer.nim:98
     for (int l = 0; l < cs.nL; ++l) {
       V4 d = o;
       if (hit) d = scale(getShadingInfo(gate.sc->lights[l], hitW).lightDir, -1.0);   // renderer.nim:99
@@ -641,8 +650,12 @@ struct ShadowTraceSample {
     StatDelta st = zeroStats();
     if (idx >= activeN(act)) return st;
     const int64_t s = sampleOf(act, idx);
-    if (cs.hitObj[s] < 0) return st;
-    const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
+    // (hit record requested together with the hit flag: one memory round trip instead of two)
+    V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
+    const int32_t ho = cs.hitObj[s];
+    NRT_KEEP_D(hitW.x); NRT_KEEP_D(hitW.y); NRT_KEEP_D(hitW.z); NRT_KEEP_D(hitW.w);
+    NRT_KEEP_D(n.x); NRT_KEEP_D(n.y); NRT_KEEP_D(n.z); NRT_KEEP_D(n.w);
+    if (ho < 0) return st;
     const V4 so = add(hitW, scale(n, fp.bias));                                   // renderer.nim:98
     for (int l = 0; l < cs.nL; ++l) {
       const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
@@ -665,10 +678,13 @@ struct Resolve {
     StatDelta st = zeroStats();
     if (idx >= activeN(act)) return st;
     const int64_t s = sampleOf(act, idx);
+    // (hit record requested together with the hit flag: one memory round trip instead of two)
+    V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
     const int objHit = cs.hitObj[s];
+    NRT_KEEP_D(hitW.x); NRT_KEEP_D(hitW.y); NRT_KEEP_D(hitW.z); NRT_KEEP_D(hitW.w);
+    NRT_KEEP_D(n.x); NRT_KEEP_D(n.y); NRT_KEEP_D(n.z); NRT_KEEP_D(n.w);
     if (objHit < 0) return st;
     const DObject& ob = sc->objects[objHit];
-    const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
     V3 local = v3(0.0, 0.0, 0.0);
     for (int l = 0; l < cs.nL; ++l) {
       if (cs.occ[s * cs.nL + l]) continue;
