@@ -448,15 +448,14 @@ struct Verify2 {  // among candidates attaining the minimum, the lowest face ind
 struct TraceOut { int obj; double t; uint32_t tri; int tests, hits; };
 // `pos` = wave position of the ray (index of its gate code): a ray that did not enter a mesh's box
 // (code 0) has t = NegInf for that mesh without touching the per-ray mesh results.
-NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d, double tNear, int64_t wi, int64_t pos) {
+// `code0` = gate code of the ray for mesh object 0, loaded by the caller together with its other inputs.
+NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d, double tNear, int64_t wi, int64_t pos, uint8_t code0) {
   TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
   // the exact shortcut of toObject() for [I | t] matrices applies to this ray?  (zero components
   // need toObject()'s per-component treatment)
   const bool f32ok = (o.w == 1.0) && (d.w == 0.0) && finite3(o) && finite3(d);
   const bool fastRay = f32ok && d.x != 0.0 && d.y != 0.0 && d.z != 0.0;
   const RayF rf = makeRayF(o, d);
-  // the gate code of the first mesh object is requested now: its latency overlaps the float32 pass below
-  const uint8_t code0 = (cs.nMO > 0) ? cs.gflag[pos] : uint8_t(0);
   // Two phases per batch of 32 objects, both in list order: a branch-free float32 pass marks the
   // objects that are not certain misses (most (ray, sphere) pairs miss by far); the float64
   // evaluation of the reference then runs for the marked ones only.
@@ -536,10 +535,10 @@ struct Shade {
     const int64_t s = sampleOf(act, idx);
     // (the ray is loaded before the activity flag is looked at: both requests are in flight together)
     const V4 d = ld4(cs.rayD, cs.S, s);
-    const uint8_t alive = cs.active[s];
+    const uint8_t alive = cs.active[s], code0 = (cs.nMO > 0) ? cs.gflag[idx] : uint8_t(0);
     const V4 o = (bounce == 0) ? primaryOrigin(*sc) : ld4(cs.rayO, cs.S, s);
     if (!alive) { cs.hitObj[s] = -1; return st; }
-    const TraceOut tr = traceObjects(*sc, cs, o, d, NRT_INF, s, idx);
+    const TraceOut tr = traceObjects(*sc, cs, o, d, NRT_INF, s, idx, code0);
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     if (bounce == 0) {
       st.v[ST_PRIMARY] = 1;
@@ -636,7 +635,7 @@ struct ShadowTrace {
     const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
     const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
     const V4 so = add(hitW, scale(n, fp.bias)), sd = scale(li.lightDir, -1.0);   // renderer.nim:98-99
-    const TraceOut tr = traceObjects(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx);
+    const TraceOut tr = traceObjects(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx, (cs.nMO > 0) ? cs.gflag[idx] : uint8_t(0));
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     cs.occ[s * cs.nL + l] = tr.obj >= 0 ? 1 : 0;
     return st;
@@ -653,6 +652,9 @@ struct ShadowTraceSample {
     // (hit record requested together with the hit flag: one memory round trip instead of two)
     V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
     const int32_t ho = cs.hitObj[s];
+    uint32_t codes = 0;   // gate codes (mesh object 0) of the first four lights, requested with the hit record
+    if (cs.nMO > 0)
+      for (int l = 0; l < cs.nL && l < 4; ++l) codes |= uint32_t(cs.gflag[idx * cs.nL + l]) << (8 * l);
     NRT_KEEP_D(hitW.x); NRT_KEEP_D(hitW.y); NRT_KEEP_D(hitW.z); NRT_KEEP_D(hitW.w);
     NRT_KEEP_D(n.x); NRT_KEEP_D(n.y); NRT_KEEP_D(n.z); NRT_KEEP_D(n.w);
     if (ho < 0) return st;
@@ -660,7 +662,8 @@ struct ShadowTraceSample {
     for (int l = 0; l < cs.nL; ++l) {
       const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
       const V4 sd = scale(li.lightDir, -1.0);                                      // renderer.nim:99
-      const TraceOut tr = traceObjects(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx * cs.nL + l);
+      const uint8_t code0 = (l < 4) ? uint8_t(codes >> (8 * l)) : ((cs.nMO > 0) ? cs.gflag[idx * cs.nL + l] : uint8_t(0));
+      const TraceOut tr = traceObjects(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx * cs.nL + l, code0);
       st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
       cs.occ[s * cs.nL + l] = tr.obj >= 0 ? 1 : 0;
     }
