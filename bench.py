@@ -49,6 +49,12 @@ def workload(name: str):
     if name == "config4":
         o = api.Options(3840, 2160, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
         return scenes.bunny_spheres(), o, "bunny + 7 spheres, 3840x2160, 16 spp grid, depth 8 (BASELINE config 4)"
+    if name == "config5":   # synthetic stress: 1M random triangles as one mesh + 10k spheres (10 % mirrors), 64 spp
+        o = api.Options(3840, 2160, antialias=api.Antialias(api.akGrid, 8), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+        return scenes.stress(), o, "1M random triangles + 10k spheres + plane, 3840x2160, 64 spp grid, depth 8 (BASELINE config 5)"
+    if name == "config5s":  # the same scene at 1/4 linear resolution and 16 spp (1/64 of the samples)
+        o = api.Options(960, 540, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+        return scenes.stress(), o, "1M random triangles + 10k spheres + plane, 960x540, 16 spp grid, depth 8 (BASELINE config 5 scene, 1/64 of its samples)"
     if name == "config1":
         return scenes.spheres_reflection(), api.Options(640, 480), "spheres-reflection.nim 640x480, 1 spp (BASELINE config 1)"
     if name == "tiny":  # CI-sized

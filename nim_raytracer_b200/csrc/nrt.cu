@@ -88,8 +88,8 @@ __device__ __forceinline__ void blockStatsAdd(const StatDelta& d, unsigned long 
 // resident CTAs per SM the register allocation aims at (measured on B200: see DESIGN.md)
 template <class F> struct MinBlocks { static constexpr int v = NRT_OCC_DEFAULT; };
 template <> struct MinBlocks<ShadowTrace> { static constexpr int v = NRT_OCC_ST; };
-template <> struct MinBlocks<ShadowTraceSample> { static constexpr int v = NRT_OCC_ST; };
-template <> struct MinBlocks<Shade> { static constexpr int v = NRT_OCC_SHADE; };
+template <bool CL> struct MinBlocks<ShadowTraceSampleT<CL>> { static constexpr int v = NRT_OCC_ST; };
+template <bool CL> struct MinBlocks<ShadeT<CL>> { static constexpr int v = NRT_OCC_SHADE; };
 template <class F>
 __global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats(F f, int64_t n, unsigned long long* stats) {
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
@@ -672,9 +672,9 @@ template <> struct CatOf<GenSimple> { static constexpr int v = KC_GEN; };
 template <> struct CatOf<GenJittered> { static constexpr int v = KC_GEN; };
 template <> struct CatOf<GenGate> { static constexpr int v = KC_GEN; };
 template <> struct CatOf<ShadowGate> { static constexpr int v = KC_GATE_FLAGS; };
-template <> struct CatOf<Shade> { static constexpr int v = KC_SHADE; };
+template <bool CL> struct CatOf<ShadeT<CL>> { static constexpr int v = KC_SHADE; };
 template <> struct CatOf<ShadowTrace> { static constexpr int v = KC_SHADOW_TRACE; };
-template <> struct CatOf<ShadowTraceSample> { static constexpr int v = KC_SHADOW_TRACE; };
+template <bool CL> struct CatOf<ShadowTraceSampleT<CL>> { static constexpr int v = KC_SHADOW_TRACE; };
 template <> struct CatOf<Resolve> { static constexpr int v = KC_RESOLVE; };
 template <> struct CatOf<Finalize> { static constexpr int v = KC_FINALIZE; };
 template <> struct CatOf<ExactMesh> { static constexpr int v = KC_EXACT; };

@@ -133,6 +133,10 @@ NRT_HD CObjF loadCObjF(const CObjF* p) {
 #endif
 }
 
+static constexpr int kClusterSize = 16;    // members per level-2 cluster, level-2 clusters per level-1 cluster
+static constexpr int kClusterMin = 64;     // fewer clusterable spheres than this: flat scan
+static constexpr int kSurvivorCap = 24;    // per-ray list of objects that need the float64 evaluation
+
 struct DLight {
   int32_t kind;
   int32_t _pad;
@@ -166,6 +170,15 @@ struct DScene {
   const DObject* objects;
   const CObj* cobjs;              // compact mirror of objects[] for the object scan
   const CObjF* cobjf;             // float32 mirror (first look at spheres)
+  // Sphere clusters (scenes with many spheres): the spheres the float32 test applies to, in Morton order
+  // of their centres, as groups of kClusterSize (level 2) inside groups of kClusterSize^2 (level 1),
+  // every group with a bounding sphere in CObjF form (tx,ty,tz = -centre).  ncl1 == 0: not built.
+  const CObjF* cl1;               // ncl1 level-1 bounds
+  const CObjF* cl2;               // ncl1 * kClusterSize level-2 bounds (padding: never-hit)
+  const CObjF* clm;               // ncl1 * kClusterSize^2 member records (padding: never-hit)
+  const uint32_t* clmIdx;         // object index of every member
+  const uint32_t* slowIdx;        // the objects that are not cluster members, ascending
+  int32_t ncl1, nslow;
   const DLight* lights;
   const DMesh* meshes;
   const int32_t* mesh_obj_index;  // mesh object k -> object index

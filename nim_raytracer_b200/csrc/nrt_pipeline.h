@@ -446,9 +446,59 @@ struct Verify2 {  // among candidates attaining the minimum, the lowest face ind
 
 // trace(): renderer.nim:47-67 with the mesh results looked up.  `wi` = wave-ray index.
 struct TraceOut { int obj; double t; uint32_t tri; int tests, hits; };
+
+// float64 evaluation of object i for trace(): the reference's intersect() (or the mesh result), then the
+// running-minimum update of renderer.nim:60-65
+NRT_HD void evalObject(const DScene& sc, const ChunkState& cs, int i, V4 o, V4 d, bool fastRay, int64_t wi, int64_t pos, TraceOut& r) {
+  const CObj c = loadCObj(sc.cobjs + i);
+  double t; uint32_t tri = kNoTri;
+  if (c.kind == GEOM_MESH) {
+    t = NRT_NEG_INF;
+    if (cs.gflag[int64_t(c.mesh_obj) * cs.NR + pos]) {
+      t = bitsd(cs.tBest[int64_t(c.mesh_obj) * cs.NR + wi]);
+      tri = cs.triBest[int64_t(c.mesh_obj) * cs.NR + wi];
+    }
+  } else {
+    V4 oo, dd;
+    if (c.xlate_only && fastRay && (o.x != 0.0 || c.t[0] != 0.0) && (o.y != 0.0 || c.t[1] != 0.0) && (o.z != 0.0 || c.t[2] != 0.0)) {
+      oo = v4(o.x + c.t[0], o.y + c.t[1], o.z + c.t[2], 1.0);
+      dd = v4(d.x, d.y, d.z, 0.0);
+    } else {
+      toObject(sc.objects[i], o, d, oo, dd);
+    }
+    // initRay's 1/dir (geom.nim:42-47) is only read by the AABB test: built for boxes only
+    // spheres: a tighter float32 discriminant bound on the float64 object-space ray first; planes: orig.y and
+    // dir.y of equal sign give t < 0, which trace() rejects (renderer.nim:60) whatever its value
+    if (c.kind == GEOM_SPHERE) t = sphereCertainMiss(c.radius, oo, dd) ? NRT_NEG_INF : sphereIntersect(c.radius, oo, dd);
+    else if (c.kind == GEOM_PLANE) {
+      // (bounded magnitudes: the quotient cannot underflow to -0.0, which `t >= 0` would accept)
+      const bool neg = ((oo.y > 1e-150 && dd.y > 1e-6) || (oo.y < -1e-150 && dd.y < -1e-6)) && fabs(oo.y) < 1e150 && fabs(dd.y) < 1e150;
+      t = neg ? NRT_NEG_INF : planeIntersect(oo, dd);
+    }
+    else if (c.kind == GEOM_BOX) t = aabbIntersect(sc.objects[i].bmin, sc.objects[i].bmax, initRay(oo, dd));
+    else t = NRT_NEG_INF;
+  }
+  if (t >= 0 && t < r.t) { r.t = t; r.obj = i; r.tri = tri; r.hits++; }
+}
+
+// float32 first look at object i (record c): true = the reference's intersect() certainly returns a
+// value trace() rejects (NegInf or t < 0), so the object is skipped (it is still counted in Stats)
+NRT_HD bool firstLookMiss(const ChunkState& cs, const CObjF& c, const RayF& rf, bool f32ok, int64_t pos, uint8_t code0) {
+  if (c.r2m < 3.0e38f) return f32ok && certainMissF(c, rf);
+  const uint32_t tag = fbits(c.tx);
+  if (tag == COF_MESH) {   // code 0: the ray did not enter the mesh's box
+    const uint32_t mo = fbits(c.ty);
+    return (mo == 0 ? code0 : cs.gflag[int64_t(mo) * cs.NR + pos]) == 0;
+  }
+  return (tag == COF_PLANE) && f32ok && planeMissF(c, rf);
+}
+
 // `pos` = wave position of the ray (index of its gate code): a ray that did not enter a mesh's box
 // (code 0) has t = NegInf for that mesh without touching the per-ray mesh results.
 // `code0` = gate code of the ray for mesh object 0, loaded by the caller together with its other inputs.
+// CL: the scene has sphere clusters (the host picks the kernel variant, so that the flat scan of small
+// scenes keeps its register budget).
+template <bool CL>
 NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d, double tNear, int64_t wi, int64_t pos, uint8_t code0) {
   TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
   // the exact shortcut of toObject() for [I | t] matrices applies to this ray?  (zero components
@@ -456,6 +506,40 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
   const bool f32ok = (o.w == 1.0) && (d.w == 0.0) && finite3(o) && finite3(d);
   const bool fastRay = f32ok && d.x != 0.0 && d.y != 0.0 && d.z != 0.0;
   const RayF rf = makeRayF(o, d);
+  if (CL && sc.ncl1 > 0 && f32ok) {
+    // Scenes with many spheres: a flattened two-level traversal of the sphere clusters.  A ray that
+    // certainly misses a cluster's bounding sphere certainly misses every member, so whole groups of
+    // 256 and 16 spheres are skipped; the objects that are not certain misses are collected in a small
+    // list kept in LIST ORDER (renderer.nim:53: the in-order scan decides ties and Stats) and evaluated
+    // in float64 afterwards.  A full list falls back to the flat in-order scan below.
+    uint32_t surv[kSurvivorCap];
+    int ns = 0;
+    bool full = false;
+    auto push = [&](uint32_t i) {
+      if (i == kInvalidRef) return;   // padding slot of a cluster
+      if (ns == kSurvivorCap) { full = true; return; }
+      int k = ns++;
+      while (k > 0 && surv[k - 1] > i) { surv[k] = surv[k - 1]; --k; }
+      surv[k] = i;
+    };
+    for (int a1 = 0; a1 < sc.ncl1 && !full; ++a1) {
+      if (certainMissF(loadCObjF(sc.cl1 + a1), rf)) continue;
+      for (int a2 = a1 * kClusterSize; a2 < (a1 + 1) * kClusterSize && !full; ++a2) {
+        if (certainMissF(loadCObjF(sc.cl2 + a2), rf)) continue;
+        for (int m = a2 * kClusterSize; m < (a2 + 1) * kClusterSize; ++m)
+          if (!certainMissF(loadCObjF(sc.clm + m), rf)) push(sc.clmIdx[m]);
+      }
+    }
+    for (int k = 0; k < sc.nslow && !full; ++k) {
+      const uint32_t i = sc.slowIdx[k];
+      if (!firstLookMiss(cs, loadCObjF(sc.cobjf + i), rf, f32ok, pos, code0)) push(i);
+    }
+    if (!full) {
+      r.tests = sc.nobjects;
+      for (int k = 0; k < ns; ++k) evalObject(sc, cs, int(surv[k]), o, d, fastRay, wi, pos, r);
+      return r;
+    }
+  }
   // Two phases per batch of 32 objects, both in list order: a branch-free float32 pass marks the
   // objects that are not certain misses (most (ray, sphere) pairs miss by far); the float64
   // evaluation of the reference then runs for the marked ones only.
@@ -465,56 +549,15 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
     {
       uint32_t miss = 0;
 #pragma unroll 4
-      for (int j = 0; j < nb; ++j) {
-        const CObjF c = loadCObjF(sc.cobjf + base + j);   // the same record for every lane: the branches are uniform
-        bool m;
-        if (c.r2m < 3.0e38f) m = f32ok && certainMissF(c, rf);
-        else {
-          const uint32_t tag = fbits(c.tx);
-          if (tag == COF_MESH) {   // code 0: the ray did not enter the mesh's box
-            const uint32_t mo = fbits(c.ty);
-            m = (mo == 0 ? code0 : cs.gflag[int64_t(mo) * cs.NR + pos]) == 0;
-          }
-          else m = (tag == COF_PLANE) && f32ok && planeMissF(c, rf);
-        }
-        miss |= uint32_t(m) << j;
-      }
+      for (int j = 0; j < nb; ++j)   // the same record for every lane: the branches inside are uniform
+        miss |= uint32_t(firstLookMiss(cs, loadCObjF(sc.cobjf + base + j), rf, f32ok, pos, code0)) << j;
       need &= ~miss;
     }
     r.tests += nb;
     while (need) {
-    const int i = base + (__builtin_ffs(int(need)) - 1);
-    need &= need - 1;
-    const CObj c = loadCObj(sc.cobjs + i);
-    double t; uint32_t tri = kNoTri;
-    if (c.kind == GEOM_MESH) {
-      t = NRT_NEG_INF;
-      if (cs.gflag[int64_t(c.mesh_obj) * cs.NR + pos]) {
-        t = bitsd(cs.tBest[int64_t(c.mesh_obj) * cs.NR + wi]);
-        tri = cs.triBest[int64_t(c.mesh_obj) * cs.NR + wi];
-      }
-    } else {
-      V4 oo, dd;
-      if (c.xlate_only && fastRay && (o.x != 0.0 || c.t[0] != 0.0) && (o.y != 0.0 || c.t[1] != 0.0) && (o.z != 0.0 || c.t[2] != 0.0)) {
-        oo = v4(o.x + c.t[0], o.y + c.t[1], o.z + c.t[2], 1.0);
-        dd = v4(d.x, d.y, d.z, 0.0);
-      } else {
-        toObject(sc.objects[i], o, d, oo, dd);
-      }
-      // initRay's 1/dir (geom.nim:42-47) is only read by the AABB test: built for boxes only
-      // spheres: most rays miss by far — a float32 discriminant bound proves delta < 0 (=> NegInf) without
-      // the float64 evaluation; planes: orig.y and dir.y of equal sign give t < 0, which trace() rejects
-      // (renderer.nim:60) whatever its value, so the division is skipped
-      if (c.kind == GEOM_SPHERE) t = sphereCertainMiss(c.radius, oo, dd) ? NRT_NEG_INF : sphereIntersect(c.radius, oo, dd);
-      else if (c.kind == GEOM_PLANE) {
-        // (bounded magnitudes: the quotient cannot underflow to -0.0, which `t >= 0` would accept)
-        const bool neg = ((oo.y > 1e-150 && dd.y > 1e-6) || (oo.y < -1e-150 && dd.y < -1e-6)) && fabs(oo.y) < 1e150 && fabs(dd.y) < 1e150;
-        t = neg ? NRT_NEG_INF : planeIntersect(oo, dd);
-      }
-      else if (c.kind == GEOM_BOX) t = aabbIntersect(sc.objects[i].bmin, sc.objects[i].bmax, initRay(oo, dd));
-      else t = NRT_NEG_INF;
-    }
-    if (t >= 0 && t < r.t) { r.t = t; r.obj = i; r.tri = tri; r.hits++; }
+      const int i = base + (__builtin_ffs(int(need)) - 1);
+      need &= need - 1;
+      evalObject(sc, cs, i, o, d, fastRay, wi, pos, r);
     }
   }
   return r;
@@ -525,7 +568,8 @@ NRT_HD StatDelta zeroStats() { StatDelta s; for (int i = 0; i < ST_COUNT; ++i) s
 
 // ---- shade: nearest hit of the path ray, hit point and normal (renderer.nim:71-88)
 struct ShadeOut { bool hit; int64_t s; V4 hitW, n; };
-struct Shade {
+template <bool CL>
+struct ShadeT {
   const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce;
   NRT_HD StatDelta operator()(int64_t idx) const { ShadeOut out; return run(idx, out); }
   NRT_HD StatDelta run(int64_t idx, ShadeOut& out) const {
@@ -538,7 +582,7 @@ struct Shade {
     const uint8_t alive = cs.active[s], code0 = (cs.nMO > 0) ? cs.gflag[idx] : uint8_t(0);
     const V4 o = (bounce == 0) ? primaryOrigin(*sc) : ld4(cs.rayO, cs.S, s);
     if (!alive) { cs.hitObj[s] = -1; return st; }
-    const TraceOut tr = traceObjects(*sc, cs, o, d, NRT_INF, s, idx, code0);
+    const TraceOut tr = traceObjects<CL>(*sc, cs, o, d, NRT_INF, s, idx, code0);
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     if (bounce == 0) {
       st.v[ST_PRIMARY] = 1;
@@ -583,6 +627,9 @@ struct Shade {
     return st;
   }
 };
+
+using Shade = ShadeT<false>;
+using ShadeClustered = ShadeT<true>;
 
 // ---- fused producer: the kernel that creates the primary rays also evaluates their gate codes while
 // the rays are in registers (the CUDA backend counts the codes per 256-position block in the same
@@ -635,7 +682,7 @@ struct ShadowTrace {
     const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
     const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
     const V4 so = add(hitW, scale(n, fp.bias)), sd = scale(li.lightDir, -1.0);   // renderer.nim:98-99
-    const TraceOut tr = traceObjects(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx, (cs.nMO > 0) ? cs.gflag[idx] : uint8_t(0));
+    const TraceOut tr = traceObjects<false>(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx, (cs.nMO > 0) ? cs.gflag[idx] : uint8_t(0));
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     cs.occ[s * cs.nL + l] = tr.obj >= 0 ? 1 : 0;
     return st;
@@ -643,7 +690,8 @@ struct ShadowTrace {
 };
 
 // The same per ACTIVE SAMPLE: its nL shadow rays share the loads of the hit record and the origin.
-struct ShadowTraceSample {
+template <bool CL>
+struct ShadowTraceSampleT {
   const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
   NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
@@ -663,13 +711,16 @@ struct ShadowTraceSample {
       const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
       const V4 sd = scale(li.lightDir, -1.0);                                      // renderer.nim:99
       const uint8_t code0 = (l < 4) ? uint8_t(codes >> (8 * l)) : ((cs.nMO > 0) ? cs.gflag[idx * cs.nL + l] : uint8_t(0));
-      const TraceOut tr = traceObjects(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx * cs.nL + l, code0);
+      const TraceOut tr = traceObjects<CL>(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx * cs.nL + l, code0);
       st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
       cs.occ[s * cs.nL + l] = tr.obj >= 0 ? 1 : 0;
     }
     return st;
   }
 };
+
+using ShadowTraceSample = ShadowTraceSampleT<false>;
+using ShadowTraceSampleClustered = ShadowTraceSampleT<true>;
 
 // ---- resolve: shadeDiffuse of the unoccluded lights + reflection set-up (renderer.nim:90-127)
 // Samples whose path continues keep active == 1; the backend compacts them IN SAMPLE ORDER into

@@ -5,6 +5,7 @@
 #pragma once
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -37,6 +38,9 @@ struct SceneData {
   std::vector<int32_t> moIndex;
   std::vector<CObj> cobjs; CObj* dCObjs = nullptr;
   std::vector<CObjF> cobjf; CObjF* dCObjF = nullptr;
+  // sphere clusters (see DScene): device copies are re-allocated when a scene update changes their sizes
+  CObjF *dCl1 = nullptr, *dCl2 = nullptr, *dClm = nullptr; uint32_t *dClmIdx = nullptr, *dSlowIdx = nullptr;
+  int64_t capCl1 = 0, capSlow = 0;
   DObject* dObjs = nullptr; DLight* dLights = nullptr; DMesh* dMeshes = nullptr; int32_t* dMo = nullptr;
   std::vector<void*> owned;
   bool anyReflective = false, anyPointLight = false;
@@ -101,6 +105,85 @@ struct SceneData {
     if (!p) { p = static_cast<T*>(be->dalloc(sizeof(T) * n)); owned.push_back(p); }
     if (src) { be->upload(p, src, sizeof(T) * n); bytes_uploaded += int64_t(sizeof(T)) * n; }
     return p;
+  }
+
+  // Sphere clusters for the object scan of scenes with many spheres (DScene.cl1 ...): the spheres the
+  // float32 test applies to are sorted by the Morton key of their centres and grouped 16 x 16; every
+  // group gets a bounding sphere in CObjF form, i.e. "a big sphere at the group's centre".  A ray that
+  // certainly misses the big sphere is farther than R >= |c_i - C| + r_i from C, hence farther than r_i
+  // from every member centre: every member's discriminant is negative with the same float32 slack.
+  static CObjF boundRecord(const double* C, double R) {
+    CObjF f;
+    const double mt = std::max(std::fabs(C[0]), std::max(std::fabs(C[1]), std::fabs(C[2]))), r2 = R * R;
+    f.tx = float(-C[0]); f.ty = float(-C[1]); f.tz = float(-C[2]);
+    f.r2m = (std::isfinite(r2) && r2 < 1e30 && mt < 1e15) ? roundUpF(r2 + 2e-6 * r2 + 2e-7 * mt * mt) : float(NRT_INF);   // Inf: never skipped
+    return f;
+  }
+  void buildClusters(bool reuse) {
+    h.ncl1 = 0; h.nslow = 0;
+    std::vector<uint32_t> fast, slow;
+    for (size_t i = 0; i < cobjf.size(); ++i) (cobjf[i].r2m < 3.0e38f ? fast : slow).push_back(uint32_t(i));
+    if (int64_t(fast.size()) < kClusterMin) return;
+    // Morton order of the centres (centre = -t for worldToObject = [I | t])
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (uint32_t i : fast) for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], -cobjs[i].t[k]); hi[k] = std::max(hi[k], -cobjs[i].t[k]); }
+    auto key = [&](uint32_t i) {
+      uint32_t q[3];
+      for (int k = 0; k < 3; ++k) {
+        const double ext = hi[k] - lo[k];
+        double t = ext > 0 ? (-cobjs[i].t[k] - lo[k]) / ext : 0.0;
+        t = std::min(std::max(t, 0.0), 0.999999);
+        q[k] = uint32_t(t * 1024.0);
+      }
+      return (uint64_t(expandBits10(q[0])) << 2) | (uint64_t(expandBits10(q[1])) << 1) | uint64_t(expandBits10(q[2]));
+    };
+    std::vector<std::pair<uint64_t, uint32_t>> order;
+    for (uint32_t i : fast) order.push_back({key(i), i});
+    std::sort(order.begin(), order.end());
+    const int64_t g2 = kClusterSize, g1 = int64_t(kClusterSize) * kClusterSize;
+    const int64_t n1 = (int64_t(order.size()) + g1 - 1) / g1;
+    CObjF never; never.tx = never.ty = never.tz = 0.f; never.r2m = -float(NRT_INF);   // b^2 < a * (+Inf): always a certain miss
+    std::vector<CObjF> clm(size_t(n1 * g1), never), cl2(size_t(n1 * g2), never), cl1(size_t(n1), never);
+    std::vector<uint32_t> idx(size_t(n1 * g1), kInvalidRef);
+    for (size_t k = 0; k < order.size(); ++k) { clm[k] = cobjf[order[k].second]; idx[k] = order[k].second; }
+    // bounding sphere of a set of spheres (centre c, radius r): centre of their box, R = max(|c - C| + r)
+    auto bound = [&](const std::vector<std::array<double, 4>>& sp) {
+      double blo[3] = {1e300, 1e300, 1e300}, bhi[3] = {-1e300, -1e300, -1e300};
+      for (auto& q : sp) for (int k = 0; k < 3; ++k) { blo[k] = std::min(blo[k], q[k] - q[3]); bhi[k] = std::max(bhi[k], q[k] + q[3]); }
+      std::array<double, 4> b{0.5 * (blo[0] + bhi[0]), 0.5 * (blo[1] + bhi[1]), 0.5 * (blo[2] + bhi[2]), 0.0};
+      for (auto& q : sp) {
+        const double dx = q[0] - b[0], dy = q[1] - b[1], dz = q[2] - b[2];
+        b[3] = std::max(b[3], std::sqrt(dx * dx + dy * dy + dz * dz) + q[3]);
+      }
+      b[3] *= 1.0 + 1e-9;
+      return b;
+    };
+    for (int64_t a1 = 0; a1 < n1; ++a1) {
+      std::vector<std::array<double, 4>> l2s;
+      for (int64_t a2 = a1 * g2; a2 < (a1 + 1) * g2; ++a2) {
+        std::vector<std::array<double, 4>> ms;
+        for (int64_t m = a2 * g2; m < (a2 + 1) * g2 && m < int64_t(order.size()); ++m) {
+          const CObj& c = cobjs[order[size_t(m)].second];
+          ms.push_back({-c.t[0], -c.t[1], -c.t[2], std::fabs(c.radius)});
+        }
+        if (ms.empty()) continue;
+        const auto b = bound(ms);
+        cl2[size_t(a2)] = boundRecord(b.data(), b[3]);
+        l2s.push_back(b);
+      }
+      const auto b = bound(l2s);
+      cl1[size_t(a1)] = boundRecord(b.data(), b[3]);
+    }
+    const bool fit = reuse && n1 <= capCl1 && int64_t(slow.size()) <= capSlow;
+    if (!fit) { capCl1 = n1; capSlow = std::max<int64_t>(1, int64_t(slow.size())); }
+    dCl1 = up(cl1.data(), n1, fit ? dCl1 : nullptr);
+    dCl2 = up(cl2.data(), n1 * g2, fit ? dCl2 : nullptr);
+    dClm = up(clm.data(), n1 * g1, fit ? dClm : nullptr);
+    dClmIdx = up(idx.data(), n1 * g1, fit ? dClmIdx : nullptr);
+    if (slow.empty()) slow.push_back(0u);
+    dSlowIdx = up(slow.data(), int64_t(slow.size()), fit ? dSlowIdx : nullptr);
+    h.ncl1 = int32_t(n1);
+    h.nslow = int32_t(std::count_if(cobjf.begin(), cobjf.end(), [](const CObjF& f) { return !(f.r2m < 3.0e38f); }));
   }
 
   // Validates and flattens `desc`; with `reuse` the existing device buffers are refilled.
@@ -229,6 +312,7 @@ struct SceneData {
       }
     }
     dCObjF = up(cobjf.data(), int64_t(cobjf.size()), reuse ? dCObjF : nullptr);
+    buildClusters(reuse);
     dCObjs = up(cobjs.data(), int64_t(cobjs.size()), reuse ? dCObjs : nullptr);
     dObjs = up(objs.data(), int64_t(objs.size()), reuse ? dObjs : nullptr);
     dLights = up(lights.data(), int64_t(lights.size()), reuse ? dLights : nullptr);
@@ -269,6 +353,7 @@ struct SceneData {
       }
       dFrames = up(frames.data(), int64_t(frames.size()), reuse ? dFrames : nullptr);
     }
+    h.cl1 = dCl1; h.cl2 = dCl2; h.clm = dClm; h.clmIdx = dClmIdx; h.slowIdx = dSlowIdx;
     h.objects = dObjs; h.cobjs = dCObjs; h.cobjf = dCObjF; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames;
     std::memcpy(h.c2w, desc->camera_to_world, sizeof(h.c2w));
     { const V4 co = mulm(h.c2w, v4(0.0, 0.0, 0.0, 1.0)); h.cam_orig[0] = co.x; h.cam_orig[1] = co.y; h.cam_orig[2] = co.z; h.cam_orig[3] = co.w; }
@@ -519,11 +604,13 @@ struct Renderer {
           uint32_t* nextCount = cs.acount + bounce + 1;
           // (act.n is exact on the host for every bounce: launches are sized to it)
           meshWave(sd, fp, WAVE_PATH, act, wave, bounce, force_exact, bounce == 0 && fuseGen); ++wave;
-          be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act, bounce}, cs.stats);
+          if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadeClustered{sd.d, fp, cs, act, bounce}, cs.stats);
+          else be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act, bounce}, cs.stats);
           if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, bounce, force_exact, false);
           ++wave;
           if (nL > 0) {
-            if (shadowTracePerSample) be->forEachStats(nullptr, act.n, ShadowTraceSample{sd.d, fp, cs, act}, cs.stats);
+            if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowTraceSampleClustered{sd.d, fp, cs, act}, cs.stats);
+            else if (shadowTracePerSample) be->forEachStats(nullptr, act.n, ShadowTraceSample{sd.d, fp, cs, act}, cs.stats);
             else be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
           }
           be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act, bounce}, cs.stats);

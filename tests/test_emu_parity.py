@@ -119,6 +119,15 @@ def test_stress_scene_small(oracle_mod):
     check(scenes.stress(ntri=800, nspheres=30), api.Options(64, 36, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
 
 
+def test_sphere_clusters(oracle_mod):
+    # >= 64 spheres: the object scan goes through the two-level sphere clusters (Morton-ordered groups of
+    # 16 x 16 with bounding spheres) and evaluates the survivors in list order; mirrors among them
+    sc = scenes.stress(ntri=300, nspheres=700)
+    check(sc, api.Options(80, 45, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=3), oracle_mod)
+    sc = scenes.stress(ntri=50, nspheres=70, seed=7)       # one partly filled level-1 cluster
+    check(sc, api.Options(64, 36), oracle_mod)
+
+
 def test_degenerate_meshes(oracle_mod):
     from nim_raytracer_b200 import loaders, linalg as L
     # zero-area and needle triangles, duplicated coplanar faces (first index must win)

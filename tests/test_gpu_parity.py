@@ -231,6 +231,12 @@ def test_stress_scene_small(oracle_mod):
     assert_parity(sc, api.Options(160, 90, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
 
 
+def test_stress_scene_sphere_clusters(oracle_mod):
+    # BASELINE config 5's object count class: thousands of spheres -> clustered object scan
+    sc = scenes.stress(ntri=20000, nspheres=3000)
+    assert_parity(sc, api.Options(240, 135, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=4), oracle_mod)
+
+
 def test_config4_full_size_properties(monkeypatch):
     # BASELINE config 4 at its full size (3840x2160, 16 spp, depth 8): size-independent properties —
     # Stats identities of renderer.nim:58,138,155 and invariance under the chunking of the frame
