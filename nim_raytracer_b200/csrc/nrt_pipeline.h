@@ -728,12 +728,16 @@ using ShadowTraceSampleClustered = ShadowTraceSampleT<true>;
 // neighbours in the queues.
 struct Resolve {
   const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce;
+  int pointLights;   // some light is a PointLight: getShadingInfo needs the hit point (a DistantLight ignores it)
   NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
     if (idx >= activeN(act)) return st;
     const int64_t s = sampleOf(act, idx);
     // (hit record requested together with the hit flag: one memory round trip instead of two)
-    V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
+    // The hit point is only read by point lights and by the reflection set-up: without point lights it is
+    // fetched for the (few) continuing samples only, 32 bytes less per sample for everyone else.
+    V4 hitW = v4(0.0, 0.0, 0.0, 1.0), n = ld4(cs.nrm, cs.S, s);
+    if (pointLights) hitW = ld4(cs.hitW, cs.S, s);
     const int objHit = cs.hitObj[s];
     NRT_KEEP_D(hitW.x); NRT_KEEP_D(hitW.y); NRT_KEEP_D(hitW.z); NRT_KEEP_D(hitW.w);
     NRT_KEEP_D(n.x); NRT_KEEP_D(n.y); NRT_KEEP_D(n.z); NRT_KEEP_D(n.w);
@@ -763,6 +767,7 @@ struct Resolve {
     cs.accum[cs.S + s] = a1 + local.y * wl;
     cs.accum[2 * cs.S + s] = a2 + local.z * wl;
     if (cont) {
+      if (!pointLights) hitW = ld4(cs.hitW, cs.S, s);
       const V4 i = ld4(cs.rayD, cs.S, s);
       const V4 r = sub(i, scale(n, 2 * dot(n, i)));  // renderer.nim:112
       st4(cs.rayO, cs.S, s, add(hitW, scale(r, fp.bias)));

@@ -613,7 +613,7 @@ struct Renderer {
             else if (shadowTracePerSample) be->forEachStats(nullptr, act.n, ShadowTraceSample{sd.d, fp, cs, act}, cs.stats);
             else be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
           }
-          be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act, bounce}, cs.stats);
+          be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act, bounce, sd.anyPointLight ? 1 : 0}, cs.stats);
           if (bounce >= maxBounces) break;
           be->compactActive(cs, act, nextList, nextCount);
           uint32_t cont = 0;
