@@ -402,8 +402,7 @@ NRT_HD V3 shadeDiffuse(const DObject& o, const ShadingInfo& si, V4 hitNormal) {
 }
 
 // renderer.nim:31-44 (orig/dir only; initRay is applied per object in trace)
-NRT_HD void castPrimaryRay(const DScene& sc, int w, int h, double x, double y, V4& orig, V4& dir) {
-  const double r = double(w) / double(h);
+NRT_HD void castPrimaryRay(const DScene& sc, double r /* = double(w) / double(h) */, int w, int h, double x, double y, V4& orig, V4& dir) {
   const double f = sc.tan_half_fov;
   const double cx = ((2 * x * r) / double(w) - r) * f;
   const double cy = (1 - 2 * y / double(h)) * f;

@@ -49,6 +49,8 @@ struct FrameParams {
   int32_t _pad;
   double bias;
   uint64_t seed;
+  double aspect;           // double(width) / double(height)   (renderer.nim:36), the same division done once on the host
+  double inv_grid;         // 1.0 / double(grid)               (sampling.nim:6-7)
 };
 
 // Device-resident state of one chunk of samples (component-major SoA).
@@ -130,9 +132,13 @@ NRT_HD void st4(double* a, int64_t n, int64_t i, V4 v) { a[i] = v.x; a[n + i] = 
 
 // 64-bit integer division is a long instruction sequence on the GPU; every index on this path fits 32 bits
 NRT_HD int64_t divFast(int64_t a, int32_t b) {
-  if (b == 1) return a;
-  if (b == 2) return a >> 1;          // a >= 0 on every call site
-  if (b == 16) return a >> 4;
+  if ((b & (b - 1)) == 0) {           // power of two (a >= 0 on every call site)
+#if defined(__CUDA_ARCH__)
+    return a >> (__ffs(b) - 1);
+#else
+    return a >> __builtin_ctz(unsigned(b));
+#endif
+  }
   return ((uint64_t(a) >> 32) == 0) ? int64_t(uint32_t(a) / uint32_t(b)) : a / b;
 }
 NRT_HD void pixelOf(const FrameParams& fp, const ChunkState& cs, int64_t p, int& x, int& y) {
@@ -220,14 +226,14 @@ struct GenSimple {
     const bool alive = !pixelSkipped(fp, x, y);
     double sx = 0.0, sy = 0.0;
     if (fp.aa_kind == AA_GRID) {  // sampling.nim:5-18, element j*m+i
-      const int m = fp.grid, i = k % m, j = k / m;
-      const double xs = 1.0 / double(m), ys = 1.0 / double(m);
+      const int m = fp.grid, j = int(divFast(k, m)), i = k - j * m;
+      const double xs = fp.inv_grid, ys = fp.inv_grid;
       const double xoffs = xs * 0.5, yoffs = xs * 0.5;
       sx = double(i) * xs + xoffs; sy = double(j) * ys + yoffs;
     }
     V4 o, d;
     // akNone: (x.float, y.float) — the pixel corner (renderer.nim:135); else x.float + sample
-    castPrimaryRay(*sc, fp.width, fp.height, fp.aa_kind == AA_NONE ? double(x) : double(x) + sx,
+    castPrimaryRay(*sc, fp.aspect, fp.width, fp.height, fp.aa_kind == AA_NONE ? double(x) : double(x) + sx,
                    fp.aa_kind == AA_NONE ? double(y) : double(y) + sy, o, d);
     initSample(cs, s, alive, d);
     out.alive = alive; out.o = o; out.d = d;
@@ -246,7 +252,7 @@ struct GenJittered {
     makeSamples(fp.aa_kind, fp.grid, rng, px, py);
     for (int k = 0; k < fp.spp; ++k) {
       V4 o, d;
-      castPrimaryRay(*sc, fp.width, fp.height, double(x) + px[k], double(y) + py[k], o, d);
+      castPrimaryRay(*sc, fp.aspect, fp.width, fp.height, double(x) + px[k], double(y) + py[k], o, d);
       initSample(cs, pl * fp.spp + k, alive, d);
     }
   }

@@ -540,6 +540,8 @@ struct Renderer {
     fp.bounce_cap = o.bounce_cap > 0 ? o.bounce_cap : 64;
     fp.nx = (o.width + step - 1) / step;
     fp.bias = o.bias; fp.seed = o.seed;
+    fp.aspect = double(o.width) / double(o.height);
+    fp.inv_grid = 1.0 / double(fp.grid);
     for (int k = 0; k < ST_COUNT; ++k) statsOut[k] = 0;
     if (rows.empty() || fp.nx == 0) return NRT_OK;
 
