@@ -245,6 +245,15 @@ int nrt_render_device(nrt_scene* scene, const nrt_options* opts,
  * rgb8 is host memory, width*height*3 bytes. */
 int nrt_framebuf_to_srgb8(const float* fb_host, int width, int height,
                           int srgb, unsigned char* rgb8);
+/* The general form of writePpm's sample conversion (utils/framebuf.nim:55-93): bits in 1..16,
+ * maxval = 2^bits - 1; `out` receives width*height*3 uint8 samples (bits <= 8) or big-endian uint16
+ * samples (bits > 8, the PPM byte order).  Host memory. */
+int nrt_framebuf_quantize(const float* fb_host, int width, int height,
+                          int bits, int srgb, void* out);
+/* ImageRGBA.copyFrom (utils/image.nim:45-54, the GUI's display copy): round(v*255) per channel,
+ * constant alpha; rgba8 is host memory, width*height*4 bytes. */
+int nrt_framebuf_to_rgba8(const float* fb_host, int width, int height,
+                          unsigned char alpha, unsigned char* rgba8);
 
 int nrt_get_profile(const nrt_scene* scene, nrt_profile* out);
 

@@ -159,6 +159,8 @@ def lib() -> C.CDLL:
                              C.POINTER(nrt_stats), C.POINTER(nrt_aov)]
     L.nrt_render_device.argtypes = L.nrt_render.argtypes
     L.nrt_framebuf_to_srgb8.argtypes = [vp, i32, i32, i32, vp]
+    L.nrt_framebuf_quantize.argtypes = [vp, i32, i32, i32, i32, vp]
+    L.nrt_framebuf_to_rgba8.argtypes = [vp, i32, i32, C.c_ubyte, vp]
     L.nrt_get_profile.argtypes = [vp, C.POINTER(nrt_profile)]
     L.nrt_set_kernel_timing.argtypes = [i32]
     L.nrt_get_kernel_times.argtypes = [vp, C.POINTER(nrt_kernel_times)]
@@ -522,11 +524,28 @@ def framebufToSrgb8(fb: Framebuf, sRGB: bool = True) -> np.ndarray:
     return out.reshape(fb.h, fb.w, 3)
 
 
+def framebufQuantize(fb: Framebuf, bits: int = 8, sRGB: bool = True) -> np.ndarray:
+    """writePpm's samples (utils/framebuf.nim:55-93) for any bits in 1..16: uint8, or big-endian uint16 above 8 bits."""
+    if not 1 <= bits <= 16:
+        raise ValueError("bits must be in 1..16 (framebuf.nim:56)")
+    out = np.zeros(fb.w * fb.h * 3, dtype=np.uint8 if bits <= 8 else ">u2")
+    check(lib().nrt_framebuf_quantize(fb.data.ctypes.data_as(C.c_void_p), fb.w, fb.h, bits, int(sRGB),
+                                      out.ctypes.data_as(C.c_void_p)), "nrt_framebuf_quantize")
+    return out.reshape(fb.h, fb.w, 3)
+
+
+def framebufToRgba8(fb: Framebuf, alpha: int = 0xFF) -> np.ndarray:
+    """ImageRGBA.copyFrom (utils/image.nim:45-54)."""
+    out = np.zeros(fb.w * fb.h * 4, dtype=np.uint8)
+    check(lib().nrt_framebuf_to_rgba8(fb.data.ctypes.data_as(C.c_void_p), fb.w, fb.h, alpha,
+                                      out.ctypes.data_as(C.c_void_p)), "nrt_framebuf_to_rgba8")
+    return out.reshape(fb.h, fb.w, 4)
+
+
 def writePpm(fb: Framebuf, filename: str, bits: int = 8, sRGB: bool = True) -> bool:
-    """utils/framebuf.nim:55-93 (8-bit path through the GPU output stage)."""
-    assert bits == 8, "16-bit PPM is host-only in the reference; not on the hot path"
-    img = framebufToSrgb8(fb, sRGB)
+    """utils/framebuf.nim:55-93: P6, maxval 2^bits - 1, 8-bit or big-endian 16-bit samples (GPU output stage)."""
+    img = framebufQuantize(fb, bits, sRGB)
     with open(filename, "wb") as f:
-        f.write(f"P6 {fb.w} {fb.h} 255 ".encode())
+        f.write(f"P6 {fb.w} {fb.h} {(1 << bits) - 1} ".encode())
         f.write(img.tobytes())
     return True

@@ -629,17 +629,33 @@ __global__ void __launch_bounds__(kBlock) k_finalize_tiled(Finalize f, int64_t n
   }
 }
 
-// clamp -> sRGB -> 8 bit (utils/framebuf.nim:74-78, utils/color.nim:17-22)
-__global__ void __launch_bounds__(kBlock) k_srgb8(const float* fb, unsigned char* out, int64_t n, int srgb) {
-  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
-  if (i >= n) return;
-  float c = fb[i];
+// Output stage: writePpm's outvalue (utils/framebuf.nim:74-78): clamp -> linearToSRGB (utils/color.nim:17-22)
+// -> round(c * maxval), maxval = 2^bits - 1; 8-bit samples for bits <= 8, big-endian 16-bit samples above
+// (the PPM byte order, framebuf.nim:67-71).
+__device__ __forceinline__ float outvalue(float c, int srgb, float maxval) {
   c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
   if (srgb) {
     if (c <= 0.0031308f) c = 12.92f * c;
     else c = float((1.0 + 0.055) * double(powf(c, float(1 / 2.4))) - 0.055);
   }
-  out[i] = (unsigned char)(roundf(c * 255.f));
+  return roundf(c * maxval);
+}
+__global__ void __launch_bounds__(kBlock) k_quantize(const float* fb, unsigned char* out, int64_t n, int srgb, int bits) {
+  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const unsigned v = unsigned(outvalue(fb[i], srgb, float((1u << bits) - 1u)));
+  if (bits <= 8) out[i] = (unsigned char)v;
+  else { out[2 * i] = (unsigned char)(v >> 8); out[2 * i + 1] = (unsigned char)(v & 0xFFu); }
+}
+// ImageRGBA.copyFrom (utils/image.nim:45-54): round(v * 255) per channel + a constant alpha (values are
+// clamped to 0..255 here; the reference's float -> uint8 conversion is undefined outside that range)
+__global__ void __launch_bounds__(kBlock) k_rgba8(const float* fb, unsigned char* out, int64_t npix, unsigned char alpha) {
+  const int64_t p = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  if (p >= npix) return;
+  uchar4 o;
+  auto q = [](float v) { const float r = roundf(v * 255.f); return (unsigned char)(r < 0.f ? 0.f : (r > 255.f ? 255.f : r)); };
+  o.x = q(fb[3 * p]); o.y = q(fb[3 * p + 1]); o.z = q(fb[3 * p + 2]); o.w = alpha;
+  reinterpret_cast<uchar4*>(out)[p] = o;
 }
 
 // register-resident FFMA loop: the float32 roofline denominator
@@ -1339,26 +1355,37 @@ int nrt_get_profile(const nrt_scene* scene, nrt_profile* out) {
   return NRT_OK;
 }
 
-int nrt_framebuf_to_srgb8(const float* fb_host, int width, int height, int srgb, unsigned char* rgb8) {
-  if (!fb_host || !rgb8 || width <= 0 || height <= 0) return fail(NRT_ERR_INVALID, "bad argument");
+static int quantizeImpl(const float* fb_host, int width, int height, int bits, int srgb, void* out, bool rgba, unsigned char alpha) {
+  if (!fb_host || !out || width <= 0 || height <= 0 || bits < 1 || bits > 16) return fail(NRT_ERR_INVALID, "bad argument");
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called");
   CudaBackend& be = g_devs[0]->be;
-  const int64_t n = int64_t(width) * height * 3;
+  const int64_t npix = int64_t(width) * height, n = npix * 3;
+  const int64_t outBytes = rgba ? npix * 4 : n * (bits <= 8 ? 1 : 2);
   float* d = nullptr; unsigned char* o = nullptr;
   try {
     d = static_cast<float*>(be.dalloc(n * sizeof(float)));
-    o = static_cast<unsigned char*>(be.dalloc(n));
+    o = static_cast<unsigned char*>(be.dalloc(size_t(outBytes)));
     be.upload(d, fb_host, n * sizeof(float));
-    k_srgb8<<<CudaBackend::blocksFor(n), kBlock, 0, be.stream>>>(d, o, n, srgb);
+    if (rgba) k_rgba8<<<CudaBackend::blocksFor(npix), kBlock, 0, be.stream>>>(d, o, npix, alpha);
+    else k_quantize<<<CudaBackend::blocksFor(n), kBlock, 0, be.stream>>>(d, o, n, srgb, bits);
     NRT_CUDA(cudaGetLastError());
-    be.download(rgb8, o, n);
+    be.download(out, o, size_t(outBytes));
   } catch (const std::exception& ex) {
     be.dfree(d); be.dfree(o);
     return fail(NRT_ERR_CUDA, ex.what());
   }
   be.dfree(d); be.dfree(o);
   return NRT_OK;
+}
+int nrt_framebuf_to_srgb8(const float* fb_host, int width, int height, int srgb, unsigned char* rgb8) {
+  return quantizeImpl(fb_host, width, height, 8, srgb, rgb8, false, 0);
+}
+int nrt_framebuf_quantize(const float* fb_host, int width, int height, int bits, int srgb, void* out) {
+  return quantizeImpl(fb_host, width, height, bits, srgb, out, false, 0);
+}
+int nrt_framebuf_to_rgba8(const float* fb_host, int width, int height, unsigned char alpha, unsigned char* rgba8) {
+  return quantizeImpl(fb_host, width, height, 8, 0, rgba8, true, alpha);
 }
 
 #define NRT_NEED_DEV0()                                                               \
