@@ -4,16 +4,19 @@
 // shade  recursively per pixel on CPU threads (renderer.nim:31-211).  Here the
 // same computation is organised as waves of rays over a chunk of samples:
 //
-//   gen      : castPrimaryRay for every sample              (renderer.nim:31-44,132-159)
+//   gen      : castPrimaryRay for every sample + the gate of its mesh boxes  (renderer.nim:31-44,132-159)
 //   per bounce:
 //     gate   : per (ray, mesh object) AABB gate of TriangleMesh.intersect
-//              (geom.nim:340) + ballot-compacted queue of float32 filter rays
-//     filter : float32 ray x triangle filter over the queue (the hot kernel)
+//              (geom.nim:340); rays that enter a box go, IN WAVE ORDER, into one
+//              queue of float32 filter rays per ray bundle
+//     prefilter / refine : float32 ray x face filter over the queues (nrt_filter.h):
+//              chunk bounds -> sub-chunk bounds -> bounding circles -> sign test
 //     verify : float64 exact re-evaluation of the candidates, nearest hit with
 //              first-index-wins ties                        (geom.nim:346-358)
 //     shade  : trace()'s in-order object scan + hit point/normal (renderer.nim:47-88)
-//     gate/filter/verify again for the shadow rays          (renderer.nim:93-104)
-//     resolve: shadow tests, shadeDiffuse, reflection ray   (renderer.nim:93-127)
+//     gate/prefilter/refine/verify again for the shadow rays (renderer.nim:93-104)
+//     shadow trace : trace() of the shadow rays -> occlusion flags (renderer.nim:101-103)
+//     resolve: shadeDiffuse of the unoccluded lights, reflection ray (renderer.nim:90-127)
 //   finalize : per-pixel sample sum, * 1/N, float32 store   (renderer.nim:147-159,204-209)
 //
 // The functors below are the per-element bodies; a backend (CUDA in nrt.cu,
