@@ -380,6 +380,7 @@ struct PreArgs {
   uint32_t* prectr;         // pre-candidate counter
   uint32_t* workctr;        // (run, chunk) pairs admitted by level 1 (may exceed pairCap: the host re-renders)
   uint32_t* subctr;         // (run, sub-chunk) pairs evaluated in full
+  uint32_t* bndctr;         // (run, chunk) pairs whose bound was tested ray by ray
   uint2* pairs;             // the work list
   uint32_t pairCap;
   uint32_t* preRay;
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_prefilter_bounds(PreArgs a) {
   const int lane = threadIdx.x & 31;
   const uint32_t nRuns = (nq + RUN - 1) / RUN, nGroups = (nChunks + 31) / 32;
   const uint32_t totalWarps = gridDim.x * FT_WARPS, gw = blockIdx.x * FT_WARPS + (threadIdx.x >> 5);
+  uint32_t bnd = 0;
   for (uint64_t item = gw; item < uint64_t(nRuns) * nGroups; item += totalWarps) {
     const uint32_t run = uint32_t(item / nGroups), gr = uint32_t(item - uint64_t(run) * nGroups);
     const uint32_t c0 = gr * 32, c1 = min(nChunks, c0 + 32);
@@ -444,9 +446,50 @@ __global__ void __launch_bounds__(FT_THREADS) k_prefilter_bounds(PreArgs a) {
     if (a.cull) {
       LaneRays<MODE, R> ry;
       ry.load(a, run, nq, lane);
-      uint32_t mine = 0;
-      for (uint32_t c = c0; c < c1; ++c) {
-        const float4 bd = __ldg(a.bounds + c);
+      uint32_t cand = (c1 - c0 >= 32) ? 0xffffffffu : ((1u << (c1 - c0)) - 1u);
+      if (MODE != FM_GENERAL) {
+        // 2-D bundles: one circle around the run's points first; lane j tests it against the circle of
+        // chunk c0 + j (32 chunks per instruction instead of 8 ray tests per lane per chunk).  A ray that
+        // passes a chunk's bound test lies within sqrt(Rc^2 + its margin + evaluation error) of the chunk
+        // centre and within Rr of the run centre, so the two circles overlap: no admitted pair is lost.
+        float xlo = ry.a0[0], xhi = ry.a0[0], ylo = ry.a1[0], yhi = ry.a1[0], mr = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          xlo = fminf(xlo, ry.a0[r]); xhi = fmaxf(xhi, ry.a0[r]); ylo = fminf(ylo, ry.a1[r]); yhi = fmaxf(yhi, ry.a1[r]);
+          mr = fmaxf(mr, fmaf(ry.a0[r], ry.a0[r], ry.a1[r] * ry.a1[r]) - ry.a2[r]);   // |p|^2 - T = the ray's margin
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, off)); xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, off));
+          ylo = fminf(ylo, __shfl_xor_sync(0xffffffffu, ylo, off)); yhi = fmaxf(yhi, __shfl_xor_sync(0xffffffffu, yhi, off));
+          mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, off));
+        }
+        const float cx = 0.5f * (xlo + xhi), cy = 0.5f * (ylo + yhi);
+        float r2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { const float dx = ry.a0[r] - cx, dy = ry.a1[r] - cy; r2 = fmaxf(r2, fmaf(dx, dx, dy * dy)); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, off));
+        const float Rr = sqrtf(r2) * 1.00001f;
+        const float p2max = fmaf(fmaxf(fabsf(xlo), fabsf(xhi)), fmaxf(fabsf(xlo), fabsf(xhi)), fmaxf(fabsf(ylo), fabsf(yhi)) * fmaxf(fabsf(ylo), fabsf(yhi)));
+        if (Rr < 1e15f && mr < 1e30f && p2max < 1e30f) {
+          bool pass = false;
+          if (c0 + lane < c1) {
+            const float4 bd = __ldg(a.bounds + c0 + lane);
+            const float Cx = 0.5f * bd.x, Cy = 0.5f * bd.y, C2 = fmaf(Cx, Cx, Cy * Cy);
+            const float Rc2 = bd.z + C2 + 2e-6f * (fabsf(bd.z) + C2 + p2max) + 1.01f * mr;
+            const float Rs = Rr + sqrtf(fmaxf(Rc2, 0.f)) + 5e-7f * (fabsf(cx) + fabsf(cy) + fabsf(Cx) + fabsf(Cy));
+            const float dx = cx - Cx, dy = cy - Cy;
+            pass = (bd.z >= 1e29f) || (bd.z > -1e29f && fmaf(dx, dx, dy * dy) <= Rs * Rs * 1.00001f);
+          }
+          cand &= __ballot_sync(0xffffffffu, pass);
+        }
+      }
+      mask = 0;
+      bnd += uint32_t(__popc(cand));
+      for (uint32_t m = cand; m; m &= m - 1) {     // the exact per-ray bound test for the remaining chunks
+        const uint32_t bit = uint32_t(__ffs(m) - 1);
+        const float4 bd = __ldg(a.bounds + c0 + bit);
         bool p = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -458,9 +501,8 @@ __global__ void __launch_bounds__(FT_THREADS) k_prefilter_bounds(PreArgs a) {
             p = p || (fmaf(bd.x, ry.a0[r], fmaf(bd.y, ry.a1[r], bd.z)) >= ry.a2[r]);
           }
         }
-        mine |= uint32_t(p) << (c - c0);
+        if (__any_sync(0xffffffffu, p)) mask |= 1u << bit;
       }
-      mask = __reduce_or_sync(0xffffffffu, mine);
     } else {
       mask = (c1 - c0 >= 32) ? 0xffffffffu : ((1u << (c1 - c0)) - 1u);
     }
@@ -472,6 +514,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_prefilter_bounds(PreArgs a) {
       if (uint32_t(lane) < n && base + lane < a.pairCap) a.pairs[base + lane] = make_uint2(run, c0 + __fns(mask, 0, lane + 1));
     }
   }
+  if (lane == 0 && bnd) atomicAdd(a.bndctr, bnd);
 }
 
 template <int MODE, int R, int U>
@@ -923,6 +966,7 @@ struct CudaBackend {
     a.prectr = cnt + cntPre(b);
     a.workctr = cnt + cntWork(b);
     a.subctr = cnt + cntSub(b);
+    a.bndctr = cnt + cntBnd(b);
     a.pairs = reinterpret_cast<uint2*>(cs.pairs);
     a.pairCap = uint32_t(std::min<int64_t>(cs.pairCap, 0xFFFFFFFFll));
     a.preRay = cs.preRay; a.preRec = cs.preRec;

@@ -29,17 +29,18 @@ namespace nrt {
 
 enum WaveKind { WAVE_PATH = 0, WAVE_SHADOW = 1 };
 
-// Counter block per (wave, mesh object): [EXACT, CAND, NE, then (QUEUE_b, TILE_b, PRE_b, WORK_b, SUB_b) per ray bundle b].
+// Counter block per (wave, mesh object): [EXACT, CAND, NE, then (QUEUE_b, TILE_b, PRE_b, WORK_b, SUB_b, BND_b) per ray bundle b].
 // Bundle 0 holds arbitrary rays (GENERAL mode; ORIGIN mode for the primary wave, whose rays share
 // the camera origin); bundle 1 + l holds the shadow rays of DistantLight l (DIR mode).
 // NE (mesh object 0's block only): 256-ray blocks of the wave with at least one ray entering a mesh box.
 enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_NE = 2, CNT_BUNDLE0 = 3 };
-NRT_HD int cntStride(int nL) { return CNT_BUNDLE0 + 5 * (1 + nL); }
-NRT_HD int cntQueue(int b) { return CNT_BUNDLE0 + 5 * b; }      // rays queued for the bundle
-NRT_HD int cntTile(int b) { return CNT_BUNDLE0 + 5 * b + 1; }   // prefilter work-item counter
-NRT_HD int cntPre(int b) { return CNT_BUNDLE0 + 5 * b + 2; }    // pre-candidates (prefilter survivors)
-NRT_HD int cntWork(int b) { return CNT_BUNDLE0 + 5 * b + 3; }   // (ray run, chunk) pairs admitted by the chunk bounds
-NRT_HD int cntSub(int b) { return CNT_BUNDLE0 + 5 * b + 4; }    // (ray run, sub-chunk) pairs evaluated in full
+NRT_HD int cntStride(int nL) { return CNT_BUNDLE0 + 6 * (1 + nL); }
+NRT_HD int cntQueue(int b) { return CNT_BUNDLE0 + 6 * b; }      // rays queued for the bundle
+NRT_HD int cntTile(int b) { return CNT_BUNDLE0 + 6 * b + 1; }   // prefilter work-item counter
+NRT_HD int cntPre(int b) { return CNT_BUNDLE0 + 6 * b + 2; }    // pre-candidates (prefilter survivors)
+NRT_HD int cntWork(int b) { return CNT_BUNDLE0 + 6 * b + 3; }   // (ray run, chunk) pairs admitted by the chunk bounds
+NRT_HD int cntSub(int b) { return CNT_BUNDLE0 + 6 * b + 4; }    // (ray run, sub-chunk) pairs evaluated in full
+NRT_HD int cntBnd(int b) { return CNT_BUNDLE0 + 6 * b + 5; }    // (ray run, chunk) pairs whose bound was tested ray by ray
 // Stats slots
 enum { ST_PRIMARY = 0, ST_TESTS = 1, ST_HITS = 2, ST_RAYS = 3, ST_CAPPED = 4, ST_CONT = 5, ST_COUNT = 8 };
 

@@ -647,9 +647,10 @@ struct Renderer {
               // per (ray, chunk); a run is the prefilterRunRays(mode) consecutive queue entries of one warp
               const int64_t nch = SceneData<BE>::numChunks(int64_t(sd.hostRecCount(mo, mode, b > 0 ? b - 1 : 0)));
               const int64_t run = prefilterRunRays(mode), nruns = (q + run - 1) / run;
-              // executed tests: chunk bounds (every run x every chunk), sub-chunk bounds of the admitted pairs,
-              // and the records of the admitted sub-chunks
-              const int64_t t = nruns * run * nch + int64_t(c[cntWork(b)]) * run * kSubPerChunk + int64_t(c[cntSub(b)]) * run * kSubRecs;
+              // executed tests: chunk bounds tested ray by ray (2-D bundles: only the chunks whose circle overlaps the
+              // run's circle), sub-chunk bounds of the admitted pairs, and the records of the admitted sub-chunks
+              (void)nruns; (void)nch;
+              const int64_t t = int64_t(c[cntBnd(b)]) * run + int64_t(c[cntWork(b)]) * run * kSubPerChunk + int64_t(c[cntSub(b)]) * run * kSubRecs;
               pacc.mesh_tests += t; pacc.tests_by_mode[mode] += t;
               queued += q;
             }

@@ -139,6 +139,7 @@ struct LoopBackend {
     };
     for (uint32_t r0 = 0; r0 < nq; r0 += run) {
       const uint32_t r1 = std::min(nq, r0 + run);
+      cnt[cntBnd(b)] += uint32_t(nch);   // (the CUDA kernel skips the chunks whose circle misses the run's circle)
       for (int64_t ch = 0; ch < nch; ++ch) {
         bool any = !cull;
         for (uint32_t rq = r0; rq < r1 && !any; ++rq) any = prefilterTest(mode, bounds + 4 * ch, rayAt(rq));
