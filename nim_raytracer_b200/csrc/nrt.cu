@@ -756,6 +756,8 @@ struct CudaBackend {
   bool cull = true;    // NRT_PREFILTER_CULL=0: evaluate every chunk (brute force over the record set)
   int splitBelow = 8;  // NRT_PREFILTER_SPLIT: measured on the 1/8-frame partitions of an 8-GPU run (2: 1.08 ms of prefilter, 8: 1.04, 32: 1.01; full frame unchanged)
   bool smemOptIn = false;
+  static constexpr size_t kPinnedBytes = 1 << 16;
+  void* pinned = nullptr;
   void* scratchPtr[2] = {nullptr, nullptr};
   size_t scratchBytes[2] = {0, 0};
 
@@ -805,8 +807,17 @@ struct CudaBackend {
     NRT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     // pageable sources are staged by the runtime before the call returns; callers may reuse src
   }
+  // device -> host with a stream sync; small reads (the per-bounce continuation count, counters, stats) go
+  // through a pinned staging buffer: a copy into pageable memory is staged by the driver and costs ~2x
   void download(void* dst, const void* src, size_t bytes) {
     use();
+    if (bytes <= kPinnedBytes) {
+      if (!pinned) NRT_CUDA(cudaHostAlloc(&pinned, kPinnedBytes, cudaHostAllocDefault));
+      NRT_CUDA(cudaMemcpyAsync(pinned, src, bytes, cudaMemcpyDeviceToHost, stream));
+      NRT_CUDA(cudaStreamSynchronize(stream));
+      std::memcpy(dst, pinned, bytes);
+      return;
+    }
     NRT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
     NRT_CUDA(cudaStreamSynchronize(stream));
   }
@@ -1027,6 +1038,8 @@ struct CudaBackend {
     for (auto& e : tEvents) cudaEventDestroy(e);
     tEvents.clear(); tCats.clear(); tUsed = 0;
     for (int k = 0; k < 2; ++k) { if (scratchPtr[k]) cudaFree(scratchPtr[k]); scratchPtr[k] = nullptr; scratchBytes[k] = 0; }
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
