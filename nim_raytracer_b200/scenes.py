@@ -174,6 +174,25 @@ def stress(ntri: int = 1_000_000, nspheres: int = 10_000, seed: int = 20161018) 
                  bgColor=vec3(0.01, 0.03, 0.05))
 
 
+def scaled_scene(k: float, stride: int = 64, nspheres: int = 5) -> Scene:
+    """Build-defined robustness scene: the mesh-bunny layout (decimated bunny, ground plane, the two
+    lights) plus a few spheres (every other one a mirror), with EVERY length multiplied by k — from
+    1e-18 to 1e25 the float32 first looks run out of range one after the other and must hand over to
+    the float64 path without changing a bit of the result."""
+    rs = np.random.RandomState(1)
+    mesh = trianglesToMesh(bunny_triangles(stride=stride) * k)
+    mesh.objectToWorld = L.translate(L.mat4(1.0), vec3(0.0, 0.0001 * k, -12.0 * k))
+    mesh.worldToObject = L.inverse(mesh.objectToWorld)
+    objects = [Object("mesh", mesh, Material(albedo=vec3(0.6, 0.9, 0.2))),
+               Object("ground", initPlane(objectToWorld=L.mat4(1.0)), Material(albedo=vec3(0.4)))]
+    for i in range(nspheres):
+        c = (rs.uniform(-3, 3) * k, rs.uniform(0.5, 3) * k, (-10 + rs.uniform(-2, 2)) * k)
+        objects.append(Object(f"s{i}", initSphere(r=rs.uniform(0.3, 1.2) * k, objectToWorld=L.translate(L.mat4(1.0), vec3(*c))),
+                              Material(albedo=vec3(0.8, 0.4, 0.2), reflection=0.4 if i % 2 else 0.0)))
+    return Scene(objects=objects, lights=_bunny_lights(), fov=50.0, cameraToWorld=_camera(0.0, 5.5 * k, 1.5 * k),
+                 bgColor=vec3(0.1, 0.2, 0.3))
+
+
 def transformed_objects(stride: int = 16) -> Scene:
     """Build-defined parity scene: every geometry kind under a NON-translation objectToWorld
     (rotation + non-uniform scale), so worldToObject*dir is not unit length (the `(x/2)*a` sphere

@@ -128,6 +128,15 @@ def test_sphere_clusters(oracle_mod):
     check(sc, api.Options(64, 36), oracle_mod)
 
 
+@pytest.mark.parametrize("k", [1e-18, 1e-6, 1.0, 1e6, 1e12, 1e18, 1e25])
+def test_extreme_scales(oracle_mod, k):
+    # every length of the scene times k: float32 first looks (sphere / plane / box / chunk bounds) run out of
+    # range and the float64 path takes over; bias 0 puts shadow and reflection origins exactly on the surfaces
+    sc = scenes.scaled_scene(k)
+    check(sc, api.Options(64, 40, antialias=api.Antialias(api.akGrid, 2), bias=1e-8 * k), oracle_mod)
+    check(sc, api.Options(48, 30, bias=0.0), oracle_mod)
+
+
 def test_degenerate_meshes(oracle_mod):
     from nim_raytracer_b200 import loaders, linalg as L
     # zero-area and needle triangles, duplicated coplanar faces (first index must win)

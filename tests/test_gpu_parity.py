@@ -231,6 +231,13 @@ def test_stress_scene_small(oracle_mod):
     assert_parity(sc, api.Options(160, 90, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
 
 
+@pytest.mark.parametrize("k", [1e-18, 1e-6, 1e6, 1e18, 1e25])
+def test_extreme_scales(oracle_mod, k):
+    sc = scenes.scaled_scene(k)
+    assert_parity(sc, api.Options(96, 60, antialias=api.Antialias(api.akGrid, 2), bias=1e-8 * k), oracle_mod)
+    assert_parity(sc, api.Options(64, 40, bias=0.0), oracle_mod)
+
+
 def test_stress_scene_sphere_clusters(oracle_mod):
     # BASELINE config 5's object count class: thousands of spheres -> clustered object scan
     sc = scenes.stress(ntri=20000, nspheres=3000)
