@@ -36,6 +36,9 @@
 #ifndef NRT_OCC_DEFAULT
 #define NRT_OCC_DEFAULT 4
 #endif
+#ifndef NRT_OCC_GATE_WRITE
+#define NRT_OCC_GATE_WRITE 0
+#endif
 #ifndef NRT_OCC_GATE
 #define NRT_OCC_GATE 6
 #endif
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(1024) k_gate_scan(ChunkState cs, const uint32_
   if (threadIdx.x == 0) cnt[mo * cst + (r < nB ? cntQueue(r) : CNT_EXACT)] = carry;
 }
 
-__global__ void __launch_bounds__(kBlock) k_gate_write(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO, const uint32_t* neCount) {
+__global__ void __launch_bounds__(kBlock, NRT_OCC_GATE_WRITE) k_gate_write(Gate g, const uint32_t* count, int64_t nHost, int mult, int nMO, const uint32_t* neCount) {
   __shared__ uint32_t wc[kBlock / 32];
   __shared__ uint32_t sh_pre;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
