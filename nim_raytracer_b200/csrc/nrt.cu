@@ -37,7 +37,7 @@
 #define NRT_OCC_DEFAULT 4
 #endif
 #ifndef NRT_OCC_GATE_WRITE
-#define NRT_OCC_GATE_WRITE 0
+#define NRT_OCC_GATE_WRITE 4   // k_gate_write: 1.63 ms at 80 registers -> 1.33 ms at 64
 #endif
 #ifndef NRT_OCC_GATE
 #define NRT_OCC_GATE 6

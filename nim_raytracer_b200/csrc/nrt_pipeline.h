@@ -522,7 +522,7 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
     // 256 and 16 spheres are skipped; the objects that are not certain misses are collected in a small
     // list kept in LIST ORDER (renderer.nim:53: the in-order scan decides ties and Stats) and evaluated
     // in float64 afterwards.  A full list falls back to the flat in-order scan below.
-    uint32_t surv[kSurvivorCap];
+    uint32_t surv[kSurvivorCap] = {0};
     int ns = 0;
     bool full = false;
     auto push = [&](uint32_t i) {
