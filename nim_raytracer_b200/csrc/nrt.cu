@@ -36,6 +36,14 @@
 #ifndef NRT_OCC_DEFAULT
 #define NRT_OCC_DEFAULT 4
 #endif
+// prefilter evaluation kernel: resident CTAs per SM = persistent grid size (2-D bundles: 3 at 80 registers; 4 at 64
+// registers measured 8 % slower; GENERAL: 2 at 94 registers, 3 no faster)
+#ifndef NRT_OCC_PRE_2D
+#define NRT_OCC_PRE_2D 3
+#endif
+#ifndef NRT_OCC_PRE_GEN
+#define NRT_OCC_PRE_GEN 2
+#endif
 #ifndef NRT_OCC_GATE_WRITE
 #define NRT_OCC_GATE_WRITE 4   // k_gate_write: 1.63 ms at 80 registers -> 1.33 ms at 64
 #endif
@@ -521,7 +529,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_prefilter_bounds(PreArgs a) {
 }
 
 template <int MODE, int R, int U>
-__global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? 2 : 3) k_mesh_prefilter(PreArgs a) {
+__global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? NRT_OCC_PRE_GEN : NRT_OCC_PRE_2D) k_mesh_prefilter(PreArgs a) {
   constexpr int NH = hotFloats(MODE);      // float2 per record pair == float4 per record quad
   constexpr int CH4 = (FT_TC / 4) * NH;    // float4 per chunk
   constexpr int SQ = kSubRecs / 4;         // record quads per sub-chunk
@@ -754,8 +762,6 @@ struct CudaBackend {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> filterEvents;
   size_t filterUsed = 0;
   std::vector<int> filterModes;
-  int gridPerSm = 3;   // resident prefilter CTAs per SM (NRT_PREFILTER_CTAS_PER_SM)
-  int gridGeneral = 2;
   bool cull = true;    // NRT_PREFILTER_CULL=0: evaluate every chunk (brute force over the record set)
   int splitBelow = 8;  // NRT_PREFILTER_SPLIT: measured on the 1/8-frame partitions of an 8-GPU run (2: 1.08 ms of prefilter, 8: 1.04, 32: 1.01; full frame unchanged)
   bool smemOptIn = false;
@@ -1010,13 +1016,13 @@ struct CudaBackend {
     const unsigned gb = unsigned(sms * 8);
     if (mode == FM_GENERAL) {
       k_prefilter_bounds<FM_GENERAL, 4><<<gb, FT_THREADS, 0, stream>>>(a);
-      k_mesh_prefilter<FM_GENERAL, 4, 2><<<unsigned(sms * gridGeneral), FT_THREADS, smGen, stream>>>(a);
+      k_mesh_prefilter<FM_GENERAL, 4, 2><<<unsigned(sms * NRT_OCC_PRE_GEN), FT_THREADS, smGen, stream>>>(a);
     } else if (mode == FM_ORIGIN) {
       k_prefilter_bounds<FM_ORIGIN, 8><<<gb, FT_THREADS, 0, stream>>>(a);
-      k_mesh_prefilter<FM_ORIGIN, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, sm2d, stream>>>(a);
+      k_mesh_prefilter<FM_ORIGIN, 8, 1><<<unsigned(sms * NRT_OCC_PRE_2D), FT_THREADS, sm2d, stream>>>(a);
     } else {
       k_prefilter_bounds<FM_DIR, 8><<<gb, FT_THREADS, 0, stream>>>(a);
-      k_mesh_prefilter<FM_DIR, 8, 1><<<unsigned(sms * gridPerSm), FT_THREADS, sm2d, stream>>>(a);
+      k_mesh_prefilter<FM_DIR, 8, 1><<<unsigned(sms * NRT_OCC_PRE_2D), FT_THREADS, sm2d, stream>>>(a);
     }
     launches += 2;
     NRT_CUDA(cudaGetLastError()); ++launches;
@@ -1096,7 +1102,6 @@ static int initLocked(int ngpu, const int* ids) {
       auto* d = new DeviceCtx();
       d->be.device = id;
       d->be.sms = p.multiProcessorCount;
-      if (const char* e = std::getenv("NRT_PREFILTER_CTAS_PER_SM")) d->be.gridPerSm = std::max(1, std::atoi(e));
       if (const char* e = std::getenv("NRT_PREFILTER_CULL")) d->be.cull = std::atoi(e) != 0;
       NRT_CUDA(cudaSetDevice(id));
       NRT_CUDA(cudaStreamCreateWithFlags(&d->be.stream, cudaStreamNonBlocking));
