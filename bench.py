@@ -205,7 +205,7 @@ STATE_BYTES_PER_SAMPLE = {
     "Shade": 102,          # R rayD 32 + active 1 + code 1;  W hitObj 4 + hitW 32 + nrm 32 (hit) | accum 24 (miss)
     "k_gate_flags": 70,    # R hitObj 4 + hitW 32 + nrm 32;  W 2 codes (one per light)
     "ShadowTrace": 72,     # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W 2 occlusion flags
-    "Resolve": 94,         # R hitObj 4 + hitW 32 + nrm 32 + 2 flags;  W accum 24
+    "Resolve": 63,         # R hitObj 4 + nrm 32 + 2 flags;  W accum 24 + active 1  (the hit point is read by point lights / continuing samples only)
     "Finalize": 25,        # R accum 24;  W 12 bytes per pixel (16 samples)
 }
 
