@@ -210,6 +210,10 @@ STATE_BYTES_PER_SAMPLE = {
 }
 
 
+# HBM bytes one frame moves per primary sample = the sum of the table above (every kernel's reads and writes)
+STATE_HBM_BYTES_PER_SAMPLE = sum(STATE_BYTES_PER_SAMPLE.values())
+
+
 def _hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -240,6 +244,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("NRT_WORKLOAD", "config4"))
     ap.add_argument("--gather", default="ipc", choices=["ipc", "gather"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # L2 between timed steps: "stream" = none needed, every frame streams its per-sample state (GBs, see
+    # config.l2 in the output) through HBM; "flush" = additionally write 256 MiB (> 126 MB L2) before every step.
+    ap.add_argument("--l2", default=os.environ.get("NRT_BENCH_L2", "stream"), choices=["stream", "flush"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -330,8 +337,9 @@ def main():
     dbg = []
     for _ in range(args.steps):
         ta = time.perf_counter()
-        flush.fill_(1)                      # L2 flush between timed iterations
-        torch.cuda.synchronize()
+        if args.l2 == "flush":
+            flush.fill_(1)                  # L2 flush between timed iterations
+            torch.cuda.synchronize()
         tb = time.perf_counter()
         step_resident()
         tc = time.perf_counter()
@@ -443,6 +451,9 @@ def main():
             roofline = {
                 "bound": "hbm", "kernel": dom["kernel"], "achieved": dom.get("achieved_GBps"), "peak": hbm_peak, "unit": "GB/s",
                 "frac": dom.get("frac_of_hbm_peak"), "traffic": _traffic(args.workload, dom["kernel"]),
+                "traffic_launch": "the family's bounce-0 launch of a whole config-4 frame (every primary sample, 132.7 M; ncu --set full, "
+                                  "profiles/kernel_traffic.json); the later bounces' launches process a few percent of that each",
+                "traffic_launch_algorithmic_bytes": STATE_BYTES_PER_SAMPLE.get(next((k for k in STATE_BYTES_PER_SAMPLE if dom["kernel"].startswith(k)), ""), 0) * 132710400.0,
                 "algorithmic_bytes_per_launch": dom.get("algorithmic_bytes", 0) / max(dom["launches"], 1),
                 "avg_launch_ms": dom["ms"] / max(dom["launches"], 1), "kernel_share_of_step": dom["share"],
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth measured on this pool)",
@@ -450,12 +461,17 @@ def main():
                         "bench.py, DESIGN.md section 6) x primary samples / the family's CUDA-event time; the kernel is issue/latency bound "
                         "below the HBM roofline (profiles/)",
             }
+        state_gb = STATE_HBM_BYTES_PER_SAMPLE * samples / 1e9
+        l2_note = ("256 MiB device fill between timed steps (inside the timed region)" if args.l2 == "flush" else
+                   f"inputs larger than L2: every frame streams {state_gb:.1f} GB of per-sample state per GPU through HBM "
+                   f"(>= {state_gb * 1e3 / 126:.0f}x the 126 MB L2), so nothing a step reads survives from the previous one except the "
+                   "scene records (L2-resident within a step as well); --l2 flush adds a 256 MiB fill per step")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 filter + f64 exact", "data": "synthetic",
             "config": {"workload": desc, "parallelism": f"scanline-interleaved x{world}, {'CUDA-IPC peer stores' if peer is not None else 'NCCL row gather'} to rank 0",
-                       "l2": "256 MiB device fill between timed steps (inside the timed region)",
+                       "l2": l2_note,
                        "warmup_extra_steps": extra_warm},
             "frames_per_s": args.steps / (t_ms * 1e-3), "rays_per_frame": total_rays / args.steps,
             "device_ms_per_step": ms_dev.value / args.steps,
