@@ -204,14 +204,15 @@ STATE_BYTES_PER_SAMPLE = {
     "gen+gate": 34,        # W rayD 32 + active 1 + gate code 1
     "Shade": 102,          # R rayD 32 + active 1 + code 1;  W hitObj 4 + hitW 32 + nrm 32 (hit) | accum 24 (miss)
     "k_gate_flags": 70,    # R hitObj 4 + hitW 32 + nrm 32;  W 2 codes (one per light)
-    "ShadowTrace": 72,     # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W 2 occlusion flags
+    "ShadowTrace": 72,     # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W 2 occlusion flags   (NRT_FUSE_RESOLVE=0)
+    "ShadowResolve": 95,   # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W accum 24 + active 1  (ShadowTrace + Resolve in one launch)
     "Resolve": 63,         # R hitObj 4 + nrm 32 + 2 flags;  W accum 24 + active 1  (the hit point is read by point lights / continuing samples only)
     "Finalize": 25,        # R accum 24;  W 12 bytes per pixel (16 samples)
 }
 
 
-# HBM bytes one frame moves per primary sample = the sum of the table above (every kernel's reads and writes)
-STATE_HBM_BYTES_PER_SAMPLE = sum(STATE_BYTES_PER_SAMPLE.values())
+# HBM bytes one frame moves per primary sample = the sum of the launched kernels' reads and writes
+STATE_HBM_BYTES_PER_SAMPLE = sum(v for k, v in STATE_BYTES_PER_SAMPLE.items() if k not in ("ShadowTrace", "Resolve"))
 
 
 def _hbm_peak():

@@ -30,6 +30,11 @@
 #ifndef NRT_OCC_ST
 #define NRT_OCC_ST 0
 #endif
+// ShadowResolve (ShadowTrace + Resolve in one launch): 80 registers with ~100 bytes of spills in the
+// Resolve tail (7.1 ms); 116 registers without spills at 2 CTAs/SM measured 8.5 ms
+#ifndef NRT_OCC_SR
+#define NRT_OCC_SR NRT_OCC_ST
+#endif
 #ifndef NRT_OCC_SHADE
 #define NRT_OCC_SHADE 0
 #endif
@@ -100,6 +105,7 @@ __device__ __forceinline__ void blockStatsAdd(const StatDelta& d, unsigned long 
 template <class F> struct MinBlocks { static constexpr int v = NRT_OCC_DEFAULT; };
 template <> struct MinBlocks<ShadowTrace> { static constexpr int v = NRT_OCC_ST; };
 template <bool CL> struct MinBlocks<ShadowTraceSampleT<CL>> { static constexpr int v = NRT_OCC_ST; };
+template <bool CL> struct MinBlocks<ShadowResolveT<CL>> { static constexpr int v = NRT_OCC_SR; };
 template <bool CL> struct MinBlocks<ShadeT<CL>> { static constexpr int v = NRT_OCC_SHADE; };
 template <class F>
 __global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats(F f, int64_t n, unsigned long long* stats) {
@@ -732,10 +738,11 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float 
 // CUDA events on the render stream.  Off by default (the events cost a little); bench.py turns it on
 // for an untimed frame to report each kernel family's share of the step.
 enum KernelCat { KC_GEN = 0, KC_GATE_FLAGS, KC_GATE_SCAN, KC_GATE_WRITE, KC_PREFILTER, KC_REFINE, KC_EXACT, KC_VERIFY,
-                 KC_SHADE, KC_SHADOW_TRACE, KC_RESOLVE, KC_COMPACT, KC_FINALIZE, KC_OTHER, KC_COUNT };
+                 KC_SHADE, KC_SHADOW_TRACE, KC_RESOLVE, KC_COMPACT, KC_FINALIZE, KC_OTHER, KC_SHADOW_RESOLVE, KC_COUNT };
 static const char* const kKernelCatNames[KC_COUNT] = {
   "gen+gate (GenGate / GenSimple / GenJittered)", "k_gate_flags", "k_gate_scan", "k_gate_write", "k_mesh_prefilter", "Refine",
-  "ExactMesh", "Verify1+Verify2", "Shade", "ShadowTrace", "Resolve", "compactActive (cub select)", "Finalize", "other"};
+  "ExactMesh", "Verify1+Verify2", "Shade", "ShadowTrace", "Resolve", "compactActive (cub select)", "Finalize", "other",
+  "ShadowResolve (ShadowTrace + Resolve)"};
 static_assert(KC_COUNT <= NRT_KERNEL_CATEGORIES, "nrt_kernel_times is too small");
 template <class F> struct CatOf { static constexpr int v = KC_OTHER; };
 template <> struct CatOf<GenSimple> { static constexpr int v = KC_GEN; };
@@ -745,6 +752,7 @@ template <> struct CatOf<ShadowGate> { static constexpr int v = KC_GATE_FLAGS; }
 template <bool CL> struct CatOf<ShadeT<CL>> { static constexpr int v = KC_SHADE; };
 template <> struct CatOf<ShadowTrace> { static constexpr int v = KC_SHADOW_TRACE; };
 template <bool CL> struct CatOf<ShadowTraceSampleT<CL>> { static constexpr int v = KC_SHADOW_TRACE; };
+template <bool CL> struct CatOf<ShadowResolveT<CL>> { static constexpr int v = KC_SHADOW_RESOLVE; };
 template <> struct CatOf<Resolve> { static constexpr int v = KC_RESOLVE; };
 template <> struct CatOf<Finalize> { static constexpr int v = KC_FINALIZE; };
 template <> struct CatOf<ExactMesh> { static constexpr int v = KC_EXACT; };

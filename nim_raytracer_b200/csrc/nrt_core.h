@@ -28,6 +28,13 @@
 #else
 #define NRT_KEEP_D(x) ((void)0)
 #endif
+// Compiler-level fence (no instruction): loads written after it are issued after it — neither hoisted
+// above the code before it nor served from a value loaded earlier and kept alive in registers.
+#if defined(__CUDA_ARCH__) && !defined(NRT_NO_FENCE)
+#define NRT_COMPILER_FENCE() asm volatile("" ::: "memory")
+#else
+#define NRT_COMPILER_FENCE() ((void)0)
+#endif
 
 namespace nrt {
 

@@ -424,6 +424,7 @@ struct Renderer {
   int64_t launches_hint = 0;
   bool shadowGatePerSample = envInt("NRT_SHADOW_GATE_PER_SAMPLE", 1) != 0;
   bool shadowTracePerSample = envInt("NRT_SHADOW_TRACE_PER_SAMPLE", 1) != 0;
+  bool fuseResolve = envInt("NRT_FUSE_RESOLVE", 1) != 0;   // ShadowTrace + Resolve in one launch (per-sample shadow kernels, <= 32 lights)
   // one entry per prefilter launch of the last frame, in launch order (NRT_TRACE_PREFILTER)
   struct PreLaunch { int wave, mo, b, mode; int64_t rays, work, pre, nch; };
   std::vector<PreLaunch> preLog;
@@ -610,12 +611,18 @@ struct Renderer {
           else be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act, bounce}, cs.stats);
           if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, bounce, force_exact, false);
           ++wave;
-          if (nL > 0) {
-            if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowTraceSampleClustered{sd.d, fp, cs, act}, cs.stats);
-            else if (shadowTracePerSample) be->forEachStats(nullptr, act.n, ShadowTraceSample{sd.d, fp, cs, act}, cs.stats);
-            else be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
+          const int pl = sd.anyPointLight ? 1 : 0;
+          if (nL > 0 && nL <= 32 && fuseResolve && (sd.h.ncl1 > 0 || shadowTracePerSample)) {
+            if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowResolveClustered{sd.d, fp, cs, act, bounce, pl}, cs.stats);
+            else be->forEachStats(nullptr, act.n, ShadowResolve{sd.d, fp, cs, act, bounce, pl}, cs.stats);
+          } else {
+            if (nL > 0) {
+              if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowTraceSampleClustered{sd.d, fp, cs, act}, cs.stats);
+              else if (shadowTracePerSample) be->forEachStats(nullptr, act.n, ShadowTraceSample{sd.d, fp, cs, act}, cs.stats);
+              else be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
+            }
+            be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act, bounce, pl}, cs.stats);
           }
-          be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act, bounce, sd.anyPointLight ? 1 : 0}, cs.stats);
           if (bounce >= maxBounces) break;
           be->compactActive(cs, act, nextList, nextCount);
           uint32_t cont = 0;
