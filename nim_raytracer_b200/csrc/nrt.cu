@@ -108,8 +108,12 @@ template <bool CL> struct MinBlocks<ShadowTraceSampleT<CL>> { static constexpr i
 template <bool CL> struct MinBlocks<ShadowResolveT<CL>> { static constexpr int v = NRT_OCC_SR; };
 template <bool CL> struct MinBlocks<ShadeT<CL>> { static constexpr int v = NRT_OCC_SHADE; };
 template <class F>
-__global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats(F f, int64_t n, unsigned long long* stats) {
+__global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats(F f, int64_t n, unsigned long long* stats, int64_t ahead) {
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  // A thread lives for one element: its first instruction after the index arithmetic waits for DRAM.
+  // Requesting the inputs of the element `ahead` positions later into L2 (about one wave of CTAs ahead)
+  // turns that wait into an L2 hit for the thread that will own it.
+  if (ahead > 0 && i + ahead < n) f.prefetch(i + ahead);
   StatDelta d = zeroStats();
   if (i < n) d = f(i);
   blockStatsAdd(d, stats);
@@ -224,9 +228,13 @@ __device__ __forceinline__ void produceCounts(const ChunkState& cs, const uint32
   }
 }
 template <class P>
-__global__ void __launch_bounds__(kBlock) k_produce_gate(P p, ChunkState cs, int64_t n, int mult, int nMO, uint32_t* neCount) {
+__global__ void __launch_bounds__(kBlock) k_produce_gate(P p, ChunkState cs, int64_t n, int mult, int nMO, uint32_t* neCount, int64_t ahead) {
   extern __shared__ uint32_t sh_pc[];   // mult * rows
   const int nB = 1 + cs.nL, nRow = nB + 1, rows = nMO * nRow;
+  {   // (see k_for_each_stats)
+    const int64_t j = int64_t(blockIdx.x) * kBlock + threadIdx.x + ahead;
+    if (ahead > 0 && j < n) p.prefetch(j);
+  }
   for (int k = threadIdx.x; k < mult * rows; k += kBlock) sh_pc[k] = 0;
   __syncthreads();
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
@@ -772,6 +780,7 @@ struct CudaBackend {
   std::vector<int> filterModes;
   bool cull = true;    // NRT_PREFILTER_CULL=0: evaluate every chunk (brute force over the record set)
   int splitBelow = 8;  // NRT_PREFILTER_SPLIT: measured on the 1/8-frame partitions of an 8-GPU run (2: 1.08 ms of prefilter, 8: 1.04, 32: 1.01; full frame unchanged)
+  int64_t prefetchAhead = 0;   // elements ahead the per-sample kernels prefetch into L2 (NRT_PREFETCH_AHEAD; 0 = off): set in init
   bool smemOptIn = false;
   static constexpr size_t kPinnedBytes = 1 << 16;
   void* pinned = nullptr;
@@ -860,7 +869,7 @@ struct CudaBackend {
     use();
     if (n <= 0) return;
     Timed tm(this, CatOf<F>::v);
-    k_for_each_stats<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, stats);
+    k_for_each_stats<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, stats, prefetchAhead);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   template <class F> void forEachCounted(const uint32_t* count, int64_t cap, const F& f) {
@@ -918,7 +927,7 @@ struct CudaBackend {
     const size_t sm = sizeof(uint32_t) * size_t(mult) * nMO * (2 + cs.nL);
     (void)stats;
     Timed tm(this, CatOf<P>::v);
-    k_produce_gate<P><<<blocksFor(n), kBlock, sm, stream>>>(p, cs, n, mult, nMO, cnt + CNT_NE);
+    k_produce_gate<P><<<blocksFor(n), kBlock, sm, stream>>>(p, cs, n, mult, nMO, cnt + CNT_NE, prefetchAhead);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   void gateFinish(const Gate& g, int64_t n, int nMO, uint32_t* cnt) {
@@ -1196,6 +1205,8 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
       be.launches = 0;
       if (const char* e = std::getenv("NRT_PREFILTER_CULL")) be.cull = std::atoi(e) != 0; else be.cull = true;
       if (const char* e = std::getenv("NRT_PREFILTER_SPLIT")) be.splitBelow = std::max(0, std::atoi(e));
+      if (const char* e = std::getenv("NRT_PREFETCH_AHEAD")) be.prefetchAhead = std::max<int64_t>(0, std::atoll(e));
+      else be.prefetchAhead = int64_t(be.sms) * 1024;
       NRT_CUDA(cudaEventRecord(dc->ev0, be.stream));
       // Host <-> staging copies of exactly the rows this worker renders (and their step x step
       // fill rows); equally spaced rows (scanline interleave) go out as one 2D copy.

@@ -36,6 +36,13 @@
 #define NRT_COMPILER_FENCE() ((void)0)
 #endif
 
+// Requests the line of `p` into L2 without a register or a scoreboard entry (no-op on the host).
+#if defined(__CUDA_ARCH__)
+#define NRT_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#else
+#define NRT_PREFETCH_L2(p) ((void)0)
+#endif
+
 namespace nrt {
 
 // ---------------------------------------------------------------- constants --

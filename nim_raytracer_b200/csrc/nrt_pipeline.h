@@ -132,6 +132,11 @@ NRT_HD int64_t queueBase(const ChunkState& cs, int mo, int b) {
 }
 
 NRT_HD V4 ld4(const double* a, int64_t n, int64_t i) { return v4(a[i], a[n + i], a[2 * n + i], a[3 * n + i]); }
+// L2 prefetch of the four planes of SoA vector i (see k_for_each_stats: the streaming kernels request the
+// inputs of the element `ahead` positions later, which a CTA scheduled about one wave later will read)
+NRT_HD void pf4(const double* a, int64_t n, int64_t i) {
+  NRT_PREFETCH_L2(a + i); NRT_PREFETCH_L2(a + n + i); NRT_PREFETCH_L2(a + 2 * n + i); NRT_PREFETCH_L2(a + 3 * n + i);
+}
 NRT_HD void st4(double* a, int64_t n, int64_t i, V4 v) { a[i] = v.x; a[n + i] = v.y; a[2 * n + i] = v.z; a[3 * n + i] = v.w; }
 
 // 64-bit integer division is a long instruction sequence on the GPU; every index on this path fits 32 bits
@@ -582,6 +587,13 @@ template <bool CL>
 struct ShadeT {
   const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce;
   NRT_HD StatDelta operator()(int64_t idx) const { ShadeOut out; return run(idx, out); }
+  NRT_HD void prefetch(int64_t idx) const {   // inputs of wave position idx (identity active set only)
+    if (act.list) return;
+    pf4(cs.rayD, cs.S, idx);
+    NRT_PREFETCH_L2(cs.active + idx);
+    if (cs.nMO > 0) NRT_PREFETCH_L2(cs.gflag + idx);
+    if (bounce != 0) pf4(cs.rayO, cs.S, idx);
+  }
   NRT_HD StatDelta run(int64_t idx, ShadeOut& out) const {
     StatDelta st = zeroStats();
     out.hit = false; out.s = 0;
@@ -648,6 +660,7 @@ using ShadeClustered = ShadeT<true>;
 // shadow-ray gate was measured slower on B200: 98 registers, two shadow rays per thread in sequence.)
 struct GenGate {      // primary rays: position == sample, mult == 1
   GenSimple gen; Gate gate; int nMO;
+  NRT_HD void prefetch(int64_t) const {}   // (no inputs in memory)
   template <class E> NRT_HD void operator()(int64_t s, E& emit) const {
     GenOut out; gen.run(s, out);
     for (int mo = 0; mo < nMO; ++mo)
@@ -659,6 +672,12 @@ struct GenGate {      // primary rays: position == sample, mult == 1
 // idx * nL + l): the hit record is loaded once and the shared origin hitW + n * bias is formed once.
 struct ShadowGate {   // gate.kind == WAVE_SHADOW, mult == nL
   Gate gate; int nMO;
+  NRT_HD void prefetch(int64_t idx) const {   // the hit record of wave position idx (identity active set only)
+    if (gate.act.list) return;
+    const ChunkState& cs = gate.cs;
+    pf4(cs.hitW, cs.S, idx); pf4(cs.nrm, cs.S, idx);
+    NRT_PREFETCH_L2(cs.hitObj + idx);
+  }
   template <class E> NRT_HD void operator()(int64_t idx, E& emit) const {
     const ChunkState& cs = gate.cs;
     const int64_t s = sampleOf(gate.act, idx);
@@ -682,6 +701,7 @@ struct ShadowGate {   // gate.kind == WAVE_SHADOW, mult == nL
 // call of renderer.nim:101-102; only "some object hit before the light" is kept (renderer.nim:103)
 struct ShadowTrace {
   const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
+  NRT_HD void prefetch(int64_t) const {}
   NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
     const int64_t si = divFast(idx, cs.nL);
@@ -703,6 +723,12 @@ struct ShadowTrace {
 template <bool CL>
 struct ShadowTraceSampleT {
   const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
+  NRT_HD void prefetch(int64_t idx) const {   // the hit record and gate codes of wave position idx (identity active set only)
+    if (act.list) return;
+    pf4(cs.hitW, cs.S, idx); pf4(cs.nrm, cs.S, idx);
+    NRT_PREFETCH_L2(cs.hitObj + idx);
+    if (cs.nMO > 0) NRT_PREFETCH_L2(cs.gflag + idx * cs.nL);
+  }
   NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
     if (idx >= activeN(act)) return st;
@@ -783,6 +809,7 @@ NRT_HD void resolveSample(const DScene* sc, const FrameParams& fp, const ChunkSt
 struct Resolve {
   const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce;
   int pointLights;   // some light is a PointLight: getShadingInfo needs the hit point (a DistantLight ignores it)
+  NRT_HD void prefetch(int64_t) const {}
   NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
     if (idx >= activeN(act)) return st;
@@ -811,6 +838,12 @@ struct Resolve {
 template <bool CL>
 struct ShadowResolveT {
   const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce; int pointLights;
+  NRT_HD void prefetch(int64_t idx) const {   // the hit record and gate codes of wave position idx (identity active set only)
+    if (act.list) return;
+    pf4(cs.hitW, cs.S, idx); pf4(cs.nrm, cs.S, idx);
+    NRT_PREFETCH_L2(cs.hitObj + idx);
+    if (cs.nMO > 0) NRT_PREFETCH_L2(cs.gflag + idx * cs.nL);
+  }
   NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
     if (idx >= activeN(act)) return st;
