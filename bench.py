@@ -375,10 +375,26 @@ def main():
               for g in {id(o.geometry): o.geometry for o in scene.objects if o.geometry.kind == api.NRT_GEOM_MESH}.values())
     h2d += len(scene.objects) * C.sizeof(api.nrt_object) + len(scene.lights) * C.sizeof(api.nrt_light) + 512
 
+    pinned_inputs = api.pinSceneArrays(scene)   # the step's inputs are copied from pinned host memory
+    # N > 1: one host framebuffer shared by the ranks of the node (POSIX shared memory, page-locked in every
+    # rank); each rank's nrt_render copies the scanlines it rendered into it over its own PCIe link.  Fallback
+    # (no /dev/shm space, registration refused): peer stores into rank 0's device buffer + one copy from there.
+    shared = None
+    if world > 1:
+        try:
+            shared = D.SharedHostFramebuffer(fb_bytes, rank, world, dist)
+            host_fb = shared.array
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] shared host framebuffer unavailable ({e}); rank 0 copies the gathered frame", file=sys.stderr)
+
     def step_e2e():
         ds.update()                                           # scene: host -> device (+ device-side precompute)
         if world == 1:
             api.check(L.nrt_render(ds.handle, C.byref(co), 0, H, 1, 1, hp, C.byref(cs), None), "nrt_render")
+        elif shared is not None:
+            api.check(L.nrt_render(ds.handle, C.byref(co), 0, H, 1, 1, shared.ptr, C.byref(cs), None), "nrt_render")
+            barrier()
         else:
             out = step_resident()
             barrier()
@@ -399,7 +415,11 @@ def main():
     e_ms = allreduce((time.perf_counter() - t0) * 1e3, OP.MAX if OP else None)
     rays_e = allreduce(float(rays_e), OP.SUM if OP else None)
     e2e = {"value": rays_e / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": fb_bytes + 64,
-           "ms_per_step": e_ms / args.steps, "frames_per_s": args.steps / (e_ms * 1e-3)}
+           "ms_per_step": e_ms / args.steps, "frames_per_s": args.steps / (e_ms * 1e-3),
+           "host_inputs": f"{len(pinned_inputs)} mesh arrays page-locked in place (nrt_host_register), small structs pageable",
+           "host_framebuffer": ("pinned, one process" if world == 1 else
+                                "shared by the ranks (POSIX shared memory, page-locked): every rank copies its own scanlines" if shared is not None
+                                else "rank 0 copies the frame gathered on its device")}
     checksum = float(np.asarray(host_fb, dtype=np.float64).sum()) if rank == 0 else 0.0
 
     # ---- per-kernel-family shares: one untimed frame with every launch bracketed by CUDA events ----
@@ -483,6 +503,11 @@ def main():
             line["cpu_baseline"] = cpu_baseline(ds.desc, opts, total_rays / args.steps)
         print(json.dumps(line), flush=True)
 
+    api.unpinSceneArrays(pinned_inputs)
+    del host_fb
+    if shared is not None:
+        barrier()
+        shared.close()
     L.nrt_host_free_pinned(hp)
     if peer is not None:
         barrier()

@@ -287,6 +287,12 @@ int nrt_timer_end(double* ms);
 /* Pinned host memory helpers for callers that want async D2H (bench e2e). */
 int nrt_host_alloc_pinned(int64_t bytes, void** host_ptr);
 int nrt_host_free_pinned(void* host_ptr);
+/* Page-locks caller-owned host memory (e.g. the Framebuf's data, or a shared-memory
+ * framebuffer several worker processes write their scanlines into, as the threads of
+ * src/raytracer.nim:67-70 do with one Framebuf) so that nrt_render copies at full
+ * PCIe speed.  Optional: nrt_render accepts pageable memory as well. */
+int nrt_host_register(void* host_ptr, int64_t bytes);
+int nrt_host_unregister(void* host_ptr);
 
 #ifdef __cplusplus
 }

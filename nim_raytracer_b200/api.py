@@ -177,6 +177,8 @@ def lib() -> C.CDLL:
     L.nrt_timer_end.argtypes = [C.POINTER(C.c_double)]
     L.nrt_host_alloc_pinned.argtypes = [i64, C.POINTER(vp)]
     L.nrt_host_free_pinned.argtypes = [vp]
+    L.nrt_host_register.argtypes = [vp, i64]
+    L.nrt_host_unregister.argtypes = [vp]
     _lib = L
     return L
 
@@ -486,6 +488,27 @@ class DeviceScene:
             self.close()
         except Exception:
             pass
+
+
+def pinSceneArrays(scene: Scene) -> list:
+    """Page-locks the mesh arrays of `scene` in place (nrt_host_register) so that DeviceScene /
+    update() upload them at full PCIe speed; returns the arrays that were registered (pass them to
+    unpinSceneArrays before they are freed).  Arrays the driver refuses stay pageable."""
+    done, seen = [], set()
+    for o in scene.objects:
+        g = o.geometry
+        if g.kind != NRT_GEOM_MESH or id(g) in seen:
+            continue
+        seen.add(id(g))
+        for a in (g.vertices, g.normals, g.vertexIdx, g.normalIdx):
+            if a.nbytes >= (1 << 16) and lib().nrt_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes) == 0:
+                done.append(a)
+    return done
+
+
+def unpinSceneArrays(arrays: list) -> None:
+    for a in arrays:
+        lib().nrt_host_unregister(a.ctypes.data_as(C.c_void_p))
 
 
 def _as_device_scene(scene) -> DeviceScene:

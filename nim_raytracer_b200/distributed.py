@@ -13,6 +13,12 @@ rank 0 in one of two ways:
   * "gather" — every rank renders into a local buffer and the rows are gathered
              with torch.distributed (NCCL on GPUs, gloo in the CPU tests).
 
+For HOST framebuffers (the reference's Framebuf) SharedHostFramebuffer maps one
+POSIX shared-memory buffer into every rank of the node: each rank's nrt_render copies
+the scanlines it rendered into it over its own PCIe link, exactly as the reference's
+worker threads write disjoint rows of one Framebuf (src/raytracer.nim:67-70) — no
+device gather and no single-GPU 100 MB device-to-host copy.
+
 torch.distributed is used for rendezvous, barriers, the max-over-ranks timing
 reduction and (only in "gather" mode) the row gather.
 """
@@ -97,3 +103,82 @@ class PeerFramebuffer:
             else:
                 L.nrt_ipc_close(self.ptr)
             self.ptr = C.c_void_p()
+
+
+class SharedHostFramebuffer:
+    """Host framebuffer (float32, nbytes) shared by the ranks of one node through /dev/shm and
+    page-locked in every rank (nrt_host_register), so that each rank's nrt_render() delivers its
+    own scanlines with a pinned 2-D copy.  `register=False` skips the page-locking (CPU tests).
+    Raises on every rank if any rank failed, so that callers can fall back together."""
+
+    def __init__(self, nbytes: int, rank: int, world: int, dist=None, register: bool = True):
+        import mmap
+        import os
+
+        self.rank, self.world, self.nbytes = rank, world, nbytes
+        self.path, self.mm, self.array, self.registered = None, None, None, False
+        self.api = None
+        box = [None]
+        if rank == 0:
+            path = f"/dev/shm/nrt_fb_{os.getpid()}_{id(self) & 0xFFFF:x}"
+            try:
+                fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                try:
+                    os.posix_fallocate(fd, 0, nbytes)      # ENOSPC here instead of SIGBUS on first touch
+                    self.mm = mmap.mmap(fd, nbytes)
+                finally:
+                    os.close(fd)
+                self.path = box[0] = path
+            except OSError:
+                if os.path.exists(path):
+                    os.unlink(path)
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        ok = box[0] is not None
+        if ok and rank != 0:
+            try:
+                fd = os.open(box[0], os.O_RDWR)
+                try:
+                    self.mm = mmap.mmap(fd, nbytes)
+                finally:
+                    os.close(fd)
+                self.path = box[0]
+            except OSError:
+                ok = False
+        if ok:
+            self.array = np.frombuffer(self.mm, dtype=np.float32)
+            if register:
+                from . import api
+
+                self.api = api
+                rc = api.lib().nrt_host_register(C.c_void_p(self.array.ctypes.data), nbytes)
+                self.registered = rc == 0
+                ok = self.registered
+        if world > 1:
+            flags = [None] * world
+            dist.all_gather_object(flags, bool(ok))
+            ok = all(flags)
+        if not ok:
+            self.close()
+            raise RuntimeError("shared host framebuffer unavailable (/dev/shm space or cudaHostRegister)")
+
+    @property
+    def ptr(self) -> C.c_void_p:
+        return C.c_void_p(self.array.ctypes.data)
+
+    def close(self) -> None:
+        import os
+
+        if self.registered and self.array is not None:
+            self.api.lib().nrt_host_unregister(C.c_void_p(self.array.ctypes.data))
+            self.registered = False
+        self.array = None
+        if self.mm is not None:
+            try:
+                self.mm.close()
+            except BufferError:      # a caller still holds a view: the mapping goes with the process
+                pass
+            self.mm = None
+        if self.rank == 0 and self.path and os.path.exists(self.path):
+            os.unlink(self.path)
+        self.path = None

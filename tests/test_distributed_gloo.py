@@ -29,6 +29,16 @@ def _worker(rank, world, port, out_path):
         rays += st.numRays
     t = torch.from_numpy(fb.image().copy())
     full = D.gather_rows(t, rank, world, dist)
+    # the same frame through the shared host framebuffer: every rank writes its own rows, no gather
+    shared = D.SharedHostFramebuffer(o.width * o.height * 12, rank, world, dist, register=False)
+    img = shared.array.reshape(o.height, o.width, 3)
+    D.merge_rows(img, fb.image(), rank, world)
+    dist.barrier()
+    if rank == 0:
+        assert (img == full.numpy()).all()
+    del img
+    dist.barrier()
+    shared.close()
     tot = torch.tensor([rays], dtype=torch.int64)
     dist.all_reduce(tot)
     ms = torch.tensor([float(rank + 1)], dtype=torch.float64)
