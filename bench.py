@@ -205,7 +205,8 @@ STATE_BYTES_PER_SAMPLE = {
     "Shade": 102,          # R rayD 32 + active 1 + code 1;  W hitObj 4 + hitW 32 + nrm 32 (hit) | accum 24 (miss)
     "k_gate_flags": 70,    # R hitObj 4 + hitW 32 + nrm 32;  W 2 codes (one per light)
     "ShadowTrace": 72,     # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W 2 occlusion flags   (NRT_FUSE_RESOLVE=0)
-    "ShadowResolve": 95,   # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W accum 24 + active 1  (ShadowTrace + Resolve in one launch)
+    "ShadowResolve": 95,   # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W accum 24 + active 1  (ShadowTrace + Resolve in one launch;
+                           # a continuing sample adds 136: ray in, ray + origin + weight out - ncu: 102.6 B per sample on config 4)
     "Resolve": 63,         # R hitObj 4 + nrm 32 + 2 flags;  W accum 24 + active 1  (the hit point is read by point lights / continuing samples only)
     "Finalize": 25,        # R accum 24;  W 12 bytes per pixel (16 samples)
 }
