@@ -310,6 +310,32 @@ def test_scene_update_and_srgb_output(oracle_mod):
     assert (img.astype(np.int32) == ref8).mean() > 0.999
 
 
+def test_page_locked_caller_memory(oracle_mod):
+    # nrt_host_register: the caller's framebuffer and mesh arrays page-locked in place (what bench.py's e2e
+    # leg and a shared multi-process host framebuffer do); results and error behaviour unchanged
+    import ctypes as C
+    L = api.lib()
+    sc, o = scenes.bunny(stride=16), api.Options(200, 120)
+    pinned = api.pinSceneArrays(sc)
+    assert 1 <= len(pinned) <= 4
+    ds = api.DeviceScene(sc)
+    fb = api.newFramebuf(o.width, o.height)
+    p = fb.data.ctypes.data_as(C.c_void_p)
+    assert L.nrt_host_register(p, fb.data.nbytes) == 0
+    assert L.nrt_host_register(p, fb.data.nbytes) != 0          # already registered: an error code, not a crash
+    assert b"cudaHostRegister" in L.nrt_last_error()
+    try:
+        st = api.renderFrame(ds, o, fb)
+        ds.update()                                               # uploads from the page-locked arrays
+        st2 = api.renderFrame(ds, o, fb)
+    finally:
+        assert L.nrt_host_unregister(p) == 0
+        api.unpinSceneArrays(pinned)
+    rfb, rst, _ = oracle_mod.render(sc, o)
+    assert (fb.data == rfb.data).all() and st == rst and st2 == rst
+    assert L.nrt_host_register(None, 16) != 0 and L.nrt_host_unregister(None) == 0
+
+
 def test_output_stage_16_bit_and_rgba(tmp_path):
     # utils/framebuf.nim:55-93 (any maxval, big-endian 16-bit samples) and utils/image.nim:45-54 on the GPU
     rs = np.random.RandomState(11)
