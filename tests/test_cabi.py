@@ -74,6 +74,25 @@ def test_no_cpu_fallback_without_gpu(built_lib):
         api.initRenderer(1)
 
 
+def test_page_locking_degrades_without_gpu(built_lib):
+    # nrt_host_register is optional: without a device it reports an error code (never aborts) and
+    # api.pinSceneArrays() simply pins nothing, so callers keep working with pageable memory
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    import numpy as np
+    from nim_raytracer_b200 import scenes
+    buf = np.zeros(1 << 16, dtype=np.float32)
+    assert built_lib.nrt_host_register(buf.ctypes.data_as(C.c_void_p), buf.nbytes) != 0
+    assert b"cudaHostRegister" in built_lib.nrt_last_error()
+    assert built_lib.nrt_host_register(None, 16) == -1 and built_lib.nrt_host_unregister(None) == 0
+    assert api.pinSceneArrays(scenes.bunny(stride=16)) == []
+
+
 def test_product_never_touches_the_oracle():
     # nothing under nim_raytracer_b200/ or include/ may import, link or name oracle/ or the emulation
     bad = []
