@@ -227,8 +227,20 @@ __device__ __forceinline__ void produceCounts(const ChunkState& cs, const uint32
     if (any) cs.gne[atomicAdd(neCount, 1u)] = uint32_t(vb);
   }
 }
+// resident CTAs per SM of the fused producer + gate kernels (0 = the compiler's choice: 64 registers, 4 CTAs).
+// Measured on B200, config 4: ShadowGate 3.67 ms at 64 registers, 4.01 at 48 (108 bytes of spills), 4.45 at 40,
+// 5.18 at 32; GenGate 2.66 / 2.71 / 2.61 / 3.19 ms.
+#ifndef NRT_OCC_PG_SHADOW
+#define NRT_OCC_PG_SHADOW 0
+#endif
+#ifndef NRT_OCC_PG_GEN
+#define NRT_OCC_PG_GEN 0
+#endif
+template <class P> struct MinBlocksPG { static constexpr int v = 0; };
+template <> struct MinBlocksPG<ShadowGate> { static constexpr int v = NRT_OCC_PG_SHADOW; };
+template <> struct MinBlocksPG<GenGate> { static constexpr int v = NRT_OCC_PG_GEN; };
 template <class P>
-__global__ void __launch_bounds__(kBlock) k_produce_gate(P p, ChunkState cs, int64_t n, int mult, int nMO, uint32_t* neCount, int64_t ahead) {
+__global__ void __launch_bounds__(kBlock, MinBlocksPG<P>::v) k_produce_gate(P p, ChunkState cs, int64_t n, int mult, int nMO, uint32_t* neCount, int64_t ahead) {
   extern __shared__ uint32_t sh_pc[];   // mult * rows
   const int nB = 1 + cs.nL, nRow = nB + 1, rows = nMO * nRow;
   {   // (see k_for_each_stats)
