@@ -219,3 +219,18 @@ def transformed_objects(stride: int = 16) -> Scene:
     ]
     return Scene(objects=objects, lights=lights, fov=55.0, cameraToWorld=_camera(0.5, 4.5, 2.0, -10.0),
                  bgColor=vec3(0.05, 0.06, 0.1))
+
+
+def with_many_lights(sc: Scene, n: int, seed: int = 5) -> Scene:
+    """`sc` lit by n - 1 random DistantLights from above and one PointLight (test scenes around the
+    32-light limit of the fused shadow + resolve kernel)."""
+    from .api import point
+    rng = np.random.default_rng(seed)
+    lights = []
+    for _ in range(n - 1):
+        x, z = rng.uniform(-1.0, 1.0, 2)
+        lights.append(DistantLight(color=vec3(*rng.uniform(0.2, 1.0, 3)), intensity=float(rng.uniform(0.05, 0.3)),
+                                   dir=L.normalize(vec(float(x), -1.0, float(z)))))
+    lights.append(PointLight(color=vec3(1.0), intensity=600.0, pos=point(2.0, 7.0, -9.0)))
+    sc.lights = lights
+    return sc

@@ -137,6 +137,19 @@ def test_extreme_scales(oracle_mod, k):
     check(sc, api.Options(48, 30, bias=0.0), oracle_mod)
 
 
+def test_separate_shadow_and_resolve_launches(oracle_mod, monkeypatch):
+    # ShadowResolve serves up to 32 lights (occlusion bits in one register); beyond that, and with
+    # NRT_FUSE_RESOLVE=0, ShadowTrace + Resolve run as separate launches through cs.occ
+    sc = scenes.bunny_spheres(stride=16)
+    o = api.Options(72, 40, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=3)
+    monkeypatch.setenv("NRT_FUSE_RESOLVE", "0")
+    check(sc, o, oracle_mod)
+    check(scenes.spheres_reflection(), api.Options(96, 72), oracle_mod)        # point light: Resolve reads the hit point
+    monkeypatch.delenv("NRT_FUSE_RESOLVE")
+    check(scenes.with_many_lights(scenes.bunny_spheres(stride=32), 32), api.Options(48, 28), oracle_mod)   # fused, all 32 bits used
+    check(scenes.with_many_lights(scenes.bunny_spheres(stride=32), 33), api.Options(48, 28), oracle_mod)   # one too many: separate launches
+
+
 def test_degenerate_meshes(oracle_mod):
     from nim_raytracer_b200 import loaders, linalg as L
     # zero-area and needle triangles, duplicated coplanar faces (first index must win)

@@ -238,6 +238,18 @@ def test_extreme_scales(oracle_mod, k):
     assert_parity(sc, api.Options(64, 40, bias=0.0), oracle_mod)
 
 
+def test_separate_shadow_and_resolve_launches(oracle_mod, monkeypatch):
+    # NRT_FUSE_RESOLVE=0 and > 32 lights: ShadowTrace + Resolve as separate launches (occlusion flags in memory)
+    sc = scenes.bunny_spheres(stride=8)
+    o = api.Options(200, 112, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=3)
+    monkeypatch.setenv("NRT_FUSE_RESOLVE", "0")
+    assert_parity(sc, o, oracle_mod)
+    assert_parity(scenes.spheres_reflection(), api.Options(160, 120), oracle_mod)
+    monkeypatch.delenv("NRT_FUSE_RESOLVE")
+    assert_parity(scenes.with_many_lights(scenes.bunny_spheres(stride=32), 32), api.Options(96, 54), oracle_mod)
+    assert_parity(scenes.with_many_lights(scenes.bunny_spheres(stride=32), 33), api.Options(96, 54), oracle_mod)
+
+
 def test_stress_scene_sphere_clusters(oracle_mod):
     # BASELINE config 5's object count class: thousands of spheres -> clustered object scan
     sc = scenes.stress(ntri=20000, nspheres=3000)
