@@ -207,6 +207,21 @@ struct Framebuf {
 };
 inline Framebuf newFramebuf(int w, int h) { Framebuf f; f.w = w; f.h = h; f.data.assign(size_t(w) * h * 3, 0.f); return f; }
 
+// Page-locks caller-owned memory for the lifetime of the object (nrt_host_register): a Framebuf's data or
+// a mesh array, so that renderLine / renderFrame / DeviceScene::update copy at full PCIe speed.  Optional:
+// when the driver refuses (no device, range already registered) the memory simply stays pageable.
+class PageLock {
+ public:
+  PageLock(void* p, size_t bytes) : p_(nrt_host_register(p, int64_t(bytes)) == NRT_OK ? p : nullptr) {}
+  explicit PageLock(Framebuf& fb) : PageLock(fb.data.data(), fb.data.size() * sizeof(float)) {}
+  ~PageLock() { if (p_) nrt_host_unregister(p_); }
+  PageLock(const PageLock&) = delete;
+  PageLock& operator=(const PageLock&) = delete;
+  bool locked() const { return p_ != nullptr; }
+ private:
+  void* p_;
+};
+
 // ---- Scene -> nrt_scene_desc (element-wise, no memcpy of glm types) -----------------------
 class DeviceScene {
  public:

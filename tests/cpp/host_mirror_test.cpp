@@ -66,6 +66,7 @@ int main(int argc, char** argv) {
       std::vector<int32_t> obj(4), tri(4); std::vector<double> th(4);
       nrt_aov aov{obj.data(), tri.data(), th.data()};
       Framebuf fb = newFramebuf(2, 2);
+      PageLock lock(fb);   // optional page-locking of the caller's framebuffer (released at scope exit)
       const nrt_options c = toC(o);
       check(nrt_render(ds.handle(), &c, 0, 2, 1, 1, fb.data.data(), nullptr, &aov), "nrt_render");
       if (!(obj[3] == 0 && tri[3] == 0 && th[3] == 5.0)) { std::cerr << "meshperftest: t = " << th[3] << "\n"; return 3; }
