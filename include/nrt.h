@@ -179,7 +179,7 @@ typedef struct nrt_profile {
 } nrt_profile;
 
 /* Device time per kernel family of one frame (measurement hook, see nrt_set_kernel_timing). */
-#define NRT_KERNEL_CATEGORIES 16
+#define NRT_KERNEL_CATEGORIES 24
 typedef struct nrt_kernel_times {
   double ms[NRT_KERNEL_CATEGORIES];        /* summed CUDA-event time of the category's launches */
   int64_t launches[NRT_KERNEL_CATEGORIES];

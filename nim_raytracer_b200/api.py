@@ -34,7 +34,8 @@ import numpy as np
 from . import linalg
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnrt.so")
+# NRT_LIB: another build of the SAME CUDA library (occupancy / flag experiments under tools/); never a fallback
+LIB_PATH = os.environ.get("NRT_LIB") or os.path.join(_HERE, "csrc", "libnrt.so")
 
 # ----------------------------------------------------------------- enums ----
 NRT_GEOM_SPHERE, NRT_GEOM_PLANE, NRT_GEOM_BOX, NRT_GEOM_MESH = 0, 1, 2, 3
@@ -106,7 +107,7 @@ class nrt_aov(C.Structure):
     ]
 
 
-NRT_KERNEL_CATEGORIES = 16
+NRT_KERNEL_CATEGORIES = 24
 
 
 class nrt_kernel_times(C.Structure):

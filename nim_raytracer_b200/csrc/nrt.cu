@@ -38,6 +38,13 @@
 #ifndef NRT_OCC_SHADE
 #define NRT_OCC_SHADE 0
 #endif
+// FusedPrimary (a whole bounce of a sample in registers) / PathTail, PathMega: the compiler's choice unless set
+#ifndef NRT_OCC_FUSED
+#define NRT_OCC_FUSED 0
+#endif
+#ifndef NRT_OCC_TAIL
+#define NRT_OCC_TAIL 0
+#endif
 #ifndef NRT_OCC_DEFAULT
 #define NRT_OCC_DEFAULT 4
 #endif
@@ -107,6 +114,7 @@ template <> struct MinBlocks<ShadowTrace> { static constexpr int v = NRT_OCC_ST;
 template <bool CL> struct MinBlocks<ShadowTraceSampleT<CL>> { static constexpr int v = NRT_OCC_ST; };
 template <bool CL> struct MinBlocks<ShadowResolveT<CL>> { static constexpr int v = NRT_OCC_SR; };
 template <bool CL> struct MinBlocks<ShadeT<CL>> { static constexpr int v = NRT_OCC_SHADE; };
+template <bool CL, int KIND> struct MinBlocks<PathSampleT<CL, KIND>> { static constexpr int v = KIND == PATH_PRIMARY ? NRT_OCC_FUSED : NRT_OCC_TAIL; };
 template <class F>
 __global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats(F f, int64_t n, unsigned long long* stats, int64_t ahead) {
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
@@ -117,6 +125,21 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats(F f,
   StatDelta d = zeroStats();
   if (i < n) d = f(i);
   blockStatsAdd(d, stats);
+}
+
+// The same over [0, min(*count, cap)) with a device-resident count (PathTail: the list is filled by the kernels
+// before it).  CTA-uniform trip count: blockStatsAdd synchronises.
+template <class F>
+__global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats_counted(F f, const uint32_t* count, int64_t cap, unsigned long long* stats) {
+  int64_t n = *count;
+  if (n > cap) n = cap;
+  for (int64_t base = int64_t(blockIdx.x) * kBlock; base < n; base += int64_t(gridDim.x) * kBlock) {
+    const int64_t i = base + threadIdx.x;
+    StatDelta d = zeroStats();
+    if (i < n) d = f(i);
+    blockStatsAdd(d, stats);
+    __syncthreads();
+  }
 }
 
 // Elements [0, min(*count, cap)) with a device-resident count (no host sync).
@@ -758,11 +781,11 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float 
 // CUDA events on the render stream.  Off by default (the events cost a little); bench.py turns it on
 // for an untimed frame to report each kernel family's share of the step.
 enum KernelCat { KC_GEN = 0, KC_GATE_FLAGS, KC_GATE_SCAN, KC_GATE_WRITE, KC_PREFILTER, KC_REFINE, KC_EXACT, KC_VERIFY,
-                 KC_SHADE, KC_SHADOW_TRACE, KC_RESOLVE, KC_COMPACT, KC_FINALIZE, KC_OTHER, KC_SHADOW_RESOLVE, KC_COUNT };
+                 KC_SHADE, KC_SHADOW_TRACE, KC_RESOLVE, KC_COMPACT, KC_FINALIZE, KC_OTHER, KC_SHADOW_RESOLVE, KC_FUSED_PRIMARY, KC_PATH_TAIL, KC_COUNT };
 static const char* const kKernelCatNames[KC_COUNT] = {
   "gen+gate (GenGate / GenSimple / GenJittered)", "k_gate_flags", "k_gate_scan", "k_gate_write", "k_mesh_prefilter", "Refine",
   "ExactMesh", "Verify1+Verify2", "Shade", "ShadowTrace", "Resolve", "compactActive (cub select)", "Finalize", "other",
-  "ShadowResolve (ShadowTrace + Resolve)"};
+  "ShadowResolve (ShadowTrace + Resolve)", "FusedPrimary (bounce 0 of a sample in registers)", "PathTail / PathMega (per-thread paths + mesh walk)"};
 static_assert(KC_COUNT <= NRT_KERNEL_CATEGORIES, "nrt_kernel_times is too small");
 template <class F> struct CatOf { static constexpr int v = KC_OTHER; };
 template <> struct CatOf<GenSimple> { static constexpr int v = KC_GEN; };
@@ -774,6 +797,7 @@ template <> struct CatOf<ShadowTrace> { static constexpr int v = KC_SHADOW_TRACE
 template <bool CL> struct CatOf<ShadowTraceSampleT<CL>> { static constexpr int v = KC_SHADOW_TRACE; };
 template <bool CL> struct CatOf<ShadowResolveT<CL>> { static constexpr int v = KC_SHADOW_RESOLVE; };
 template <> struct CatOf<Resolve> { static constexpr int v = KC_RESOLVE; };
+template <bool CL, int KIND> struct CatOf<PathSampleT<CL, KIND>> { static constexpr int v = KIND == PATH_PRIMARY ? KC_FUSED_PRIMARY : KC_PATH_TAIL; };
 template <> struct CatOf<Finalize> { static constexpr int v = KC_FINALIZE; };
 template <> struct CatOf<ExactMesh> { static constexpr int v = KC_EXACT; };
 template <class A> struct CatOf<Refine<A>> { static constexpr int v = KC_REFINE; };
@@ -882,6 +906,13 @@ struct CudaBackend {
     if (n <= 0) return;
     Timed tm(this, CatOf<F>::v);
     k_for_each_stats<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, stats, prefetchAhead);
+    NRT_CUDA(cudaGetLastError()); ++launches;
+  }
+  template <class F> void forEachStatsCounted(const uint32_t* count, int64_t cap, const F& f, unsigned long long* stats) {
+    use();
+    if (cap <= 0) return;
+    Timed tm(this, CatOf<F>::v);
+    k_for_each_stats_counted<F><<<unsigned(std::min<int64_t>(int64_t(sms) * 8, (cap + kBlock - 1) / kBlock)), kBlock, 0, stream>>>(f, count, cap, stats);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   template <class F> void forEachCounted(const uint32_t* count, int64_t cap, const F& f) {

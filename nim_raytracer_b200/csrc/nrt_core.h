@@ -178,6 +178,7 @@ struct DMesh {
 };
 
 struct BundleFrame;  // nrt_filter.h
+struct RecSet;       // nrt_filter.h
 
 struct DScene {
   int32_t nobjects, nlights, nmeshes, nmesh_objs;
@@ -197,6 +198,7 @@ struct DScene {
   const DMesh* meshes;
   const int32_t* mesh_obj_index;  // mesh object k -> object index
   const BundleFrame* frames;      // [mo * (2 + nlights) + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
+  const RecSet* recsets;          // same index: the filter record set of the bundle (per-thread mesh walk of the path kernels)
   double c2w[16];
   double cam_orig[4];             // c2w * (0,0,0,1): castPrimaryRay's origin (renderer.nim:42), the same product done once on the host
   double tan_half_fov;            // f of renderer.nim:38 (host libm, shared with nothing else)

@@ -261,6 +261,17 @@ struct BundleFrame {
   double b1[3], b2[3], f[3];   // orthonormal; f = projection axis (DIR: the shared direction, unit)
   double valid;    // 0: no usable frame (degenerate direction) => the bundle's rays are treated as GENERAL
 };
+// One filter record set (device pointers), indexed like the frames: what a thread needs to walk the
+// flattened hierarchy of a mesh object by itself (nrt_pipeline.h: meshIntersectWalk).
+struct RecSet {
+  const float* hot;      // hot records, pair-interleaved, padded to kRecPad
+  const float* bounds;   // one hot-format bound per chunk of kRecPad records
+  const float* sub;      // one hot-format bound per sub-chunk of kSubRecs records
+  const float* recs;     // full records (64-byte rows)
+  const uint32_t* ids;   // GENERAL: record position -> face (Morton order); else null (the id is in the record)
+  uint32_t nrec;         // records kept (before padding)
+  uint32_t usable;       // the set was built (valid frame)
+};
 NRT_HD int frameIndex(int nlights, int mo, int mode, int l) { return mo * (2 + nlights) + (mode == FM_GENERAL ? 0 : (mode == FM_ORIGIN ? 1 : 2 + l)); }
 
 NRT_HD void neverHitHot(int mode, float* h) {

@@ -110,6 +110,9 @@ struct ChunkState {
   uint32_t* alist;     // 2*S: compacted sample indices of the continuing paths (ping-pong per bounce)
   uint32_t* acount;    // per bounce: entries of the list consumed by that bounce
   unsigned long long* stats;  // ST_COUNT
+  // fused path (FusedPrimary / PathTail): the samples whose path continues after bounce 0, in any order
+  uint32_t* tailList;  // S entries (null: the wavefront loop handles every bounce)
+  uint32_t* tailCount; // 1
   // pixel list of this worker
   const int32_t* rows; // device array of row indices
   int64_t p0;          // first pixel (in the worker's pixel list) of this chunk
@@ -228,6 +231,10 @@ struct GenSimple {
   const DScene* sc; FrameParams fp; ChunkState cs;
   NRT_HD void operator()(int64_t s) const { GenOut out; run(s, out); }
   NRT_HD void run(int64_t s, GenOut& out) const {
+    compute(s, out);
+    initSample(cs, s, out.alive, out.d);
+  }
+  NRT_HD void compute(int64_t s, GenOut& out) const {   // the ray of sample s, nothing stored
     const int64_t sp = divFast(s, fp.spp);
     const int64_t p = cs.p0 + sp;
     const int k = int(s - sp * fp.spp);
@@ -244,7 +251,6 @@ struct GenSimple {
     // akNone: (x.float, y.float) — the pixel corner (renderer.nim:135); else x.float + sample
     castPrimaryRay(*sc, fp.aspect, fp.width, fp.height, fp.aa_kind == AA_NONE ? double(x) : double(x) + sx,
                    fp.aa_kind == AA_NONE ? double(y) : double(y) + sy, o, d);
-    initSample(cs, s, alive, d);
     out.alive = alive; out.o = o; out.d = d;
   }
 };
@@ -459,20 +465,112 @@ struct Verify2 {  // among candidates attaining the minimum, the lowest face ind
   }
 };
 
-// trace(): renderer.nim:47-67 with the mesh results looked up.  `wi` = wave-ray index.
+// ---- TriangleMesh.intersect for ONE ray by ONE thread (the path kernels below) -------------------
+// The AABB gate (geom.nim:340), then a walk of the same flattened hierarchy the wavefront prefilter uses
+// (chunk bounds -> sub-chunk bounds -> the face's bounding circle / sphere -> float32 sign test), and the
+// reference's float64 evaluation of the survivors.  Every float32 stage is conservative, so the result —
+// nearest accepted t, lowest face index on ties (geom.nim:346-356) — is the reference's whatever the
+// bundle `mode` used for the walk.  Rays the filter cannot take go through all faces in float64.
+struct MeshHit { double t; uint32_t tri; };
+NRT_HD bool meshGatePass(const DScene& sc, int mo, V4 o, V4 d) {
+  const DObject& ob = sc.objects[sc.mesh_obj_index[mo]];
+  const DMesh& m = sc.meshes[ob.mesh];
+  V4 oo, dd;
+  toObject(ob, o, d, oo, dd);                      // renderer.nim:54-55
+  if (boxCertainMiss(m, oo, dd)) return false;
+  const double tmin = aabbIntersect(m.bmin, m.bmax, initRay(oo, dd));
+  return !(tmin < 0);
+}
+NRT_HD MeshHit meshIntersectWalk(const DScene& sc, int mo, int mode, int l, V4 o, V4 d, int force_exact) {
+  MeshHit h; h.t = NRT_NEG_INF; h.tri = kNoTri;
+  const DObject& ob = sc.objects[sc.mesh_obj_index[mo]];
+  const DMesh& m = sc.meshes[ob.mesh];
+  V4 oo, dd;
+  toObject(ob, o, d, oo, dd);                      // renderer.nim:54-55
+  if (boxCertainMiss(m, oo, dd)) return h;
+  const Ray r = initRay(oo, dd);
+  if (aabbIntersect(m.bmin, m.bmax, r) < 0) return h;   // geom.nim:340 (NegInf: no box hit)
+  double best = NRT_INF; uint32_t bt = kNoTri;     // geom.nim:343
+  if (mode != FM_GENERAL && !(sc.frames[frameIndex(sc.nlights, mo, mode, l)].valid > 0)) mode = FM_GENERAL;
+  const int fi = frameIndex(sc.nlights, mo, mode, l);
+  const RecSet rs = sc.recsets[fi];
+  FilterRay fr; HotRay hr;
+  const bool safe = !force_exact && rs.usable && makeFilterRay(mode, m, r, fr) && makeHotRay(mode, sc.frames[fi], r, hr);
+  if (!safe) {
+    for (int64_t f = 0; f < m.nfaces; ++f) {       // geom.nim:346-356
+      const double t = rayTriangleExact(r, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2]);
+      if (t >= 0 && t < best) { best = t; bt = uint32_t(f); }
+    }
+  } else {
+    const int nh = hotFloats(mode), nc = recFloats(mode);
+    const int64_t nch = paddedFaces(int64_t(rs.nrec)) / kRecPad;
+    const float p0[4] = {fr.ax, fr.ay, fr.az, fr.rr}, p1[4] = {fr.mx, fr.my, fr.mz, 0.f};
+    for (int64_t ch = 0; ch < nch; ++ch) {
+      if (!prefilterTest(mode, rs.bounds + 4 * ch, hr)) continue;
+      for (int sb = 0; sb < kSubPerChunk; ++sb) {
+        const int64_t sub = ch * kSubPerChunk + sb;
+        if (!prefilterTest(mode, rs.sub + 4 * sub, hr)) continue;
+        for (int k = 0; k < kSubRecs; ++k) {
+          const int64_t rec = sub * kSubRecs + k;
+          float hh[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < nh; ++j) hh[j] = rs.hot[recIndex(rec, j, nh)];
+          if (!prefilterTest(mode, hh, hr)) continue;
+          float q[16];
+          for (int j = 0; j < nc; ++j) q[j] = rs.recs[fullIndex(rec, j)];
+          if (int32_t(filterTest(mode, q, p0, p1, fr.rr)) < 0) continue;
+          uint32_t tri = rs.ids ? rs.ids[rec] : uint32_t(rec);
+          if (recSlotId(mode) >= 0) tri = fbits(q[recSlotId(mode)]);
+          const double t = rayTriangleExact(r, m.verts + 4 * m.vidx[3 * int64_t(tri)], m.verts + 4 * m.vidx[3 * int64_t(tri) + 1],
+                                            m.verts + 4 * m.vidx[3 * int64_t(tri) + 2]);
+          if (t >= 0 && (t < best || (t == best && tri < bt))) { best = t; bt = tri; }
+        }
+      }
+    }
+  }
+  h.t = (best == 0) ? 0.0 : best;   // -0.0 -> +0.0 (as Verify1 / ExactMesh)
+  h.tri = bt;
+  return h;
+}
+
+// How trace() obtains TriangleMesh.intersect of the current ray for mesh object `mo`:
+//   WaveMesh  the wavefront: gate code of the ray's wave position + the results of the mesh wave
+//   NoMesh    the caller has shown that the ray enters no mesh box (FusedPrimary): NegInf
+//   WalkMesh  the thread walks the mesh itself (PathTail)
+struct WaveMesh {
+  const ChunkState& cs; int64_t wi, pos; uint8_t code0;   // code0 = gate code for mesh object 0, loaded by the caller with its other inputs
+  NRT_HD bool miss(uint32_t mo) const { return (mo == 0 ? code0 : cs.gflag[int64_t(mo) * cs.NR + pos]) == 0; }
+  NRT_HD void eval(int mo, V4, V4, double& t, uint32_t& tri) const {
+    t = NRT_NEG_INF; tri = kNoTri;
+    if (cs.gflag[int64_t(mo) * cs.NR + pos]) {
+      t = bitsd(cs.tBest[int64_t(mo) * cs.NR + wi]);
+      tri = cs.triBest[int64_t(mo) * cs.NR + wi];
+    }
+  }
+};
+struct NoMesh {
+  NRT_HD bool miss(uint32_t) const { return true; }
+  NRT_HD void eval(int, V4, V4, double& t, uint32_t& tri) const { t = NRT_NEG_INF; tri = kNoTri; }
+};
+struct WalkMesh {
+  const DScene* sc; int mode, l, force_exact;
+  NRT_HD bool miss(uint32_t) const { return false; }
+  NRT_HD void eval(int mo, V4 o, V4 d, double& t, uint32_t& tri) const {
+    const MeshHit h = meshIntersectWalk(*sc, mo, mode, l, o, d, force_exact);
+    t = h.t; tri = h.tri;
+  }
+};
+
+// trace(): renderer.nim:47-67; the mesh results come from the policy `mp` (above).
 struct TraceOut { int obj; double t; uint32_t tri; int tests, hits; };
 
 // float64 evaluation of object i for trace(): the reference's intersect() (or the mesh result), then the
 // running-minimum update of renderer.nim:60-65
-NRT_HD void evalObject(const DScene& sc, const ChunkState& cs, int i, V4 o, V4 d, bool fastRay, int64_t wi, int64_t pos, TraceOut& r) {
+template <class MP>
+NRT_HD void evalObject(const DScene& sc, const MP& mp, int i, V4 o, V4 d, bool fastRay, TraceOut& r) {
   const CObj c = loadCObj(sc.cobjs + i);
   double t; uint32_t tri = kNoTri;
   if (c.kind == GEOM_MESH) {
-    t = NRT_NEG_INF;
-    if (cs.gflag[int64_t(c.mesh_obj) * cs.NR + pos]) {
-      t = bitsd(cs.tBest[int64_t(c.mesh_obj) * cs.NR + wi]);
-      tri = cs.triBest[int64_t(c.mesh_obj) * cs.NR + wi];
-    }
+    mp.eval(c.mesh_obj, o, d, t, tri);
   } else {
     V4 oo, dd;
     if (c.xlate_only && fastRay && (o.x != 0.0 || c.t[0] != 0.0) && (o.y != 0.0 || c.t[1] != 0.0) && (o.z != 0.0 || c.t[2] != 0.0)) {
@@ -498,13 +596,11 @@ NRT_HD void evalObject(const DScene& sc, const ChunkState& cs, int i, V4 o, V4 d
 
 // float32 first look at object i (record c): true = the reference's intersect() certainly returns a
 // value trace() rejects (NegInf or t < 0), so the object is skipped (it is still counted in Stats)
-NRT_HD bool firstLookMiss(const ChunkState& cs, const CObjF& c, const RayF& rf, bool f32ok, int64_t pos, uint8_t code0) {
+template <class MP>
+NRT_HD bool firstLookMiss(const MP& mp, const CObjF& c, const RayF& rf, bool f32ok) {
   if (c.r2m < 3.0e38f) return f32ok && certainMissF(c, rf);
   const uint32_t tag = fbits(c.tx);
-  if (tag == COF_MESH) {   // code 0: the ray did not enter the mesh's box
-    const uint32_t mo = fbits(c.ty);
-    return (mo == 0 ? code0 : cs.gflag[int64_t(mo) * cs.NR + pos]) == 0;
-  }
+  if (tag == COF_MESH) return mp.miss(fbits(c.ty));   // (wavefront: gate code 0 = the ray did not enter the mesh's box)
   return (tag == COF_PLANE) && f32ok && planeMissF(c, rf);
 }
 
@@ -513,8 +609,8 @@ NRT_HD bool firstLookMiss(const ChunkState& cs, const CObjF& c, const RayF& rf, 
 // `code0` = gate code of the ray for mesh object 0, loaded by the caller together with its other inputs.
 // CL: the scene has sphere clusters (the host picks the kernel variant, so that the flat scan of small
 // scenes keeps its register budget).
-template <bool CL>
-NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d, double tNear, int64_t wi, int64_t pos, uint8_t code0) {
+template <bool CL, class MP>
+NRT_HD TraceOut traceObjects(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear) {
   TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
   // the exact shortcut of toObject() for [I | t] matrices applies to this ray?  (zero components
   // need toObject()'s per-component treatment)
@@ -547,11 +643,11 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
     }
     for (int k = 0; k < sc.nslow && !full; ++k) {
       const uint32_t i = sc.slowIdx[k];
-      if (!firstLookMiss(cs, loadCObjF(sc.cobjf + i), rf, f32ok, pos, code0)) push(i);
+      if (!firstLookMiss(mp, loadCObjF(sc.cobjf + i), rf, f32ok)) push(i);
     }
     if (!full) {
       r.tests = sc.nobjects;
-      for (int k = 0; k < ns; ++k) evalObject(sc, cs, int(surv[k]), o, d, fastRay, wi, pos, r);
+      for (int k = 0; k < ns; ++k) evalObject(sc, mp, int(surv[k]), o, d, fastRay, r);
       return r;
     }
   }
@@ -565,14 +661,14 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const ChunkState& cs, V4 o, V4 d,
       uint32_t miss = 0;
 #pragma unroll 4
       for (int j = 0; j < nb; ++j)   // the same record for every lane: the branches inside are uniform
-        miss |= uint32_t(firstLookMiss(cs, loadCObjF(sc.cobjf + base + j), rf, f32ok, pos, code0)) << j;
+        miss |= uint32_t(firstLookMiss(mp, loadCObjF(sc.cobjf + base + j), rf, f32ok)) << j;
       need &= ~miss;
     }
     r.tests += nb;
     while (need) {
       const int i = base + (__builtin_ffs(int(need)) - 1);
       need &= need - 1;
-      evalObject(sc, cs, i, o, d, fastRay, wi, pos, r);
+      evalObject(sc, mp, i, o, d, fastRay, r);
     }
   }
   return r;
@@ -604,7 +700,7 @@ struct ShadeT {
     const uint8_t alive = cs.active[s], code0 = (cs.nMO > 0) ? cs.gflag[idx] : uint8_t(0);
     const V4 o = (bounce == 0) ? primaryOrigin(*sc) : ld4(cs.rayO, cs.S, s);
     if (!alive) { cs.hitObj[s] = -1; return st; }
-    const TraceOut tr = traceObjects<CL>(*sc, cs, o, d, NRT_INF, s, idx, code0);
+    const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s, idx, code0}, o, d, NRT_INF);
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     if (bounce == 0) {
       st.v[ST_PRIMARY] = 1;
@@ -712,7 +808,7 @@ struct ShadowTrace {
     const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
     const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
     const V4 so = add(hitW, scale(n, fp.bias)), sd = scale(li.lightDir, -1.0);   // renderer.nim:98-99
-    const TraceOut tr = traceObjects<false>(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx, (cs.nMO > 0) ? cs.gflag[idx] : uint8_t(0));
+    const TraceOut tr = traceObjects<false>(*sc, WaveMesh{cs, s * cs.nL + l, idx, (cs.nMO > 0) ? cs.gflag[idx] : uint8_t(0)}, so, sd, li.lightDistance);
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     cs.occ[s * cs.nL + l] = tr.obj >= 0 ? 1 : 0;
     return st;
@@ -747,7 +843,7 @@ struct ShadowTraceSampleT {
       const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
       const V4 sd = scale(li.lightDir, -1.0);                                      // renderer.nim:99
       const uint8_t code0 = (l < 4) ? uint8_t(codes >> (8 * l)) : ((cs.nMO > 0) ? cs.gflag[idx * cs.nL + l] : uint8_t(0));
-      const TraceOut tr = traceObjects<CL>(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx * cs.nL + l, code0);
+      const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s * cs.nL + l, idx * cs.nL + l, code0}, so, sd, li.lightDistance);
       st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
       cs.occ[s * cs.nL + l] = tr.obj >= 0 ? 1 : 0;
     }
@@ -765,6 +861,22 @@ using ShadowTraceSampleClustered = ShadowTraceSampleT<true>;
 // The work of one hit sample after its shadow rays are known.  `occluded(l)`: the shadow ray towards
 // light l hit something (renderer.nim:103).  `hitW` is only valid with point lights (a DistantLight
 // ignores it); without them it is fetched here for the (few) continuing samples only.
+// Appends sample s to the list of the samples PathTail finishes (order is irrelevant there: every sample
+// is independent).  On the GPU the lanes of a warp that arrive together share one atomic.
+NRT_HD void pushTail(const ChunkState& cs, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  const unsigned m = __activemask();
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (int(lane) == leader) base = atomicAdd(cs.tailCount, uint32_t(__popc(m)));
+  base = __shfl_sync(m, base, leader);
+  cs.tailList[base + __popc(m & ((1u << lane) - 1u))] = s;
+#else
+  cs.tailList[(*cs.tailCount)++] = s;
+#endif
+}
+
 template <class OCC>
 NRT_HD void resolveSample(const DScene* sc, const FrameParams& fp, const ChunkState& cs, int bounce, int pointLights,
                           int64_t s, int objHit, V4 hitW, const V4& n, const OCC& occluded, StatDelta& st) {
@@ -800,6 +912,7 @@ NRT_HD void resolveSample(const DScene* sc, const FrameParams& fp, const ChunkSt
     st4(cs.rayD, cs.S, s, r);
     cs.weight[s] = w * k;
     cs.active[s] = 1;
+    if (cs.tailList) pushTail(cs, uint32_t(s));
     st.v[ST_CONT] = 1;
   } else {
     cs.active[s] = 0;
@@ -864,7 +977,7 @@ struct ShadowResolveT {
         const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
         const V4 sd = scale(li.lightDir, -1.0);                                      // renderer.nim:99
         const uint8_t code0 = (l < 4) ? uint8_t(codes >> (8 * l)) : ((cs.nMO > 0) ? cs.gflag[idx * cs.nL + l] : uint8_t(0));
-        const TraceOut tr = traceObjects<CL>(*sc, cs, so, sd, li.lightDistance, s * cs.nL + l, idx * cs.nL + l, code0);
+        const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s * cs.nL + l, idx * cs.nL + l, code0}, so, sd, li.lightDistance);
         st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
         occ |= uint32_t(tr.obj >= 0 ? 1u : 0u) << l;
       }
@@ -879,6 +992,146 @@ struct ShadowResolveT {
 };
 using ShadowResolve = ShadowResolveT<false>;
 using ShadowResolveClustered = ShadowResolveT<true>;
+
+// ---- fused path kernels -----------------------------------------------------------------------------
+// The wavefront above streams every sample's float64 state through HBM five times per bounce.  Most samples
+// never need it: in a frame of BASELINE config 4 about 88 % of the samples have NO ray (primary or shadow)
+// that enters a mesh box, so their whole bounce — castPrimaryRay, trace, shade's shadow rays, shadeDiffuse,
+// the reflection set-up (renderer.nim:31-127) — is done by ONE thread in registers:
+//   FusedPrimary  bounce 0 of every sample.  A sample one of whose rays passes a mesh's AABB gate is handed
+//                 to the wavefront instead (its ray and active = 1 are stored, nothing else, and it adds
+//                 nothing to Stats: the wavefront redoes it from the ray); every other sample is finished
+//                 here: accumulator written once, and, if its path continues, the reflection ray is stored
+//                 and the sample appended to the tail list.
+//   PathTail      all later bounces of the samples on the tail list (few: ~0.4 % of the samples), one thread
+//                 per sample to the end of its path; a ray that enters a mesh box walks the flattened
+//                 hierarchy of the mesh by itself (meshIntersectWalk).  No launch chain, no host round trip
+//                 per bounce.
+//   PathMega      FusedPrimary + PathTail in one: every sample start to end in one thread, meshes walked
+//                 (NRT_PATH=mega; small frames, where a single launch beats the ~25 of the wavefront).
+// The arithmetic is the wavefront's, operation by operation (Shade, ShadowResolve, resolveSample).
+enum PathKind { PATH_PRIMARY = 0, PATH_TAIL = 1, PATH_MEGA = 2 };
+template <bool CL, int KIND>
+struct PathSampleT {
+  const DScene* sc; FrameParams fp; ChunkState cs; int force_exact;
+  int genFromState;   // the primary rays are in cs.rayD / cs.active already (jittered kinds: GenJittered)
+  NRT_HD void prefetch(int64_t) const {}
+  template <class MP>
+  NRT_HD TraceOut trace(const MP& mp, V4 o, V4 d, double tNear) const { return traceObjects<CL>(*sc, mp, o, d, tNear); }
+  NRT_HD StatDelta operator()(int64_t idx) const {
+    StatDelta st = zeroStats();
+    int64_t s = idx;
+    V4 o, d;
+    double w = 1.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    int bounce = 0;
+    if (KIND == PATH_TAIL) {
+      s = int64_t(cs.tailList[idx]);
+      o = ld4(cs.rayO, cs.S, s); d = ld4(cs.rayD, cs.S, s);
+      w = cs.weight[s];
+      a0 = cs.accum[s]; a1 = cs.accum[cs.S + s]; a2 = cs.accum[2 * cs.S + s];
+      bounce = 1;
+    } else {
+      bool alive;
+      if (genFromState) {
+        o = primaryOrigin(*sc); d = ld4(cs.rayD, cs.S, s); alive = cs.active[s] != 0;
+      } else {
+        GenOut g; GenSimple{sc, fp, cs}.compute(s, g);
+        o = g.o; d = g.d; alive = g.alive;
+      }
+      if (!alive) { if (KIND == PATH_PRIMARY) cs.active[s] = 0; return st; }   // (skipped pixel of a progressive pass)
+    }
+    const int nMO = cs.nMO, nL = cs.nL;
+    for (;;) {
+      if (KIND == PATH_PRIMARY) {
+        for (int mo = 0; mo < nMO; ++mo)
+          if (meshGatePass(*sc, mo, o, d)) return toWavefront(s, d);
+      }
+      const TraceOut tr = (KIND == PATH_PRIMARY) ? trace(NoMesh{}, o, d, NRT_INF)
+                                                 : trace(WalkMesh{sc, bounce == 0 ? FM_ORIGIN : FM_GENERAL, 0, force_exact}, o, d, NRT_INF);
+      st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
+      if (bounce == 0) st.v[ST_PRIMARY] = 1;
+      if (tr.obj < 0) {   // renderer.nim:74-75 / :123-124: background
+        if (bounce == 0) writeAov(s, tr);
+        a0 = a0 + sc->bg[0] * w; a1 = a1 + sc->bg[1] * w; a2 = a2 + sc->bg[2] * w;
+        break;
+      }
+      const DObject& ob = sc->objects[tr.obj];
+      const V4 hitW = add(o, scale(d, tr.t));
+      V4 n;
+      if (tr.tri == kNoTri) {
+        if (ob.kind == GEOM_PLANE) n = v4(ob.plane_nw[0], ob.plane_nw[1], ob.plane_nw[2], ob.plane_nw[3]);
+        else n = mulm(ob.o2w, geomNormal(ob, mulm(ob.w2o, hitW)));
+      } else {
+        const DMesh& m = sc->meshes[ob.mesh];
+        const double* nn = m.normals + 4 * m.nidx[3 * int64_t(tr.tri)];
+        n = mulm(ob.o2w, v4(nn[0], nn[1], nn[2], nn[3]));
+      }
+      const V4 so = add(hitW, scale(n, fp.bias));                                    // renderer.nim:98
+      if (KIND == PATH_PRIMARY) {   // a shadow ray that enters a mesh box: the wavefront takes the sample
+        for (int l = 0; l < nL; ++l) {
+          const V4 sdir = scale(getShadingInfo(sc->lights[l], hitW).lightDir, -1.0);
+          for (int mo = 0; mo < nMO; ++mo)
+            if (meshGatePass(*sc, mo, so, sdir)) return toWavefront(s, d);
+        }
+      }
+      if (bounce == 0) writeAov(s, tr);
+      V3 local = v3(0.0, 0.0, 0.0);
+      for (int l = 0; l < nL; ++l) {
+        const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
+        const V4 sdir = scale(li.lightDir, -1.0);                                    // renderer.nim:99
+        const TraceOut ts = (KIND == PATH_PRIMARY)
+            ? trace(NoMesh{}, so, sdir, li.lightDistance)
+            : trace(WalkMesh{sc, sc->lights[l].kind == LIGHT_DISTANT ? FM_DIR : FM_GENERAL, l, force_exact}, so, sdir, li.lightDistance);
+        st.v[ST_RAYS] += 1; st.v[ST_TESTS] += ts.tests; st.v[ST_HITS] += ts.hits;
+        if (ts.obj < 0) local = add(local, shadeDiffuse(ob, li, n));                 // renderer.nim:103-105
+      }
+      // resolveSample's arithmetic
+      const double k = ob.reflection;
+      const int depth = (fp.depth_mode == DEPTH_INTENDED) ? (1 + bounce) : 0;      // renderer.nim:108 + depth bug
+      bool cont = false;
+      double wl = w;
+      if (k > 0.0 && depth <= fp.max_ray_depth) {
+        if (bounce >= fp.bounce_cap) st.v[ST_CAPPED] += 1;
+        else { cont = true; wl = w * (1.0 - k); }
+      }
+      a0 = a0 + local.x * wl; a1 = a1 + local.y * wl; a2 = a2 + local.z * wl;
+      if (!cont) break;
+      const V4 r = sub(d, scale(n, 2 * dot(n, d)));                                  // renderer.nim:112
+      o = add(hitW, scale(r, fp.bias)); d = r; w = w * k;
+      if (KIND == PATH_PRIMARY) {
+        st4(cs.rayO, cs.S, s, o); st4(cs.rayD, cs.S, s, d);
+        cs.weight[s] = w;
+        pushTail(cs, uint32_t(s));
+        break;
+      }
+      ++bounce;
+    }
+    cs.accum[s] = a0; cs.accum[cs.S + s] = a1; cs.accum[2 * cs.S + s] = a2;
+    if (KIND == PATH_PRIMARY) cs.active[s] = 0;
+    return st;
+  }
+  // hands sample s to the wavefront: its primary ray + active = 1 (= a member of the bounce-0 active list)
+  NRT_HD StatDelta toWavefront(int64_t s, V4 d) const {
+    if (!genFromState) st4(cs.rayD, cs.S, s, d);
+    cs.active[s] = 1;
+    return zeroStats();
+  }
+  NRT_HD void writeAov(int64_t s, const TraceOut& tr) const {
+    if ((cs.aovObj || cs.aovTri || cs.aovT) && s == divFast(s, fp.spp) * fp.spp) {
+      int x, y; pixelOf(fp, cs, cs.p0 + divFast(s, fp.spp), x, y);
+      const int64_t pi = int64_t(y) * fp.width + x;
+      if (cs.aovObj) cs.aovObj[pi] = tr.obj;
+      if (cs.aovTri) cs.aovTri[pi] = (tr.obj >= 0 && tr.tri != kNoTri) ? int32_t(tr.tri) : -1;
+      if (cs.aovT) cs.aovT[pi] = tr.t;
+    }
+  }
+};
+using FusedPrimary = PathSampleT<false, PATH_PRIMARY>;
+using FusedPrimaryClustered = PathSampleT<true, PATH_PRIMARY>;
+using PathTail = PathSampleT<false, PATH_TAIL>;
+using PathTailClustered = PathSampleT<true, PATH_TAIL>;
+using PathMega = PathSampleT<false, PATH_MEGA>;
+using PathMegaClustered = PathSampleT<true, PATH_MEGA>;
 
 // ---- finalize: sample sum in order, * 1/N, float32 store (+ step x step fill)
 struct Finalize {

@@ -49,6 +49,7 @@ struct SceneData {
   struct MoRecs { float* origin = nullptr; float* originHot = nullptr; float* originBounds = nullptr; std::vector<float*> dir, dirHot, dirBounds; };
   std::vector<BundleFrame> frames;        // host copy, [mo * recStride() + j]
   BundleFrame* dFrames = nullptr;
+  RecSet* dRecSets = nullptr;             // device table of the record sets, indexed like the frames (DScene.recsets)
   bool anyGeneralShadow = false;          // some shadow rays need the GENERAL bundle (point light / unusable frame)
   std::vector<MoRecs> moRecs;
   uint32_t* dRecCount = nullptr;          // [mo * recStride() + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
@@ -195,6 +196,37 @@ struct SceneData {
     if (reuse && (desc->nobjects != h.nobjects || desc->nlights != h.nlights || desc->nmeshes != h.nmeshes)) {
       err = "nrt_scene_update: scene shape differs from the created scene"; return NRT_ERR_INVALID;
     }
+    // Validate the WHOLE description before anything of the live scene is touched: a failed
+    // nrt_scene_update leaves the scene exactly as it was (and renderable).
+    for (int i = 0; i < desc->nmeshes; ++i) {
+      const nrt_mesh& m = desc->meshes[i];
+      if (m.nverts < 0 || m.nfaces < 0 || m.nnormals < 0 || (m.nfaces > 0 && (!m.vertices || !m.vertex_idx || !m.normal_idx)) ||
+          (m.nnormals > 0 && !m.normals) || m.nfaces > 0xFFFFFFF0ll) { err = "bad mesh description"; return NRT_ERR_INVALID; }
+      if (reuse && (m.nverts != meshes[i].nverts || m.nfaces != meshes[i].nfaces || m.nnormals != meshes[i].nnormals)) {
+        err = "nrt_scene_update: mesh shape differs"; return NRT_ERR_INVALID;
+      }
+      for (int64_t f = 0; f < m.nfaces * 3; ++f) {
+        if (m.vertex_idx[f] < 0 || m.vertex_idx[f] >= m.nverts) { err = "vertex index out of range"; return NRT_ERR_INVALID; }
+        // only normalIdx[0] of a face is ever read (renderer.nim:87)
+        if (f % 3 == 0 && (m.normal_idx[f] < 0 || m.normal_idx[f] >= m.nnormals)) { err = "normal index out of range"; return NRT_ERR_INVALID; }
+      }
+    }
+    for (int i = 0; i < desc->nobjects; ++i) {
+      const nrt_object& o = desc->objects[i];
+      if (o.kind < 0 || o.kind > 3) { err = "bad geometry kind"; return NRT_ERR_INVALID; }
+      if (o.kind == NRT_GEOM_MESH && (o.mesh < 0 || o.mesh >= desc->nmeshes)) { err = "mesh index out of range"; return NRT_ERR_INVALID; }
+      // the reused buffers (record sets per mesh object, frames, counters) are sized by which objects are
+      // meshes and by the mesh each one refers to: an update must keep both
+      if (reuse && (o.kind != objs[i].kind || (o.kind == NRT_GEOM_MESH && o.mesh != objs[i].mesh))) {
+        err = "nrt_scene_update: object kind or mesh index differs from the created scene"; return NRT_ERR_INVALID;
+      }
+    }
+    for (int i = 0; i < desc->nlights; ++i) {
+      const int k = desc->lights[i].kind;
+      if (k != NRT_LIGHT_DISTANT && k != NRT_LIGHT_POINT) { err = "bad light kind"; return NRT_ERR_INVALID; }
+      // DIR record sets exist per DistantLight: the kind of a light is part of the scene's shape too
+      if (reuse && k != lights[i].kind) { err = "nrt_scene_update: light kind differs from the created scene"; return NRT_ERR_INVALID; }
+    }
     bytes_uploaded = 0;
     std::vector<DMesh> old = meshes;
     std::vector<MoRecs> oldRecs = moRecs;
@@ -204,16 +236,6 @@ struct SceneData {
     moIndex.clear();
     for (int i = 0; i < desc->nmeshes; ++i) {
       const nrt_mesh& m = desc->meshes[i];
-      if (m.nverts < 0 || m.nfaces < 0 || m.nnormals < 0 || (m.nfaces > 0 && (!m.vertices || !m.vertex_idx || !m.normal_idx)) ||
-          m.nfaces > 0xFFFFFFF0ll) { err = "bad mesh description"; return NRT_ERR_INVALID; }
-      if (reuse && (m.nverts != old[i].nverts || m.nfaces != old[i].nfaces || m.nnormals != old[i].nnormals)) {
-        err = "nrt_scene_update: mesh shape differs"; return NRT_ERR_INVALID;
-      }
-      for (int64_t f = 0; f < m.nfaces * 3; ++f) {
-        if (m.vertex_idx[f] < 0 || m.vertex_idx[f] >= m.nverts) { err = "vertex index out of range"; return NRT_ERR_INVALID; }
-        // only normalIdx[0] of a face is ever read (renderer.nim:87)
-        if (f % 3 == 0 && (m.normal_idx[f] < 0 || m.normal_idx[f] >= m.nnormals)) { err = "normal index out of range"; return NRT_ERR_INVALID; }
-      }
       DMesh& dm = meshes[i];
       dm.nverts = m.nverts; dm.nnormals = m.nnormals; dm.nfaces = m.nfaces;
       dm.verts = up(m.vertices, m.nverts * 4, reuse ? const_cast<double*>(old[i].verts) : nullptr);
@@ -244,7 +266,6 @@ struct SceneData {
     for (int i = 0; i < desc->nobjects; ++i) {
       const nrt_object& o = desc->objects[i];
       DObject& dob = objs[i];
-      if (o.kind < 0 || o.kind > 3) { err = "bad geometry kind"; return NRT_ERR_INVALID; }
       dob.kind = o.kind; dob.mesh = -1; dob.mesh_obj = -1;
       {  // exactly [I | t] with finite t?
         const double* w = o.world_to_object;
@@ -268,7 +289,6 @@ struct SceneData {
       dob.reflection = o.reflection;
       if (o.reflection > 0.0) anyReflective = true;
       if (o.kind == NRT_GEOM_MESH) {
-        if (o.mesh < 0 || o.mesh >= desc->nmeshes) { err = "mesh index out of range"; return NRT_ERR_INVALID; }
         dob.mesh = o.mesh;
         dob.mesh_obj = int32_t(moIndex.size());
         moIndex.push_back(i);
@@ -278,7 +298,6 @@ struct SceneData {
     }
     for (int i = 0; i < desc->nlights; ++i) {
       const nrt_light& l = desc->lights[i];
-      if (l.kind != NRT_LIGHT_DISTANT && l.kind != NRT_LIGHT_POINT) { err = "bad light kind"; return NRT_ERR_INVALID; }
       DLight& dl = lights[i];
       dl.kind = l.kind;
       if (l.kind == NRT_LIGHT_POINT) anyPointLight = true;
@@ -352,9 +371,10 @@ struct SceneData {
         }
       }
       dFrames = up(frames.data(), int64_t(frames.size()), reuse ? dFrames : nullptr);
+      dRecSets = up<RecSet>(nullptr, int64_t(frames.size()), reuse ? dRecSets : nullptr);   // filled once the records exist
     }
     h.cl1 = dCl1; h.cl2 = dCl2; h.clm = dClm; h.clmIdx = dClmIdx; h.slowIdx = dSlowIdx;
-    h.objects = dObjs; h.cobjs = dCObjs; h.cobjf = dCObjF; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames;
+    h.objects = dObjs; h.cobjs = dCObjs; h.cobjf = dCObjF; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames; h.recsets = dRecSets;
     std::memcpy(h.c2w, desc->camera_to_world, sizeof(h.c2w));
     { const V4 co = mulm(h.c2w, v4(0.0, 0.0, 0.0, 1.0)); h.cam_orig[0] = co.x; h.cam_orig[1] = co.y; h.cam_orig[2] = co.z; h.cam_orig[3] = co.w; }
     h.tan_half_fov = std::tan((desc->fov * (kPi / 180.0)) / 2);  // renderer.nim:38; Nim degToRad = d * (PI/180)
@@ -401,6 +421,24 @@ struct SceneData {
         if (moRecs[mo].dirHot[l]) be->forEach(nch * (1 + kSubPerChunk), BuildBounds{FM_DIR, moRecs[mo].dirHot[l], dRecCount + mo * rs + 2 + l, moRecs[mo].dirBounds[l], nch});
     }
     be->download(hRecCount.data(), dRecCount, sizeof(uint32_t) * hRecCount.size());
+    {   // the record-set table of the per-thread mesh walk (meshIntersectWalk)
+      std::vector<RecSet> sets(frames.size(), RecSet{});
+      for (int mo = 0; mo < nMO; ++mo) {
+        const DMesh& m = meshes[objs[moIndex[mo]].mesh];
+        for (int j = 0; j < rs; ++j) {
+          const int mode = j == 0 ? FM_GENERAL : (j == 1 ? FM_ORIGIN : FM_DIR), l = j >= 2 ? j - 2 : 0;
+          RecSet& r = sets[size_t(mo * rs + j)];
+          const float* hot = hotOf(mo, mode, l);
+          r.usable = (m.nfaces > 0 && hot && (mode == FM_GENERAL || frameValid(mo, mode, l))) ? 1u : 0u;
+          if (!r.usable) continue;
+          r.hot = hot; r.bounds = boundsOf(mo, mode, l); r.sub = r.bounds + 4 * numChunks(m.nfaces);
+          r.recs = recsOf(mo, mode, l); r.ids = mode == FM_GENERAL ? m.order : nullptr;
+          r.nrec = hRecCount[size_t(mo * rs + j)];
+        }
+      }
+      be->upload(dRecSets, sets.data(), sizeof(RecSet) * sets.size());
+      bytes_uploaded += int64_t(sizeof(RecSet) * sets.size());
+    }
     return NRT_OK;
   }
 
@@ -420,6 +458,10 @@ struct Renderer {
   int capMO = -1, capNL = -1, capWaves = 0, capRows = 0;
   std::vector<void*> owned;
   int32_t* dRows = nullptr;
+  uint32_t* dTailCount = nullptr;
+  // NRT_PATH: 0 = the wavefront for every bounce (round-1 pipeline), 1 = FusedPrimary + wavefront for the samples
+  // with mesh rays at bounce 0 + PathTail (default), 2 = PathMega (one thread per sample start to end)
+  int pathMode = int(envInt("NRT_PATH", 1));
   ProfileAcc prof;
   int64_t launches_hint = 0;
   bool shadowGatePerSample = envInt("NRT_SHADOW_GATE_PER_SAMPLE", 1) != 0;
@@ -432,7 +474,7 @@ struct Renderer {
   void freeAll() {
     for (void* p : owned) be->dfree(p);
     owned.clear();
-    capS = capNR = capCand = capPairs = 0; capMO = -1; capNL = -1; capWaves = 0; capRows = 0; dRows = nullptr;
+    capS = capNR = capCand = capPairs = 0; capMO = -1; capNL = -1; capWaves = 0; capRows = 0; dRows = nullptr; dTailCount = nullptr;
     wantedS = 0;
   }
   template <class T> T* al(int64_t n) { T* p = static_cast<T*>(be->dalloc(sizeof(T) * std::max<int64_t>(n, 1))); owned.push_back(p); return p; }
@@ -475,6 +517,7 @@ struct Renderer {
       cs.gne = al<uint32_t>(cs.gvb);
       be->zero(cs.gseg, sizeof(uint32_t) * grows * cs.gsn);
       dRows = al<int32_t>(nrows);
+      dTailCount = al<uint32_t>(4);
     }
     cs.pairCap = capPairs;
     cs.S = capS; cs.NR = capNR; cs.QCAP = capNR + int64_t(nL) * capS; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.preCap = 4 * capCand; cs.rows = dRows;
@@ -529,6 +572,22 @@ struct Renderer {
     }
   }
 
+  // trace() of the shadow rays of the active samples + shadeDiffuse / reflection set-up (renderer.nim:90-127)
+  void shadowAndResolve(const SceneData<BE>& sd, const FrameParams& fp, const ActiveSet& act, int bounce) {
+    const int nL = cs.nL, pl = sd.anyPointLight ? 1 : 0;
+    if (nL > 0 && nL <= 32 && fuseResolve && (sd.h.ncl1 > 0 || shadowTracePerSample)) {
+      if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowResolveClustered{sd.d, fp, cs, act, bounce, pl}, cs.stats);
+      else be->forEachStats(nullptr, act.n, ShadowResolve{sd.d, fp, cs, act, bounce, pl}, cs.stats);
+    } else {
+      if (nL > 0) {
+        if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowTraceSampleClustered{sd.d, fp, cs, act}, cs.stats);
+        else if (shadowTracePerSample) be->forEachStats(nullptr, act.n, ShadowTraceSample{sd.d, fp, cs, act}, cs.stats);
+        else be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
+      }
+      be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act, bounce, pl}, cs.stats);
+    }
+  }
+
   // Renders the rows `rows` (already filtered by step) of one worker.
   int render(const SceneData<BE>& sd, const nrt_options& o, const std::vector<int32_t>& rows, int step, int max_step,
              float* fb, int32_t* aovObj, int32_t* aovTri, double* aovT, unsigned long long* statsOut, std::string& err) {
@@ -548,6 +607,7 @@ struct Renderer {
 
     const int nL = sd.h.nlights, nMO = sd.h.nmesh_objs;
     const bool jitter = o.aa_kind >= NRT_AA_JITTERED;
+    pathMode = int(envInt("NRT_PATH", 1));
     // An INTENDED-mode frame can reflect at most max_ray_depth times.
     int maxBounces = sd.anyReflective ? fp.bounce_cap : 0;
     if (sd.anyReflective && o.depth_mode == NRT_DEPTH_INTENDED) maxBounces = std::min(maxBounces, std::max(0, o.max_ray_depth));
@@ -597,6 +657,42 @@ struct Renderer {
         be->zero(cs.acount, sizeof(uint32_t) * (waves + 2));
         int wave = 0;
         ActiveSet act{nullptr, nullptr, nS};   // bounce 0: every sample of the chunk
+        cs.tailList = nullptr; cs.tailCount = nullptr;
+        if (pathMode != 0) {
+          // ---- fused path (nrt_pipeline.h: PathSampleT) ----
+          cs.tailList = cs.alist + cs.S; cs.tailCount = dTailCount;
+          be->zero(dTailCount, sizeof(uint32_t) * 4);
+          if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
+          const int gfs = jitter ? 1 : 0;
+          if (pathMode == 2) {
+            if (sd.h.ncl1 > 0) be->forEachStats(nullptr, nS, PathMegaClustered{sd.d, fp, cs, force_exact, gfs}, cs.stats);
+            else be->forEachStats(nullptr, nS, PathMega{sd.d, fp, cs, force_exact, gfs}, cs.stats);
+          } else {
+            if (sd.h.ncl1 > 0) be->forEachStats(nullptr, nS, FusedPrimaryClustered{sd.d, fp, cs, force_exact, gfs}, cs.stats);
+            else be->forEachStats(nullptr, nS, FusedPrimary{sd.d, fp, cs, force_exact, gfs}, cs.stats);
+            if (nMO > 0) {
+              // the samples with a mesh ray at bounce 0, in sample order (= the wavefront's bounce-0 active list)
+              uint32_t* hardList = cs.alist;
+              uint32_t* hardCount = cs.acount;
+              be->compactActive(cs, act, hardList, hardCount);
+              uint32_t n0 = 0;
+              be->download(&n0, hardCount, sizeof(n0));
+              if (n0 > 0) {
+                const ActiveSet hard{hardList, hardCount, int64_t(n0)};
+                meshWave(sd, fp, WAVE_PATH, hard, wave, 0, force_exact, false); ++wave;
+                if (sd.h.ncl1 > 0) be->forEachStats(nullptr, hard.n, ShadeClustered{sd.d, fp, cs, hard, 0}, cs.stats);
+                else be->forEachStats(nullptr, hard.n, Shade{sd.d, fp, cs, hard, 0}, cs.stats);
+                if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, hard, wave, 0, force_exact, false);
+                ++wave;
+                shadowAndResolve(sd, fp, hard, 0);
+              }
+            }
+            if (maxBounces > 0) {
+              if (sd.h.ncl1 > 0) be->forEachStatsCounted(cs.tailCount, cs.S, PathTailClustered{sd.d, fp, cs, force_exact, 0}, cs.stats);
+              else be->forEachStatsCounted(cs.tailCount, cs.S, PathTail{sd.d, fp, cs, force_exact, 0}, cs.stats);
+            }
+          }
+        } else {
         // primary rays: generated and gated in one kernel (the jittered kinds generate per pixel: separate gate)
         const bool fuseGen = !jitter && nMO > 0;
         if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
@@ -611,24 +707,14 @@ struct Renderer {
           else be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act, bounce}, cs.stats);
           if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, bounce, force_exact, false);
           ++wave;
-          const int pl = sd.anyPointLight ? 1 : 0;
-          if (nL > 0 && nL <= 32 && fuseResolve && (sd.h.ncl1 > 0 || shadowTracePerSample)) {
-            if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowResolveClustered{sd.d, fp, cs, act, bounce, pl}, cs.stats);
-            else be->forEachStats(nullptr, act.n, ShadowResolve{sd.d, fp, cs, act, bounce, pl}, cs.stats);
-          } else {
-            if (nL > 0) {
-              if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowTraceSampleClustered{sd.d, fp, cs, act}, cs.stats);
-              else if (shadowTracePerSample) be->forEachStats(nullptr, act.n, ShadowTraceSample{sd.d, fp, cs, act}, cs.stats);
-              else be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
-            }
-            be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act, bounce, pl}, cs.stats);
-          }
+          shadowAndResolve(sd, fp, act, bounce);
           if (bounce >= maxBounces) break;
           be->compactActive(cs, act, nextList, nextCount);
           uint32_t cont = 0;
           be->download(&cont, nextCount, sizeof(cont));
           if (cont == 0) break;  // no sample continued
           act = ActiveSet{nextList, nextCount, int64_t(cont)};
+        }
         }
         be->finalize(npix, Finalize{fp, cs});
         // chunk epilogue: counters (profile + overflow check) and stats

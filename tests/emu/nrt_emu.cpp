@@ -39,6 +39,9 @@ struct LoopBackend {
     for (int64_t i = 0; i < n; ++i) { const StatDelta d = f(i); for (int k = 0; k < ST_COUNT; ++k) st[k] += d.v[k]; }
     ++launches;
   }
+  template <class F> void forEachStatsCounted(const uint32_t* count, int64_t cap, const F& f, unsigned long long* st) {
+    forEachStats(nullptr, std::min<int64_t>(*count, cap), f, st);
+  }
   template <class F> void forEachCounted(const uint32_t* c, int64_t cap, const F& f) {
     const int64_t n = std::min<int64_t>(*c, cap);
     for (int64_t i = 0; i < n; ++i) f(i);

@@ -15,7 +15,7 @@ _lib = None
 def build(force: bool = False) -> str:
     out = os.path.join(_HERE, "libnrt_emu.so")
     srcs = [os.path.join(_HERE, "nrt_emu.cpp")] + [
-        os.path.join(_ROOT, "nim_raytracer_b200", "csrc", n) for n in ("nrt_core.h", "nrt_pipeline.h", "nrt_renderer.h")
+        os.path.join(_ROOT, "nim_raytracer_b200", "csrc", n) for n in ("nrt_core.h", "nrt_filter.h", "nrt_pipeline.h", "nrt_renderer.h")
     ] + [os.path.join(_ROOT, "include", "nrt.h")]
     if force or not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.run(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-shared", "-fPIC",

@@ -10,6 +10,7 @@ Stats, and every 8th row verbatim (ids + float32 RGB) so a mismatch can be locat
 """
 import hashlib
 import os
+import zlib
 import sys
 import time
 
@@ -43,6 +44,10 @@ def make(name, scene, opts, row_stride=8):
         rows=rows,
         fb_rows=fb.image()[rows], obj_rows=aov.obj_id.reshape(h, w)[rows].astype(np.int8),
         tri_rows=aov.tri_id.reshape(h, w)[rows],
+        # one CRC32 per scanline of the float32 framebuffer / the ids: locates a mismatch in a full-size frame
+        fb_row_crc=np.array([zlib.crc32(r.tobytes()) for r in fb.image()], dtype=np.uint32),
+        id_row_crc=np.array([zlib.crc32(a.tobytes() + b.tobytes()) for a, b in
+                             zip(aov.obj_id.reshape(h, w), aov.tri_id.reshape(h, w))], dtype=np.uint32),
     )
     print(f"{name}: {time.time() - t:.1f}s  {st}")
 
@@ -57,3 +62,11 @@ if __name__ == "__main__":
         make("config3_bunny_spheres_480x270_g2", scenes.bunny_spheres(),
              api.Options(480, 270, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED,
                          maxRayDepth=8), row_stride=4)
+    if "config3" in which:   # BASELINE config 3 at its stated size: 1920x1080, 16 spp grid, intended depth 8 (~11 min on 8 cores)
+        make("config3_bunny_spheres_1920x1080_g4", scenes.bunny_spheres(),
+             api.Options(1920, 1080, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED,
+                         maxRayDepth=8), row_stride=16)
+    if "config4" in which:   # BASELINE config 4 (the bench workload) at its stated size: 3840x2160, 16 spp (~45 min on 8 cores)
+        make("config4_bunny_spheres_3840x2160_g4", scenes.bunny_spheres(),
+             api.Options(3840, 2160, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED,
+                         maxRayDepth=8), row_stride=48)

@@ -215,6 +215,44 @@ def test_golden_config3_reduced():
     _check_golden("config3_bunny_spheres_480x270_g2", scenes.bunny_spheres(), o)
 
 
+def _check_row_crcs(name, fb, aov):
+    """Per-scanline CRC32 of the framebuffer and ids against the fixture: names the first rows that differ."""
+    import zlib
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    if "fb_row_crc" not in g:
+        return
+    h, w = int(g["height"]), int(g["width"])
+    crc = np.array([zlib.crc32(r.tobytes()) for r in fb.image()], dtype=np.uint32)
+    bad = np.nonzero(crc != g["fb_row_crc"])[0]
+    assert bad.size == 0, f"{bad.size} framebuffer rows differ from the oracle, first {bad[:8].tolist()}"
+    icrc = np.array([zlib.crc32(a.tobytes() + b.tobytes()) for a, b in
+                     zip(aov.obj_id.reshape(h, w), aov.tri_id.reshape(h, w))], dtype=np.uint32)
+    bad = np.nonzero(icrc != g["id_row_crc"])[0]
+    assert bad.size == 0, f"{bad.size} id rows differ from the oracle, first {bad[:8].tolist()}"
+
+
+def test_golden_config3_full_size():
+    # BASELINE config 3 at its stated size: bunny + 7 spheres (reflection 0 / 0.5 / 1), 1920x1080, 16 spp grid,
+    # intended depth 8 - every pixel's ids, t, float32 RGB and the Stats equal the CPU oracle's (renderer.nim:144-159)
+    o = api.Options(1920, 1080, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+    fb, st, aov = _check_golden("config3_bunny_spheres_1920x1080_g4", scenes.bunny_spheres(), o)
+    _check_row_crcs("config3_bunny_spheres_1920x1080_g4", fb, aov)
+
+
+@pytest.mark.parametrize("path", ["0", "2"])
+def test_path_modes_agree(oracle_mod, monkeypatch, path):
+    # NRT_PATH: 0 = the wavefront for every bounce, 1 (default) = FusedPrimary + wavefront + PathTail, 2 = PathMega
+    # (one thread per sample, meshes walked by the thread): three formulations, one result
+    monkeypatch.setenv("NRT_PATH", path)
+    sc = scenes.bunny_spheres(stride=4)
+    o = api.Options(320, 180, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+    assert_parity(sc, o, oracle_mod)
+    assert_parity(sc, api.Options(200, 112), oracle_mod)                 # reference depth bug: cap 64
+    assert_parity(scenes.transformed_objects(), api.Options(240, 135, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
+    assert_parity(scenes.bunny(flip_winding=False, stride=2), api.Options(240, 135), oracle_mod)
+    assert_parity(scenes.spheres_reflection(), api.Options(160, 120, antialias=api.Antialias(api.akJittered, 3), seed=11), oracle_mod)
+
+
 def test_full_size_filter_vs_exact(monkeypatch):
     # BASELINE config 2 scene at 960x540: float32 filter + float64 verify == float64 brute force, all ids
     sc, o = scenes.bunny(), api.Options(960, 540)

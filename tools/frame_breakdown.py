@@ -27,4 +27,9 @@ for wl in sys.argv[1:] or ["config2"]:
     api.setKernelTiming(True); step(); kt = ds.kernelTimes(); api.setKernelTiming(False)
     tot = sum(ms for ms, _ in kt.values())
     print("   " + " | ".join(f"{k.split(' ')[0]} {ms:.2f}" for k, (ms, n) in sorted(kt.items(), key=lambda kv: -kv[1][0])) + f" | sum {tot:.2f}")
+    import hashlib, numpy as np
+    host = np.empty(o.width * o.height * 3, dtype=np.float32)
+    api.check(L.nrt_copy_to_host(host.ctypes.data_as(C.c_void_p), fb, host.nbytes), "copy")
+    print(f"   fb sha256 {hashlib.sha256(host.tobytes()).hexdigest()[:16]} stats {cs.num_primary_rays} {cs.num_intersection_tests} {cs.num_intersection_hits} {cs.num_rays} {cs.num_capped_samples}"
+          f"  NRT_PATH={os.environ.get('NRT_PATH', '1')} lib={os.path.basename(api.LIB_PATH)}")
     L.nrt_device_free(fb); ds.close()
