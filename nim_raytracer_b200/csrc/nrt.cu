@@ -13,6 +13,7 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/permutation_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <atomic>
 #include <type_traits>
@@ -43,7 +44,7 @@
 #define NRT_OCC_FUSED 0
 #endif
 #ifndef NRT_OCC_TAIL
-#define NRT_OCC_TAIL 0
+#define NRT_OCC_TAIL 1
 #endif
 #ifndef NRT_OCC_DEFAULT
 #define NRT_OCC_DEFAULT 4
@@ -114,7 +115,7 @@ template <> struct MinBlocks<ShadowTrace> { static constexpr int v = NRT_OCC_ST;
 template <bool CL> struct MinBlocks<ShadowTraceSampleT<CL>> { static constexpr int v = NRT_OCC_ST; };
 template <bool CL> struct MinBlocks<ShadowResolveT<CL>> { static constexpr int v = NRT_OCC_SR; };
 template <bool CL> struct MinBlocks<ShadeT<CL>> { static constexpr int v = NRT_OCC_SHADE; };
-template <bool CL, int KIND> struct MinBlocks<PathSampleT<CL, KIND>> { static constexpr int v = KIND == PATH_PRIMARY ? NRT_OCC_FUSED : NRT_OCC_TAIL; };
+template <bool CL> struct MinBlocks<FusedPrimaryT<CL>> { static constexpr int v = NRT_OCC_FUSED; };
 template <class F>
 __global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats(F f, int64_t n, unsigned long long* stats, int64_t ahead) {
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
@@ -127,16 +128,95 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats(F f,
   blockStatsAdd(d, stats);
 }
 
-// The same over [0, min(*count, cap)) with a device-resident count (PathTail: the list is filled by the kernels
-// before it).  CTA-uniform trip count: blockStatsAdd synchronises.
+// ---- warp-cooperative mesh walk (PathTail / PathMega, nrt_pipeline.h: PathWarpT) ---------------------
+// TriangleMesh.intersect (geom.nim:339-358) of ONE ray by the 32 lanes of a warp, over the flattened
+// hierarchy of a record set: 32 chunk bounds per step (lane j <-> chunk base + j, one ballot), the sub-chunk
+// bounds of two admitted chunks per step (16 lanes each), the records of two admitted sub-chunks per step
+// (16 lanes each: bounding circle / sphere, float32 sign test, the reference's float64 evaluation — side by
+// side in different lanes), then the warp's minimum of (t, face index).
+__device__ __forceinline__ MeshHit walkWarp(const DMesh& m, const RecSet& rs, int mode, const WalkRay& w, unsigned lane) {
+  const Ray r = walkRayAsRay(w);
+  const HotRay hr = walkRayHot(w);
+  double best = NRT_INF; uint32_t bt = kNoTri;     // geom.nim:343
+  const uint32_t nch = uint32_t(paddedFaces(int64_t(rs.nrec)) / kRecPad);
+  const unsigned half = lane >> 4, sl = lane & 15u;
+  for (uint32_t base = 0; base < nch; base += 32) {
+    const uint32_t c = base + lane;
+    unsigned m1 = __ballot_sync(0xffffffffu, c < nch && prefilterTest(mode, rs.bounds + 4 * size_t(c), hr));
+    while (m1) {
+      const int b0 = __ffs(m1) - 1; m1 &= m1 - 1;
+      int b1 = -1;
+      if (m1) { b1 = __ffs(m1) - 1; m1 &= m1 - 1; }
+      const int myb = half ? b1 : b0;
+      unsigned m2 = __ballot_sync(0xffffffffu, myb >= 0 && prefilterTest(mode, rs.sub + 4 * (size_t(base + myb) * kSubPerChunk + sl), hr));
+      while (m2) {
+        const int s0 = __ffs(m2) - 1; m2 &= m2 - 1;
+        int s1 = -1;
+        if (m2) { s1 = __ffs(m2) - 1; m2 &= m2 - 1; }
+        const int mys = half ? s1 : s0;
+        if (mys >= 0) {
+          const int64_t sub = int64_t(base + (mys < 16 ? b0 : b1)) * kSubPerChunk + (mys & 15);
+          walkRecord(m, rs, mode, sub * kSubRecs + sl, w, r, hr, best, bt);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ot = __shfl_xor_sync(0xffffffffu, best, off);
+    const uint32_t otri = __shfl_xor_sync(0xffffffffu, bt, off);
+    if (ot < best || (ot == best && otri < bt)) { best = ot; bt = otri; }
+  }
+  MeshHit h; h.t = (best == 0) ? 0.0 : best; h.tri = bt;
+  return h;
+}
+struct WarpCoop {
+  __device__ __forceinline__ bool any(bool x) const { return __any_sync(0xffffffffu, x); }
+  // every lane arrives here (dead lanes with need == false): the rays that passed their AABB gate are taken one
+  // at a time — ballot, broadcast of the ray from its lane, walk by the whole warp, result back to its lane
+  __device__ __forceinline__ void meshAll(const DScene& sc, bool need, int mode, int l, V4 o, V4 d, int force_exact, MeshRes& mr) const {
+    const unsigned lane = threadIdx.x & 31u;
+    for (int mo = 0; mo < sc.nmesh_objs && mo < kMaxWalkMO; ++mo) {
+      mr.t[mo] = NRT_NEG_INF; mr.tri[mo] = kNoTri;
+      const int md = walkMode(sc, mo, mode, l);
+      WalkRay w;
+      w.ox = w.oy = w.oz = w.dx = w.dy = w.dz = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { w.f[k] = 0.f; w.h[k] = 0.f; }
+      bool safe = false;
+      const bool pass = need && walkPrep(sc, mo, md, l, o, d, force_exact, w, safe);
+      if (pass) { mr.t[mo] = NRT_INF; }
+      if (pass && !safe) {   // float64 over all faces by the lane itself (rays the float32 filter cannot take: rare)
+        const MeshHit h = walkScalar(sc, mo, md, l, w, false);
+        mr.t[mo] = h.t; mr.tri[mo] = h.tri;
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, pass && safe);
+      if (!todo) continue;
+      const DMesh& m = sc.meshes[sc.objects[sc.mesh_obj_index[mo]].mesh];
+      const RecSet rs = sc.recsets[frameIndex(sc.nlights, mo, md, l)];
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        WalkRay b;
+        b.ox = __shfl_sync(0xffffffffu, w.ox, src); b.oy = __shfl_sync(0xffffffffu, w.oy, src); b.oz = __shfl_sync(0xffffffffu, w.oz, src);
+        b.dx = __shfl_sync(0xffffffffu, w.dx, src); b.dy = __shfl_sync(0xffffffffu, w.dy, src); b.dz = __shfl_sync(0xffffffffu, w.dz, src);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { b.f[k] = __shfl_sync(0xffffffffu, w.f[k], src); b.h[k] = __shfl_sync(0xffffffffu, w.h[k], src); }
+        const MeshHit h = walkWarp(m, rs, md, b, lane);
+        if (int(lane) == src) { mr.t[mo] = h.t; mr.tri[mo] = h.tri; }
+      }
+    }
+  }
+};
+// lane <-> element i of [0, n) (n = min(*count, nHost) when the count lives on the device); whole warps stay in
+// f.run() until their last lane's path has ended; CTA-uniform trip count (blockStatsAdd synchronises)
 template <class F>
-__global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats_counted(F f, const uint32_t* count, int64_t cap, unsigned long long* stats) {
-  int64_t n = *count;
-  if (n > cap) n = cap;
+__global__ void __launch_bounds__(kBlock, NRT_OCC_TAIL) k_path_warp(F f, const uint32_t* count, int64_t nHost, unsigned long long* stats) {
+  int64_t n = nHost;
+  if (count) { n = *count; if (n > nHost) n = nHost; }
   for (int64_t base = int64_t(blockIdx.x) * kBlock; base < n; base += int64_t(gridDim.x) * kBlock) {
     const int64_t i = base + threadIdx.x;
-    StatDelta d = zeroStats();
-    if (i < n) d = f(i);
+    const StatDelta d = f.run(i, i < n, WarpCoop{});
     blockStatsAdd(d, stats);
     __syncthreads();
   }
@@ -797,7 +877,8 @@ template <> struct CatOf<ShadowTrace> { static constexpr int v = KC_SHADOW_TRACE
 template <bool CL> struct CatOf<ShadowTraceSampleT<CL>> { static constexpr int v = KC_SHADOW_TRACE; };
 template <bool CL> struct CatOf<ShadowResolveT<CL>> { static constexpr int v = KC_SHADOW_RESOLVE; };
 template <> struct CatOf<Resolve> { static constexpr int v = KC_RESOLVE; };
-template <bool CL, int KIND> struct CatOf<PathSampleT<CL, KIND>> { static constexpr int v = KIND == PATH_PRIMARY ? KC_FUSED_PRIMARY : KC_PATH_TAIL; };
+template <bool CL> struct CatOf<FusedPrimaryT<CL>> { static constexpr int v = KC_FUSED_PRIMARY; };
+template <bool CL, int KIND> struct CatOf<PathWarpT<CL, KIND>> { static constexpr int v = KC_PATH_TAIL; };
 template <> struct CatOf<Finalize> { static constexpr int v = KC_FINALIZE; };
 template <> struct CatOf<ExactMesh> { static constexpr int v = KC_EXACT; };
 template <class A> struct CatOf<Refine<A>> { static constexpr int v = KC_REFINE; };
@@ -908,11 +989,13 @@ struct CudaBackend {
     k_for_each_stats<F><<<blocksFor(n), kBlock, 0, stream>>>(f, n, stats, prefetchAhead);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
-  template <class F> void forEachStatsCounted(const uint32_t* count, int64_t cap, const F& f, unsigned long long* stats) {
+  // PathTail (count on the device, at most n) / PathMega (count == nullptr: n elements)
+  template <class F> void pathWarp(const uint32_t* count, int64_t n, const F& f, unsigned long long* stats) {
     use();
-    if (cap <= 0) return;
+    if (n <= 0) return;
     Timed tm(this, CatOf<F>::v);
-    k_for_each_stats_counted<F><<<unsigned(std::min<int64_t>(int64_t(sms) * 8, (cap + kBlock - 1) / kBlock)), kBlock, 0, stream>>>(f, count, cap, stats);
+    const int64_t blocks = count ? std::min<int64_t>(int64_t(sms) * 8, (n + kBlock - 1) / kBlock) : (n + kBlock - 1) / kBlock;
+    k_path_warp<F><<<unsigned(blocks), kBlock, 0, stream>>>(f, count, n, stats);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   template <class F> void forEachCounted(const uint32_t* count, int64_t cap, const F& f) {
@@ -1013,11 +1096,19 @@ struct CudaBackend {
     NRT_CUDA(cudaGetLastError()); launches += 4;
   }
   // next bounce's active list: the samples of the current set with active == 1, in sample order
-  void compactActive(const ChunkState& cs, const ActiveSet& act, uint32_t* list, uint32_t* count) {
+  // `match` != 0: only the samples whose flag equals it (FusedPrimary's kFlagWavefront), identity set only
+  struct FlagIs { uint8_t v; __host__ __device__ bool operator()(uint8_t f) const { return f == v; } };
+  void compactActive(const ChunkState& cs, const ActiveSet& act, uint32_t* list, uint32_t* count, uint8_t match) {
     use();
     Timed tm(this, KC_COMPACT);
     size_t tb = 0;
-    if (!act.list) {
+    if (!act.list && match) {
+      thrust::counting_iterator<uint32_t> ids(0u);
+      auto flags = thrust::make_transform_iterator(cs.active, FlagIs{match});
+      NRT_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids, flags, list, count, int(act.n), stream));
+      void* tmp = scratch(0, tb);
+      NRT_CUDA(cub::DeviceSelect::Flagged(tmp, tb, ids, flags, list, count, int(act.n), stream));
+    } else if (!act.list) {
       thrust::counting_iterator<uint32_t> ids(0u);
       NRT_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids, cs.active, list, count, int(act.n), stream));
       void* tmp = scratch(0, tb);

@@ -110,9 +110,6 @@ struct ChunkState {
   uint32_t* alist;     // 2*S: compacted sample indices of the continuing paths (ping-pong per bounce)
   uint32_t* acount;    // per bounce: entries of the list consumed by that bounce
   unsigned long long* stats;  // ST_COUNT
-  // fused path (FusedPrimary / PathTail): the samples whose path continues after bounce 0, in any order
-  uint32_t* tailList;  // S entries (null: the wavefront loop handles every bounce)
-  uint32_t* tailCount; // 1
   // pixel list of this worker
   const int32_t* rows; // device array of row indices
   int64_t p0;          // first pixel (in the worker's pixel list) of this chunk
@@ -481,55 +478,94 @@ NRT_HD bool meshGatePass(const DScene& sc, int mo, V4 o, V4 d) {
   const double tmin = aabbIntersect(m.bmin, m.bmax, initRay(oo, dd));
   return !(tmin < 0);
 }
-NRT_HD MeshHit meshIntersectWalk(const DScene& sc, int mo, int mode, int l, V4 o, V4 d, int force_exact) {
-  MeshHit h; h.t = NRT_NEG_INF; h.tri = kNoTri;
+// What a walk of mesh object `mo` needs for one ray: the gate's verdict, the object-space ray (orig / dir are
+// all rayTriangleExact reads) and, when the float32 filter can take the ray (`safe`), its two filter forms.
+struct WalkRay {
+  double ox, oy, oz, dx, dy, dz;   // object-space ray
+  float f[8];                      // FilterRay: (a.xyz, rr | m.xyz, 0)
+  float h[8];                      // HotRay:    (a0..a3 | b0..b2, 0)
+};
+NRT_HD Ray walkRayAsRay(const WalkRay& w) {
+  Ray r; r.orig = v4(w.ox, w.oy, w.oz, 1.0); r.dir = v4(w.dx, w.dy, w.dz, 0.0);
+  r.ix = r.iy = r.iz = 0.0; r.sx = r.sy = r.sz = 0;   // (invDir / sign are only read by the AABB test)
+  return r;
+}
+NRT_HD HotRay walkRayHot(const WalkRay& w) {
+  HotRay h; h.a0 = w.h[0]; h.a1 = w.h[1]; h.a2 = w.h[2]; h.a3 = w.h[3]; h.b0 = w.h[4]; h.b1 = w.h[5]; h.b2 = w.h[6]; h.b3 = 0.f;
+  return h;
+}
+// the bundle a ray of hint `mode` is walked in (a bundle without a usable frame falls back to GENERAL)
+NRT_HD int walkMode(const DScene& sc, int mo, int mode, int l) {
+  if (mode != FM_GENERAL && !(sc.frames[frameIndex(sc.nlights, mo, mode, l)].valid > 0)) return FM_GENERAL;
+  return mode;
+}
+// returns pass (the ray enters the box, geom.nim:340); `safe`: the filter walk applies, else all faces in float64
+NRT_HD bool walkPrep(const DScene& sc, int mo, int mode, int l, V4 o, V4 d, int force_exact, WalkRay& w, bool& safe) {
+  safe = false;
   const DObject& ob = sc.objects[sc.mesh_obj_index[mo]];
   const DMesh& m = sc.meshes[ob.mesh];
   V4 oo, dd;
   toObject(ob, o, d, oo, dd);                      // renderer.nim:54-55
-  if (boxCertainMiss(m, oo, dd)) return h;
+  if (boxCertainMiss(m, oo, dd)) return false;
   const Ray r = initRay(oo, dd);
-  if (aabbIntersect(m.bmin, m.bmax, r) < 0) return h;   // geom.nim:340 (NegInf: no box hit)
-  double best = NRT_INF; uint32_t bt = kNoTri;     // geom.nim:343
-  if (mode != FM_GENERAL && !(sc.frames[frameIndex(sc.nlights, mo, mode, l)].valid > 0)) mode = FM_GENERAL;
+  if (aabbIntersect(m.bmin, m.bmax, r) < 0) return false;   // geom.nim:340 (NegInf: no box hit)
+  w.ox = oo.x; w.oy = oo.y; w.oz = oo.z; w.dx = dd.x; w.dy = dd.y; w.dz = dd.z;
   const int fi = frameIndex(sc.nlights, mo, mode, l);
-  const RecSet rs = sc.recsets[fi];
   FilterRay fr; HotRay hr;
-  const bool safe = !force_exact && rs.usable && makeFilterRay(mode, m, r, fr) && makeHotRay(mode, sc.frames[fi], r, hr);
+  safe = !force_exact && sc.recsets[fi].usable && makeFilterRay(mode, m, r, fr) && makeHotRay(mode, sc.frames[fi], r, hr);
+  if (safe) {
+    w.f[0] = fr.ax; w.f[1] = fr.ay; w.f[2] = fr.az; w.f[3] = fr.rr; w.f[4] = fr.mx; w.f[5] = fr.my; w.f[6] = fr.mz; w.f[7] = 0.f;
+    w.h[0] = hr.a0; w.h[1] = hr.a1; w.h[2] = hr.a2; w.h[3] = hr.a3; w.h[4] = hr.b0; w.h[5] = hr.b1; w.h[6] = hr.b2; w.h[7] = 0.f;
+  }
+  return true;
+}
+// record `rec` of set `rs` against the ray: bounding circle / sphere, float32 sign test, float64 (geom.nim:283-336);
+// keeps the nearest accepted t, the lowest face index on ties
+NRT_HD void walkRecord(const DMesh& m, const RecSet& rs, int mode, int64_t rec, const WalkRay& w, const Ray& r, const HotRay& hr, double& best, uint32_t& bt) {
+  const int nh = hotFloats(mode), nc = recFloats(mode);
+  float hh[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < nh; ++j) hh[j] = rs.hot[recIndex(rec, j, nh)];
+  if (!prefilterTest(mode, hh, hr)) return;
+  float q[16];
+  for (int j = 0; j < nc; ++j) q[j] = rs.recs[fullIndex(rec, j)];
+  if (int32_t(filterTest(mode, q, w.f, w.f + 4, w.f[3])) < 0) return;
+  uint32_t tri = rs.ids ? rs.ids[rec] : uint32_t(rec);
+  if (recSlotId(mode) >= 0) tri = fbits(q[recSlotId(mode)]);
+  const double t = rayTriangleExact(r, m.verts + 4 * m.vidx[3 * int64_t(tri)], m.verts + 4 * m.vidx[3 * int64_t(tri) + 1],
+                                    m.verts + 4 * m.vidx[3 * int64_t(tri) + 2]);
+  if (t >= 0 && (t < best || (t == best && tri < bt))) { best = t; bt = tri; }
+}
+NRT_HD MeshHit walkScalar(const DScene& sc, int mo, int mode, int l, const WalkRay& w, bool safe) {
+  const DMesh& m = sc.meshes[sc.objects[sc.mesh_obj_index[mo]].mesh];
+  const Ray r = walkRayAsRay(w);
+  double best = NRT_INF; uint32_t bt = kNoTri;     // geom.nim:343
   if (!safe) {
     for (int64_t f = 0; f < m.nfaces; ++f) {       // geom.nim:346-356
       const double t = rayTriangleExact(r, m.verts + 4 * m.vidx[3 * f], m.verts + 4 * m.vidx[3 * f + 1], m.verts + 4 * m.vidx[3 * f + 2]);
       if (t >= 0 && t < best) { best = t; bt = uint32_t(f); }
     }
   } else {
-    const int nh = hotFloats(mode), nc = recFloats(mode);
+    const RecSet rs = sc.recsets[frameIndex(sc.nlights, mo, mode, l)];
+    const HotRay hr = walkRayHot(w);
     const int64_t nch = paddedFaces(int64_t(rs.nrec)) / kRecPad;
-    const float p0[4] = {fr.ax, fr.ay, fr.az, fr.rr}, p1[4] = {fr.mx, fr.my, fr.mz, 0.f};
     for (int64_t ch = 0; ch < nch; ++ch) {
       if (!prefilterTest(mode, rs.bounds + 4 * ch, hr)) continue;
       for (int sb = 0; sb < kSubPerChunk; ++sb) {
         const int64_t sub = ch * kSubPerChunk + sb;
         if (!prefilterTest(mode, rs.sub + 4 * sub, hr)) continue;
-        for (int k = 0; k < kSubRecs; ++k) {
-          const int64_t rec = sub * kSubRecs + k;
-          float hh[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int j = 0; j < nh; ++j) hh[j] = rs.hot[recIndex(rec, j, nh)];
-          if (!prefilterTest(mode, hh, hr)) continue;
-          float q[16];
-          for (int j = 0; j < nc; ++j) q[j] = rs.recs[fullIndex(rec, j)];
-          if (int32_t(filterTest(mode, q, p0, p1, fr.rr)) < 0) continue;
-          uint32_t tri = rs.ids ? rs.ids[rec] : uint32_t(rec);
-          if (recSlotId(mode) >= 0) tri = fbits(q[recSlotId(mode)]);
-          const double t = rayTriangleExact(r, m.verts + 4 * m.vidx[3 * int64_t(tri)], m.verts + 4 * m.vidx[3 * int64_t(tri) + 1],
-                                            m.verts + 4 * m.vidx[3 * int64_t(tri) + 2]);
-          if (t >= 0 && (t < best || (t == best && tri < bt))) { best = t; bt = tri; }
-        }
+        for (int k = 0; k < kSubRecs; ++k) walkRecord(m, rs, mode, sub * kSubRecs + k, w, r, hr, best, bt);
       }
     }
   }
-  h.t = (best == 0) ? 0.0 : best;   // -0.0 -> +0.0 (as Verify1 / ExactMesh)
-  h.tri = bt;
+  MeshHit h; h.t = (best == 0) ? 0.0 : best; h.tri = bt;   // -0.0 -> +0.0 (as Verify1 / ExactMesh)
   return h;
+}
+NRT_HD MeshHit meshIntersectWalk(const DScene& sc, int mo, int mode, int l, V4 o, V4 d, int force_exact) {
+  MeshHit h; h.t = NRT_NEG_INF; h.tri = kNoTri;
+  mode = walkMode(sc, mo, mode, l);
+  WalkRay w; bool safe;
+  if (!walkPrep(sc, mo, mode, l, o, d, force_exact, w, safe)) return h;
+  return walkScalar(sc, mo, mode, l, w, safe);
 }
 
 // How trace() obtains TriangleMesh.intersect of the current ray for mesh object `mo`:
@@ -557,6 +593,19 @@ struct WalkMesh {
   NRT_HD void eval(int mo, V4 o, V4 d, double& t, uint32_t& tri) const {
     const MeshHit h = meshIntersectWalk(*sc, mo, mode, l, o, d, force_exact);
     t = h.t; tri = h.tri;
+  }
+};
+
+// The mesh results of the current ray were computed before trace() is entered (PathWarp: by the whole warp);
+// mesh objects beyond the kMaxWalkMO slots are walked by the thread itself.
+static constexpr int kMaxWalkMO = 2;
+struct MeshRes { double t[kMaxWalkMO]; uint32_t tri[kMaxWalkMO]; };
+struct PreMesh {
+  const MeshRes& res; WalkMesh rest;
+  NRT_HD bool miss(uint32_t mo) const { return mo < uint32_t(kMaxWalkMO) && !(res.t[mo] >= 0); }
+  NRT_HD void eval(int mo, V4 o, V4 d, double& t, uint32_t& tri) const {
+    if (mo < kMaxWalkMO) { t = res.t[mo]; tri = res.tri[mo]; }
+    else rest.eval(mo, o, d, t, tri);
   }
 };
 
@@ -861,22 +910,6 @@ using ShadowTraceSampleClustered = ShadowTraceSampleT<true>;
 // The work of one hit sample after its shadow rays are known.  `occluded(l)`: the shadow ray towards
 // light l hit something (renderer.nim:103).  `hitW` is only valid with point lights (a DistantLight
 // ignores it); without them it is fetched here for the (few) continuing samples only.
-// Appends sample s to the list of the samples PathTail finishes (order is irrelevant there: every sample
-// is independent).  On the GPU the lanes of a warp that arrive together share one atomic.
-NRT_HD void pushTail(const ChunkState& cs, uint32_t s) {
-#if defined(__CUDA_ARCH__)
-  const unsigned m = __activemask();
-  const unsigned lane = threadIdx.x & 31u;
-  const int leader = __ffs(m) - 1;
-  uint32_t base = 0;
-  if (int(lane) == leader) base = atomicAdd(cs.tailCount, uint32_t(__popc(m)));
-  base = __shfl_sync(m, base, leader);
-  cs.tailList[base + __popc(m & ((1u << lane) - 1u))] = s;
-#else
-  cs.tailList[(*cs.tailCount)++] = s;
-#endif
-}
-
 template <class OCC>
 NRT_HD void resolveSample(const DScene* sc, const FrameParams& fp, const ChunkState& cs, int bounce, int pointLights,
                           int64_t s, int objHit, V4 hitW, const V4& n, const OCC& occluded, StatDelta& st) {
@@ -912,7 +945,6 @@ NRT_HD void resolveSample(const DScene* sc, const FrameParams& fp, const ChunkSt
     st4(cs.rayD, cs.S, s, r);
     cs.weight[s] = w * k;
     cs.active[s] = 1;
-    if (cs.tailList) pushTail(cs, uint32_t(s));
     st.v[ST_CONT] = 1;
   } else {
     cs.active[s] = 0;
@@ -1002,136 +1034,230 @@ using ShadowResolveClustered = ShadowResolveT<true>;
 //                 to the wavefront instead (its ray and active = 1 are stored, nothing else, and it adds
 //                 nothing to Stats: the wavefront redoes it from the ray); every other sample is finished
 //                 here: accumulator written once, and, if its path continues, the reflection ray is stored
-//                 and the sample appended to the tail list.
-//   PathTail      all later bounces of the samples on the tail list (few: ~0.4 % of the samples), one thread
-//                 per sample to the end of its path; a ray that enters a mesh box walks the flattened
-//                 hierarchy of the mesh by itself (meshIntersectWalk).  No launch chain, no host round trip
-//                 per bounce.
-//   PathMega      FusedPrimary + PathTail in one: every sample start to end in one thread, meshes walked
-//                 (NRT_PATH=mega; small frames, where a single launch beats the ~25 of the wavefront).
+//                 (flag kFlagContinues).
+//   PathTail      the remaining bounces of a SMALL active list (below NRT_TAIL_BELOW samples), one lane per
+//                 sample to the end of its path, the warp walking the mesh hierarchy for the rays that enter a
+//                 box: one launch instead of ~25 dependent launches and a host round trip per bounce for waves
+//                 of a few thousand samples.  (Large waves stay with the wavefront: its prefilter shares every
+//                 record it loads among the 256 rays of a run — measured 10x the walk's throughput per ray.)
+//   PathMega      every sample start to end in one launch (NRT_PATH=2; for comparison and very small frames).
 // The arithmetic is the wavefront's, operation by operation (Shade, ShadowResolve, resolveSample).
 enum PathKind { PATH_PRIMARY = 0, PATH_TAIL = 1, PATH_MEGA = 2 };
-template <bool CL, int KIND>
-struct PathSampleT {
+NRT_HD void writeAovOf(const FrameParams& fp, const ChunkState& cs, int64_t s, const TraceOut& tr) {
+  if ((cs.aovObj || cs.aovTri || cs.aovT) && s == divFast(s, fp.spp) * fp.spp) {
+    int x, y; pixelOf(fp, cs, cs.p0 + divFast(s, fp.spp), x, y);
+    const int64_t pi = int64_t(y) * fp.width + x;
+    if (cs.aovObj) cs.aovObj[pi] = tr.obj;
+    if (cs.aovTri) cs.aovTri[pi] = (tr.obj >= 0 && tr.tri != kNoTri) ? int32_t(tr.tri) : -1;
+    if (cs.aovT) cs.aovT[pi] = tr.t;
+  }
+}
+// normal at the hit (renderer.nim:76-88)
+NRT_HD V4 hitNormal(const DScene& sc, const DObject& ob, const TraceOut& tr, V4 hitW) {
+  if (tr.tri == kNoTri) {
+    if (ob.kind == GEOM_PLANE) return v4(ob.plane_nw[0], ob.plane_nw[1], ob.plane_nw[2], ob.plane_nw[3]);   // the product was done at scene build
+    return mulm(ob.o2w, geomNormal(ob, mulm(ob.w2o, hitW)));
+  }
+  const DMesh& m = sc.meshes[ob.mesh];
+  const double* nn = m.normals + 4 * m.nidx[3 * int64_t(tr.tri)];
+  return mulm(ob.o2w, v4(nn[0], nn[1], nn[2], nn[3]));
+}
+
+// cs.active after FusedPrimary: 0 = the sample is finished, kFlagWavefront = bounce 0 is the wavefront's,
+// kFlagContinues = bounce 0 done here, the reflection ray is stored.  After the wavefront's bounce 0 every
+// nonzero flag is a sample whose path continues (Resolve writes 0 / 1 for its samples).
+static constexpr uint8_t kFlagWavefront = 1, kFlagContinues = 2;
+template <bool CL>
+struct FusedPrimaryT {
   const DScene* sc; FrameParams fp; ChunkState cs; int force_exact;
   int genFromState;   // the primary rays are in cs.rayD / cs.active already (jittered kinds: GenJittered)
   NRT_HD void prefetch(int64_t) const {}
-  template <class MP>
-  NRT_HD TraceOut trace(const MP& mp, V4 o, V4 d, double tNear) const { return traceObjects<CL>(*sc, mp, o, d, tNear); }
-  NRT_HD StatDelta operator()(int64_t idx) const {
+  NRT_HD StatDelta operator()(int64_t s) const {
     StatDelta st = zeroStats();
-    int64_t s = idx;
     V4 o, d;
-    double w = 1.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    int bounce = 0;
-    if (KIND == PATH_TAIL) {
-      s = int64_t(cs.tailList[idx]);
-      o = ld4(cs.rayO, cs.S, s); d = ld4(cs.rayD, cs.S, s);
-      w = cs.weight[s];
-      a0 = cs.accum[s]; a1 = cs.accum[cs.S + s]; a2 = cs.accum[2 * cs.S + s];
-      bounce = 1;
+    bool alive;
+    if (genFromState) {
+      o = primaryOrigin(*sc); d = ld4(cs.rayD, cs.S, s); alive = cs.active[s] != 0;
     } else {
-      bool alive;
-      if (genFromState) {
-        o = primaryOrigin(*sc); d = ld4(cs.rayD, cs.S, s); alive = cs.active[s] != 0;
-      } else {
-        GenOut g; GenSimple{sc, fp, cs}.compute(s, g);
-        o = g.o; d = g.d; alive = g.alive;
-      }
-      if (!alive) { if (KIND == PATH_PRIMARY) cs.active[s] = 0; return st; }   // (skipped pixel of a progressive pass)
+      GenOut g; GenSimple{sc, fp, cs}.compute(s, g);
+      o = g.o; d = g.d; alive = g.alive;
     }
+    if (!alive) { cs.active[s] = 0; return st; }   // (skipped pixel of a progressive pass)
     const int nMO = cs.nMO, nL = cs.nL;
-    for (;;) {
-      if (KIND == PATH_PRIMARY) {
-        for (int mo = 0; mo < nMO; ++mo)
-          if (meshGatePass(*sc, mo, o, d)) return toWavefront(s, d);
-      }
-      const TraceOut tr = (KIND == PATH_PRIMARY) ? trace(NoMesh{}, o, d, NRT_INF)
-                                                 : trace(WalkMesh{sc, bounce == 0 ? FM_ORIGIN : FM_GENERAL, 0, force_exact}, o, d, NRT_INF);
-      st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
-      if (bounce == 0) st.v[ST_PRIMARY] = 1;
-      if (tr.obj < 0) {   // renderer.nim:74-75 / :123-124: background
-        if (bounce == 0) writeAov(s, tr);
-        a0 = a0 + sc->bg[0] * w; a1 = a1 + sc->bg[1] * w; a2 = a2 + sc->bg[2] * w;
-        break;
-      }
+    for (int mo = 0; mo < nMO; ++mo)
+      if (meshGatePass(*sc, mo, o, d)) return toWavefront(s, d);
+    const TraceOut tr = traceObjects<CL>(*sc, NoMesh{}, o, d, NRT_INF);
+    st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits; st.v[ST_PRIMARY] = 1;
+    double a0, a1, a2;
+    uint8_t flag = 0;
+    if (tr.obj < 0) {   // renderer.nim:74-75: background
+      writeAovOf(fp, cs, s, tr);
+      a0 = 0.0 + sc->bg[0] * 1.0; a1 = 0.0 + sc->bg[1] * 1.0; a2 = 0.0 + sc->bg[2] * 1.0;
+    } else {
       const DObject& ob = sc->objects[tr.obj];
       const V4 hitW = add(o, scale(d, tr.t));
-      V4 n;
-      if (tr.tri == kNoTri) {
-        if (ob.kind == GEOM_PLANE) n = v4(ob.plane_nw[0], ob.plane_nw[1], ob.plane_nw[2], ob.plane_nw[3]);
-        else n = mulm(ob.o2w, geomNormal(ob, mulm(ob.w2o, hitW)));
-      } else {
-        const DMesh& m = sc->meshes[ob.mesh];
-        const double* nn = m.normals + 4 * m.nidx[3 * int64_t(tr.tri)];
-        n = mulm(ob.o2w, v4(nn[0], nn[1], nn[2], nn[3]));
-      }
+      const V4 n = hitNormal(*sc, ob, tr, hitW);
       const V4 so = add(hitW, scale(n, fp.bias));                                    // renderer.nim:98
-      if (KIND == PATH_PRIMARY) {   // a shadow ray that enters a mesh box: the wavefront takes the sample
-        for (int l = 0; l < nL; ++l) {
-          const V4 sdir = scale(getShadingInfo(sc->lights[l], hitW).lightDir, -1.0);
-          for (int mo = 0; mo < nMO; ++mo)
-            if (meshGatePass(*sc, mo, so, sdir)) return toWavefront(s, d);
-        }
+      for (int l = 0; l < nL; ++l) {   // a shadow ray that enters a mesh box: the wavefront takes the sample
+        const V4 sdir = scale(getShadingInfo(sc->lights[l], hitW).lightDir, -1.0);
+        for (int mo = 0; mo < nMO; ++mo)
+          if (meshGatePass(*sc, mo, so, sdir)) return toWavefront(s, d);
       }
-      if (bounce == 0) writeAov(s, tr);
+      writeAovOf(fp, cs, s, tr);
       V3 local = v3(0.0, 0.0, 0.0);
       for (int l = 0; l < nL; ++l) {
         const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
         const V4 sdir = scale(li.lightDir, -1.0);                                    // renderer.nim:99
-        const TraceOut ts = (KIND == PATH_PRIMARY)
-            ? trace(NoMesh{}, so, sdir, li.lightDistance)
-            : trace(WalkMesh{sc, sc->lights[l].kind == LIGHT_DISTANT ? FM_DIR : FM_GENERAL, l, force_exact}, so, sdir, li.lightDistance);
+        const TraceOut ts = traceObjects<CL>(*sc, NoMesh{}, so, sdir, li.lightDistance);
         st.v[ST_RAYS] += 1; st.v[ST_TESTS] += ts.tests; st.v[ST_HITS] += ts.hits;
         if (ts.obj < 0) local = add(local, shadeDiffuse(ob, li, n));                 // renderer.nim:103-105
       }
-      // resolveSample's arithmetic
-      const double k = ob.reflection;
-      const int depth = (fp.depth_mode == DEPTH_INTENDED) ? (1 + bounce) : 0;      // renderer.nim:108 + depth bug
+      // resolveSample's arithmetic at bounce 0 (weight 1, accumulator 0)
+      const double k = ob.reflection, w = 1.0;
+      const int depth = (fp.depth_mode == DEPTH_INTENDED) ? 1 : 0;                  // renderer.nim:108 + depth bug
       bool cont = false;
       double wl = w;
       if (k > 0.0 && depth <= fp.max_ray_depth) {
-        if (bounce >= fp.bounce_cap) st.v[ST_CAPPED] += 1;
+        if (0 >= fp.bounce_cap) st.v[ST_CAPPED] = 1;
         else { cont = true; wl = w * (1.0 - k); }
       }
-      a0 = a0 + local.x * wl; a1 = a1 + local.y * wl; a2 = a2 + local.z * wl;
-      if (!cont) break;
-      const V4 r = sub(d, scale(n, 2 * dot(n, d)));                                  // renderer.nim:112
-      o = add(hitW, scale(r, fp.bias)); d = r; w = w * k;
-      if (KIND == PATH_PRIMARY) {
-        st4(cs.rayO, cs.S, s, o); st4(cs.rayD, cs.S, s, d);
-        cs.weight[s] = w;
-        pushTail(cs, uint32_t(s));
-        break;
+      a0 = 0.0 + local.x * wl; a1 = 0.0 + local.y * wl; a2 = 0.0 + local.z * wl;
+      if (cont) {
+        const V4 r = sub(d, scale(n, 2 * dot(n, d)));                                // renderer.nim:112
+        st4(cs.rayO, cs.S, s, add(hitW, scale(r, fp.bias))); st4(cs.rayD, cs.S, s, r);
+        cs.weight[s] = w * k;
+        flag = kFlagContinues;
       }
-      ++bounce;
     }
     cs.accum[s] = a0; cs.accum[cs.S + s] = a1; cs.accum[2 * cs.S + s] = a2;
-    if (KIND == PATH_PRIMARY) cs.active[s] = 0;
+    cs.active[s] = flag;
     return st;
   }
-  // hands sample s to the wavefront: its primary ray + active = 1 (= a member of the bounce-0 active list)
+  // hands sample s to the wavefront: its primary ray + the flag that puts it on the bounce-0 list of the wavefront
   NRT_HD StatDelta toWavefront(int64_t s, V4 d) const {
     if (!genFromState) st4(cs.rayD, cs.S, s, d);
-    cs.active[s] = 1;
+    cs.active[s] = kFlagWavefront;
     return zeroStats();
   }
-  NRT_HD void writeAov(int64_t s, const TraceOut& tr) const {
-    if ((cs.aovObj || cs.aovTri || cs.aovT) && s == divFast(s, fp.spp) * fp.spp) {
-      int x, y; pixelOf(fp, cs, cs.p0 + divFast(s, fp.spp), x, y);
-      const int64_t pi = int64_t(y) * fp.width + x;
-      if (cs.aovObj) cs.aovObj[pi] = tr.obj;
-      if (cs.aovTri) cs.aovTri[pi] = (tr.obj >= 0 && tr.tri != kNoTri) ? int32_t(tr.tri) : -1;
-      if (cs.aovT) cs.aovT[pi] = tr.t;
+};
+using FusedPrimary = FusedPrimaryT<false>;
+using FusedPrimaryClustered = FusedPrimaryT<true>;
+
+// ---- PathTail / PathMega: warp-synchronous paths -----------------------------------------------------
+// One lane per sample; the lanes of a warp walk through the bounces together (`while any lane alive`), so
+// that the mesh intersections of the warp's current rays happen at points where all 32 lanes are present:
+// there the warp takes the rays that passed an AABB gate one at a time and walks the mesh hierarchy for
+// each with all its lanes (nrt.cu: WarpCoop — 32 chunk bounds per step, ballots, two sub-chunks of 16 per
+// step, the float64 evaluations of the survivors side by side in different lanes).  A thread walking the
+// hierarchy alone (ScalarCoop: the emulation, and mesh objects beyond kMaxWalkMO) serialises on divergence:
+// measured 13.5 ms for the 0.56 M tail samples of a config-4 frame against ~1 ms of the wavefront.
+// `W::any(x)`: some lane of the warp has x;  `W::meshAll(...)`: TriangleMesh.intersect for every lane's ray.
+struct ScalarCoop {
+  NRT_HD bool any(bool x) const { return x; }
+  NRT_HD void meshAll(const DScene& sc, bool need, int mode, int l, V4 o, V4 d, int force_exact, MeshRes& mr) const {
+    for (int mo = 0; mo < sc.nmesh_objs && mo < kMaxWalkMO; ++mo) {
+      mr.t[mo] = NRT_NEG_INF; mr.tri[mo] = kNoTri;
+      if (!need) continue;
+      const MeshHit h = meshIntersectWalk(sc, mo, mode, l, o, d, force_exact);
+      mr.t[mo] = h.t; mr.tri[mo] = h.tri;
     }
   }
 };
-using FusedPrimary = PathSampleT<false, PATH_PRIMARY>;
-using FusedPrimaryClustered = PathSampleT<true, PATH_PRIMARY>;
-using PathTail = PathSampleT<false, PATH_TAIL>;
-using PathTailClustered = PathSampleT<true, PATH_TAIL>;
-using PathMega = PathSampleT<false, PATH_MEGA>;
-using PathMegaClustered = PathSampleT<true, PATH_MEGA>;
+
+template <bool CL, int KIND>   // KIND: PATH_TAIL (the samples of the tail list, from bounce 1) or PATH_MEGA (every sample, from its primary ray)
+struct PathWarpT {
+  const DScene* sc; FrameParams fp; ChunkState cs; int force_exact;
+  int genFromState;
+  ActiveSet act;     // PATH_TAIL: the samples to finish (list + count on the device)
+  int bounce0;       // PATH_TAIL: the bounce their stored rays belong to
+  NRT_HD void prefetch(int64_t) const {}
+  NRT_HD StatDelta operator()(int64_t idx) const { return run(idx, true, ScalarCoop{}); }
+  template <class W>
+  NRT_HD StatDelta run(int64_t idx, bool valid, const W& coop) const {
+    StatDelta st = zeroStats();
+    int64_t s = 0;
+    V4 o = v4(0.0, 0.0, 0.0, 1.0), d = v4(0.0, 0.0, -1.0, 0.0);
+    double w = 1.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    int bounce = (KIND == PATH_TAIL) ? bounce0 : 0;
+    bool alive = valid;
+    if (valid) {
+      if (KIND == PATH_TAIL) {
+        s = sampleOf(act, idx);
+        o = ld4(cs.rayO, cs.S, s); d = ld4(cs.rayD, cs.S, s);
+        w = cs.weight[s];
+        a0 = cs.accum[s]; a1 = cs.accum[cs.S + s]; a2 = cs.accum[2 * cs.S + s];
+      } else {
+        s = idx;
+        if (genFromState) {
+          o = primaryOrigin(*sc); d = ld4(cs.rayD, cs.S, s); alive = cs.active[s] != 0;
+        } else {
+          GenOut g; GenSimple{sc, fp, cs}.compute(s, g);
+          o = g.o; d = g.d; alive = g.alive;
+        }
+      }
+    }
+    const bool started = alive;
+    const int nL = cs.nL;
+    while (coop.any(alive)) {
+      MeshRes mr;
+      coop.meshAll(*sc, alive, bounce == 0 ? FM_ORIGIN : FM_GENERAL, 0, o, d, force_exact, mr);
+      bool hit = false;
+      TraceOut tr; tr.obj = -1; tr.t = 0.0; tr.tri = kNoTri; tr.tests = 0; tr.hits = 0;
+      V4 hitW = o, n = d, so = o;
+      if (alive) {
+        tr = traceObjects<CL>(*sc, PreMesh{mr, WalkMesh{sc, bounce == 0 ? FM_ORIGIN : FM_GENERAL, 0, force_exact}}, o, d, NRT_INF);
+        st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
+        if (bounce == 0) { st.v[ST_PRIMARY] = 1; writeAovOf(fp, cs, s, tr); }
+        if (tr.obj < 0) {   // renderer.nim:74-75 / :123-124: background
+          a0 = a0 + sc->bg[0] * w; a1 = a1 + sc->bg[1] * w; a2 = a2 + sc->bg[2] * w;
+          alive = false;
+        } else {
+          hit = true;
+          hitW = add(o, scale(d, tr.t));
+          n = hitNormal(*sc, sc->objects[tr.obj], tr, hitW);
+          so = add(hitW, scale(n, fp.bias));                                         // renderer.nim:98
+        }
+      }
+      V3 local = v3(0.0, 0.0, 0.0);
+      for (int l = 0; l < nL; ++l) {
+        ShadingInfo li; li.lightDir = d; li.lightIntensity = v3(0.0, 0.0, 0.0); li.lightDistance = NRT_INF;
+        if (hit) li = getShadingInfo(sc->lights[l], hitW);
+        const V4 sdir = scale(li.lightDir, -1.0);                                    // renderer.nim:99
+        const int smode = sc->lights[l].kind == LIGHT_DISTANT ? FM_DIR : FM_GENERAL;
+        coop.meshAll(*sc, hit, smode, l, so, sdir, force_exact, mr);
+        if (hit) {
+          const TraceOut ts = traceObjects<CL>(*sc, PreMesh{mr, WalkMesh{sc, smode, l, force_exact}}, so, sdir, li.lightDistance);
+          st.v[ST_RAYS] += 1; st.v[ST_TESTS] += ts.tests; st.v[ST_HITS] += ts.hits;
+          if (ts.obj < 0) local = add(local, shadeDiffuse(sc->objects[tr.obj], li, n));   // renderer.nim:103-105
+        }
+      }
+      if (hit) {   // resolveSample's arithmetic
+        const double k = sc->objects[tr.obj].reflection;
+        const int depth = (fp.depth_mode == DEPTH_INTENDED) ? (1 + bounce) : 0;    // renderer.nim:108 + depth bug
+        bool cont = false;
+        double wl = w;
+        if (k > 0.0 && depth <= fp.max_ray_depth) {
+          if (bounce >= fp.bounce_cap) st.v[ST_CAPPED] += 1;
+          else { cont = true; wl = w * (1.0 - k); }
+        }
+        a0 = a0 + local.x * wl; a1 = a1 + local.y * wl; a2 = a2 + local.z * wl;
+        if (cont) {
+          const V4 r = sub(d, scale(n, 2 * dot(n, d)));                              // renderer.nim:112
+          o = add(hitW, scale(r, fp.bias)); d = r; w = w * k;
+        } else {
+          alive = false;
+        }
+      }
+      ++bounce;   // (the same for every lane that is still alive)
+    }
+    if (started) { cs.accum[s] = a0; cs.accum[cs.S + s] = a1; cs.accum[2 * cs.S + s] = a2; }
+    return st;
+  }
+};
+using PathTail = PathWarpT<false, PATH_TAIL>;
+using PathTailClustered = PathWarpT<true, PATH_TAIL>;
+using PathMega = PathWarpT<false, PATH_MEGA>;
+using PathMegaClustered = PathWarpT<true, PATH_MEGA>;
 
 // ---- finalize: sample sum in order, * 1/N, float32 store (+ step x step fill)
 struct Finalize {

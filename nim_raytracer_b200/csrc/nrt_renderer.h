@@ -458,7 +458,7 @@ struct Renderer {
   int capMO = -1, capNL = -1, capWaves = 0, capRows = 0;
   std::vector<void*> owned;
   int32_t* dRows = nullptr;
-  uint32_t* dTailCount = nullptr;
+  int64_t tailBelow = 32768;   // NRT_TAIL_BELOW: active lists shorter than this are finished by one PathTail launch
   // NRT_PATH: 0 = the wavefront for every bounce (round-1 pipeline), 1 = FusedPrimary + wavefront for the samples
   // with mesh rays at bounce 0 + PathTail (default), 2 = PathMega (one thread per sample start to end)
   int pathMode = int(envInt("NRT_PATH", 1));
@@ -474,7 +474,7 @@ struct Renderer {
   void freeAll() {
     for (void* p : owned) be->dfree(p);
     owned.clear();
-    capS = capNR = capCand = capPairs = 0; capMO = -1; capNL = -1; capWaves = 0; capRows = 0; dRows = nullptr; dTailCount = nullptr;
+    capS = capNR = capCand = capPairs = 0; capMO = -1; capNL = -1; capWaves = 0; capRows = 0; dRows = nullptr;
     wantedS = 0;
   }
   template <class T> T* al(int64_t n) { T* p = static_cast<T*>(be->dalloc(sizeof(T) * std::max<int64_t>(n, 1))); owned.push_back(p); return p; }
@@ -517,7 +517,6 @@ struct Renderer {
       cs.gne = al<uint32_t>(cs.gvb);
       be->zero(cs.gseg, sizeof(uint32_t) * grows * cs.gsn);
       dRows = al<int32_t>(nrows);
-      dTailCount = al<uint32_t>(4);
     }
     cs.pairCap = capPairs;
     cs.S = capS; cs.NR = capNR; cs.QCAP = capNR + int64_t(nL) * capS; cs.nMO = nMO; cs.nL = nL; cs.candCap = capCand; cs.preCap = 4 * capCand; cs.rows = dRows;
@@ -608,6 +607,7 @@ struct Renderer {
     const int nL = sd.h.nlights, nMO = sd.h.nmesh_objs;
     const bool jitter = o.aa_kind >= NRT_AA_JITTERED;
     pathMode = int(envInt("NRT_PATH", 1));
+    tailBelow = envInt("NRT_TAIL_BELOW", 32768);
     // An INTENDED-mode frame can reflect at most max_ray_depth times.
     int maxBounces = sd.anyReflective ? fp.bounce_cap : 0;
     if (sd.anyReflective && o.depth_mode == NRT_DEPTH_INTENDED) maxBounces = std::min(maxBounces, std::max(0, o.max_ray_depth));
@@ -657,50 +657,64 @@ struct Renderer {
         be->zero(cs.acount, sizeof(uint32_t) * (waves + 2));
         int wave = 0;
         ActiveSet act{nullptr, nullptr, nS};   // bounce 0: every sample of the chunk
-        cs.tailList = nullptr; cs.tailCount = nullptr;
-        if (pathMode != 0) {
-          // ---- fused path (nrt_pipeline.h: PathSampleT) ----
-          cs.tailList = cs.alist + cs.S; cs.tailCount = dTailCount;
-          be->zero(dTailCount, sizeof(uint32_t) * 4);
+        int bounceStart = 0;   // first bounce of the wavefront loop below
+        const bool fusedPath = pathMode != 0;
+        if (pathMode == 2) {
+          // ---- PathMega: every sample start to end in one launch ----
+          if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
+          if (sd.h.ncl1 > 0) be->pathWarp(nullptr, nS, PathMegaClustered{sd.d, fp, cs, force_exact, jitter ? 1 : 0, act, 0}, cs.stats);
+          else be->pathWarp(nullptr, nS, PathMega{sd.d, fp, cs, force_exact, jitter ? 1 : 0, act, 0}, cs.stats);
+          bounceStart = -1;    // nothing left
+        } else if (fusedPath) {
+          // ---- fused path (nrt_pipeline.h: FusedPrimaryT, PathWarpT) ----
           if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
           const int gfs = jitter ? 1 : 0;
-          if (pathMode == 2) {
-            if (sd.h.ncl1 > 0) be->forEachStats(nullptr, nS, PathMegaClustered{sd.d, fp, cs, force_exact, gfs}, cs.stats);
-            else be->forEachStats(nullptr, nS, PathMega{sd.d, fp, cs, force_exact, gfs}, cs.stats);
-          } else {
-            if (sd.h.ncl1 > 0) be->forEachStats(nullptr, nS, FusedPrimaryClustered{sd.d, fp, cs, force_exact, gfs}, cs.stats);
-            else be->forEachStats(nullptr, nS, FusedPrimary{sd.d, fp, cs, force_exact, gfs}, cs.stats);
-            if (nMO > 0) {
-              // the samples with a mesh ray at bounce 0, in sample order (= the wavefront's bounce-0 active list)
-              uint32_t* hardList = cs.alist;
-              uint32_t* hardCount = cs.acount;
-              be->compactActive(cs, act, hardList, hardCount);
-              uint32_t n0 = 0;
-              be->download(&n0, hardCount, sizeof(n0));
-              if (n0 > 0) {
-                const ActiveSet hard{hardList, hardCount, int64_t(n0)};
-                meshWave(sd, fp, WAVE_PATH, hard, wave, 0, force_exact, false); ++wave;
-                if (sd.h.ncl1 > 0) be->forEachStats(nullptr, hard.n, ShadeClustered{sd.d, fp, cs, hard, 0}, cs.stats);
-                else be->forEachStats(nullptr, hard.n, Shade{sd.d, fp, cs, hard, 0}, cs.stats);
-                if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, hard, wave, 0, force_exact, false);
-                ++wave;
-                shadowAndResolve(sd, fp, hard, 0);
-              }
-            }
-            if (maxBounces > 0) {
-              if (sd.h.ncl1 > 0) be->forEachStatsCounted(cs.tailCount, cs.S, PathTailClustered{sd.d, fp, cs, force_exact, 0}, cs.stats);
-              else be->forEachStatsCounted(cs.tailCount, cs.S, PathTail{sd.d, fp, cs, force_exact, 0}, cs.stats);
-            }
+          if (sd.h.ncl1 > 0) be->forEachStats(nullptr, nS, FusedPrimaryClustered{sd.d, fp, cs, force_exact, gfs}, cs.stats);
+          else be->forEachStats(nullptr, nS, FusedPrimary{sd.d, fp, cs, force_exact, gfs}, cs.stats);
+          if (nMO > 0) {
+            // the samples with a mesh ray at bounce 0, in sample order (= the wavefront's bounce-0 active list)
+            uint32_t* hardList = cs.alist;            // (bounce 1's list goes to the other half)
+            uint32_t* hardCount = cs.acount;
+            be->compactActive(cs, act, hardList, hardCount, kFlagWavefront);
+            uint32_t n0 = 0;
+            be->download(&n0, hardCount, sizeof(n0));
+            if (n0 > 0) {
+              const ActiveSet hard{hardList, hardCount, int64_t(n0)};
+              meshWave(sd, fp, WAVE_PATH, hard, wave, 0, force_exact, false); ++wave;
+              if (sd.h.ncl1 > 0) be->forEachStats(nullptr, hard.n, ShadeClustered{sd.d, fp, cs, hard, 0}, cs.stats);
+              else be->forEachStats(nullptr, hard.n, Shade{sd.d, fp, cs, hard, 0}, cs.stats);
+              if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, hard, wave, 0, force_exact, false);
+              ++wave;
+              shadowAndResolve(sd, fp, hard, 0);
+            } else wave += 2;
+          } else wave += 2;
+          // bounce 1's active set: every sample with a nonzero flag (FusedPrimary: continues; Resolve: continues)
+          bounceStart = -1;
+          if (maxBounces > 0) {
+            uint32_t* nextList = cs.alist + cs.S;
+            uint32_t* nextCount = cs.acount + 1;
+            be->compactActive(cs, act, nextList, nextCount, 0);
+            uint32_t cont = 0;
+            be->download(&cont, nextCount, sizeof(cont));
+            if (cont > 0) { act = ActiveSet{nextList, nextCount, int64_t(cont)}; bounceStart = 1; }
           }
-        } else {
+        }
+        if (bounceStart >= 0) {
         // primary rays: generated and gated in one kernel (the jittered kinds generate per pixel: separate gate)
-        const bool fuseGen = !jitter && nMO > 0;
-        if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
+        const bool fuseGen = !fusedPath && !jitter && nMO > 0;
+        if (fusedPath) {}
+        else if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
         else if (fuseGen) be->produceGate(nS, 1, GenGate{GenSimple{sd.d, fp, cs}, makeGate(sd, fp, WAVE_PATH, act, 0, force_exact), nMO}, cs, nMO, waveCounters(0), nullptr);
         else be->forEach(nS, GenSimple{sd.d, fp, cs});
-        for (int bounce = 0;; ++bounce) {
+        for (int bounce = bounceStart;; ++bounce) {
           uint32_t* nextList = cs.alist + int64_t((bounce + 1) & 1) * cs.S;
           uint32_t* nextCount = cs.acount + bounce + 1;
+          // a small wave: one PathTail launch takes its samples to the end of their paths
+          if (bounce > 0 && fusedPath && act.n < tailBelow) {
+            if (sd.h.ncl1 > 0) be->pathWarp(act.count, act.n, PathTailClustered{sd.d, fp, cs, force_exact, 0, act, bounce}, cs.stats);
+            else be->pathWarp(act.count, act.n, PathTail{sd.d, fp, cs, force_exact, 0, act, bounce}, cs.stats);
+            break;
+          }
           // (act.n is exact on the host for every bounce: launches are sized to it)
           meshWave(sd, fp, WAVE_PATH, act, wave, bounce, force_exact, bounce == 0 && fuseGen); ++wave;
           if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadeClustered{sd.d, fp, cs, act, bounce}, cs.stats);
@@ -709,7 +723,7 @@ struct Renderer {
           ++wave;
           shadowAndResolve(sd, fp, act, bounce);
           if (bounce >= maxBounces) break;
-          be->compactActive(cs, act, nextList, nextCount);
+          be->compactActive(cs, act, nextList, nextCount, 0);
           uint32_t cont = 0;
           be->download(&cont, nextCount, sizeof(cont));
           if (cont == 0) break;  // no sample continued

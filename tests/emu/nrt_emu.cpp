@@ -39,8 +39,9 @@ struct LoopBackend {
     for (int64_t i = 0; i < n; ++i) { const StatDelta d = f(i); for (int k = 0; k < ST_COUNT; ++k) st[k] += d.v[k]; }
     ++launches;
   }
-  template <class F> void forEachStatsCounted(const uint32_t* count, int64_t cap, const F& f, unsigned long long* st) {
-    forEachStats(nullptr, std::min<int64_t>(*count, cap), f, st);
+  // PathTail / PathMega: elements [0, *count) (or [0, n) when count is null), one "lane" at a time (ScalarCoop)
+  template <class F> void pathWarp(const uint32_t* count, int64_t n, const F& f, unsigned long long* st) {
+    forEachStats(nullptr, count ? std::min<int64_t>(*count, n) : n, f, st);
   }
   template <class F> void forEachCounted(const uint32_t* c, int64_t cap, const F& f) {
     const int64_t n = std::min<int64_t>(*c, cap);
@@ -171,11 +172,11 @@ struct LoopBackend {
     ++launches;
   }
   // next bounce's active list: the samples of the current set with active == 1, in sample order
-  void compactActive(const ChunkState& cs, const ActiveSet& act, uint32_t* list, uint32_t* count) {
+  void compactActive(const ChunkState& cs, const ActiveSet& act, uint32_t* list, uint32_t* count, uint8_t match) {
     uint32_t n = 0;
     for (int64_t i = 0; i < act.n; ++i) {
       const int64_t s = act.list ? int64_t(act.list[i]) : i;
-      if (cs.active[s]) list[n++] = uint32_t(s);
+      if (match ? cs.active[s] == match : cs.active[s] != 0) list[n++] = uint32_t(s);
     }
     *count = n;
     ++launches;
