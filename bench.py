@@ -422,6 +422,18 @@ def main():
                                 "shared by the ranks (POSIX shared memory, page-locked): every rank copies its own scanlines" if shared is not None
                                 else "rank 0 copies the frame gathered on its device")}
     checksum = float(np.asarray(host_fb, dtype=np.float64).sum()) if rank == 0 else 0.0
+    # the timed frame is the verified frame: sha256 of the float32 framebuffer the e2e steps delivered against the
+    # CPU oracle's frame of the same workload (tests/golden/, generated by make_goldens.py)
+    golden = {"config4": "config4_bunny_spheres_3840x2160_g4", "config3": "config3_bunny_spheres_1920x1080_g4",
+              "config2": "config2_bunny_1920x1080", "config1": "config1_spheres_640x480"}.get(args.workload)
+    parity = None
+    if rank == 0 and golden and os.path.exists(os.path.join(ROOT, "tests", "golden", golden + ".npz")):
+        import hashlib
+        want = str(np.load(os.path.join(ROOT, "tests", "golden", golden + ".npz"))["fb_sha256"])
+        got = hashlib.sha256(np.ascontiguousarray(host_fb).tobytes()).hexdigest()
+        parity = {"golden": f"tests/golden/{golden}.npz", "fb_sha256": got, "matches_oracle": got == want}
+        if got != want:
+            raise SystemExit(f"bench: the rendered frame differs from the oracle's ({got} != {want})")
 
     # ---- per-kernel-family shares: one untimed frame with every launch bracketed by CUDA events ----
     api.setKernelTiming(True)
@@ -498,7 +510,7 @@ def main():
             "frames_per_s": args.steps / (t_ms * 1e-3), "rays_per_frame": total_rays / args.steps,
             "device_ms_per_step": ms_dev.value / args.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(klaunches),
-            "roofline": roofline, "intersection_kernel": intersection, "kernels": kernels, "kernel_timing_frame_ms": kframe_ms, "fb_checksum": checksum,
+            "roofline": roofline, "intersection_kernel": intersection, "kernels": kernels, "kernel_timing_frame_ms": kframe_ms, "fb_checksum": checksum, "parity": parity,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(ds.desc, opts, total_rays / args.steps)

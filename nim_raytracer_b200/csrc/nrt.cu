@@ -21,6 +21,9 @@
 #include <stdexcept>
 #include <mutex>
 #include <thread>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 
 #include "nrt_renderer.h"
 
@@ -210,13 +213,17 @@ struct WarpCoop {
 };
 // lane <-> element i of [0, n) (n = min(*count, nHost) when the count lives on the device); whole warps stay in
 // f.run() until their last lane's path has ended; CTA-uniform trip count (blockStatsAdd synchronises)
+// `lpw` lanes of every warp own an element, the others only help with the walks: a short list is spread over
+// many warps (a warp takes its rays' walks one after the other, so the length of a launch is the longest warp's).
 template <class F>
-__global__ void __launch_bounds__(kBlock, NRT_OCC_TAIL) k_path_warp(F f, const uint32_t* count, int64_t nHost, unsigned long long* stats) {
+__global__ void __launch_bounds__(kBlock, NRT_OCC_TAIL) k_path_warp(F f, const uint32_t* count, int64_t nHost, int lpw, unsigned long long* stats) {
   int64_t n = nHost;
   if (count) { n = *count; if (n > nHost) n = nHost; }
-  for (int64_t base = int64_t(blockIdx.x) * kBlock; base < n; base += int64_t(gridDim.x) * kBlock) {
-    const int64_t i = base + threadIdx.x;
-    const StatDelta d = f.run(i, i < n, WarpCoop{});
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t perCta = int64_t(kBlock / 32) * lpw;
+  for (int64_t base = int64_t(blockIdx.x) * perCta; base < n; base += int64_t(gridDim.x) * perCta) {
+    const int64_t i = base + int64_t(warp) * lpw + lane;
+    const StatDelta d = f.run(i, lane < lpw && i < n, WarpCoop{});
     blockStatsAdd(d, stats);
     __syncthreads();
   }
@@ -994,8 +1001,13 @@ struct CudaBackend {
     use();
     if (n <= 0) return;
     Timed tm(this, CatOf<F>::v);
-    const int64_t blocks = count ? std::min<int64_t>(int64_t(sms) * 8, (n + kBlock - 1) / kBlock) : (n + kBlock - 1) / kBlock;
-    k_path_warp<F><<<unsigned(blocks), kBlock, 0, stream>>>(f, count, n, stats);
+    // elements per warp: all 32 lanes when the list fills the GPU's resident warps (8 per SM at this kernel's
+    // register count), fewer for short lists
+    int lpw = 32;
+    while (lpw > 1 && n * 32 / lpw < int64_t(sms) * 8 * 32 / 2) lpw >>= 1;   // i.e. while warps(n, lpw) < half the resident warps
+    const int64_t perCta = int64_t(kBlock / 32) * lpw;
+    const int64_t blocks = (n + perCta - 1) / perCta;
+    k_path_warp<F><<<unsigned(blocks), kBlock, 0, stream>>>(f, count, n, lpw, stats);
     NRT_CUDA(cudaGetLastError()); ++launches;
   }
   template <class F> void forEachCounted(const uint32_t* count, int64_t cap, const F& f) {
@@ -1206,19 +1218,71 @@ struct CudaBackend {
 };
 
 // ------------------------------------------------------------ global state ----
+// Lanes: a GPU's share of a frame is rendered as up to kMaxLanes INDEPENDENT pipelines (pixels are independent:
+// lane k of K takes every K-th of the worker's scanlines), each with its own stream, buffers and host thread.
+// A pipeline is a chain of dependent launches with a few host round trips; late bounces and small frames (a
+// 1/8 frame on each of eight GPUs) leave the GPU mostly idle inside one chain — several chains in flight fill it.
+static constexpr int kMaxLanes = 8;
 struct DeviceCtx {
-  CudaBackend be;
+  CudaBackend be;                              // lane 0 (also scene builds, output stage, timers)
+  std::vector<CudaBackend*> extra;             // lanes 1 ..
+  CudaBackend& lane(int k) { return k == 0 ? be : *extra[size_t(k - 1)]; }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // frame bracket (nrt_profile.total_ms)
   cudaEvent_t tb0 = nullptr, tb1 = nullptr;   // user bracket (nrt_timer_begin/end)
+  std::vector<cudaEvent_t> laneDone;           // per extra lane: its part of the frame is complete
 };
 
 static std::mutex g_mu;
 static std::vector<DeviceCtx*> g_devs;
 static int g_part_index = 0, g_part_count = 1;
 
+// persistent host threads for the lanes / devices beyond the calling thread's
+class HostPool {
+ public:
+  void run(std::vector<std::function<void()>>& jobs) {   // jobs[0] runs on the caller
+    if (jobs.empty()) return;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      while (threads_.size() + 1 < jobs.size()) threads_.emplace_back([this] { loop(); });
+      pending_ = int(jobs.size()) - 1;
+      for (size_t i = 1; i < jobs.size(); ++i) q_.push_back(&jobs[i]);
+    }
+    cv_.notify_all();
+    jobs[0]();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+  ~HostPool() {
+    { std::unique_lock<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+ private:
+  void loop() {
+    for (;;) {
+      std::function<void()>* job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+        if (stop_ && q_.empty()) return;
+        job = q_.front(); q_.pop_front();
+      }
+      (*job)();
+      { std::unique_lock<std::mutex> lk(mu_); if (--pending_ == 0) done_.notify_all(); }
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  std::deque<std::function<void()>*> q_;
+  std::vector<std::thread> threads_;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+static HostPool g_pool;
+
 struct PerDevice {
   SceneData<CudaBackend> sd;
-  Renderer<CudaBackend> rn;
+  Renderer<CudaBackend> rn[kMaxLanes];
   float* fbStage = nullptr; int64_t fbStageN = 0;
   int32_t* aovObj = nullptr; int32_t* aovTri = nullptr; double* aovT = nullptr; int64_t aovN = 0;
 };
@@ -1279,11 +1343,17 @@ static int initLocked(int ngpu, const int* ids) {
   return NRT_OK;
 }
 
-// rows [y0,y1) with (y-y0) % step == 0 owned by `worker` of `nworkers` (scanline interleave)
-static std::vector<int32_t> rowsFor(int height, int y0, int y1, int step, int worker, int nworkers) {
+// The rendered rows of [y0, y1) — (y - y0) % step == 0, numbered i = (y - y0) / step — owned by lane `lane` of
+// partition `part`: i % nparts == part (scanline interleave over the GPUs / ranks: the reference's work items,
+// raytracer.nim:67-70; counted among the RENDERED rows, so a progressive pass with step >= nparts still spreads
+// over every GPU), and among a partition's rows every nlanes-th goes to the same lane.
+static std::vector<int32_t> rowsFor(int height, int y0, int y1, int step, int part, int nparts, int lane, int nlanes) {
   std::vector<int32_t> r;
-  for (int y = std::max(0, y0); y < std::min(y1, height); ++y)
-    if ((y - y0) % step == 0 && (y % nworkers) == worker) r.push_back(y);
+  for (int y = std::max(0, y0); y < std::min(y1, height); ++y) {
+    if ((y - y0) % step != 0) continue;
+    const int i = (y - y0) / step;
+    if (i % nparts == part && (i / nparts) % nlanes == lane) r.push_back(y);
+  }
   return r;
 }
 
@@ -1299,49 +1369,84 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called");
   const int nd = int(sc->dev.size());
-  const int nworkers = nd * g_part_count;
   const int64_t npx = int64_t(o->width) * o->height;
-  std::vector<int> rc(nd, NRT_OK);
-  std::vector<std::string> errs(nd);
-  std::vector<std::vector<unsigned long long>> st(nd, std::vector<unsigned long long>(ST_COUNT, 0));
+  // lanes per device: NRT_LANES, else by the device's share of the frame (a lane should keep >= ~1 M samples;
+  // kernel timing wants one chain so that the per-launch events do not overlap)
+  int nlanes = 4;
+  if (const char* e = std::getenv("NRT_LANES")) nlanes = std::atoi(e);
+  {
+    const int spp = o->aa_kind == NRT_AA_NONE ? 1 : o->grid_size * o->grid_size;
+    const int64_t rowsAll = (std::min(y1, o->height) - std::max(0, y0) + step - 1) / std::max(step, 1);
+    const int64_t samples = std::max<int64_t>(0, rowsAll) * ((o->width + step - 1) / step) * spp / std::max(1, nd * g_part_count);
+    if (!std::getenv("NRT_LANES")) nlanes = int(std::min<int64_t>(4, std::max<int64_t>(1, samples / (int64_t(1) << 20))));
+    if (g_devs[0]->be.timing) nlanes = 1;
+  }
+  nlanes = std::max(1, std::min(nlanes, kMaxLanes));
+  const int nunits = nd * nlanes;
+  std::vector<int> rc(nunits, NRT_OK);
+  std::vector<std::string> errs(nunits);
+  std::vector<std::vector<unsigned long long>> st(nunits, std::vector<unsigned long long>(ST_COUNT, 0));
   const bool wantAov = aov && (aov->obj_id || aov->tri_id || aov->t_hit);
 
-  auto work = [&](int di) {
-    PerDevice& pd = sc->dev[di];
-    DeviceCtx* dc = g_devs[di];
-    CudaBackend& be = dc->be;
-    try {
+  // per device, before the lanes start: staging buffers, the extra lanes' backends, the frame's start event
+  try {
+    for (int di = 0; di < nd; ++di) {
+      PerDevice& pd = sc->dev[di];
+      DeviceCtx* dc = g_devs[di];
+      CudaBackend& be = dc->be;
       be.use();
-      const int worker = g_part_index * nd + di;
-      const std::vector<int32_t> rows = rowsFor(o->height, y0, y1, step, worker, nworkers);
-      float* target = fb;
-      int32_t *aObj = nullptr, *aTri = nullptr; double* aT = nullptr;
+      while (int(dc->extra.size()) + 1 < nlanes) {
+        auto* b = new CudaBackend();
+        b->device = be.device; b->sms = be.sms;
+        NRT_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+        dc->extra.push_back(b);
+        cudaEvent_t e; NRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        dc->laneDone.push_back(e);
+      }
       if (!deviceOut) {
         if (pd.fbStageN < npx * 3) {
           be.dfree(pd.fbStage);
           pd.fbStage = static_cast<float*>(be.dalloc(sizeof(float) * npx * 3));
           pd.fbStageN = npx * 3;
         }
-        target = pd.fbStage;
-        if (wantAov) {
-          if (pd.aovN < npx) {
-            be.dfree(pd.aovObj); be.dfree(pd.aovTri); be.dfree(pd.aovT);
-            pd.aovObj = static_cast<int32_t*>(be.dalloc(sizeof(int32_t) * npx));
-            pd.aovTri = static_cast<int32_t*>(be.dalloc(sizeof(int32_t) * npx));
-            pd.aovT = static_cast<double*>(be.dalloc(sizeof(double) * npx));
-            pd.aovN = npx;
-          }
-          aObj = aov->obj_id ? pd.aovObj : nullptr; aTri = aov->tri_id ? pd.aovTri : nullptr; aT = aov->t_hit ? pd.aovT : nullptr;
+        if (wantAov && pd.aovN < npx) {
+          be.dfree(pd.aovObj); be.dfree(pd.aovTri); be.dfree(pd.aovT);
+          pd.aovObj = static_cast<int32_t*>(be.dalloc(sizeof(int32_t) * npx));
+          pd.aovTri = static_cast<int32_t*>(be.dalloc(sizeof(int32_t) * npx));
+          pd.aovT = static_cast<double*>(be.dalloc(sizeof(double) * npx));
+          pd.aovN = npx;
         }
+      }
+      NRT_CUDA(cudaEventRecord(dc->ev0, be.stream));
+      for (int k = 1; k < nlanes; ++k) NRT_CUDA(cudaStreamWaitEvent(dc->lane(k).stream, dc->ev0, 0));
+    }
+  } catch (const std::exception& ex) {
+    return fail(NRT_ERR_CUDA, ex.what());
+  }
+
+  auto work = [&](int unit) {
+    const int di = unit / nlanes, ln = unit % nlanes;
+    PerDevice& pd = sc->dev[di];
+    DeviceCtx* dc = g_devs[di];
+    CudaBackend& be = dc->lane(ln);
+    pd.rn[ln].be = &be;
+    try {
+      be.use();
+      const std::vector<int32_t> rows = rowsFor(o->height, y0, y1, step, g_part_index * nd + di, nd * g_part_count, ln, nlanes);
+      float* target = fb;
+      int32_t *aObj = nullptr, *aTri = nullptr; double* aT = nullptr;
+      if (!deviceOut) {
+        target = pd.fbStage;
+        if (wantAov) { aObj = aov->obj_id ? pd.aovObj : nullptr; aTri = aov->tri_id ? pd.aovTri : nullptr; aT = aov->t_hit ? pd.aovT : nullptr; }
       } else if (wantAov) {
         aObj = aov->obj_id; aTri = aov->tri_id; aT = aov->t_hit;
       }
       be.launches = 0;
+      be.timing = dc->be.timing;
       if (const char* e = std::getenv("NRT_PREFILTER_CULL")) be.cull = std::atoi(e) != 0; else be.cull = true;
       if (const char* e = std::getenv("NRT_PREFILTER_SPLIT")) be.splitBelow = std::max(0, std::atoi(e));
       if (const char* e = std::getenv("NRT_PREFETCH_AHEAD")) be.prefetchAhead = std::max<int64_t>(0, std::atoll(e));
       else be.prefetchAhead = int64_t(be.sms) * 512;   // measured on B200, config 4: off 25.23 ms; 256..2048 per SM 24.75-24.81; 4096 per SM 25.28
-      NRT_CUDA(cudaEventRecord(dc->ev0, be.stream));
       // Host <-> staging copies of exactly the rows this worker renders (and their step x step
       // fill rows); equally spaced rows (scanline interleave) go out as one 2D copy.
       auto copyRows = [&](bool toHost) {
@@ -1372,43 +1477,54 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
       // Progressive passes leave some pixels of the touched rows untouched (renderer.nim:175-178,
       // and AOVs exist only at rendered pixels): round-trip the caller's current content.
       if (!deviceOut && (step > 1 || step < max_step)) copyRows(false);
-      rc[di] = pd.rn.render(pd.sd, *o, rows, step, max_step, target, aObj, aTri, aT, st[di].data(), errs[di]);
-      if (rc[di] == NRT_OK && !deviceOut) copyRows(true);
-      NRT_CUDA(cudaEventRecord(dc->ev1, be.stream));
+      rc[unit] = pd.rn[ln].render(pd.sd, *o, rows, step, max_step, target, aObj, aTri, aT, st[unit].data(), errs[unit]);
+      if (rc[unit] == NRT_OK && !deviceOut) copyRows(true);
+      if (ln > 0) NRT_CUDA(cudaEventRecord(dc->laneDone[size_t(ln - 1)], be.stream));
       NRT_CUDA(cudaStreamSynchronize(be.stream));
     } catch (const std::exception& ex) {
-      rc[di] = NRT_ERR_CUDA;
-      errs[di] = ex.what();
+      rc[unit] = NRT_ERR_CUDA;
+      errs[unit] = ex.what();
     }
   };
 
-  if (nd == 1) work(0);
+  if (nunits == 1) work(0);
   else {
-    std::vector<std::thread> th;
-    for (int d = 1; d < nd; ++d) th.emplace_back(work, d);
-    work(0);
-    for (auto& t : th) t.join();
+    std::vector<std::function<void()>> jobs;
+    for (int u = 0; u < nunits; ++u) jobs.emplace_back([&work, u] { work(u); });
+    g_pool.run(jobs);
   }
-  for (int d = 0; d < nd; ++d)
-    if (rc[d] != NRT_OK) return fail(rc[d], errs[d]);
+  // the frame ends when every lane of the device has ended: ev1 on lane 0's stream behind the other lanes' events
+  for (int di = 0; di < nd; ++di) {
+    DeviceCtx* dc = g_devs[di];
+    cudaSetDevice(dc->be.device);
+    for (int k = 1; k < nlanes; ++k) cudaStreamWaitEvent(dc->be.stream, dc->laneDone[size_t(k - 1)], 0);
+    cudaEventRecord(dc->ev1, dc->be.stream);
+    cudaStreamSynchronize(dc->be.stream);
+  }
+  for (int u = 0; u < nunits; ++u)
+    if (rc[u] != NRT_OK) return fail(rc[u], errs[u]);
 
   nrt_profile& p = sc->prof;
   p = nrt_profile{};
   unsigned long long tot[ST_COUNT] = {0};
+  for (int u = 0; u < nunits; ++u)
+    for (int k = 0; k < ST_COUNT; ++k) tot[k] += st[u][k];
   for (int d = 0; d < nd; ++d) {
-    for (int k = 0; k < ST_COUNT; ++k) tot[k] += st[d][k];
     DeviceCtx* dc = g_devs[d];
     float ms = 0;
     cudaSetDevice(dc->be.device);
     cudaEventElapsedTime(&ms, dc->ev0, dc->ev1);
     p.total_ms = std::max(p.total_ms, double(ms));
+   double fmsDev = 0;
+   for (int ln = 0; ln < nlanes; ++ln) {
+    CudaBackend& lbe = dc->lane(ln);
     int64_t nl = 0;
     double byMode[4] = {0, 0, 0, 0};
     std::vector<float> each;
     const bool traceP = std::getenv("NRT_TRACE_PREFILTER") != nullptr;
-    const double fms = dc->be.filterMs(&nl, byMode, traceP ? &each : nullptr);
+    const double fms = lbe.filterMs(&nl, byMode, traceP ? &each : nullptr);
     if (traceP) {
-      const auto& lg = sc->dev[d].rn.preLog;
+      const auto& lg = sc->dev[d].rn[ln].preLog;
       for (size_t i = 0; i < lg.size() && i < each.size(); ++i)
         fprintf(stderr, "[prefilter] dev %d wave %2d mo %d bundle %d mode %d rays %9lld runs %7lld chunks %4lld work %9lld (%.2f per run) pre %9lld  %8.1f us\n",
                 d, lg[i].wave, lg[i].mo, lg[i].b, lg[i].mode, (long long)lg[i].rays,
@@ -1416,26 +1532,28 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
                 (long long)lg[i].work, double(lg[i].work) / std::max<double>(1.0, double((lg[i].rays + prefilterRunRays(lg[i].mode) - 1) / prefilterRunRays(lg[i].mode))),
                 (long long)lg[i].pre, each[i] * 1e3);
     }
-    p.mesh_filter_ms = std::max(p.mesh_filter_ms, fms);
+    fmsDev += fms;   // (the lanes' prefilter launches of one device: summed CUDA-event time; they may overlap)
     p.mesh_filter_launches += nl;
-    const ProfileAcc& a = sc->dev[d].rn.prof;
+    const ProfileAcc& a = sc->dev[d].rn[ln].prof;
     p.mesh_tests += a.mesh_tests; p.mesh_tests_ref += a.mesh_tests_ref; p.mesh_rays += a.mesh_rays;
     p.candidates += a.candidates;
     p.pre_candidates += a.pre_candidates;
-    p.kernel_launches += dc->be.launches;
-    if (dc->be.timing && d == 0) {
+    p.kernel_launches += lbe.launches;
+    if (lbe.timing && d == 0 && ln == 0) {
       sc->ktimes = nrt_kernel_times{};
-      dc->be.collectTimes(sc->ktimes.ms, sc->ktimes.launches);
-    } else if (dc->be.timing) {
+      lbe.collectTimes(sc->ktimes.ms, sc->ktimes.launches);
+    } else if (lbe.timing) {
       nrt_kernel_times scratchT{};
-      dc->be.collectTimes(scratchT.ms, scratchT.launches);
+      lbe.collectTimes(scratchT.ms, scratchT.launches);
     }
     for (int m = 0; m < 3; ++m) {
       p.mesh_tests_by_mode[m] += a.tests_by_mode[m];
-      p.mesh_ms_by_mode[m] = std::max(p.mesh_ms_by_mode[m], byMode[m]);
+      p.mesh_ms_by_mode[m] += byMode[m];
       // executed float32 flops per prefilter test (FFMA = 2): nrt_filter.h prefilterFlops()
       p.fp32_flops += double(a.tests_by_mode[m]) * prefilterFlops(m);
     }
+   }
+   p.mesh_filter_ms = std::max(p.mesh_filter_ms, fmsDev);
   }
   if (stats) {
     stats->num_primary_rays = int64_t(tot[ST_PRIMARY]);
@@ -1471,6 +1589,8 @@ void nrt_shutdown(void) {
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->tb0) cudaEventDestroy(d->tb0);
     if (d->tb1) cudaEventDestroy(d->tb1);
+    for (auto e : d->laneDone) cudaEventDestroy(e);
+    for (auto* b : d->extra) { b->destroy(); delete b; }
     d->be.destroy();
     delete d;
   }
@@ -1495,7 +1615,7 @@ static int sceneBuild(nrt_scene* s, const nrt_scene_desc* desc, bool reuse) {
     std::string err;
     try {
       PerDevice& pd = s->dev[d];
-      pd.rn.be = &g_devs[d]->be;
+      for (int k = 0; k < kMaxLanes; ++k) if (!pd.rn[k].be) pd.rn[k].be = &g_devs[d]->be;
       const int rc = pd.sd.build(&g_devs[d]->be, desc, reuse, err);
       if (rc != NRT_OK) return fail(rc, err);
       g_devs[d]->be.sync();
@@ -1536,7 +1656,7 @@ void nrt_scene_destroy(nrt_scene* scene) {
     PerDevice& pd = scene->dev[d];
     CudaBackend& be = g_devs[d]->be;
     pd.sd.destroy();
-    pd.rn.freeAll();
+    for (int k = 0; k < kMaxLanes; ++k) if (pd.rn[k].be) pd.rn[k].freeAll();
     be.dfree(pd.fbStage); be.dfree(pd.aovObj); be.dfree(pd.aovTri); be.dfree(pd.aovT);
   }
   delete scene;

@@ -622,7 +622,12 @@ NRT_HD void evalObject(const DScene& sc, const MP& mp, int i, V4 o, V4 d, bool f
     mp.eval(c.mesh_obj, o, d, t, tri);
   } else {
     V4 oo, dd;
-    if (c.xlate_only && fastRay && (o.x != 0.0 || c.t[0] != 0.0) && (o.y != 0.0 || c.t[1] != 0.0) && (o.z != 0.0 || c.t[2] != 0.0)) {
+    // A Plane reads only the y components (geom.nim:240-248 with n = (0,1,0,0)): with dir.y != 0 and a nonzero
+    // height, denom = ((0*dx + 1*dy) + 0*dz) + 0*dw = dy and dot(orig, n) = oy exactly, whatever the signs of the
+    // zero products — so zero x / z components (a camera at x = 0 over a ground plane at the origin) do not need
+    // toObject()'s literal evaluation.
+    const bool planeY = c.kind == GEOM_PLANE && (o.y + c.t[1]) != 0.0;
+    if (c.xlate_only && fastRay && (planeY || ((o.x != 0.0 || c.t[0] != 0.0) && (o.y != 0.0 || c.t[1] != 0.0) && (o.z != 0.0 || c.t[2] != 0.0)))) {
       oo = v4(o.x + c.t[0], o.y + c.t[1], o.z + c.t[2], 1.0);
       dd = v4(d.x, d.y, d.z, 0.0);
     } else {
@@ -707,16 +712,20 @@ NRT_HD TraceOut traceObjects(const DScene& sc, const MP& mp, V4 o, V4 d, double 
     const int nb = (sc.nobjects - base < 32) ? sc.nobjects - base : 32;
     uint32_t need = (nb == 32) ? 0xFFFFFFFFu : ((1u << nb) - 1u);
     {
+      // branch-free: EVERY record goes through the sphere formula — a record that is not a float32 sphere has
+      // r2m = +Inf, for which the test is never true, and is looked at again (by tag) below
       uint32_t miss = 0;
 #pragma unroll 4
-      for (int j = 0; j < nb; ++j)   // the same record for every lane: the branches inside are uniform
-        miss |= uint32_t(firstLookMiss(mp, loadCObjF(sc.cobjf + base + j), rf, f32ok)) << j;
-      need &= ~miss;
+      for (int j = 0; j < nb; ++j)   // the same record for every lane
+        miss |= uint32_t(certainMissF(loadCObjF(sc.cobjf + base + j), rf)) << j;
+      if (f32ok) need &= ~miss;
     }
     r.tests += nb;
     while (need) {
       const int i = base + (__builtin_ffs(int(need)) - 1);
       need &= need - 1;
+      const CObjF c = loadCObjF(sc.cobjf + i);
+      if (!(c.r2m < 3.0e38f) && firstLookMiss(mp, c, rf, f32ok)) continue;   // plane below / above the ray, mesh box not entered
       evalObject(sc, mp, i, o, d, fastRay, r);
     }
   }

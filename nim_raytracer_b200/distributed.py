@@ -31,9 +31,11 @@ import numpy as np
 
 
 def rows_of(rank: int, world: int, height: int, y0: int = 0, y1: Optional[int] = None, step: int = 1) -> List[int]:
-    """Scanlines of [y0, y1) with (y - y0) mod step == 0 owned by `rank` (csrc/nrt.cu: rowsFor)."""
+    """Scanlines of [y0, y1) with (y - y0) mod step == 0 owned by `rank` (csrc/nrt.cu: rowsFor): the rendered
+    rows are numbered i = (y - y0) / step and dealt out round-robin, so a progressive pass with step >= world
+    still uses every rank.  For whole frames (y0 = 0, step = 1) this is y mod world == rank."""
     y1 = height if y1 is None else y1
-    return [y for y in range(max(0, y0), min(y1, height)) if (y - y0) % step == 0 and y % world == rank]
+    return [y for y in range(max(0, y0), min(y1, height)) if (y - y0) % step == 0 and ((y - y0) // step) % world == rank]
 
 
 def merge_rows(dst: np.ndarray, src: np.ndarray, rank: int, world: int) -> None:

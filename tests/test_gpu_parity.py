@@ -239,6 +239,15 @@ def test_golden_config3_full_size():
     _check_row_crcs("config3_bunny_spheres_1920x1080_g4", fb, aov)
 
 
+def test_golden_config4_full_size():
+    # BASELINE config 4 — the workload bench.py times — at its stated size: 3840x2160, 16 spp grid, depth 8.
+    # 132.7 M samples / 361.9 M rays: every pixel's ids, t, float32 RGB and the Stats equal the CPU oracle's frame
+    # (tests/golden/make_goldens.py config4: 38 minutes of brute force on 8 cores; renderer.nim:144-159)
+    o = api.Options(3840, 2160, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+    fb, st, aov = _check_golden("config4_bunny_spheres_3840x2160_g4", scenes.bunny_spheres(), o)
+    _check_row_crcs("config4_bunny_spheres_3840x2160_g4", fb, aov)
+
+
 @pytest.mark.parametrize("path", ["0", "2"])
 def test_path_modes_agree(oracle_mod, monkeypatch, path):
     # NRT_PATH: 0 = the wavefront for every bounce, 1 (default) = FusedPrimary + wavefront + PathTail, 2 = PathMega
