@@ -42,7 +42,7 @@
 #ifndef NRT_OCC_SHADE
 #define NRT_OCC_SHADE 0
 #endif
-// FusedPrimary (a whole bounce of a sample in registers) / PathTail, PathMega: the compiler's choice unless set
+// FusedBounce (a whole bounce of a sample in registers) / PathTail, PathMega: the compiler's choice unless set
 #ifndef NRT_OCC_FUSED
 #define NRT_OCC_FUSED 0
 #endif
@@ -118,7 +118,7 @@ template <> struct MinBlocks<ShadowTrace> { static constexpr int v = NRT_OCC_ST;
 template <bool CL> struct MinBlocks<ShadowTraceSampleT<CL>> { static constexpr int v = NRT_OCC_ST; };
 template <bool CL> struct MinBlocks<ShadowResolveT<CL>> { static constexpr int v = NRT_OCC_SR; };
 template <bool CL> struct MinBlocks<ShadeT<CL>> { static constexpr int v = NRT_OCC_SHADE; };
-template <bool CL> struct MinBlocks<FusedPrimaryT<CL>> { static constexpr int v = NRT_OCC_FUSED; };
+template <bool CL> struct MinBlocks<FusedBounceT<CL>> { static constexpr int v = NRT_OCC_FUSED; };
 template <class F>
 __global__ void __launch_bounds__(kBlock, MinBlocks<F>::v) k_for_each_stats(F f, int64_t n, unsigned long long* stats, int64_t ahead) {
   const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
@@ -848,6 +848,16 @@ __global__ void __launch_bounds__(kBlock) k_rgba8(const float* fb, unsigned char
   reinterpret_cast<uchar4*>(out)[p] = o;
 }
 
+// word-wise comparison of two device arrays (nrt_scene_update: is the uploaded description the resident one?)
+__global__ void __launch_bounds__(kBlock) k_diff(const uint2* a, const uint2* b, int64_t n, uint32_t* flag) {
+  bool d = false;
+  for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
+    const uint2 x = a[i], y = b[i];
+    d = d || x.x != y.x || x.y != y.y;
+  }
+  if (__syncthreads_or(d) && threadIdx.x == 0) atomicOr(flag, 1u);
+}
+
 // register-resident FFMA loop: the float32 roofline denominator
 __global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float a, float b) {
   float x[16];
@@ -872,7 +882,7 @@ enum KernelCat { KC_GEN = 0, KC_GATE_FLAGS, KC_GATE_SCAN, KC_GATE_WRITE, KC_PREF
 static const char* const kKernelCatNames[KC_COUNT] = {
   "gen+gate (GenGate / GenSimple / GenJittered)", "k_gate_flags", "k_gate_scan", "k_gate_write", "k_mesh_prefilter", "Refine",
   "ExactMesh", "Verify1+Verify2", "Shade", "ShadowTrace", "Resolve", "compactActive (cub select)", "Finalize", "other",
-  "ShadowResolve (ShadowTrace + Resolve)", "FusedPrimary (bounce 0 of a sample in registers)", "PathTail / PathMega (per-thread paths + mesh walk)"};
+  "ShadowResolve (ShadowTrace + Resolve)", "FusedBounce (a whole bounce of a sample in registers)", "PathTail / PathMega (per-thread paths + mesh walk)"};
 static_assert(KC_COUNT <= NRT_KERNEL_CATEGORIES, "nrt_kernel_times is too small");
 template <class F> struct CatOf { static constexpr int v = KC_OTHER; };
 template <> struct CatOf<GenSimple> { static constexpr int v = KC_GEN; };
@@ -884,7 +894,7 @@ template <> struct CatOf<ShadowTrace> { static constexpr int v = KC_SHADOW_TRACE
 template <bool CL> struct CatOf<ShadowTraceSampleT<CL>> { static constexpr int v = KC_SHADOW_TRACE; };
 template <bool CL> struct CatOf<ShadowResolveT<CL>> { static constexpr int v = KC_SHADOW_RESOLVE; };
 template <> struct CatOf<Resolve> { static constexpr int v = KC_RESOLVE; };
-template <bool CL> struct CatOf<FusedPrimaryT<CL>> { static constexpr int v = KC_FUSED_PRIMARY; };
+template <bool CL> struct CatOf<FusedBounceT<CL>> { static constexpr int v = KC_FUSED_PRIMARY; };
 template <bool CL, int KIND> struct CatOf<PathWarpT<CL, KIND>> { static constexpr int v = KC_PATH_TAIL; };
 template <> struct CatOf<Finalize> { static constexpr int v = KC_FINALIZE; };
 template <> struct CatOf<ExactMesh> { static constexpr int v = KC_EXACT; };
@@ -972,6 +982,20 @@ struct CudaBackend {
     NRT_CUDA(cudaStreamSynchronize(stream));
   }
   void sync() { use(); NRT_CUDA(cudaStreamSynchronize(stream)); }
+  uint32_t* dDiff = nullptr;
+  void diffBegin() {
+    use();
+    if (!dDiff) NRT_CUDA(cudaMalloc(&dDiff, 16));
+    NRT_CUDA(cudaMemsetAsync(dDiff, 0, 4, stream));
+  }
+  void diffAdd(const void* a, const void* b, size_t bytes) {   // (all scene arrays are float64 / int64: 8-byte words)
+    const int64_t n = int64_t(bytes / 8);
+    if (n <= 0) return;
+    k_diff<<<unsigned(std::min<int64_t>(int64_t(sms) * 8, (n + kBlock - 1) / kBlock)), kBlock, 0, stream>>>(
+        static_cast<const uint2*>(a), static_cast<const uint2*>(b), n, dDiff);
+    NRT_CUDA(cudaGetLastError()); ++launches;
+  }
+  bool diffEnd() { uint32_t f = 0; download(&f, dDiff, sizeof(f)); return f != 0; }
   // free device memory + what the caller already holds (its buffers are reused or replaced)
   int64_t memAvailable(int64_t held) {
     use();
@@ -1108,7 +1132,7 @@ struct CudaBackend {
     NRT_CUDA(cudaGetLastError()); launches += 4;
   }
   // next bounce's active list: the samples of the current set with active == 1, in sample order
-  // `match` != 0: only the samples whose flag equals it (FusedPrimary's kFlagWavefront), identity set only
+  // `match` != 0: only the samples whose flag equals it (FusedBounce's kFlagWavefront), identity set only
   struct FlagIs { uint8_t v; __host__ __device__ bool operator()(uint8_t f) const { return f == v; } };
   void compactActive(const ChunkState& cs, const ActiveSet& act, uint32_t* list, uint32_t* count, uint8_t match) {
     use();
@@ -1120,6 +1144,11 @@ struct CudaBackend {
       NRT_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids, flags, list, count, int(act.n), stream));
       void* tmp = scratch(0, tb);
       NRT_CUDA(cub::DeviceSelect::Flagged(tmp, tb, ids, flags, list, count, int(act.n), stream));
+    } else if (match) {
+      auto flags = thrust::make_transform_iterator(thrust::make_permutation_iterator(cs.active, act.list), FlagIs{match});
+      NRT_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, act.list, flags, list, count, int(act.n), stream));
+      void* tmp = scratch(0, tb);
+      NRT_CUDA(cub::DeviceSelect::Flagged(tmp, tb, act.list, flags, list, count, int(act.n), stream));
     } else if (!act.list) {
       thrust::counting_iterator<uint32_t> ids(0u);
       NRT_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids, cs.active, list, count, int(act.n), stream));
@@ -1212,6 +1241,8 @@ struct CudaBackend {
     for (int k = 0; k < 2; ++k) { if (scratchPtr[k]) cudaFree(scratchPtr[k]); scratchPtr[k] = nullptr; scratchBytes[k] = 0; }
     if (pinned) cudaFreeHost(pinned);
     pinned = nullptr;
+    if (dDiff) cudaFree(dDiff);
+    dDiff = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }

@@ -108,6 +108,7 @@ struct ChunkState {
   double* candT;     // candCap
   uint32_t* counters;  // maxWaves*nMO*cntStride(nL)
   uint32_t* alist;     // 2*S: compacted sample indices of the continuing paths (ping-pong per bounce)
+  uint32_t* hlist;     // S: the samples of the current bounce that go through the wavefront (fused path)
   uint32_t* acount;    // per bounce: entries of the list consumed by that bounce
   unsigned long long* stats;  // ST_COUNT
   // pixel list of this worker
@@ -570,7 +571,7 @@ NRT_HD MeshHit meshIntersectWalk(const DScene& sc, int mo, int mode, int l, V4 o
 
 // How trace() obtains TriangleMesh.intersect of the current ray for mesh object `mo`:
 //   WaveMesh  the wavefront: gate code of the ray's wave position + the results of the mesh wave
-//   NoMesh    the caller has shown that the ray enters no mesh box (FusedPrimary): NegInf
+//   NoMesh    the caller has shown that the ray enters no mesh box (FusedBounce): NegInf
 //   WalkMesh  the thread walks the mesh itself (PathTail)
 struct WaveMesh {
   const ChunkState& cs; int64_t wi, pos; uint8_t code0;   // code0 = gate code for mesh object 0, loaded by the caller with its other inputs
@@ -1039,7 +1040,7 @@ using ShadowResolveClustered = ShadowResolveT<true>;
 // never need it: in a frame of BASELINE config 4 about 88 % of the samples have NO ray (primary or shadow)
 // that enters a mesh box, so their whole bounce — castPrimaryRay, trace, shade's shadow rays, shadeDiffuse,
 // the reflection set-up (renderer.nim:31-127) — is done by ONE thread in registers:
-//   FusedPrimary  bounce 0 of every sample.  A sample one of whose rays passes a mesh's AABB gate is handed
+//   FusedBounce   one bounce of every active sample (bounce 0: from castPrimaryRay; later: from the stored ray).  A sample one of whose rays passes a mesh's AABB gate is handed
 //                 to the wavefront instead (its ray and active = 1 are stored, nothing else, and it adds
 //                 nothing to Stats: the wavefront redoes it from the ray); every other sample is finished
 //                 here: accumulator written once, and, if its path continues, the reflection ray is stored
@@ -1072,36 +1073,46 @@ NRT_HD V4 hitNormal(const DScene& sc, const DObject& ob, const TraceOut& tr, V4 
   return mulm(ob.o2w, v4(nn[0], nn[1], nn[2], nn[3]));
 }
 
-// cs.active after FusedPrimary: 0 = the sample is finished, kFlagWavefront = bounce 0 is the wavefront's,
+// cs.active after FusedBounce: 0 = the sample is finished, kFlagWavefront = bounce 0 is the wavefront's,
 // kFlagContinues = bounce 0 done here, the reflection ray is stored.  After the wavefront's bounce 0 every
 // nonzero flag is a sample whose path continues (Resolve writes 0 / 1 for its samples).
 static constexpr uint8_t kFlagWavefront = 1, kFlagContinues = 2;
 template <bool CL>
-struct FusedPrimaryT {
+struct FusedBounceT {
   const DScene* sc; FrameParams fp; ChunkState cs; int force_exact;
-  int genFromState;   // the primary rays are in cs.rayD / cs.active already (jittered kinds: GenJittered)
+  int genFromState;   // bounce 0: the primary rays are in cs.rayD / cs.active already (jittered kinds: GenJittered)
+  ActiveSet act;      // the samples of this bounce (bounce 0: every sample of the chunk)
+  int bounce;
   NRT_HD void prefetch(int64_t) const {}
-  NRT_HD StatDelta operator()(int64_t s) const {
+  NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
+    const int64_t s = sampleOf(act, idx);
     V4 o, d;
-    bool alive;
-    if (genFromState) {
-      o = primaryOrigin(*sc); d = ld4(cs.rayD, cs.S, s); alive = cs.active[s] != 0;
+    double w = 1.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (bounce == 0) {
+      bool alive;
+      if (genFromState) {
+        o = primaryOrigin(*sc); d = ld4(cs.rayD, cs.S, s); alive = cs.active[s] != 0;
+      } else {
+        GenOut g; GenSimple{sc, fp, cs}.compute(s, g);
+        o = g.o; d = g.d; alive = g.alive;
+      }
+      if (!alive) { cs.active[s] = 0; return st; }   // (skipped pixel of a progressive pass)
     } else {
-      GenOut g; GenSimple{sc, fp, cs}.compute(s, g);
-      o = g.o; d = g.d; alive = g.alive;
+      o = ld4(cs.rayO, cs.S, s); d = ld4(cs.rayD, cs.S, s);
+      w = cs.weight[s];
+      a0 = cs.accum[s]; a1 = cs.accum[cs.S + s]; a2 = cs.accum[2 * cs.S + s];
     }
-    if (!alive) { cs.active[s] = 0; return st; }   // (skipped pixel of a progressive pass)
     const int nMO = cs.nMO, nL = cs.nL;
     for (int mo = 0; mo < nMO; ++mo)
       if (meshGatePass(*sc, mo, o, d)) return toWavefront(s, d);
     const TraceOut tr = traceObjects<CL>(*sc, NoMesh{}, o, d, NRT_INF);
-    st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits; st.v[ST_PRIMARY] = 1;
-    double a0, a1, a2;
+    st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
+    if (bounce == 0) st.v[ST_PRIMARY] = 1;
     uint8_t flag = 0;
-    if (tr.obj < 0) {   // renderer.nim:74-75: background
-      writeAovOf(fp, cs, s, tr);
-      a0 = 0.0 + sc->bg[0] * 1.0; a1 = 0.0 + sc->bg[1] * 1.0; a2 = 0.0 + sc->bg[2] * 1.0;
+    if (tr.obj < 0) {   // renderer.nim:74-75 / :123-124: background
+      if (bounce == 0) writeAovOf(fp, cs, s, tr);
+      a0 = a0 + sc->bg[0] * w; a1 = a1 + sc->bg[1] * w; a2 = a2 + sc->bg[2] * w;
     } else {
       const DObject& ob = sc->objects[tr.obj];
       const V4 hitW = add(o, scale(d, tr.t));
@@ -1112,7 +1123,7 @@ struct FusedPrimaryT {
         for (int mo = 0; mo < nMO; ++mo)
           if (meshGatePass(*sc, mo, so, sdir)) return toWavefront(s, d);
       }
-      writeAovOf(fp, cs, s, tr);
+      if (bounce == 0) writeAovOf(fp, cs, s, tr);
       V3 local = v3(0.0, 0.0, 0.0);
       for (int l = 0; l < nL; ++l) {
         const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
@@ -1121,16 +1132,16 @@ struct FusedPrimaryT {
         st.v[ST_RAYS] += 1; st.v[ST_TESTS] += ts.tests; st.v[ST_HITS] += ts.hits;
         if (ts.obj < 0) local = add(local, shadeDiffuse(ob, li, n));                 // renderer.nim:103-105
       }
-      // resolveSample's arithmetic at bounce 0 (weight 1, accumulator 0)
-      const double k = ob.reflection, w = 1.0;
-      const int depth = (fp.depth_mode == DEPTH_INTENDED) ? 1 : 0;                  // renderer.nim:108 + depth bug
+      // resolveSample's arithmetic
+      const double k = ob.reflection;
+      const int depth = (fp.depth_mode == DEPTH_INTENDED) ? (1 + bounce) : 0;      // renderer.nim:108 + depth bug
       bool cont = false;
       double wl = w;
       if (k > 0.0 && depth <= fp.max_ray_depth) {
-        if (0 >= fp.bounce_cap) st.v[ST_CAPPED] = 1;
+        if (bounce >= fp.bounce_cap) st.v[ST_CAPPED] = 1;
         else { cont = true; wl = w * (1.0 - k); }
       }
-      a0 = 0.0 + local.x * wl; a1 = 0.0 + local.y * wl; a2 = 0.0 + local.z * wl;
+      a0 = a0 + local.x * wl; a1 = a1 + local.y * wl; a2 = a2 + local.z * wl;
       if (cont) {
         const V4 r = sub(d, scale(n, 2 * dot(n, d)));                                // renderer.nim:112
         st4(cs.rayO, cs.S, s, add(hitW, scale(r, fp.bias))); st4(cs.rayD, cs.S, s, r);
@@ -1142,15 +1153,16 @@ struct FusedPrimaryT {
     cs.active[s] = flag;
     return st;
   }
-  // hands sample s to the wavefront: its primary ray + the flag that puts it on the bounce-0 list of the wavefront
+  // hands sample s to the wavefront for this bounce: its ray (already stored from bounce 1 on) + the flag that puts
+  // it on the wavefront's list; nothing else is written and nothing is counted (the wavefront redoes the bounce)
   NRT_HD StatDelta toWavefront(int64_t s, V4 d) const {
-    if (!genFromState) st4(cs.rayD, cs.S, s, d);
+    if (bounce == 0 && !genFromState) st4(cs.rayD, cs.S, s, d);
     cs.active[s] = kFlagWavefront;
     return zeroStats();
   }
 };
-using FusedPrimary = FusedPrimaryT<false>;
-using FusedPrimaryClustered = FusedPrimaryT<true>;
+using FusedBounce = FusedBounceT<false>;
+using FusedBounceClustered = FusedBounceT<true>;
 
 // ---- PathTail / PathMega: warp-synchronous paths -----------------------------------------------------
 // One lane per sample; the lanes of a warp walk through the bounces together (`while any lane alive`), so

@@ -45,6 +45,30 @@ struct SceneData {
   std::vector<void*> owned;
   bool anyReflective = false, anyPointLight = false;
   int64_t bytes_uploaded = 0;
+  // nrt_scene_update of a description that is bit-identical to the resident one: the inputs are still copied to
+  // the device (into staging arrays, compared there with the live ones), the device-side precompute is skipped
+  struct MeshStage { double* verts = nullptr; double* normals = nullptr; int64_t* vidx = nullptr; int64_t* nidx = nullptr; };
+  std::vector<MeshStage> stage;
+  std::vector<nrt_object> lastObjs;
+  std::vector<nrt_light> lastLights;
+  double lastCam[16] = {0}, lastFov = 0, lastBg[3] = {0, 0, 0};
+  bool haveLast = false;
+  int64_t rebuilds = 0, rebuildsSkipped = 0;
+  bool sameSmallParts(const nrt_scene_desc* desc) const {
+    if (!haveLast || size_t(desc->nobjects) != lastObjs.size() || size_t(desc->nlights) != lastLights.size()) return false;
+    if (desc->nobjects && std::memcmp(desc->objects, lastObjs.data(), sizeof(nrt_object) * lastObjs.size()) != 0) return false;
+    if (desc->nlights && std::memcmp(desc->lights, lastLights.data(), sizeof(nrt_light) * lastLights.size()) != 0) return false;
+    return std::memcmp(desc->camera_to_world, lastCam, sizeof(lastCam)) == 0 && std::memcmp(&desc->fov, &lastFov, sizeof(double)) == 0 &&
+           std::memcmp(desc->bg_color, lastBg, sizeof(lastBg)) == 0;
+  }
+  void rememberSmallParts(const nrt_scene_desc* desc) {
+    lastObjs.assign(desc->objects, desc->objects + desc->nobjects);
+    lastLights.assign(desc->lights, desc->lights + desc->nlights);
+    std::memcpy(lastCam, desc->camera_to_world, sizeof(lastCam));
+    lastFov = desc->fov;
+    std::memcpy(lastBg, desc->bg_color, sizeof(lastBg));
+    haveLast = true;
+  }
   // Filter record sets per mesh object (device): ORIGIN (camera) and DIR per DistantLight.
   struct MoRecs { float* origin = nullptr; float* originHot = nullptr; float* originBounds = nullptr; std::vector<float*> dir, dirHot, dirBounds; };
   std::vector<BundleFrame> frames;        // host copy, [mo * recStride() + j]
@@ -228,6 +252,20 @@ struct SceneData {
       if (reuse && k != lights[i].kind) { err = "nrt_scene_update: light kind differs from the created scene"; return NRT_ERR_INVALID; }
     }
     bytes_uploaded = 0;
+    if (reuse && sameSmallParts(desc) && std::getenv("NRT_UPDATE_ALWAYS_REBUILD") == nullptr) {
+      stage.resize(size_t(desc->nmeshes));
+      be->diffBegin();
+      for (int i = 0; i < desc->nmeshes; ++i) {
+        const nrt_mesh& m = desc->meshes[i];
+        MeshStage& st = stage[size_t(i)];
+        st.verts = up(m.vertices, m.nverts * 4, st.verts);     be->diffAdd(st.verts, meshes[i].verts, sizeof(double) * size_t(m.nverts) * 4);
+        st.normals = up(m.normals, m.nnormals * 4, st.normals); be->diffAdd(st.normals, meshes[i].normals, sizeof(double) * size_t(m.nnormals) * 4);
+        st.vidx = up(m.vertex_idx, m.nfaces * 3, st.vidx);      be->diffAdd(st.vidx, meshes[i].vidx, sizeof(int64_t) * size_t(m.nfaces) * 3);
+        st.nidx = up(m.normal_idx, m.nfaces * 3, st.nidx);      be->diffAdd(st.nidx, meshes[i].nidx, sizeof(int64_t) * size_t(m.nfaces) * 3);
+      }
+      if (!be->diffEnd()) { ++rebuildsSkipped; return NRT_OK; }   // identical: the resident records are this description's
+    }
+    ++rebuilds;
     std::vector<DMesh> old = meshes;
     std::vector<MoRecs> oldRecs = moRecs;
     objs.assign(desc->nobjects, DObject{});
@@ -439,6 +477,7 @@ struct SceneData {
       be->upload(dRecSets, sets.data(), sizeof(RecSet) * sets.size());
       bytes_uploaded += int64_t(sizeof(RecSet) * sets.size());
     }
+    rememberSmallParts(desc);
     return NRT_OK;
   }
 
@@ -459,7 +498,7 @@ struct Renderer {
   std::vector<void*> owned;
   int32_t* dRows = nullptr;
   int64_t tailBelow = 32768;   // NRT_TAIL_BELOW: active lists shorter than this are finished by one PathTail launch
-  // NRT_PATH: 0 = the wavefront for every bounce (round-1 pipeline), 1 = FusedPrimary + wavefront for the samples
+  // NRT_PATH: 0 = the wavefront for every bounce (round-1 pipeline), 1 = FusedBounce + wavefront for the samples
   // with mesh rays at bounce 0 + PathTail (default), 2 = PathMega (one thread per sample start to end)
   int pathMode = int(envInt("NRT_PATH", 1));
   ProfileAcc prof;
@@ -504,7 +543,7 @@ struct Renderer {
       cs.pairs = al<uint32_t>(2 * capPairs);
       cs.candRef = al<uint32_t>(cand); cs.candTri = al<uint32_t>(cand); cs.candT = al<double>(cand);
       cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * cntStride(nL));
-      cs.alist = al<uint32_t>(2 * S); cs.acount = al<uint32_t>(waves + 2);
+      cs.alist = al<uint32_t>(2 * S); cs.hlist = al<uint32_t>(S); cs.acount = al<uint32_t>(waves + 4);
       cs.stats = al<unsigned long long>(ST_COUNT);
       cs.gvb = (NR + 255) / 256 + 1;
       cs.gsn = (cs.gvb + 255) / 256;
@@ -608,6 +647,7 @@ struct Renderer {
     const bool jitter = o.aa_kind >= NRT_AA_JITTERED;
     pathMode = int(envInt("NRT_PATH", 1));
     tailBelow = envInt("NRT_TAIL_BELOW", 32768);
+    if (pathMode < 0 || pathMode > 2) pathMode = 1;
     // An INTENDED-mode frame can reflect at most max_ray_depth times.
     int maxBounces = sd.anyReflective ? fp.bounce_cap : 0;
     if (sd.anyReflective && o.depth_mode == NRT_DEPTH_INTENDED) maxBounces = std::min(maxBounces, std::max(0, o.max_ray_depth));
@@ -654,81 +694,73 @@ struct Renderer {
         const int64_t ncnt = int64_t(waves) * std::max(nMO, 1) * cntStride(nL);
         be->zero(cs.counters, sizeof(uint32_t) * ncnt);
         be->zero(cs.stats, sizeof(unsigned long long) * ST_COUNT);
-        be->zero(cs.acount, sizeof(uint32_t) * (waves + 2));
+        be->zero(cs.acount, sizeof(uint32_t) * (waves + 4));
         int wave = 0;
         ActiveSet act{nullptr, nullptr, nS};   // bounce 0: every sample of the chunk
-        int bounceStart = 0;   // first bounce of the wavefront loop below
-        const bool fusedPath = pathMode != 0;
+        auto wavefrontBounce = [&](const ActiveSet& set, int bounce, bool gated) {
+          meshWave(sd, fp, WAVE_PATH, set, 2 * bounce, bounce, force_exact, gated);
+          if (sd.h.ncl1 > 0) be->forEachStats(nullptr, set.n, ShadeClustered{sd.d, fp, cs, set, bounce}, cs.stats);
+          else be->forEachStats(nullptr, set.n, Shade{sd.d, fp, cs, set, bounce}, cs.stats);
+          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, set, 2 * bounce + 1, bounce, force_exact, false);
+          shadowAndResolve(sd, fp, set, bounce);
+          wave = std::max(wave, 2 * bounce + 2);
+        };
+        auto pathTail = [&](const ActiveSet& set, int bounce) {
+          if (sd.h.ncl1 > 0) be->pathWarp(set.count, set.n, PathTailClustered{sd.d, fp, cs, force_exact, 0, set, bounce}, cs.stats);
+          else be->pathWarp(set.count, set.n, PathTail{sd.d, fp, cs, force_exact, 0, set, bounce}, cs.stats);
+        };
         if (pathMode == 2) {
           // ---- PathMega: every sample start to end in one launch ----
           if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
           if (sd.h.ncl1 > 0) be->pathWarp(nullptr, nS, PathMegaClustered{sd.d, fp, cs, force_exact, jitter ? 1 : 0, act, 0}, cs.stats);
           else be->pathWarp(nullptr, nS, PathMega{sd.d, fp, cs, force_exact, jitter ? 1 : 0, act, 0}, cs.stats);
-          bounceStart = -1;    // nothing left
-        } else if (fusedPath) {
-          // ---- fused path (nrt_pipeline.h: FusedPrimaryT, PathWarpT) ----
+        } else if (pathMode == 1) {
+          // ---- fused path (nrt_pipeline.h: FusedBounceT, PathWarpT): per bounce, ONE kernel takes every active sample
+          // through the whole bounce in registers unless one of its rays enters a mesh box; those samples (flag
+          // kFlagWavefront, listed in sample order) go through the wavefront for that bounce.
           if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
-          const int gfs = jitter ? 1 : 0;
-          if (sd.h.ncl1 > 0) be->forEachStats(nullptr, nS, FusedPrimaryClustered{sd.d, fp, cs, force_exact, gfs}, cs.stats);
-          else be->forEachStats(nullptr, nS, FusedPrimary{sd.d, fp, cs, force_exact, gfs}, cs.stats);
-          if (nMO > 0) {
-            // the samples with a mesh ray at bounce 0, in sample order (= the wavefront's bounce-0 active list)
-            uint32_t* hardList = cs.alist;            // (bounce 1's list goes to the other half)
-            uint32_t* hardCount = cs.acount;
-            be->compactActive(cs, act, hardList, hardCount, kFlagWavefront);
-            uint32_t n0 = 0;
-            be->download(&n0, hardCount, sizeof(n0));
-            if (n0 > 0) {
-              const ActiveSet hard{hardList, hardCount, int64_t(n0)};
-              meshWave(sd, fp, WAVE_PATH, hard, wave, 0, force_exact, false); ++wave;
-              if (sd.h.ncl1 > 0) be->forEachStats(nullptr, hard.n, ShadeClustered{sd.d, fp, cs, hard, 0}, cs.stats);
-              else be->forEachStats(nullptr, hard.n, Shade{sd.d, fp, cs, hard, 0}, cs.stats);
-              if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, hard, wave, 0, force_exact, false);
-              ++wave;
-              shadowAndResolve(sd, fp, hard, 0);
-            } else wave += 2;
-          } else wave += 2;
-          // bounce 1's active set: every sample with a nonzero flag (FusedPrimary: continues; Resolve: continues)
-          bounceStart = -1;
-          if (maxBounces > 0) {
-            uint32_t* nextList = cs.alist + cs.S;
-            uint32_t* nextCount = cs.acount + 1;
+          for (int bounce = 0;; ++bounce) {
+            if (bounce > 0 && act.n < tailBelow) { pathTail(act, bounce); break; }   // a small wave: one launch to the end of its paths
+            const int gfs = (bounce == 0 && jitter) ? 1 : 0;
+            if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, FusedBounceClustered{sd.d, fp, cs, force_exact, gfs, act, bounce}, cs.stats);
+            else be->forEachStats(nullptr, act.n, FusedBounce{sd.d, fp, cs, force_exact, gfs, act, bounce}, cs.stats);
+            if (nMO > 0) {
+              uint32_t* hardCount = cs.acount + 2 * bounce;
+              be->compactActive(cs, act, cs.hlist, hardCount, kFlagWavefront);
+              uint32_t nh = 0;
+              be->download(&nh, hardCount, sizeof(nh));
+              if (nh > 0) wavefrontBounce(ActiveSet{cs.hlist, hardCount, int64_t(nh)}, bounce, false);
+            }
+            if (bounce >= maxBounces) break;
+            // the next bounce's active set: every sample of this one whose flag is nonzero (FusedBounce: continues;
+            // Resolve: continues), in sample order
+            uint32_t* nextList = cs.alist + int64_t((bounce + 1) & 1) * cs.S;
+            uint32_t* nextCount = cs.acount + 2 * bounce + 1;
             be->compactActive(cs, act, nextList, nextCount, 0);
             uint32_t cont = 0;
             be->download(&cont, nextCount, sizeof(cont));
-            if (cont > 0) { act = ActiveSet{nextList, nextCount, int64_t(cont)}; bounceStart = 1; }
+            if (cont == 0) break;
+            act = ActiveSet{nextList, nextCount, int64_t(cont)};
           }
-        }
-        if (bounceStart >= 0) {
-        // primary rays: generated and gated in one kernel (the jittered kinds generate per pixel: separate gate)
-        const bool fuseGen = !fusedPath && !jitter && nMO > 0;
-        if (fusedPath) {}
-        else if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
-        else if (fuseGen) be->produceGate(nS, 1, GenGate{GenSimple{sd.d, fp, cs}, makeGate(sd, fp, WAVE_PATH, act, 0, force_exact), nMO}, cs, nMO, waveCounters(0), nullptr);
-        else be->forEach(nS, GenSimple{sd.d, fp, cs});
-        for (int bounce = bounceStart;; ++bounce) {
-          uint32_t* nextList = cs.alist + int64_t((bounce + 1) & 1) * cs.S;
-          uint32_t* nextCount = cs.acount + bounce + 1;
-          // a small wave: one PathTail launch takes its samples to the end of their paths
-          if (bounce > 0 && fusedPath && act.n < tailBelow) {
-            if (sd.h.ncl1 > 0) be->pathWarp(act.count, act.n, PathTailClustered{sd.d, fp, cs, force_exact, 0, act, bounce}, cs.stats);
-            else be->pathWarp(act.count, act.n, PathTail{sd.d, fp, cs, force_exact, 0, act, bounce}, cs.stats);
-            break;
+        } else {
+          // ---- the wavefront for every bounce (round-1 pipeline; NRT_PATH=0) ----
+          // primary rays: generated and gated in one kernel (the jittered kinds generate per pixel: separate gate)
+          const bool fuseGen = !jitter && nMO > 0;
+          if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
+          else if (fuseGen) be->produceGate(nS, 1, GenGate{GenSimple{sd.d, fp, cs}, makeGate(sd, fp, WAVE_PATH, act, 0, force_exact), nMO}, cs, nMO, waveCounters(0), nullptr);
+          else be->forEach(nS, GenSimple{sd.d, fp, cs});
+          for (int bounce = 0;; ++bounce) {
+            uint32_t* nextList = cs.alist + int64_t((bounce + 1) & 1) * cs.S;
+            uint32_t* nextCount = cs.acount + 2 * bounce + 1;
+            // (act.n is exact on the host for every bounce: launches are sized to it)
+            wavefrontBounce(act, bounce, bounce == 0 && fuseGen);
+            if (bounce >= maxBounces) break;
+            be->compactActive(cs, act, nextList, nextCount, 0);
+            uint32_t cont = 0;
+            be->download(&cont, nextCount, sizeof(cont));
+            if (cont == 0) break;  // no sample continued
+            act = ActiveSet{nextList, nextCount, int64_t(cont)};
           }
-          // (act.n is exact on the host for every bounce: launches are sized to it)
-          meshWave(sd, fp, WAVE_PATH, act, wave, bounce, force_exact, bounce == 0 && fuseGen); ++wave;
-          if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadeClustered{sd.d, fp, cs, act, bounce}, cs.stats);
-          else be->forEachStats(nullptr, act.n, Shade{sd.d, fp, cs, act, bounce}, cs.stats);
-          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, act, wave, bounce, force_exact, false);
-          ++wave;
-          shadowAndResolve(sd, fp, act, bounce);
-          if (bounce >= maxBounces) break;
-          be->compactActive(cs, act, nextList, nextCount, 0);
-          uint32_t cont = 0;
-          be->download(&cont, nextCount, sizeof(cont));
-          if (cont == 0) break;  // no sample continued
-          act = ActiveSet{nextList, nextCount, int64_t(cont)};
-        }
         }
         be->finalize(npix, Finalize{fp, cs});
         // chunk epilogue: counters (profile + overflow check) and stats

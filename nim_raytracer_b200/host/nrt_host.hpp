@@ -393,4 +393,19 @@ inline std::shared_ptr<TriangleMesh> loadGeom(const std::string& fname) {
   return m;
 }
 
+// objconv.nim:139-153: int32 triangle count, then the three vertices of every face as 9 float32
+inline void writeGeom(const std::string& fname, const TriangleMesh& m) {
+  std::ofstream f(fname, std::ios::binary);
+  if (!f) throw Error(NRT_ERR_INVALID, "cannot create " + fname);
+  const int32_t n = int32_t(m.faces.size());
+  f.write(reinterpret_cast<const char*>(&n), 4);
+  for (const Triangle& t : m.faces)
+    for (int i = 0; i < 3; ++i) {
+      const Vec4& v = m.vertices[size_t(t.vertexIdx[i])];
+      const float p[3] = {float(v.x), float(v.y), float(v.z)};
+      f.write(reinterpret_cast<const char*>(p), 12);
+    }
+  if (!f) throw Error(NRT_ERR_INVALID, "write failed: " + fname);
+}
+
 }  // namespace nimrt

@@ -94,9 +94,145 @@ def mesh_scene(mesh, albedo=(0.6, 0.9, 0.2), reflection=0.0, extra_objects=()) -
                  bgColor=vec3(0.01, 0.03, 0.05))
 
 
-def teapot_scene(obj_path: str) -> Scene:
-    """src/data/scenes/mesh-bunny.nim verbatim (it loads data/meshes/teapot.obj)."""
+TEAPOT_OBJ = os.path.join(DATA_DIR, "teapot.obj")  # == src/data/meshes/teapot.obj of the reference (data, 6,320 triangles)
+
+
+def teapot_scene(obj_path: str = TEAPOT_OBJ) -> Scene:
+    """src/data/scenes/mesh-bunny.nim:1-42 verbatim (it loads data/meshes/teapot.obj): the scene the reference's
+    default front-end renders (src/raytracer.nim:43-54: 300x200, akNone, bias 1e-8, maxRayDepth 5)."""
     return mesh_scene(loadObj(obj_path))
+
+
+def _spheres_layout(lights, bg) -> Scene:
+    """The seven r = 2 spheres + ground plane shared by src/data/scenes/spheres-{pointlight1,pointlight2,warm,blue,
+    purple}.nim:1-58 (no reflection), camera Rx(-12 deg) . T(1, 5.5, 3.5), fov 50."""
+    def ball(name, x, y, z, albedo):
+        return Object(name, initSphere(r=2, objectToWorld=L.translate(L.mat4(1.0), vec3(x, y, z))), Material(albedo=vec3(*albedo)))
+    objects = [
+        ball("ball1", -5.0, 2.0, -18.0, (0.9, 0.3, 0.2)),
+        ball("ball2", 0.5, 2.0, -8.0, (0.6, 0.9, 0.2)),
+        ball("ball3", -5.0, 2.0, -10.0, (0.1, 0.7, 0.2)),
+        ball("ball4", 8.0, 2.0, -15.0, (0.2, 0.3, 0.9)),
+        ball("ball5", 4.0, 2.0, -16.0, (0.2, 0.5, 0.9)),
+        ball("ball6", -2.0, 2.0, -42.0, (0.9, 0.5, 0.2)),
+        ball("ball7", 9.0, 2.0, -30.0, (0.6, 0.5, 0.9)),
+        Object("ground", initPlane(objectToWorld=L.mat4(1.0)), Material(albedo=vec3(0.4))),
+    ]
+    return Scene(objects=objects, lights=lights, fov=50.0, cameraToWorld=_camera(1.0, 5.5, 3.5), bgColor=vec3(*bg))
+
+
+def spheres_pointlight1() -> Scene:
+    """src/data/scenes/spheres-pointlight1.nim:1-76."""
+    return _spheres_layout([PointLight(color=vec3(1.0, 0.8, 0.5), intensity=2000.0, pos=point(3.0, 6.0, -12.0))], (0.0, 0.0, 0.0))
+
+
+def spheres_pointlight2() -> Scene:
+    """src/data/scenes/spheres-pointlight2.nim:1-76."""
+    return _spheres_layout([PointLight(color=vec3(1.0, 0.8, 0.5), intensity=5000.0, pos=point(0.0, 8.0, -35.0))], (0.0, 0.0, 0.0))
+
+
+def spheres_warm() -> Scene:
+    """src/data/scenes/spheres-warm.nim:1-80."""
+    return _spheres_layout(_bunny_lights(), (0.01, 0.03, 0.05))
+
+
+def spheres_blue() -> Scene:
+    """src/data/scenes/spheres-blue.nim:1-80."""
+    return _spheres_layout([
+        DistantLight(color=vec3(1.0), intensity=0.2, dir=L.normalize(vec(-2.0, -0.8, -0.3))),
+        DistantLight(color=vec3(0.1, 0.6, 0.8), intensity=8.0, dir=L.normalize(vec(0.5, -0.4, 0.8))),
+    ], (0.1, 0.6, 0.8))
+
+
+def spheres_purple() -> Scene:
+    """src/data/scenes/spheres-purple.nim:1-80."""
+    return _spheres_layout([
+        DistantLight(color=vec3(1.0, 0.0, 0.0), intensity=4.5, dir=L.normalize(vec(1.7, -0.5, 2.3))),
+        DistantLight(color=vec3(1.0, 0.0, 1.0), intensity=1.5, dir=L.normalize(vec(-2.7, -0.5, 2.3))),
+    ], (0.30, 0.00, 0.02))
+
+
+def boxes() -> Scene:
+    """src/data/scenes/boxes.nim:1-70: ground plane + 4 x 4 x 4 boxes, camera rotated about TWO axes
+    (Rx(-34 deg) . Ry(-35 deg) . T(-3.5, 20.5, 9.5)), fov 65.  The loop variables advance exactly as in the file
+    (x += PAD inside the innermost loop, so the accumulated float64 sums are the reference's)."""
+    objects = [Object("ground", initPlane(objectToWorld=L.mat4(1.0)), Material(albedo=vec3(0.4)))]
+    ROWS, PAD = 4, 3.8
+    xs, ys, zs = 0.0, 3.0, -18.0
+    x, y, z = xs, ys, zs
+    for i in range(ROWS):
+        for j in range(ROWS):
+            for k in range(ROWS):
+                objects.append(Object("box", initBox(objectToWorld=L.translate(L.mat4(1.0), vec3(x, y, z)),
+                                                     vmin=vec(-1.3, -1.3, -1.3), vmax=vec(1.3, 1.3, 1.3)),
+                                      Material(albedo=vec3(1.0 / float(ROWS) * float(ROWS - k),
+                                                           1.0 / float(ROWS) * float(ROWS - j),
+                                                           1.0 / float(ROWS) * float(ROWS - i)))))
+                x += PAD
+            y += PAD
+            x = xs
+        z -= PAD
+        x = xs
+        y = ys
+    lights = [
+        DistantLight(color=vec3(1.0), intensity=9.0, dir=L.normalize(vec(-2.0, -0.8, -0.3))),
+        DistantLight(color=vec3(0.8, 0.3, 0.0), intensity=2.0, dir=L.normalize(vec(2.0, -0.8, -1.3))),
+    ]
+    cam = L.translate(L.rotate(L.rotate(L.mat4(1.0), L.X_AXIS, L.deg_to_rad(-34.0)), L.Y_AXIS, L.deg_to_rad(-35.0)),
+                      vec3(-3.5, 20.5, 9.5))
+    return Scene(objects=objects, lights=lights, fov=65.0, cameraToWorld=cam, bgColor=vec3(0.15, 0.09, 0.07))
+
+
+def boxes2() -> Scene:
+    """src/data/scenes/boxes2.nim:1-62: platform box, ball and a ring of 13 boxes each under
+    T(0, 1, Z) . Ry(rot) . T(0, 0, 5) with rot accumulated by 360 / 13; one distant light, fov 20."""
+    Z_DIST = -18.0
+    objects = [
+        Object("ground", initPlane(objectToWorld=L.mat4(1.0)), Material(albedo=vec3(0.3))),
+        Object("platform", initBox(objectToWorld=L.translate(L.mat4(1.0), vec3(0.0, 0.0, Z_DIST)),
+                                   vmin=vec(-6.3, 0.0, -6.3), vmax=vec(6.3, 0.5, 6.3)), Material(albedo=vec3(0.5))),
+        Object("ball", initSphere(objectToWorld=L.translate(L.mat4(1.0), vec3(0.0, 4.8, Z_DIST)), r=1.5),
+               Material(albedo=vec3(0.5))),
+    ]
+    N, rot = 13, 0.0
+    for i in range(N):
+        m = L.translate(L.rotate(L.translate(L.mat4(1.0), vec3(0.0, 1.0, Z_DIST)), L.Y_AXIS, L.deg_to_rad(rot)), vec3(0.0, 0.0, 5.0))
+        objects.append(Object(f"box{i}", initBox(objectToWorld=m, vmin=vec(-0.5, -0.5, -0.5), vmax=vec(0.5, 0.5, 0.5)),
+                              Material(albedo=vec3(0.5))))
+        rot += 360.0 / float(N)
+    lights = [DistantLight(color=vec3(1.0, 1.0, 1.0), intensity=0.5, dir=L.normalize(vec(3.0, -0.5, -4.0)))]
+    return Scene(objects=objects, lights=lights, fov=20.0, cameraToWorld=_camera(0.0, 6.0, 20.0, -15.0),
+                 bgColor=vec3(0.15, 0.07, 0.04))
+
+
+def boxes_pointlight1() -> Scene:
+    """src/data/scenes/boxes-pointlight1.nim:1-88: seven boxes each under T . Rx(angle), ground plane, the two
+    mesh-bunny lights (the file's name notwithstanding, both are DistantLights), camera Rx(-12 deg) . T(0.5, 5.5, 3.5)."""
+    def box(name, t, deg, albedo):
+        m = L.rotate(L.translate(L.mat4(1.0), vec3(*t)), L.X_AXIS, L.deg_to_rad(deg))
+        return Object(name, initBox(objectToWorld=m, vmin=vec(-1.0, -1.0, -1.0), vmax=vec(1.0, 1.0, 1.0)), Material(albedo=vec3(*albedo)))
+    objects = [
+        box("box-red", (-5.0, 2.0, -18.0), -10.0, (0.9, 0.3, 0.2)),
+        box("box-yellow", (0.5, 2.0, -6.0), -50.0, (0.6, 0.9, 0.2)),
+        box("box3", (-5.0, 2.0, -10.0), -50.0, (0.1, 0.7, 0.2)),
+        box("box4", (8.0, 2.0, -15.0), -70.0, (0.2, 0.3, 0.9)),
+        box("box5", (4.0, 2.0, -16.0), -60.0, (0.2, 0.5, 0.9)),
+        box("box6", (-2.0, 2.0, -52.0), -40.0, (0.9, 0.5, 0.2)),
+        box("box7", (9.0, 2.0, -30.0), -20.0, (0.6, 0.5, 0.9)),
+        Object("ground", initPlane(objectToWorld=L.mat4(1.0)), Material(albedo=vec3(0.4))),
+    ]
+    return Scene(objects=objects, lights=_bunny_lights(), fov=50.0, cameraToWorld=_camera(0.5, 5.5, 3.5),
+                 bgColor=vec3(0.6, 0.6, 0.5))
+
+
+# the reference's scene files (src/data/scenes/*.nim) by name; first.nim predates the Object / Geometry types
+# (`Sphere(o: ..., albedo: ...)`) and does not compile against the renderer of this tree
+REFERENCE_SCENES = {
+    "spheres-reflection": spheres_reflection, "boxtest": boxtest, "mesh-cube": mesh_cube, "mesh-bunny": teapot_scene,
+    "spheres-pointlight1": spheres_pointlight1, "spheres-pointlight2": spheres_pointlight2, "spheres-warm": spheres_warm,
+    "spheres-blue": spheres_blue, "spheres-purple": spheres_purple, "boxes": boxes, "boxes2": boxes2,
+    "boxes-pointlight1": boxes_pointlight1,
+}
 
 
 def bunny_triangles(flip_winding: bool = True, scale: float = 20.0, max_faces: int | None = None,

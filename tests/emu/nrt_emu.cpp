@@ -32,6 +32,10 @@ struct LoopBackend {
   void upload(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
   void download(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
   void sync() {}
+  bool diff_ = false;
+  void diffBegin() { diff_ = false; }
+  void diffAdd(const void* a, const void* b, size_t bytes) { if (bytes && std::memcmp(a, b, bytes) != 0) diff_ = true; }
+  bool diffEnd() { return diff_; }
   int64_t memAvailable(int64_t) { return int64_t(1) << 40; }
   template <class F> void forEach(int64_t n, const F& f) { for (int64_t i = 0; i < n; ++i) f(i); ++launches; }
   template <class F> void forEachStats(const uint32_t* count, int64_t n, const F& f, unsigned long long* st) {

@@ -70,3 +70,9 @@ if __name__ == "__main__":
         make("config4_bunny_spheres_3840x2160_g4", scenes.bunny_spheres(),
              api.Options(3840, 2160, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED,
                          maxRayDepth=8), row_stride=48)
+    if "reference_scenes" in which:
+        # every scene file of the reference (src/data/scenes/*.nim, restated in nim_raytracer_b200/scenes.py) with the
+        # options of its default front-end (src/raytracer.nim:43-54: 300x200, akNone, bias 1e-8, maxRayDepth 5);
+        # "mesh-bunny" is the scene that front-end includes: the teapot (src/data/meshes/teapot.obj)
+        for name, build in scenes.REFERENCE_SCENES.items():
+            make("ref_" + name.replace("-", "_") + "_300x200", build(), api.Options(300, 200, bias=0.00000001, maxRayDepth=5), row_stride=25)

@@ -250,7 +250,7 @@ def test_golden_config4_full_size():
 
 @pytest.mark.parametrize("path", ["0", "2"])
 def test_path_modes_agree(oracle_mod, monkeypatch, path):
-    # NRT_PATH: 0 = the wavefront for every bounce, 1 (default) = FusedPrimary + wavefront + PathTail, 2 = PathMega
+    # NRT_PATH: 0 = the wavefront for every bounce, 1 (default) = FusedBounce + wavefront + PathTail, 2 = PathMega
     # (one thread per sample, meshes walked by the thread): three formulations, one result
     monkeypatch.setenv("NRT_PATH", path)
     sc = scenes.bunny_spheres(stride=4)
@@ -367,6 +367,42 @@ def test_scene_update_and_srgb_output(oracle_mod):
     ref8 = np.round(s.astype(np.float32) * np.float32(255)).astype(np.int32)
     assert np.abs(img.astype(np.int32) - ref8).max() <= 1
     assert (img.astype(np.int32) == ref8).mean() > 0.999
+
+
+def test_scene_update_identical_changed_and_rejected(oracle_mod):
+    # nrt_scene_update: (1) a bit-identical description is copied to the device and compared there - the records are
+    # kept; (2) one changed vertex is detected and everything is rebuilt; (3) a description whose shape differs
+    # (object kind, mesh index, light kind) is rejected BEFORE anything is touched: the scene still renders
+    sc = scenes.bunny_spheres(stride=16)
+    o = api.Options(160, 90)
+    ds = api.DeviceScene(sc)
+    fb = api.newFramebuf(160, 90)
+    api.renderFrame(ds, o, fb)
+    ref, rst, _ = oracle_mod.render(sc, o)
+    assert (fb.data == ref.data).all()
+    ds.update()                                                  # (1)
+    fb1 = api.newFramebuf(160, 90)
+    st1 = api.renderFrame(ds, o, fb1)
+    assert (fb1.data == ref.data).all() and st1 == rst
+    sc.objects[0].geometry.vertices[7, 1] += 0.25                # (2) the mesh arrays are shared with the description
+    sc.objects[0].geometry.vertices[8, 0] -= 0.125
+    ds.update(sc)
+    fb2 = api.newFramebuf(160, 90)
+    st2 = api.renderFrame(ds, o, fb2)
+    ref2, rst2, _ = oracle_mod.render(sc, o)
+    assert (fb2.data == ref2.data).all() and st2 == rst2
+    bad = scenes.bunny_spheres(stride=16)                        # (3)
+    bad.objects[0].geometry.vertices[:] = sc.objects[0].geometry.vertices
+    bad.objects[2], bad.objects[0] = bad.objects[0], bad.objects[2]   # a sphere where the mesh was and vice versa
+    with pytest.raises(api.NrtError):
+        ds.update(bad)
+    bad2 = scenes.bunny_spheres(stride=16)
+    bad2.lights[1] = api.PointLight(color=api.vec3(1.0), intensity=100.0, pos=api.point(0.0, 5.0, -5.0))
+    with pytest.raises(api.NrtError):
+        ds.update(bad2)
+    fb3 = api.newFramebuf(160, 90)
+    st3 = api.renderFrame(ds, o, fb3)
+    assert (fb3.data == ref2.data).all() and st3 == rst2
 
 
 def test_page_locked_caller_memory(oracle_mod):
