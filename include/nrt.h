@@ -255,6 +255,28 @@ int nrt_framebuf_quantize(const float* fb_host, int width, int height,
 int nrt_framebuf_to_rgba8(const float* fb_host, int width, int height,
                           unsigned char alpha, unsigned char* rgba8);
 
+/* The same conversions on DEVICE memory (fb_dev from nrt_render_device / nrt_device_alloc): no staging, no copies. */
+int nrt_framebuf_quantize_device(const float* fb_dev, int width, int height,
+                                 int bits, int srgb, void* out_dev);
+int nrt_framebuf_to_rgba8_device(const float* fb_dev, int width, int height,
+                                 unsigned char alpha, unsigned char* rgba8_dev);
+
+/* renderLine* + writePpm / ImageRGBA.copyFrom in one call (renderer.nim:162-211 followed by
+ * utils/framebuf.nim:55-93 or utils/image.nim:45-54): the output stage runs as the epilogue of the
+ * kernel that stores the pixels, and only the integer image leaves the GPU — 3 (bits <= 8), 6 (bits > 8,
+ * big-endian) or 4 (NRT_OUT_RGBA8) bytes per pixel instead of 12.  `image` is HOST memory laid out like the
+ * PPM sample stream / ImageRGBA.data: offset (y*width+x) * bytes-per-pixel.  Only the pixels of the requested
+ * lines (and their step x step fill blocks) are written.  srgb / bits are ignored for NRT_OUT_RGBA8. */
+enum { NRT_OUT_RGB = 0, NRT_OUT_RGBA8 = 1 };
+/* The table the device-side sRGB conversion searches (no device needed): thr[k-1] = the smallest float32 input of
+ * linearToSRGB's pow branch (utils/color.nim:21) whose sample is >= k, k = 1 .. 2^bits - 1.  thr_host holds
+ * 2^bits - 1 floats.  tests/ compares it with the oracle over EVERY float32 of the branch. */
+int nrt_output_cut_points(int bits, float* thr_host);
+int nrt_render_quantized(nrt_scene* scene, const nrt_options* opts,
+                         int y0, int y1, int step, int max_step,
+                         int format, int bits, int srgb, int alpha,
+                         void* image, nrt_stats* stats);
+
 int nrt_get_profile(const nrt_scene* scene, nrt_profile* out);
 
 /* Per-kernel-family timing (no reference counterpart; the reference only prints a wall-clock total,
@@ -270,6 +292,7 @@ int nrt_device_alloc(int64_t bytes, void** dev_ptr);         /* on group device 
 int nrt_device_free(void* dev_ptr);
 int nrt_device_memset(void* dev_ptr, int value, int64_t bytes);
 int nrt_copy_to_host(void* host_dst, const void* dev_src, int64_t bytes);
+int nrt_copy_to_device(void* dev_dst, const void* host_src, int64_t bytes);
 int nrt_ipc_export(void* dev_ptr, nrt_ipc_handle* out);
 int nrt_ipc_open(const nrt_ipc_handle* handle, void** dev_ptr);
 int nrt_ipc_close(void* dev_ptr);

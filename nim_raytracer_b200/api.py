@@ -566,6 +566,36 @@ def framebufToRgba8(fb: Framebuf, alpha: int = 0xFF) -> np.ndarray:
     return out.reshape(fb.h, fb.w, 4)
 
 
+NRT_OUT_RGB, NRT_OUT_RGBA8 = 0, 1
+
+
+def outputCutPoints(bits: int = 8) -> np.ndarray:
+    """The cut-point table of the sRGB pow branch for `bits` (host computation inside libnrt.so; no GPU needed)."""
+    out = np.zeros((1 << bits) - 1, dtype=np.float32)
+    L = lib()
+    L.nrt_output_cut_points.argtypes = [C.c_int, C.c_void_p]
+    check(L.nrt_output_cut_points(bits, out.ctypes.data_as(C.c_void_p)), "nrt_output_cut_points")
+    return out
+
+
+def renderFrameQuantized(scene, opts: "Options", bits: int = 8, sRGB: bool = True, rgba: bool = False, alpha: int = 0xFF,
+                         step: int = 1, maxStep: int = 1, image: Optional[np.ndarray] = None):
+    """renderFrame + writePpm's samples (or ImageRGBA bytes with rgba=True) in one call: the output stage is the
+    epilogue of the pixel-store kernel and only the integer image is copied to the host.  Returns (image, Stats);
+    image is (h, w, 3) uint8 / big-endian uint16, or (h, w, 4) uint8."""
+    ds = _as_device_scene(scene)
+    h, w = opts.height, opts.width
+    if image is None:
+        image = np.zeros((h, w, 4), dtype=np.uint8) if rgba else np.zeros((h, w, 3), dtype=np.uint8 if bits <= 8 else ">u2")
+    co, cs = opts.to_c(), nrt_stats()
+    L = lib()
+    L.nrt_render_quantized.argtypes = [C.c_void_p, C.POINTER(nrt_options), C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(nrt_stats)]
+    check(L.nrt_render_quantized(ds.handle, C.byref(co), 0, h, step, maxStep, NRT_OUT_RGBA8 if rgba else NRT_OUT_RGB,
+                                 bits, int(sRGB), alpha, image.ctypes.data_as(C.c_void_p), C.byref(cs)), "nrt_render_quantized")
+    return image, Stats.from_c(cs)
+
+
 def writePpm(fb: Framebuf, filename: str, bits: int = 8, sRGB: bool = True) -> bool:
     """utils/framebuf.nim:55-93: P6, maxval 2^bits - 1, 8-bit or big-endian 16-bit samples (GPU output stage)."""
     img = framebufQuantize(fb, bits, sRGB)

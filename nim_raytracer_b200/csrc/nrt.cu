@@ -819,33 +819,12 @@ __global__ void __launch_bounds__(kBlock) k_finalize_tiled(Finalize f, int64_t n
   }
 }
 
-// Output stage: writePpm's outvalue (utils/framebuf.nim:74-78): clamp -> linearToSRGB (utils/color.nim:17-22)
-// -> round(c * maxval), maxval = 2^bits - 1; 8-bit samples for bits <= 8, big-endian 16-bit samples above
-// (the PPM byte order, framebuf.nim:67-71).
-__device__ __forceinline__ float outvalue(float c, int srgb, float maxval) {
-  c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
-  if (srgb) {
-    if (c <= 0.0031308f) c = 12.92f * c;
-    else c = float((1.0 + 0.055) * double(powf(c, float(1 / 2.4))) - 0.055);
-  }
-  return roundf(c * maxval);
-}
-__global__ void __launch_bounds__(kBlock) k_quantize(const float* fb, unsigned char* out, int64_t n, int srgb, int bits) {
-  const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
-  if (i >= n) return;
-  const unsigned v = unsigned(outvalue(fb[i], srgb, float((1u << bits) - 1u)));
-  if (bits <= 8) out[i] = (unsigned char)v;
-  else { out[2 * i] = (unsigned char)(v >> 8); out[2 * i + 1] = (unsigned char)(v & 0xFFu); }
-}
-// ImageRGBA.copyFrom (utils/image.nim:45-54): round(v * 255) per channel + a constant alpha (values are
-// clamped to 0..255 here; the reference's float -> uint8 conversion is undefined outside that range)
-__global__ void __launch_bounds__(kBlock) k_rgba8(const float* fb, unsigned char* out, int64_t npix, unsigned char alpha) {
+// Output stage on an existing float32 framebuffer (nrt_framebuf_*): the same conversions Finalize's fused epilogue
+// makes (nrt_pipeline.h: OutStage / storeQ), one thread per pixel.
+__global__ void __launch_bounds__(kBlock) k_out_stage(const float* fb, OutStage q, int64_t npix) {
   const int64_t p = int64_t(blockIdx.x) * kBlock + threadIdx.x;
   if (p >= npix) return;
-  uchar4 o;
-  auto q = [](float v) { const float r = roundf(v * 255.f); return (unsigned char)(r < 0.f ? 0.f : (r > 255.f ? 255.f : r)); };
-  o.x = q(fb[3 * p]); o.y = q(fb[3 * p + 1]); o.z = q(fb[3 * p + 2]); o.w = alpha;
-  reinterpret_cast<uchar4*>(out)[p] = o;
+  storeQ(q, p, fb[3 * p], fb[3 * p + 1], fb[3 * p + 2]);
 }
 
 // word-wise comparison of two device arrays (nrt_scene_update: is the uploaded description the resident one?)
@@ -1261,6 +1240,8 @@ struct DeviceCtx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // frame bracket (nrt_profile.total_ms)
   cudaEvent_t tb0 = nullptr, tb1 = nullptr;   // user bracket (nrt_timer_begin/end)
   std::vector<cudaEvent_t> laneDone;           // per extra lane: its part of the frame is complete
+  float* thr[17] = {nullptr};                  // output stage: cut points of the sRGB pow branch per bit depth (device)
+  float* outFb = nullptr; unsigned char* outQ = nullptr; int64_t outFbN = 0, outQN = 0;   // nrt_framebuf_* staging (grow-only)
 };
 
 static std::mutex g_mu;
@@ -1315,6 +1296,7 @@ struct PerDevice {
   SceneData<CudaBackend> sd;
   Renderer<CudaBackend> rn[kMaxLanes];
   float* fbStage = nullptr; int64_t fbStageN = 0;
+  unsigned char* qStage = nullptr; int64_t qStageN = 0;   // nrt_render_quantized: the integer image
   int32_t* aovObj = nullptr; int32_t* aovTri = nullptr; double* aovT = nullptr; int64_t aovN = 0;
 };
 
@@ -1374,6 +1356,53 @@ static int initLocked(int ngpu, const int* ids) {
   return NRT_OK;
 }
 
+// ---- output stage: the cut points of linearToSRGB's pow branch (nrt_pipeline.h: OutStage) ----
+// utils/color.nim:17-22 with the literals in the float32 type of `v` and `a` a float64 (see oracle/ref_cpu.cpp);
+// powf is the libm call the reference's C back-end makes
+static float hostLinearToSRGBPow(float v) {
+  const double a = 0.055;
+  return float((1 + a) * double(powf(v, float(1 / 2.4))) - a);
+}
+static uint32_t hostLevel(float v, float maxval) { return uint32_t(roundf(hostLinearToSRGBPow(v) * maxval)); }
+static uint32_t fbitsHost(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+static float bitsfHost(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+// thr[k - 1] = the smallest float32 in (0.0031308, 1] whose sample is >= k.  Positive floats order like their bit
+// patterns, so this is a binary search over patterns; the conversion's monotonicity — which the search and the
+// device's counting rely on — is checked on 32 neighbours either side of every cut point.
+static bool buildCutPoints(int bits, std::vector<float>& thr) {
+  const uint32_t maxv = (1u << bits) - 1u;
+  const float maxval = float(maxv);
+  const uint32_t lo0 = fbitsHost(0.0031308f) + 1, hi0 = fbitsHost(1.0f);
+  thr.assign(maxv, 0.f);
+  for (uint32_t k = 1; k <= maxv; ++k) {
+    uint32_t lo = lo0, hi = hi0;            // invariant: level(hi) >= k (level(1.0) == maxval)
+    if (hostLevel(bitsfHost(lo), maxval) >= k) hi = lo;
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (hostLevel(bitsfHost(mid), maxval) >= k) hi = mid; else lo = mid + 1;
+    }
+    thr[k - 1] = bitsfHost(hi);
+    for (uint32_t d = 1; d <= 32; ++d) {
+      if (hi >= lo0 + d && hostLevel(bitsfHost(hi - d), maxval) >= k) return false;
+      if (hi + d <= hi0 && hostLevel(bitsfHost(hi + d), maxval) < k) return false;
+    }
+  }
+  return true;
+}
+// device copy of the table for `bits` on device context dc (built once)
+static const float* cutPoints(DeviceCtx* dc, int bits) {
+  if (dc->thr[bits]) return dc->thr[bits];
+  std::vector<float> t;
+  if (!buildCutPoints(bits, t)) throw std::runtime_error("output stage: powf is not monotonic around a cut point on this host");
+  float* d = static_cast<float*>(dc->be.dalloc(sizeof(float) * t.size()));
+  dc->be.upload(d, t.data(), sizeof(float) * t.size());
+  dc->be.sync();
+  dc->thr[bits] = d;
+  return d;
+}
+struct OutSpec { int bits, srgb, rgba, alpha; };
+static int64_t outBytesPerPixel(const OutSpec& q) { return q.rgba ? 4 : (q.bits <= 8 ? 3 : 6); }
+
 // The rendered rows of [y0, y1) — (y - y0) % step == 0, numbered i = (y - y0) / step — owned by lane `lane` of
 // partition `part`: i % nparts == part (scanline interleave over the GPUs / ranks: the reference's work items,
 // raytracer.nim:67-70; counted among the RENDERED rows, so a progressive pass with step >= nparts still spreads
@@ -1388,9 +1417,11 @@ static std::vector<int32_t> rowsFor(int height, int y0, int y1, int step, int pa
   return r;
 }
 
+// `qspec` != null: `fb` is the caller's INTEGER image (host memory): Finalize's epilogue converts, only those bytes travel
 static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int step, int max_step, float* fb,
-                      nrt_stats* stats, const nrt_aov* aov, bool deviceOut) {
+                      nrt_stats* stats, const nrt_aov* aov, bool deviceOut, const OutSpec* qspec = nullptr) {
   if (!sc || !o || !fb) return fail(NRT_ERR_INVALID, "null scene, options or framebuffer");
+  if (qspec && (qspec->bits < 1 || qspec->bits > 16)) return fail(NRT_ERR_INVALID, "bits must be in 1..16 (framebuf.nim:56)");
   if (o->width <= 0 || o->height <= 0) return fail(NRT_ERR_INVALID, "non-positive image size");
   if (!isPow2(step) || !isPow2(max_step) || max_step < step)
     return fail(NRT_ERR_UNSUPPORTED, "step and maxStep must be powers of two with maxStep >= step (renderer.nim:166-168)");
@@ -1434,8 +1465,13 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
         cudaEvent_t e; NRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         dc->laneDone.push_back(e);
       }
+      if (qspec) {
+        const int64_t need = npx * outBytesPerPixel(*qspec);
+        if (pd.qStageN < need) { be.dfree(pd.qStage); pd.qStage = static_cast<unsigned char*>(be.dalloc(size_t(need))); pd.qStageN = need; }
+        if (!qspec->rgba && qspec->srgb) cutPoints(dc, qspec->bits);
+      }
       if (!deviceOut) {
-        if (pd.fbStageN < npx * 3) {
+        if (!qspec && pd.fbStageN < npx * 3) {
           be.dfree(pd.fbStage);
           pd.fbStage = static_cast<float*>(be.dalloc(sizeof(float) * npx * 3));
           pd.fbStageN = npx * 3;
@@ -1466,6 +1502,13 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
       const std::vector<int32_t> rows = rowsFor(o->height, y0, y1, step, g_part_index * nd + di, nd * g_part_count, ln, nlanes);
       float* target = fb;
       int32_t *aObj = nullptr, *aTri = nullptr; double* aT = nullptr;
+      OutStage qs{};
+      if (qspec) {
+        qs.out = pd.qStage; qs.bits = qspec->bits; qs.srgb = qspec->srgb; qs.rgba = qspec->rgba; qs.alpha = qspec->alpha;
+        qs.thr = (!qspec->rgba && qspec->srgb) ? dc->thr[qspec->bits] : nullptr;
+      }
+      const size_t fbElem = qspec ? size_t(outBytesPerPixel(*qspec)) : 3 * sizeof(float);
+      void* const fbDev = qspec ? static_cast<void*>(pd.qStage) : static_cast<void*>(pd.fbStage);
       if (!deviceOut) {
         target = pd.fbStage;
         if (wantAov) { aObj = aov->obj_id ? pd.aovObj : nullptr; aTri = aov->tri_id ? pd.aovTri : nullptr; aT = aov->t_hit ? pd.aovT : nullptr; }
@@ -1498,7 +1541,7 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
           const int stride = (j < rows.size()) ? rows[j] - rows[i] : 0;
           while (stride > 0 && j < rows.size() && rows[j] - rows[j - 1] == stride && std::min(step, o->height - rows[j]) == fill) ++j;
           const size_t cnt = j - i;
-          one(fb, target, 3 * sizeof(float), size_t(rows[i]), stride, fill, cnt);
+          one(fb, fbDev, fbElem, size_t(rows[i]), stride, fill, cnt);
           if (aObj) one(aov->obj_id, aObj, sizeof(int32_t), size_t(rows[i]), stride, fill, cnt);
           if (aTri) one(aov->tri_id, aTri, sizeof(int32_t), size_t(rows[i]), stride, fill, cnt);
           if (aT) one(aov->t_hit, aT, sizeof(double), size_t(rows[i]), stride, fill, cnt);
@@ -1508,7 +1551,7 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
       // Progressive passes leave some pixels of the touched rows untouched (renderer.nim:175-178,
       // and AOVs exist only at rendered pixels): round-trip the caller's current content.
       if (!deviceOut && (step > 1 || step < max_step)) copyRows(false);
-      rc[unit] = pd.rn[ln].render(pd.sd, *o, rows, step, max_step, target, aObj, aTri, aT, st[unit].data(), errs[unit]);
+      rc[unit] = pd.rn[ln].render(pd.sd, *o, rows, step, max_step, target, aObj, aTri, aT, st[unit].data(), errs[unit], qspec ? &qs : nullptr);
       if (rc[unit] == NRT_OK && !deviceOut) copyRows(true);
       if (ln > 0) NRT_CUDA(cudaEventRecord(dc->laneDone[size_t(ln - 1)], be.stream));
       NRT_CUDA(cudaStreamSynchronize(be.stream));
@@ -1621,6 +1664,9 @@ void nrt_shutdown(void) {
     if (d->tb0) cudaEventDestroy(d->tb0);
     if (d->tb1) cudaEventDestroy(d->tb1);
     for (auto e : d->laneDone) cudaEventDestroy(e);
+    for (auto*& t : d->thr) { if (t) cudaFree(t); t = nullptr; }
+    if (d->outFb) cudaFree(d->outFb);
+    if (d->outQ) cudaFree(d->outQ);
     for (auto* b : d->extra) { b->destroy(); delete b; }
     d->be.destroy();
     delete d;
@@ -1688,7 +1734,7 @@ void nrt_scene_destroy(nrt_scene* scene) {
     CudaBackend& be = g_devs[d]->be;
     pd.sd.destroy();
     for (int k = 0; k < kMaxLanes; ++k) if (pd.rn[k].be) pd.rn[k].freeAll();
-    be.dfree(pd.fbStage); be.dfree(pd.aovObj); be.dfree(pd.aovTri); be.dfree(pd.aovT);
+    be.dfree(pd.fbStage); be.dfree(pd.qStage); be.dfree(pd.aovObj); be.dfree(pd.aovTri); be.dfree(pd.aovT);
   }
   delete scene;
 }
@@ -1724,37 +1770,67 @@ int nrt_get_profile(const nrt_scene* scene, nrt_profile* out) {
   return NRT_OK;
 }
 
-static int quantizeImpl(const float* fb_host, int width, int height, int bits, int srgb, void* out, bool rgba, unsigned char alpha) {
-  if (!fb_host || !out || width <= 0 || height <= 0 || bits < 1 || bits > 16) return fail(NRT_ERR_INVALID, "bad argument");
+int nrt_output_cut_points(int bits, float* thr_host) {
+  if (bits < 1 || bits > 16 || !thr_host) return fail(NRT_ERR_INVALID, "bad argument");
+  std::vector<float> t;
+  if (!buildCutPoints(bits, t)) return fail(NRT_ERR_UNSUPPORTED, "powf is not monotonic around a cut point on this host");
+  std::memcpy(thr_host, t.data(), sizeof(float) * t.size());
+  return NRT_OK;
+}
+
+int nrt_render_quantized(nrt_scene* scene, const nrt_options* opts, int y0, int y1, int step, int max_step,
+                         int format, int bits, int srgb, int alpha, void* image, nrt_stats* stats) {
+  if (format != NRT_OUT_RGB && format != NRT_OUT_RGBA8) return fail(NRT_ERR_INVALID, "bad output format");
+  const OutSpec q{format == NRT_OUT_RGBA8 ? 8 : bits, format == NRT_OUT_RGBA8 ? 0 : (srgb != 0), format == NRT_OUT_RGBA8, alpha & 0xFF};
+  return renderImpl(scene, opts, y0, y1, step, max_step, static_cast<float*>(image), stats, nullptr, false, &q);
+}
+
+// fb / out: device pointers when `device`, else host memory staged through grow-only device buffers
+static int quantizeImpl(const float* fb, int width, int height, int bits, int srgb, void* out, bool rgba, unsigned char alpha, bool device) {
+  if (!fb || !out || width <= 0 || height <= 0 || bits < 1 || bits > 16) return fail(NRT_ERR_INVALID, "bad argument");
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_devs.empty()) return fail(NRT_ERR_NOT_INIT, "nrt_init() has not been called");
-  CudaBackend& be = g_devs[0]->be;
+  DeviceCtx* dc = g_devs[0];
+  CudaBackend& be = dc->be;
   const int64_t npix = int64_t(width) * height, n = npix * 3;
-  const int64_t outBytes = rgba ? npix * 4 : n * (bits <= 8 ? 1 : 2);
-  float* d = nullptr; unsigned char* o = nullptr;
+  const OutSpec spec{bits, srgb != 0, rgba, alpha};
+  const int64_t outBytes = npix * outBytesPerPixel(spec);
   try {
-    d = static_cast<float*>(be.dalloc(n * sizeof(float)));
-    o = static_cast<unsigned char*>(be.dalloc(size_t(outBytes)));
-    be.upload(d, fb_host, n * sizeof(float));
-    if (rgba) k_rgba8<<<CudaBackend::blocksFor(npix), kBlock, 0, be.stream>>>(d, o, npix, alpha);
-    else k_quantize<<<CudaBackend::blocksFor(n), kBlock, 0, be.stream>>>(d, o, n, srgb, bits);
+    be.use();
+    OutStage q{};
+    q.bits = bits; q.srgb = srgb != 0; q.rgba = rgba; q.alpha = alpha;
+    q.thr = (!rgba && srgb) ? cutPoints(dc, bits) : nullptr;
+    const float* src = fb;
+    if (device) q.out = static_cast<unsigned char*>(out);
+    else {
+      if (dc->outFbN < n) { be.dfree(dc->outFb); dc->outFb = static_cast<float*>(be.dalloc(size_t(n) * sizeof(float))); dc->outFbN = n; }
+      if (dc->outQN < outBytes) { be.dfree(dc->outQ); dc->outQ = static_cast<unsigned char*>(be.dalloc(size_t(outBytes))); dc->outQN = outBytes; }
+      be.upload(dc->outFb, fb, size_t(n) * sizeof(float));
+      src = dc->outFb; q.out = dc->outQ;
+    }
+    k_out_stage<<<CudaBackend::blocksFor(npix), kBlock, 0, be.stream>>>(src, q, npix);
     NRT_CUDA(cudaGetLastError());
-    be.download(out, o, size_t(outBytes));
+    if (device) be.sync();
+    else be.download(out, dc->outQ, size_t(outBytes));
   } catch (const std::exception& ex) {
-    be.dfree(d); be.dfree(o);
     return fail(NRT_ERR_CUDA, ex.what());
   }
-  be.dfree(d); be.dfree(o);
   return NRT_OK;
 }
 int nrt_framebuf_to_srgb8(const float* fb_host, int width, int height, int srgb, unsigned char* rgb8) {
-  return quantizeImpl(fb_host, width, height, 8, srgb, rgb8, false, 0);
+  return quantizeImpl(fb_host, width, height, 8, srgb, rgb8, false, 0, false);
 }
 int nrt_framebuf_quantize(const float* fb_host, int width, int height, int bits, int srgb, void* out) {
-  return quantizeImpl(fb_host, width, height, bits, srgb, out, false, 0);
+  return quantizeImpl(fb_host, width, height, bits, srgb, out, false, 0, false);
 }
 int nrt_framebuf_to_rgba8(const float* fb_host, int width, int height, unsigned char alpha, unsigned char* rgba8) {
-  return quantizeImpl(fb_host, width, height, 8, 0, rgba8, true, alpha);
+  return quantizeImpl(fb_host, width, height, 8, 0, rgba8, true, alpha, false);
+}
+int nrt_framebuf_quantize_device(const float* fb_dev, int width, int height, int bits, int srgb, void* out_dev) {
+  return quantizeImpl(fb_dev, width, height, bits, srgb, out_dev, false, 0, true);
+}
+int nrt_framebuf_to_rgba8_device(const float* fb_dev, int width, int height, unsigned char alpha, unsigned char* rgba8_dev) {
+  return quantizeImpl(fb_dev, width, height, 8, 0, rgba8_dev, true, alpha, true);
 }
 
 #define NRT_NEED_DEV0()                                                               \
@@ -1777,6 +1853,12 @@ int nrt_device_memset(void* dev_ptr, int value, int64_t bytes) {
   NRT_NEED_DEV0();
   try { be.use(); NRT_CUDA(cudaMemsetAsync(dev_ptr, value, size_t(bytes), be.stream)); be.sync(); }
   catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
+  return NRT_OK;
+}
+int nrt_copy_to_device(void* dev_dst, const void* host_src, int64_t bytes) {
+  if (!dev_dst || !host_src || bytes < 0) return fail(NRT_ERR_INVALID, "bad argument");
+  NRT_NEED_DEV0();
+  try { be.upload(dev_dst, host_src, size_t(bytes)); be.sync(); } catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
   return NRT_OK;
 }
 int nrt_copy_to_host(void* host_dst, const void* dev_src, int64_t bytes) {

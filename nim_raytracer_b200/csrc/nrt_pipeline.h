@@ -57,6 +57,61 @@ struct FrameParams {
   double inv_grid;         // 1.0 / double(grid)               (sampling.nim:6-7)
 };
 
+// ---- output stage: the reference's float32 -> integer sample conversions -------------
+//   writePpm's outvalue   utils/framebuf.nim:74-78: clamp(v, 0, 1) -> linearToSRGB (utils/color.nim:17-22) ->
+//                         Natural(round(c * maxval)), maxval = float32(2^bits - 1); 8-bit samples for bits <= 8,
+//                         big-endian 16-bit above (framebuf.nim:67-71)
+//   ImageRGBA.copyFrom    utils/image.nim:45-54: round(v * 0xff).uint8 per channel + a constant alpha
+// Byte work must equal the reference's bit for bit.  Everything except the pow() of linearToSRGB is a handful of
+// exactly rounded float32 operations, evaluated here as written.  For the pow branch the library builds, on the host
+// with the SAME libm call the reference's C back-end makes (powf), the table of cut points
+//   thr[k - 1] = the smallest float32 input in (0.0031308, 1] whose sample is >= k,   k = 1 .. maxval
+// (the conversion is monotonic; nrt.cu verifies that around every cut point) and the device counts the cut points
+// <= v with a binary search: exact by construction, no device pow.  NaN samples (Natural(NaN) is undefined in the
+// reference) are defined as 0.
+struct OutStage {
+  unsigned char* out;     // null: no integer output
+  const float* thr;       // cut points of the sRGB pow branch for `bits` (device), maxval entries
+  int32_t bits, srgb;     // RGB samples: bits in 1..16
+  int32_t rgba, alpha;    // rgba != 0: ImageRGBA bytes (r, g, b, alpha) instead
+};
+NRT_HD uint32_t outvalueQ(float v, int bits, int srgb, const float* thr) {
+  if (v != v) return 0u;
+  const float c = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+  const uint32_t maxv = (1u << bits) - 1u;
+  const float maxval = float(maxv);
+  if (!srgb) return uint32_t(roundf(c * maxval));
+  if (c <= 0.0031308f) return uint32_t(roundf((12.92f * c) * maxval));
+  uint32_t lo = 0, hi = maxv;          // number of cut points <= c
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (thr[mid] <= c) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+NRT_HD unsigned char rgbaByteQ(float v) {
+  const float r = roundf(v * 255.0f);
+  return (unsigned char)(r != r ? 0.0f : (r < 0.0f ? 0.0f : (r > 255.0f ? 255.0f : r)));
+}
+// pixel `pi` of an integer image
+NRT_HD void storeQ(const OutStage& q, int64_t pi, float r, float g, float b) {
+  if (q.rgba) {
+    unsigned char* p = q.out + 4 * pi;
+    p[0] = rgbaByteQ(r); p[1] = rgbaByteQ(g); p[2] = rgbaByteQ(b); p[3] = (unsigned char)q.alpha;
+    return;
+  }
+  const uint32_t vr = outvalueQ(r, q.bits, q.srgb, q.thr), vg = outvalueQ(g, q.bits, q.srgb, q.thr), vb = outvalueQ(b, q.bits, q.srgb, q.thr);
+  if (q.bits <= 8) {
+    unsigned char* p = q.out + 3 * pi;
+    p[0] = (unsigned char)vr; p[1] = (unsigned char)vg; p[2] = (unsigned char)vb;
+  } else {
+    unsigned char* p = q.out + 6 * pi;
+    p[0] = (unsigned char)(vr >> 8); p[1] = (unsigned char)(vr & 0xFFu);
+    p[2] = (unsigned char)(vg >> 8); p[3] = (unsigned char)(vg & 0xFFu);
+    p[4] = (unsigned char)(vb >> 8); p[5] = (unsigned char)(vb & 0xFFu);
+  }
+}
+
 // Device-resident state of one chunk of samples (component-major SoA).
 struct ChunkState {
   int64_t S;         // sample capacity
@@ -116,6 +171,7 @@ struct ChunkState {
   int64_t p0;          // first pixel (in the worker's pixel list) of this chunk
   int64_t npix;        // pixels in this chunk
   // outputs
+  OutStage q;          // q.out != null: Finalize stores writePpm / ImageRGBA samples there instead of floats into fb
   float* fb;           // width*height*3 (may be peer memory)
   int32_t* aovObj;     // may be null
   int32_t* aovTri;
@@ -1311,7 +1367,9 @@ struct Finalize {
     const int y1 = (fp.step > 1) ? (y + fp.step < fp.height ? y + fp.step : fp.height) : y + 1;
     for (int j = y; j < y1; ++j)
       for (int i = x; i < x1; ++i) {
-        float* p = cs.fb + (int64_t(j) * fp.width + i) * 3;
+        const int64_t pi = int64_t(j) * fp.width + i;
+        if (cs.q.out) { storeQ(cs.q, pi, fr, fg, fbv); continue; }   // output stage fused into the pixel store
+        float* p = cs.fb + pi * 3;
         p[0] = fr; p[1] = fg; p[2] = fbv;
       }
   }

@@ -628,7 +628,8 @@ struct Renderer {
 
   // Renders the rows `rows` (already filtered by step) of one worker.
   int render(const SceneData<BE>& sd, const nrt_options& o, const std::vector<int32_t>& rows, int step, int max_step,
-             float* fb, int32_t* aovObj, int32_t* aovTri, double* aovT, unsigned long long* statsOut, std::string& err) {
+             float* fb, int32_t* aovObj, int32_t* aovTri, double* aovT, unsigned long long* statsOut, std::string& err,
+             const OutStage* qout = nullptr) {
     FrameParams fp{};
     fp.width = o.width; fp.height = o.height; fp.aa_kind = o.aa_kind;
     fp.grid = o.aa_kind == NRT_AA_NONE ? 1 : o.grid_size;
@@ -682,6 +683,7 @@ struct Renderer {
     for (int attempt = 0;; ++attempt) {
       ensure(S, nL, nMO, waves, cand, int(rows.size()), pairsReq);
       cs.fb = fb; cs.aovObj = aovObj; cs.aovTri = aovTri; cs.aovT = aovT;
+      cs.q = qout ? *qout : OutStage{};
       be->upload(dRows, rows.data(), sizeof(int32_t) * rows.size());
       preLog.clear();
       bool overflow = false;

@@ -143,3 +143,33 @@ def samples(kind, m, seed=0, width=1, x=0, y=0):
     out = np.zeros(2 * m * m)
     lib().oracle_samples(kind, m, seed, width, x, y, out.ctypes.data_as(C.POINTER(C.c_double)))
     return out.reshape(m * m, 2)
+
+
+def outvalues(fb_data: np.ndarray, bits: int = 8, sRGB: bool = True) -> np.ndarray:
+    """writePpm's samples (utils/framebuf.nim:74-89) of float32 components: uint8, or big-endian uint16 above 8 bits."""
+    a = np.ascontiguousarray(fb_data, dtype=np.float32).reshape(-1)
+    out = np.zeros(a.size * (1 if bits <= 8 else 2), dtype=np.uint8)
+    L = lib()
+    L.oracle_outvalues.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
+    L.oracle_outvalues.restype = None
+    L.oracle_outvalues(a.ctypes.data_as(C.c_void_p), a.size, bits, int(sRGB), out.ctypes.data_as(C.c_void_p))
+    return out if bits <= 8 else out.view(">u2")
+
+
+def rgba8(fb_data: np.ndarray, alpha: int = 0xFF) -> np.ndarray:
+    """ImageRGBA.copyFrom (utils/image.nim:45-54)."""
+    a = np.ascontiguousarray(fb_data, dtype=np.float32).reshape(-1)
+    out = np.zeros(a.size // 3 * 4, dtype=np.uint8)
+    L = lib()
+    L.oracle_rgba8.argtypes = [C.c_void_p, C.c_int64, C.c_ubyte, C.c_void_p]
+    L.oracle_rgba8.restype = None
+    L.oracle_rgba8(a.ctypes.data_as(C.c_void_p), a.size // 3, alpha, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def write_ppm(fb, filename: str, bits: int = 8, sRGB: bool = True) -> bool:
+    """utils/framebuf.nim:55-93: "P6 w h maxval " + the samples."""
+    with open(filename, "wb") as f:
+        f.write(f"P6 {fb.w} {fb.h} {(1 << bits) - 1} ".encode())
+        f.write(outvalues(fb.data, bits, sRGB).tobytes())
+    return True

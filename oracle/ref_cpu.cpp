@@ -629,4 +629,44 @@ void oracle_samples(int kind, int m, uint64_t seed, int width, int x, int y, dou
   std::memcpy(out, p.data(), p.size() * sizeof(double));
 }
 
+// ---- output stage --------------------------------------------------------------
+// utils/color.nim:17-22 linearToSRGB(v: float32): `let a = 0.055` is a float64, the literals 12.92 and 1/2.4 take
+// the float32 type of `v` (pow -> powf), the affine part is evaluated in float64 and narrowed to the float32
+// result.  (Nim's float32 / float64 conversions are implicit both ways; which overload a mixed expression picks
+// cannot be checked without a Nim compiler: this reading is the frozen one, "parity unpinned" like glm.)
+static float linearToSRGB(float v) {
+  const double a = 0.055;
+  if (v <= 0.0031308f) return 12.92f * v;
+  return float((1 + a) * double(powf(v, float(1 / 2.4))) - a);
+}
+// utils/framebuf.nim:74-78 outvalue: clamp(v, 0.0, 1.0) -> linearToSRGB -> Natural(round(c * maxval)), maxval =
+// float32(2^bits - 1).  Nim's clamp lets NaN through and Natural(NaN) is undefined: defined as 0 here (and in the product).
+static uint32_t outvalue(float v, int bits, int srgb) {
+  const float maxval = float((1u << bits) - 1u);
+  if (v != v) return 0;
+  float c = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+  if (srgb) c = linearToSRGB(c);
+  return uint32_t(roundf(c * maxval));
+}
+// writePpm's sample stream (framebuf.nim:80-89): n float32 components -> n uint8 (bits <= 8) or n big-endian
+// uint16 (framebuf.nim:67-71)
+void oracle_outvalues(const float* fb, int64_t n, int bits, int srgb, unsigned char* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t v = outvalue(fb[i], bits, srgb);
+    if (bits <= 8) out[i] = (unsigned char)v;
+    else { out[2 * i] = (unsigned char)(v >> 8); out[2 * i + 1] = (unsigned char)(v & 0xFFu); }
+  }
+}
+// utils/image.nim:45-54 ImageRGBA.copyFrom: round(v * 0xff).uint8 per channel + alpha.  The float -> uint8
+// conversion is undefined outside 0..255 in the reference: clamped here (and in the product); NaN -> 0.
+void oracle_rgba8(const float* fb, int64_t npix, unsigned char alpha, unsigned char* out) {
+  for (int64_t p = 0; p < npix; ++p) {
+    for (int k = 0; k < 3; ++k) {
+      const float r = roundf(fb[3 * p + k] * 255.0f);
+      out[4 * p + k] = (unsigned char)(r != r ? 0.0f : (r < 0.0f ? 0.0f : (r > 255.0f ? 255.0f : r)));
+    }
+    out[4 * p + 3] = alpha;
+  }
+}
+
 }  // extern "C"
