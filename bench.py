@@ -311,7 +311,7 @@ def main():
         target = peer.ptr if peer is not None else C.c_void_p(local_t.data_ptr())
         api.check(L.nrt_render_device(ds.handle, C.byref(co), 0, H, 1, 1, target, C.byref(cs), None), "nrt_render_device")
         if peer is None and world > 1:
-            return D.gather_rows(local_t, rank, world, dist)
+            return D.gather_rows(local_t, rank, world, dist, band=api.bandRows(opts))
         return None
 
     # ---- device-resident throughput ------------------------------------------------

@@ -208,7 +208,12 @@ int nrt_abi_version(void);
  * nrt_render* call; other pixels are left untouched.  Default (0,1).
  * Reference counterpart: the per-scanline work items of raytracer.nim:67-70. */
 int nrt_set_partition(int index, int count);
-int nrt_band_rows(void);
+int nrt_band_rows(void);   /* 1: the band height of progressive passes (kept for ABI v1 callers) */
+/* Band height T of a pass with these options: whole-resolution passes (step == max_step == 1) deal the image out in
+ * bands of T scanlines — rows of T x T screen-space tiles, enumerated tile by tile inside a band — where T is the
+ * largest power of two with T*T*spp <= 256 (16 spp: 4); partition `index` renders the bands index, index + count, ...
+ * counted from y0.  Progressive passes: 1. */
+int nrt_band_rows_for(const nrt_options* opts, int step, int max_step);
 
 /* Deep-copies and flattens a Scene (scene.nim:13-18) to every selected GPU:
  * replaces building `Scene`/`Object`/`TriangleMesh` refs that renderLine reads

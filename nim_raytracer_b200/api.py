@@ -569,6 +569,15 @@ def framebufToRgba8(fb: Framebuf, alpha: int = 0xFF) -> np.ndarray:
 NRT_OUT_RGB, NRT_OUT_RGBA8 = 0, 1
 
 
+def bandRows(opts: "Options", step: int = 1, maxStep: int = 1) -> int:
+    """Band height T of a pass (nrt_band_rows_for): whole-resolution passes are dealt out in bands of T scanlines
+    (rows of T x T tiles); progressive passes in single scanlines."""
+    L = lib()
+    L.nrt_band_rows_for.argtypes = [C.POINTER(nrt_options), C.c_int, C.c_int]
+    co = opts.to_c()
+    return int(L.nrt_band_rows_for(C.byref(co), step, maxStep))
+
+
 def outputCutPoints(bits: int = 8) -> np.ndarray:
     """The cut-point table of the sRGB pow branch for `bits` (host computation inside libnrt.so; no GPU needed)."""
     out = np.zeros((1 << bits) - 1, dtype=np.float32)

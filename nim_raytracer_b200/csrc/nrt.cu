@@ -42,9 +42,12 @@
 #ifndef NRT_OCC_SHADE
 #define NRT_OCC_SHADE 0
 #endif
-// FusedBounce (a whole bounce of a sample in registers) / PathTail, PathMega: the compiler's choice unless set
+// FusedBounce (a whole bounce of a sample in registers).  Measured on B200, config 4 (all launches of a frame): the
+// compiler's choice, 126 registers without spills (2 CTAs/SM), 13.06 ms; 3 CTAs/SM = 80 registers with ~300 bytes of
+// spills 11.77 ms; 4 CTAs/SM = 64 registers 12.25 ms.  The kernel waits on fixed-latency float64 chains: warps in
+// flight are worth more than the spills cost.
 #ifndef NRT_OCC_FUSED
-#define NRT_OCC_FUSED 0
+#define NRT_OCC_FUSED 3
 #endif
 #ifndef NRT_OCC_TAIL
 #define NRT_OCC_TAIL 1
@@ -1407,11 +1410,14 @@ static int64_t outBytesPerPixel(const OutSpec& q) { return q.rgba ? 4 : (q.bits 
 // partition `part`: i % nparts == part (scanline interleave over the GPUs / ranks: the reference's work items,
 // raytracer.nim:67-70; counted among the RENDERED rows, so a progressive pass with step >= nparts still spreads
 // over every GPU), and among a partition's rows every nlanes-th goes to the same lane.
-static std::vector<int32_t> rowsFor(int height, int y0, int y1, int step, int part, int nparts, int lane, int nlanes) {
+// With T > 1 (tile order, step == 1) the units dealt out are BANDS of T scanlines — rows of T x T tiles; the vector
+// holds their first rows.
+static std::vector<int32_t> rowsFor(int height, int y0, int y1, int step, int part, int nparts, int lane, int nlanes, int T = 1) {
   std::vector<int32_t> r;
+  const int unit = step * T;
   for (int y = std::max(0, y0); y < std::min(y1, height); ++y) {
-    if ((y - y0) % step != 0) continue;
-    const int i = (y - y0) / step;
+    if ((y - y0) % unit != 0) continue;
+    const int i = (y - y0) / unit;
     if (i % nparts == part && (i / nparts) % nlanes == lane) r.push_back(y);
   }
   return r;
@@ -1444,6 +1450,8 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     if (g_devs[0]->be.timing) nlanes = 1;
   }
   nlanes = std::max(1, std::min(nlanes, kMaxLanes));
+  const int tshift = tileShiftFor(*o, step, max_step), T = 1 << tshift;   // T > 1: bands of T scanlines, tile order inside
+  const int yEnd = std::min(y1, o->height);
   const int nunits = nd * nlanes;
   std::vector<int> rc(nunits, NRT_OK);
   std::vector<std::string> errs(nunits);
@@ -1499,7 +1507,7 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     pd.rn[ln].be = &be;
     try {
       be.use();
-      const std::vector<int32_t> rows = rowsFor(o->height, y0, y1, step, g_part_index * nd + di, nd * g_part_count, ln, nlanes);
+      const std::vector<int32_t> rows = rowsFor(o->height, y0, y1, step, g_part_index * nd + di, nd * g_part_count, ln, nlanes, T);
       float* target = fb;
       int32_t *aObj = nullptr, *aTri = nullptr; double* aT = nullptr;
       OutStage qs{};
@@ -1537,9 +1545,11 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
         size_t i = 0;
         while (i < rows.size()) {
           size_t j = i + 1;
-          const int fill = std::min(step, o->height - rows[i]);
+          // rows a unit covers: its step x step fill block (progressive) or its band of T scanlines, clipped
+          auto fillOf = [&](int row) { return T > 1 ? std::min(T, yEnd - row) : std::min(step, o->height - row); };
+          const int fill = fillOf(rows[i]);
           const int stride = (j < rows.size()) ? rows[j] - rows[i] : 0;
-          while (stride > 0 && j < rows.size() && rows[j] - rows[j - 1] == stride && std::min(step, o->height - rows[j]) == fill) ++j;
+          while (stride > 0 && j < rows.size() && rows[j] - rows[j - 1] == stride && fillOf(rows[j]) == fill) ++j;
           const size_t cnt = j - i;
           one(fb, fbDev, fbElem, size_t(rows[i]), stride, fill, cnt);
           if (aObj) one(aov->obj_id, aObj, sizeof(int32_t), size_t(rows[i]), stride, fill, cnt);
@@ -1551,7 +1561,7 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
       // Progressive passes leave some pixels of the touched rows untouched (renderer.nim:175-178,
       // and AOVs exist only at rendered pixels): round-trip the caller's current content.
       if (!deviceOut && (step > 1 || step < max_step)) copyRows(false);
-      rc[unit] = pd.rn[ln].render(pd.sd, *o, rows, step, max_step, target, aObj, aTri, aT, st[unit].data(), errs[unit], qspec ? &qs : nullptr);
+      rc[unit] = pd.rn[ln].render(pd.sd, *o, rows, step, max_step, target, aObj, aTri, aT, st[unit].data(), errs[unit], qspec ? &qs : nullptr, tshift, yEnd);
       if (rc[unit] == NRT_OK && !deviceOut) copyRows(true);
       if (ln > 0) NRT_CUDA(cudaEventRecord(dc->laneDone[size_t(ln - 1)], be.stream));
       NRT_CUDA(cudaStreamSynchronize(be.stream));
@@ -1649,6 +1659,7 @@ extern "C" {
 int nrt_abi_version(void) { return NRT_ABI_VERSION; }
 const char* nrt_last_error(void) { return g_err.c_str(); }
 int nrt_band_rows(void) { return 1; }
+int nrt_band_rows_for(const nrt_options* opts, int step, int max_step) { return opts ? (1 << tileShiftFor(*opts, step, max_step)) : 1; }
 
 int nrt_init(int ngpu, const int* dev_ids) {
   std::lock_guard<std::mutex> lk(g_mu);

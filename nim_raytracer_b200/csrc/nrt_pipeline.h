@@ -50,7 +50,14 @@ struct FrameParams {
   int32_t step, max_step;
   int32_t depth_mode, max_ray_depth, bounce_cap;
   int32_t nx;              // x positions per row = ceil(width / step)
-  int32_t _pad;
+  // Pixel order of a worker's samples.  tshift == 0: scanline by scanline (cs.rows = the rows).  tshift > 0
+  // (whole-resolution passes): cs.rows are the first rows of BANDS of T = 2^tshift scanlines, and inside a band
+  // the pixels are enumerated tile by tile (T x T pixels, left to right; row-major inside a tile) — so that the 256
+  // consecutive queue entries one prefilter warp works on are a compact 2-D patch of the image (4 x 4 pixels x 16
+  // samples) instead of a 16 x 1 strip: smaller patches admit fewer chunks and sub-chunks of the mesh.
+  int32_t tshift;
+  int32_t band_pix;        // pixel slots per band = ceil(width / T) * T * T (slots right of the image are dead)
+  int32_t y_end;           // rows >= y_end are dead (a band clipped by the end of the requested range)
   double bias;
   uint64_t seed;
   double aspect;           // double(width) / double(height)   (renderer.nim:36), the same division done once on the host
@@ -208,11 +215,20 @@ NRT_HD int64_t divFast(int64_t a, int32_t b) {
   return ((uint64_t(a) >> 32) == 0) ? int64_t(uint32_t(a) / uint32_t(b)) : a / b;
 }
 NRT_HD void pixelOf(const FrameParams& fp, const ChunkState& cs, int64_t p, int& x, int& y) {
+  if (fp.tshift > 0) {
+    const int64_t u = divFast(p, fp.band_pix);
+    const int32_t r = int32_t(p - u * fp.band_pix);
+    const int tt = 2 * fp.tshift, q = r & ((1 << tt) - 1);
+    x = ((r >> tt) << fp.tshift) + (q & ((1 << fp.tshift) - 1));
+    y = cs.rows[u] + (q >> fp.tshift);
+    return;
+  }
   const int64_t ri = divFast(p, fp.nx);
   x = int(p - ri * fp.nx) * fp.step;
   y = cs.rows[ri];
 }
 NRT_HD bool pixelSkipped(const FrameParams& fp, int x, int y) {  // renderer.nim:175-178
+  if (x >= fp.width || y >= fp.y_end) return true;   // dead slot of a tile that overlaps the edge of the image / of the range
   if (fp.step < fp.max_step) {
     const int mask = fp.step * 2 - 1;
     if (((x & mask) == 0) && ((y & mask) == 0)) return true;

@@ -26,6 +26,21 @@ struct ProfileAcc {
 
 inline bool isPow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// log2 of the tile edge T of a pass (FrameParams::tshift): whole-resolution passes use the largest power of two
+// with T * T * spp <= 256 (one prefilter run = one tile where the numbers allow: 16 spp -> 4 x 4 pixels), capped
+// at 16; progressive passes (step > 1 or pixels to skip) keep scanline order.  NRT_TILE overrides (1 = scanlines).
+inline int tileShiftFor(const nrt_options& o, int step, int max_step) {
+  if (step != 1 || max_step != 1) return 0;
+  const int spp = o.aa_kind == NRT_AA_NONE ? 1 : o.grid_size * o.grid_size;
+  int t = 0;
+  while (t < 4 && (int64_t(1) << (2 * (t + 1))) * spp <= 256) ++t;
+  if (const char* e = std::getenv("NRT_TILE")) {
+    const int v = std::atoi(e);
+    if (v >= 1 && v <= 64 && isPow2(v)) { t = 0; while ((1 << t) < v) ++t; }
+  }
+  return t;
+}
+
 // ------------------------------------------------------------------ scene ----
 template <class BE>
 struct SceneData {
@@ -629,7 +644,7 @@ struct Renderer {
   // Renders the rows `rows` (already filtered by step) of one worker.
   int render(const SceneData<BE>& sd, const nrt_options& o, const std::vector<int32_t>& rows, int step, int max_step,
              float* fb, int32_t* aovObj, int32_t* aovTri, double* aovT, unsigned long long* statsOut, std::string& err,
-             const OutStage* qout = nullptr) {
+             const OutStage* qout = nullptr, int tshift = 0, int yEnd = -1) {
     FrameParams fp{};
     fp.width = o.width; fp.height = o.height; fp.aa_kind = o.aa_kind;
     fp.grid = o.aa_kind == NRT_AA_NONE ? 1 : o.grid_size;
@@ -638,6 +653,9 @@ struct Renderer {
     fp.depth_mode = o.depth_mode; fp.max_ray_depth = o.max_ray_depth;
     fp.bounce_cap = o.bounce_cap > 0 ? o.bounce_cap : 64;
     fp.nx = (o.width + step - 1) / step;
+    fp.tshift = tshift;                       // > 0: `rows` are the first rows of bands of T scanlines (tile order inside)
+    fp.band_pix = tshift > 0 ? (((o.width + (1 << tshift) - 1) >> tshift) << (2 * tshift)) : fp.nx;
+    fp.y_end = (yEnd < 0 || yEnd > o.height) ? o.height : yEnd;
     fp.bias = o.bias; fp.seed = o.seed;
     fp.aspect = double(o.width) / double(o.height);
     fp.inv_grid = 1.0 / double(fp.grid);
@@ -653,7 +671,7 @@ struct Renderer {
     int maxBounces = sd.anyReflective ? fp.bounce_cap : 0;
     if (sd.anyReflective && o.depth_mode == NRT_DEPTH_INTENDED) maxBounces = std::min(maxBounces, std::max(0, o.max_ray_depth));
     const int waves = 2 * (maxBounces + 1);
-    const int64_t npixTotal = int64_t(rows.size()) * fp.nx;
+    const int64_t npixTotal = int64_t(rows.size()) * fp.band_pix;
     // Samples per chunk: as many as fit in 96 GB or 60 % of the free device memory (~470 B of state per
     // sample for one mesh object and two lights; a 3840x2160x16 frame is ONE chunk of 62 GB on a 180 GB
     // B200).  Every bounce costs ~25 launches and a host check whatever the chunk size, so large chunks pay.

@@ -30,23 +30,33 @@ from typing import List, Optional
 import numpy as np
 
 
-def rows_of(rank: int, world: int, height: int, y0: int = 0, y1: Optional[int] = None, step: int = 1) -> List[int]:
-    """Scanlines of [y0, y1) with (y - y0) mod step == 0 owned by `rank` (csrc/nrt.cu: rowsFor): the rendered
-    rows are numbered i = (y - y0) / step and dealt out round-robin, so a progressive pass with step >= world
-    still uses every rank.  For whole frames (y0 = 0, step = 1) this is y mod world == rank."""
+def rows_of(rank: int, world: int, height: int, y0: int = 0, y1: Optional[int] = None, step: int = 1, band: int = 1) -> List[int]:
+    """First rows of the units of [y0, y1) owned by `rank` (csrc/nrt.cu: rowsFor).  A unit is a rendered scanline
+    of a progressive pass ((y - y0) mod step == 0; band == 1) or a band of `band` scanlines of a whole-resolution
+    pass (step == 1; band = api.bandRows(opts): rows of T x T tiles).  Units are numbered from y0 and dealt out
+    round-robin, so a progressive pass with step >= world still uses every rank.  For whole frames in scanline
+    order (y0 = 0, step = band = 1) this is y mod world == rank."""
     y1 = height if y1 is None else y1
-    return [y for y in range(max(0, y0), min(y1, height)) if (y - y0) % step == 0 and ((y - y0) // step) % world == rank]
+    unit = step * band
+    return [y for y in range(max(0, y0), min(y1, height)) if (y - y0) % unit == 0 and ((y - y0) // unit) % world == rank]
 
 
-def merge_rows(dst: np.ndarray, src: np.ndarray, rank: int, world: int) -> None:
+def owned_rows(rank: int, world: int, height: int, band: int = 1) -> np.ndarray:
+    """Every scanline of a whole frame that `rank` renders: the bands rank, rank + world, ... of `band` rows."""
+    y = np.arange(height)
+    return y[(y // band) % world == rank]
+
+
+def merge_rows(dst: np.ndarray, src: np.ndarray, rank: int, world: int, band: int = 1) -> None:
     """Copies the rows owned by `rank` from a full-size (H, ...) buffer into dst."""
-    dst[rank::world] = src[rank::world]
+    rows = owned_rows(rank, world, dst.shape[0], band)
+    dst[rows] = src[rows]
 
 
-def gather_rows(local, rank: int, world: int, dist=None, group=None, dst: int = 0):
-    """Gathers the row-interleaved pieces of a (H, W, C) torch tensor on rank `dst`.
+def gather_rows(local, rank: int, world: int, dist=None, group=None, dst: int = 0, band: int = 1):
+    """Gathers the band-interleaved pieces of a (H, W, C) torch tensor on rank `dst`.
 
-    Every rank passes its full-size buffer of which only rows rank::world are
+    Every rank passes its full-size buffer of which only its own bands (owned_rows) are
     valid.  Works with any torch.distributed backend (nccl for CUDA tensors,
     gloo for CPU tensors).  Returns the assembled frame on `dst`, None elsewhere."""
     import torch
@@ -54,8 +64,9 @@ def gather_rows(local, rank: int, world: int, dist=None, group=None, dst: int = 
     if world == 1:
         return local
     H = local.shape[0]
-    per = (H + world - 1) // world
-    mine = local[rank::world]
+    idx = [torch.as_tensor(owned_rows(r, world, H, band), device=local.device) for r in range(world)]
+    per = max(int(i.numel()) for i in idx)
+    mine = local[idx[rank]]
     pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: mine.shape[0]] = mine
     bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
@@ -64,8 +75,7 @@ def gather_rows(local, rank: int, world: int, dist=None, group=None, dst: int = 
         return None
     out = torch.empty_like(local)
     for r in range(world):
-        n = out[r::world].shape[0]
-        out[r::world] = bufs[r][:n]
+        out[idx[r]] = bufs[r][: idx[r].numel()]
     return out
 
 

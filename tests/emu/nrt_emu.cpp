@@ -206,11 +206,12 @@ int emu_render(const nrt_scene_desc* desc, const nrt_options* o, int y0, int y1,
   Renderer<LoopBackend> rn;
   rn.be = &be;
   std::vector<int32_t> rows;
+  const int tshift = tileShiftFor(*o, step, max_step), T = 1 << tshift;   // T > 1: bands of T rows, tile order inside
   for (int y = std::max(0, y0); y < std::min(y1, o->height); ++y)
-    if ((y - y0) % step == 0) rows.push_back(y);
+    if ((y - y0) % (step * T) == 0) rows.push_back(y);
   unsigned long long st[ST_COUNT];
   rc = rn.render(sd, *o, rows, step, max_step, fb, aov ? aov->obj_id : nullptr, aov ? aov->tri_id : nullptr,
-                 aov ? aov->t_hit : nullptr, st, err);
+                 aov ? aov->t_hit : nullptr, st, err, nullptr, tshift, std::min(y1, o->height));
   if (rc != NRT_OK) std::fprintf(stderr, "emu: %s\n", err.c_str());
   if (stats) {
     stats->num_primary_rays = int64_t(st[ST_PRIMARY]);

@@ -24,15 +24,17 @@ def _worker(rank, world, port, out_path):
     sc, o = scenes.bunny(stride=32), api.Options(64, 37)      # odd height: ragged shards
     fb = api.newFramebuf(o.width, o.height)
     rays = 0
-    for y in D.rows_of(rank, world, o.height):
-        _, st, _, _ = emu.render(sc, o, fb=fb, y0=y, y1=y + 1)
+    band = api.bandRows(o)                                    # 1 spp: bands of 16 scanlines (rows of 16 x 16 tiles)
+    assert band == 16
+    for y in D.rows_of(rank, world, o.height, band=band):
+        _, st, _, _ = emu.render(sc, o, fb=fb, y0=y, y1=min(y + band, o.height))
         rays += st.numRays
     t = torch.from_numpy(fb.image().copy())
-    full = D.gather_rows(t, rank, world, dist)
+    full = D.gather_rows(t, rank, world, dist, band=band)
     # the same frame through the shared host framebuffer: every rank writes its own rows, no gather
     shared = D.SharedHostFramebuffer(o.width * o.height * 12, rank, world, dist, register=False)
     img = shared.array.reshape(o.height, o.width, 3)
-    D.merge_rows(img, fb.image(), rank, world)
+    D.merge_rows(img, fb.image(), rank, world, band=band)
     dist.barrier()
     if rank == 0:
         assert (img == full.numpy()).all()
@@ -73,3 +75,11 @@ def test_rows_partition_properties():
                 seen += D.rows_of(r, world, h, y0, y1, step)
             want = [y for y in range(max(0, y0), h if y1 is None else min(y1, h)) if (y - y0) % step == 0]
             assert sorted(seen) == want and len(set(seen)) == len(seen)
+        # whole-resolution passes: bands of T scanlines (rows of T x T tiles) dealt out round-robin
+        for (h, band) in ((2160, 4), (37, 16), (5, 2)):
+            starts = sorted(sum((D.rows_of(r, world, h, band=band) for r in range(world)), []))
+            assert starts == list(range(0, h, band))
+            cover = np.concatenate([D.owned_rows(r, world, h, band) for r in range(world)])
+            assert sorted(cover.tolist()) == list(range(h))
+            for r in range(world):
+                assert set(D.owned_rows(r, world, h, band).tolist()) == {y for s0 in D.rows_of(r, world, h, band=band) for y in range(s0, min(s0 + band, h))}
