@@ -177,6 +177,12 @@ struct DMesh {
   uint32_t* order;          // faces in Morton order of their centroids: record r <-> face order[r]
 };
 
+// float32 first look at the AABB gate of a mesh object (geom.nim:340) from the WORLD-space ray, for objects whose
+// worldToObject is exactly [I | t]: the bounding sphere of the mesh box moved to world space, c = centre - t
+// (object-space ray origin - centre = world origin - c), in the format and with the margins of a sphere's CObjF:
+//   r2m = rb^2 (1 + 2e-6) + 2e-7 |c|_inf^2 (rounded up),   mm = 2e-7 |c|_inf^2 (rounded up)
+// valid == 0: no float32 shortcut for this object (general matrix, non-finite values).
+struct alignas(16) MeshGateF { float cx, cy, cz, r2m; float mm, valid, pad0, pad1; };
 struct BundleFrame;  // nrt_filter.h
 struct RecSet;       // nrt_filter.h
 
@@ -199,6 +205,7 @@ struct DScene {
   const int32_t* mesh_obj_index;  // mesh object k -> object index
   const BundleFrame* frames;      // [mo * (2 + nlights) + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
   const RecSet* recsets;          // same index: the filter record set of the bundle (per-thread mesh walk of the path kernels)
+  const MeshGateF* mgate;         // per mesh object: float32 world-space bounding sphere of its box (meshGateMissF)
   double c2w[16];
   double cam_orig[4];             // c2w * (0,0,0,1): castPrimaryRay's origin (renderer.nim:42), the same product done once on the host
   double tan_half_fov;            // f of renderer.nim:38 (host libm, shared with nothing else)
@@ -294,6 +301,24 @@ NRT_HD bool certainMissF(const CObjF& c, const RayF& r) {
   const float b = fmaf(r.dx, ox, fmaf(r.dy, oy, r.dz * oz));
   const float o2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
   return b * b < r.a * fmaf(o2, 0.999995f, -(c.r2m + r.mray));
+}
+
+// true => the ray (t >= 0) certainly does not enter the mesh object's box, i.e. the reference's slab test
+// (geom.nim:76-96) returns NegInf or a negative tmin and TriangleMesh.intersect returns at geom.nim:340:
+//   (1) the ray's LINE misses the bounding sphere — certainMissF's test with r2m = the sphere's; or
+//   (2) the origin is outside the sphere and the ray moves away from its centre: b = d.(o - c) > 0.
+// With oc the float32 value of o - c (each component off by at most delta = 2.01u(|o|_inf + |c|_inf), see
+// certainMissF), |b - b*| <= 3u |d||oc| + sqrt(3) |d| delta, so b > 0 and b^2 > a (1e-5 |oc|^2 + mray + mm) — the
+// margins exceed 2 (3u)^2 |oc|^2 + 6 delta^2 by ten orders of magnitude — prove b* > 0; "outside" is the same
+// expression that is negative in (1): |oc|^2 (1 - 5e-6) - r2m - mray > 0 proves |o - c|^2 > rb^2.
+// NaN / Inf compare false: not certain.  Only valid for rays with w components exactly (1, 0) and finite xyz.
+NRT_HD bool meshGateMissF(const MeshGateF& g, const RayF& r) {
+  const float ox = r.ox - g.cx, oy = r.oy - g.cy, oz = r.oz - g.cz;
+  const float b = fmaf(r.dx, ox, fmaf(r.dy, oy, r.dz * oz));
+  const float o2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
+  const float e = fmaf(o2, 0.999995f, -(g.r2m + r.mray));
+  if (b * b < r.a * e) return true;
+  return (e > 0.f) && (b > 0.f) && (b * b > r.a * fmaf(1e-5f, o2, r.mray + g.mm));
 }
 
 // Plane (object space y = 0, geom.nim:240-248) with worldToObject = [I | t]: when the object-space

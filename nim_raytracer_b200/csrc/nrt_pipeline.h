@@ -736,14 +736,40 @@ NRT_HD bool firstLookMiss(const MP& mp, const CObjF& c, const RayF& rf, bool f32
 // `code0` = gate code of the ray for mesh object 0, loaded by the caller together with its other inputs.
 // CL: the scene has sphere clusters (the host picks the kernel variant, so that the flat scan of small
 // scenes keeps its register budget).
-template <bool CL, class MP>
-NRT_HD TraceOut traceObjects(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear) {
-  TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
+// Per-ray facts shared by every float32 first look at the ray (object scan, mesh gates)
+struct RayPre { RayF rf; bool f32ok, fastRay; };
+NRT_HD RayPre makeRayPre(V4 o, V4 d) {
+  RayPre p;
   // the exact shortcut of toObject() for [I | t] matrices applies to this ray?  (zero components
   // need toObject()'s per-component treatment)
-  const bool f32ok = (o.w == 1.0) && (d.w == 0.0) && finite3(o) && finite3(d);
-  const bool fastRay = f32ok && d.x != 0.0 && d.y != 0.0 && d.z != 0.0;
-  const RayF rf = makeRayF(o, d);
+  p.f32ok = (o.w == 1.0) && (d.w == 0.0) && finite3(o) && finite3(d);
+  p.fastRay = p.f32ok && d.x != 0.0 && d.y != 0.0 && d.z != 0.0;
+  p.rf = makeRayF(o, d);
+  return p;
+}
+// the AABB gate of mesh object mo for a world-space ray: float32 first look, then the reference's evaluation
+NRT_HD bool meshGatePassPre(const DScene& sc, int mo, V4 o, V4 d, const RayPre& pre) {
+#if defined(__CUDA_ARCH__)
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(sc.mgate + mo)), g1 = __ldg(reinterpret_cast<const float4*>(sc.mgate + mo) + 1);
+  MeshGateF g; g.cx = g0.x; g.cy = g0.y; g.cz = g0.z; g.r2m = g0.w; g.mm = g1.x; g.valid = g1.y; g.pad0 = g.pad1 = 0.f;
+#else
+  const MeshGateF g = sc.mgate[mo];
+#endif
+  if (pre.f32ok && g.valid > 0.f && meshGateMissF(g, pre.rf)) return false;
+  return meshGatePass(sc, mo, o, d);
+}
+
+template <bool CL, class MP>
+NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, const RayPre& pre);
+template <bool CL, class MP>
+NRT_HD TraceOut traceObjects(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear) {
+  return traceObjectsPre<CL>(sc, mp, o, d, tNear, makeRayPre(o, d));
+}
+template <bool CL, class MP>
+NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, const RayPre& pre) {
+  TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
+  const bool f32ok = pre.f32ok, fastRay = pre.fastRay;
+  const RayF rf = pre.rf;
   if (CL && sc.ncl1 > 0 && f32ok) {
     // Scenes with many spheres: a flattened two-level traversal of the sphere clusters.  A ray that
     // certainly misses a cluster's bounding sphere certainly misses every member, so whole groups of
@@ -1176,9 +1202,10 @@ struct FusedBounceT {
       a0 = cs.accum[s]; a1 = cs.accum[cs.S + s]; a2 = cs.accum[2 * cs.S + s];
     }
     const int nMO = cs.nMO, nL = cs.nL;
+    const RayPre pre = makeRayPre(o, d);
     for (int mo = 0; mo < nMO; ++mo)
-      if (meshGatePass(*sc, mo, o, d)) return toWavefront(s, d);
-    const TraceOut tr = traceObjects<CL>(*sc, NoMesh{}, o, d, NRT_INF);
+      if (meshGatePassPre(*sc, mo, o, d, pre)) return toWavefront(s, d);
+    const TraceOut tr = traceObjectsPre<CL>(*sc, NoMesh{}, o, d, NRT_INF, pre);
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     if (bounce == 0) st.v[ST_PRIMARY] = 1;
     uint8_t flag = 0;
@@ -1190,11 +1217,13 @@ struct FusedBounceT {
       const V4 hitW = add(o, scale(d, tr.t));
       const V4 n = hitNormal(*sc, ob, tr, hitW);
       const V4 so = add(hitW, scale(n, fp.bias));                                    // renderer.nim:98
-      for (int l = 0; l < nL; ++l) {   // a shadow ray that enters a mesh box: the wavefront takes the sample
-        const V4 sdir = scale(getShadingInfo(sc->lights[l], hitW).lightDir, -1.0);
-        for (int mo = 0; mo < nMO; ++mo)
-          if (meshGatePass(*sc, mo, so, sdir)) return toWavefront(s, d);
-      }
+      if (nMO > 0)
+        for (int l = 0; l < nL; ++l) {   // a shadow ray that enters a mesh box: the wavefront takes the sample
+          const V4 sdir = scale(getShadingInfo(sc->lights[l], hitW).lightDir, -1.0);
+          const RayPre sp = makeRayPre(so, sdir);
+          for (int mo = 0; mo < nMO; ++mo)
+            if (meshGatePassPre(*sc, mo, so, sdir, sp)) return toWavefront(s, d);
+        }
       if (bounce == 0) writeAovOf(fp, cs, s, tr);
       V3 local = v3(0.0, 0.0, 0.0);
       for (int l = 0; l < nL; ++l) {

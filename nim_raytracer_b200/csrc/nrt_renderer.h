@@ -89,6 +89,7 @@ struct SceneData {
   std::vector<BundleFrame> frames;        // host copy, [mo * recStride() + j]
   BundleFrame* dFrames = nullptr;
   RecSet* dRecSets = nullptr;             // device table of the record sets, indexed like the frames (DScene.recsets)
+  MeshGateF* dMGate = nullptr;            // float32 gate records per mesh object (DScene.mgate)
   bool anyGeneralShadow = false;          // some shadow rays need the GENERAL bundle (point light / unusable frame)
   std::vector<MoRecs> moRecs;
   uint32_t* dRecCount = nullptr;          // [mo * recStride() + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
@@ -423,11 +424,29 @@ struct SceneData {
           if (!(fd.valid > 0)) anyGeneralShadow = true;
         }
       }
+      {   // float32 gate records (nrt_core.h: MeshGateF)
+        std::vector<MeshGateF> mg(size_t(std::max(1, nMOf)), MeshGateF{});
+        for (int mo = 0; mo < nMOf; ++mo) {
+          const DObject& ob = objs[moIndex[mo]];
+          const DMesh& m = meshes[ob.mesh];
+          MeshGateF& g = mg[size_t(mo)];
+          const double c[3] = {m.center[0] - ob.w2o[12], m.center[1] - ob.w2o[13], m.center[2] - ob.w2o[14]};
+          const double mc = std::max(std::fabs(c[0]), std::max(std::fabs(c[1]), std::fabs(c[2])));
+          const double rb2 = double(m.rb2f);
+          if (ob.xlate_only && std::isfinite(mc) && mc < 1e15 && rb2 < 1e30 && m.L > 0) {
+            g.cx = float(c[0]); g.cy = float(c[1]); g.cz = float(c[2]);
+            g.r2m = roundUpF(rb2 * (1.0 + 2e-6) + 2e-7 * mc * mc);
+            g.mm = roundUpF(2e-7 * mc * mc);
+            g.valid = 1.f;
+          }
+        }
+        dMGate = up(mg.data(), int64_t(mg.size()), reuse ? dMGate : nullptr);
+      }
       dFrames = up(frames.data(), int64_t(frames.size()), reuse ? dFrames : nullptr);
       dRecSets = up<RecSet>(nullptr, int64_t(frames.size()), reuse ? dRecSets : nullptr);   // filled once the records exist
     }
     h.cl1 = dCl1; h.cl2 = dCl2; h.clm = dClm; h.clmIdx = dClmIdx; h.slowIdx = dSlowIdx;
-    h.objects = dObjs; h.cobjs = dCObjs; h.cobjf = dCObjF; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames; h.recsets = dRecSets;
+    h.objects = dObjs; h.cobjs = dCObjs; h.cobjf = dCObjF; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames; h.recsets = dRecSets; h.mgate = dMGate;
     std::memcpy(h.c2w, desc->camera_to_world, sizeof(h.c2w));
     { const V4 co = mulm(h.c2w, v4(0.0, 0.0, 0.0, 1.0)); h.cam_orig[0] = co.x; h.cam_orig[1] = co.y; h.cam_orig[2] = co.z; h.cam_orig[3] = co.w; }
     h.tan_half_fov = std::tan((desc->fov * (kPi / 180.0)) / 2);  // renderer.nim:38; Nim degToRad = d * (PI/180)
