@@ -197,23 +197,21 @@ def cpu_baseline(scene_desc, opts, rays_per_frame, budget_s=12.0):
             "frames_per_s_extrapolated": v * 1e6 / max(rays_per_frame, 1)}
 
 
-# Modelled algorithmic bytes per primary sample of the streaming kernels over the per-sample state
-# (float64 SoA; two lights, one mesh object, bounce 0 only - later bounces add
-# ~15 % more launches of the same kernels, so the achieved figures are slightly understated).
+# Modelled algorithmic bytes per sample a kernel family's launch works on (float64 SoA state, DESIGN.md section 6;
+# two lights, one mesh object).  FusedBounce takes every active sample of a bounce; the wavefront kernels take the
+# samples with a mesh ray (nrt_profile.wavefront_samples).
 STATE_BYTES_PER_SAMPLE = {
-    "gen+gate": 34,        # W rayD 32 + active 1 + gate code 1
+    "FusedBounce": 25,     # W accum 24 + flag 1 (a sample handed to the wavefront: W ray 32 + flag 1; a continuing one: + ray,
+                           # origin, weight 72) - the kernel is COMPUTE bound (float64 pipe / issue slots), see `compute`
+    "gen+gate": 34,        # NRT_PATH=0 only: W rayD 32 + active 1 + gate code 1
     "Shade": 102,          # R rayD 32 + active 1 + code 1;  W hitObj 4 + hitW 32 + nrm 32 (hit) | accum 24 (miss)
     "k_gate_flags": 70,    # R hitObj 4 + hitW 32 + nrm 32;  W 2 codes (one per light)
     "ShadowTrace": 72,     # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W 2 occlusion flags   (NRT_FUSE_RESOLVE=0)
-    "ShadowResolve": 95,   # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W accum 24 + active 1  (ShadowTrace + Resolve in one launch;
-                           # a continuing sample adds 136: ray in, ray + origin + weight out - ncu: 102.6 B per sample on config 4)
-    "Resolve": 63,         # R hitObj 4 + nrm 32 + 2 flags;  W accum 24 + active 1  (the hit point is read by point lights / continuing samples only)
+    "ShadowResolve": 95,   # R hitObj 4 + hitW 32 + nrm 32 + 2 codes;  W accum 24 + active 1  (ShadowTrace + Resolve in one launch)
+    "Resolve": 63,         # R hitObj 4 + nrm 32 + 2 flags;  W accum 24 + active 1
     "Finalize": 25,        # R accum 24;  W 12 bytes per pixel (16 samples)
 }
-
-
-# HBM bytes one frame moves per primary sample = the sum of the launched kernels' reads and writes
-STATE_HBM_BYTES_PER_SAMPLE = sum(v for k, v in STATE_BYTES_PER_SAMPLE.items() if k not in ("ShadowTrace", "Resolve"))
+WAVEFRONT_FAMILIES = ("Shade", "k_gate_flags", "ShadowTrace", "ShadowResolve", "Resolve")
 
 
 def _hbm_peak():
@@ -235,6 +233,16 @@ def _traffic(workload_name, kernel):
         return None
 
 
+def _traffic_entry(workload_name, kernel):
+    """The committed ncu figures of one launch of `kernel` (profiles/kernel_traffic.json) or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+            tab = json.load(f).get(workload_name, {})
+        return next((v for k, v in tab.items() if kernel.startswith(k)), None)
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,6 +254,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("NRT_WORKLOAD", "config4"))
     ap.add_argument("--gather", default="ipc", choices=["ipc", "gather"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # one process driving every GPU (nrt_init(0) + host framebuffer): the way a single-process caller such as the
+    # reference's front-end would use N GPUs; run WITHOUT torchrun:  python bench.py --gpus N --inproc
+    ap.add_argument("--inproc", action="store_true")
     # L2 between timed steps: "stream" = none needed, every frame streams its per-sample state (GBs, see
     # config.l2 in the output) through HBM; "flush" = additionally write 256 MiB (> 126 MB L2) before every step.
     ap.add_argument("--l2", default=os.environ.get("NRT_BENCH_L2", "stream"), choices=["stream", "flush"])
@@ -284,7 +295,12 @@ def main():
         return float(t.item())
 
     L = api.lib()
-    api.initRenderer(devices=[local_rank])
+    if args.inproc:
+        if world != 1:
+            raise SystemExit("--inproc is a single process: run it without torchrun")
+        api.initRenderer(devices=list(range(args.gpus)))
+    else:
+        api.initRenderer(devices=[local_rank])
     api.setPartition(rank, world)
     scene, opts, desc = workload(args.workload)
     ds = api.DeviceScene(scene)
@@ -444,8 +460,10 @@ def main():
     api.setKernelTiming(False)
 
     if rank == 0:
-        peak = C.c_double(); clk = C.c_double()
+        peak = C.c_double(); clk = C.c_double(); peak64 = C.c_double()
         api.check(L.nrt_measure_fp32_peak(C.byref(peak), C.byref(clk)), "nrt_measure_fp32_peak")
+        L.nrt_measure_fp64_peak.argtypes = [C.POINTER(C.c_double)]
+        api.check(L.nrt_measure_fp64_peak(C.byref(peak64)), "nrt_measure_fp64_peak")
         achieved = prof_acc["flops"] / max(prof_acc["mesh_ms"] * 1e-3, 1e-12) / 1e12
         intersection = {
             "bound": "fp32", "kernel": "k_mesh_prefilter", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
@@ -456,61 +474,102 @@ def main():
             "flops_per_test": prof_acc["flops"] / max(prof_acc["tests"], 1), "tests_per_step": prof_acc["tests"] / args.steps,
             "ref_tests_per_step": prof_acc["tests_ref"] / args.steps,
             "avg_launch_ms": prof_acc["mesh_ms"] / max(prof_acc["launches"], 1),
-            "kernel_share_of_step": prof_acc["mesh_ms"] / max(prof_acc["frame_ms"], 1e-9),
             "gtests_per_s": prof_acc["tests"] / max(prof_acc["mesh_ms"] * 1e-3, 1e-12) / 1e9,
             "candidates_per_step": prof_acc["cand"] / args.steps, "pre_candidates_per_step": prof_acc["pre"] / args.steps,
             "mesh_rays_per_step": prof_acc["rays_mesh"] / args.steps,
-            "note": "achieved = executed float32 flops of the prefilter launches (FFMA = 2) / their CUDA-event time; "
+            "note": "achieved = executed float32 flops of the prefilter launches (FFMA = 2) / their summed CUDA-event time (the lanes' "
+                    "launches overlap in the timed frames, so this understates the kernel alone; `kernels` below times one lane); "
                     "ref_tests = rays x all faces, what geom.nim:346 would evaluate (reported, never used for the fraction)",
         }
         ksum = sum(ms for ms, _ in ktimes.values()) or 1.0
         samples = float(cs.num_primary_rays)   # primary samples this rank rendered in the last frame
         hbm_peak = _hbm_peak()
+        kprof = ds.profile()                   # of the kernel-timing frame (one lane)
+        wf0 = float(kprof.wavefront_samples[0])
         kernels = []
+        frame_bytes = 0.0
         for name, (ms, nl) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
-            k = {"kernel": name, "ms": ms, "share": ms / ksum, "launches": nl}
-            bps = next((v for key, v in STATE_BYTES_PER_SAMPLE.items() if name.startswith(key)), None)
-            if bps is not None:   # streaming kernels over the per-sample state: modelled algorithmic bytes
-                gbs = bps * samples / max(ms * 1e-3, 1e-12) / 1e9
-                k.update({"bound": "hbm", "algorithmic_bytes": bps * samples, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
+            k = {"kernel": name, "ms": ms, "share": ms / ksum, "launches": nl, "longest_launch_ms": ds.kernelMaxMs.get(name)}
+            key = next((key for key in STATE_BYTES_PER_SAMPLE if name.startswith(key)), None)
+            if key is not None:   # streaming kernels over the per-sample state: modelled algorithmic bytes
+                bps = STATE_BYTES_PER_SAMPLE[key]
+                # samples of the family's LONGEST launch (bounce 0): every sample for FusedBounce / Finalize, the samples with a
+                # mesh ray for the wavefront kernels; all its launches: the active / wavefront samples of every bounce
+                n1 = wf0 if key in WAVEFRONT_FAMILIES else samples
+                nall = (sum(kprof.wavefront_samples) if key in WAVEFRONT_FAMILIES else
+                        sum(kprof.active_samples) if key == "FusedBounce" else samples)
+                lms = k["longest_launch_ms"] or ms
+                gbs = bps * n1 / max(lms * 1e-3, 1e-12) / 1e9
+                k.update({"bound": "hbm", "algorithmic_bytes_longest_launch": bps * n1, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
+                          "samples_longest_launch": n1})
+                frame_bytes += bps * nall
             kernels.append(k)
         pre_ms = ktimes.get("k_mesh_prefilter", (0.0, 0))[0]
         intersection["kernel_share_of_step"] = pre_ms / ksum
-        intersection["share_source"] = "CUDA events around every launch of one untimed frame (nrt_set_kernel_timing); 'kernels' lists every family"
-        # `roofline` = the dominant kernel family of the step by measured share
+        intersection["share_source"] = "CUDA events around every launch of one untimed single-lane frame (nrt_set_kernel_timing); 'kernels' lists every family"
+        if pre_ms > 0 and kprof.mesh_filter_ms > 0:
+            # the kernel ALONE (the single-lane kernel-timing frame: nothing else in flight) is the roofline figure — in the timed
+            # frames the lanes' launches overlap each other and other kernels, so their summed event time counts shared time twice
+            alone = kprof.fp32_flops / (kprof.mesh_filter_ms * 1e-3) / 1e12
+            intersection.update({"achieved_overlapped_sum": intersection["achieved"], "achieved": alone,
+                                 "frac": alone / peak.value if peak.value > 0 else None, "frac_of_nominal": alone / NOMINAL_FP32_TFLOPS,
+                                 "avg_launch_ms": kprof.mesh_filter_ms / max(kprof.mesh_filter_launches, 1),
+                                 "gtests_per_s": kprof.mesh_tests / (kprof.mesh_filter_ms * 1e-3) / 1e9})
+        # `roofline` = the dominant kernel family of the step by measured share; per LAUNCH (its longest = bounce-0 launch)
         dom = kernels[0]
         if dom["kernel"].startswith("k_mesh_prefilter"):
             roofline = dict(intersection)
         else:
+            tr = _traffic_entry(args.workload, dom["kernel"])
             roofline = {
                 "bound": "hbm", "kernel": dom["kernel"], "achieved": dom.get("achieved_GBps"), "peak": hbm_peak, "unit": "GB/s",
-                "frac": dom.get("frac_of_hbm_peak"), "traffic": _traffic(args.workload, dom["kernel"]),
-                "traffic_launch": "the family's bounce-0 launch of a whole config-4 frame (every primary sample, 132.7 M; ncu --set full, "
-                                  "profiles/kernel_traffic.json); the later bounces' launches process a few percent of that each",
-                "traffic_launch_algorithmic_bytes": STATE_BYTES_PER_SAMPLE.get(next((k for k in STATE_BYTES_PER_SAMPLE if dom["kernel"].startswith(k)), ""), 0) * 132710400.0,
-                "algorithmic_bytes_per_launch": dom.get("algorithmic_bytes", 0) / max(dom["launches"], 1),
-                "avg_launch_ms": dom["ms"] / max(dom["launches"], 1), "kernel_share_of_step": dom["share"],
+                "frac": dom.get("frac_of_hbm_peak"), "traffic": tr.get("dram_bytes_per_launch") if tr else None,
+                "algorithmic_bytes_per_launch": dom.get("algorithmic_bytes_longest_launch"),
+                "launch": "the family's longest launch of the frame = its bounce-0 launch over every primary sample",
+                "launch_ms": dom.get("longest_launch_ms"), "kernel_share_of_step": dom["share"],
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth measured on this pool)",
-                "note": "streaming kernel over the float64 per-sample state; achieved = modelled algorithmic bytes (STATE_BYTES_PER_SAMPLE in "
-                        "bench.py, DESIGN.md section 6) x primary samples / the family's CUDA-event time; the kernel is issue/latency bound "
-                        "below the HBM roofline (profiles/)",
             }
-        state_gb = STATE_HBM_BYTES_PER_SAMPLE * samples / 1e9
+            if dom["kernel"].startswith("FusedBounce"):
+                # The kernel keeps a sample's whole bounce in registers: it writes 25 bytes per sample and is bound by the
+                # float64 pipe and issue slots (the reference's float64 arithmetic, operation by operation).  Its compute
+                # roofline: float64 thread-instructions per launch (ncu smsp__inst_executed_pipe_fp64 of the same launch,
+                # profiles/kernel_traffic.json) / launch time, against the DFMA micro-kernel measured in this run.
+                comp = {"bound": "fp64 pipe", "peak": peak64.value / 2.0, "unit": "T float64 instr/s (thread level)",
+                        "peak_source": "register-resident DFMA micro-kernel measured in this run (TFLOP/s / 2)"}
+                if tr and tr.get("fp64_thread_inst_per_launch") and dom.get("longest_launch_ms"):
+                    scale = samples / float(tr.get("samples_per_launch", samples))
+                    ach = tr["fp64_thread_inst_per_launch"] * scale / (dom["longest_launch_ms"] * 1e-3) / 1e12
+                    comp.update({"achieved": ach, "frac": ach / comp["peak"] if comp["peak"] > 0 else None,
+                                 "fp64_thread_inst_per_sample": tr["fp64_thread_inst_per_launch"] / float(tr.get("samples_per_launch", samples)),
+                                 "issue_slot_frac_ncu": tr.get("issue_active_frac"), "fp64_pipe_frac_ncu": tr.get("fp64_pipe_frac")})
+                roofline["compute"] = comp
+                roofline["note"] = ("FusedBounce replaces four HBM-streaming kernels (r01: 43 GB of per-sample state per frame) by one "
+                                    "register-resident kernel: it is NOT memory bound (frac = its 25 algorithmic bytes per sample against "
+                                    "the HBM peak); what bounds it is `compute` - the float64 pipe and issue slots")
         l2_note = ("256 MiB device fill between timed steps (inside the timed region)" if args.l2 == "flush" else
-                   f"inputs larger than L2: every frame streams {state_gb:.1f} GB of per-sample state per GPU through HBM "
-                   f"(>= {state_gb * 1e3 / 126:.0f}x the 126 MB L2), so nothing a step reads survives from the previous one except the "
+                   f"inputs larger than L2: every frame streams {frame_bytes / 1e9:.1f} GB of per-sample state per GPU through HBM "
+                   f"(>= {frame_bytes / 126e6:.0f}x the 126 MB L2), so nothing a step reads survives from the previous one except the "
                    "scene records (L2-resident within a step as well); --l2 flush adds a 256 MiB fill per step")
+        band = api.bandRows(opts)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus if args.inproc else world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 filter + f64 exact", "data": "synthetic",
-            "config": {"workload": desc, "parallelism": f"scanline-interleaved x{world}, {'CUDA-IPC peer stores' if peer is not None else 'NCCL row gather'} to rank 0",
+            "dtype": "f64 (reference order) behind f32 first looks", "data": "synthetic",
+            "config": {"workload": desc,
+                       "parallelism": (f"bands of {band} scanlines (rows of {band}x{band} screen-space tiles) dealt out round-robin x"
+                                       f"{args.gpus if args.inproc else world} GPUs, up to 4 concurrent lanes per GPU; "
+                                       + ("one process, peer stores into device 0" if args.inproc else
+                                          ("CUDA-IPC peer stores" if peer is not None else "NCCL row gather") + " to rank 0")),
                        "l2": l2_note,
                        "warmup_extra_steps": extra_warm},
             "frames_per_s": args.steps / (t_ms * 1e-3), "rays_per_frame": total_rays / args.steps,
             "device_ms_per_step": ms_dev.value / args.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(klaunches),
-            "roofline": roofline, "intersection_kernel": intersection, "kernels": kernels, "kernel_timing_frame_ms": kframe_ms, "fb_checksum": checksum, "parity": parity,
+            "roofline": roofline, "intersection_kernel": intersection, "kernels": kernels, "kernel_timing_frame_ms": kframe_ms,
+            "frame_hbm_bytes_model": frame_bytes,
+            "fused_path": {"active_samples_per_bounce": list(kprof.active_samples), "wavefront_samples_per_bounce": list(kprof.wavefront_samples),
+                           "tail_samples": int(kprof.tail_samples)},
+            "fb_checksum": checksum, "parity": parity,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(ds.desc, opts, total_rays / args.steps)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NRT_ABI_VERSION 1
+#define NRT_ABI_VERSION 2
 
 /* ---------------------------------------------------------------- status -- */
 typedef enum nrt_status {
@@ -176,6 +176,12 @@ typedef struct nrt_profile {
   double fp32_flops;            /* FP32 flops executed by the mesh kernel (2/FFMA) */
   int64_t mesh_tests_by_mode[4];/* general / shared-origin / shared-dir / reserved */
   double mesh_ms_by_mode[4];
+  /* fused path (ABI v2): per bounce b < 8, the samples FusedBounce took (active set) and, of those, the samples with a
+   * ray entering a mesh box, which went through the wavefront for that bounce; samples finished by PathTail */
+  int64_t active_samples[8];
+  int64_t wavefront_samples[8];
+  int64_t tail_samples;
+  int64_t lanes;                /* concurrent pipelines per GPU used for the frame */
 } nrt_profile;
 
 /* Device time per kernel family of one frame (measurement hook, see nrt_set_kernel_timing). */
@@ -183,6 +189,7 @@ typedef struct nrt_profile {
 typedef struct nrt_kernel_times {
   double ms[NRT_KERNEL_CATEGORIES];        /* summed CUDA-event time of the category's launches */
   int64_t launches[NRT_KERNEL_CATEGORIES];
+  double max_ms[NRT_KERNEL_CATEGORIES];    /* the category's longest single launch (the bounce-0 launch over every sample) */
 } nrt_kernel_times;
 
 typedef struct nrt_scene nrt_scene;
@@ -306,6 +313,9 @@ int nrt_device_synchronize(void);
 /* Measured FP32 FFMA peak of device 0 in TFLOP/s (register-resident FFMA
  * micro-kernel, CUDA-event timed) — the denominator BASELINE.md asks for. */
 int nrt_measure_fp32_peak(double* tflops, double* sm_clock_mhz_hint);
+/* The same for the float64 pipe (register-resident DFMA loop): the per-sample kernels do the reference's float64
+ * arithmetic operation by operation, so this is the pipe that bounds them. */
+int nrt_measure_fp64_peak(double* tflops);
 
 /* CUDA-event bracket on the library's own stream(s): elapsed device time between
  * the two calls, max over the selected devices (bench.py's timed region). */

@@ -111,7 +111,8 @@ NRT_KERNEL_CATEGORIES = 24
 
 
 class nrt_kernel_times(C.Structure):
-    _fields_ = [("ms", C.c_double * NRT_KERNEL_CATEGORIES), ("launches", C.c_int64 * NRT_KERNEL_CATEGORIES)]
+    _fields_ = [("ms", C.c_double * NRT_KERNEL_CATEGORIES), ("launches", C.c_int64 * NRT_KERNEL_CATEGORIES),
+                ("max_ms", C.c_double * NRT_KERNEL_CATEGORIES)]
 
 
 class nrt_profile(C.Structure):
@@ -122,6 +123,7 @@ class nrt_profile(C.Structure):
         ("pre_candidates", C.c_int64),
         ("kernel_launches", C.c_int64), ("fp32_flops", C.c_double),
         ("mesh_tests_by_mode", C.c_int64 * 4), ("mesh_ms_by_mode", C.c_double * 4),
+        ("active_samples", C.c_int64 * 8), ("wavefront_samples", C.c_int64 * 8), ("tail_samples", C.c_int64), ("lanes", C.c_int64),
     ]
 
 
@@ -477,6 +479,7 @@ class DeviceScene:
             name = lib().nrt_kernel_category_name(i).decode()
             if name and t.launches[i]:
                 out[name] = (t.ms[i], int(t.launches[i]))
+        self.kernelMaxMs = {lib().nrt_kernel_category_name(i).decode(): t.max_ms[i] for i in range(NRT_KERNEL_CATEGORIES) if t.launches[i]}
         return out
 
     def close(self) -> None:

@@ -30,7 +30,7 @@ def test_exports_every_declared_symbol(built_lib):
     assert len(names) >= 25
     for n in names:
         assert hasattr(built_lib, n), f"{n} declared in include/nrt.h but not exported by libnrt.so"
-    assert built_lib.nrt_abi_version() == 1
+    assert built_lib.nrt_abi_version() == 2
 
 
 def test_built_for_sm_100a_only(built_lib):
