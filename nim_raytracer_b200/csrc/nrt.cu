@@ -932,10 +932,13 @@ struct CudaBackend {
     ~Timed() { if (slot != size_t(-1)) cudaEventRecord(be->tEvents[2 * slot + 1], be->stream); }
   };
   // call after a stream sync; adds this frame's per-category times and launch counts
-  void collectTimes(double* ms, int64_t* n) {
+  void collectTimes(double* ms, int64_t* n, double* mx) {
     for (size_t i = 0; i < tUsed; ++i) {
       float t = 0;
-      if (cudaEventElapsedTime(&t, tEvents[2 * i], tEvents[2 * i + 1]) == cudaSuccess) { ms[tCats[i]] += t; n[tCats[i]] += 1; }
+      if (cudaEventElapsedTime(&t, tEvents[2 * i], tEvents[2 * i + 1]) == cudaSuccess) {
+        ms[tCats[i]] += t; n[tCats[i]] += 1;
+        if (double(t) > mx[tCats[i]]) mx[tCats[i]] = double(t);
+      }
     }
     tUsed = 0;
   }
@@ -1622,13 +1625,16 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     p.mesh_tests += a.mesh_tests; p.mesh_tests_ref += a.mesh_tests_ref; p.mesh_rays += a.mesh_rays;
     p.candidates += a.candidates;
     p.pre_candidates += a.pre_candidates;
+    for (int b = 0; b < 8; ++b) { p.active_samples[b] += a.active[b]; p.wavefront_samples[b] += a.wavefront[b]; }
+    p.tail_samples += a.tail;
+    p.lanes = nlanes;
     p.kernel_launches += lbe.launches;
     if (lbe.timing && d == 0 && ln == 0) {
       sc->ktimes = nrt_kernel_times{};
-      lbe.collectTimes(sc->ktimes.ms, sc->ktimes.launches);
+      lbe.collectTimes(sc->ktimes.ms, sc->ktimes.launches, sc->ktimes.max_ms);
     } else if (lbe.timing) {
       nrt_kernel_times scratchT{};
-      lbe.collectTimes(scratchT.ms, scratchT.launches);
+      lbe.collectTimes(scratchT.ms, scratchT.launches, scratchT.max_ms);
     }
     for (int m = 0; m < 3; ++m) {
       p.mesh_tests_by_mode[m] += a.tests_by_mode[m];
@@ -1940,6 +1946,47 @@ int nrt_measure_fp32_peak(double* tflops, double* sm_clock_mhz_hint) {
       cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, be.device);
       *sm_clock_mhz_hint = khz / 1000.0;
     }
+  } catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
+  return NRT_OK;
+}
+
+// register-resident DFMA loop: the float64 pipe's roofline denominator (FusedBounce is bound by it and by issue slots)
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+  double x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = double(threadIdx.x + k);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = fma(x[k], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += x[k];
+  if (s == 12345.678) out[0] = s;
+}
+int nrt_measure_fp64_peak(double* tflops) {
+  if (!tflops) return fail(NRT_ERR_INVALID, "null argument");
+  NRT_NEED_DEV0();
+  try {
+    be.use();
+    double* out = static_cast<double*>(be.dalloc(16));
+    cudaEvent_t e0, e1;
+    NRT_CUDA(cudaEventCreate(&e0)); NRT_CUDA(cudaEventCreate(&e1));
+    const int iters = 2048, blocks = be.sms * 8;
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+      NRT_CUDA(cudaEventRecord(e0, be.stream));
+      k_dfma_peak<<<blocks, 256, 0, be.stream>>>(out, iters, 1.0001, 0.0001);
+      NRT_CUDA(cudaEventRecord(e1, be.stream));
+      NRT_CUDA(cudaStreamSynchronize(be.stream));
+      float ms = 0;
+      NRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double fl = double(blocks) * 256.0 * iters * 8.0 * 2.0;
+      if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    be.dfree(out);
+    *tflops = best;
   } catch (const std::exception& ex) { return fail(NRT_ERR_CUDA, ex.what()); }
   return NRT_OK;
 }

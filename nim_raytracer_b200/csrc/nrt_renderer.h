@@ -22,6 +22,7 @@ struct ProfileAcc {
   int64_t mesh_tests = 0, mesh_tests_ref = 0, mesh_rays = 0, candidates = 0, exact_rays = 0;
   int64_t tests_by_mode[3] = {0, 0, 0};
   int64_t pre_candidates = 0;
+  int64_t active[8] = {0}, wavefront[8] = {0}, tail = 0;   // fused path: samples per bounce / through the wavefront / finished by PathTail
 };
 
 inline bool isPow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -759,7 +760,8 @@ struct Renderer {
           // kFlagWavefront, listed in sample order) go through the wavefront for that bounce.
           if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
           for (int bounce = 0;; ++bounce) {
-            if (bounce > 0 && act.n < tailBelow) { pathTail(act, bounce); break; }   // a small wave: one launch to the end of its paths
+            if (bounce > 0 && act.n < tailBelow) { pathTail(act, bounce); pacc.tail += act.n; break; }   // a small wave: one launch to the end of its paths
+            if (bounce < 8) pacc.active[bounce] += act.n;
             const int gfs = (bounce == 0 && jitter) ? 1 : 0;
             if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, FusedBounceClustered{sd.d, fp, cs, force_exact, gfs, act, bounce}, cs.stats);
             else be->forEachStats(nullptr, act.n, FusedBounce{sd.d, fp, cs, force_exact, gfs, act, bounce}, cs.stats);
@@ -769,6 +771,7 @@ struct Renderer {
               uint32_t nh = 0;
               be->download(&nh, hardCount, sizeof(nh));
               if (nh > 0) wavefrontBounce(ActiveSet{cs.hlist, hardCount, int64_t(nh)}, bounce, false);
+              if (bounce < 8) pacc.wavefront[bounce] += nh;
             }
             if (bounce >= maxBounces) break;
             // the next bounce's active set: every sample of this one whose flag is nonzero (FusedBounce: continues;
