@@ -1067,6 +1067,9 @@ struct CudaBackend {
     { Timed tm(this, KC_GATE_WRITE); k_gate_write<<<unsigned(sms * 8), kBlock, 0, stream>>>(g, count, n, mult, nMO, ne); }
     NRT_CUDA(cudaGetLastError()); launches += 3;
   }
+  // the fused producer + gate kernel counts in mult * nMO * (2 + nL) shared-memory words: beyond the 48 KiB a launch gets
+  // without opting in (e.g. 32 lights x 12 mesh objects) the caller takes the separate flags kernel instead
+  bool produceGateFits(int mult, int nMO, int nL) const { return sizeof(uint32_t) * size_t(mult) * size_t(nMO) * size_t(2 + nL) <= size_t(48) * 1024; }
   // fused producer + gate flags (GenGate: mult 1; ShadeGate: mult nL, with Stats); gateFinish() completes the gate
   template <class P> void produceGate(int64_t n, int mult, const P& p, const ChunkState& cs, int nMO, uint32_t* cnt, unsigned long long* stats) {
     use();

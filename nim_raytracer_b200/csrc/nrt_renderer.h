@@ -535,7 +535,9 @@ struct Renderer {
   int64_t tailBelow = 32768;   // NRT_TAIL_BELOW: active lists shorter than this are finished by one PathTail launch
   // NRT_PATH: 0 = the wavefront for every bounce (round-1 pipeline), 1 = FusedBounce + wavefront for the samples
   // with mesh rays at bounce 0 + PathTail (default), 2 = PathMega (one thread per sample start to end)
-  int pathMode = int(envInt("NRT_PATH", 1));
+  int pathMode = 1;
+  double meshShare = 0.0;   // see render(): picks the path of the next frame when NRT_PATH is not set
+  int autoMode = 1;
   ProfileAcc prof;
   int64_t launches_hint = 0;
   bool shadowGatePerSample = envInt("NRT_SHADOW_GATE_PER_SAMPLE", 1) != 0;
@@ -611,7 +613,7 @@ struct Renderer {
     const int mult = (kind == WAVE_SHADOW) ? nL : 1;
     const Gate g = makeGate(sd, fp, kind, act, bounce, force_exact);
     if (gated) be->gateFinish(g, act.n * mult, nMO, cnt);
-    else if (kind == WAVE_SHADOW && shadowGatePerSample) {
+    else if (kind == WAVE_SHADOW && shadowGatePerSample && be->produceGateFits(nL, nMO, nL)) {
       be->produceGate(act.n, nL, ShadowGate{g, nMO}, cs, nMO, cnt, nullptr);
       be->gateFinish(g, act.n * mult, nMO, cnt);
     }
@@ -684,9 +686,16 @@ struct Renderer {
 
     const int nL = sd.h.nlights, nMO = sd.h.nmesh_objs;
     const bool jitter = o.aa_kind >= NRT_AA_JITTERED;
-    pathMode = int(envInt("NRT_PATH", 1));
+    pathMode = int(envInt("NRT_PATH", -1));
     tailBelow = envInt("NRT_TAIL_BELOW", 32768);
-    if (pathMode < 0 || pathMode > 2) pathMode = 1;
+    if (pathMode < 0 || pathMode > 2) {
+      // automatic: the fused path, unless the last frame of this pipeline showed that most samples have a ray entering
+      // a mesh box (a scene that is mostly mesh: FusedBounce would do a sample's bounce only to hand it over) — then the
+      // wavefront for every bounce, until the share of rays entering a box says otherwise
+      // (hysteresis: the two estimates below are not the same quantity)
+      autoMode = (meshShare > (autoMode == 0 ? 0.25 : 0.5)) ? 0 : 1;
+      pathMode = autoMode;
+    }
     // An INTENDED-mode frame can reflect at most max_ray_depth times.
     int maxBounces = sd.anyReflective ? fp.bounce_cap : 0;
     if (sd.anyReflective && o.depth_mode == NRT_DEPTH_INTENDED) maxBounces = std::min(maxBounces, std::max(0, o.max_ray_depth));
@@ -851,6 +860,10 @@ struct Renderer {
       if (!overflow) {
         for (int k = 0; k < ST_COUNT; ++k) statsOut[k] = total[k];
         prof = pacc;
+        // the share of mesh work seen by this frame: samples handed to the wavefront at bounce 0 (fused path), or rays
+        // that entered a box per sample (wavefront path: <= 1 + nL rays per sample and bounce)
+        if (pathMode == 1 && pacc.active[0] > 0) meshShare = double(pacc.wavefront[0]) / double(pacc.active[0]);
+        else if (pathMode == 0 && total[ST_PRIMARY] > 0) meshShare = std::min(1.0, double(pacc.mesh_rays) / double(total[ST_PRIMARY]));
         return NRT_OK;
       }
       if (attempt >= 3) { err = "candidate buffer overflow"; return NRT_ERR_OVERFLOW; }

@@ -370,3 +370,20 @@ def with_many_lights(sc: Scene, n: int, seed: int = 5) -> Scene:
     lights.append(PointLight(color=vec3(1.0), intensity=600.0, pos=point(2.0, 7.0, -9.0)))
     sc.lights = lights
     return sc
+
+
+def many_meshes_many_lights(nmesh: int = 12, nlights: int = 32, seed: int = 9) -> Scene:
+    """Build-defined scene at the edge of the fused shadow-gate kernel's shared memory (32 lights x 12 mesh objects:
+    32 * 12 * 34 counters = 52 KiB > 48 KiB): `nmesh` small meshes (decimated bunnies at different places, sharing
+    nothing), a ground plane, a mirror ball, `nlights` lights."""
+    rng = np.random.default_rng(seed)
+    objects = [Object("ground", initPlane(objectToWorld=L.mat4(1.0)), Material(albedo=vec3(0.4)))]
+    for k in range(nmesh):
+        mesh = trianglesToMesh(bunny_triangles(stride=256 + 16 * k))
+        mesh.objectToWorld = L.translate(L.mat4(1.0), vec3(float(-9.0 + 3.5 * (k % 6)), 0.0001, float(-10.0 - 5.0 * (k // 6))))
+        mesh.worldToObject = L.inverse(mesh.objectToWorld)
+        objects.append(Object(f"mesh{k}", mesh, Material(albedo=vec3(*rng.uniform(0.3, 0.9, 3)))))
+    objects.append(Object("mirror", initSphere(r=1.5, objectToWorld=L.translate(L.mat4(1.0), vec3(0.0, 1.5, -6.0))),
+                          Material(albedo=vec3(0.9), reflection=0.7)))
+    sc = Scene(objects=objects, lights=[], fov=60.0, cameraToWorld=_camera(0.0, 6.0, 4.0, -15.0), bgColor=vec3(0.02, 0.03, 0.05))
+    return with_many_lights(sc, nlights, seed)

@@ -32,6 +32,7 @@ struct LoopBackend {
   void upload(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
   void download(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
   void sync() {}
+  bool produceGateFits(int, int, int) const { return true; }
   bool diff_ = false;
   void diffBegin() { diff_ = false; }
   void diffAdd(const void* a, const void* b, size_t bytes) { if (bytes && std::memcmp(a, b, bytes) != 0) diff_ = true; }

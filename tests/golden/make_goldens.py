@@ -76,3 +76,9 @@ if __name__ == "__main__":
         # "mesh-bunny" is the scene that front-end includes: the teapot (src/data/meshes/teapot.obj)
         for name, build in scenes.REFERENCE_SCENES.items():
             make("ref_" + name.replace("-", "_") + "_300x200", build(), api.Options(300, 200, bias=0.00000001, maxRayDepth=5), row_stride=25)
+    if "config5_class" in which:
+        # BASELINE config 5's class at a size the brute-force oracle finishes in minutes: 100,000 random triangles as ONE
+        # mesh + 10,000 spheres (10 % mirrors) + plane, 200x112, 4 spp grid, intended depth 4 (scenes.stress, the frozen
+        # generator of BASELINE.md section 3)
+        make("config5_class_100k_tris_10k_spheres_200x112_g2", scenes.stress(ntri=100_000, nspheres=10_000),
+             api.Options(200, 112, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=4), row_stride=8)

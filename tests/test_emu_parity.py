@@ -166,3 +166,9 @@ def test_degenerate_meshes(oracle_mod):
     oracle_mod.render(sc, api.Options(96, 54), aov=a1)
     assert set(np.unique(a1.tri_id)) >= {-1, 1}          # duplicate #2 never wins over #1
     check(sc, api.Options(96, 54), oracle_mod)
+
+
+def test_many_mesh_objects_and_lights(oracle_mod):
+    # several mesh objects (kMaxWalkMO = 2 result slots of the path kernels: the third is walked by the thread) x many lights
+    check(scenes.many_meshes_many_lights(3, 5), api.Options(64, 36, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
+    check(scenes.many_meshes_many_lights(12, 33), api.Options(32, 18), oracle_mod)

@@ -297,6 +297,14 @@ def test_separate_shadow_and_resolve_launches(oracle_mod, monkeypatch):
     assert_parity(scenes.with_many_lights(scenes.bunny_spheres(stride=32), 33), api.Options(96, 54), oracle_mod)
 
 
+def test_many_mesh_objects_and_lights(oracle_mod):
+    # 12 mesh objects x 32 lights: the fused shadow-gate kernel would need 52 KiB of shared-memory counters (> the 48 KiB a
+    # launch gets without opting in): the separate flags kernel takes over; 33 lights: separate ShadowTrace + Resolve
+    for nl in (32, 33):
+        assert_parity(scenes.many_meshes_many_lights(12, nl), api.Options(96, 54), oracle_mod)
+    assert_parity(scenes.many_meshes_many_lights(3, 5), api.Options(120, 68, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
+
+
 def test_stress_scene_sphere_clusters(oracle_mod):
     # BASELINE config 5's object count class: thousands of spheres -> clustered object scan
     sc = scenes.stress(ntri=20000, nspheres=3000)
