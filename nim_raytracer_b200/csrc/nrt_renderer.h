@@ -693,7 +693,7 @@ struct Renderer {
       // a mesh box (a scene that is mostly mesh: FusedBounce would do a sample's bounce only to hand it over) — then the
       // wavefront for every bounce, until the share of rays entering a box says otherwise
       // (hysteresis: the two estimates below are not the same quantity)
-      autoMode = (meshShare > (autoMode == 0 ? 0.25 : 0.5)) ? 0 : 1;
+      autoMode = (meshShare > (autoMode == 0 ? 0.15 : 0.3)) ? 0 : 1;
       pathMode = autoMode;
     }
     // An INTENDED-mode frame can reflect at most max_ray_depth times.

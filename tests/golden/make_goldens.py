@@ -42,7 +42,8 @@ def make(name, scene, opts, row_stride=8):
         stats=np.array([st.numPrimaryRays, st.numIntersectionTests, st.numIntersectionHits, st.numRays,
                         st.numCappedSamples], dtype=np.int64),
         rows=rows,
-        fb_rows=fb.image()[rows], obj_rows=aov.obj_id.reshape(h, w)[rows].astype(np.int8),
+        fb_rows=fb.image()[rows],
+        obj_rows=aov.obj_id.reshape(h, w)[rows].astype(np.int8 if len(scene.objects) < 128 else np.int32),
         tri_rows=aov.tri_id.reshape(h, w)[rows],
         # one CRC32 per scanline of the float32 framebuffer / the ids: locates a mismatch in a full-size frame
         fb_row_crc=np.array([zlib.crc32(r.tobytes()) for r in fb.image()], dtype=np.uint32),

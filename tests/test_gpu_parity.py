@@ -248,6 +248,19 @@ def test_golden_config4_full_size():
     _check_row_crcs("config4_bunny_spheres_3840x2160_g4", fb, aov)
 
 
+def test_golden_config5_class():
+    # BASELINE config 5's class: 100,000 random triangles as ONE mesh + 10,000 spheres (sphere clusters in the object scan,
+    # 10 % mirrors) + plane, 200x112, 4 spp, intended depth 4 - against the brute-force oracle's frame (27 s on 8 cores).
+    # Rendered twice: the first frame takes the fused path, sees that most samples have a ray entering the mesh box and
+    # the second takes the wavefront for every bounce (nrt_renderer.h: automatic NRT_PATH) - same frame both times.
+    sc = scenes.stress(ntri=100_000, nspheres=10_000)
+    o = api.Options(200, 112, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=4)
+    ds = api.DeviceScene(sc)
+    for _ in range(2):
+        _check_golden("config5_class_100k_tris_10k_spheres_200x112_g2", ds, o)
+    ds.close()
+
+
 @pytest.mark.parametrize("path", ["0", "2"])
 def test_path_modes_agree(oracle_mod, monkeypatch, path):
     # NRT_PATH: 0 = the wavefront for every bounce, 1 (default) = FusedBounce + wavefront + PathTail, 2 = PathMega

@@ -26,6 +26,7 @@ for wl in sys.argv[1:] or ["config2"]:
           f"tests {list(p.mesh_tests_by_mode)[:3]} pre {p.pre_candidates} cand {p.candidates} launches {p.kernel_launches} Mrays/s {cs.num_rays / wall / 1e3:.0f}")
     api.setKernelTiming(True); step(); kt = ds.kernelTimes(); api.setKernelTiming(False)
     tot = sum(ms for ms, _ in kt.values())
+    print(f"   active/bounce {list(p.active_samples)[:4]} wavefront/bounce {list(p.wavefront_samples)[:4]} tail {p.tail_samples} lanes {p.lanes}")
     print("   " + " | ".join(f"{k.split(' ')[0]} {ms:.2f}" for k, (ms, n) in sorted(kt.items(), key=lambda kv: -kv[1][0])) + f" | sum {tot:.2f}")
     import hashlib, numpy as np
     host = np.empty(o.width * o.height * 3, dtype=np.float32)
