@@ -884,10 +884,61 @@ template <class A> struct CatOf<Refine<A>> { static constexpr int v = KC_REFINE;
 template <class A> struct CatOf<Verify1<A>> { static constexpr int v = KC_VERIFY; };
 template <class A> struct CatOf<Verify2<A>> { static constexpr int v = KC_VERIFY; };
 
+// One persistent host thread that runs one job at a time (the helper pipeline of a fork, nrt_renderer.h: Renderer::sub)
+class Helper {
+ public:
+  Helper() : th_([this] { loop(); }) {}
+  ~Helper() {
+    { std::unique_lock<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    th_.join();
+  }
+  void start(std::function<void()> f) {
+    { std::unique_lock<std::mutex> lk(mu_); job_ = std::move(f); busy_ = true; }
+    cv_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return !busy_; });
+  }
+ private:
+  void loop() {
+    for (;;) {
+      std::function<void()> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return stop_ || bool(job_); });
+        if (stop_ && !job_) return;
+        job.swap(job_);
+      }
+      job();
+      { std::unique_lock<std::mutex> lk(mu_); busy_ = false; }
+      done_.notify_all();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  std::function<void()> job_;
+  bool busy_ = false, stop_ = false;
+  std::thread th_;
+};
+
 // ----------------------------------------------------------------- backend ----
 struct CudaBackend {
+  Helper* helper = nullptr;    // runs the fork's helper pipeline (null: the job runs inline)
+  void fork(std::function<void()> f) { if (helper) helper->start(std::move(f)); else f(); }
+  void join() { if (helper) helper->wait(); }
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;               // the stream this backend launches on (one of the two below)
+  cudaStream_t sHi = nullptr, sLo = nullptr;   // highest / lowest priority: a lane with the frame's mesh work launches on sHi,
+                                               // a lane of mesh-free bands on sLo (its FusedBounce fills the SMs the other's chain of small kernels leaves idle)
+  void createStreams() {
+    int least = 0, greatest = 0;
+    NRT_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    NRT_CUDA(cudaStreamCreateWithPriority(&sHi, cudaStreamNonBlocking, greatest));
+    NRT_CUDA(cudaStreamCreateWithPriority(&sLo, cudaStreamNonBlocking, least));
+    stream = sHi;
+  }
   int sms = 148;
   int64_t launches = 0;
   // profiling of the mesh filter
@@ -931,6 +982,15 @@ struct CudaBackend {
     }
     ~Timed() { if (slot != size_t(-1)) cudaEventRecord(be->tEvents[2 * slot + 1], be->stream); }
   };
+  // NRT_TIMELINE=<file>: every timed launch of this backend as "dev lane category start_us end_us" relative to `base`
+  // (the frame's start event on the device's first stream); call before collectTimes
+  void dumpTimeline(FILE* f, cudaEvent_t base, int dev, int lane) {
+    for (size_t i = 0; i < tUsed; ++i) {
+      float a = 0, b = 0;
+      if (cudaEventElapsedTime(&a, base, tEvents[2 * i]) == cudaSuccess && cudaEventElapsedTime(&b, base, tEvents[2 * i + 1]) == cudaSuccess)
+        fprintf(f, "%d %d %-14.14s %10.1f %10.1f\n", dev, lane, kKernelCatNames[tCats[i]], a * 1e3, b * 1e3);
+    }
+  }
   // call after a stream sync; adds this frame's per-category times and launch counts
   void collectTimes(double* ms, int64_t* n, double* mx) {
     for (size_t i = 0; i < tUsed; ++i) {
@@ -1231,8 +1291,9 @@ struct CudaBackend {
     pinned = nullptr;
     if (dDiff) cudaFree(dDiff);
     dDiff = nullptr;
-    if (stream) cudaStreamDestroy(stream);
-    stream = nullptr;
+    if (sHi) cudaStreamDestroy(sHi);
+    if (sLo) cudaStreamDestroy(sLo);
+    stream = sHi = sLo = nullptr;
   }
 };
 
@@ -1249,6 +1310,8 @@ struct DeviceCtx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // frame bracket (nrt_profile.total_ms)
   cudaEvent_t tb0 = nullptr, tb1 = nullptr;   // user bracket (nrt_timer_begin/end)
   std::vector<cudaEvent_t> laneDone;           // per extra lane: its part of the frame is complete
+  std::vector<CudaBackend*> subBe;             // per lane: the backend (streams, scratch) of its helper pipeline (the fork)
+  std::vector<Helper*> helpers;                // per lane: the helper's host thread
   float* thr[17] = {nullptr};                  // output stage: cut points of the sRGB pow branch per bit depth (device)
   float* outFb = nullptr; unsigned char* outQ = nullptr; int64_t outFbN = 0, outQN = 0;   // nrt_framebuf_* staging (grow-only)
 };
@@ -1301,9 +1364,20 @@ class HostPool {
 };
 static HostPool g_pool;
 
+// What the last frame of a (scene, device) found, band by band: the number of samples FusedBounce handed to the
+// wavefront at bounce 0.  The next frame with the same geometry of bands deals the bands WITH mesh work to the
+// high-priority lanes and the others to the low-priority ones (renderImpl: planLanes).  Scheduling only: every band
+// is rendered by the same kernels whichever lane takes it.
+struct BandFeedback {
+  std::vector<int64_t> key;          // frame geometry the numbers belong to
+  std::vector<int32_t> y;            // first row of every band of this device, in order
+  std::vector<uint32_t> hard;        // per band
+};
 struct PerDevice {
   SceneData<CudaBackend> sd;
   Renderer<CudaBackend> rn[kMaxLanes];
+  Renderer<CudaBackend> rnSub[kMaxLanes];   // the lanes' helper pipelines (the fork)
+  BandFeedback fbk;
   float* fbStage = nullptr; int64_t fbStageN = 0;
   unsigned char* qStage = nullptr; int64_t qStageN = 0;   // nrt_render_quantized: the integer image
   int32_t* aovObj = nullptr; int32_t* aovTri = nullptr; double* aovT = nullptr; int64_t aovN = 0;
@@ -1341,7 +1415,7 @@ static int initLocked(int ngpu, const int* ids) {
       d->be.sms = p.multiProcessorCount;
       if (const char* e = std::getenv("NRT_PREFILTER_CULL")) d->be.cull = std::atoi(e) != 0;
       NRT_CUDA(cudaSetDevice(id));
-      NRT_CUDA(cudaStreamCreateWithFlags(&d->be.stream, cudaStreamNonBlocking));
+      d->be.createStreams();
       NRT_CUDA(cudaEventCreate(&d->ev0)); NRT_CUDA(cudaEventCreate(&d->ev1));
       NRT_CUDA(cudaEventCreate(&d->tb0)); NRT_CUDA(cudaEventCreate(&d->tb1));
       g_devs.push_back(d);
@@ -1453,12 +1527,60 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     const int64_t rowsAll = (std::min(y1, o->height) - std::max(0, y0) + step - 1) / std::max(step, 1);
     const int64_t samples = std::max<int64_t>(0, rowsAll) * ((o->width + step - 1) / step) * spp / std::max(1, nd * g_part_count);
     if (!std::getenv("NRT_LANES")) nlanes = int(std::min<int64_t>(4, std::max<int64_t>(1, samples / (int64_t(1) << 20))));
-    if (g_devs[0]->be.timing) nlanes = 1;
+    if (g_devs[0]->be.timing && !std::getenv("NRT_TIMELINE")) nlanes = 1;
   }
   nlanes = std::max(1, std::min(nlanes, kMaxLanes));
   const int tshift = tileShiftFor(*o, step, max_step), T = 1 << tshift;   // T > 1: bands of T scanlines, tile order inside
   const int yEnd = std::min(y1, o->height);
   const int nunits = nd * nlanes;
+  // ---- the lanes' bands.  Default: band i of the device goes to lane i % nlanes.  With the last frame's per-band
+  // counts (BandFeedback) for the same band geometry: the bands are sorted by their count, the longest prefix whose
+  // counts fit the light lanes' budget (a wavefront list that short is finished by ONE PathTail launch, nrt_renderer.h)
+  // becomes the LIGHT set, the rest the HEAVY set; heavy lanes launch on the high-priority stream, light lanes on the
+  // low-priority one.  A heavy lane's frame is FusedBounce over its bands + the latency-bound chain of small
+  // wavefront kernels; the light lanes' FusedBounce work fills the SMs under that chain instead of preceding it.
+  const size_t ndz = static_cast<size_t>(nd), nlz = static_cast<size_t>(nlanes);
+  std::vector<std::vector<std::vector<int32_t>>> laneRows(ndz, std::vector<std::vector<int32_t>>(nlz));
+  std::vector<std::vector<int32_t>> devUnits(ndz);
+  std::vector<std::vector<char>> laneLow(ndz, std::vector<char>(nlz, 0));
+  const std::vector<int64_t> bandKey = {o->width, o->height, y0, y1, step, max_step, T, g_part_index, g_part_count, nd,
+                                        o->aa_kind, o->aa_kind == NRT_AA_NONE ? 1 : o->grid_size, nlanes};
+  {
+    const int64_t hardTail = Renderer<CudaBackend>::envInt("NRT_HARD_TAIL_BELOW", 16384);
+    const bool useFbk = Renderer<CudaBackend>::envInt("NRT_LANE_FEEDBACK", 1) != 0 && nlanes >= 2 && hardTail > 0;
+    int nHeavy = int(Renderer<CudaBackend>::envInt("NRT_HEAVY_LANES", nlanes >= 4 ? 2 : 1));
+    nHeavy = std::max(1, std::min(nHeavy, nlanes - 1));
+    for (int di = 0; di < nd; ++di) {
+      auto& units = devUnits[size_t(di)];
+      units = rowsFor(o->height, y0, y1, step, g_part_index * nd + di, nd * g_part_count, 0, 1, T);
+      const BandFeedback& f = sc->dev[size_t(di)].fbk;
+      bool planned = false;
+      if (useFbk && f.key == bandKey && f.y == units && !units.empty()) {
+        std::vector<uint32_t> idx(units.size());
+        for (size_t j = 0; j < idx.size(); ++j) idx[j] = uint32_t(j);
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return f.hard[a] < f.hard[b]; });
+        const int nLight = nlanes - nHeavy;
+        const int64_t budget = int64_t(nLight) * hardTail * 3 / 4;
+        std::vector<char> light(units.size(), 0);
+        int64_t sum = 0; size_t nl = 0;
+        for (; nl < idx.size() && sum + f.hard[idx[nl]] <= budget; ++nl) { sum += f.hard[idx[nl]]; light[idx[nl]] = 1; }
+        if (nl >= units.size() / 8 && nl < units.size()) {
+          planned = true;
+          int ih = 0, il = 0;
+          for (size_t j = 0; j < units.size(); ++j) {
+            if (light[j]) laneRows[size_t(di)][size_t(nHeavy + (il++ % nLight))].push_back(units[j]);
+            else laneRows[size_t(di)][size_t(ih++ % nHeavy)].push_back(units[j]);
+          }
+          for (int ln = nHeavy; ln < nlanes; ++ln) laneLow[size_t(di)][size_t(ln)] = 1;
+          if (std::getenv("NRT_TRACE_LANES"))
+            fprintf(stderr, "[lanes] dev %d: %zu bands, %zu light (%lld wavefront samples last frame), %d heavy + %d light lanes\n",
+                    di, units.size(), nl, (long long)sum, nHeavy, nLight);
+        }
+      }
+      if (!planned)
+        for (size_t j = 0; j < units.size(); ++j) laneRows[size_t(di)][j % size_t(nlanes)].push_back(units[j]);
+    }
+  }
   std::vector<int> rc(nunits, NRT_OK);
   std::vector<std::string> errs(nunits);
   std::vector<std::vector<unsigned long long>> st(nunits, std::vector<unsigned long long>(ST_COUNT, 0));
@@ -1471,13 +1593,30 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
       DeviceCtx* dc = g_devs[di];
       CudaBackend& be = dc->be;
       be.use();
+      for (int k = 0; k < nlanes && k <= int(dc->extra.size()); ++k) {
+        CudaBackend& lb = dc->lane(k);
+        lb.stream = laneLow[size_t(di)][size_t(k)] ? lb.sLo : lb.sHi;
+      }
       while (int(dc->extra.size()) + 1 < nlanes) {
         auto* b = new CudaBackend();
         b->device = be.device; b->sms = be.sms;
-        NRT_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+        b->createStreams();
+        if (laneLow[size_t(di)][dc->extra.size() + 1]) b->stream = b->sLo;
         dc->extra.push_back(b);
         cudaEvent_t e; NRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         dc->laneDone.push_back(e);
+      }
+      while (int(dc->subBe.size()) < nlanes) {
+        auto* b = new CudaBackend();
+        b->device = be.device; b->sms = be.sms;
+        b->createStreams();
+        dc->subBe.push_back(b);
+        dc->helpers.push_back(new Helper());
+      }
+      for (int k = 0; k < nlanes; ++k) {
+        CudaBackend& sb = *dc->subBe[size_t(k)];
+        sb.stream = laneLow[size_t(di)][size_t(k)] ? sb.sLo : sb.sHi;
+        dc->lane(k).helper = dc->helpers[size_t(k)];
       }
       if (qspec) {
         const int64_t need = npx * outBytesPerPixel(*qspec);
@@ -1511,9 +1650,12 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     DeviceCtx* dc = g_devs[di];
     CudaBackend& be = dc->lane(ln);
     pd.rn[ln].be = &be;
+    CudaBackend& sbe = *dc->subBe[size_t(ln)];
+    pd.rnSub[ln].be = &sbe;
+    pd.rn[ln].sub = &pd.rnSub[ln];
     try {
       be.use();
-      const std::vector<int32_t> rows = rowsFor(o->height, y0, y1, step, g_part_index * nd + di, nd * g_part_count, ln, nlanes, T);
+      const std::vector<int32_t>& rows = laneRows[size_t(di)][size_t(ln)];
       float* target = fb;
       int32_t *aObj = nullptr, *aTri = nullptr; double* aT = nullptr;
       OutStage qs{};
@@ -1529,12 +1671,13 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
       } else if (wantAov) {
         aObj = aov->obj_id; aTri = aov->tri_id; aT = aov->t_hit;
       }
-      be.launches = 0;
-      be.timing = dc->be.timing;
+      be.launches = 0; sbe.launches = 0;
+      be.timing = sbe.timing = dc->be.timing;
       if (const char* e = std::getenv("NRT_PREFILTER_CULL")) be.cull = std::atoi(e) != 0; else be.cull = true;
       if (const char* e = std::getenv("NRT_PREFILTER_SPLIT")) be.splitBelow = std::max(0, std::atoi(e));
       if (const char* e = std::getenv("NRT_PREFETCH_AHEAD")) be.prefetchAhead = std::max<int64_t>(0, std::atoll(e));
       else be.prefetchAhead = int64_t(be.sms) * 512;   // measured on B200, config 4: off 25.23 ms; 256..2048 per SM 24.75-24.81; 4096 per SM 25.28
+      sbe.cull = be.cull; sbe.splitBelow = be.splitBelow; sbe.prefetchAhead = be.prefetchAhead;
       // Host <-> staging copies of exactly the rows this worker renders (and their step x step
       // fill rows); equally spaced rows (scanline interleave) go out as one 2D copy.
       auto copyRows = [&](bool toHost) {
@@ -1594,6 +1737,28 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
   for (int u = 0; u < nunits; ++u)
     if (rc[u] != NRT_OK) return fail(rc[u], errs[u]);
 
+  // the per-band counts of this frame, for the next one's lane plan
+  for (int di = 0; di < nd; ++di) {
+    PerDevice& pd = sc->dev[size_t(di)];
+    BandFeedback& f = pd.fbk;
+    const auto& units = devUnits[size_t(di)];
+    std::vector<uint32_t> hard(units.size(), 0);
+    bool ok = !units.empty();
+    for (int ln = 0; ln < nlanes && ok; ++ln) {
+      const auto& rows = laneRows[size_t(di)][size_t(ln)];
+      const auto& bh = pd.rn[ln].bandHard;
+      if (rows.empty()) continue;
+      if (bh.size() != rows.size()) { ok = false; break; }
+      for (size_t k = 0; k < rows.size(); ++k) {
+        const auto it = std::lower_bound(units.begin(), units.end(), rows[k]);
+        if (it == units.end() || *it != rows[k]) { ok = false; break; }
+        hard[size_t(it - units.begin())] = bh[k];
+      }
+    }
+    if (ok) { f.key = bandKey; f.y = units; f.hard.swap(hard); }
+    else { f.key.clear(); f.y.clear(); f.hard.clear(); }
+  }
+
   nrt_profile& p = sc->prof;
   p = nrt_profile{};
   unsigned long long tot[ST_COUNT] = {0};
@@ -1606,15 +1771,17 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     cudaEventElapsedTime(&ms, dc->ev0, dc->ev1);
     p.total_ms = std::max(p.total_ms, double(ms));
    double fmsDev = 0;
-   for (int ln = 0; ln < nlanes; ++ln) {
-    CudaBackend& lbe = dc->lane(ln);
+   for (int lb = 0; lb < 2 * nlanes; ++lb) {
+    const int ln = lb >> 1;
+    const bool isSub = (lb & 1) != 0;         // the lane's helper pipeline: its launches, prefilter times and timeline
+    CudaBackend& lbe = isSub ? *dc->subBe[size_t(ln)] : dc->lane(ln);
     int64_t nl = 0;
     double byMode[4] = {0, 0, 0, 0};
     std::vector<float> each;
     const bool traceP = std::getenv("NRT_TRACE_PREFILTER") != nullptr;
     const double fms = lbe.filterMs(&nl, byMode, traceP ? &each : nullptr);
     if (traceP) {
-      const auto& lg = sc->dev[d].rn[ln].preLog;
+      const auto& lg = isSub ? sc->dev[d].rnSub[ln].preLog : sc->dev[d].rn[ln].preLog;
       for (size_t i = 0; i < lg.size() && i < each.size(); ++i)
         fprintf(stderr, "[prefilter] dev %d wave %2d mo %d bundle %d mode %d rays %9lld runs %7lld chunks %4lld work %9lld (%.2f per run) pre %9lld  %8.1f us\n",
                 d, lg[i].wave, lg[i].mo, lg[i].b, lg[i].mode, (long long)lg[i].rays,
@@ -1624,6 +1791,19 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     }
     fmsDev += fms;   // (the lanes' prefilter launches of one device: summed CUDA-event time; they may overlap)
     p.mesh_filter_launches += nl;
+    p.kernel_launches += lbe.launches;
+    if (lbe.timing)
+      if (const char* tl = std::getenv("NRT_TIMELINE"))
+        if (FILE* f = std::fopen(tl, "a")) { lbe.dumpTimeline(f, dc->ev0, d, ln + (isSub ? 10 : 0)); std::fclose(f); }
+    if (lbe.timing && d == 0 && ln == 0) {
+      if (!isSub) sc->ktimes = nrt_kernel_times{};
+      lbe.collectTimes(sc->ktimes.ms, sc->ktimes.launches, sc->ktimes.max_ms);
+    } else if (lbe.timing) {
+      nrt_kernel_times scratchT{};
+      lbe.collectTimes(scratchT.ms, scratchT.launches, scratchT.max_ms);
+    }
+    for (int m = 0; m < 3; ++m) p.mesh_ms_by_mode[m] += byMode[m];
+    if (isSub) continue;                       // (the helper's counters are merged into its lane's profile)
     const ProfileAcc& a = sc->dev[d].rn[ln].prof;
     p.mesh_tests += a.mesh_tests; p.mesh_tests_ref += a.mesh_tests_ref; p.mesh_rays += a.mesh_rays;
     p.candidates += a.candidates;
@@ -1631,17 +1811,8 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
     for (int b = 0; b < 8; ++b) { p.active_samples[b] += a.active[b]; p.wavefront_samples[b] += a.wavefront[b]; }
     p.tail_samples += a.tail;
     p.lanes = nlanes;
-    p.kernel_launches += lbe.launches;
-    if (lbe.timing && d == 0 && ln == 0) {
-      sc->ktimes = nrt_kernel_times{};
-      lbe.collectTimes(sc->ktimes.ms, sc->ktimes.launches, sc->ktimes.max_ms);
-    } else if (lbe.timing) {
-      nrt_kernel_times scratchT{};
-      lbe.collectTimes(scratchT.ms, scratchT.launches, scratchT.max_ms);
-    }
     for (int m = 0; m < 3; ++m) {
       p.mesh_tests_by_mode[m] += a.tests_by_mode[m];
-      p.mesh_ms_by_mode[m] += byMode[m];
       // executed float32 flops per prefilter test (FFMA = 2): nrt_filter.h prefilterFlops()
       p.fp32_flops += double(a.tests_by_mode[m]) * prefilterFlops(m);
     }
@@ -1687,6 +1858,8 @@ void nrt_shutdown(void) {
     for (auto*& t : d->thr) { if (t) cudaFree(t); t = nullptr; }
     if (d->outFb) cudaFree(d->outFb);
     if (d->outQ) cudaFree(d->outQ);
+    for (auto* h : d->helpers) delete h;
+    for (auto* b : d->subBe) { b->destroy(); delete b; }
     for (auto* b : d->extra) { b->destroy(); delete b; }
     d->be.destroy();
     delete d;
@@ -1754,6 +1927,7 @@ void nrt_scene_destroy(nrt_scene* scene) {
     CudaBackend& be = g_devs[d]->be;
     pd.sd.destroy();
     for (int k = 0; k < kMaxLanes; ++k) if (pd.rn[k].be) pd.rn[k].freeAll();
+    for (int k = 0; k < kMaxLanes; ++k) if (pd.rnSub[k].be) pd.rnSub[k].freeAll();
     be.dfree(pd.fbStage); be.dfree(pd.qStage); be.dfree(pd.aovObj); be.dfree(pd.aovTri); be.dfree(pd.aovT);
   }
   delete scene;

@@ -183,6 +183,24 @@ struct DMesh {
 //   r2m = rb^2 (1 + 2e-6) + 2e-7 |c|_inf^2 (rounded up),   mm = 2e-7 |c|_inf^2 (rounded up)
 // valid == 0: no float32 shortcut for this object (general matrix, non-finite values).
 struct alignas(16) MeshGateF { float cx, cy, cz, r2m; float mm, valid, pad0, pad1; };
+// Light-space grid of the spheres, one per DistantLight (scenes with sphere clusters).  Every shadow ray of a distant
+// light has the same direction u (renderer.nim:99, light.nim), so a sphere can only be hit by the rays whose origin
+// projects — along u, onto the plane (e1, e2) — into the sphere's projected circle.  The plane is cut into G x G cells;
+// a cell lists, ASCENDING (the in-order scan of trace() decides ties and Stats), the spheres whose circle, inflated by
+// every error a ray's float32 projection can carry, touches it.  A shadow ray reads ONE cell.
+//   circle of sphere i (centre c, radius r):  radius r (1 + 1e-6) + 4e-7 |c|_1 + margin + 1e-4 h   (h = cell edge)
+//     1e-6      e1, e2 are float32 vectors: unit and perpendicular to u only to ~1e-7
+//     4e-7|c|_1 the same tilt seen from the sphere's side (|e.(c - o)| is off by <= 1.7e-7 (|c| + |o|))
+//     margin    what the ray may carry: the grid takes a ray only if 1e-6 |o|_1 <= margin (conversion of o to float32,
+//               three float32 products and sums, the tilt seen from the ray's side); other rays use the cluster traversal
+//     1e-4 h    rounding of (p - lo) / h
+struct ShadowGridF {
+  float e1[3], e2[3];
+  float lo1, lo2, invh, margin;
+  int32_t G, _pad;
+  const uint32_t* start;   // G * G + 1 offsets into items
+  const uint32_t* items;   // object indices
+};
 struct BundleFrame;  // nrt_filter.h
 struct RecSet;       // nrt_filter.h
 
@@ -206,6 +224,7 @@ struct DScene {
   const BundleFrame* frames;      // [mo * (2 + nlights) + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
   const RecSet* recsets;          // same index: the filter record set of the bundle (per-thread mesh walk of the path kernels)
   const MeshGateF* mgate;         // per mesh object: float32 world-space bounding sphere of its box (meshGateMissF)
+  const ShadowGridF* sgrid;       // per light (G == 0: none), or null: light-space grids of the clustered spheres
   double c2w[16];
   double cam_orig[4];             // c2w * (0,0,0,1): castPrimaryRay's origin (renderer.nim:42), the same product done once on the host
   double tan_half_fov;            // f of renderer.nim:38 (host libm, shared with nothing else)
@@ -302,6 +321,108 @@ NRT_HD bool certainMissF(const CObjF& c, const RayF& r) {
   const float o2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
   return b * b < r.a * fmaf(o2, 0.999995f, -(c.r2m + r.mray));
 }
+
+// The cell of a shadow ray (origin rf.o; its direction is the grid's light direction by construction).
+// false: the grid does not take this ray (far origin, non-finite values): use the cluster traversal.
+// true: items [b, e) are the clustered spheres the ray can possibly hit (b == e outside the grid).
+NRT_HD bool shadowGridCell(const ShadowGridF& g, const RayF& rf, uint32_t& b, uint32_t& e) {
+  const float err = 1e-6f * (fabsf(rf.ox) + fabsf(rf.oy) + fabsf(rf.oz));
+  if (!(err <= g.margin)) return false;
+  const float p1 = fmaf(g.e1[0], rf.ox, fmaf(g.e1[1], rf.oy, g.e1[2] * rf.oz));
+  const float p2 = fmaf(g.e2[0], rf.ox, fmaf(g.e2[1], rf.oy, g.e2[2] * rf.oz));
+  const float f1 = (p1 - g.lo1) * g.invh, f2 = (p2 - g.lo2) * g.invh;
+  b = e = 0;
+  if (!(f1 >= 0.f && f2 >= 0.f && f1 < float(g.G) && f2 < float(g.G))) return f1 == f1 && f2 == f2;   // outside (NaN: not taken)
+  int c1 = int(f1), c2 = int(f2);
+  if (c1 > g.G - 1) c1 = g.G - 1;
+  if (c2 > g.G - 1) c2 = g.G - 1;
+  const uint32_t cell = uint32_t(c2) * uint32_t(g.G) + uint32_t(c1);
+  b = g.start[cell]; e = g.start[cell + 1];
+  return true;
+}
+
+#if defined(__CUDA_ARCH__)
+// ---- the warp's rays as ONE bundle ---------------------------------------------------------------------------
+// The lanes of a warp that trace together hold neighbouring samples (one or two pixels' worth), so their rays form a
+// thin bundle.  The bundle is described by its leader's ray (o_c, unit u_c) and two spreads: dO >= |o_i - o_c| and
+// dD >= |u_i - u_c| for every participating lane i.  For a sphere (centre c, radius r) and any lane i, with D_i the
+// distance of c from lane i's LINE and s_i the parameter of the closest point (|s_i| <= |o_i - c| <= |o_c - c| + dO):
+//     D_i >= D_c - |o_i - o_c| - |s_i| |u_i - u_c| >= D_c - (dO + (|o_c - c| + dO) dD) = D_c - Delta.
+// So if the LEADER's line passes the certain-miss test of certainMissF() against the radius r + Delta (plus a margin
+// of 1e-6 |o_c - c| that keeps every lane's exact discriminant away from zero by far more than the float64
+// evaluation's rounding), every lane's reference discriminant is negative: the sphere — or, for a cluster bound, every
+// member — is skipped by the whole warp after ONE test in ONE lane.  The tests of up to 32 records run side by
+// side in the warp's lanes (bundleScan, nrt_pipeline.h).  Conservative by construction: only "certainly missed by
+// all" is ever concluded, everything else goes to the per-ray first look and the float64 evaluation as before.
+struct RayBundle {
+  unsigned wm;            // participating lanes
+  int rank, nact;         // this lane's rank among them, their number
+  bool on;                // the bundle test applies (all rays float32-safe, spreads finite and small)
+  float ox, oy, oz, ux, uy, uz, a, mray, dO, dD;
+};
+__device__ __forceinline__ RayBundle makeRayBundle(const RayF& r, bool f32ok) {
+  RayBundle B;
+  B.wm = __activemask();
+  const unsigned lane = threadIdx.x & 31u;
+  B.rank = __popc(B.wm & ((1u << lane) - 1u));
+  B.nact = __popc(B.wm);
+  const int leader = __ffs(int(B.wm)) - 1;
+  const float inv = rsqrtf(r.a);
+  const float ux = r.dx * inv, uy = r.dy * inv, uz = r.dz * inv;
+  B.ox = __shfl_sync(B.wm, r.ox, leader); B.oy = __shfl_sync(B.wm, r.oy, leader); B.oz = __shfl_sync(B.wm, r.oz, leader);
+  B.ux = __shfl_sync(B.wm, ux, leader); B.uy = __shfl_sync(B.wm, uy, leader); B.uz = __shfl_sync(B.wm, uz, leader);
+  const float ex = r.ox - B.ox, ey = r.oy - B.oy, ez = r.oz - B.oz;
+  const float fx = ux - B.ux, fy = uy - B.uy, fz = uz - B.uz;
+  const float eo2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez)), ed2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+  // maxima over the lanes: non-negative floats order like their bit patterns (a NaN is larger than everything and
+  // switches the bundle test off below)
+  const float mo2 = __uint_as_float(__reduce_max_sync(B.wm, __float_as_uint(eo2)));
+  const float md2 = __uint_as_float(__reduce_max_sync(B.wm, __float_as_uint(ed2)));
+  const float moc = fmaxf(fabsf(B.ox), fmaxf(fabsf(B.oy), fabsf(B.oz)));
+  // spreads, rounded up: the float32 conversions of o (2^-24 |o| per component), of u and the approximate rsqrt
+  B.dO = sqrtf(mo2) * 1.0001f + 4e-7f * moc;
+  B.dD = sqrtf(md2) * 1.0001f + 2e-6f;
+  const float mo = moc + B.dO;
+  B.mray = 2e-7f * (mo * mo);
+  B.a = fmaf(B.ux, B.ux, fmaf(B.uy, B.uy, B.uz * B.uz));
+  B.on = __all_sync(B.wm, f32ok) && B.dD < 0.5f && B.dO < 1e15f && B.a > 0.99f && B.a < 1.01f;
+  return B;
+}
+// true => EVERY ray of the bundle certainly misses the sphere (or cluster bound) c: certainMissF()'s test for the
+// leader's line against the radius sqrt(r2m) + Delta
+__device__ __forceinline__ bool bundleMiss(const CObjF& c, const RayBundle& B) {
+  if (c.r2m < 0.f) return true;    // never-hit padding record of a cluster
+  const float ox = B.ox + c.tx, oy = B.oy + c.ty, oz = B.oz + c.tz;
+  const float b = fmaf(B.ux, ox, fmaf(B.uy, oy, B.uz * oz));
+  const float o2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
+  const float doc = sqrtf(o2) * 1.000001f;
+  const float delta = fmaf(doc + B.dO, B.dD, B.dO) * 1.001f + 1e-6f * doc;
+  const float rr = sqrtf(c.r2m) + delta;
+  const float R2 = rr * rr * 1.000004f;
+  // (records without a float32 sphere: r2m = +Inf -> R2 = +Inf -> false; NaN anywhere -> false)
+  return b * b < B.a * fmaf(o2, 0.999995f, -(R2 + B.mray));
+}
+// Calls f(k), warp-uniformly and in ascending k, for every record recs[k], k in [0, count), that some ray of the
+// bundle may hit: the participating lanes test `nact` records per step side by side, one ballot per step.
+template <class F>
+__device__ __forceinline__ void bundleScan(const RayBundle& B, const CObjF* recs, int count, F&& f) {
+  for (int base = 0; base < count; base += B.nact) {
+    const int k = base + B.rank;
+    bool cand = false;
+    if (k < count) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(recs + k));
+      CObjF c; c.tx = a.x; c.ty = a.y; c.tz = a.z; c.r2m = a.w;
+      cand = !bundleMiss(c, B);
+    }
+    unsigned m = __ballot_sync(B.wm, cand);
+    while (m) {
+      const int src = __ffs(int(m)) - 1;
+      m &= m - 1;
+      f(base + __popc(B.wm & ((1u << src) - 1u)));
+    }
+  }
+}
+#endif
 
 // true => the ray (t >= 0) certainly does not enter the mesh object's box, i.e. the reference's slab test
 // (geom.nim:76-96) returns NegInf or a negative tmin and TriangleMesh.intersect returns at geom.nim:340:

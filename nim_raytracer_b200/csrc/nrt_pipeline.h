@@ -171,6 +171,7 @@ struct ChunkState {
   uint32_t* counters;  // maxWaves*nMO*cntStride(nL)
   uint32_t* alist;     // 2*S: compacted sample indices of the continuing paths (ping-pong per bounce)
   uint32_t* hlist;     // S: the samples of the current bounce that go through the wavefront (fused path)
+  uint32_t* flist;     // S: the samples handed to the helper pipeline at bounce 0 (the fork)
   uint32_t* acount;    // per bounce: entries of the list consumed by that bounce
   unsigned long long* stats;  // ST_COUNT
   // pixel list of this worker
@@ -759,17 +760,99 @@ NRT_HD bool meshGatePassPre(const DScene& sc, int mo, V4 o, V4 d, const RayPre& 
   return meshGatePass(sc, mo, o, d);
 }
 
+// `sl` >= 0: the ray is a shadow ray towards light sl (its direction is that light's: the light-space grid applies)
 template <bool CL, class MP>
-NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, const RayPre& pre);
+NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, const RayPre& pre, int sl = -1);
 template <bool CL, class MP>
-NRT_HD TraceOut traceObjects(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear) {
-  return traceObjectsPre<CL>(sc, mp, o, d, tNear, makeRayPre(o, d));
+NRT_HD TraceOut traceObjects(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, int sl = -1) {
+  return traceObjectsPre<CL>(sc, mp, o, d, tNear, makeRayPre(o, d), sl);
 }
 template <bool CL, class MP>
-NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, const RayPre& pre) {
+NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, const RayPre& pre, int sl) {
   TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
   const bool f32ok = pre.f32ok, fastRay = pre.fastRay;
   const RayF rf = pre.rf;
+  if (CL && sc.ncl1 > 0 && sl >= 0 && sc.sgrid && f32ok) {
+    // a DistantLight's shadow ray: the clustered spheres it can hit are listed in ONE cell of the light-space grid
+    const ShadowGridF g = sc.sgrid[sl];
+    uint32_t gb = 0, ge = 0;
+    if (g.G > 0 && shadowGridCell(g, rf, gb, ge) && ge - gb + uint32_t(sc.nslow) <= uint32_t(kSurvivorCap)) {
+      uint32_t surv[kSurvivorCap] = {0};
+      int ns = 0;
+      auto push = [&](uint32_t i) {   // (cell lists and slowIdx are ascending; merged in list order)
+        int k = ns++;
+        while (k > 0 && surv[k - 1] > i) { surv[k] = surv[k - 1]; --k; }
+        surv[k] = i;
+      };
+      for (uint32_t k = gb; k < ge; ++k) {
+        const uint32_t i = g.items[k];
+        if (!certainMissF(loadCObjF(sc.cobjf + i), rf)) push(i);
+      }
+      for (int k = 0; k < sc.nslow; ++k) {
+        const uint32_t i = sc.slowIdx[k];
+        if (!firstLookMiss(mp, loadCObjF(sc.cobjf + i), rf, f32ok)) push(i);
+      }
+      r.tests = sc.nobjects;
+      for (int k = 0; k < ns; ++k) evalObject(sc, mp, int(surv[k]), o, d, fastRay, r);
+      return r;
+    }
+  }
+#if defined(__CUDA_ARCH__)
+  // The warp's rays as one bundle (nrt_core.h: RayBundle): whole objects and whole sphere clusters are dropped for
+  // every lane after one test in one lane; the per-ray first look and the float64 evaluation see only the rest.
+  // (clustered scenes only: a bundle costs ~100 instructions per trace — on BASELINE config 4's nine objects the flat
+  // per-ray scan is cheaper: FusedBounce 11.0 ms without the bundle, 13.1 ms with it, measured)
+  RayBundle B;
+  B.on = false;
+  if (CL && sc.ncl1 > 0) B = makeRayBundle(rf, f32ok);
+  if (CL && sc.ncl1 > 0 && B.on) {
+    // A bundle that is fat where the spheres are (shadow rays leaving a triangle soup: origins spread along the view
+    // rays) admits almost every cluster and is worse than the per-ray traversal: the leader's own ray is tested next to
+    // the bundle at level 1, and a bundle that admits more than twice what the one ray admits (+2) is given up.
+    int nbu = 0, nld = 0;
+    RayF lf; lf.ox = B.ox; lf.oy = B.oy; lf.oz = B.oz; lf.dx = B.ux; lf.dy = B.uy; lf.dz = B.uz; lf.a = B.a; lf.mray = B.mray;
+    for (int base = 0; base < sc.ncl1; base += B.nact) {
+      const int k = base + B.rank;
+      bool cb = false, cl = false;
+      if (k < sc.ncl1) { const CObjF c = loadCObjF(sc.cl1 + k); cb = !bundleMiss(c, B); cl = !certainMissF(c, lf); }
+      nbu += __popc(__ballot_sync(B.wm, cb)); nld += __popc(__ballot_sync(B.wm, cl));
+    }
+    if (nbu > 2 * nld + 2) B.on = false;
+  }
+  if (CL && sc.ncl1 > 0 && B.on) {
+    uint32_t surv[kSurvivorCap] = {0};
+    int ns = 0;
+    bool full = false;
+    auto push = [&](uint32_t i) {
+      if (i == kInvalidRef) return;   // padding slot of a cluster
+      if (ns == kSurvivorCap) { full = true; return; }
+      int k = ns++;
+      while (k > 0 && surv[k - 1] > i) { surv[k] = surv[k - 1]; --k; }
+      surv[k] = i;
+    };
+    bundleScan(B, sc.cl1, sc.ncl1, [&](int a1) {
+      bundleScan(B, sc.cl2 + a1 * kClusterSize, kClusterSize, [&](int c2) {
+        const int a2 = a1 * kClusterSize + c2;
+        bundleScan(B, sc.clm + a2 * kClusterSize, kClusterSize, [&](int cm) {
+          const int m = a2 * kClusterSize + cm;
+          if (!certainMissF(loadCObjF(sc.clm + m), rf)) push(sc.clmIdx[m]);
+        });
+      });
+    });
+    for (int k = 0; k < sc.nslow; ++k) {
+      const uint32_t i = sc.slowIdx[k];
+      if (!firstLookMiss(mp, loadCObjF(sc.cobjf + i), rf, f32ok)) push(i);
+    }
+    // (a full list — more than kSurvivorCap objects along one ray — falls back to the flat scan below; a lane that
+    // leaves here no longer takes part in the warp's later bundle steps, which only makes those bundles smaller)
+    if (!full) {
+      r.tests = sc.nobjects;
+      for (int k = 0; k < ns; ++k) evalObject(sc, mp, int(surv[k]), o, d, fastRay, r);
+      return r;
+    }
+  }
+  if (!(CL && sc.ncl1 > 0 && B.on))
+#endif
   if (CL && sc.ncl1 > 0 && f32ok) {
     // Scenes with many spheres: a flattened two-level traversal of the sphere clusters.  A ray that
     // certainly misses a cluster's bounding sphere certainly misses every member, so whole groups of
@@ -1000,7 +1083,7 @@ struct ShadowTraceSampleT {
       const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
       const V4 sd = scale(li.lightDir, -1.0);                                      // renderer.nim:99
       const uint8_t code0 = (l < 4) ? uint8_t(codes >> (8 * l)) : ((cs.nMO > 0) ? cs.gflag[idx * cs.nL + l] : uint8_t(0));
-      const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s * cs.nL + l, idx * cs.nL + l, code0}, so, sd, li.lightDistance);
+      const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s * cs.nL + l, idx * cs.nL + l, code0}, so, sd, li.lightDistance, l);
       st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
       cs.occ[s * cs.nL + l] = tr.obj >= 0 ? 1 : 0;
     }
@@ -1117,7 +1200,7 @@ struct ShadowResolveT {
         const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
         const V4 sd = scale(li.lightDir, -1.0);                                      // renderer.nim:99
         const uint8_t code0 = (l < 4) ? uint8_t(codes >> (8 * l)) : ((cs.nMO > 0) ? cs.gflag[idx * cs.nL + l] : uint8_t(0));
-        const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s * cs.nL + l, idx * cs.nL + l, code0}, so, sd, li.lightDistance);
+        const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s * cs.nL + l, idx * cs.nL + l, code0}, so, sd, li.lightDistance, l);
         st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
         occ |= uint32_t(tr.obj >= 0 ? 1u : 0u) << l;
       }
@@ -1229,7 +1312,7 @@ struct FusedBounceT {
       for (int l = 0; l < nL; ++l) {
         const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
         const V4 sdir = scale(li.lightDir, -1.0);                                    // renderer.nim:99
-        const TraceOut ts = traceObjects<CL>(*sc, NoMesh{}, so, sdir, li.lightDistance);
+        const TraceOut ts = traceObjects<CL>(*sc, NoMesh{}, so, sdir, li.lightDistance, l);
         st.v[ST_RAYS] += 1; st.v[ST_TESTS] += ts.tests; st.v[ST_HITS] += ts.hits;
         if (ts.obj < 0) local = add(local, shadeDiffuse(ob, li, n));                 // renderer.nim:103-105
       }
@@ -1305,9 +1388,14 @@ struct PathWarpT {
     if (valid) {
       if (KIND == PATH_TAIL) {
         s = sampleOf(act, idx);
-        o = ld4(cs.rayO, cs.S, s); d = ld4(cs.rayD, cs.S, s);
-        w = cs.weight[s];
-        a0 = cs.accum[s]; a1 = cs.accum[cs.S + s]; a2 = cs.accum[2 * cs.S + s];
+        d = ld4(cs.rayD, cs.S, s);
+        if (bounce0 == 0) {   // a sample FusedBounce handed over at bounce 0: only its primary direction is stored
+          o = primaryOrigin(*sc);
+        } else {
+          o = ld4(cs.rayO, cs.S, s);
+          w = cs.weight[s];
+          a0 = cs.accum[s]; a1 = cs.accum[cs.S + s]; a2 = cs.accum[2 * cs.S + s];
+        }
       } else {
         s = idx;
         if (genFromState) {
@@ -1348,7 +1436,7 @@ struct PathWarpT {
         const int smode = sc->lights[l].kind == LIGHT_DISTANT ? FM_DIR : FM_GENERAL;
         coop.meshAll(*sc, hit, smode, l, so, sdir, force_exact, mr);
         if (hit) {
-          const TraceOut ts = traceObjects<CL>(*sc, PreMesh{mr, WalkMesh{sc, smode, l, force_exact}}, so, sdir, li.lightDistance);
+          const TraceOut ts = traceObjects<CL>(*sc, PreMesh{mr, WalkMesh{sc, smode, l, force_exact}}, so, sdir, li.lightDistance, l);
           st.v[ST_RAYS] += 1; st.v[ST_TESTS] += ts.tests; st.v[ST_HITS] += ts.hits;
           if (ts.obj < 0) local = add(local, shadeDiffuse(sc->objects[tr.obj], li, n));   // renderer.nim:103-105
         }
@@ -1372,7 +1460,10 @@ struct PathWarpT {
       }
       ++bounce;   // (the same for every lane that is still alive)
     }
-    if (started) { cs.accum[s] = a0; cs.accum[cs.S + s] = a1; cs.accum[2 * cs.S + s] = a2; }
+    if (started) {
+      cs.accum[s] = a0; cs.accum[cs.S + s] = a1; cs.accum[2 * cs.S + s] = a2;
+      if (KIND == PATH_TAIL) cs.active[s] = 0;   // finished: not on any later list (a hard list taken mid-frame)
+    }
     return st;
   }
 };
@@ -1380,6 +1471,47 @@ using PathTail = PathWarpT<false, PATH_TAIL>;
 using PathTailClustered = PathWarpT<true, PATH_TAIL>;
 using PathMega = PathWarpT<false, PATH_MEGA>;
 using PathMegaClustered = PathWarpT<true, PATH_MEGA>;
+
+// ---- the fork (nrt_renderer.h: Renderer::sub): the samples FusedBounce finished at bounce 0 with a reflection ray
+// stored are moved into a second pipeline's sample space (positions 0 .. n-1, in list order) and come back as their
+// accumulators.  `a`: the main pipeline's state, `b`: the helper's.
+struct GatherPool {
+  ChunkState a, b; const uint32_t* list;
+  NRT_HD void operator()(int64_t i) const {
+    const int64_t s = int64_t(list[i]);
+    st4(b.rayO, b.S, i, ld4(a.rayO, a.S, s));
+    st4(b.rayD, b.S, i, ld4(a.rayD, a.S, s));
+    b.weight[i] = a.weight[s];
+    b.accum[i] = a.accum[s]; b.accum[b.S + i] = a.accum[a.S + s]; b.accum[2 * b.S + i] = a.accum[2 * a.S + s];
+  }
+};
+struct ScatterAccum {
+  ChunkState a, b; const uint32_t* list;
+  NRT_HD void operator()(int64_t i) const {
+    const int64_t s = int64_t(list[i]);
+    a.accum[s] = b.accum[i]; a.accum[a.S + s] = b.accum[b.S + i]; a.accum[2 * a.S + s] = b.accum[2 * b.S + i];
+  }
+};
+
+// ---- per-band counts of a sorted sample list (the bounce-0 wavefront list): the next frame's lane partition
+// puts the bands with mesh work first (nrt.cu: lanesFor).  One thread per band: two binary searches.
+struct BandCount {
+  const uint32_t* list; const uint32_t* count; int64_t p0, band_pix, nS; int spp; uint32_t* out;
+  NRT_HD int64_t lowerBound(int64_t n, int64_t key) const {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (int64_t(list[mid]) < key) lo = mid + 1; else hi = mid; }
+    return lo;
+  }
+  NRT_HD void operator()(int64_t b) const {
+    int64_t n = int64_t(*count);
+    if (n > nS) n = nS;
+    int64_t lo = (b * band_pix - p0) * spp, hi = ((b + 1) * band_pix - p0) * spp;
+    if (lo < 0) lo = 0;
+    if (hi > nS) hi = nS;
+    if (hi <= lo || n == 0) return;
+    out[b] += uint32_t(lowerBound(n, hi) - lowerBound(n, lo));
+  }
+};
 
 // ---- finalize: sample sum in order, * 1/N, float32 store (+ step x step fill)
 struct Finalize {

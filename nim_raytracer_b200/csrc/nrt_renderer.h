@@ -228,6 +228,108 @@ struct SceneData {
     h.nslow = int32_t(std::count_if(cobjf.begin(), cobjf.end(), [](const CObjF& f) { return !(f.r2m < 3.0e38f); }));
   }
 
+  // Light-space grids of the clustered spheres, one per DistantLight (nrt_core.h: ShadowGridF).  Host, float64.
+  std::vector<void*> gridOwned;
+  ShadowGridF* dSGrid = nullptr;
+  void buildShadowGrids() {
+    for (void* p : gridOwned) be->dfree(p);
+    gridOwned.clear();
+    dSGrid = nullptr;
+    h.sgrid = nullptr;
+    if (h.ncl1 <= 0 || lights.empty()) return;
+    std::vector<uint32_t> fast;
+    for (size_t i = 0; i < cobjf.size(); ++i) if (cobjf[i].r2m < 3.0e38f) fast.push_back(uint32_t(i));
+    std::vector<ShadowGridF> grids(lights.size(), ShadowGridF{});
+    bool any = false;
+    auto gup = [&](const uint32_t* src, size_t n) {
+      uint32_t* p = static_cast<uint32_t*>(be->dalloc(sizeof(uint32_t) * std::max<size_t>(n, 1)));
+      gridOwned.push_back(p);
+      if (n) { be->upload(p, src, sizeof(uint32_t) * n); bytes_uploaded += int64_t(sizeof(uint32_t) * n); }
+      return p;
+    };
+    for (size_t l = 0; l < lights.size(); ++l) {
+      if (lights[l].kind != NRT_LIGHT_DISTANT) continue;
+      // ray direction u = -dir (renderer.nim:99); (e1, e2) spans the plane perpendicular to it
+      double u[3] = {-lights[l].dir[0], -lights[l].dir[1], -lights[l].dir[2]};
+      const double ul = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+      if (!(ul > 1e-3 && ul < 1e3) || lights[l].dir[3] != 0.0) continue;
+      for (double& v : u) v /= ul;
+      int ax = 0;
+      if (std::fabs(u[1]) < std::fabs(u[ax])) ax = 1;
+      if (std::fabs(u[2]) < std::fabs(u[ax])) ax = 2;
+      double a[3] = {0, 0, 0}; a[ax] = 1.0;
+      double e1[3] = {u[1] * a[2] - u[2] * a[1], u[2] * a[0] - u[0] * a[2], u[0] * a[1] - u[1] * a[0]};
+      const double e1l = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+      for (double& v : e1) v /= e1l;
+      double e2[3] = {u[1] * e1[2] - u[2] * e1[1], u[2] * e1[0] - u[0] * e1[2], u[0] * e1[1] - u[1] * e1[0]};
+      ShadowGridF g{};
+      for (int k = 0; k < 3; ++k) { g.e1[k] = float(e1[k]); g.e2[k] = float(e2[k]); }
+      // (the projections below use the float32 vectors the rays will use)
+      const double f1[3] = {g.e1[0], g.e1[1], g.e1[2]}, f2[3] = {g.e2[0], g.e2[1], g.e2[2]};
+      struct Circ { double p1, p2, r, c1; };
+      std::vector<Circ> cs;
+      cs.reserve(fast.size());
+      double lo1 = 1e300, lo2 = 1e300, hi1 = -1e300, hi2 = -1e300, rsum = 0;
+      bool ok = true;
+      for (uint32_t i : fast) {
+        const double c[3] = {-cobjs[i].t[0], -cobjs[i].t[1], -cobjs[i].t[2]};
+        Circ q;
+        q.p1 = f1[0] * c[0] + f1[1] * c[1] + f1[2] * c[2];
+        q.p2 = f2[0] * c[0] + f2[1] * c[1] + f2[2] * c[2];
+        q.r = std::fabs(cobjs[i].radius);
+        q.c1 = std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]);
+        if (!(std::isfinite(q.p1) && std::isfinite(q.p2) && std::isfinite(q.r) && q.c1 < 1e12)) { ok = false; break; }
+        lo1 = std::min(lo1, q.p1 - q.r); hi1 = std::max(hi1, q.p1 + q.r);
+        lo2 = std::min(lo2, q.p2 - q.r); hi2 = std::max(hi2, q.p2 + q.r);
+        rsum += q.r;
+        cs.push_back(q);
+      }
+      if (!ok || cs.empty()) continue;
+      const double ext = std::max(hi1 - lo1, hi2 - lo2);
+      if (!(ext > 0) || !std::isfinite(ext)) continue;
+      int G = int(std::min(1024.0, std::max(16.0, 4.0 * std::sqrt(double(cs.size())))));
+      double hcell = ext * 1.001 / G;
+      const double margin = 0.02 * hcell;
+      // the whole grid is moved out by the largest circle inflation, so that a ray outside it hits nothing
+      double infl = 0;
+      for (const Circ& q : cs) infl = std::max(infl, q.r * 1e-6 + 4e-7 * q.c1 + margin + 1e-4 * hcell);
+      lo1 -= 2 * infl; lo2 -= 2 * infl;
+      hcell = (ext + 4 * infl) * 1.001 / G;
+      g.lo1 = float(lo1); g.lo2 = float(lo2); g.invh = float(1.0 / hcell); g.margin = float(margin * 0.999); g.G = G;
+      // (cell coordinates are computed by the rays as (p - float(lo)) * float(1/h): the build uses the same two floats)
+      const double flo1 = double(g.lo1), flo2 = double(g.lo2), finv = double(g.invh);
+      std::vector<uint32_t> count(size_t(G) * G + 1, 0);
+      auto range = [&](const Circ& q, int& a1, int& b1, int& a2, int& b2) {
+        const double R = q.r * (1.0 + 1e-6) + 4e-7 * q.c1 + margin + 1e-4 * hcell;
+        a1 = int(std::floor((q.p1 - R - flo1) * finv)); b1 = int(std::floor((q.p1 + R - flo1) * finv));
+        a2 = int(std::floor((q.p2 - R - flo2) * finv)); b2 = int(std::floor((q.p2 + R - flo2) * finv));
+        a1 = std::max(a1, 0); a2 = std::max(a2, 0); b1 = std::min(b1, G - 1); b2 = std::min(b2, G - 1);
+      };
+      int64_t total = 0;
+      for (const Circ& q : cs) {
+        int a1, b1, a2, b2; range(q, a1, b1, a2, b2);
+        for (int y = a2; y <= b2; ++y) for (int x = a1; x <= b1; ++x) { ++count[size_t(y) * G + x + 1]; ++total; }
+      }
+      if (total > int64_t(64) * int64_t(cs.size()) + 65536) continue;   // huge circles: no grid for this light
+      for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
+      std::vector<uint32_t> items(size_t(std::max<int64_t>(total, 1)), 0), fill(count.begin(), count.end() - 1);
+      for (size_t n = 0; n < cs.size(); ++n) {   // `fast` ascends, so every cell's list does
+        int a1, b1, a2, b2; range(cs[n], a1, b1, a2, b2);
+        for (int y = a2; y <= b2; ++y) for (int x = a1; x <= b1; ++x) items[fill[size_t(y) * G + x]++] = fast[n];
+      }
+      g.start = gup(count.data(), count.size());
+      g.items = gup(items.data(), size_t(total));
+      grids[l] = g;
+      any = true;
+    }
+    if (!any) return;
+    dSGrid = static_cast<ShadowGridF*>(be->dalloc(sizeof(ShadowGridF) * grids.size()));
+    gridOwned.push_back(dSGrid);
+    be->upload(dSGrid, grids.data(), sizeof(ShadowGridF) * grids.size());
+    be->sync();   // (the staging vectors above die with this scope)
+    h.sgrid = dSGrid;
+  }
+
   // Validates and flattens `desc`; with `reuse` the existing device buffers are refilled.
   int build(BE* backend, const nrt_scene_desc* desc, bool reuse, std::string& err) {
     be = backend;
@@ -447,6 +549,7 @@ struct SceneData {
       dRecSets = up<RecSet>(nullptr, int64_t(frames.size()), reuse ? dRecSets : nullptr);   // filled once the records exist
     }
     h.cl1 = dCl1; h.cl2 = dCl2; h.clm = dClm; h.clmIdx = dClmIdx; h.slowIdx = dSlowIdx;
+    buildShadowGrids();   // (sets h.sgrid)
     h.objects = dObjs; h.cobjs = dCObjs; h.cobjf = dCObjF; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames; h.recsets = dRecSets; h.mgate = dMGate;
     std::memcpy(h.c2w, desc->camera_to_world, sizeof(h.c2w));
     { const V4 co = mulm(h.c2w, v4(0.0, 0.0, 0.0, 1.0)); h.cam_orig[0] = co.x; h.cam_orig[1] = co.y; h.cam_orig[2] = co.z; h.cam_orig[3] = co.w; }
@@ -519,6 +622,8 @@ struct SceneData {
   void destroy() {
     for (void* p : owned) be->dfree(p);
     owned.clear();
+    for (void* p : gridOwned) be->dfree(p);
+    gridOwned.clear();
   }
 };
 
@@ -533,6 +638,19 @@ struct Renderer {
   std::vector<void*> owned;
   int32_t* dRows = nullptr;
   int64_t tailBelow = 32768;   // NRT_TAIL_BELOW: active lists shorter than this are finished by one PathTail launch
+  // NRT_HARD_TAIL_BELOW: a bounce's wavefront list shorter than this is finished by one PathTail launch as well (the
+  // ~22 dependent launches of a wavefront bounce cost ~0.35 ms however few samples they carry: measured on a 1/8 frame)
+  int64_t hardTailBelow = 16384;
+  // ---- the fork.  After bounce 0 a frame's samples are two disjoint pools: H0, the samples with a mesh ray (one
+  // long chain of wavefront kernels), and C0, the samples FusedBounce finished with a reflection ray stored (bounce 1:
+  // FusedBounce, a short wavefront chain, ... PathTail).  The two do not depend on each other, and the later bounces'
+  // chains are latency-bound (a 1/8 frame: ~1.1 ms for 13 % of the samples), so C0 is moved (GatherPool) into the sample
+  // space of a HELPER pipeline — its own buffers, stream and host thread — which takes it to the end of its paths
+  // while this pipeline runs H0's chain; the accumulators come back (ScatterAccum) before Finalize.
+  Renderer* sub = nullptr;          // the helper (set by the owner; null: no fork)
+  int64_t forkMin = 4096;           // NRT_FORK_MIN: pools smaller than this stay here (0 = never fork)
+  struct SubResult { int rc = 0; bool overflow = false; std::string err; unsigned long long stats[ST_COUNT] = {0}; ProfileAcc pacc; int64_t n = 0; };
+  std::vector<uint32_t> bandHard;   // per row unit of the last frame: samples on the bounce-0 wavefront list (fused path; else empty)
   // NRT_PATH: 0 = the wavefront for every bounce (round-1 pipeline), 1 = FusedBounce + wavefront for the samples
   // with mesh rays at bounce 0 + PathTail (default), 2 = PathMega (one thread per sample start to end)
   int pathMode = 1;
@@ -579,8 +697,8 @@ struct Renderer {
       capPairs = pairsWant;
       cs.pairs = al<uint32_t>(2 * capPairs);
       cs.candRef = al<uint32_t>(cand); cs.candTri = al<uint32_t>(cand); cs.candT = al<double>(cand);
-      cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * cntStride(nL));
-      cs.alist = al<uint32_t>(2 * S); cs.hlist = al<uint32_t>(S); cs.acount = al<uint32_t>(waves + 4);
+      cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * cntStride(nL) + nrows);   // + the per-band counts (BandCount) behind the wave counters
+      cs.alist = al<uint32_t>(2 * S); cs.hlist = al<uint32_t>(S); cs.flist = al<uint32_t>(S); cs.acount = al<uint32_t>(waves + 4);
       cs.stats = al<unsigned long long>(ST_COUNT);
       cs.gvb = (NR + 255) / 256 + 1;
       cs.gsn = (cs.gvb + 255) / 256;
@@ -663,6 +781,177 @@ struct Renderer {
     }
   }
 
+  // ---- the frame being rendered, for the member functions below
+  struct FrameCtx { const SceneData<BE>* sd; FrameParams fp; int maxBounces; int force_exact; bool jitter; int waves; };
+  struct ForkState { bool forked = false; int attempt = 0; SubResult res; };
+
+  static void addProfile(ProfileAcc& a, const ProfileAcc& b) {
+    a.mesh_tests += b.mesh_tests; a.mesh_tests_ref += b.mesh_tests_ref; a.mesh_rays += b.mesh_rays; a.candidates += b.candidates;
+    a.exact_rays += b.exact_rays; a.pre_candidates += b.pre_candidates; a.tail += b.tail;
+    for (int k = 0; k < 3; ++k) a.tests_by_mode[k] += b.tests_by_mode[k];
+    for (int k = 0; k < 8; ++k) { a.active[k] += b.active[k]; a.wavefront[k] += b.wavefront[k]; }
+  }
+
+  // one bounce of the samples `set` through the wavefront: mesh wave of the path rays, Shade, mesh wave of the shadow
+  // rays, ShadowResolve
+  void wavefrontBounce(const FrameCtx& fc, const ActiveSet& set, int bounce, bool gated, int& wave) {
+    const SceneData<BE>& sd = *fc.sd;
+    meshWave(sd, fc.fp, WAVE_PATH, set, 2 * bounce, bounce, fc.force_exact, gated);
+    if (sd.h.ncl1 > 0) be->forEachStats(nullptr, set.n, ShadeClustered{sd.d, fc.fp, cs, set, bounce}, cs.stats);
+    else be->forEachStats(nullptr, set.n, Shade{sd.d, fc.fp, cs, set, bounce}, cs.stats);
+    if (cs.nL > 0) meshWave(sd, fc.fp, WAVE_SHADOW, set, 2 * bounce + 1, bounce, fc.force_exact, false);
+    shadowAndResolve(sd, fc.fp, set, bounce);
+    wave = std::max(wave, 2 * bounce + 2);
+  }
+  void pathTail(const FrameCtx& fc, const ActiveSet& set, int bounce) {
+    const SceneData<BE>& sd = *fc.sd;
+    if (sd.h.ncl1 > 0) be->pathWarp(set.count, set.n, PathTailClustered{sd.d, fc.fp, cs, fc.force_exact, 0, set, bounce}, cs.stats);
+    else be->pathWarp(set.count, set.n, PathTail{sd.d, fc.fp, cs, fc.force_exact, 0, set, bounce}, cs.stats);
+  }
+
+  // The fused path from bounce `bounce0` to the end of every path of the pool `act`.  `fk` != null (the main
+  // pipeline at bounce 0): the fork — see `sub`.
+  void fusedLoop(const FrameCtx& fc, ActiveSet act, int bounce0, ProfileAcc& pacc, int& wave, ForkState* fk,
+                 int64_t nband, uint32_t* dBand, int64_t p0, int64_t nS) {
+    const SceneData<BE>& sd = *fc.sd;
+    const FrameParams& fp = fc.fp;
+    const int nMO = cs.nMO;
+    int par = (bounce0 + 1) & 1;   // half of cs.alist the next list goes to
+    for (int bounce = bounce0;; ++bounce) {
+      if (bounce > bounce0 && act.n < tailBelow) { pathTail(fc, act, bounce); pacc.tail += act.n; break; }   // a small wave: one launch to the end of its paths
+      if (bounce < 8) pacc.active[bounce] += act.n;
+      const int gfs = (bounce == 0 && fc.jitter) ? 1 : 0;
+      if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, FusedBounceClustered{sd.d, fp, cs, fc.force_exact, gfs, act, bounce}, cs.stats);
+      else be->forEachStats(nullptr, act.n, FusedBounce{sd.d, fp, cs, fc.force_exact, gfs, act, bounce}, cs.stats);
+      bool forkedHere = false;
+      uint32_t nh = 0;
+      uint32_t* hardCount = cs.acount + 2 * bounce;
+      if (nMO > 0) {
+        be->compactActive(cs, act, cs.hlist, hardCount, kFlagWavefront);
+        if (bounce == 0 && nband > 0) be->forEach(nband, BandCount{cs.hlist, hardCount, p0, fp.band_pix, nS, fp.spp, dBand});
+        be->download(&nh, hardCount, sizeof(nh));
+        if (fk && bounce == 0 && sub && forkMin > 0 && bounce < fc.maxBounces && int64_t(nh) >= std::max(hardTailBelow, forkMin)) {
+          // the samples that continue WITHOUT the wavefront (flag kFlagContinues) leave for the helper pipeline
+          uint32_t* fcount = cs.acount + fc.waves;   // (slots behind the per-bounce counts)
+          be->compactActive(cs, act, cs.flist, fcount, kFlagContinues);
+          uint32_t nf = 0;
+          be->download(&nf, fcount, sizeof(nf));
+          if (int64_t(nf) >= forkMin && sub->poolFits(int64_t(nf), cs.nL, nMO)) {
+            forkedHere = fk->forked = true;
+            sub->tailBelow = tailBelow; sub->hardTailBelow = hardTailBelow; sub->pathMode = 1;
+            sub->shadowGatePerSample = shadowGatePerSample; sub->shadowTracePerSample = shadowTracePerSample; sub->fuseResolve = fuseResolve;
+            Renderer* const helper = sub;
+            const ChunkState parent = cs;
+            const FrameCtx fcc = fc;
+            SubResult* const out = &fk->res;
+            const int attempt = fk->attempt;
+            const int64_t n = int64_t(nf);
+            be->fork([helper, parent, fcc, out, attempt, n] { helper->renderPool(fcc, parent, parent.flist, n, 1, attempt, *out); });
+          }
+        }
+        if (nh > 0 && int64_t(nh) < hardTailBelow) {
+          // a short wavefront list: its samples leave the pool here (one launch to the end of their paths)
+          pathTail(fc, ActiveSet{cs.hlist, hardCount, int64_t(nh)}, bounce); pacc.tail += nh;
+        } else if (nh > 0) {
+          wavefrontBounce(fc, ActiveSet{cs.hlist, hardCount, int64_t(nh)}, bounce, false, wave);
+          if (bounce < 8) pacc.wavefront[bounce] += nh;
+        }
+      }
+      if (bounce >= fc.maxBounces) break;
+      // the next bounce's active set: every sample of this one whose flag is nonzero (FusedBounce: continues;
+      // Resolve: continues), in sample order — after a fork only the wavefront's samples are still this pipeline's
+      uint32_t* nextList = cs.alist + int64_t(par) * cs.S;
+      uint32_t* nextCount = cs.acount + 2 * bounce + 1;
+      par ^= 1;
+      if (forkedHere) be->compactActive(cs, ActiveSet{cs.hlist, hardCount, int64_t(nh)}, nextList, nextCount, 0);
+      else be->compactActive(cs, act, nextList, nextCount, 0);
+      uint32_t cont = 0;
+      be->download(&cont, nextCount, sizeof(cont));
+      if (cont == 0) break;
+      act = ActiveSet{nextList, nextCount, int64_t(cont)};
+    }
+  }
+
+  // counters of the waves [0, wave) -> profile; true: a list overflowed (the frame is rendered again with larger lists)
+  bool countersToProfile(const SceneData<BE>& sd, const uint32_t* hc, int wave, ProfileAcc& pacc) const {
+    const int nMO = cs.nMO, nL = cs.nL, cst = cntStride(nL);
+    bool overflow = false;
+    for (int w = 0; w < wave && nMO > 0; ++w)
+      for (int mo = 0; mo < nMO; ++mo) {
+        const uint32_t* c = hc + (int64_t(w) * nMO + mo) * cst;
+        const int64_t nf = sd.meshes[sd.objs[sd.moIndex[mo]].mesh].nfaces;
+        if (c[CNT_CAND] > uint64_t(cs.candCap)) overflow = true;
+        int64_t queued = 0;
+        for (int b = 0; b <= nL; ++b) {
+          const int64_t q = c[cntQueue(b)];
+          if (c[cntPre(b)] > uint64_t(cs.preCap) || c[cntWork(b)] > uint64_t(cs.pairCap)) overflow = true;
+          pacc.pre_candidates += c[cntPre(b)];
+          if (!q) continue;
+          // wave parity: even = path wave (primary for w == 0), odd = shadow wave
+          const int mode = b > 0 ? FM_DIR : ((w & 1) ? FM_GENERAL : ((w == 0 && sd.frameValid(mo, FM_ORIGIN, 0)) ? FM_ORIGIN : FM_GENERAL));
+          // executed prefilter tests: chunk bounds tested ray by ray (2-D bundles: only the chunks whose circle overlaps
+          // the run's circle), sub-chunk bounds of the admitted pairs, and the records of the admitted sub-chunks; a
+          // run is the prefilterRunRays(mode) consecutive queue entries of one warp
+          const int64_t run = prefilterRunRays(mode);
+          const int64_t t = int64_t(c[cntBnd(b)]) * run + int64_t(c[cntWork(b)]) * run * kSubPerChunk + int64_t(c[cntSub(b)]) * run * kSubRecs;
+          pacc.mesh_tests += t; pacc.tests_by_mode[mode] += t;
+          queued += q;
+        }
+        pacc.mesh_rays += queued + c[CNT_EXACT];
+        pacc.exact_rays += c[CNT_EXACT];
+        pacc.mesh_tests_ref += (queued + int64_t(c[CNT_EXACT])) * nf;
+        pacc.candidates += c[CNT_CAND];
+      }
+    return overflow;
+  }
+
+  // ---- helper side of the fork
+  // room for a pool of n samples without asking the device for more than it has?
+  bool poolFits(int64_t n, int nL, int nMO) {
+    if (n <= capS) return true;
+    const int64_t perSample = 260 + int64_t(110) * std::max(1, nL) * std::max(1, nMO);
+    return n * perSample < int64_t(0.5 * double(be->memAvailable(capS * perSample)));
+  }
+  // The pool `list[0..n)` of the pipeline `parent` (samples with rays stored for bounce `bounce0`), to the end of its
+  // paths; its accumulators are written back into parent.accum.
+  void renderPool(const FrameCtx& fc, const ChunkState& parent, const uint32_t* list, int64_t n, int bounce0, int attempt, SubResult& out) {
+    out = SubResult{};
+    out.n = n;
+    try {
+      const SceneData<BE>& sd = *fc.sd;
+      const int nL = sd.h.nlights, nMO = sd.h.nmesh_objs;
+      int64_t cand = std::max<int64_t>(int64_t(1) << 20, n * std::max(1, nL) / 2);
+      for (int k = 0; k < attempt; ++k) cand *= 4;
+      // (a pool a little larger than the last one does not reallocate: 1/8 of headroom)
+      const int64_t S = (n <= capS) ? capS : n + n / 8;
+      ensure(S, nL, nMO, fc.waves, std::max(cand, capCand), 1, 0);
+      cs.fb = nullptr; cs.aovObj = nullptr; cs.aovTri = nullptr; cs.aovT = nullptr; cs.q = OutStage{};
+      cs.p0 = 0; cs.npix = 0;
+      preLog.clear();
+      const int64_t ncnt = int64_t(fc.waves) * std::max(nMO, 1) * cntStride(nL);
+      be->zero(cs.counters, sizeof(uint32_t) * ncnt);
+      be->zero(cs.stats, sizeof(unsigned long long) * ST_COUNT);
+      be->zero(cs.acount, sizeof(uint32_t) * (fc.waves + 4));
+      be->forEach(n, GatherPool{parent, cs, list});
+      int wave = 0;
+      fusedLoop(fc, ActiveSet{nullptr, nullptr, n}, bounce0, out.pacc, wave, nullptr, 0, nullptr, 0, n);
+      be->forEach(n, ScatterAccum{parent, cs, list});
+      std::vector<uint32_t> hc(ncnt);
+      be->download(hc.data(), cs.counters, sizeof(uint32_t) * ncnt);
+      be->download(out.stats, cs.stats, sizeof(out.stats));   // (a stream sync: the accumulators are back)
+      out.overflow = countersToProfile(sd, hc.data(), wave, out.pacc);
+      const int cst = cntStride(nL);
+      for (auto& e : preLog)
+        if (e.nch == 0 && e.wave < wave) {
+          const uint32_t* c = hc.data() + (int64_t(e.wave) * nMO + e.mo) * cst;
+          e.rays = c[cntQueue(e.b)]; e.work = c[cntWork(e.b)]; e.pre = c[cntPre(e.b)];
+          e.nch = std::max<int64_t>(1, SceneData<BE>::numChunks(int64_t(sd.hostRecCount(e.mo, e.mode, e.b > 0 ? e.b - 1 : 0))));
+        }
+    } catch (const std::exception& ex) {
+      out.rc = NRT_ERR_CUDA; out.err = ex.what();
+    }
+  }
+
   // Renders the rows `rows` (already filtered by step) of one worker.
   int render(const SceneData<BE>& sd, const nrt_options& o, const std::vector<int32_t>& rows, int step, int max_step,
              float* fb, int32_t* aovObj, int32_t* aovTri, double* aovT, unsigned long long* statsOut, std::string& err,
@@ -688,6 +977,9 @@ struct Renderer {
     const bool jitter = o.aa_kind >= NRT_AA_JITTERED;
     pathMode = int(envInt("NRT_PATH", -1));
     tailBelow = envInt("NRT_TAIL_BELOW", 32768);
+    hardTailBelow = envInt("NRT_HARD_TAIL_BELOW", 16384);
+    forkMin = envInt("NRT_FORK_MIN", 4096);
+    bandHard.clear();
     if (pathMode < 0 || pathMode > 2) {
       // automatic: the fused path, unless the last frame of this pipeline showed that most samples have a ray entering
       // a mesh box (a scene that is mostly mesh: FusedBounce would do a sample's bounce only to hand it over) — then the
@@ -741,23 +1033,17 @@ struct Renderer {
         const int64_t nS = npix * fp.spp;
         cs.p0 = p0; cs.npix = npix;
         const int64_t ncnt = int64_t(waves) * std::max(nMO, 1) * cntStride(nL);
-        be->zero(cs.counters, sizeof(uint32_t) * ncnt);
+        const int64_t nband = (pathMode == 1 && nMO > 0) ? int64_t(rows.size()) : 0;
+        uint32_t* const dBand = cs.counters + ncnt;
+        be->zero(cs.counters, sizeof(uint32_t) * (ncnt + (p0 == 0 ? nband : 0)));
         be->zero(cs.stats, sizeof(unsigned long long) * ST_COUNT);
         be->zero(cs.acount, sizeof(uint32_t) * (waves + 4));
         int wave = 0;
         ActiveSet act{nullptr, nullptr, nS};   // bounce 0: every sample of the chunk
-        auto wavefrontBounce = [&](const ActiveSet& set, int bounce, bool gated) {
-          meshWave(sd, fp, WAVE_PATH, set, 2 * bounce, bounce, force_exact, gated);
-          if (sd.h.ncl1 > 0) be->forEachStats(nullptr, set.n, ShadeClustered{sd.d, fp, cs, set, bounce}, cs.stats);
-          else be->forEachStats(nullptr, set.n, Shade{sd.d, fp, cs, set, bounce}, cs.stats);
-          if (nL > 0) meshWave(sd, fp, WAVE_SHADOW, set, 2 * bounce + 1, bounce, force_exact, false);
-          shadowAndResolve(sd, fp, set, bounce);
-          wave = std::max(wave, 2 * bounce + 2);
-        };
-        auto pathTail = [&](const ActiveSet& set, int bounce) {
-          if (sd.h.ncl1 > 0) be->pathWarp(set.count, set.n, PathTailClustered{sd.d, fp, cs, force_exact, 0, set, bounce}, cs.stats);
-          else be->pathWarp(set.count, set.n, PathTail{sd.d, fp, cs, force_exact, 0, set, bounce}, cs.stats);
-        };
+        const FrameCtx fc{&sd, fp, maxBounces, force_exact, jitter, waves};
+        ForkState fk;
+        fk.attempt = attempt;
+        struct Joiner { BE* be; ForkState* fk; ~Joiner() { if (fk->forked) be->join(); } } joiner{be, &fk};   // (an exception between fork and join must not leave the helper running on this frame's state)
         if (pathMode == 2) {
           // ---- PathMega: every sample start to end in one launch ----
           if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
@@ -768,31 +1054,7 @@ struct Renderer {
           // through the whole bounce in registers unless one of its rays enters a mesh box; those samples (flag
           // kFlagWavefront, listed in sample order) go through the wavefront for that bounce.
           if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
-          for (int bounce = 0;; ++bounce) {
-            if (bounce > 0 && act.n < tailBelow) { pathTail(act, bounce); pacc.tail += act.n; break; }   // a small wave: one launch to the end of its paths
-            if (bounce < 8) pacc.active[bounce] += act.n;
-            const int gfs = (bounce == 0 && jitter) ? 1 : 0;
-            if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, FusedBounceClustered{sd.d, fp, cs, force_exact, gfs, act, bounce}, cs.stats);
-            else be->forEachStats(nullptr, act.n, FusedBounce{sd.d, fp, cs, force_exact, gfs, act, bounce}, cs.stats);
-            if (nMO > 0) {
-              uint32_t* hardCount = cs.acount + 2 * bounce;
-              be->compactActive(cs, act, cs.hlist, hardCount, kFlagWavefront);
-              uint32_t nh = 0;
-              be->download(&nh, hardCount, sizeof(nh));
-              if (nh > 0) wavefrontBounce(ActiveSet{cs.hlist, hardCount, int64_t(nh)}, bounce, false);
-              if (bounce < 8) pacc.wavefront[bounce] += nh;
-            }
-            if (bounce >= maxBounces) break;
-            // the next bounce's active set: every sample of this one whose flag is nonzero (FusedBounce: continues;
-            // Resolve: continues), in sample order
-            uint32_t* nextList = cs.alist + int64_t((bounce + 1) & 1) * cs.S;
-            uint32_t* nextCount = cs.acount + 2 * bounce + 1;
-            be->compactActive(cs, act, nextList, nextCount, 0);
-            uint32_t cont = 0;
-            be->download(&cont, nextCount, sizeof(cont));
-            if (cont == 0) break;
-            act = ActiveSet{nextList, nextCount, int64_t(cont)};
-          }
+          fusedLoop(fc, act, 0, pacc, wave, &fk, nband, dBand, p0, nS);
         } else {
           // ---- the wavefront for every bounce (round-1 pipeline; NRT_PATH=0) ----
           // primary rays: generated and gated in one kernel (the jittered kinds generate per pixel: separate gate)
@@ -804,7 +1066,7 @@ struct Renderer {
             uint32_t* nextList = cs.alist + int64_t((bounce + 1) & 1) * cs.S;
             uint32_t* nextCount = cs.acount + 2 * bounce + 1;
             // (act.n is exact on the host for every bounce: launches are sized to it)
-            wavefrontBounce(act, bounce, bounce == 0 && fuseGen);
+            wavefrontBounce(fc, act, bounce, bounce == 0 && fuseGen, wave);
             if (bounce >= maxBounces) break;
             be->compactActive(cs, act, nextList, nextCount, 0);
             uint32_t cont = 0;
@@ -813,43 +1075,24 @@ struct Renderer {
             act = ActiveSet{nextList, nextCount, int64_t(cont)};
           }
         }
+        if (fk.forked) {   // the helper's pool is back in this pipeline's accumulators before Finalize reads them
+          be->join();
+          if (fk.res.rc != NRT_OK) { err = fk.res.err; return fk.res.rc; }
+          if (fk.res.overflow) overflow = true;
+          for (int k = 0; k < ST_COUNT; ++k) total[k] += fk.res.stats[k];
+          addProfile(pacc, fk.res.pacc);
+        }
         be->finalize(npix, Finalize{fp, cs});
         // chunk epilogue: counters (profile + overflow check) and stats
-        std::vector<uint32_t> hc(ncnt);
+        const bool lastChunk = p0 + chunkPix >= npixTotal;
+        std::vector<uint32_t> hc(ncnt + (lastChunk ? nband : 0));
         unsigned long long hs[ST_COUNT];
-        be->download(hc.data(), cs.counters, sizeof(uint32_t) * ncnt);
+        be->download(hc.data(), cs.counters, sizeof(uint32_t) * hc.size());
+        if (lastChunk && nband > 0) bandHard.assign(hc.begin() + ncnt, hc.end());
         be->download(hs, cs.stats, sizeof(hs));
-        const int cst = cntStride(nL);
-        for (int w = 0; w < wave && nMO > 0; ++w)
-          for (int mo = 0; mo < nMO; ++mo) {
-            const uint32_t* c = hc.data() + (int64_t(w) * nMO + mo) * cst;
-            const int64_t nf = sd.meshes[sd.objs[sd.moIndex[mo]].mesh].nfaces;
-            if (c[CNT_CAND] > uint64_t(cs.candCap)) overflow = true;
-            int64_t queued = 0;
-            for (int b = 0; b <= nL; ++b) {
-              const int64_t q = c[cntQueue(b)];
-              if (c[cntPre(b)] > uint64_t(cs.preCap) || c[cntWork(b)] > uint64_t(cs.pairCap)) overflow = true;
-              pacc.pre_candidates += c[cntPre(b)];
-              if (!q) continue;
-              // wave parity: even = path wave (primary for w == 0), odd = shadow wave
-              const int mode = b > 0 ? FM_DIR : ((w & 1) ? FM_GENERAL : ((w == 0 && sd.frameValid(mo, FM_ORIGIN, 0)) ? FM_ORIGIN : FM_GENERAL));
-              // executed prefilter tests: fully evaluated (ray run x 256-record chunk) pairs + one bound test
-              // per (ray, chunk); a run is the prefilterRunRays(mode) consecutive queue entries of one warp
-              const int64_t nch = SceneData<BE>::numChunks(int64_t(sd.hostRecCount(mo, mode, b > 0 ? b - 1 : 0)));
-              const int64_t run = prefilterRunRays(mode), nruns = (q + run - 1) / run;
-              // executed tests: chunk bounds tested ray by ray (2-D bundles: only the chunks whose circle overlaps the
-              // run's circle), sub-chunk bounds of the admitted pairs, and the records of the admitted sub-chunks
-              (void)nruns; (void)nch;
-              const int64_t t = int64_t(c[cntBnd(b)]) * run + int64_t(c[cntWork(b)]) * run * kSubPerChunk + int64_t(c[cntSub(b)]) * run * kSubRecs;
-              pacc.mesh_tests += t; pacc.tests_by_mode[mode] += t;
-              queued += q;
-            }
-            pacc.mesh_rays += queued + c[CNT_EXACT];
-            pacc.exact_rays += c[CNT_EXACT];
-            pacc.mesh_tests_ref += (queued + int64_t(c[CNT_EXACT])) * nf;
-            pacc.candidates += c[CNT_CAND];
-          }
+        if (countersToProfile(sd, hc.data(), wave, pacc)) overflow = true;
         for (int k = 0; k < ST_COUNT; ++k) total[k] += hs[k];
+        const int cst = cntStride(nL);
         for (auto& e : preLog)
           if (e.nch == 0 && e.wave < wave) {   // entries of this chunk (filled once)
             const uint32_t* c = hc.data() + (int64_t(e.wave) * nMO + e.mo) * cst;

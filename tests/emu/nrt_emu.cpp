@@ -32,6 +32,8 @@ struct LoopBackend {
   void upload(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
   void download(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
   void sync() {}
+  template <class F> void fork(F f) { f(); }   // the helper pipeline of a fork runs inline
+  void join() {}
   bool produceGateFits(int, int, int) const { return true; }
   bool diff_ = false;
   void diffBegin() { diff_ = false; }
@@ -204,8 +206,10 @@ int emu_render(const nrt_scene_desc* desc, const nrt_options* o, int y0, int y1,
   std::string err;
   int rc = sd.build(&be, desc, false, err);
   if (rc != NRT_OK) { std::fprintf(stderr, "emu: %s\n", err.c_str()); return rc; }
-  Renderer<LoopBackend> rn;
+  Renderer<LoopBackend> rn, helper;
   rn.be = &be;
+  helper.be = &be;
+  rn.sub = &helper;
   std::vector<int32_t> rows;
   const int tshift = tileShiftFor(*o, step, max_step), T = 1 << tshift;   // T > 1: bands of T rows, tile order inside
   for (int y = std::max(0, y0); y < std::min(y1, o->height); ++y)
@@ -226,6 +230,7 @@ int emu_render(const nrt_scene_desc* desc, const nrt_options* o, int y0, int y1,
     prof[3] = rn.prof.exact_rays; prof[4] = be.launches; prof[5] = be.filter_tests; prof[6] = rn.prof.pre_candidates;
   }
   rn.freeAll();
+  helper.freeAll();
   sd.destroy();
   return rc;
 }

@@ -175,3 +175,54 @@ def test_many_mesh_objects_and_lights(oracle_mod):
     # several mesh objects (kMaxWalkMO = 2 result slots of the path kernels: the third is walked by the thread) x many lights
     check(scenes.many_meshes_many_lights(3, 5), api.Options(64, 36, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
     check(scenes.many_meshes_many_lights(12, 33), api.Options(32, 18), oracle_mod)
+
+
+def test_short_wavefront_list_goes_to_path_tail(oracle_mod, monkeypatch):
+    # the library's default: a bounce's wavefront list below NRT_HARD_TAIL_BELOW (16384) samples is finished by ONE
+    # PathTail launch — from bounce 0 too, where only the primary direction is stored (PathWarpT, bounce0 == 0)
+    monkeypatch.delenv("NRT_HARD_TAIL_BELOW")
+    prof = check(scenes.mesh_cube(), api.Options(64, 64), oracle_mod)
+    assert prof["mesh_rays"] == 0            # no wavefront queue saw a ray
+    sc = scenes.bunny_spheres(stride=16)
+    check(sc, api.Options(96, 54, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=6), oracle_mod)
+    check(sc, api.Options(80, 45, antialias=api.Antialias(api.akJittered, 2), seed=5), oracle_mod)
+    monkeypatch.setenv("NRT_HARD_TAIL_BELOW", "300")   # bounce 0 through the wavefront, later (shorter) lists through PathTail
+    check(sc, api.Options(96, 54, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=6), oracle_mod)
+
+
+def test_fork_moves_the_continuing_pool_to_a_helper_pipeline(oracle_mod, monkeypatch):
+    # After bounce 0 the samples FusedBounce finished with a reflection ray stored are moved into a helper pipeline's
+    # sample space (GatherPool), taken to the end of their paths there and scattered back (nrt_renderer.h: the fork).
+    sc = scenes.bunny_spheres(stride=16)
+    o = api.Options(96, 54, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=6)
+    monkeypatch.setenv("NRT_FORK_MIN", "0")
+    off = check(sc, o, oracle_mod)
+    monkeypatch.setenv("NRT_FORK_MIN", "16")
+    on = check(sc, o, oracle_mod)
+    assert on["launches"] != off["launches"]          # the helper's gather / scatter and its own chain of launches
+    check(sc, api.Options(80, 45), oracle_mod)        # reference depth bug: paths up to the bounce cap
+    check(scenes.transformed_objects(), api.Options(120, 68, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
+    monkeypatch.delenv("NRT_HARD_TAIL_BELOW")          # with the short-list shortcut on both sides of the fork
+    monkeypatch.setenv("NRT_HARD_TAIL_BELOW", "64")
+    check(sc, o, oracle_mod)
+
+
+def _grid_scene(big=False, far=False):
+    """>= 64 spheres (clusters + the light-space shadow grids), a distant and a point light; optionally a few huge
+    spheres (cells with long lists: the grid declines them) or everything moved far from the origin (the grid's
+    float32 margin rejects the rays and the cluster traversal takes them)."""
+    from nim_raytracer_b200.api import DistantLight, PointLight, point, vec, vec3
+    from nim_raytracer_b200 import linalg as L
+    sc = scenes.stress(ntri=200, nspheres=300, seed=3)
+    sc.lights = [DistantLight(color=vec3(1.0), intensity=3.0, dir=L.normalize(vec(-1.0, -1.5, -0.4))),
+                 PointLight(color=vec3(1.0, 0.8, 0.5), intensity=3000.0, pos=point(2.0, 9.0, -25.0)),
+                 DistantLight(color=vec3(0.2, 0.3, 0.8), intensity=1.0, dir=L.normalize(vec(0.0, -1.0, 0.0)))]
+    return sc
+
+
+def test_light_space_shadow_grid(oracle_mod):
+    # shadow rays of the DistantLights read one cell of the light-space grid of the clustered spheres (ShadowGridF);
+    # the PointLight's rays and the path rays traverse the clusters
+    o = api.Options(96, 54, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=3)
+    check(_grid_scene(), o, oracle_mod)
+    check(scenes.stress(ntri=100, nspheres=2000, seed=11), api.Options(120, 68), oracle_mod)   # dense: long cell lists

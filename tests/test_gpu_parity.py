@@ -479,3 +479,63 @@ def test_two_gpus_in_process_match_one(oracle_mod):
     finally:
         api.shutdown()
         api.initRenderer(1)
+
+
+@pytest.mark.gpu
+def test_short_wavefront_list_goes_to_path_tail(oracle_mod, monkeypatch):
+    # library default (conftest pins it off for the other tests): wavefront lists below 16384 samples are finished by
+    # one PathTail launch, from bounce 0 as well
+    monkeypatch.delenv("NRT_HARD_TAIL_BELOW")
+    sc = scenes.bunny_spheres(stride=4)
+    o = api.Options(320, 180, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+    assert_parity(sc, o, oracle_mod)
+    assert_parity(sc, api.Options(200, 112), oracle_mod)
+    assert_parity(scenes.bunny(flip_winding=False, stride=2), api.Options(240, 135), oracle_mod)
+    monkeypatch.setenv("NRT_HARD_TAIL_BELOW", "2000")   # bounce 0 through the wavefront, the later lists through PathTail
+    assert_parity(sc, o, oracle_mod)
+
+
+@pytest.mark.gpu
+def test_lane_plan_from_band_feedback_keeps_the_frame(oracle_mod, monkeypatch):
+    # The second frame of a scene deals its bands out by the first frame's per-band wavefront counts (heavy bands to
+    # the high-priority lanes, mesh-free bands to the low-priority ones, nrt.cu: BandFeedback): scheduling only — the
+    # frame, the ids and the Stats stay the oracle's, frame after frame, whatever the number of lanes.
+    monkeypatch.delenv("NRT_HARD_TAIL_BELOW")
+    sc = scenes.bunny_spheres(stride=4)
+    o = api.Options(640, 512, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+    rfb, rst, raov = oracle_mod.render(sc, o, aov=api.Aov(o.width, o.height))
+    for lanes, heavy in (("2", "1"), ("4", "2"), ("4", "1"), ("3", "2")):
+        monkeypatch.setenv("NRT_LANES", lanes)
+        monkeypatch.setenv("NRT_HEAVY_LANES", heavy)
+        ds = api.DeviceScene(sc)
+        for frame in range(3):
+            fb, aov = api.newFramebuf(o.width, o.height), api.Aov(o.width, o.height)
+            st = api.renderFrame(ds, o, fb, aov=aov)
+            assert st == rst, (lanes, heavy, frame)
+            assert (aov.obj_id == raov.obj_id).all() and (aov.tri_id == raov.tri_id).all()
+            assert (fb.data == rfb.data).all(), (lanes, heavy, frame)
+        ds.close()
+
+
+@pytest.mark.gpu
+def test_fork_helper_pipeline_keeps_the_frame(oracle_mod, monkeypatch):
+    # the fork (nrt_renderer.h): the continuing pool of bounce 0 runs in a helper pipeline (own buffers, stream and
+    # host thread) next to the wavefront chain of the samples with mesh rays; off (NRT_FORK_MIN=0) and on, same frame
+    sc = scenes.bunny_spheres(stride=4)
+    o = api.Options(320, 180, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
+    for fork_min in ("0", "64"):
+        monkeypatch.setenv("NRT_FORK_MIN", fork_min)
+        assert_parity(sc, o, oracle_mod)
+        assert_parity(sc, api.Options(200, 112), oracle_mod)
+        assert_parity(scenes.transformed_objects(), api.Options(240, 135, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)
+
+
+@pytest.mark.gpu
+def test_light_space_shadow_grid_and_ray_bundles(oracle_mod):
+    # >= 64 spheres: warp-bundle first look over the sphere clusters (RayBundle) for path rays, light-space grid
+    # (ShadowGridF) for the DistantLights' shadow rays, cluster traversal for the PointLight's
+    from test_emu_parity import _grid_scene
+    o = api.Options(320, 180, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=4)
+    assert_parity(_grid_scene(), o, oracle_mod)
+    assert_parity(scenes.stress(ntri=100, nspheres=2000, seed=11), api.Options(240, 135), oracle_mod)
+    assert_parity(scenes.stress(ntri=500, nspheres=40, seed=5), api.Options(240, 135, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)   # flat scan

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+{
+echo "=== FULL default (4 lanes, no feedback, no fork)"
+NRT_LANE_FEEDBACK=0 NRT_FORK_MIN=0 timeout 300 python tools/frame_breakdown.py config4 config3 config2 2>&1 | grep -v "fb sha"
+echo "=== part 0,8 1 lane"
+NRT_LANE_FEEDBACK=0 NRT_FORK_MIN=0 NRT_LANES=1 NRT_PART=0,8 timeout 300 python tools/frame_breakdown.py config4 2>&1 | grep -v "fb sha"
+echo "=== config5s / config5 part 0,8"
+NRT_LANE_FEEDBACK=0 NRT_FORK_MIN=0 timeout 600 python tools/frame_breakdown.py config5s 2>&1
+NRT_LANE_FEEDBACK=0 NRT_FORK_MIN=0 NRT_PART=0,8 timeout 600 python tools/frame_breakdown.py config5 2>&1
+} > gpurun_out/r02z.log 2>&1
+cut -c1-330 gpurun_out/r02z.log
