@@ -531,6 +531,7 @@ struct PreArgs {
   uint32_t* workctr;        // (run, chunk) pairs admitted by level 1 (may exceed pairCap: the host re-renders)
   uint32_t* subctr;         // (run, sub-chunk) pairs evaluated in full
   uint32_t* bndctr;         // (run, chunk) pairs whose bound was tested ray by ray
+  float4* runc;             // per run: (cx, cy, Rr, margin) of its points' bounding circle, Rr < 0: none (2-D bundles, level 1 -> level 2)
   uint2* pairs;             // the work list
   uint32_t pairCap;
   uint32_t* preRay;
@@ -622,7 +623,10 @@ __global__ void __launch_bounds__(FT_THREADS) k_prefilter_bounds(PreArgs a) {
         for (int off = 16; off > 0; off >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, off));
         const float Rr = sqrtf(r2) * 1.00001f;
         const float p2max = fmaf(fmaxf(fabsf(xlo), fabsf(xhi)), fmaxf(fabsf(xlo), fabsf(xhi)), fmaxf(fabsf(ylo), fabsf(yhi)) * fmaxf(fabsf(ylo), fabsf(yhi)));
-        if (Rr < 1e15f && mr < 1e30f && p2max < 1e30f) {
+        const bool circOk = Rr < 1e15f && mr < 1e30f && p2max < 1e30f;
+        // the run's circle, for level 2's look at the sub-chunk bounds (k_mesh_prefilter)
+        if (gr == 0 && lane == 0) a.runc[run] = make_float4(cx, cy, circOk ? Rr : -1.f, mr);
+        if (circOk) {
           bool pass = false;
           if (c0 + lane < c1) {
             const float4 bd = __ldg(a.bounds + c0 + lane);
@@ -667,6 +671,22 @@ __global__ void __launch_bounds__(FT_THREADS) k_prefilter_bounds(PreArgs a) {
   if (lane == 0 && bnd) atomicAdd(a.bndctr, bnd);
 }
 
+// writes a warp's buffered survivors to the global pre-candidate list: one atomic, coalesced stores (every lane calls)
+__device__ __noinline__ void preFlush(const uint2* wbuf, uint32_t wn, uint32_t* prectr, uint32_t* preRay, uint32_t* preRec, uint32_t preCap) {
+  const uint32_t lane = threadIdx.x & 31u;
+  __syncwarp();
+  if (wn) {
+    uint32_t gb = 0;
+    if (lane == 0) gb = atomicAdd(prectr, wn);
+    gb = __shfl_sync(0xffffffffu, gb, 0);
+    for (uint32_t k = lane; k < wn; k += 32) {
+      const uint2 e = wbuf[k];
+      if (gb + k < preCap) { preRay[gb + k] = e.x; preRec[gb + k] = e.y; }
+    }
+  }
+  __syncwarp();
+}
+
 template <int MODE, int R, int U>
 __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? NRT_OCC_PRE_GEN : NRT_OCC_PRE_2D) k_mesh_prefilter(PreArgs a) {
   constexpr int NH = hotFloats(MODE);      // float2 per record pair == float4 per record quad
@@ -683,15 +703,27 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? NRT_OCC_PRE_G
   // per-warp survivor buffer behind the tiles: FT_WB (ray, record) pairs + a counter
   uint2* const wbuf = reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * (CH4 + kSubPerChunk)) + size_t(warp) * FT_WB;
   uint32_t* const wcnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint2*>(smem_tiles + size_t(FT_WARPS) * (CH4 + kSubPerChunk)) + size_t(FT_WARPS) * FT_WB) + warp;
-  if (lane == 0) *wcnt = 0;
-  __syncwarp();
-  auto emit = [&](uint32_t ray, uint32_t rec) {
-    const uint32_t slot = atomicAdd(wcnt, 1u);
-    if (slot < uint32_t(FT_WB)) wbuf[slot] = make_uint2(ray, rec);
-    else {  // buffer full (dense hits, e.g. always-candidate records): straight to the global list
-      const uint32_t gs = atomicAdd(a.prectr, 1u);
-      if (gs < a.preCap) { a.preRay[gs] = ray; a.preRec[gs] = rec; }
-    }
+  (void)wcnt;
+  // Survivors are compacted with warp votes: every lane reaches emit() (p = this lane has a survivor), one ballot
+  // gives the lanes their slots behind the warp's running count `wn` (a register, the same in every lane) — no
+  // shared-memory atomic and no wait for one (r02 ncu: the warp-aggregated ATOMS of the per-lane emit and the SHFLs
+  // that broadcast their results carried ~45 % of the kernel's stall samples).
+  // The buffer is written out when it is full (and once at the end), not per item: one global atomic per FT_WB
+  // survivors (the per-item flush's atomic and, in dense items, one global atomic per emit were ~55 % of the stalls).
+  uint32_t wn = 0;
+  const uint32_t ltmask = (1u << lane) - 1u;
+  auto flush = [&]() {   // every lane (a call, not inline code: emit() is instantiated at 32 sites, and the first
+                         // inlined version ran out of instruction cache — 18 cycles of no_instruction stall per issue)
+    preFlush(wbuf, wn, a.prectr, a.preRay, a.preRec, a.preCap);
+    wn = 0;
+  };
+  auto emit = [&](bool p, uint32_t ray, uint32_t rec) {   // every lane
+    const uint32_t bal = __ballot_sync(0xffffffffu, p);
+    if (!bal) return;
+    const uint32_t n = uint32_t(__popc(bal));
+    if (wn + n > uint32_t(FT_WB)) flush();
+    if (p) wbuf[wn + uint32_t(__popc(bal & ltmask))] = make_uint2(ray, rec);
+    wn += n;
   };
   // short lists: items of half / quarter chunks so that the launch still fills the GPU
   const uint32_t totalWarps = gridDim.x * FT_WARPS;
@@ -699,14 +731,23 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? NRT_OCC_PRE_G
   while (SP < 4 && uint64_t(nPairs) * SP < uint64_t(a.splitBelow) * totalWarps) SP <<= 1;
   const uint32_t SN = kSubPerChunk / SP;               // sub-chunks per item
   const uint64_t nItems = uint64_t(nPairs) * SP;
-  uint32_t subWork = 0;
+  uint32_t subWork = 0, sbTested = 0;   // sub-chunks evaluated in full / sub-chunk bounds tested ray by ray
+  // The item counter and the work list are read TWO / ONE items ahead: the global atomic (~700 cycles) and the
+  // dependent load of the pair are in flight while the current item is evaluated (they were 11 % + 5 % of the stalls).
+  auto pop = [&]() { uint32_t v = 0; if (lane == 0) v = atomicAdd(a.itemctr, 1u); return v; };   // (lane 0's register; broadcast where it is used)
+  uint32_t itemA = __shfl_sync(0xffffffffu, pop(), 0);
+  uint32_t rawB = pop();
+  uint2 pairA = make_uint2(0u, 0u);
+  if (itemA < nItems) pairA = a.pairs[itemA / SP];
   for (;;) {
-    uint32_t item = 0;
-    if (lane == 0) item = atomicAdd(a.itemctr, 1u);
-    item = __shfl_sync(0xffffffffu, item, 0);
+    const uint32_t item = itemA;
     if (item >= nItems) break;
     const uint32_t pi = item / SP, part = item - pi * SP;
-    const uint2 pr = a.pairs[pi];
+    const uint2 pr = pairA;
+    // next item: its index arrived during the previous item; its pair is requested now, the index after it as well
+    itemA = __shfl_sync(0xffffffffu, rawB, 0);
+    if (itemA < nItems) pairA = a.pairs[itemA / SP];
+    rawB = pop();
     // stage this item's part of the chunk and its sub-chunk bounds (16 bytes per lane and step), rays meanwhile
     {
       const float4* src = a.hot + size_t(pr.y) * CH4 + size_t(part) * SN * SQ * NH;
@@ -719,7 +760,29 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? NRT_OCC_PRE_G
     __pipeline_wait_prior(0);
     __syncwarp();                            // the records are in the slice for every lane
     const uint32_t base = pr.y * FT_TC + part * SN * kSubRecs;
-    for (uint32_t sb = 0; sb < SN; ++sb) {
+    // ---- level 2, first look (2-D bundles): the run's circle against the circles of the item's sub-chunks, one
+    // sub-chunk per lane (the test of k_prefilter_bounds' level 1, same margins); the exact ray-by-ray bound test
+    // below then runs for the overlapping sub-chunks only (it was ~30 % of an item's instructions)
+    uint32_t smask = (SN >= 32u) ? 0xffffffffu : ((1u << SN) - 1u);
+    if (MODE != FM_GENERAL && a.cull) {
+      const float4 rc = __ldg(a.runc + pr.x);
+      if (rc.z >= 0.f) {
+        bool pass = false;
+        if (uint32_t(lane) < SN) {
+          const float4 bd = stile[lane];
+          const float Cx = 0.5f * bd.x, Cy = 0.5f * bd.y, C2 = fmaf(Cx, Cx, Cy * Cy);
+          const float px = fabsf(rc.x) + rc.z, py = fabsf(rc.y) + rc.z, p2max = fmaf(px, px, py * py);
+          const float Rc2 = bd.z + C2 + 2e-6f * (fabsf(bd.z) + C2 + p2max) + 1.01f * rc.w;
+          const float Rs = rc.z + sqrtf(fmaxf(Rc2, 0.f)) + 5e-7f * (fabsf(rc.x) + fabsf(rc.y) + fabsf(Cx) + fabsf(Cy));
+          const float dx = rc.x - Cx, dy = rc.y - Cy;
+          pass = (bd.z >= 1e29f) || (bd.z > -1e29f && fmaf(dx, dx, dy * dy) <= Rs * Rs * 1.00001f) || !(p2max < 1e30f);
+        }
+        smask &= __ballot_sync(0xffffffffu, pass);
+      }
+    }
+    sbTested += uint32_t(__popc(smask));
+    for (uint32_t sm = smask; sm; sm &= sm - 1) {
+      const uint32_t sb = uint32_t(__ffs(int(sm)) - 1);
       // ---- level 2: can any ray of the run reach this sub-chunk? ----
       if (a.cull) {
         const float4 bd = stile[sb];
@@ -738,7 +801,14 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? NRT_OCC_PRE_G
       }
       ++subWork;
       // ---- level 3: run x the sub-chunk's records ----
-#pragma unroll U
+      // A ray keeps ONE running maximum of its left-hand sides over the sub-chunk's 16 records (FMNMX3: two new values
+      // per instruction) and is compared with its threshold once per sub-chunk; per (ray, record quad) that is
+      // 4 FFMA2 + 2 FMNMX3 instead of 4 FFMA2 + FMNMX + FMNMX3 + FSETP + SEL + IADD (the ALU pipe, not the FMA pipe,
+      // was the busier one: r01q ncu).  The rare sub-chunk with a passing ray is evaluated again for those rays.
+      float mx[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) mx[r] = -3.0e38f;
+#pragma unroll
       for (uint32_t tq = 0; tq < uint32_t(SQ); ++tq) {
         const uint32_t t = sb * SQ + tq;
         float2 q[2 * NH];   // two record pairs: q[j * NH + k] = coefficient k of pair j
@@ -748,50 +818,51 @@ __global__ void __launch_bounds__(FT_THREADS, MODE == FM_GENERAL ? NRT_OCC_PRE_G
           q[2 * c] = make_float2(v4.x, v4.y);
           q[2 * c + 1] = make_float2(v4.z, v4.w);
         }
-        uint32_t hm = 0;   // bit r: ray r passed one of the four tests
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const float thr = (MODE == FM_GENERAL) ? ry.a3[r] : ry.a2[r];
           const float2 g0 = prefilterPair<MODE>(q, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
           const float2 g1 = prefilterPair<MODE>(q + NH, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
-          // one compare per ray: max of its four left-hand sides against its threshold (FMNMX3 + FSETP)
-          const float m = fmaxf(fmaxf(g0.x, g0.y), fmaxf(g1.x, g1.y));
-          if (m >= thr) hm |= 1u << r;
+          mx[r] = fmaxf(fmaxf(mx[r], g0.x), g0.y);
+          mx[r] = fmaxf(fmaxf(mx[r], g1.x), g1.y);
         }
-        if (hm) {  // re-evaluate the rays that passed and emit their survivors
+      }
+      uint32_t hm = 0;   // bit r: ray r passed one of the sub-chunk's tests
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float thr = (MODE == FM_GENERAL) ? ry.a3[r] : ry.a2[r];
+        if (mx[r] >= thr) hm |= 1u << r;
+      }
+      if (__any_sync(0xffffffffu, hm != 0)) {  // (warp-uniform) re-evaluate the rays that passed and emit their survivors
+#pragma unroll 1
+        for (uint32_t tq = 0; tq < uint32_t(SQ); ++tq) {
+          const uint32_t t = sb * SQ + tq;
+          float2 q[2 * NH];
+#pragma unroll
+          for (int c = 0; c < NH; ++c) {
+            const float4 v4 = tile[t * NH + c];
+            q[2 * c] = make_float2(v4.x, v4.y);
+            q[2 * c + 1] = make_float2(v4.z, v4.w);
+          }
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            if (!(hm & (1u << r)) || ry.idx[r] == kInvalidRef) continue;
+            const bool mine = (hm & (1u << r)) != 0 && ry.idx[r] != kInvalidRef;
+            if (!__any_sync(0xffffffffu, mine)) continue;   // no lane's ray r passed: warp-uniform
             const float thr = (MODE == FM_GENERAL) ? ry.a3[r] : ry.a2[r];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const float2 g = prefilterPair<MODE>(q + j * NH, ry.a0[r], ry.a1[r], ry.a2[r], ry.b0[r], ry.b1[r], ry.b2[r]);
-              if (g.x >= thr) emit(ry.idx[r], base + 4 * t + 2 * j);
-              if (g.y >= thr) emit(ry.idx[r], base + 4 * t + 2 * j + 1);
+              emit(mine && g.x >= thr, ry.idx[r], base + 4 * t + 2 * j);
+              emit(mine && g.y >= thr, ry.idx[r], base + 4 * t + 2 * j + 1);
             }
           }
         }
       }
     }
-    // flush the warp's survivors: one global atomic per item, coalesced stores
-    __syncwarp();
-    {
-      const uint32_t nb = min(*wcnt, uint32_t(FT_WB));
-      if (nb) {
-        uint32_t gb = 0;
-        if (lane == 0) gb = atomicAdd(a.prectr, nb);
-        gb = __shfl_sync(0xffffffffu, gb, 0);
-        for (uint32_t k = lane; k < nb; k += 32) {
-          const uint2 e = wbuf[k];
-          if (gb + k < a.preCap) { a.preRay[gb + k] = e.x; a.preRec[gb + k] = e.y; }
-        }
-        __syncwarp();
-        if (lane == 0) *wcnt = 0;
-      }
-    }
     __syncwarp();                            // every lane left the slice before it is staged again
   }
+  flush();
   if (lane == 0 && subWork) atomicAdd(a.subctr, subWork);
+  if (lane == 0 && sbTested) atomicAdd(a.bndctr, sbTested);
 }
 
 // Finalize with coalesced reads: a pixel's samples are contiguous in the accumulator planes, so one
@@ -1073,7 +1144,8 @@ struct CudaBackend {
     // elements per warp: all 32 lanes when the list fills the GPU's resident warps (8 per SM at this kernel's
     // register count), fewer for short lists
     int lpw = 32;
-    while (lpw > 1 && n * 32 / lpw < int64_t(sms) * 8 * 32 / 2) lpw >>= 1;   // i.e. while warps(n, lpw) < half the resident warps
+    static const int64_t fill = [] { const char* e = std::getenv("NRT_TAIL_FILL"); return e ? std::max<int64_t>(1, std::atoll(e)) : int64_t(1); }();
+    while (lpw > 1 && n * 32 / lpw < int64_t(sms) * 8 * 32 * fill / 2) lpw >>= 1;   // i.e. while warps(n, lpw) < fill/2 x the resident warps
     const int64_t perCta = int64_t(kBlock / 32) * lpw;
     const int64_t blocks = (n + perCta - 1) / perCta;
     k_path_warp<F><<<unsigned(blocks), kBlock, 0, stream>>>(f, count, n, lpw, stats);
@@ -1228,6 +1300,7 @@ struct CudaBackend {
     a.subctr = cnt + cntSub(b);
     a.bndctr = cnt + cntBnd(b);
     a.pairs = reinterpret_cast<uint2*>(cs.pairs);
+    a.runc = reinterpret_cast<float4*>(cs.runc);
     a.pairCap = uint32_t(std::min<int64_t>(cs.pairCap, 0xFFFFFFFFll));
     a.preRay = cs.preRay; a.preRec = cs.preRec;
     a.preCap = uint32_t(std::min<int64_t>(cs.preCap, 0xFFFFFFFFll));
@@ -1521,12 +1594,17 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
   // lanes per device: NRT_LANES, else by the device's share of the frame (a lane should keep >= ~1 M samples;
   // kernel timing wants one chain so that the per-launch events do not overlap)
   int nlanes = 4;
+  bool smallShare = false;
   if (const char* e = std::getenv("NRT_LANES")) nlanes = std::atoi(e);
   {
     const int spp = o->aa_kind == NRT_AA_NONE ? 1 : o->grid_size * o->grid_size;
     const int64_t rowsAll = (std::min(y1, o->height) - std::max(0, y0) + step - 1) / std::max(step, 1);
     const int64_t samples = std::max<int64_t>(0, rowsAll) * ((o->width + step - 1) / step) * spp / std::max(1, nd * g_part_count);
-    if (!std::getenv("NRT_LANES")) nlanes = int(std::min<int64_t>(4, std::max<int64_t>(1, samples / (int64_t(1) << 20))));
+    // (small shares — a 1/8 frame — are latency-bound in the wavefront chains: three lanes, one of them taking the bands
+    // with mesh work at high priority, measured 3.30 ms against 3.55 ms for four equal lanes; a whole frame is
+    // throughput-bound and does best with four equal lanes: 19.8 ms against 21-22 ms with the heavy / light plan)
+    smallShare = samples < (int64_t(24) << 20);
+    if (!std::getenv("NRT_LANES")) nlanes = int(std::min<int64_t>(smallShare ? 3 : 4, std::max<int64_t>(1, samples / (int64_t(1) << 20))));
     if (g_devs[0]->be.timing && !std::getenv("NRT_TIMELINE")) nlanes = 1;
   }
   nlanes = std::max(1, std::min(nlanes, kMaxLanes));
@@ -1547,8 +1625,8 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
                                         o->aa_kind, o->aa_kind == NRT_AA_NONE ? 1 : o->grid_size, nlanes};
   {
     const int64_t hardTail = Renderer<CudaBackend>::envInt("NRT_HARD_TAIL_BELOW", 16384);
-    const bool useFbk = Renderer<CudaBackend>::envInt("NRT_LANE_FEEDBACK", 1) != 0 && nlanes >= 2 && hardTail > 0;
-    int nHeavy = int(Renderer<CudaBackend>::envInt("NRT_HEAVY_LANES", nlanes >= 4 ? 2 : 1));
+    const bool useFbk = Renderer<CudaBackend>::envInt("NRT_LANE_FEEDBACK", smallShare ? 1 : 0) != 0 && nlanes >= 2 && hardTail > 0;
+    int nHeavy = int(Renderer<CudaBackend>::envInt("NRT_HEAVY_LANES", 1));
     nHeavy = std::max(1, std::min(nHeavy, nlanes - 1));
     for (int di = 0; di < nd; ++di) {
       auto& units = devUnits[size_t(di)];

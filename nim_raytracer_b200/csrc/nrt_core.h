@@ -194,12 +194,19 @@ struct alignas(16) MeshGateF { float cx, cy, cz, r2m; float mm, valid, pad0, pad
 //     margin    what the ray may carry: the grid takes a ray only if 1e-6 |o|_1 <= margin (conversion of o to float32,
 //               three float32 products and sums, the tilt seen from the ray's side); other rays use the cluster traversal
 //     1e-4 h    rounding of (p - lo) / h
+//
+// The same structure serves the PRIMARY rays (entry `nlights` of DScene.sgrid, persp = 1): they share the camera origin
+// (renderer.nim:42), so a sphere can only be hit by the directions inside its silhouette cone.  With (e1, e2, e3) the
+// rows of the world-to-camera rotation, a direction d maps to (X, Y) = (e1.d, e2.d) / e3.d on the plane one unit in
+// front of the camera, and a sphere to the bounding rectangle of its silhouette there (tangent angles in the (x, z)
+// and (y, z) planes).  Built for rigid cameras only; rays outside the grid or not facing forward take the clusters.
 struct ShadowGridF {
   float e1[3], e2[3];
   float lo1, lo2, invh, margin;
-  int32_t G, _pad;
+  int32_t G, persp;
   const uint32_t* start;   // G * G + 1 offsets into items
   const uint32_t* items;   // object indices
+  float e3[3], _padf;
 };
 struct BundleFrame;  // nrt_filter.h
 struct RecSet;       // nrt_filter.h
@@ -224,7 +231,7 @@ struct DScene {
   const BundleFrame* frames;      // [mo * (2 + nlights) + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
   const RecSet* recsets;          // same index: the filter record set of the bundle (per-thread mesh walk of the path kernels)
   const MeshGateF* mgate;         // per mesh object: float32 world-space bounding sphere of its box (meshGateMissF)
-  const ShadowGridF* sgrid;       // per light (G == 0: none), or null: light-space grids of the clustered spheres
+  const ShadowGridF* sgrid;       // nlights + 1 entries (G == 0: none), or null: light-space grids of the clustered spheres per DistantLight, then the camera grid
   double c2w[16];
   double cam_orig[4];             // c2w * (0,0,0,1): castPrimaryRay's origin (renderer.nim:42), the same product done once on the host
   double tan_half_fov;            // f of renderer.nim:38 (host libm, shared with nothing else)
@@ -326,13 +333,21 @@ NRT_HD bool certainMissF(const CObjF& c, const RayF& r) {
 // false: the grid does not take this ray (far origin, non-finite values): use the cluster traversal.
 // true: items [b, e) are the clustered spheres the ray can possibly hit (b == e outside the grid).
 NRT_HD bool shadowGridCell(const ShadowGridF& g, const RayF& rf, uint32_t& b, uint32_t& e) {
-  const float err = 1e-6f * (fabsf(rf.ox) + fabsf(rf.oy) + fabsf(rf.oz));
-  if (!(err <= g.margin)) return false;
-  const float p1 = fmaf(g.e1[0], rf.ox, fmaf(g.e1[1], rf.oy, g.e1[2] * rf.oz));
-  const float p2 = fmaf(g.e2[0], rf.ox, fmaf(g.e2[1], rf.oy, g.e2[2] * rf.oz));
+  float p1, p2;
+  if (g.persp) {   // a primary ray: its direction on the plane one unit in front of the camera
+    const float dz = fmaf(g.e3[0], rf.dx, fmaf(g.e3[1], rf.dy, g.e3[2] * rf.dz));
+    if (!(dz * dz > 0.09f * rf.a && dz > 0.f)) return false;    // not facing forward enough (or non-finite)
+    p1 = fmaf(g.e1[0], rf.dx, fmaf(g.e1[1], rf.dy, g.e1[2] * rf.dz)) / dz;
+    p2 = fmaf(g.e2[0], rf.dx, fmaf(g.e2[1], rf.dy, g.e2[2] * rf.dz)) / dz;
+  } else {
+    const float err = 1e-6f * (fabsf(rf.ox) + fabsf(rf.oy) + fabsf(rf.oz));
+    if (!(err <= g.margin)) return false;
+    p1 = fmaf(g.e1[0], rf.ox, fmaf(g.e1[1], rf.oy, g.e1[2] * rf.oz));
+    p2 = fmaf(g.e2[0], rf.ox, fmaf(g.e2[1], rf.oy, g.e2[2] * rf.oz));
+  }
   const float f1 = (p1 - g.lo1) * g.invh, f2 = (p2 - g.lo2) * g.invh;
   b = e = 0;
-  if (!(f1 >= 0.f && f2 >= 0.f && f1 < float(g.G) && f2 < float(g.G))) return f1 == f1 && f2 == f2;   // outside (NaN: not taken)
+  if (!(f1 >= 0.f && f2 >= 0.f && f1 < float(g.G) && f2 < float(g.G))) return !g.persp && f1 == f1 && f2 == f2;   // outside: nothing to hit (light grid) / not covered (camera grid); NaN: not taken
   int c1 = int(f1), c2 = int(f2);
   if (c1 > g.G - 1) c1 = g.G - 1;
   if (c2 > g.G - 1) c2 = g.G - 1;

@@ -153,6 +153,7 @@ struct ChunkState {
   // (run, chunk) pairs admitted by the chunk bounds of the current bundle (CUDA backend)
   int64_t pairCap;
   uint32_t* pairs;   // 2*pairCap
+  float* runc;       // 4 floats per ray run of the current bundle: the run's bounding circle (2-D bundles; CUDA backend)
   uint8_t* occ;      // NR         shadow ray (sample, light) found an occluder (ShadowTrace -> Resolve)
   // ordered queue compaction (CUDA backend): gate pass 1 writes a code per (mesh object, wave
   // position) and per-block counts; a scan turns the counts into queue offsets; pass 2 writes the
@@ -760,7 +761,9 @@ NRT_HD bool meshGatePassPre(const DScene& sc, int mo, V4 o, V4 d, const RayPre& 
   return meshGatePass(sc, mo, o, d);
 }
 
-// `sl` >= 0: the ray is a shadow ray towards light sl (its direction is that light's: the light-space grid applies)
+// `sl` >= 0: the ray is a shadow ray towards light sl (its direction is that light's: the light-space grid applies);
+// kPrimaryRay: a primary ray (its origin is the camera's: the camera grid applies)
+static constexpr int kPrimaryRay = -2;
 template <bool CL, class MP>
 NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, const RayPre& pre, int sl = -1);
 template <bool CL, class MP>
@@ -772,9 +775,9 @@ NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, doub
   TraceOut r; r.obj = -1; r.t = tNear; r.tri = kNoTri; r.tests = 0; r.hits = 0;
   const bool f32ok = pre.f32ok, fastRay = pre.fastRay;
   const RayF rf = pre.rf;
-  if (CL && sc.ncl1 > 0 && sl >= 0 && sc.sgrid && f32ok) {
-    // a DistantLight's shadow ray: the clustered spheres it can hit are listed in ONE cell of the light-space grid
-    const ShadowGridF g = sc.sgrid[sl];
+  if (CL && sc.ncl1 > 0 && (sl >= 0 || sl == kPrimaryRay) && sc.sgrid && f32ok) {
+    // a DistantLight's shadow ray / a primary ray: the clustered spheres it can hit are listed in ONE cell of the grid
+    const ShadowGridF g = sc.sgrid[sl >= 0 ? sl : sc.nlights];
     uint32_t gb = 0, ge = 0;
     if (g.G > 0 && shadowGridCell(g, rf, gb, ge) && ge - gb + uint32_t(sc.nslow) <= uint32_t(kSurvivorCap)) {
       uint32_t surv[kSurvivorCap] = {0};
@@ -940,7 +943,7 @@ struct ShadeT {
     const uint8_t alive = cs.active[s], code0 = (cs.nMO > 0) ? cs.gflag[idx] : uint8_t(0);
     const V4 o = (bounce == 0) ? primaryOrigin(*sc) : ld4(cs.rayO, cs.S, s);
     if (!alive) { cs.hitObj[s] = -1; return st; }
-    const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s, idx, code0}, o, d, NRT_INF);
+    const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s, idx, code0}, o, d, NRT_INF, bounce == 0 ? kPrimaryRay : -1);
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     if (bounce == 0) {
       st.v[ST_PRIMARY] = 1;
@@ -1288,7 +1291,7 @@ struct FusedBounceT {
     const RayPre pre = makeRayPre(o, d);
     for (int mo = 0; mo < nMO; ++mo)
       if (meshGatePassPre(*sc, mo, o, d, pre)) return toWavefront(s, d);
-    const TraceOut tr = traceObjectsPre<CL>(*sc, NoMesh{}, o, d, NRT_INF, pre);
+    const TraceOut tr = traceObjectsPre<CL>(*sc, NoMesh{}, o, d, NRT_INF, pre, bounce == 0 ? kPrimaryRay : -1);
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
     if (bounce == 0) st.v[ST_PRIMARY] = 1;
     uint8_t flag = 0;
@@ -1415,7 +1418,7 @@ struct PathWarpT {
       TraceOut tr; tr.obj = -1; tr.t = 0.0; tr.tri = kNoTri; tr.tests = 0; tr.hits = 0;
       V4 hitW = o, n = d, so = o;
       if (alive) {
-        tr = traceObjects<CL>(*sc, PreMesh{mr, WalkMesh{sc, bounce == 0 ? FM_ORIGIN : FM_GENERAL, 0, force_exact}}, o, d, NRT_INF);
+        tr = traceObjects<CL>(*sc, PreMesh{mr, WalkMesh{sc, bounce == 0 ? FM_ORIGIN : FM_GENERAL, 0, force_exact}}, o, d, NRT_INF, bounce == 0 ? kPrimaryRay : -1);
         st.v[ST_RAYS] += 1; st.v[ST_TESTS] += tr.tests; st.v[ST_HITS] += tr.hits;
         if (bounce == 0) { st.v[ST_PRIMARY] = 1; writeAovOf(fp, cs, s, tr); }
         if (tr.obj < 0) {   // renderer.nim:74-75 / :123-124: background

@@ -228,25 +228,57 @@ struct SceneData {
     h.nslow = int32_t(std::count_if(cobjf.begin(), cobjf.end(), [](const CObjF& f) { return !(f.r2m < 3.0e38f); }));
   }
 
-  // Light-space grids of the clustered spheres, one per DistantLight (nrt_core.h: ShadowGridF).  Host, float64.
+  // Light-space grids of the clustered spheres, one per DistantLight, and the camera grid (nrt_core.h: ShadowGridF).
+  // Host, float64.
   std::vector<void*> gridOwned;
   ShadowGridF* dSGrid = nullptr;
-  void buildShadowGrids() {
-    for (void* p : gridOwned) be->dfree(p);
-    gridOwned.clear();
-    dSGrid = nullptr;
-    h.sgrid = nullptr;
-    if (h.ncl1 <= 0 || lights.empty()) return;
-    std::vector<uint32_t> fast;
-    for (size_t i = 0; i < cobjf.size(); ++i) if (cobjf[i].r2m < 3.0e38f) fast.push_back(uint32_t(i));
-    std::vector<ShadowGridF> grids(lights.size(), ShadowGridF{});
-    bool any = false;
+  struct GridRect { double a1, b1, a2, b2; uint32_t obj; };   // conservative rectangle of an object on the grid's plane
+  // bins the rectangles (ascending obj) into G x G cells from (lo1, lo2), cell edge hcell; false: too many items
+  bool fillGrid(ShadowGridF& g, const std::vector<GridRect>& rects, double lo1, double lo2, double hcell, int G, double margin) {
+    g.lo1 = float(lo1); g.lo2 = float(lo2); g.invh = float(1.0 / hcell); g.margin = float(margin * 0.999); g.G = G;
+    // (cell coordinates are computed by the rays as (p - float(lo)) * float(1/h): the build uses the same two floats,
+    // and every rectangle is widened by 1e-4 h for the rounding of that expression)
+    const double flo1 = double(g.lo1), flo2 = double(g.lo2), finv = double(g.invh), pad = 1e-4 * hcell;
+    std::vector<uint32_t> count(size_t(G) * G + 1, 0);
+    auto range = [&](const GridRect& q, int& a1, int& b1, int& a2, int& b2) {
+      a1 = int(std::floor((q.a1 - pad - flo1) * finv)); b1 = int(std::floor((q.b1 + pad - flo1) * finv));
+      a2 = int(std::floor((q.a2 - pad - flo2) * finv)); b2 = int(std::floor((q.b2 + pad - flo2) * finv));
+      a1 = std::max(a1, 0); a2 = std::max(a2, 0); b1 = std::min(b1, G - 1); b2 = std::min(b2, G - 1);
+    };
+    int64_t total = 0;
+    for (const GridRect& q : rects) {
+      int a1, b1, a2, b2; range(q, a1, b1, a2, b2);
+      for (int y = a2; y <= b2; ++y) for (int x = a1; x <= b1; ++x) { ++count[size_t(y) * G + x + 1]; ++total; }
+    }
+    if (total > int64_t(64) * int64_t(rects.size()) + 65536) return false;   // huge footprints: no grid
+    for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
+    std::vector<uint32_t> items(size_t(std::max<int64_t>(total, 1)), 0), fill(count.begin(), count.end() - 1);
+    for (const GridRect& q : rects) {   // rects ascend by obj, so every cell's list does
+      int a1, b1, a2, b2; range(q, a1, b1, a2, b2);
+      for (int y = a2; y <= b2; ++y) for (int x = a1; x <= b1; ++x) items[fill[size_t(y) * G + x]++] = q.obj;
+    }
     auto gup = [&](const uint32_t* src, size_t n) {
       uint32_t* p = static_cast<uint32_t*>(be->dalloc(sizeof(uint32_t) * std::max<size_t>(n, 1)));
       gridOwned.push_back(p);
       if (n) { be->upload(p, src, sizeof(uint32_t) * n); bytes_uploaded += int64_t(sizeof(uint32_t) * n); }
       return p;
     };
+    g.start = gup(count.data(), count.size());
+    g.items = gup(items.data(), size_t(total));
+    be->sync();   // (the staging vectors die with this scope)
+    return true;
+  }
+  void buildShadowGrids(const nrt_scene_desc* desc) {
+    for (void* p : gridOwned) be->dfree(p);
+    gridOwned.clear();
+    dSGrid = nullptr;
+    h.sgrid = nullptr;
+    if (h.ncl1 <= 0) return;
+    std::vector<uint32_t> fast;
+    for (size_t i = 0; i < cobjf.size(); ++i) if (cobjf[i].r2m < 3.0e38f) fast.push_back(uint32_t(i));
+    if (fast.empty()) return;
+    std::vector<ShadowGridF> grids(lights.size() + 1, ShadowGridF{});
+    bool any = false;
     for (size_t l = 0; l < lights.size(); ++l) {
       if (lights[l].kind != NRT_LIGHT_DISTANT) continue;
       // ray direction u = -dir (renderer.nim:99); (e1, e2) spans the plane perpendicular to it
@@ -269,7 +301,7 @@ struct SceneData {
       struct Circ { double p1, p2, r, c1; };
       std::vector<Circ> cs;
       cs.reserve(fast.size());
-      double lo1 = 1e300, lo2 = 1e300, hi1 = -1e300, hi2 = -1e300, rsum = 0;
+      double lo1 = 1e300, lo2 = 1e300, hi1 = -1e300, hi2 = -1e300;
       bool ok = true;
       for (uint32_t i : fast) {
         const double c[3] = {-cobjs[i].t[0], -cobjs[i].t[1], -cobjs[i].t[2]};
@@ -281,52 +313,91 @@ struct SceneData {
         if (!(std::isfinite(q.p1) && std::isfinite(q.p2) && std::isfinite(q.r) && q.c1 < 1e12)) { ok = false; break; }
         lo1 = std::min(lo1, q.p1 - q.r); hi1 = std::max(hi1, q.p1 + q.r);
         lo2 = std::min(lo2, q.p2 - q.r); hi2 = std::max(hi2, q.p2 + q.r);
-        rsum += q.r;
         cs.push_back(q);
       }
-      if (!ok || cs.empty()) continue;
+      if (!ok) continue;
       const double ext = std::max(hi1 - lo1, hi2 - lo2);
       if (!(ext > 0) || !std::isfinite(ext)) continue;
-      int G = int(std::min(1024.0, std::max(16.0, 4.0 * std::sqrt(double(cs.size())))));
+      const int G = int(std::min(1024.0, std::max(16.0, 4.0 * std::sqrt(double(cs.size())))));
       double hcell = ext * 1.001 / G;
       const double margin = 0.02 * hcell;
       // the whole grid is moved out by the largest circle inflation, so that a ray outside it hits nothing
       double infl = 0;
-      for (const Circ& q : cs) infl = std::max(infl, q.r * 1e-6 + 4e-7 * q.c1 + margin + 1e-4 * hcell);
+      for (const Circ& q : cs) infl = std::max(infl, q.r * 1e-6 + 4e-7 * q.c1 + margin);
       lo1 -= 2 * infl; lo2 -= 2 * infl;
       hcell = (ext + 4 * infl) * 1.001 / G;
-      g.lo1 = float(lo1); g.lo2 = float(lo2); g.invh = float(1.0 / hcell); g.margin = float(margin * 0.999); g.G = G;
-      // (cell coordinates are computed by the rays as (p - float(lo)) * float(1/h): the build uses the same two floats)
-      const double flo1 = double(g.lo1), flo2 = double(g.lo2), finv = double(g.invh);
-      std::vector<uint32_t> count(size_t(G) * G + 1, 0);
-      auto range = [&](const Circ& q, int& a1, int& b1, int& a2, int& b2) {
-        const double R = q.r * (1.0 + 1e-6) + 4e-7 * q.c1 + margin + 1e-4 * hcell;
-        a1 = int(std::floor((q.p1 - R - flo1) * finv)); b1 = int(std::floor((q.p1 + R - flo1) * finv));
-        a2 = int(std::floor((q.p2 - R - flo2) * finv)); b2 = int(std::floor((q.p2 + R - flo2) * finv));
-        a1 = std::max(a1, 0); a2 = std::max(a2, 0); b1 = std::min(b1, G - 1); b2 = std::min(b2, G - 1);
-      };
-      int64_t total = 0;
-      for (const Circ& q : cs) {
-        int a1, b1, a2, b2; range(q, a1, b1, a2, b2);
-        for (int y = a2; y <= b2; ++y) for (int x = a1; x <= b1; ++x) { ++count[size_t(y) * G + x + 1]; ++total; }
+      std::vector<GridRect> rects;
+      rects.reserve(cs.size());
+      for (size_t n = 0; n < cs.size(); ++n) {
+        const double R = cs[n].r * (1.0 + 1e-6) + 4e-7 * cs[n].c1 + margin;
+        rects.push_back(GridRect{cs[n].p1 - R, cs[n].p1 + R, cs[n].p2 - R, cs[n].p2 + R, fast[n]});
       }
-      if (total > int64_t(64) * int64_t(cs.size()) + 65536) continue;   // huge circles: no grid for this light
-      for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
-      std::vector<uint32_t> items(size_t(std::max<int64_t>(total, 1)), 0), fill(count.begin(), count.end() - 1);
-      for (size_t n = 0; n < cs.size(); ++n) {   // `fast` ascends, so every cell's list does
-        int a1, b1, a2, b2; range(cs[n], a1, b1, a2, b2);
-        for (int y = a2; y <= b2; ++y) for (int x = a1; x <= b1; ++x) items[fill[size_t(y) * G + x]++] = fast[n];
-      }
-      g.start = gup(count.data(), count.size());
-      g.items = gup(items.data(), size_t(total));
+      if (!fillGrid(g, rects, lo1, lo2, hcell, G, margin)) continue;
       grids[l] = g;
       any = true;
+    }
+    // ---- the camera grid: rigid cameras only (the rows of the inverse rotation are then orthonormal, and a sphere
+    // stays a sphere of its own radius in camera space)
+    {
+      const double* M = desc->camera_to_world;   // m[col*4+row]
+      double E[3][3];   // rows of the inverse rotation = columns of the rotation; camera looks down -z: e3 = -(third column)
+      for (int k = 0; k < 3; ++k) { E[0][k] = M[0 * 4 + k]; E[1][k] = M[1 * 4 + k]; E[2][k] = -M[2 * 4 + k]; }
+      bool rigid = M[3] == 0.0 && M[7] == 0.0 && M[11] == 0.0 && M[15] == 1.0;
+      for (int i = 0; i < 3 && rigid; ++i)
+        for (int j = 0; j < 3; ++j) {
+          const double dp = E[i][0] * E[j][0] + E[i][1] * E[j][1] + E[i][2] * E[j][2];
+          if (!(std::fabs(dp - (i == j ? 1.0 : 0.0)) < 1e-9)) rigid = false;
+        }
+      const double fext = 2.5 * h.tan_half_fov;   // covers aspect ratios up to 2.5; other rays take the clusters
+      if (rigid && std::isfinite(fext) && fext > 1e-3 && fext <= 5.0) {   // (tan(1.45) = 8.2 lies outside the grid)
+        ShadowGridF g{};
+        g.persp = 1;
+        for (int k = 0; k < 3; ++k) { g.e1[k] = float(E[0][k]); g.e2[k] = float(E[1][k]); g.e3[k] = float(E[2][k]); }
+        const int G = int(std::min(512.0, std::max(32.0, 8.0 * std::sqrt(double(fast.size())))));
+        const double hcell = 2.0 * fext / G, margin = 0.02 * hcell;
+        // a ray's (X, Y) carries <= ~1.4e-6 (1 + |X|) of float32 error (three products per dot, the division, e3.d >= 0.3 |d|)
+        bool ok = margin >= 4e-6 * (1.0 + fext);
+        std::vector<GridRect> rects;
+        const double co[3] = {h.cam_orig[0], h.cam_orig[1], h.cam_orig[2]};
+        for (size_t n = 0; n < fast.size() && ok; ++n) {
+          const uint32_t i = fast[n];
+          const double c[3] = {-cobjs[i].t[0] - co[0], -cobjs[i].t[1] - co[1], -cobjs[i].t[2] - co[2]};
+          // camera-space centre through the float32 rows the rays use
+          double v[3];
+          for (int k = 0; k < 3; ++k) {
+            const float* e = k == 0 ? g.e1 : (k == 1 ? g.e2 : g.e3);
+            v[k] = double(e[0]) * c[0] + double(e[1]) * c[1] + double(e[2]) * c[2];
+          }
+          const double cl = std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]);
+          const double R = std::fabs(cobjs[i].radius) * (1.0 + 1e-5) + 1e-6 * cl;   // float32 rows: rigid only to ~1e-7
+          if (!(std::isfinite(R) && std::isfinite(cl) && cl < 1e12)) { ok = false; break; }
+          if (v[2] + R < 0.0) continue;   // entirely behind the camera plane: no forward ray reaches it
+          // extent of the silhouette in X: tangent angles of the circle (v[0], v[2]; R) seen from the origin
+          auto extent = [&](double x, double z, double& lo, double& hi) {
+            const double rho = std::sqrt(x * x + z * z);
+            lo = -fext; hi = fext;
+            if (!(rho > R * 1.001)) return;   // the origin is inside (or on) the circle: every direction
+            const double th = std::atan2(x, z), al = std::asin(R / rho);
+            if (th - al > -1.45) lo = std::tan(th - al);
+            if (th + al < 1.45) hi = std::tan(th + al);
+            if (th - al >= 1.45) lo = fext * 2;    // entirely beyond the grid on the + side
+            if (th + al <= -1.45) hi = -fext * 2;
+          };
+          GridRect q; q.obj = i;
+          extent(v[0], v[2], q.a1, q.b1);
+          extent(v[1], v[2], q.a2, q.b2);
+          q.a1 -= margin; q.b1 += margin; q.a2 -= margin; q.b2 += margin;
+          if (q.b1 < -fext || q.a1 > fext || q.b2 < -fext || q.a2 > fext) continue;   // outside the grid
+          rects.push_back(q);
+        }
+        if (ok && fillGrid(g, rects, -fext, -fext, hcell, G, margin)) { grids[lights.size()] = g; any = true; }
+      }
     }
     if (!any) return;
     dSGrid = static_cast<ShadowGridF*>(be->dalloc(sizeof(ShadowGridF) * grids.size()));
     gridOwned.push_back(dSGrid);
     be->upload(dSGrid, grids.data(), sizeof(ShadowGridF) * grids.size());
-    be->sync();   // (the staging vectors above die with this scope)
+    be->sync();
     h.sgrid = dSGrid;
   }
 
@@ -549,12 +620,12 @@ struct SceneData {
       dRecSets = up<RecSet>(nullptr, int64_t(frames.size()), reuse ? dRecSets : nullptr);   // filled once the records exist
     }
     h.cl1 = dCl1; h.cl2 = dCl2; h.clm = dClm; h.clmIdx = dClmIdx; h.slowIdx = dSlowIdx;
-    buildShadowGrids();   // (sets h.sgrid)
     h.objects = dObjs; h.cobjs = dCObjs; h.cobjf = dCObjF; h.lights = dLights; h.meshes = dMeshes; h.mesh_obj_index = dMo; h.frames = dFrames; h.recsets = dRecSets; h.mgate = dMGate;
     std::memcpy(h.c2w, desc->camera_to_world, sizeof(h.c2w));
     { const V4 co = mulm(h.c2w, v4(0.0, 0.0, 0.0, 1.0)); h.cam_orig[0] = co.x; h.cam_orig[1] = co.y; h.cam_orig[2] = co.z; h.cam_orig[3] = co.w; }
     h.tan_half_fov = std::tan((desc->fov * (kPi / 180.0)) / 2);  // renderer.nim:38; Nim degToRad = d * (PI/180)
     std::memcpy(h.bg, desc->bg_color, sizeof(h.bg));
+    buildShadowGrids(desc);   // (sets h.sgrid; needs h.cam_orig / h.tan_half_fov)
     d = up(&h, 1, reuse ? d : nullptr);
     // ---- filter records: GENERAL per mesh; ORIGIN / DIR per mesh object (device-side build) ----
     for (auto& m : meshes)
@@ -648,7 +719,10 @@ struct Renderer {
   // space of a HELPER pipeline — its own buffers, stream and host thread — which takes it to the end of its paths
   // while this pipeline runs H0's chain; the accumulators come back (ScatterAccum) before Finalize.
   Renderer* sub = nullptr;          // the helper (set by the owner; null: no fork)
-  int64_t forkMin = 4096;           // NRT_FORK_MIN: pools smaller than this stay here (0 = never fork)
+  // NRT_FORK_MIN: pools smaller than this stay here; 0 (the default) = never fork.  MEASURED AND LEFT OFF: the chains'
+  // kernels are persistent grids that occupy every SM while they wait on memory, so two chains in flight mostly
+  // take turns (1/8 frame: 3.56 -> 3.39 ms with one lane, nothing on top of three lanes; whole frame: 19.8 -> 20.4 ms)
+  int64_t forkMin = 0;
   struct SubResult { int rc = 0; bool overflow = false; std::string err; unsigned long long stats[ST_COUNT] = {0}; ProfileAcc pacc; int64_t n = 0; };
   std::vector<uint32_t> bandHard;   // per row unit of the last frame: samples on the bounce-0 wavefront list (fused path; else empty)
   // NRT_PATH: 0 = the wavefront for every bounce (round-1 pipeline), 1 = FusedBounce + wavefront for the samples
@@ -696,6 +770,7 @@ struct Renderer {
       cs.preRay = al<uint32_t>(4 * cand); cs.preRec = al<uint32_t>(4 * cand);
       capPairs = pairsWant;
       cs.pairs = al<uint32_t>(2 * capPairs);
+      cs.runc = al<float>(4 * (qcap / 128 + 8));   // (a run is >= 128 queue entries)
       cs.candRef = al<uint32_t>(cand); cs.candTri = al<uint32_t>(cand); cs.candT = al<double>(cand);
       cs.counters = al<uint32_t>(int64_t(waves) * std::max(nMO, 1) * cntStride(nL) + nrows);   // + the per-band counts (BandCount) behind the wave counters
       cs.alist = al<uint32_t>(2 * S); cs.hlist = al<uint32_t>(S); cs.flist = al<uint32_t>(S); cs.acount = al<uint32_t>(waves + 4);
@@ -893,7 +968,9 @@ struct Renderer {
           // the run's circle), sub-chunk bounds of the admitted pairs, and the records of the admitted sub-chunks; a
           // run is the prefilterRunRays(mode) consecutive queue entries of one warp
           const int64_t run = prefilterRunRays(mode);
-          const int64_t t = int64_t(c[cntBnd(b)]) * run + int64_t(c[cntWork(b)]) * run * kSubPerChunk + int64_t(c[cntSub(b)]) * run * kSubRecs;
+          // (cntBnd: chunk bounds AND sub-chunk bounds that were tested ray by ray; the sub-chunk circles of the 2-D
+          // bundles' first look at level 2 cost one test each)
+          const int64_t t = int64_t(c[cntBnd(b)]) * run + int64_t(c[cntWork(b)]) * kSubPerChunk + int64_t(c[cntSub(b)]) * run * kSubRecs;
           pacc.mesh_tests += t; pacc.tests_by_mode[mode] += t;
           queued += q;
         }
@@ -978,7 +1055,7 @@ struct Renderer {
     pathMode = int(envInt("NRT_PATH", -1));
     tailBelow = envInt("NRT_TAIL_BELOW", 32768);
     hardTailBelow = envInt("NRT_HARD_TAIL_BELOW", 16384);
-    forkMin = envInt("NRT_FORK_MIN", 4096);
+    forkMin = envInt("NRT_FORK_MIN", 0);
     bandHard.clear();
     if (pathMode < 0 || pathMode > 2) {
       // automatic: the fused path, unless the last frame of this pipeline showed that most samples have a ray entering

@@ -156,6 +156,7 @@ struct LoopBackend {
         for (uint32_t rq = r0; rq < r1 && !any; ++rq) any = prefilterTest(mode, bounds + 4 * ch, rayAt(rq));
         if (!any) continue;
         ++cnt[cntWork(b)];
+        cnt[cntBnd(b)] += uint32_t(kSubPerChunk);   // its sub-chunk bounds, tested ray by ray (nrt_renderer.h: countersToProfile)
         for (int64_t sb = ch * kSubPerChunk; sb < (ch + 1) * kSubPerChunk; ++sb) {
           bool anyS = !cull;
           for (uint32_t rq = r0; rq < r1 && !anyS; ++rq) anyS = prefilterTest(mode, sub + 4 * sb, rayAt(rq));

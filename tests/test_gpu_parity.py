@@ -504,6 +504,7 @@ def test_lane_plan_from_band_feedback_keeps_the_frame(oracle_mod, monkeypatch):
     sc = scenes.bunny_spheres(stride=4)
     o = api.Options(640, 512, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)
     rfb, rst, raov = oracle_mod.render(sc, o, aov=api.Aov(o.width, o.height))
+    monkeypatch.setenv("NRT_LANE_FEEDBACK", "1")
     for lanes, heavy in (("2", "1"), ("4", "2"), ("4", "1"), ("3", "2")):
         monkeypatch.setenv("NRT_LANES", lanes)
         monkeypatch.setenv("NRT_HEAVY_LANES", heavy)
