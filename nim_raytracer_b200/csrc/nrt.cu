@@ -47,7 +47,7 @@
 // spills 11.77 ms; 4 CTAs/SM = 64 registers 12.25 ms.  The kernel waits on fixed-latency float64 chains: warps in
 // flight are worth more than the spills cost.
 #ifndef NRT_OCC_FUSED
-#define NRT_OCC_FUSED 3
+#define NRT_OCC_FUSED 4   // r02 (mask grids, merged shadow loop): 3 CTAs/SM at 80 registers 10.28 ms, 4 at 64 registers 9.84 ms
 #endif
 #ifndef NRT_OCC_TAIL
 #define NRT_OCC_TAIL 1
@@ -1144,7 +1144,7 @@ struct CudaBackend {
     // elements per warp: all 32 lanes when the list fills the GPU's resident warps (8 per SM at this kernel's
     // register count), fewer for short lists
     int lpw = 32;
-    static const int64_t fill = [] { const char* e = std::getenv("NRT_TAIL_FILL"); return e ? std::max<int64_t>(1, std::atoll(e)) : int64_t(1); }();
+    static const int64_t fill = [] { const char* e = std::getenv("NRT_TAIL_FILL"); return e ? std::max<int64_t>(1, std::atoll(e)) : int64_t(4); }();   // measured on a 1/8 frame: 1 -> 0.29 ms, 4 -> 0.19 ms, 16 -> 0.21 ms
     while (lpw > 1 && n * 32 / lpw < int64_t(sms) * 8 * 32 * fill / 2) lpw >>= 1;   // i.e. while warps(n, lpw) < fill/2 x the resident warps
     const int64_t perCta = int64_t(kBlock / 32) * lpw;
     const int64_t blocks = (n + perCta - 1) / perCta;

@@ -200,6 +200,10 @@ struct alignas(16) MeshGateF { float cx, cy, cz, r2m; float mm, valid, pad0, pad
 // rows of the world-to-camera rotation, a direction d maps to (X, Y) = (e1.d, e2.d) / e3.d on the plane one unit in
 // front of the camera, and a sphere to the bounding rectangle of its silhouette there (tangent angles in the (x, z)
 // and (y, z) planes).  Built for rigid cameras only; rays outside the grid or not facing forward take the clusters.
+//
+// Scenes of at most 32 objects (every scene the reference ships) use the same grids with a 32-bit OBJECT MASK per cell
+// instead of a list (start == null, items[cell] = mask): one load replaces the first look at every object, and the
+// bounding spheres of the mesh boxes are binned too, so the same mask answers "can this ray enter mesh object mo's box".
 struct ShadowGridF {
   float e1[3], e2[3];
   float lo1, lo2, invh, margin;
@@ -231,6 +235,8 @@ struct DScene {
   const BundleFrame* frames;      // [mo * (2 + nlights) + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
   const RecSet* recsets;          // same index: the filter record set of the bundle (per-thread mesh walk of the path kernels)
   const MeshGateF* mgate;         // per mesh object: float32 world-space bounding sphere of its box (meshGateMissF)
+  uint32_t slowMask;              // scenes of <= 32 objects with mask grids: the objects the grids do not cover (always looked at)
+  int32_t maskGrids;              // 1: sgrid's cells hold ONE 32-bit object mask each (items[cell], start == null)
   const ShadowGridF* sgrid;       // nlights + 1 entries (G == 0: none), or null: light-space grids of the clustered spheres per DistantLight, then the camera grid
   double c2w[16];
   double cam_orig[4];             // c2w * (0,0,0,1): castPrimaryRay's origin (renderer.nim:42), the same product done once on the host
@@ -352,6 +358,7 @@ NRT_HD bool shadowGridCell(const ShadowGridF& g, const RayF& rf, uint32_t& b, ui
   if (c1 > g.G - 1) c1 = g.G - 1;
   if (c2 > g.G - 1) c2 = g.G - 1;
   const uint32_t cell = uint32_t(c2) * uint32_t(g.G) + uint32_t(c1);
+  if (!g.start) { b = g.items[cell]; e = 0; return true; }   // mask grid: the mask is returned in b
   b = g.start[cell]; e = g.start[cell + 1];
   return true;
 }
@@ -579,12 +586,15 @@ NRT_HD V3 shadeDiffuse(const DObject& o, const ShadingInfo& si, V4 hitNormal) {
 }
 
 // renderer.nim:31-44 (orig/dir only; initRay is applied per object in trace)
-NRT_HD void castPrimaryRay(const DScene& sc, double r /* = double(w) / double(h) */, int w, int h, double x, double y, V4& orig, V4& dir) {
-  const double f = sc.tan_half_fov;
-  const double cx = ((2 * x * r) / double(w) - r) * f;
-  const double cy = (1 - 2 * y / double(h)) * f;
+// (cx, cy) of renderer.nim:39-40
+NRT_HD double primaryCx(const DScene& sc, double r, int w, double x) { return ((2 * x * r) / double(w) - r) * sc.tan_half_fov; }
+NRT_HD double primaryCy(const DScene& sc, int h, double y) { return (1 - 2 * y / double(h)) * sc.tan_half_fov; }
+NRT_HD void castPrimaryRayC(const DScene& sc, double cx, double cy, V4& orig, V4& dir) {
   orig = v4(sc.cam_orig[0], sc.cam_orig[1], sc.cam_orig[2], sc.cam_orig[3]);
   dir = mulm(sc.c2w, normalize(v4(cx, cy, -1, 0.0)));
+}
+NRT_HD void castPrimaryRay(const DScene& sc, double r /* = double(w) / double(h) */, int w, int h, double x, double y, V4& orig, V4& dir) {
+  castPrimaryRayC(sc, primaryCx(sc, r, w, x), primaryCy(sc, h, y), orig, dir);
 }
 
 // counter-based RNG for the jittered AA kinds (same spec as the oracle)

@@ -298,7 +298,18 @@ NRT_HD void initSample(const ChunkState& cs, int64_t s, bool alive, V4 d) {
 }
 
 // ---- gen: one element per SAMPLE (akNone / akGrid) ---------------------------
-struct GenOut { bool alive; V4 o, d; };
+struct GenOut { bool alive; V4 o, d; double cx, cy; };
+// sample position of grid sample (i, j) inside its pixel (sampling.nim:5-18) / the pixel corner for akNone (renderer.nim:135)
+NRT_HD double sampleX(const FrameParams& fp, int x, int i) {
+  if (fp.aa_kind == AA_NONE) return double(x);
+  const double xs = fp.inv_grid, xoffs = xs * 0.5;
+  return double(x) + (double(i) * xs + xoffs);
+}
+NRT_HD double sampleY(const FrameParams& fp, int y, int j) {
+  if (fp.aa_kind == AA_NONE) return double(y);
+  const double xs = fp.inv_grid, ys = fp.inv_grid, yoffs = xs * 0.5;
+  return double(y) + (double(j) * ys + yoffs);
+}
 struct GenSimple {
   const DScene* sc; FrameParams fp; ChunkState cs;
   NRT_HD void operator()(int64_t s) const { GenOut out; run(s, out); }
@@ -312,18 +323,16 @@ struct GenSimple {
     const int k = int(s - sp * fp.spp);
     int x, y; pixelOf(fp, cs, p, x, y);
     const bool alive = !pixelSkipped(fp, x, y);
-    double sx = 0.0, sy = 0.0;
-    if (fp.aa_kind == AA_GRID) {  // sampling.nim:5-18, element j*m+i
-      const int m = fp.grid, j = int(divFast(k, m)), i = k - j * m;
-      const double xs = fp.inv_grid, ys = fp.inv_grid;
-      const double xoffs = xs * 0.5, yoffs = xs * 0.5;
-      sx = double(i) * xs + xoffs; sy = double(j) * ys + yoffs;
-    }
+    int i = 0, j = 0;
+    if (fp.aa_kind == AA_GRID) { j = int(divFast(k, fp.grid)); i = k - j * fp.grid; }   // sampling.nim:5-18, element j*m+i
     V4 o, d;
     // akNone: (x.float, y.float) — the pixel corner (renderer.nim:135); else x.float + sample
-    castPrimaryRay(*sc, fp.aspect, fp.width, fp.height, fp.aa_kind == AA_NONE ? double(x) : double(x) + sx,
-                   fp.aa_kind == AA_NONE ? double(y) : double(y) + sy, o, d);
-    out.alive = alive; out.o = o; out.d = d;
+    // (per-column / per-row tables of cx and cy — two loads instead of two float64 divisions per sample — were
+    // measured and dropped: FusedBounce 9.42 ms with them, 9.41 ms without; the kernel waits on latency, not on issue)
+    const double cx = primaryCx(*sc, fp.aspect, fp.width, sampleX(fp, x, i));
+    const double cy = primaryCy(*sc, fp.height, sampleY(fp, y, j));
+    castPrimaryRayC(*sc, cx, cy, o, d);
+    out.alive = alive; out.o = o; out.d = d; out.cx = cx; out.cy = cy;
   }
 };
 
@@ -739,9 +748,12 @@ NRT_HD bool firstLookMiss(const MP& mp, const CObjF& c, const RayF& rf, bool f32
 // CL: the scene has sphere clusters (the host picks the kernel variant, so that the flat scan of small
 // scenes keeps its register budget).
 // Per-ray facts shared by every float32 first look at the ray (object scan, mesh gates)
-struct RayPre { RayF rf; bool f32ok, fastRay; };
+// gridOk: `gridMask` lists (bit i <-> object i) every object of a mask-grid scene the ray can possibly hit — spheres the
+// float32 test applies to and mesh boxes with a float32 gate record; the other objects are in DScene.slowMask
+struct RayPre { RayF rf; bool f32ok, fastRay, gridOk; uint32_t gridMask; };
 NRT_HD RayPre makeRayPre(V4 o, V4 d) {
   RayPre p;
+  p.gridOk = false; p.gridMask = 0xFFFFFFFFu;
   // the exact shortcut of toObject() for [I | t] matrices applies to this ray?  (zero components
   // need toObject()'s per-component treatment)
   p.f32ok = (o.w == 1.0) && (d.w == 0.0) && finite3(o) && finite3(d);
@@ -749,8 +761,40 @@ NRT_HD RayPre makeRayPre(V4 o, V4 d) {
   p.rf = makeRayF(o, d);
   return p;
 }
+static constexpr int kPrimaryRay = -2;
+// makeRayPre + the ray's cell of the scene's mask grid: `sl` >= 0: a shadow ray towards light sl (its direction is that
+// light's), kPrimaryRay: a primary ray (its origin is the camera's), anything else: no grid applies
+NRT_HD RayPre makeRayPreGrid(const DScene& sc, V4 o, V4 d, int sl) {
+  RayPre p = makeRayPre(o, d);
+  if (sc.maskGrids && sc.sgrid && p.f32ok && (sl >= 0 || sl == kPrimaryRay)) {
+    const ShadowGridF g = sc.sgrid[sl >= 0 ? sl : sc.nlights];
+    uint32_t m = 0, e = 0;
+    if (g.G > 0 && shadowGridCell(g, p.rf, m, e)) { p.gridOk = true; p.gridMask = m | sc.slowMask; }
+  }
+  return p;
+}
+// the same for a primary ray whose (cx, cy) of castPrimaryRay is known: that IS its point on the camera grid's plane
+// (the direction is c2w * normalize(cx, cy, -1)), so the three dot products and two divisions of the lookup are skipped
+NRT_HD RayPre makeRayPrePrimary(const DScene& sc, V4 o, V4 d, double cx, double cy) {
+  RayPre p = makeRayPre(o, d);
+  if (sc.maskGrids && sc.sgrid && p.f32ok) {
+    const ShadowGridF g = sc.sgrid[sc.nlights];
+    if (g.G > 0 && g.persp) {
+      const float f1 = (float(cx) - g.lo1) * g.invh, f2 = (float(cy) - g.lo2) * g.invh;
+      if (f1 >= 0.f && f2 >= 0.f && f1 < float(g.G) && f2 < float(g.G)) {
+        int c1 = int(f1), c2 = int(f2);
+        if (c1 > g.G - 1) c1 = g.G - 1;
+        if (c2 > g.G - 1) c2 = g.G - 1;
+        p.gridOk = true;
+        p.gridMask = g.items[uint32_t(c2) * uint32_t(g.G) + uint32_t(c1)] | sc.slowMask;
+      }
+    }
+  }
+  return p;
+}
 // the AABB gate of mesh object mo for a world-space ray: float32 first look, then the reference's evaluation
 NRT_HD bool meshGatePassPre(const DScene& sc, int mo, V4 o, V4 d, const RayPre& pre) {
+  if (pre.gridOk && !((pre.gridMask >> (uint32_t(sc.mesh_obj_index[mo]) & 31u)) & 1u)) return false;   // the ray's line misses the box's bounding sphere
 #if defined(__CUDA_ARCH__)
   const float4 g0 = __ldg(reinterpret_cast<const float4*>(sc.mgate + mo)), g1 = __ldg(reinterpret_cast<const float4*>(sc.mgate + mo) + 1);
   MeshGateF g; g.cx = g0.x; g.cy = g0.y; g.cz = g0.z; g.r2m = g0.w; g.mm = g1.x; g.valid = g1.y; g.pad0 = g.pad1 = 0.f;
@@ -763,12 +807,11 @@ NRT_HD bool meshGatePassPre(const DScene& sc, int mo, V4 o, V4 d, const RayPre& 
 
 // `sl` >= 0: the ray is a shadow ray towards light sl (its direction is that light's: the light-space grid applies);
 // kPrimaryRay: a primary ray (its origin is the camera's: the camera grid applies)
-static constexpr int kPrimaryRay = -2;
 template <bool CL, class MP>
 NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, const RayPre& pre, int sl = -1);
 template <bool CL, class MP>
 NRT_HD TraceOut traceObjects(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, int sl = -1) {
-  return traceObjectsPre<CL>(sc, mp, o, d, tNear, makeRayPre(o, d), sl);
+  return traceObjectsPre<CL>(sc, mp, o, d, tNear, makeRayPreGrid(sc, o, d, sl), sl);
 }
 template <bool CL, class MP>
 NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, double tNear, const RayPre& pre, int sl) {
@@ -896,7 +939,10 @@ NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, doub
   for (int base = 0; base < sc.nobjects; base += 32) {
     const int nb = (sc.nobjects - base < 32) ? sc.nobjects - base : 32;
     uint32_t need = (nb == 32) ? 0xFFFFFFFFu : ((1u << nb) - 1u);
-    {
+    if (pre.gridOk) {
+      // mask-grid scene (<= 32 objects: one batch): the ray's cell already lists what it can hit
+      need &= pre.gridMask;
+    } else {
       // branch-free: EVERY record goes through the sphere formula — a record that is not a float32 sphere has
       // r2m = +Inf, for which the test is never true, and is looked at again (by tag) below
       uint32_t miss = 0;
@@ -911,6 +957,7 @@ NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, doub
       need &= need - 1;
       const CObjF c = loadCObjF(sc.cobjf + i);
       if (!(c.r2m < 3.0e38f) && firstLookMiss(mp, c, rf, f32ok)) continue;   // plane below / above the ray, mesh box not entered
+      if (pre.gridOk && c.r2m < 3.0e38f && certainMissF(c, rf)) continue;     // (the cell's spheres: the per-ray first look)
       evalObject(sc, mp, i, o, d, fastRay, r);
     }
   }
@@ -1273,13 +1320,15 @@ struct FusedBounceT {
     const int64_t s = sampleOf(act, idx);
     V4 o, d;
     double w = 1.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    double pcx = 0.0, pcy = 0.0;   // castPrimaryRay's (cx, cy) when this thread generated the ray
+    bool havePc = false;
     if (bounce == 0) {
       bool alive;
       if (genFromState) {
         o = primaryOrigin(*sc); d = ld4(cs.rayD, cs.S, s); alive = cs.active[s] != 0;
       } else {
         GenOut g; GenSimple{sc, fp, cs}.compute(s, g);
-        o = g.o; d = g.d; alive = g.alive;
+        o = g.o; d = g.d; alive = g.alive; pcx = g.cx; pcy = g.cy; havePc = true;
       }
       if (!alive) { cs.active[s] = 0; return st; }   // (skipped pixel of a progressive pass)
     } else {
@@ -1288,7 +1337,7 @@ struct FusedBounceT {
       a0 = cs.accum[s]; a1 = cs.accum[cs.S + s]; a2 = cs.accum[2 * cs.S + s];
     }
     const int nMO = cs.nMO, nL = cs.nL;
-    const RayPre pre = makeRayPre(o, d);
+    const RayPre pre = havePc ? makeRayPrePrimary(*sc, o, d, pcx, pcy) : makeRayPreGrid(*sc, o, d, bounce == 0 ? kPrimaryRay : -1);
     for (int mo = 0; mo < nMO; ++mo)
       if (meshGatePassPre(*sc, mo, o, d, pre)) return toWavefront(s, d);
     const TraceOut tr = traceObjectsPre<CL>(*sc, NoMesh{}, o, d, NRT_INF, pre, bounce == 0 ? kPrimaryRay : -1);
@@ -1303,22 +1352,21 @@ struct FusedBounceT {
       const V4 hitW = add(o, scale(d, tr.t));
       const V4 n = hitNormal(*sc, ob, tr, hitW);
       const V4 so = add(hitW, scale(n, fp.bias));                                    // renderer.nim:98
-      if (nMO > 0)
-        for (int l = 0; l < nL; ++l) {   // a shadow ray that enters a mesh box: the wavefront takes the sample
-          const V4 sdir = scale(getShadingInfo(sc->lights[l], hitW).lightDir, -1.0);
-          const RayPre sp = makeRayPre(so, sdir);
-          for (int mo = 0; mo < nMO; ++mo)
-            if (meshGatePassPre(*sc, mo, so, sdir, sp)) return toWavefront(s, d);
-        }
-      if (bounce == 0) writeAovOf(fp, cs, s, tr);
+      // One pass over the lights: a shadow ray that enters a mesh box hands the sample to the wavefront (nothing has
+      // been written or counted yet: `st` and `local` die with the return), any other is traced here — the ray's
+      // float32 image and grid cell (RayPre) serve the gate and the object scan alike.
       V3 local = v3(0.0, 0.0, 0.0);
       for (int l = 0; l < nL; ++l) {
         const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
         const V4 sdir = scale(li.lightDir, -1.0);                                    // renderer.nim:99
-        const TraceOut ts = traceObjects<CL>(*sc, NoMesh{}, so, sdir, li.lightDistance, l);
+        const RayPre sp = makeRayPreGrid(*sc, so, sdir, l);
+        for (int mo = 0; mo < nMO; ++mo)
+          if (meshGatePassPre(*sc, mo, so, sdir, sp)) return toWavefront(s, d);
+        const TraceOut ts = traceObjectsPre<CL>(*sc, NoMesh{}, so, sdir, li.lightDistance, sp, l);
         st.v[ST_RAYS] += 1; st.v[ST_TESTS] += ts.tests; st.v[ST_HITS] += ts.hits;
         if (ts.obj < 0) local = add(local, shadeDiffuse(ob, li, n));                 // renderer.nim:103-105
       }
+      if (bounce == 0) writeAovOf(fp, cs, s, tr);
       // resolveSample's arithmetic
       const double k = ob.reflection;
       const int depth = (fp.depth_mode == DEPTH_INTENDED) ? (1 + bounce) : 0;      // renderer.nim:108 + depth bug

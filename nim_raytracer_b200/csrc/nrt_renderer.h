@@ -91,6 +91,7 @@ struct SceneData {
   BundleFrame* dFrames = nullptr;
   RecSet* dRecSets = nullptr;             // device table of the record sets, indexed like the frames (DScene.recsets)
   MeshGateF* dMGate = nullptr;            // float32 gate records per mesh object (DScene.mgate)
+  std::vector<MeshGateF> hMGate;          // host copy (mask grids bin the boxes' bounding spheres)
   bool anyGeneralShadow = false;          // some shadow rays need the GENERAL bundle (point light / unusable frame)
   std::vector<MoRecs> moRecs;
   uint32_t* dRecCount = nullptr;          // [mo * recStride() + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
@@ -234,8 +235,25 @@ struct SceneData {
   ShadowGridF* dSGrid = nullptr;
   struct GridRect { double a1, b1, a2, b2; uint32_t obj; };   // conservative rectangle of an object on the grid's plane
   // bins the rectangles (ascending obj) into G x G cells from (lo1, lo2), cell edge hcell; false: too many items
-  bool fillGrid(ShadowGridF& g, const std::vector<GridRect>& rects, double lo1, double lo2, double hcell, int G, double margin) {
+  bool fillGrid(ShadowGridF& g, const std::vector<GridRect>& rects, double lo1, double lo2, double hcell, int G, double margin, bool masks = false) {
     g.lo1 = float(lo1); g.lo2 = float(lo2); g.invh = float(1.0 / hcell); g.margin = float(margin * 0.999); g.G = G;
+    if (masks) {   // one 32-bit object mask per cell (scenes of <= 32 objects)
+      const double flo1 = double(g.lo1), flo2 = double(g.lo2), finv = double(g.invh), pad = 1e-4 * hcell;
+      std::vector<uint32_t> cell(size_t(G) * G, 0u);
+      for (const GridRect& q : rects) {
+        int a1 = int(std::floor((q.a1 - pad - flo1) * finv)), b1 = int(std::floor((q.b1 + pad - flo1) * finv));
+        int a2 = int(std::floor((q.a2 - pad - flo2) * finv)), b2 = int(std::floor((q.b2 + pad - flo2) * finv));
+        a1 = std::max(a1, 0); a2 = std::max(a2, 0); b1 = std::min(b1, G - 1); b2 = std::min(b2, G - 1);
+        for (int y = a2; y <= b2; ++y) for (int x = a1; x <= b1; ++x) cell[size_t(y) * G + x] |= 1u << (q.obj & 31u);
+      }
+      uint32_t* p = static_cast<uint32_t*>(be->dalloc(sizeof(uint32_t) * cell.size()));
+      gridOwned.push_back(p);
+      be->upload(p, cell.data(), sizeof(uint32_t) * cell.size());
+      bytes_uploaded += int64_t(sizeof(uint32_t) * cell.size());
+      be->sync();
+      g.start = nullptr; g.items = p;
+      return true;
+    }
     // (cell coordinates are computed by the rays as (p - float(lo)) * float(1/h): the build uses the same two floats,
     // and every rectangle is widened by 1e-4 h for the rounding of that expression)
     const double flo1 = double(g.lo1), flo2 = double(g.lo2), finv = double(g.invh), pad = 1e-4 * hcell;
@@ -273,10 +291,33 @@ struct SceneData {
     gridOwned.clear();
     dSGrid = nullptr;
     h.sgrid = nullptr;
-    if (h.ncl1 <= 0) return;
+    h.maskGrids = 0; h.slowMask = 0;
+    // list grids for clustered scenes, mask grids for scenes of at most 32 objects, nothing in between (flat scan)
+    const bool masks = h.ncl1 <= 0 && cobjf.size() <= 32;
+    if (h.ncl1 <= 0 && !masks) return;
+    // the bounding spheres the grids bin: the spheres the float32 first look applies to and, in mask grids, the mesh
+    // boxes with a float32 gate record (centre and radius with the record's margins)
+    struct Ball { double c[3], r; uint32_t obj; };
+    std::vector<Ball> balls;
     std::vector<uint32_t> fast;
-    for (size_t i = 0; i < cobjf.size(); ++i) if (cobjf[i].r2m < 3.0e38f) fast.push_back(uint32_t(i));
-    if (fast.empty()) return;
+    uint32_t covered = 0;
+    for (size_t i = 0; i < cobjf.size(); ++i)
+      if (cobjf[i].r2m < 3.0e38f) {
+        fast.push_back(uint32_t(i));
+        balls.push_back(Ball{{-cobjs[i].t[0], -cobjs[i].t[1], -cobjs[i].t[2]}, std::fabs(cobjs[i].radius), uint32_t(i)});
+        covered |= 1u << (i & 31u);
+      }
+    if (masks) {
+      for (size_t mo = 0; mo < moIndex.size() && mo < hMGate.size(); ++mo) {
+        const MeshGateF& mg = hMGate[mo];
+        if (!(mg.valid > 0.f) || !(mg.r2m < 3.0e38f)) continue;
+        balls.push_back(Ball{{double(mg.cx), double(mg.cy), double(mg.cz)}, std::sqrt(double(mg.r2m)) * (1.0 + 1e-6), uint32_t(moIndex[mo])});
+        covered |= 1u << (uint32_t(moIndex[mo]) & 31u);
+      }
+      std::sort(balls.begin(), balls.end(), [](const Ball& a, const Ball& b) { return a.obj < b.obj; });
+      h.slowMask = ~covered;
+    }
+    if (balls.empty()) return;
     std::vector<ShadowGridF> grids(lights.size() + 1, ShadowGridF{});
     bool any = false;
     for (size_t l = 0; l < lights.size(); ++l) {
@@ -303,12 +344,12 @@ struct SceneData {
       cs.reserve(fast.size());
       double lo1 = 1e300, lo2 = 1e300, hi1 = -1e300, hi2 = -1e300;
       bool ok = true;
-      for (uint32_t i : fast) {
-        const double c[3] = {-cobjs[i].t[0], -cobjs[i].t[1], -cobjs[i].t[2]};
+      for (const Ball& bl : balls) {
+        const double* c = bl.c;
         Circ q;
         q.p1 = f1[0] * c[0] + f1[1] * c[1] + f1[2] * c[2];
         q.p2 = f2[0] * c[0] + f2[1] * c[1] + f2[2] * c[2];
-        q.r = std::fabs(cobjs[i].radius);
+        q.r = bl.r;
         q.c1 = std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]);
         if (!(std::isfinite(q.p1) && std::isfinite(q.p2) && std::isfinite(q.r) && q.c1 < 1e12)) { ok = false; break; }
         lo1 = std::min(lo1, q.p1 - q.r); hi1 = std::max(hi1, q.p1 + q.r);
@@ -318,7 +359,7 @@ struct SceneData {
       if (!ok) continue;
       const double ext = std::max(hi1 - lo1, hi2 - lo2);
       if (!(ext > 0) || !std::isfinite(ext)) continue;
-      const int G = int(std::min(1024.0, std::max(16.0, 4.0 * std::sqrt(double(cs.size())))));
+      const int G = masks ? 256 : int(std::min(1024.0, std::max(16.0, 4.0 * std::sqrt(double(cs.size())))));
       double hcell = ext * 1.001 / G;
       const double margin = 0.02 * hcell;
       // the whole grid is moved out by the largest circle inflation, so that a ray outside it hits nothing
@@ -330,9 +371,9 @@ struct SceneData {
       rects.reserve(cs.size());
       for (size_t n = 0; n < cs.size(); ++n) {
         const double R = cs[n].r * (1.0 + 1e-6) + 4e-7 * cs[n].c1 + margin;
-        rects.push_back(GridRect{cs[n].p1 - R, cs[n].p1 + R, cs[n].p2 - R, cs[n].p2 + R, fast[n]});
+        rects.push_back(GridRect{cs[n].p1 - R, cs[n].p1 + R, cs[n].p2 - R, cs[n].p2 + R, balls[n].obj});
       }
-      if (!fillGrid(g, rects, lo1, lo2, hcell, G, margin)) continue;
+      if (!fillGrid(g, rects, lo1, lo2, hcell, G, margin, masks)) continue;
       grids[l] = g;
       any = true;
     }
@@ -353,15 +394,15 @@ struct SceneData {
         ShadowGridF g{};
         g.persp = 1;
         for (int k = 0; k < 3; ++k) { g.e1[k] = float(E[0][k]); g.e2[k] = float(E[1][k]); g.e3[k] = float(E[2][k]); }
-        const int G = int(std::min(512.0, std::max(32.0, 8.0 * std::sqrt(double(fast.size())))));
+        const int G = masks ? 512 : int(std::min(512.0, std::max(32.0, 8.0 * std::sqrt(double(fast.size())))));
         const double hcell = 2.0 * fext / G, margin = 0.02 * hcell;
         // a ray's (X, Y) carries <= ~1.4e-6 (1 + |X|) of float32 error (three products per dot, the division, e3.d >= 0.3 |d|)
         bool ok = margin >= 4e-6 * (1.0 + fext);
         std::vector<GridRect> rects;
         const double co[3] = {h.cam_orig[0], h.cam_orig[1], h.cam_orig[2]};
-        for (size_t n = 0; n < fast.size() && ok; ++n) {
-          const uint32_t i = fast[n];
-          const double c[3] = {-cobjs[i].t[0] - co[0], -cobjs[i].t[1] - co[1], -cobjs[i].t[2] - co[2]};
+        for (size_t n = 0; n < balls.size() && ok; ++n) {
+          const uint32_t i = balls[n].obj;
+          const double c[3] = {balls[n].c[0] - co[0], balls[n].c[1] - co[1], balls[n].c[2] - co[2]};
           // camera-space centre through the float32 rows the rays use
           double v[3];
           for (int k = 0; k < 3; ++k) {
@@ -369,7 +410,7 @@ struct SceneData {
             v[k] = double(e[0]) * c[0] + double(e[1]) * c[1] + double(e[2]) * c[2];
           }
           const double cl = std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]);
-          const double R = std::fabs(cobjs[i].radius) * (1.0 + 1e-5) + 1e-6 * cl;   // float32 rows: rigid only to ~1e-7
+          const double R = balls[n].r * (1.0 + 1e-5) + 1e-6 * cl;   // float32 rows: rigid only to ~1e-7
           if (!(std::isfinite(R) && std::isfinite(cl) && cl < 1e12)) { ok = false; break; }
           if (v[2] + R < 0.0) continue;   // entirely behind the camera plane: no forward ray reaches it
           // extent of the silhouette in X: tangent angles of the circle (v[0], v[2]; R) seen from the origin
@@ -390,7 +431,7 @@ struct SceneData {
           if (q.b1 < -fext || q.a1 > fext || q.b2 < -fext || q.a2 > fext) continue;   // outside the grid
           rects.push_back(q);
         }
-        if (ok && fillGrid(g, rects, -fext, -fext, hcell, G, margin)) { grids[lights.size()] = g; any = true; }
+        if (ok && fillGrid(g, rects, -fext, -fext, hcell, G, margin, masks)) { grids[lights.size()] = g; any = true; }
       }
     }
     if (!any) return;
@@ -399,6 +440,7 @@ struct SceneData {
     be->upload(dSGrid, grids.data(), sizeof(ShadowGridF) * grids.size());
     be->sync();
     h.sgrid = dSGrid;
+    h.maskGrids = masks ? 1 : 0;
   }
 
   // Validates and flattens `desc`; with `reuse` the existing device buffers are refilled.
@@ -615,6 +657,7 @@ struct SceneData {
           }
         }
         dMGate = up(mg.data(), int64_t(mg.size()), reuse ? dMGate : nullptr);
+        hMGate = mg;
       }
       dFrames = up(frames.data(), int64_t(frames.size()), reuse ? dFrames : nullptr);
       dRecSets = up<RecSet>(nullptr, int64_t(frames.size()), reuse ? dRecSets : nullptr);   // filled once the records exist

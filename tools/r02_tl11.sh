@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+{
+echo "=== FULL default"
+timeout 300 python tools/frame_breakdown.py config4 config3 2>&1 | grep -v "fb sha"
+echo "=== FULL FB at 4 CTAs/SM"
+NRT_LIB=/root/repo/tools/ab/libnrt_fb4.so timeout 300 python tools/frame_breakdown.py config4 2>&1 | grep -v "fb sha"
+echo "=== part 0,8"
+NRT_TAIL_FILL=4 NRT_PART=0,8 timeout 300 python tools/frame_breakdown.py config4 2>&1 | grep -v "fb sha"
+} > gpurun_out/r02ze.log 2>&1
+cut -c1-330 gpurun_out/r02ze.log
