@@ -301,6 +301,10 @@ def main():
         api.initRenderer(devices=list(range(args.gpus)))
     else:
         api.initRenderer(devices=[local_rank])
+        # one process per GPU: run on the CPUs close to it (the render chain is dependent launches with host round
+        # trips; NRT_BENCH_PIN=0 leaves the placement to the OS).  The library pins its own lane threads itself.
+        if os.environ.get("NRT_BENCH_PIN", "1") != "0":
+            api.pinToDevice(0)
     api.setPartition(rank, world)
     scene, opts, desc = workload(args.workload)
     ds = api.DeviceScene(scene)
@@ -380,6 +384,12 @@ def main():
     if dist is not None:
         OP = dist.ReduceOp
     t_ms = allreduce(max(wall_ms, ms_dev.value), OP.MAX if OP else None)
+    # per-rank view of the timed region (diagnostic: which rank the MAX comes from, host vs device time)
+    rank_times = [{"rank": rank, "wall_ms_per_step": wall_ms / args.steps, "device_ms_per_step": ms_dev.value / args.steps}]
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, rank_times[0])
+        rank_times = gathered
     total_rays = allreduce(float(rays), OP.SUM if OP else None)
     klaunches = allreduce(float(prof_acc["klaunches"]), OP.SUM if OP else None)
     value = total_rays / (t_ms * 1e-3) / 1e6
@@ -564,6 +574,7 @@ def main():
                        "warmup_extra_steps": extra_warm},
             "frames_per_s": args.steps / (t_ms * 1e-3), "rays_per_frame": total_rays / args.steps,
             "device_ms_per_step": ms_dev.value / args.steps,
+            "ranks": rank_times,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(klaunches),
             "roofline": roofline, "intersection_kernel": intersection, "kernels": kernels, "kernel_timing_frame_ms": kframe_ms,
             "frame_hbm_bytes_model": frame_bytes,

@@ -207,18 +207,27 @@ typedef struct nrt_ipc_handle { unsigned char bytes[64]; } nrt_ipc_handle;
 int nrt_init(int ngpu, const int* dev_ids);
 void nrt_shutdown(void);
 int nrt_device_count(void);           /* devices selected by nrt_init            */
+/* The CPUs close to selected device `index` as a Linux cpulist ("0-31,64-95"; "" when unknown).  The library runs its
+ * own host threads there; the caller — the Nim main thread that replaces raytracer.nim:61-70's worker pool — does
+ * well to run there too (a frame is a chain of dependent launches with host round trips).  No reference counterpart. */
+int nrt_device_local_cpus(int index, char* buf, int buflen);
 const char* nrt_last_error(void);     /* thread-local message of the last failure */
 int nrt_abi_version(void);
 
 /* Multi-process sharding (one process per GPU): this process renders only the
- * row bands `index, index+count, ...` (band height nrt_band_rows()) of every
+ * row bands it owns (nrt_unit_owner; band height nrt_band_rows_for()) of every
  * nrt_render* call; other pixels are left untouched.  Default (0,1).
  * Reference counterpart: the per-scanline work items of raytracer.nim:67-70. */
 int nrt_set_partition(int index, int count);
+/* The partition that renders unit `unit` (band or rendered scanline, counted from y0) when `count` partitions share
+ * a pass: unit mod count in even rounds of `count` units, count - 1 - (unit mod count) in odd rounds (a serpentine
+ * deal: equal mean position inside a round for every partition).  Callers that assemble the frame themselves
+ * (distributed.py: owned_rows / gather_rows) use it to know whose rows are whose. */
+int nrt_unit_owner(long long unit, int count);
 int nrt_band_rows(void);   /* 1: the band height of progressive passes (kept for ABI v1 callers) */
 /* Band height T of a pass with these options: whole-resolution passes (step == max_step == 1) deal the image out in
  * bands of T scanlines — rows of T x T screen-space tiles, enumerated tile by tile inside a band — where T is the
- * largest power of two with T*T*spp <= 256 (16 spp: 4); partition `index` renders the bands index, index + count, ...
+ * largest power of two with T*T*spp <= 256 (16 spp: 4); partition `index` renders the bands nrt_unit_owner gives it,
  * counted from y0.  Progressive passes: 1. */
 int nrt_band_rows_for(const nrt_options* opts, int step, int max_step);
 

@@ -435,6 +435,34 @@ def initRenderer(ngpu: int = 1, devices: Optional[Sequence[int]] = None) -> None
     _initialised = True
 
 
+def deviceLocalCpus(index: int = 0) -> List[int]:
+    """CPUs close to selected device `index` (nrt_device_local_cpus); [] when unknown."""
+    buf = C.create_string_buffer(4096)
+    L = lib()
+    L.nrt_device_local_cpus.argtypes = [C.c_int, C.c_char_p, C.c_int]
+    check(L.nrt_device_local_cpus(index, buf, len(buf)), "nrt_device_local_cpus")
+    cpus: List[int] = []
+    for part in buf.value.decode().split(","):
+        part = part.strip()
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def pinToDevice(index: int = 0) -> bool:
+    """Runs the calling process' threads on the CPUs close to device `index` (threads created later inherit it)."""
+    cpus = deviceLocalCpus(index)
+    if not cpus:
+        return False
+    try:
+        os.sched_setaffinity(0, set(cpus) & os.sched_getaffinity(0) or set(cpus))
+        return True
+    except OSError:
+        return False
+
+
 def shutdown() -> None:
     global _initialised
     if _lib is not None:

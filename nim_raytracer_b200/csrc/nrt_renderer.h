@@ -767,6 +767,7 @@ struct Renderer {
   // take turns (1/8 frame: 3.56 -> 3.39 ms with one lane, nothing on top of three lanes; whole frame: 19.8 -> 20.4 ms)
   int64_t forkMin = 0;
   struct SubResult { int rc = 0; bool overflow = false; std::string err; unsigned long long stats[ST_COUNT] = {0}; ProfileAcc pacc; int64_t n = 0; };
+  bool wantBandCounts = false;      // set by the owner when the next frame's lane plan will read bandHard
   std::vector<uint32_t> bandHard;   // per row unit of the last frame: samples on the bounce-0 wavefront list (fused path; else empty)
   // NRT_PATH: 0 = the wavefront for every bounce (round-1 pipeline), 1 = FusedBounce + wavefront for the samples
   // with mesh rays at bounce 0 + PathTail (default), 2 = PathMega (one thread per sample start to end)
@@ -1153,7 +1154,7 @@ struct Renderer {
         const int64_t nS = npix * fp.spp;
         cs.p0 = p0; cs.npix = npix;
         const int64_t ncnt = int64_t(waves) * std::max(nMO, 1) * cntStride(nL);
-        const int64_t nband = (pathMode == 1 && nMO > 0) ? int64_t(rows.size()) : 0;
+        const int64_t nband = (pathMode == 1 && nMO > 0 && wantBandCounts) ? int64_t(rows.size()) : 0;
         uint32_t* const dBand = cs.counters + ncnt;
         be->zero(cs.counters, sizeof(uint32_t) * (ncnt + (p0 == 0 ? nband : 0)));
         be->zero(cs.stats, sizeof(unsigned long long) * ST_COUNT);

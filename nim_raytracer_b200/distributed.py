@@ -30,21 +30,27 @@ from typing import List, Optional
 import numpy as np
 
 
+def unit_owner(unit, world: int):
+    """nrt_unit_owner (csrc/nrt.cu: unitOwner): the serpentine deal of units (bands / rendered scanlines) to ranks.
+    Works on ints and numpy arrays."""
+    r = unit % world
+    return np.where((unit // world) % 2 == 1, world - 1 - r, r) if isinstance(unit, np.ndarray) else (world - 1 - r if (unit // world) % 2 else r)
+
+
 def rows_of(rank: int, world: int, height: int, y0: int = 0, y1: Optional[int] = None, step: int = 1, band: int = 1) -> List[int]:
     """First rows of the units of [y0, y1) owned by `rank` (csrc/nrt.cu: rowsFor).  A unit is a rendered scanline
     of a progressive pass ((y - y0) mod step == 0; band == 1) or a band of `band` scanlines of a whole-resolution
     pass (step == 1; band = api.bandRows(opts): rows of T x T tiles).  Units are numbered from y0 and dealt out
-    round-robin, so a progressive pass with step >= world still uses every rank.  For whole frames in scanline
-    order (y0 = 0, step = band = 1) this is y mod world == rank."""
+    in the serpentine order of unit_owner, so a progressive pass with step >= world still uses every rank.  """
     y1 = height if y1 is None else y1
     unit = step * band
-    return [y for y in range(max(0, y0), min(y1, height)) if (y - y0) % unit == 0 and ((y - y0) // unit) % world == rank]
+    return [y for y in range(max(0, y0), min(y1, height)) if (y - y0) % unit == 0 and unit_owner((y - y0) // unit, world) == rank]
 
 
 def owned_rows(rank: int, world: int, height: int, band: int = 1) -> np.ndarray:
-    """Every scanline of a whole frame that `rank` renders: the bands rank, rank + world, ... of `band` rows."""
+    """Every scanline of a whole frame that `rank` renders: the bands of `band` rows that unit_owner gives it."""
     y = np.arange(height)
-    return y[(y // band) % world == rank]
+    return y[unit_owner(y // band, world) == rank]
 
 
 def merge_rows(dst: np.ndarray, src: np.ndarray, rank: int, world: int, band: int = 1) -> None:

@@ -106,3 +106,23 @@ def test_product_never_touches_the_oracle():
     assert not bad, bad
     syms = subprocess.run(["nm", "-D", "--defined-only", api.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle_" not in syms and "emu_" not in syms
+
+
+def test_unit_owner_matches_the_python_mirror():
+    # the serpentine deal of bands to partitions: the library's definition (nrt_unit_owner) and distributed.py's
+    import ctypes as C
+    import numpy as np
+    from nim_raytracer_b200 import api, distributed as D
+    L = api.lib()
+    L.nrt_unit_owner.argtypes = [C.c_longlong, C.c_int]
+    L.nrt_unit_owner.restype = C.c_int
+    for world in (1, 2, 3, 4, 8):
+        units = np.arange(0, 100)
+        mine = D.unit_owner(units, world)
+        for u in units:
+            assert L.nrt_unit_owner(int(u), world) == int(mine[u]) == D.unit_owner(int(u), world)
+        # every partition gets the same number of units per two rounds, at the same mean position
+        for r in range(world):
+            pos = [u % (2 * world) for u in range(2 * world) if D.unit_owner(u, world) == r]
+            assert len(pos) == 2 and sum(pos) == 2 * world - 1
+    assert L.nrt_unit_owner(-1, 4) == -1 and L.nrt_unit_owner(3, 0) == -1

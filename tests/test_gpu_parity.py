@@ -540,3 +540,32 @@ def test_light_space_shadow_grid_and_ray_bundles(oracle_mod):
     assert_parity(_grid_scene(), o, oracle_mod)
     assert_parity(scenes.stress(ntri=100, nspheres=2000, seed=11), api.Options(240, 135), oracle_mod)
     assert_parity(scenes.stress(ntri=500, nspheres=40, seed=5), api.Options(240, 135, antialias=api.Antialias(api.akGrid, 2)), oracle_mod)   # flat scan
+
+
+@pytest.mark.gpu
+def test_partitions_render_the_rows_the_python_mirror_says(oracle_mod):
+    # nrt_set_partition(k, n): the bands of partition k (nrt_unit_owner: serpentine deal) are rendered, every other row
+    # is left untouched; distributed.owned_rows names the same rows and the n pieces assemble to the oracle's frame
+    from nim_raytracer_b200 import distributed as D
+    sc = scenes.bunny_spheres(stride=8)
+    o = api.Options(256, 200, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=4)
+    rfb, rst, _ = oracle_mod.render(sc, o)
+    band = api.bandRows(o)
+    ds = api.DeviceScene(sc)
+    try:
+        for n in (2, 3, 8):
+            out = np.zeros_like(rfb.image())
+            for k in range(n):
+                api.setPartition(k, n)
+                fb = api.newFramebuf(o.width, o.height)
+                fb.data[:] = -1.0
+                api.renderFrame(ds, o, fb)
+                img = fb.image()
+                rows = D.owned_rows(k, n, o.height, band)
+                touched = np.where((img != -1.0).any(axis=(1, 2)))[0]
+                assert touched.tolist() == rows.tolist(), (n, k)
+                D.merge_rows(out, img, k, n, band=band)
+            assert (out == rfb.image()).all(), n
+    finally:
+        api.setPartition(0, 1)
+        ds.close()
