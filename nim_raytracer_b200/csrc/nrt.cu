@@ -1703,6 +1703,9 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
                     di, units.size(), nl, (long long)sum, nHeavy, nLight);
         }
       }
+      if (!planned && useFbk && std::getenv("NRT_TRACE_LANES"))
+        fprintf(stderr, "[lanes] dev %d: no plan (feedback key %s, rows %s, %zu bands)\n", di, f.key == bandKey ? "same" : "differs",
+                f.y == units ? "same" : "differ", units.size());
       if (!planned)
         for (size_t j = 0; j < units.size(); ++j) laneRows[size_t(di)][j % size_t(nlanes)].push_back(units[j]);
     }
@@ -1872,6 +1875,27 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
   for (int u = 0; u < nunits; ++u)
     if (rc[u] != NRT_OK) return fail(rc[u], errs[u]);
 
+  // The automatic path choice (nrt_renderer.h: meshShare) is a property of the device's share of the frame, not of a
+  // lane: with the heavy / light lane plan the heavy lane alone would cross the threshold, fall back to the wavefront
+  // for every bounce, deliver no band counts, lose the plan for the next frame, cross back ... (seen on five of eight
+  // ranks: 3.3 ms and 2.9 ms frames in turn).  Every lane gets the device-wide figure.
+  for (int di = 0; di < nd; ++di) {
+    PerDevice& pd = sc->dev[size_t(di)];
+    double wave0 = 0, act0 = 0, meshRays = 0, primary = 0;
+    bool anyFused = false, anyWave = false;
+    for (int ln = 0; ln < nlanes; ++ln) {
+      if (laneRows[size_t(di)][size_t(ln)].empty()) continue;
+      const Renderer<CudaBackend>& r = pd.rn[ln];
+      if (r.pathMode == 1) { anyFused = true; wave0 += double(r.prof.wavefront[0]); act0 += double(r.prof.active[0]); }
+      else if (r.pathMode == 0) { anyWave = true; meshRays += double(r.prof.mesh_rays); primary += double(st[size_t(di * nlanes + ln)][ST_PRIMARY]); }
+    }
+    double share = -1.0;
+    if (anyFused && !anyWave && act0 > 0) share = wave0 / act0;
+    else if (anyWave && !anyFused && primary > 0) share = std::min(1.0, meshRays / primary);
+    if (share >= 0.0)
+      for (int ln = 0; ln < kMaxLanes; ++ln) pd.rn[ln].meshShare = share;
+  }
+
   // the per-band counts of this frame, for the next one's lane plan
   for (int di = 0; di < nd; ++di) {
     PerDevice& pd = sc->dev[size_t(di)];
@@ -1891,7 +1915,14 @@ static int renderImpl(nrt_scene* sc, const nrt_options* o, int y0, int y1, int s
       }
     }
     if (ok) { f.key = bandKey; f.y = units; f.hard.swap(hard); }
-    else { f.key.clear(); f.y.clear(); f.hard.clear(); }
+    else {
+      if (useFbk && std::getenv("NRT_TRACE_LANES")) {
+        fprintf(stderr, "[lanes] dev %d: feedback dropped:", di);
+        for (int ln = 0; ln < nlanes; ++ln) fprintf(stderr, " lane %d rows %zu counts %zu", ln, laneRows[size_t(di)][size_t(ln)].size(), pd.rn[ln].bandHard.size());
+        fprintf(stderr, "\n");
+      }
+      f.key.clear(); f.y.clear(); f.hard.clear();
+    }
   }
 
   nrt_profile& p = sc->prof;
