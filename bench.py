@@ -9,8 +9,9 @@ A "step" is one whole frame of the workload (default: BASELINE config 4 — the 
 scene at 3840x2160, 16 spp, reflections to depth 8: the configuration BASELINE.json's target and
 scaling requirement are quoted on; `--workload config2` selects the 1920x1080 1-spp bunny frame
 used for the single-kernel roofline runs under profiles/).  The frame is
-strong-scaled: rank r of N renders the scanlines y mod N == r and every rank's
-final pixel-store kernel writes its rows into rank 0's device framebuffer over
+strong-scaled: the frame's bands (rows of T x T screen-space tiles, T scanlines high)
+are dealt out to the N ranks in serpentine order (nrt_unit_owner) and every rank's
+final pixel-store kernel writes its tiles into rank 0's device framebuffer over
 NVLink (CUDA IPC peer pointer); `value` = rays traced by all ranks / max-over-ranks
 device time.  `e2e` goes through the host-buffer C-ABI call (nrt_scene_update +
 nrt_render): scene host->device and framebuffer device->host inside the timed
@@ -474,7 +475,10 @@ def main():
         api.check(L.nrt_measure_fp32_peak(C.byref(peak), C.byref(clk)), "nrt_measure_fp32_peak")
         L.nrt_measure_fp64_peak.argtypes = [C.POINTER(C.c_double)]
         api.check(L.nrt_measure_fp64_peak(C.byref(peak64)), "nrt_measure_fp64_peak")
-        achieved = prof_acc["flops"] / max(prof_acc["mesh_ms"] * 1e-3, 1e-12) / 1e12
+        # --inproc: the library's profile sums tests / flops / samples over the process's devices while its times are one
+        # device's (the slowest): roofline figures are PER DEVICE, so the sums are divided by the device count
+        ndev = float(args.gpus) if args.inproc else 1.0
+        achieved = prof_acc["flops"] / ndev / max(prof_acc["mesh_ms"] * 1e-3, 1e-12) / 1e12
         intersection = {
             "bound": "fp32", "kernel": "k_mesh_prefilter", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
             "frac": achieved / peak.value if peak.value > 0 else None,
@@ -484,7 +488,7 @@ def main():
             "flops_per_test": prof_acc["flops"] / max(prof_acc["tests"], 1), "tests_per_step": prof_acc["tests"] / args.steps,
             "ref_tests_per_step": prof_acc["tests_ref"] / args.steps,
             "avg_launch_ms": prof_acc["mesh_ms"] / max(prof_acc["launches"], 1),
-            "gtests_per_s": prof_acc["tests"] / max(prof_acc["mesh_ms"] * 1e-3, 1e-12) / 1e9,
+            "gtests_per_s": prof_acc["tests"] / ndev / max(prof_acc["mesh_ms"] * 1e-3, 1e-12) / 1e9,
             "candidates_per_step": prof_acc["cand"] / args.steps, "pre_candidates_per_step": prof_acc["pre"] / args.steps,
             "mesh_rays_per_step": prof_acc["rays_mesh"] / args.steps,
             "note": "achieved = executed float32 flops of the prefilter launches (FFMA = 2) / their summed CUDA-event time (the lanes' "
@@ -492,10 +496,10 @@ def main():
                     "ref_tests = rays x all faces, what geom.nim:346 would evaluate (reported, never used for the fraction)",
         }
         ksum = sum(ms for ms, _ in ktimes.values()) or 1.0
-        samples = float(cs.num_primary_rays)   # primary samples this rank rendered in the last frame
+        samples = float(cs.num_primary_rays) / ndev   # primary samples this rank (--inproc: one device) rendered in the last frame
         hbm_peak = _hbm_peak()
         kprof = ds.profile()                   # of the kernel-timing frame (one lane)
-        wf0 = float(kprof.wavefront_samples[0])
+        wf0 = float(kprof.wavefront_samples[0]) / ndev
         kernels = []
         frame_bytes = 0.0
         for name, (ms, nl) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
@@ -506,8 +510,8 @@ def main():
                 # samples of the family's LONGEST launch (bounce 0): every sample for FusedBounce / Finalize, the samples with a
                 # mesh ray for the wavefront kernels; all its launches: the active / wavefront samples of every bounce
                 n1 = wf0 if key in WAVEFRONT_FAMILIES else samples
-                nall = (sum(kprof.wavefront_samples) if key in WAVEFRONT_FAMILIES else
-                        sum(kprof.active_samples) if key == "FusedBounce" else samples)
+                nall = (sum(kprof.wavefront_samples) / ndev if key in WAVEFRONT_FAMILIES else
+                        sum(kprof.active_samples) / ndev if key == "FusedBounce" else samples)
                 lms = k["longest_launch_ms"] or ms
                 gbs = bps * n1 / max(lms * 1e-3, 1e-12) / 1e9
                 k.update({"bound": "hbm", "algorithmic_bytes_longest_launch": bps * n1, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
@@ -520,11 +524,13 @@ def main():
         if pre_ms > 0 and kprof.mesh_filter_ms > 0:
             # the kernel ALONE (the single-lane kernel-timing frame: nothing else in flight) is the roofline figure — in the timed
             # frames the lanes' launches overlap each other and other kernels, so their summed event time counts shared time twice
-            alone = kprof.fp32_flops / (kprof.mesh_filter_ms * 1e-3) / 1e12
+            alone = kprof.fp32_flops / ndev / (kprof.mesh_filter_ms * 1e-3) / 1e12
             intersection.update({"achieved_overlapped_sum": intersection["achieved"], "achieved": alone,
                                  "frac": alone / peak.value if peak.value > 0 else None, "frac_of_nominal": alone / NOMINAL_FP32_TFLOPS,
                                  "avg_launch_ms": kprof.mesh_filter_ms / max(kprof.mesh_filter_launches, 1),
-                                 "gtests_per_s": kprof.mesh_tests / (kprof.mesh_filter_ms * 1e-3) / 1e9})
+                                 "gtests_per_s": kprof.mesh_tests / ndev / (kprof.mesh_filter_ms * 1e-3) / 1e9})
+            if ndev > 1:
+                intersection["per_device"] = "tests and flops of the process's devices / device count (times are the slowest device's)"
         # `roofline` = the dominant kernel family of the step by measured share; per LAUNCH (its longest = bounce-0 launch)
         dom = kernels[0]
         if dom["kernel"].startswith("k_mesh_prefilter"):
@@ -566,7 +572,7 @@ def main():
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 (reference order) behind f32 first looks", "data": "synthetic",
             "config": {"workload": desc,
-                       "parallelism": (f"bands of {band} scanlines (rows of {band}x{band} screen-space tiles) dealt out round-robin x"
+                       "parallelism": (f"bands of {band} scanlines (rows of {band}x{band} screen-space tiles) dealt out in serpentine order x"
                                        f"{args.gpus if args.inproc else world} GPUs, up to 4 concurrent lanes per GPU; "
                                        + ("one process, peer stores into device 0" if args.inproc else
                                           ("CUDA-IPC peer stores" if peer is not None else "NCCL row gather") + " to rank 0")),

@@ -215,6 +215,7 @@ struct ShadowGridF {
 struct BundleFrame;  // nrt_filter.h
 struct RecSet;       // nrt_filter.h
 
+static constexpr int kHotLights = 2, kHotMO = 1;
 struct DScene {
   int32_t nobjects, nlights, nmeshes, nmesh_objs;
   const DObject* objects;
@@ -242,7 +243,18 @@ struct DScene {
   double cam_orig[4];             // c2w * (0,0,0,1): castPrimaryRay's origin (renderer.nim:42), the same product done once on the host
   double tan_half_fov;            // f of renderer.nim:38 (host libm, shared with nothing else)
   double bg[3];
+  // Hot copies of the small tables, for the kernels that carry this header BY VALUE (FusedBounceT: kernel-parameter
+  // space, so a light, a grid header or a gate record is a uniform constant load instead of a dependent chain of
+  // global loads).  hotOk != 0 only in the host's by-value copy (SceneData::h) and only when the tables fit
+  // (nlights <= kHotLights, nmesh_objs <= kHotMO); the device-resident header keeps 0 and reads the tables.
+  int32_t hotOk, moIndexv[kHotMO];
+  DLight lightv[kHotLights];
+  ShadowGridF sgridv[kHotLights + 1];
+  MeshGateF mgatev[kHotMO];
 };
+// a light / a grid header / a float32 gate record of the scene, from the hot copies when the header has them
+NRT_HD DLight lightOf(const DScene& sc, int l) { if (sc.hotOk) return sc.lightv[l]; return sc.lights[l]; }
+NRT_HD ShadowGridF sgridOf(const DScene& sc, int i) { if (sc.hotOk) return sc.sgridv[i]; return sc.sgrid[i]; }
 
 // ----------------------------------------------------------------------- Ray --
 struct Ray {            // geom.nim:32-39 (depth/x/y omitted: never read)

@@ -767,7 +767,7 @@ static constexpr int kPrimaryRay = -2;
 NRT_HD RayPre makeRayPreGrid(const DScene& sc, V4 o, V4 d, int sl) {
   RayPre p = makeRayPre(o, d);
   if (sc.maskGrids && sc.sgrid && p.f32ok && (sl >= 0 || sl == kPrimaryRay)) {
-    const ShadowGridF g = sc.sgrid[sl >= 0 ? sl : sc.nlights];
+    const ShadowGridF g = sgridOf(sc, sl >= 0 ? sl : sc.nlights);
     uint32_t m = 0, e = 0;
     if (g.G > 0 && shadowGridCell(g, p.rf, m, e)) { p.gridOk = true; p.gridMask = m | sc.slowMask; }
   }
@@ -778,7 +778,7 @@ NRT_HD RayPre makeRayPreGrid(const DScene& sc, V4 o, V4 d, int sl) {
 NRT_HD RayPre makeRayPrePrimary(const DScene& sc, V4 o, V4 d, double cx, double cy) {
   RayPre p = makeRayPre(o, d);
   if (sc.maskGrids && sc.sgrid && p.f32ok) {
-    const ShadowGridF g = sc.sgrid[sc.nlights];
+    const ShadowGridF g = sgridOf(sc, sc.nlights);
     if (g.G > 0 && g.persp) {
       const float f1 = (float(cx) - g.lo1) * g.invh, f2 = (float(cy) - g.lo2) * g.invh;
       if (f1 >= 0.f && f2 >= 0.f && f1 < float(g.G) && f2 < float(g.G)) {
@@ -794,6 +794,12 @@ NRT_HD RayPre makeRayPrePrimary(const DScene& sc, V4 o, V4 d, double cx, double 
 }
 // the AABB gate of mesh object mo for a world-space ray: float32 first look, then the reference's evaluation
 NRT_HD bool meshGatePassPre(const DScene& sc, int mo, V4 o, V4 d, const RayPre& pre) {
+  if (sc.hotOk) {   // (the header's own copies: mo < kHotMO)
+    if (pre.gridOk && !((pre.gridMask >> (uint32_t(sc.moIndexv[mo]) & 31u)) & 1u)) return false;
+    const MeshGateF gh = sc.mgatev[mo];
+    if (pre.f32ok && gh.valid > 0.f && meshGateMissF(gh, pre.rf)) return false;
+    return meshGatePass(sc, mo, o, d);
+  }
   if (pre.gridOk && !((pre.gridMask >> (uint32_t(sc.mesh_obj_index[mo]) & 31u)) & 1u)) return false;   // the ray's line misses the box's bounding sphere
 #if defined(__CUDA_ARCH__)
   const float4 g0 = __ldg(reinterpret_cast<const float4*>(sc.mgate + mo)), g1 = __ldg(reinterpret_cast<const float4*>(sc.mgate + mo) + 1);
@@ -820,7 +826,7 @@ NRT_HD TraceOut traceObjectsPre(const DScene& sc, const MP& mp, V4 o, V4 d, doub
   const RayF rf = pre.rf;
   if (CL && sc.ncl1 > 0 && (sl >= 0 || sl == kPrimaryRay) && sc.sgrid && f32ok) {
     // a DistantLight's shadow ray / a primary ray: the clustered spheres it can hit are listed in ONE cell of the grid
-    const ShadowGridF g = sc.sgrid[sl >= 0 ? sl : sc.nlights];
+    const ShadowGridF g = sgridOf(sc, sl >= 0 ? sl : sc.nlights);
     uint32_t gb = 0, ge = 0;
     if (g.G > 0 && shadowGridCell(g, rf, gb, ge) && ge - gb + uint32_t(sc.nslow) <= uint32_t(kSurvivorCap)) {
       uint32_t surv[kSurvivorCap] = {0};
@@ -1308,14 +1314,30 @@ NRT_HD V4 hitNormal(const DScene& sc, const DObject& ob, const TraceOut& tr, V4 
 // kFlagContinues = bounce 0 done here, the reflection ray is stored.  After the wavefront's bounce 0 every
 // nonzero flag is a sample whose path continues (Resolve writes 0 / 1 for its samples).
 static constexpr uint8_t kFlagWavefront = 1, kFlagContinues = 2;
+#ifndef NRT_FB_SCENE_BYVAL
+#define NRT_FB_SCENE_BYVAL 1
+#endif
+#if NRT_FB_SCENE_BYVAL
+#define NRT_FB_SCENE_T DScene
+#define NRT_FB_SCENE_PTR(x) (&(x))
+#define NRT_FB_SCENE_ARG(sd) (sd).h
+#else
+#define NRT_FB_SCENE_T const DScene*
+#define NRT_FB_SCENE_PTR(x) (x)
+#define NRT_FB_SCENE_ARG(sd) (sd).d
+#endif
 template <bool CL>
 struct FusedBounceT {
-  const DScene* sc; FrameParams fp; ChunkState cs; int force_exact;
+  // The scene header travels BY VALUE (kernel-parameter space = constant bank): camera matrix and origin, tan(fov/2),
+  // background, the table pointers and counts are operands or uniform constant loads instead of ~30 generic 64-bit loads
+  // per sample through a pointer (r02 ncu: 47 LD + 46 LDG per sample, long-scoreboard the top stall of this kernel).
+  NRT_FB_SCENE_T scn; FrameParams fp; ChunkState cs; int force_exact;
   int genFromState;   // bounce 0: the primary rays are in cs.rayD / cs.active already (jittered kinds: GenJittered)
   ActiveSet act;      // the samples of this bounce (bounce 0: every sample of the chunk)
   int bounce;
   NRT_HD void prefetch(int64_t) const {}
   NRT_HD StatDelta operator()(int64_t idx) const {
+    const DScene* const sc = NRT_FB_SCENE_PTR(scn);
     StatDelta st = zeroStats();
     const int64_t s = sampleOf(act, idx);
     V4 o, d;
@@ -1357,7 +1379,7 @@ struct FusedBounceT {
       // float32 image and grid cell (RayPre) serve the gate and the object scan alike.
       V3 local = v3(0.0, 0.0, 0.0);
       for (int l = 0; l < nL; ++l) {
-        const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
+        const ShadingInfo li = getShadingInfo(lightOf(*sc, l), hitW);
         const V4 sdir = scale(li.lightDir, -1.0);                                    // renderer.nim:99
         const RayPre sp = makeRayPreGrid(*sc, so, sdir, l);
         for (int mo = 0; mo < nMO; ++mo)

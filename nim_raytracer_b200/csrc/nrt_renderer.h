@@ -92,6 +92,8 @@ struct SceneData {
   RecSet* dRecSets = nullptr;             // device table of the record sets, indexed like the frames (DScene.recsets)
   MeshGateF* dMGate = nullptr;            // float32 gate records per mesh object (DScene.mgate)
   std::vector<MeshGateF> hMGate;          // host copy (mask grids bin the boxes' bounding spheres)
+  std::vector<ShadowGridF> hSGrid;        // host copy of the grid headers (DScene::sgridv)
+  static bool envHot() { const char* e = std::getenv("NRT_HOT_HEADER"); return !(e && *e == '0'); }
   bool anyGeneralShadow = false;          // some shadow rays need the GENERAL bundle (point light / unusable frame)
   std::vector<MoRecs> moRecs;
   uint32_t* dRecCount = nullptr;          // [mo * recStride() + j]: j = 0 GENERAL, 1 ORIGIN, 2 + l DIR(l)
@@ -292,6 +294,7 @@ struct SceneData {
     dSGrid = nullptr;
     h.sgrid = nullptr;
     h.maskGrids = 0; h.slowMask = 0;
+    hSGrid.clear();
     // list grids for clustered scenes, mask grids for scenes of at most 32 objects, nothing in between (flat scan)
     const bool masks = h.ncl1 <= 0 && cobjf.size() <= 32;
     if (h.ncl1 <= 0 && !masks) return;
@@ -441,6 +444,7 @@ struct SceneData {
     be->sync();
     h.sgrid = dSGrid;
     h.maskGrids = masks ? 1 : 0;
+    hSGrid = grids;
   }
 
   // Validates and flattens `desc`; with `reuse` the existing device buffers are refilled.
@@ -669,7 +673,16 @@ struct SceneData {
     h.tan_half_fov = std::tan((desc->fov * (kPi / 180.0)) / 2);  // renderer.nim:38; Nim degToRad = d * (PI/180)
     std::memcpy(h.bg, desc->bg_color, sizeof(h.bg));
     buildShadowGrids(desc);   // (sets h.sgrid; needs h.cam_orig / h.tan_half_fov)
+    h.hotOk = 0;
     d = up(&h, 1, reuse ? d : nullptr);
+    // the by-value copy of the header (FusedBounceT) carries the small tables itself (nrt_core.h: DScene::hotOk)
+    if (int(lights.size()) <= kHotLights && int(moIndex.size()) <= kHotMO && hMGate.size() >= moIndex.size() &&
+        (h.sgrid == nullptr || hSGrid.size() == lights.size() + 1) && envHot()) {
+      for (size_t l = 0; l < lights.size(); ++l) h.lightv[l] = lights[l];
+      for (size_t g = 0; g < lights.size() + 1; ++g) h.sgridv[g] = (h.sgrid != nullptr) ? hSGrid[g] : ShadowGridF{};
+      for (size_t mo = 0; mo < moIndex.size(); ++mo) { h.mgatev[mo] = hMGate[mo]; h.moIndexv[mo] = moIndex[mo]; }
+      h.hotOk = 1;
+    }
     // ---- filter records: GENERAL per mesh; ORIGIN / DIR per mesh object (device-side build) ----
     for (auto& m : meshes)
       if (m.nfaces > 0) be->sortFaces(m);   // fills m.order (Morton order of the face centroids)
@@ -940,8 +953,8 @@ struct Renderer {
       if (bounce > bounce0 && act.n < tailBelow) { pathTail(fc, act, bounce); pacc.tail += act.n; break; }   // a small wave: one launch to the end of its paths
       if (bounce < 8) pacc.active[bounce] += act.n;
       const int gfs = (bounce == 0 && fc.jitter) ? 1 : 0;
-      if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, FusedBounceClustered{sd.d, fp, cs, fc.force_exact, gfs, act, bounce}, cs.stats);
-      else be->forEachStats(nullptr, act.n, FusedBounce{sd.d, fp, cs, fc.force_exact, gfs, act, bounce}, cs.stats);
+      if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, FusedBounceClustered{NRT_FB_SCENE_ARG(sd), fp, cs, fc.force_exact, gfs, act, bounce}, cs.stats);
+      else be->forEachStats(nullptr, act.n, FusedBounce{NRT_FB_SCENE_ARG(sd), fp, cs, fc.force_exact, gfs, act, bounce}, cs.stats);
       bool forkedHere = false;
       uint32_t nh = 0;
       uint32_t* hardCount = cs.acount + 2 * bounce;
