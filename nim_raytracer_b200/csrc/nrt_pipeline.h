@@ -297,6 +297,31 @@ NRT_HD void initSample(const ChunkState& cs, int64_t s, bool alive, V4 d) {
   cs.active[s] = alive ? 1 : 0;
 }
 
+// How a kernel functor carries the scene header.  By value (the default): the header lives in kernel-parameter space
+// (constant bank), so the camera, the counts, the table pointers and — DScene::hotOk — the lights, grid headers and
+// gate records are uniform constant loads / operands instead of chains of dependent global loads through a pointer
+// (FusedBounce 9.44 -> 8.72 ms on BASELINE config 4).  `sc->x`, `*sc` and passing `sc` as a pointer read the same.
+#ifndef NRT_SCENE_BYVAL
+#define NRT_SCENE_BYVAL 1
+#endif
+#if NRT_SCENE_BYVAL
+struct SceneArg {
+  DScene v;
+  NRT_HD const DScene* operator->() const { return &v; }
+  NRT_HD const DScene& operator*() const { return v; }
+  NRT_HD operator const DScene*() const { return &v; }
+};
+#define NRT_SCENE_ARG(sd) (sd).h
+#else
+struct SceneArg {
+  const DScene* p;
+  NRT_HD const DScene* operator->() const { return p; }
+  NRT_HD const DScene& operator*() const { return *p; }
+  NRT_HD operator const DScene*() const { return p; }
+};
+#define NRT_SCENE_ARG(sd) (sd).d
+#endif
+
 // ---- gen: one element per SAMPLE (akNone / akGrid) ---------------------------
 struct GenOut { bool alive; V4 o, d; double cx, cy; };
 // sample position of grid sample (i, j) inside its pixel (sampling.nim:5-18) / the pixel corner for akNone (renderer.nim:135)
@@ -367,7 +392,7 @@ NRT_HD bool waveRay(const DScene& sc, const FrameParams& fp, const ChunkState& c
   const int l = int(i - s * cs.nL);
   if (cs.hitObj[s] < 0) return false;
   const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
-  const ShadingInfo si = getShadingInfo(sc.lights[l], hitW);
+  const ShadingInfo si = getShadingInfo(lightOf(sc, l), hitW);
   o = add(hitW, scale(n, fp.bias));
   d = scale(si.lightDir, -1.0);
   return true;
@@ -401,7 +426,7 @@ NRT_HD Ray objectRay(const DObject& ob, V4 o, V4 d) {  // renderer.nim:54-55
 // ---- gate: TriangleMesh.intersect's AABB test (geom.nim:340) per (ray, mesh object)
 struct GateOut { bool pass, safe; int bundle; uint32_t wi; FilterRay fr; HotRay hr; };
 struct Gate {
-  const DScene* sc; FrameParams fp; ChunkState cs; int kind; ActiveSet act; int force_exact;
+  SceneArg sc; FrameParams fp; ChunkState cs; int kind; ActiveSet act; int force_exact;
   int path_mode;   // FM_ORIGIN for the primary wave (all rays share the camera origin), else FM_GENERAL
   int bounce;      // host loop's bounce number of the wave
   // wave-ray index (the slot of the ray's mesh results) of wave position idx < wave size
@@ -448,7 +473,7 @@ struct Gate {
       int mode = path_mode, l = 0;
       if (kind == WAVE_SHADOW) {
         l = lsh;
-        mode = (sc->lights[l].kind == LIGHT_DISTANT) ? FM_DIR : FM_GENERAL;
+        mode = (lightOf(*sc, l).kind == LIGHT_DISTANT) ? FM_DIR : FM_GENERAL;
       }
       if (mode != FM_GENERAL && !(sc->frames[frameIndex(sc->nlights, mo, mode, l)].valid > 0)) mode = FM_GENERAL;
       g.bundle = (mode == FM_DIR) ? 1 + l : 0;
@@ -463,7 +488,7 @@ NRT_HD uint8_t gateCode(const GateOut& o) { return o.pass ? (o.safe ? uint8_t(1 
 
 // ---- exact: float64 brute force over ALL faces for rays the filter cannot take
 struct ExactMesh {
-  const DScene* sc; FrameParams fp; ChunkState cs; int kind; int mo; const uint32_t* count; int bounce;
+  SceneArg sc; FrameParams fp; ChunkState cs; int kind; int mo; const uint32_t* count; int bounce;
   NRT_HD void operator()(int64_t qi) const {
     const uint32_t ref = cs.xref[int64_t(mo) * cs.NR + qi];
     V4 o, d;
@@ -516,7 +541,7 @@ struct Refine {
 // atomics supplied by the backend
 template <class A>
 struct Verify1 {  // float64 re-evaluation of candidate c; running minimum of t per ray
-  const DScene* sc; FrameParams fp; ChunkState cs; int kind; int mo; int bounce;
+  SceneArg sc; FrameParams fp; ChunkState cs; int kind; int mo; int bounce;
   NRT_HD void operator()(int64_t c) const {
     const uint32_t ref = cs.candRef[c], tri = cs.candTri[c];
     V4 o, d;
@@ -977,7 +1002,7 @@ NRT_HD StatDelta zeroStats() { StatDelta s; for (int i = 0; i < ST_COUNT; ++i) s
 struct ShadeOut { bool hit; int64_t s; V4 hitW, n; };
 template <bool CL>
 struct ShadeT {
-  const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce;
+  SceneArg sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce;
   NRT_HD StatDelta operator()(int64_t idx) const { ShadeOut out; return run(idx, out); }
   NRT_HD void prefetch(int64_t idx) const {   // inputs of wave position idx (identity active set only)
     if (act.list) return;
@@ -1082,7 +1107,7 @@ struct ShadowGate {   // gate.kind == WAVE_SHADOW, mult == nL
     if (hit) o = add(hitW, scale(nrm, gate.fp.bias));   // renderer.nim:98
     for (int l = 0; l < cs.nL; ++l) {
       V4 d = o;
-      if (hit) d = scale(getShadingInfo(gate.sc->lights[l], hitW).lightDir, -1.0);   // renderer.nim:99
+      if (hit) d = scale(getShadingInfo(lightOf(*gate.sc, l), hitW).lightDir, -1.0);   // renderer.nim:99
       for (int mo = 0; mo < nMO; ++mo)
         emit(l, mo, hit ? gateCode(gate.evalRay(o, d, uint32_t(s * cs.nL + l), mo, l)) : uint8_t(0));
     }
@@ -1092,7 +1117,7 @@ struct ShadowGate {   // gate.kind == WAVE_SHADOW, mult == nL
 // ---- shadow trace: one element per shadow ray (active sample i / nL, light i % nL): the trace()
 // call of renderer.nim:101-102; only "some object hit before the light" is kept (renderer.nim:103)
 struct ShadowTrace {
-  const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
+  SceneArg sc; FrameParams fp; ChunkState cs; ActiveSet act;
   NRT_HD void prefetch(int64_t) const {}
   NRT_HD StatDelta operator()(int64_t idx) const {
     StatDelta st = zeroStats();
@@ -1102,7 +1127,7 @@ struct ShadowTrace {
     const int64_t s = sampleOf(act, si);
     if (cs.hitObj[s] < 0) return st;
     const V4 hitW = ld4(cs.hitW, cs.S, s), n = ld4(cs.nrm, cs.S, s);
-    const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
+    const ShadingInfo li = getShadingInfo(lightOf(*sc, l), hitW);
     const V4 so = add(hitW, scale(n, fp.bias)), sd = scale(li.lightDir, -1.0);   // renderer.nim:98-99
     const TraceOut tr = traceObjects<false>(*sc, WaveMesh{cs, s * cs.nL + l, idx, (cs.nMO > 0) ? cs.gflag[idx] : uint8_t(0)}, so, sd, li.lightDistance);
     st.v[ST_RAYS] = 1; st.v[ST_TESTS] = tr.tests; st.v[ST_HITS] = tr.hits;
@@ -1114,7 +1139,7 @@ struct ShadowTrace {
 // The same per ACTIVE SAMPLE: its nL shadow rays share the loads of the hit record and the origin.
 template <bool CL>
 struct ShadowTraceSampleT {
-  const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act;
+  SceneArg sc; FrameParams fp; ChunkState cs; ActiveSet act;
   NRT_HD void prefetch(int64_t idx) const {   // the hit record and gate codes of wave position idx (identity active set only)
     if (act.list) return;
     pf4(cs.hitW, cs.S, idx); pf4(cs.nrm, cs.S, idx);
@@ -1136,7 +1161,7 @@ struct ShadowTraceSampleT {
     if (ho < 0) return st;
     const V4 so = add(hitW, scale(n, fp.bias));                                   // renderer.nim:98
     for (int l = 0; l < cs.nL; ++l) {
-      const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
+      const ShadingInfo li = getShadingInfo(lightOf(*sc, l), hitW);
       const V4 sd = scale(li.lightDir, -1.0);                                      // renderer.nim:99
       const uint8_t code0 = (l < 4) ? uint8_t(codes >> (8 * l)) : ((cs.nMO > 0) ? cs.gflag[idx * cs.nL + l] : uint8_t(0));
       const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s * cs.nL + l, idx * cs.nL + l, code0}, so, sd, li.lightDistance, l);
@@ -1164,7 +1189,7 @@ NRT_HD void resolveSample(const DScene* sc, const FrameParams& fp, const ChunkSt
   V3 local = v3(0.0, 0.0, 0.0);
   for (int l = 0; l < cs.nL; ++l) {
     if (occluded(l)) continue;
-    const ShadingInfo si = getShadingInfo(sc->lights[l], hitW);
+    const ShadingInfo si = getShadingInfo(lightOf(*sc, l), hitW);
     local = add(local, shadeDiffuse(ob, si, n));
   }
   const double k = ob.reflection, w = (bounce == 0) ? 1.0 : cs.weight[s];
@@ -1199,7 +1224,7 @@ NRT_HD void resolveSample(const DScene* sc, const FrameParams& fp, const ChunkSt
 }
 
 struct Resolve {
-  const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce;
+  SceneArg sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce;
   int pointLights;   // some light is a PointLight: getShadingInfo needs the hit point (a DistantLight ignores it)
   NRT_HD void prefetch(int64_t) const {}
   NRT_HD StatDelta operator()(int64_t idx) const {
@@ -1229,7 +1254,7 @@ struct Resolve {
 // Per sample of HBM traffic this drops Resolve's 38 bytes of reads and the 2 flag bytes written.
 template <bool CL>
 struct ShadowResolveT {
-  const DScene* sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce; int pointLights;
+  SceneArg sc; FrameParams fp; ChunkState cs; ActiveSet act; int bounce; int pointLights;
   NRT_HD void prefetch(int64_t idx) const {   // the hit record and gate codes of wave position idx (identity active set only)
     if (act.list) return;
     pf4(cs.hitW, cs.S, idx); pf4(cs.nrm, cs.S, idx);
@@ -1253,7 +1278,7 @@ struct ShadowResolveT {
       if (ho < 0) return st;
       const V4 so = add(hitW, scale(n, fp.bias));                                   // renderer.nim:98
       for (int l = 0; l < cs.nL; ++l) {
-        const ShadingInfo li = getShadingInfo(sc->lights[l], hitW);
+        const ShadingInfo li = getShadingInfo(lightOf(*sc, l), hitW);
         const V4 sd = scale(li.lightDir, -1.0);                                      // renderer.nim:99
         const uint8_t code0 = (l < 4) ? uint8_t(codes >> (8 * l)) : ((cs.nMO > 0) ? cs.gflag[idx * cs.nL + l] : uint8_t(0));
         const TraceOut tr = traceObjects<CL>(*sc, WaveMesh{cs, s * cs.nL + l, idx * cs.nL + l, code0}, so, sd, li.lightDistance, l);
@@ -1314,30 +1339,17 @@ NRT_HD V4 hitNormal(const DScene& sc, const DObject& ob, const TraceOut& tr, V4 
 // kFlagContinues = bounce 0 done here, the reflection ray is stored.  After the wavefront's bounce 0 every
 // nonzero flag is a sample whose path continues (Resolve writes 0 / 1 for its samples).
 static constexpr uint8_t kFlagWavefront = 1, kFlagContinues = 2;
-#ifndef NRT_FB_SCENE_BYVAL
-#define NRT_FB_SCENE_BYVAL 1
-#endif
-#if NRT_FB_SCENE_BYVAL
-#define NRT_FB_SCENE_T DScene
-#define NRT_FB_SCENE_PTR(x) (&(x))
-#define NRT_FB_SCENE_ARG(sd) (sd).h
-#else
-#define NRT_FB_SCENE_T const DScene*
-#define NRT_FB_SCENE_PTR(x) (x)
-#define NRT_FB_SCENE_ARG(sd) (sd).d
-#endif
 template <bool CL>
 struct FusedBounceT {
   // The scene header travels BY VALUE (kernel-parameter space = constant bank): camera matrix and origin, tan(fov/2),
   // background, the table pointers and counts are operands or uniform constant loads instead of ~30 generic 64-bit loads
   // per sample through a pointer (r02 ncu: 47 LD + 46 LDG per sample, long-scoreboard the top stall of this kernel).
-  NRT_FB_SCENE_T scn; FrameParams fp; ChunkState cs; int force_exact;
+  SceneArg sc; FrameParams fp; ChunkState cs; int force_exact;
   int genFromState;   // bounce 0: the primary rays are in cs.rayD / cs.active already (jittered kinds: GenJittered)
   ActiveSet act;      // the samples of this bounce (bounce 0: every sample of the chunk)
   int bounce;
   NRT_HD void prefetch(int64_t) const {}
   NRT_HD StatDelta operator()(int64_t idx) const {
-    const DScene* const sc = NRT_FB_SCENE_PTR(scn);
     StatDelta st = zeroStats();
     const int64_t s = sampleOf(act, idx);
     V4 o, d;
@@ -1444,7 +1456,7 @@ struct ScalarCoop {
 
 template <bool CL, int KIND>   // KIND: PATH_TAIL (the samples of the tail list, from bounce 1) or PATH_MEGA (every sample, from its primary ray)
 struct PathWarpT {
-  const DScene* sc; FrameParams fp; ChunkState cs; int force_exact;
+  SceneArg sc; FrameParams fp; ChunkState cs; int force_exact;
   int genFromState;
   ActiveSet act;     // PATH_TAIL: the samples to finish (list + count on the device)
   int bounce0;       // PATH_TAIL: the bounce their stored rays belong to
@@ -1504,9 +1516,9 @@ struct PathWarpT {
       V3 local = v3(0.0, 0.0, 0.0);
       for (int l = 0; l < nL; ++l) {
         ShadingInfo li; li.lightDir = d; li.lightIntensity = v3(0.0, 0.0, 0.0); li.lightDistance = NRT_INF;
-        if (hit) li = getShadingInfo(sc->lights[l], hitW);
+        if (hit) li = getShadingInfo(lightOf(*sc, l), hitW);
         const V4 sdir = scale(li.lightDir, -1.0);                                    // renderer.nim:99
-        const int smode = sc->lights[l].kind == LIGHT_DISTANT ? FM_DIR : FM_GENERAL;
+        const int smode = lightOf(*sc, l).kind == LIGHT_DISTANT ? FM_DIR : FM_GENERAL;
         coop.meshAll(*sc, hit, smode, l, so, sdir, force_exact, mr);
         if (hit) {
           const TraceOut ts = traceObjects<CL>(*sc, PreMesh{mr, WalkMesh{sc, smode, l, force_exact}}, so, sdir, li.lightDistance, l);

@@ -849,7 +849,7 @@ struct Renderer {
   }
 
   Gate makeGate(const SceneData<BE>& sd, const FrameParams& fp, int kind, const ActiveSet& act, int bounce, int force_exact) const {
-    return Gate{sd.d, fp, cs, kind, act, force_exact, (bounce == 0 && kind == WAVE_PATH) ? FM_ORIGIN : FM_GENERAL, bounce};
+    return Gate{NRT_SCENE_ARG(sd), fp, cs, kind, act, force_exact, (bounce == 0 && kind == WAVE_PATH) ? FM_ORIGIN : FM_GENERAL, bounce};
   }
   uint32_t* waveCounters(int wave) const { return cs.counters + int64_t(wave) * cs.nMO * cntStride(cs.nL); }
 
@@ -891,8 +891,8 @@ struct Renderer {
         }
       }
       // (one launch: the float64 brute-force queue is empty on every scene seen so far)
-      be->forEachCounted2(c + CNT_EXACT, cs.NR, ExactMesh{sd.d, fp, cs, kind, mo, c + CNT_EXACT, bounce},
-                          c + CNT_CAND, cs.candCap, Verify1<typename BE::Atom>{sd.d, fp, cs, kind, mo, bounce});
+      be->forEachCounted2(c + CNT_EXACT, cs.NR, ExactMesh{NRT_SCENE_ARG(sd), fp, cs, kind, mo, c + CNT_EXACT, bounce},
+                          c + CNT_CAND, cs.candCap, Verify1<typename BE::Atom>{NRT_SCENE_ARG(sd), fp, cs, kind, mo, bounce});
       be->forEachCounted(c + CNT_CAND, cs.candCap, Verify2<typename BE::Atom>{cs, mo});
     }
   }
@@ -901,15 +901,15 @@ struct Renderer {
   void shadowAndResolve(const SceneData<BE>& sd, const FrameParams& fp, const ActiveSet& act, int bounce) {
     const int nL = cs.nL, pl = sd.anyPointLight ? 1 : 0;
     if (nL > 0 && nL <= 32 && fuseResolve && (sd.h.ncl1 > 0 || shadowTracePerSample)) {
-      if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowResolveClustered{sd.d, fp, cs, act, bounce, pl}, cs.stats);
-      else be->forEachStats(nullptr, act.n, ShadowResolve{sd.d, fp, cs, act, bounce, pl}, cs.stats);
+      if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowResolveClustered{NRT_SCENE_ARG(sd), fp, cs, act, bounce, pl}, cs.stats);
+      else be->forEachStats(nullptr, act.n, ShadowResolve{NRT_SCENE_ARG(sd), fp, cs, act, bounce, pl}, cs.stats);
     } else {
       if (nL > 0) {
-        if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowTraceSampleClustered{sd.d, fp, cs, act}, cs.stats);
-        else if (shadowTracePerSample) be->forEachStats(nullptr, act.n, ShadowTraceSample{sd.d, fp, cs, act}, cs.stats);
-        else be->forEachStats(nullptr, act.n * nL, ShadowTrace{sd.d, fp, cs, act}, cs.stats);
+        if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, ShadowTraceSampleClustered{NRT_SCENE_ARG(sd), fp, cs, act}, cs.stats);
+        else if (shadowTracePerSample) be->forEachStats(nullptr, act.n, ShadowTraceSample{NRT_SCENE_ARG(sd), fp, cs, act}, cs.stats);
+        else be->forEachStats(nullptr, act.n * nL, ShadowTrace{NRT_SCENE_ARG(sd), fp, cs, act}, cs.stats);
       }
-      be->forEachStats(nullptr, act.n, Resolve{sd.d, fp, cs, act, bounce, pl}, cs.stats);
+      be->forEachStats(nullptr, act.n, Resolve{NRT_SCENE_ARG(sd), fp, cs, act, bounce, pl}, cs.stats);
     }
   }
 
@@ -929,16 +929,16 @@ struct Renderer {
   void wavefrontBounce(const FrameCtx& fc, const ActiveSet& set, int bounce, bool gated, int& wave) {
     const SceneData<BE>& sd = *fc.sd;
     meshWave(sd, fc.fp, WAVE_PATH, set, 2 * bounce, bounce, fc.force_exact, gated);
-    if (sd.h.ncl1 > 0) be->forEachStats(nullptr, set.n, ShadeClustered{sd.d, fc.fp, cs, set, bounce}, cs.stats);
-    else be->forEachStats(nullptr, set.n, Shade{sd.d, fc.fp, cs, set, bounce}, cs.stats);
+    if (sd.h.ncl1 > 0) be->forEachStats(nullptr, set.n, ShadeClustered{NRT_SCENE_ARG(sd), fc.fp, cs, set, bounce}, cs.stats);
+    else be->forEachStats(nullptr, set.n, Shade{NRT_SCENE_ARG(sd), fc.fp, cs, set, bounce}, cs.stats);
     if (cs.nL > 0) meshWave(sd, fc.fp, WAVE_SHADOW, set, 2 * bounce + 1, bounce, fc.force_exact, false);
     shadowAndResolve(sd, fc.fp, set, bounce);
     wave = std::max(wave, 2 * bounce + 2);
   }
   void pathTail(const FrameCtx& fc, const ActiveSet& set, int bounce) {
     const SceneData<BE>& sd = *fc.sd;
-    if (sd.h.ncl1 > 0) be->pathWarp(set.count, set.n, PathTailClustered{sd.d, fc.fp, cs, fc.force_exact, 0, set, bounce}, cs.stats);
-    else be->pathWarp(set.count, set.n, PathTail{sd.d, fc.fp, cs, fc.force_exact, 0, set, bounce}, cs.stats);
+    if (sd.h.ncl1 > 0) be->pathWarp(set.count, set.n, PathTailClustered{NRT_SCENE_ARG(sd), fc.fp, cs, fc.force_exact, 0, set, bounce}, cs.stats);
+    else be->pathWarp(set.count, set.n, PathTail{NRT_SCENE_ARG(sd), fc.fp, cs, fc.force_exact, 0, set, bounce}, cs.stats);
   }
 
   // The fused path from bounce `bounce0` to the end of every path of the pool `act`.  `fk` != null (the main
@@ -953,8 +953,8 @@ struct Renderer {
       if (bounce > bounce0 && act.n < tailBelow) { pathTail(fc, act, bounce); pacc.tail += act.n; break; }   // a small wave: one launch to the end of its paths
       if (bounce < 8) pacc.active[bounce] += act.n;
       const int gfs = (bounce == 0 && fc.jitter) ? 1 : 0;
-      if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, FusedBounceClustered{NRT_FB_SCENE_ARG(sd), fp, cs, fc.force_exact, gfs, act, bounce}, cs.stats);
-      else be->forEachStats(nullptr, act.n, FusedBounce{NRT_FB_SCENE_ARG(sd), fp, cs, fc.force_exact, gfs, act, bounce}, cs.stats);
+      if (sd.h.ncl1 > 0) be->forEachStats(nullptr, act.n, FusedBounceClustered{NRT_SCENE_ARG(sd), fp, cs, fc.force_exact, gfs, act, bounce}, cs.stats);
+      else be->forEachStats(nullptr, act.n, FusedBounce{NRT_SCENE_ARG(sd), fp, cs, fc.force_exact, gfs, act, bounce}, cs.stats);
       bool forkedHere = false;
       uint32_t nh = 0;
       uint32_t* hardCount = cs.acount + 2 * bounce;
@@ -1181,8 +1181,8 @@ struct Renderer {
         if (pathMode == 2) {
           // ---- PathMega: every sample start to end in one launch ----
           if (jitter) be->forEach(npix, GenJittered{sd.d, fp, cs});
-          if (sd.h.ncl1 > 0) be->pathWarp(nullptr, nS, PathMegaClustered{sd.d, fp, cs, force_exact, jitter ? 1 : 0, act, 0}, cs.stats);
-          else be->pathWarp(nullptr, nS, PathMega{sd.d, fp, cs, force_exact, jitter ? 1 : 0, act, 0}, cs.stats);
+          if (sd.h.ncl1 > 0) be->pathWarp(nullptr, nS, PathMegaClustered{NRT_SCENE_ARG(sd), fp, cs, force_exact, jitter ? 1 : 0, act, 0}, cs.stats);
+          else be->pathWarp(nullptr, nS, PathMega{NRT_SCENE_ARG(sd), fp, cs, force_exact, jitter ? 1 : 0, act, 0}, cs.stats);
         } else if (pathMode == 1) {
           // ---- fused path (nrt_pipeline.h: FusedBounceT, PathWarpT): per bounce, ONE kernel takes every active sample
           // through the whole bounce in registers unless one of its rays enters a mesh box; those samples (flag
