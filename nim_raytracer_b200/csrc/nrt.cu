@@ -1032,7 +1032,7 @@ enum KernelCat { KC_GEN = 0, KC_GATE_FLAGS, KC_GATE_SCAN, KC_GATE_WRITE, KC_PREF
                  KC_SHADE, KC_SHADOW_TRACE, KC_RESOLVE, KC_COMPACT, KC_FINALIZE, KC_OTHER, KC_SHADOW_RESOLVE, KC_FUSED_PRIMARY, KC_PATH_TAIL, KC_COUNT };
 static const char* const kKernelCatNames[KC_COUNT] = {
   "gen+gate (GenGate / GenSimple / GenJittered)", "k_gate_flags", "k_gate_scan", "k_gate_write", "k_mesh_prefilter", "Refine",
-  "ExactMesh", "Verify1+Verify2", "Shade", "ShadowTrace", "Resolve", "compactActive (cub select)", "Finalize", "other",
+  "ExactMesh", "Verify1+Verify2", "Shade", "ShadowTrace", "Resolve", "compactActive (ordered select)", "Finalize", "other",
   "ShadowResolve (ShadowTrace + Resolve)", "FusedBounce (a whole bounce of a sample in registers)", "PathTail / PathMega (per-thread paths + mesh walk)"};
 static_assert(KC_COUNT <= NRT_KERNEL_CATEGORIES, "nrt_kernel_times is too small");
 template <class F> struct CatOf { static constexpr int v = KC_OTHER; };
