@@ -327,17 +327,46 @@ inline Stats renderFrame(const DeviceScene& scene, const Options& opts, Framebuf
   return r;
 }
 
-// utils/framebuf.nim:55-93 (8-bit P6; clamp -> sRGB -> round on the GPU output stage)
-inline bool writePpm(const Framebuf& fb, const std::string& filename, int bits = 8, bool sRGB = true) {
-  if (bits != 8) return false;
-  std::vector<unsigned char> rgb(size_t(fb.w) * fb.h * 3);
-  if (nrt_framebuf_to_srgb8(fb.data.data(), fb.w, fb.h, sRGB ? 1 : 0, rgb.data()) != NRT_OK) return false;
+// utils/framebuf.nim:55-93: P6, maxval 2^bits - 1, 8-bit samples up to 8 bits, big-endian 16-bit samples above;
+// clamp -> linearToSRGB -> round on the GPU output stage (bit-exact: DESIGN.md section 13)
+inline bool writePpmSamples(const std::string& filename, int w, int h, int bits, const std::vector<unsigned char>& samples) {
   std::ofstream f(filename, std::ios::binary);
   if (!f) return false;
-  f << "P6 " << fb.w << " " << fb.h << " 255 ";
-  f.write(reinterpret_cast<const char*>(rgb.data()), std::streamsize(rgb.size()));
+  f << "P6 " << w << " " << h << " " << ((1 << bits) - 1) << " ";   // framebuf.nim:62-65
+  f.write(reinterpret_cast<const char*>(samples.data()), std::streamsize(samples.size()));
   return bool(f);
 }
+inline bool writePpm(const Framebuf& fb, const std::string& filename, int bits = 8, bool sRGB = true) {
+  if (bits < 1 || bits > 16) return false;   // framebuf.nim:56
+  std::vector<unsigned char> img(size_t(fb.w) * fb.h * (bits <= 8 ? 3 : 6));
+  if (nrt_framebuf_quantize(fb.data.data(), fb.w, fb.h, bits, sRGB ? 1 : 0, img.data()) != NRT_OK) return false;
+  return writePpmSamples(filename, fb.w, fb.h, bits, img);
+}
+
+// renderFrame followed by writePpm in ONE call (nrt_render_quantized): the conversion runs as the epilogue of the
+// kernel that stores the pixels and only the integer samples leave the GPU (3 or 6 bytes per pixel instead of 12).
+// `samples` receives the PPM sample stream (what writePpm would write after its header).
+inline Stats renderFrameQuantized(const DeviceScene& scene, const Options& opts, std::vector<unsigned char>& samples,
+                                  int bits = 8, bool sRGB = true) {
+  const nrt_options c = toC(opts);
+  nrt_stats st{};
+  samples.assign(size_t(opts.width) * opts.height * (bits <= 8 ? 3 : 6), 0);
+  check(nrt_render_quantized(scene.handle(), &c, 0, opts.height, 1, 1, NRT_OUT_RGB, bits, sRGB ? 1 : 0, 255, samples.data(), &st),
+        "nrt_render_quantized");
+  Stats r; r.numPrimaryRays = st.num_primary_rays; r.numIntersectionTests = st.num_intersection_tests; r.numIntersectionHits = st.num_intersection_hits;
+  return r;
+}
+
+// utils/image.nim:45-54 (ImageRGBA.copyFrom, the GUI's display copy): round(v * 255) per channel + a constant alpha
+inline bool toRGBA8(const Framebuf& fb, std::vector<unsigned char>& rgba, unsigned char alpha = 255) {
+  rgba.assign(size_t(fb.w) * fb.h * 4, 0);
+  return nrt_framebuf_to_rgba8(fb.data.data(), fb.w, fb.h, alpha, rgba.data()) == NRT_OK;
+}
+
+// Which partition of `count` renders unit (band / rendered scanline) `unit` of a pass: the serpentine deal of
+// raytracer.nim:67-70's work items to GPUs / processes (nrt_set_partition selects this process's share).
+inline int unitOwner(long long unit, int count) { return nrt_unit_owner(unit, count); }
+inline void shutdown() { nrt_shutdown(); }
 
 // ---- loaders: obj.nim:65-126 (v / f only, one flat normal per face) and the .geom format ----
 inline void calcNormals(TriangleMesh& m) {  // obj.nim:65-84

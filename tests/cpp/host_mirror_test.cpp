@@ -90,7 +90,19 @@ int main(int argc, char** argv) {
     std::ofstream raw(argv[2], std::ios::binary);
     raw.write(reinterpret_cast<const char*>(framebuf.data.data()), std::streamsize(framebuf.data.size() * sizeof(float)));
     if (!writePpm(framebuf, argv[3], 8, true)) { std::cerr << "writePpm failed\n"; return 6; }
-    nrt_shutdown();
+    {   // renderFrame + writePpm in one call: the same samples, 8-bit and big-endian 16-bit
+      for (int bits : {8, 16}) {
+        std::vector<unsigned char> fused, staged(size_t(opts.width) * opts.height * (bits <= 8 ? 3 : 6));
+        const Stats qs = renderFrameQuantized(ds, opts, fused, bits, true);
+        check(nrt_framebuf_quantize(framebuf.data.data(), opts.width, opts.height, bits, 1, staged.data()), "nrt_framebuf_quantize");
+        if (fused != staged) { std::cerr << "renderFrameQuantized != renderFrame + writePpm at " << bits << " bits\n"; return 7; }
+        if (qs.numPrimaryRays != frameStats.numPrimaryRays || qs.numIntersectionTests != frameStats.numIntersectionTests) { std::cerr << "quantized stats differ\n"; return 8; }
+      }
+      std::vector<unsigned char> rgba;
+      if (!toRGBA8(framebuf, rgba, 200) || rgba.size() != size_t(opts.width) * opts.height * 4 || rgba[3] != 200) { std::cerr << "toRGBA8 failed\n"; return 9; }
+      std::cout << "output stage: fused == staged (8, 16 bits), rgba8 ok\n";
+    }
+    shutdown();
   } catch (const Error& e) {
     std::cerr << "error " << e.code << ": " << e.what() << "\n";
     return 1;
