@@ -1356,7 +1356,8 @@ struct CudaBackend {
     use();
     Timed tm(this, KC_COMPACT);
     size_t tb = 0;
-    static const bool ownSelect = [] { const char* e = std::getenv("NRT_OWN_SELECT"); return !(e && *e == '0'); }();
+    const char* const ose = std::getenv("NRT_OWN_SELECT");   // (read per call: the tests switch it inside one process)
+    const bool ownSelect = !(ose && *ose == '0');
     if (!act.list && ownSelect && act.n >= (int64_t(1) << 20)) {
       // a whole chunk's flags: three small launches taking 16 flags per thread (see k_sel_count); the same list as cub's.
       // (List-based sets stay with cub: the gathered variant of the same kernels — `in` != null — measured slower,

@@ -226,3 +226,19 @@ def test_light_space_shadow_grid(oracle_mod):
     o = api.Options(96, 54, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=3)
     check(_grid_scene(), o, oracle_mod)
     check(scenes.stress(ntri=100, nspheres=2000, seed=11), api.Options(120, 68), oracle_mod)   # dense: long cell lists
+
+
+@pytest.mark.parametrize("hot", ["1", "0"])
+def test_scene_header_by_value_with_and_without_hot_copies(oracle_mod, monkeypatch, hot):
+    """The per-sample functors carry the scene header by value (nrt_pipeline.h: SceneArg); with DScene::hotOk the
+    lights, grid headers and mesh gate records are read from the header's own copies, otherwise (NRT_HOT_HEADER=0, or a
+    scene with more than two lights / more than one mesh object) from the device tables.  Same bits either way, on the
+    fused path and on the wavefront-only path."""
+    monkeypatch.setenv("NRT_HOT_HEADER", hot)
+    sc = scenes.bunny_spheres(stride=8)
+    o = api.Options(96, 54, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=4)
+    for path in ("1", "0"):
+        monkeypatch.setenv("NRT_PATH", path)
+        check(sc, o, oracle_mod)
+    monkeypatch.delenv("NRT_PATH")
+    check(scenes.transformed_objects(), api.Options(80, 60), oracle_mod)   # point light + rotated boxes: hot copy of a PointLight

@@ -275,6 +275,20 @@ def test_path_modes_agree(oracle_mod, monkeypatch, path):
     assert_parity(scenes.spheres_reflection(), api.Options(160, 120, antialias=api.Antialias(api.akJittered, 3), seed=11), oracle_mod)
 
 
+def test_scene_header_without_hot_copies_and_cub_select(oracle_mod, monkeypatch):
+    # NRT_HOT_HEADER=0: the by-value scene header reads lights / grid headers / gate records from the device tables
+    # (what scenes with > 2 lights or > 1 mesh object do); NRT_OWN_SELECT=0: cub::DeviceSelect instead of the
+    # 16-flags-per-thread ordered select.  Same bits as the defaults (every other test) and as the oracle.
+    sc = scenes.bunny_spheres(stride=4)
+    o = api.Options(640, 360, antialias=api.Antialias(api.akGrid, 4), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8)   # 3.7 M samples: the own select runs
+    a_fb, a_st, a_aov = gpu_render(sc, o)
+    monkeypatch.setenv("NRT_HOT_HEADER", "0")
+    monkeypatch.setenv("NRT_OWN_SELECT", "0")
+    b_fb, b_st, b_aov = gpu_render(sc, o)
+    assert (a_fb.data == b_fb.data).all() and a_st == b_st and (a_aov.tri_id == b_aov.tri_id).all() and (a_aov.t_hit == b_aov.t_hit).all()
+    assert_parity(sc, api.Options(200, 112, antialias=api.Antialias(api.akGrid, 2), depthMode=api.NRT_DEPTH_INTENDED, maxRayDepth=8), oracle_mod)
+
+
 def test_full_size_filter_vs_exact(monkeypatch):
     # BASELINE config 2 scene at 960x540: float32 filter + float64 verify == float64 brute force, all ids
     sc, o = scenes.bunny(), api.Options(960, 540)
