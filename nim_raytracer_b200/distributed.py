@@ -2,9 +2,11 @@
 
 The reference shards a frame by scanline with zero communication
 (src/raytracer.nim:67-70: one WorkMsg per line pulled by worker threads).  Here
-rank r of W renders the scanlines y with y mod W == r (nrt_set_partition; same
-rule as rowsFor() in csrc/nrt.cu) and the float32 framebuffer is assembled on
-rank 0 in one of two ways:
+rank r of W renders the units — bands of T scanlines (rows of T x T screen-space
+tiles) of a whole-resolution pass, rendered scanlines of a progressive pass —
+that the serpentine deal nrt_unit_owner gives it (nrt_set_partition; unit_owner()
+below is the same rule as rowsFor() in csrc/nrt.cu) and the float32 framebuffer
+is assembled on rank 0 in one of two ways:
 
   * "ipc"  — rank 0 owns the device framebuffer, exports it with CUDA IPC
              (nrt_ipc_export) and every rank's final pixel-store kernel writes its
