@@ -17,6 +17,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <fstream>
 #include <map>
@@ -389,10 +390,27 @@ inline std::shared_ptr<TriangleMesh> loadObj(const std::string& fname) {
     std::istringstream ss(line);
     std::string tag;
     if (!(ss >> tag)) continue;
-    if (tag == "v") { double x = 0, y = 0, z = 0; ss >> x >> y >> z; m->vertices.push_back(point(x, y, z)); }
+    // obj.nim:25-63: a token that does not parse leaves the coordinate at 0.0 / the index at 0 (`except ValueError:
+    // discard`); the vertex index of a v/vt/vn token is read (a deliberate superset, as in loaders.py)
+    if (tag == "v") {
+      double xyz[3] = {0, 0, 0};
+      for (int k = 0; k < 3; ++k) {
+        std::string tok; ss >> tok;
+        char* end = nullptr;
+        const double v = std::strtod(tok.c_str(), &end);
+        xyz[k] = (!tok.empty() && end && *end == '\0') ? v : 0.0;
+      }
+      m->vertices.push_back(point(xyz[0], xyz[1], xyz[2]));
+    }
     else if (tag == "f") {
       Triangle t{};
-      for (int k = 0; k < 3; ++k) { std::string tok; ss >> tok; t.vertexIdx[k] = std::stoll(tok) - 1; }
+      for (int k = 0; k < 3; ++k) {
+        std::string tok; ss >> tok;
+        tok = tok.substr(0, tok.find('/'));
+        char* end = nullptr;
+        const long long v = std::strtoll(tok.c_str(), &end, 10);
+        t.vertexIdx[k] = (!tok.empty() && end && *end == '\0') ? int64_t(v) - 1 : 0;
+      }
       m->faces.push_back(t);
     }
   }

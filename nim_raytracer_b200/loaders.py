@@ -35,6 +35,24 @@ def calcNormals(vertices: np.ndarray, vertexIdx: np.ndarray):
     return normals, np.stack([k, k, k], axis=1)
 
 
+def _objFloat(tok: str) -> float:
+    """obj.nim:25-43: a coordinate that does not parse is left at its default 0.0 (`except ValueError: discard`)."""
+    try:
+        return float(tok)
+    except ValueError:
+        return 0.0
+
+
+def _objIndex(tok: str) -> int:
+    """obj.nim:46-63: parseInt(s) - 1; a token that does not parse leaves the index at its default 0.
+    Deliberate superset: the vertex index of a `v/vt/vn` token is read (the reference's parseInt fails on the
+    slash and yields index 0 — a degenerate face; it ships no such file)."""
+    try:
+        return int(tok.split("/")[0]) - 1
+    except ValueError:
+        return 0
+
+
 def loadObj(fname: str, objectToWorld=None) -> Geometry:
     verts, faces = [], []
     with open(fname) as f:
@@ -43,11 +61,9 @@ def loadObj(fname: str, objectToWorld=None) -> Geometry:
             if not c:
                 continue
             if c[0] == "v":
-                verts.append([float(c[1]), float(c[2]), float(c[3]), 1.0])
+                verts.append([_objFloat(c[1]), _objFloat(c[2]), _objFloat(c[3]), 1.0])
             elif c[0] == "f":
-                # obj.nim:46-63 parseInt(s)-1 on the bare token (no v/vt/vn support)
-                faces.append([int(c[1].split("/")[0]) - 1, int(c[2].split("/")[0]) - 1,
-                              int(c[3].split("/")[0]) - 1])
+                faces.append([_objIndex(c[1]), _objIndex(c[2]), _objIndex(c[3])])
     vertices = np.asarray(verts, dtype=np.float64).reshape(-1, 4)
     vertexIdx = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
     normals, normalIdx = calcNormals(vertices, vertexIdx)

@@ -88,3 +88,25 @@ def test_cpp_host_mirror_loaders_equal_python(tmp_path):
     nv, nf = raw[:16].view("<i8")
     assert nv == b.vertices.shape[0] and nf == 69451
     assert (raw[16:16 + nv * 32].view("<f8").reshape(nv, 4) == b.vertices).all()
+
+
+def test_malformed_obj_tokens_follow_the_reference(tmp_path):
+    # obj.nim:25-63: `except ValueError: discard` leaves a coordinate at 0.0 and a vertex index at 0; comments, other
+    # records and empty lines are skipped; only the first three tokens of an `f` record are read (obj.nim:116-118).
+    src = tmp_path / "odd.obj"
+    src.write_text("# comment\n\nv 1 2 3\nv 4.5 oops 6\nv -1e0 0.25 7 1.0\nvn 0 1 0\nf 1 2 3\nf 3 x 1 2\nf 1/9/9 2//7 3\n")
+    m = loaders.loadObj(str(src))
+    assert m.vertices.tolist() == [[1, 2, 3, 1], [4.5, 0.0, 6, 1], [-1.0, 0.25, 7, 1]]
+    assert m.vertexIdx.tolist() == [[0, 1, 2], [2, 0, 0], [0, 1, 2]]
+    # the C++ host mirror reads the same arrays
+    exe = str(tmp_path / "loader_tool")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", os.path.join(HERE, "cpp", "loader_tool.cpp"), "-o", exe,
+                    "-I" + os.path.join(ROOT, "include")], check=True)
+    geom, dump = str(tmp_path / "o.geom"), str(tmp_path / "o.bin")
+    subprocess.run([exe, str(src), geom, dump], check=True)
+    raw = np.fromfile(dump, dtype=np.uint8)
+    nv, nf = raw[:16].view("<i8")
+    assert (nv, nf) == (3, 3)
+    v = raw[16:16 + nv * 32].view("<f8").reshape(nv, 4)
+    vi = raw[16 + nv * 32 + nf * 32:16 + nv * 32 + nf * 32 + nf * 24].view("<i8").reshape(nf, 3)
+    assert (v == m.vertices).all() and (vi == m.vertexIdx).all()
