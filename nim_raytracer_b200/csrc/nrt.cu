@@ -1368,7 +1368,7 @@ struct CudaBackend {
       k_sel_scan<<<1, 1024, 0, stream>>>(tiles, ntiles, count);
       k_sel_write<<<unsigned(ntiles), kBlock, 0, stream>>>(cs.active, act.list, act.n, match, tiles, list);
       NRT_CUDA(cudaGetLastError());
-      ++launches;
+      launches += 3;   // (three kernels of this library; a cub select counts as one launch of its sweep)
       return;
     }
     if (!act.list && match) {
