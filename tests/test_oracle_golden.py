@@ -177,3 +177,18 @@ def test_progressive_steps(oracle_mod):
         oracle_mod.render(sc, o, fb=fb, step=step, maxStep=8)
         step //= 2
     assert (fb.data == full.data).all()
+
+
+def test_sphere_known_answer_of_geomtest_nim(oracle_mod):
+    # test/geomtest.nim:86-106 (commented out there since the API changed, but the expectation stands): a sphere of
+    # radius 4.4 at (7, 9, -5), a ray from (7, 9, 0) along -z: `assert eq(r.tHit, 0.6)`.
+    # Object space = world - centre (geom.nim:137-143: worldToObject = inverse(translate)).
+    t = oracle_mod.sphere_intersect(4.4, [0.0, 0.0, 5.0], [0.0, 0.0, -1.0])
+    assert abs(t - 0.6) <= 1e-15 * 5.0          # 5 - 4.4 in float64: the cancellation costs one ulp of 5
+    # and through the whole path: the same sphere as a scene object, the ray as the centre pixel's primary ray
+    sph = api.initSphere(4.4, L.translate(L.mat4(1.0), api.vec3(7.0, 9.0, -5.0)))
+    cam = L.translate(L.mat4(1.0), api.vec3(7.0, 9.0, 0.0))
+    sc = api.Scene([api.Object("s", sph, api.Material(api.vec3(0.0, 0.6, 0.2)))], [], 90.0, cam, api.vec3(0.0))
+    aov = api.Aov(2, 2)
+    oracle_mod.render(sc, api.Options(2, 2), aov=aov)
+    assert aov.obj_id[3] == 0 and aov.t_hit[3] == t     # pixel (1,1) = the image centre: dir (0,0,-1)
