@@ -23,6 +23,7 @@ struct ProfileAcc {
   int64_t tests_by_mode[3] = {0, 0, 0};
   int64_t pre_candidates = 0;
   int64_t active[8] = {0}, wavefront[8] = {0}, tail = 0;   // fused path: samples per bounce / through the wavefront / finished by PathTail
+  int64_t need_cand = 0, need_pairs = 0;   // the largest list any (wave, mesh object) asked for (counters keep counting past a full list)
 };
 
 inline bool isPow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -922,6 +923,7 @@ struct Renderer {
     a.exact_rays += b.exact_rays; a.pre_candidates += b.pre_candidates; a.tail += b.tail;
     for (int k = 0; k < 3; ++k) a.tests_by_mode[k] += b.tests_by_mode[k];
     for (int k = 0; k < 8; ++k) { a.active[k] += b.active[k]; a.wavefront[k] += b.wavefront[k]; }
+    a.need_cand = std::max(a.need_cand, b.need_cand); a.need_pairs = std::max(a.need_pairs, b.need_pairs);
   }
 
   // one bounce of the samples `set` through the wavefront: mesh wave of the path rays, Shade, mesh wave of the shadow
@@ -1013,10 +1015,13 @@ struct Renderer {
         const uint32_t* c = hc + (int64_t(w) * nMO + mo) * cst;
         const int64_t nf = sd.meshes[sd.objs[sd.moIndex[mo]].mesh].nfaces;
         if (c[CNT_CAND] > uint64_t(cs.candCap)) overflow = true;
+        pacc.need_cand = std::max<int64_t>(pacc.need_cand, c[CNT_CAND]);
         int64_t queued = 0;
         for (int b = 0; b <= nL; ++b) {
           const int64_t q = c[cntQueue(b)];
           if (c[cntPre(b)] > uint64_t(cs.preCap) || c[cntWork(b)] > uint64_t(cs.pairCap)) overflow = true;
+          pacc.need_cand = std::max<int64_t>(pacc.need_cand, (int64_t(c[cntPre(b)]) + 3) / 4);   // (preCap = 4 * candCap)
+          pacc.need_pairs = std::max<int64_t>(pacc.need_pairs, c[cntWork(b)]);
           pacc.pre_candidates += c[cntPre(b)];
           if (!q) continue;
           // wave parity: even = path wave (primary for w == 0), odd = shadow wave
@@ -1162,7 +1167,9 @@ struct Renderer {
       bool overflow = false;
       unsigned long long total[ST_COUNT] = {0};
       ProfileAcc pacc;
-      for (int64_t p0 = 0; p0 < npixTotal && !overflow; p0 += chunkPix) {
+      // (an overflowed attempt still walks every chunk: its frame is discarded, but the re-render then knows what the
+      // WHOLE frame's lists asked for instead of finding the next chunk's overflow one attempt at a time)
+      for (int64_t p0 = 0; p0 < npixTotal; p0 += chunkPix) {
         const int64_t npix = std::min(chunkPix, npixTotal - p0);
         const int64_t nS = npix * fp.spp;
         cs.p0 = p0; cs.npix = npix;
@@ -1243,9 +1250,14 @@ struct Renderer {
         else if (pathMode == 0 && total[ST_PRIMARY] > 0) meshShare = std::min(1.0, double(pacc.mesh_rays) / double(total[ST_PRIMARY]));
         return NRT_OK;
       }
-      if (attempt >= 3) { err = "candidate buffer overflow"; return NRT_ERR_OVERFLOW; }
-      cand *= 4;  // re-render the frame with larger candidate / pair buffers (outputs are simply overwritten)
-      pairsReq *= 8;
+      if (attempt >= 4) { err = "candidate buffer overflow"; return NRT_ERR_OVERFLOW; }
+      // re-render the frame with larger candidate / pair buffers (outputs are simply overwritten): at least what the
+      // overflowed attempt asked for (+ 25 %) — a full list hides what the lists behind it would have needed (pairs ->
+      // pre-candidates -> candidates), so up to three resizes can follow one another — and never less than 4x / 8x
+      cand = std::max(cand * 4, pacc.need_cand + pacc.need_cand / 4 + 1);
+      const int64_t pairsNeed = pacc.need_pairs + pacc.need_pairs / 4 + 1;
+      if (pairsReq > 0) pairsReq = std::max(pairsReq * 8, pairsNeed);
+      else if (pairsNeed > std::max<int64_t>(int64_t(1) << 20, cand / 8)) pairsReq = pairsNeed;
     }
   }
 };

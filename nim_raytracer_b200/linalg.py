@@ -75,8 +75,9 @@ def inverse(m: np.ndarray) -> np.ndarray:
                 + minor[0, 2] * (minor[1, 0] * minor[2, 1] - minor[1, 1] * minor[2, 0])
             )
             cof[r, c] = d if (r + c) % 2 == 0 else -d
-    det = float(m[0, :] @ cof[0, :])
-    return cof.T * (1.0 / det)
+    det = np.float64(m[0, :] @ cof[0, :])
+    with np.errstate(all="ignore"):   # (a singular matrix gives inf / nan entries, as the reference's float division does; no exception)
+        return cof.T * (np.float64(1.0) / det)
 
 
 def deg_to_rad(d: float) -> float:
@@ -85,7 +86,8 @@ def deg_to_rad(d: float) -> float:
 
 def normalize(v) -> np.ndarray:
     v = np.asarray(v, dtype=np.float64)
-    return v * (1.0 / math.sqrt(float(v @ v)))
+    with np.errstate(all="ignore"):   # (the zero vector normalises to nan, as in the reference; no exception)
+        return v * (np.float64(1.0) / np.sqrt(np.float64(v @ v)))
 
 
 def to_c(m: np.ndarray):
