@@ -32,7 +32,7 @@ typedef enum nrt_status {
   NRT_ERR_CUDA = -2,         /* a CUDA runtime call failed; see nrt_last_error()     */
   NRT_ERR_NO_DEVICE = -3,    /* no usable sm_100 device; there is NO CPU fallback    */
   NRT_ERR_NOT_INIT = -4,     /* nrt_init() has not been called                       */
-  NRT_ERR_OVERFLOW = -5,     /* candidate buffer overflow after the retry budget      */
+  NRT_ERR_OVERFLOW = -5,     /* internal work lists still too small after five attempts, each sized from what the previous one asked for */
   NRT_ERR_UNSUPPORTED = -6   /* e.g. step/maxStep not a power of two (renderer.nim:166-168) */
 } nrt_status;
 

@@ -46,6 +46,8 @@ def _mesh(rng, centre):
     kind = rng.random()
     if kind < 0.5:       # a decimated bunny (flipped or native winding)
         stride = int(rng.choice([16, 32, 64, 128, 256]))
+        if BIG:
+            stride = max(2, stride // 8)
         tri = scenes.bunny_triangles(flip_winding=bool(rng.random() < 0.7), stride=stride)
         spread = np.array([3.0, 0.5, 3.0])
     elif kind < 0.8:     # a soup of small random triangles
@@ -65,6 +67,7 @@ def _mesh(rng, centre):
     return g
 
 
+BIG = os.environ.get("NRT_FUZZ_BIG") == "1"   # `--big`: 3x the resolution, 8x denser bunnies (seconds per seed)
 DEGENERATE = 1 << 20   # seeds from here on: the scene of seed - DEGENERATE with degenerate parts worked in (_degenerate)
 
 
@@ -173,6 +176,8 @@ def case(seed: int):
     sc = Scene(objects=objects, lights=lights, fov=float(rng.uniform(30.0, 80.0)), cameraToWorld=cam,
                bgColor=vec3(*rng.uniform(0.0, 0.4, 3)))
     w, h = int(rng.integers(8, 97)), int(rng.integers(4, 65))
+    if BIG:       # (frames whose waves exceed the tail thresholds, so that the library's DEFAULT routing is what runs)
+        w, h = 3 * w + 64, 3 * h + 36
     if nl > 32:   # (34 rays per sample and bounce through the single-threaded emulation: keep these frames small)
         w, h = min(w, 40), min(h, 30)
     aa_kind = int(rng.choice([api.akNone, api.akNone, api.akGrid, api.akGrid, api.akJittered, api.akMultiJittered,
@@ -325,7 +330,11 @@ def main():
     ap.add_argument("--seeds", default="0:200")
     ap.add_argument("--jobs", type=int, default=max(1, (os.cpu_count() or 2) // 2))
     ap.add_argument("--gpu", action="store_true", help="the CUDA path through the C ABI instead of the emulation (one process)")
+    ap.add_argument("--big", action="store_true", help="3x the resolution and 8x denser bunnies (set before the workers start)")
     a = ap.parse_args()
+    if a.big and not BIG:
+        os.environ["NRT_FUZZ_BIG"] = "1"
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     if a.gpu:
         os.environ["NRT_FUZZ_GPU"] = "1"
         a.jobs = 1
