@@ -325,6 +325,18 @@ def _job(seed):
                 f.write(f"done {seed}\n")
 
 
+class _NoPool:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    @staticmethod
+    def imap_unordered(fn, it):
+        return map(fn, it)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", default="0:200")
@@ -346,7 +358,7 @@ def main():
     oracle.build()
     from multiprocessing import Pool
     fails = 0
-    with Pool(a.jobs) as pool:
+    with Pool(a.jobs) if not a.gpu else _NoPool() as pool:   # (--gpu: in this process — a CUDA context does not survive fork)
         for seed, msg in pool.imap_unordered(_job, range(lo, hi)):
             if msg:
                 fails += 1
