@@ -262,6 +262,11 @@ def run(seed: int, render=None) -> str | None:
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)
+        if os.environ.get("NRT_FUZZ_PATH"):   # (every seed on one path, e.g. 2 = PathMega, which the seeds themselves never draw)
+            os.environ["NRT_PATH"] = os.environ["NRT_FUZZ_PATH"]
+        for kv in filter(None, os.environ.get("NRT_FUZZ_EXTRA", "").split(",")):   # e.g. NRT_FUZZ_EXTRA=NRT_FORK_MIN=1
+            k, v = kv.split("=", 1)
+            os.environ[k] = v
         a1, a2 = api.Aov(opts.width, opts.height), api.Aov(opts.width, opts.height)
         rfb, rst, _ = oracle.render(sc, opts, aov=a1)
         try:
