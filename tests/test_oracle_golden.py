@@ -192,3 +192,19 @@ def test_sphere_known_answer_of_geomtest_nim(oracle_mod):
     aov = api.Aov(2, 2)
     oracle_mod.render(sc, api.Options(2, 2), aov=aov)
     assert aov.obj_id[3] == 0 and aov.t_hit[3] == t     # pixel (1,1) = the image centre: dir (0,0,-1)
+
+
+def test_host_linalg_follows_ieee_on_singular_input():
+    """The Python mirror of the glm calls the scene files make (geom.nim:159-172: worldToObject = inverse(objectToWorld);
+    light.nim / scene files: normalize): the reference's float division does not raise — a singular matrix inverts to
+    inf / nan entries and the zero vector normalises to nan, and the renderer then makes of them what IEEE says
+    (tools/fuzz_emu.py, degenerate seeds).  Regular input: inverse(m) @ m = I to rounding."""
+    from nim_raytracer_b200.api import vec, vec3
+    m = L.scale(L.rotate(L.translate(L.mat4(1.0), vec3(1.5, -2.0, 7.0)), L.Y_AXIS, L.deg_to_rad(33.0)), (0.5, 2.0, 1.25))
+    assert np.abs(L.inverse(m) @ m - np.eye(4)).max() < 1e-14
+    s = m.copy()
+    s[:3, 1] = 0.0                                        # a zero scale along y: determinant 0
+    inv = L.inverse(s)
+    assert inv.shape == (4, 4) and not np.isfinite(inv).all()
+    assert np.isnan(L.normalize(vec(0.0, 0.0, 0.0))).all()
+    assert (L.normalize(vec(3.0, 0.0, 4.0))[:3] == np.array([3.0, 0.0, 4.0]) * (1.0 / 5.0)).all()
