@@ -1,8 +1,12 @@
-"""Random-scene parity fuzzer, CPU only: the device code's per-element bodies and host orchestration (through the
+"""Random-scene parity fuzzer (CPU; --gpu: the C ABI on a B200): the device code's per-element bodies and host orchestration (through the
 TEST-ONLY emulation build, tests/emu) against the oracle, bit for bit — ids, t_hit, float32 framebuffer, Stats.
 
-    python tools/fuzz_emu.py [--seeds A:B] [--jobs N] [--gpu]
+    python tools/fuzz_emu.py [--seeds A:B] [--jobs N] [--big] [--gpu]
+    NRT_FUZZ_PATH=2 ...            every seed on one NRT_PATH (2 = PathMega, which the seeds never draw)
+    NRT_FUZZ_EXTRA=K=V,K=V ...     further environment for every seed
+    NRT_FUZZ_LOG=file ...          "start seed" / "done seed" lines (a seed that never returns is the one without "done")
 
+Seeds below 2^20 are ordinary scenes; seed 2^20 + s is the scene of s with degenerate parts worked in (_degenerate).
 Every case draws a scene (spheres / planes / boxes / meshes under random affine transforms, distant + point lights,
 a random camera), render options (resolution, antialiasing kind, depth mode, maxRayDepth, bias) and a setting of the
 library's path knobs (NRT_PATH, NRT_HARD_TAIL_BELOW, NRT_TILE, NRT_CHUNK_SAMPLES, NRT_CAND_CAP ...) from its seed.
