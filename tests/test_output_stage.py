@@ -132,3 +132,35 @@ def test_render_quantized_is_render_then_writePpm(oracle_mod):
         assert (img.reshape(-1) == oracle_mod.outvalues(ref.data, 8, True)).all(), step
         step //= 2
     ds.close()
+
+
+def test_framebuf_nim_self_test_replay(oracle_mod, tmp_path):
+    """utils/framebuf.nim:98-129, the reference's own self-test of this stage: store / load round trip of two pixels
+    (float32 storage: `eq` at 1e-15 cannot hold — its "TODO fix tests" — the float32 roundings do), then the 1024 x 768
+    gradient written as 8- and 16-bit PPMs.  The reference checks only that writePpm returns true; here the oracle's
+    files are checked against first principles and the product's cut-point tables must give the same samples."""
+    W, H = 1024, 768
+    fb = api.newFramebuf(W, H)
+    img = fb.data.reshape(H, W, 3)
+    img[0, 0] = (0.2, 0.6, 0.5)
+    assert img[0, 0].tolist() == [float(np.float32(0.2)), float(np.float32(0.6)), 0.5]
+    y, x = np.mgrid[0:H, 0:W].astype(np.float64)
+    img[..., 0], img[..., 1], img[..., 2] = y / (H - 1), x / (W - 1), (H - 1 - y) / (H - 1)    # framebuf.nim:121-126
+    for bits in (8, 16):
+        path = str(tmp_path / f"test-{bits}bit.ppm")
+        assert oracle_mod.write_ppm(fb, path, bits=bits)
+        raw = open(path, "rb").read()
+        head = f"P6 {W} {H} {(1 << bits) - 1} ".encode()
+        assert raw.startswith(head) and len(raw) == len(head) + W * H * 3 * (bits // 8)
+        s = np.frombuffer(raw[len(head):], dtype=np.uint8 if bits == 8 else ">u2").reshape(H, W, 3).astype(np.int64)
+        top = (1 << bits) - 1
+        assert s[0, 0].tolist() == [0, 0, top] and s[H - 1, W - 1].tolist() == [top, top, 0]
+        assert (np.diff(s[:, 0, 0]) >= 0).all() and (np.diff(s[0, :, 1]) >= 0).all() and (s[:, :, 0] + s[::-1, :, 2] == 2 * s[:, :, 0]).all()
+        # the product's conversion of the same framebuffer (what the device evaluates: count of cut points <= v on the
+        # pow branch, the exactly rounded linear segment below it)
+        v = fb.data
+        want = oracle_mod.outvalues(v, bits, True).astype(np.int64)
+        assert (want == s.reshape(-1)).all()
+        thr = api.outputCutPoints(bits)
+        hi = v > LO
+        assert (np.searchsorted(thr, v[hi], side="right") == want[hi]).all()
