@@ -230,6 +230,13 @@ int nrt_band_rows(void);   /* 1: the band height of progressive passes (kept for
  * largest power of two with T*T*spp <= 256 (16 spp: 4); partition `index` renders the bands nrt_unit_owner gives it,
  * counted from y0.  Progressive passes: 1. */
 int nrt_band_rows_for(const nrt_options* opts, int step, int max_step);
+/* The first scanlines of the units of [y0, y1) that partition `index` of `count` renders in a pass with this `step`
+ * and band height `band` (nrt_band_rows_for): the library's own enumeration (a unit starts where (y - y0) mod
+ * (step * band) == 0 and goes to nrt_unit_owner(its number, count)), for callers that assemble a frame from the parts
+ * of several processes.  Writes at most `cap` rows (rows may be null with cap 0) and returns how many there are,
+ * or -1 for arguments outside height > 0, step > 0, band > 0, 0 <= index < count.  No device needed.
+ * Reference counterpart: the scanline work items of raytracer.nim:67-70. */
+int nrt_partition_rows(int height, int y0, int y1, int step, int band, int index, int count, int* rows, int cap);
 
 /* Deep-copies and flattens a Scene (scene.nim:13-18) to every selected GPU:
  * replaces building `Scene`/`Object`/`TriangleMesh` refs that renderLine reads

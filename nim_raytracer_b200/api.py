@@ -609,6 +609,20 @@ def bandRows(opts: "Options", step: int = 1, maxStep: int = 1) -> int:
     return int(L.nrt_band_rows_for(C.byref(co), step, maxStep))
 
 
+def partitionRows(height: int, index: int, count: int, y0: int = 0, y1: Optional[int] = None, step: int = 1, band: int = 1) -> List[int]:
+    """First scanlines of the units of [y0, y1) that partition `index` of `count` renders (nrt_partition_rows: the
+    library's own enumeration of raytracer.nim:67-70's work items; distributed.rows_of is its Python mirror)."""
+    L = lib()
+    L.nrt_partition_rows.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_int), C.c_int]
+    y1 = height if y1 is None else y1
+    n = int(L.nrt_partition_rows(height, y0, y1, step, band, index, count, None, 0))
+    if n < 0:
+        raise NrtError("nrt_partition_rows: NRT_ERR_INVALID")
+    buf = (C.c_int * max(n, 1))()
+    L.nrt_partition_rows(height, y0, y1, step, band, index, count, buf, n)
+    return list(buf[:n])
+
+
 def outputCutPoints(bits: int = 8) -> np.ndarray:
     """The cut-point table of the sRGB pow branch for `bits` (host computation inside libnrt.so; no GPU needed)."""
     out = np.zeros((1 << bits) - 1, dtype=np.float32)

@@ -2116,6 +2116,12 @@ int nrt_abi_version(void) { return NRT_ABI_VERSION; }
 const char* nrt_last_error(void) { return g_err.c_str(); }
 int nrt_band_rows(void) { return 1; }
 int nrt_band_rows_for(const nrt_options* opts, int step, int max_step) { return opts ? (1 << tileShiftFor(*opts, step, max_step)) : 1; }
+int nrt_partition_rows(int height, int y0, int y1, int step, int band, int index, int count, int* rows, int cap) {
+  if (height <= 0 || step <= 0 || band <= 0 || count <= 0 || index < 0 || index >= count || cap < 0 || (cap > 0 && !rows)) return -1;
+  const std::vector<int32_t> r = rowsFor(height, y0, y1, step, index, count, 0, 1, band);   // (the enumeration renderImpl deals out)
+  for (size_t k = 0; k < r.size() && k < size_t(cap); ++k) rows[k] = r[k];
+  return int(r.size());
+}
 
 int nrt_init(int ngpu, const int* dev_ids) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -40,7 +40,8 @@ def unit_owner(unit, world: int):
 
 
 def rows_of(rank: int, world: int, height: int, y0: int = 0, y1: Optional[int] = None, step: int = 1, band: int = 1) -> List[int]:
-    """First rows of the units of [y0, y1) owned by `rank` (csrc/nrt.cu: rowsFor).  A unit is a rendered scanline
+    """First rows of the units of [y0, y1) owned by `rank` (csrc/nrt.cu: rowsFor; the library's own answer is
+    nrt_partition_rows / api.partitionRows, and tests/test_cabi.py holds the two equal).  A unit is a rendered scanline
     of a progressive pass ((y - y0) mod step == 0; band == 1) or a band of `band` scanlines of a whole-resolution
     pass (step == 1; band = api.bandRows(opts): rows of T x T tiles).  Units are numbered from y0 and dealt out
     in the serpentine order of unit_owner, so a progressive pass with step >= world still uses every rank.  """

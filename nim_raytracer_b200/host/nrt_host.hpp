@@ -367,6 +367,14 @@ inline bool toRGBA8(const Framebuf& fb, std::vector<unsigned char>& rgba, unsign
 // Which partition of `count` renders unit (band / rendered scanline) `unit` of a pass: the serpentine deal of
 // raytracer.nim:67-70's work items to GPUs / processes (nrt_set_partition selects this process's share).
 inline int unitOwner(long long unit, int count) { return nrt_unit_owner(unit, count); }
+// The first scanlines of the units partition `index` of `count` renders in [y0, y1) (nrt_partition_rows).
+inline std::vector<int> partitionRows(int height, int index, int count, int y0, int y1, int step = 1, int band = 1) {
+  const int n = nrt_partition_rows(height, y0, y1, step, band, index, count, nullptr, 0);
+  if (n < 0) throw Error(NRT_ERR_INVALID, "nrt_partition_rows: bad arguments");
+  std::vector<int> rows(static_cast<size_t>(n));
+  if (n > 0) nrt_partition_rows(height, y0, y1, step, band, index, count, rows.data(), n);
+  return rows;
+}
 inline void shutdown() { nrt_shutdown(); }
 
 // ---- loaders: obj.nim:65-126 (v / f only, one flat normal per face) and the .geom format ----

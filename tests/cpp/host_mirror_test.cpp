@@ -40,6 +40,10 @@ static Scene bunnyScene(const std::string& geom) {
 
 int main(int argc, char** argv) {
   if (argc == 2 && std::strcmp(argv[1], "--expect-no-device") == 0) {
+    // host logic that needs no device: the units of raytracer.nim:67-70 as two partitions would share them
+    // (serpentine deal: 0 | 1 1 | 0 0 | 1 1 | 0 ...)
+    if (partitionRows(8, 0, 2, 0, 8) != std::vector<int>{0, 3, 4, 7} || partitionRows(8, 1, 2, 0, 8) != std::vector<int>{1, 2, 5, 6} ||
+        unitOwner(5, 2) != 1) { std::cerr << "partitionRows / unitOwner\n"; return 3; }
     try {
       initRenderer();
     } catch (const Error& e) {

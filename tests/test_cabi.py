@@ -5,6 +5,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 from nim_raytracer_b200 import api
@@ -126,3 +127,31 @@ def test_unit_owner_matches_the_python_mirror():
             pos = [u % (2 * world) for u in range(2 * world) if D.unit_owner(u, world) == r]
             assert len(pos) == 2 and sum(pos) == 2 * world - 1
     assert L.nrt_unit_owner(-1, 4) == -1 and L.nrt_unit_owner(3, 0) == -1
+
+
+def test_partition_rows_is_a_partition_and_equals_the_python_mirror():
+    # nrt_partition_rows (the library's own enumeration of the units renderImpl deals out) against distributed.rows_of;
+    # over all partitions the units are disjoint and complete, whatever y0 / y1 / step / band — progressive passes with
+    # step >= count included (every partition still gets rows).  Host logic: no device needed.
+    from nim_raytracer_b200 import distributed as D
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        height = int(rng.integers(1, 400))
+        y0 = int(rng.integers(-3, height))
+        y1 = int(rng.integers(y0, height + 5))
+        step = 1 << int(rng.integers(0, 4))
+        band = 1 if step > 1 else 1 << int(rng.integers(0, 5))
+        count = int(rng.integers(1, 10))
+        seen = []
+        for k in range(count):
+            rows = api.partitionRows(height, k, count, y0, y1, step, band)
+            assert rows == D.rows_of(k, count, height, y0, y1, step, band)
+            seen += rows
+        want = [y for y in range(max(0, y0), min(y1, height)) if (y - y0) % (step * band) == 0]
+        assert sorted(seen) == want and len(set(seen)) == len(seen)
+        if len(want) >= 2 * count:
+            assert all(api.partitionRows(height, k, count, y0, y1, step, band) for k in range(count))
+    L = api.lib()
+    assert L.nrt_partition_rows(0, 0, 1, 1, 1, 0, 1, None, 0) == -1 and L.nrt_partition_rows(8, 0, 8, 1, 1, 2, 2, None, 0) == -1
+    buf = (C.c_int * 2)()
+    assert L.nrt_partition_rows(16, 0, 16, 1, 1, 0, 2, buf, 2) == 8 and list(buf) == [0, 3]    # truncated write, full count
