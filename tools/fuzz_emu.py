@@ -117,7 +117,7 @@ def _degenerate(rng, sc):
             # (inside [0, 1] or negative = off.  Outside that range the recursion's (1-k)*local + k*refl and the device's
             # path weights are no longer sums of same-signed terms: cancellation magnifies their float64 rounding
             # difference into visible bits, and products of two huge k overflow differently)
-            o.material.reflection = float(rng.choice([-0.5, 1.0, 1e-300, 0.999999]))
+            o.material.reflection = float(rng.choice([-0.5, 1.0, 1e-9, 0.999999]))   # (1e-300: seed 2^20 + 10287 — two of them underflow the weight to 0, and 0 * an infinite albedo is nan where the recursion keeps inf)
         elif k == 5:
             o.material.albedo = vec3(*rng.choice([0.0, -1.0, 1e30, np.inf], 3))
         elif k == 6 and sc.lights:
